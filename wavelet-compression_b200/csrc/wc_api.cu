@@ -1,0 +1,1213 @@
+// libwcgpu C ABI (include/wcgpu.h): contexts, plans, buffers and the launch sequences.
+// No CPU fallback anywhere in this file: every numeric result comes from a CUDA kernel.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "wc_common.cuh"
+#include "wc_fused.h"
+#include "wc_kernels.h"
+
+using namespace wc;
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void*  p   = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p   = nullptr;
+        cap = 0;
+        size_t want = (bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p   = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void*  p   = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p   = nullptr;
+        cap = 0;
+        size_t want = (bytes + 4095) & ~size_t(4095);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p   = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline size_t dtype_size(int dt) { return dt == WC_F64 ? 8 : 4; }
+
+struct CopyRange {
+    char*       dst;
+    const char* src;
+    size_t      bytes;
+};
+
+// merges copies whose source and destination are both contiguous with the previous one
+struct CopyList {
+    std::vector<CopyRange> r;
+    void add(void* dst, const void* src, size_t bytes) {
+        if (bytes == 0) return;
+        if (!r.empty()) {
+            CopyRange& b = r.back();
+            if (b.dst + b.bytes == (char*)dst && b.src + b.bytes == (const char*)src) {
+                b.bytes += bytes;
+                return;
+            }
+        }
+        r.push_back({ (char*)dst, (const char*)src, bytes });
+    }
+};
+
+} // namespace
+
+struct wc_ctx {
+    int          device     = 0;
+    cudaStream_t stream     = nullptr;
+    bool         own_stream = false;
+    std::string  last_error;
+    LaunchStats  ls;
+    uint64_t     h2d = 0, d2h = 0;
+    int          opt_path = 0;
+    int          sm_count = 0;
+    wc_plan*     batch_plan = nullptr; // owner of the memory handed out by wc_compress_batch
+    // workspace of the blocking decompress / rmse / primitive calls (grow-only)
+    DevBuf ws_pairs, ws_coef, ws_boxes, ws_tbl0, ws_tbl1, ws_tbl2, ws_tiles0, ws_tiles1, ws_sum,
+        ws_misc, ws_a, ws_b;
+    PinBuf ws_pin;
+};
+
+struct wc_plan {
+    wc_ctx* ctx      = nullptr;
+    int     n_units  = 0;
+    int     in_space = WC_DEVICE;
+    std::vector<wc_box_desc> units;
+    std::vector<UnitDev>     h_units;
+    std::vector<int>         fused1, fused8, generic; // unit ids per path
+    long long total_n = 0;     // sum of ncoef
+    size_t    in_bytes = 0;    // sum of input bytes
+    // device memory
+    DevBuf d_units, d_states, d_in, d_out, d_coef, d_xtiles, d_ctiles, d_tile_i, d_gkey,
+        d_offsets, d_dense, d_f1, d_f8, d_dec_units, d_inv_units, d_inv_tiles, d_ptiles, d_psum,
+        d_err, d_rmse_units, d_rmse_sum, d_rmse, d_stage_out;
+    PinBuf h_states, h_dense, h_misc;
+    int    n_xtiles = 0, n_ctiles = 0;
+    int    n_f1 = 0, n_f8 = 0;
+    bool   compressed = false;
+    bool   transformed = false;
+    std::vector<size_t> in_dev_off; // per unit offset in d_in (host inputs)
+};
+
+#define CTX_CUDA(ctx, call)                                                                        \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+            cudaGetLastError();                                                                    \
+            return e__ == cudaErrorMemoryAllocation ? WC_ERR_OOM : WC_ERR_CUDA;                    \
+        }                                                                                          \
+    } while (0)
+
+static int check_dims(int nx, int ny, int nz) {
+    if (nx < 0 || ny < 0 || nz < 0) return WC_ERR_BAD_DIMS;
+    long long n = (long long)nx * ny * nz;
+    if (n >= (1ll << 31) - 1) return WC_ERR_BAD_DIMS;
+    return WC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// library / context
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int wc_version(void) { return WCGPU_VERSION; }
+
+const char* wc_strerror(int status) {
+    switch (status) {
+    case WC_OK: return "ok";
+    case WC_ERR_INVALID_ARG: return "invalid argument";
+    case WC_ERR_BAD_DIMS: return "bad box dimensions";
+    case WC_ERR_NO_DEVICE: return "no usable CUDA device (libwcgpu has no CPU fallback)";
+    case WC_ERR_CUDA: return "CUDA error (see wc_last_error)";
+    case WC_ERR_OOM: return "out of device or pinned host memory";
+    case WC_ERR_CAPACITY: return "output buffer too small";
+    case WC_ERR_CORRUPT: return "corrupt packed stream";
+    case WC_ERR_STATE: return "call order violated";
+    default: return "unknown status";
+    }
+}
+
+int wc_device_count(int* count) {
+    if (!count) return WC_ERR_INVALID_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return WC_ERR_NO_DEVICE;
+    }
+    *count = n;
+    return WC_OK;
+}
+
+static int create_impl(wc_ctx** out, int device_id, void* stream, bool use_given) {
+    if (!out) return WC_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return WC_ERR_NO_DEVICE;
+    }
+    if (device_id < 0 || device_id >= n) return WC_ERR_INVALID_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) {
+        cudaGetLastError();
+        return WC_ERR_NO_DEVICE;
+    }
+    if (prop.major != 10) return WC_ERR_NO_DEVICE; // the only code in this library is sm_100a SASS
+    wc_ctx* c = new (std::nothrow) wc_ctx();
+    if (!c) return WC_ERR_OOM;
+    c->device   = device_id;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device_id) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return WC_ERR_NO_DEVICE;
+    }
+    if (use_given) {
+        c->stream     = static_cast<cudaStream_t>(stream);
+        c->own_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            delete c;
+            return WC_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return WC_OK;
+}
+
+int wc_create(wc_ctx** ctx, int device_id) { return create_impl(ctx, device_id, nullptr, false); }
+int wc_create_on_stream(wc_ctx** ctx, int device_id, void* cuda_stream) {
+    return create_impl(ctx, device_id, cuda_stream, true);
+}
+
+int wc_plan_destroy(wc_plan* plan);
+
+int wc_destroy(wc_ctx* ctx) {
+    if (!ctx) return WC_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->batch_plan) wc_plan_destroy(ctx->batch_plan);
+    DevBuf* bufs[] = { &ctx->ws_pairs, &ctx->ws_coef, &ctx->ws_boxes, &ctx->ws_tbl0, &ctx->ws_tbl1,
+                       &ctx->ws_tbl2, &ctx->ws_tiles0, &ctx->ws_tiles1, &ctx->ws_sum, &ctx->ws_misc,
+                       &ctx->ws_a, &ctx->ws_b };
+    for (DevBuf* b : bufs) b->release();
+    ctx->ws_pin.release();
+    ctx->ls.destroy();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
+    delete ctx;
+    return WC_OK;
+}
+
+int wc_sync(wc_ctx* ctx) {
+    if (!ctx) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return WC_OK;
+}
+
+const char* wc_last_error(const wc_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int wc_set_option(wc_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return WC_ERR_INVALID_ARG;
+    switch (option) {
+    case WC_OPT_PATH:
+        if (value < 0 || value > 2) return WC_ERR_INVALID_ARG;
+        ctx->opt_path = (int)value;
+        return WC_OK;
+    case WC_OPT_PROFILE:
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->ls.collect();
+        ctx->ls.profile = value != 0;
+        return WC_OK;
+    default: return WC_ERR_INVALID_ARG;
+    }
+}
+
+int wc_get_counter(const wc_ctx* ctx, int counter, uint64_t* value) {
+    if (!ctx || !value) return WC_ERR_INVALID_ARG;
+    switch (counter) {
+    case WC_CTR_KERNEL_LAUNCHES: *value = ctx->ls.launches; return WC_OK;
+    case WC_CTR_H2D_BYTES: *value = ctx->h2d; return WC_OK;
+    case WC_CTR_D2H_BYTES: *value = ctx->d2h; return WC_OK;
+    default: return WC_ERR_INVALID_ARG;
+    }
+}
+
+int wc_kernel_stats(wc_ctx* ctx, int index, const char** name, double* total_ms, uint64_t* launches) {
+    if (!ctx || index < 0) return WC_ERR_INVALID_ARG;
+    if (index >= KID_N) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ls.collect();
+    if (name) *name = kernel_name(index);
+    if (total_ms) *total_ms = ctx->ls.ms[index];
+    if (launches) *launches = ctx->ls.count[index];
+    return WC_OK;
+}
+
+int wc_reset_counters(wc_ctx* ctx) {
+    if (!ctx) return WC_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->ls.collect();
+    ctx->ls.reset();
+    ctx->h2d = ctx->d2h = 0;
+    return WC_OK;
+}
+
+int wc_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return WC_ERR_INVALID_ARG;
+    *ptr = nullptr;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? WC_ERR_OOM : WC_ERR_NO_DEVICE;
+    }
+    return WC_OK;
+}
+
+int wc_host_free(void* ptr) {
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return WC_ERR_CUDA;
+    }
+    return WC_OK;
+}
+
+int wc_device_alloc(wc_ctx* ctx, void** ptr, size_t bytes) {
+    if (!ctx || !ptr) return WC_ERR_INVALID_ARG;
+    *ptr = nullptr;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    CTX_CUDA(ctx, cudaMalloc(ptr, bytes ? bytes : 1));
+    return WC_OK;
+}
+
+int wc_device_free(wc_ctx* ctx, void* ptr) {
+    if (!ctx) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ptr) CTX_CUDA(ctx, cudaFree(ptr));
+    return WC_OK;
+}
+
+int wc_memcpy(wc_ctx* ctx, void* dst, const void* src, size_t bytes, int kind) {
+    if (!ctx || (bytes && (!dst || !src)) || kind < 0 || kind > 2) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice
+                                 : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CTX_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (kind == 0) ctx->h2d += bytes;
+    if (kind == 1) ctx->d2h += bytes;
+    return WC_OK;
+}
+
+int wc_serialize_header(const wc_packed* unit, uint8_t header_out[20]) {
+    if (!unit || !header_out) return WC_ERR_INVALID_ARG;
+    int32_t h[5] = { unit->shape[0], unit->shape[1], unit->shape[2], unit->ncoef, unit->npairs };
+    std::memcpy(header_out, h, 20); // native byte order, as serialize_int (src/compressor.cpp:47-51)
+    return WC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plans
+// ---------------------------------------------------------------------------------------------
+static int plan_upload_units(wc_plan* p) {
+    wc_ctx* ctx = p->ctx;
+    if (p->n_units == 0) return WC_OK;
+    CTX_CUDA(ctx, cudaMemcpyAsync(p->d_units.p, p->h_units.data(), sizeof(UnitDev) * p->n_units,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    // h_units is pageable: the copy above is staged synchronously by the runtime, safe to reuse
+    return WC_OK;
+}
+
+int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_space,
+                   wc_plan** out) {
+    if (!ctx || !out || n_units < 0 || (n_units > 0 && !units) ||
+        (in_space != WC_HOST && in_space != WC_DEVICE))
+        return WC_ERR_INVALID_ARG;
+    *out = nullptr;
+    for (int i = 0; i < n_units; ++i) {
+        int rc = check_dims(units[i].nx, units[i].ny, units[i].nz);
+        if (rc != WC_OK) return rc;
+        if (units[i].dtype != WC_F32 && units[i].dtype != WC_F64) return WC_ERR_INVALID_ARG;
+        long long n = (long long)units[i].nx * units[i].ny * units[i].nz;
+        if (n > 0 && !units[i].data) return WC_ERR_INVALID_ARG;
+    }
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    wc_plan* p = new (std::nothrow) wc_plan();
+    if (!p) return WC_ERR_OOM;
+    p->ctx      = ctx;
+    p->n_units  = n_units;
+    p->in_space = in_space;
+    p->units.assign(units, units + n_units);
+    p->h_units.resize(n_units);
+    p->in_dev_off.resize(n_units);
+
+    // classify + lay out
+    size_t slot_pairs = 0, coef_floats = 0, in_off = 0;
+    std::vector<size_t> slot_off(n_units), coef_off(n_units);
+    std::vector<int2> xtiles, ctiles;
+    for (int i = 0; i < n_units; ++i) {
+        const wc_box_desc& b = units[i];
+        long long n = (long long)b.nx * b.ny * b.nz;
+        UnitDev& u  = p->h_units[i];
+        std::memset(&u, 0, sizeof(u));
+        u.nx = b.nx; u.ny = b.ny; u.nz = b.nz; u.n = (int32_t)n; u.dtype = b.dtype;
+        p->total_n += n;
+        size_t bytes = (size_t)n * dtype_size(b.dtype);
+        p->in_bytes += bytes;
+        p->in_dev_off[i] = in_off;
+        in_off += (bytes % 16 == 0) ? bytes : align_up(bytes, 256);
+        slot_off[i] = slot_pairs;
+        slot_pairs += align_up((size_t)n, 2); // keep every slot 16-byte aligned
+
+        int cls = fused_class(b.nx, b.ny, b.nz);
+        if (ctx->opt_path == 1) cls = 0;
+        if (ctx->opt_path == 2 && cls == 0 && n > 0) {
+            delete p;
+            return WC_ERR_BAD_DIMS;
+        }
+        if (n == 0) cls = -1; // nothing to do: K = 0
+        if (cls == 1) p->fused1.push_back(i);
+        else if (cls == 8) p->fused8.push_back(i);
+        else if (cls == 0) {
+            p->generic.push_back(i);
+            coef_off[i] = coef_floats;
+            coef_floats += align_up((size_t)n, 4);
+            int nt = xtile_count(b.nx, b.ny, b.nz);
+            for (int t = 0; t < nt; ++t) xtiles.push_back(make_int2(i, t));
+            u.ctile0  = (int32_t)ctiles.size();
+            u.nctiles = ctile_count(n);
+            for (int t = 0; t < u.nctiles; ++t) ctiles.push_back(make_int2(i, t));
+        }
+    }
+    p->n_xtiles = (int)xtiles.size();
+    p->n_ctiles = (int)ctiles.size();
+
+    auto fail = [&](cudaError_t e, const char* what) {
+        ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        cudaGetLastError();
+        wc_plan_destroy(p);
+        return e == cudaErrorMemoryAllocation ? WC_ERR_OOM : WC_ERR_CUDA;
+    };
+    cudaError_t e;
+#define PLAN_RESERVE(buf, bytes)                                      \
+    if ((e = (buf).reserve(bytes)) != cudaSuccess) return fail(e, "plan alloc " #buf)
+    PLAN_RESERVE(p->d_units, sizeof(UnitDev) * std::max(n_units, 1));
+    PLAN_RESERVE(p->d_states, sizeof(UnitState) * std::max(n_units, 1));
+    PLAN_RESERVE(p->d_out, sizeof(wc_pair) * std::max<size_t>(slot_pairs, 2));
+    PLAN_RESERVE(p->d_gkey, 64);
+    if (coef_floats) PLAN_RESERVE(p->d_coef, sizeof(float) * coef_floats);
+    if (p->n_xtiles) PLAN_RESERVE(p->d_xtiles, sizeof(int2) * p->n_xtiles);
+    if (p->n_ctiles) {
+        PLAN_RESERVE(p->d_ctiles, sizeof(int2) * p->n_ctiles);
+        PLAN_RESERVE(p->d_tile_i, sizeof(int) * 4 * (size_t)p->n_ctiles);
+    }
+    if (in_space == WC_HOST && in_off) PLAN_RESERVE(p->d_in, in_off);
+    if ((e = p->h_states.reserve(sizeof(UnitState) * std::max(n_units, 1) + 64)) != cudaSuccess)
+        return fail(e, "plan pinned alloc");
+
+    for (int i = 0; i < n_units; ++i) {
+        UnitDev& u = p->h_units[i];
+        u.in   = in_space == WC_HOST ? (const void*)(p->d_in.as<char>() + p->in_dev_off[i]) : units[i].data;
+        u.out  = p->d_out.as<wc_pair>() + slot_off[i];
+        u.coef = p->d_coef.p ? p->d_coef.as<float>() + coef_off[i] : nullptr;
+    }
+    int rc = plan_upload_units(p);
+    if (rc != WC_OK) { wc_plan_destroy(p); return rc; }
+    if (p->n_xtiles)
+        if ((e = cudaMemcpyAsync(p->d_xtiles.p, xtiles.data(), sizeof(int2) * p->n_xtiles,
+                                 cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+            return fail(e, "xtiles upload");
+    if (p->n_ctiles)
+        if ((e = cudaMemcpyAsync(p->d_ctiles.p, ctiles.data(), sizeof(int2) * p->n_ctiles,
+                                 cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+            return fail(e, "ctiles upload");
+    // fused work lists
+    p->n_f1 = (int)p->fused1.size();
+    p->n_f8 = (int)p->fused8.size();
+    if (p->n_f1) {
+        PLAN_RESERVE(p->d_f1, sizeof(int) * p->n_f1);
+        if ((e = cudaMemcpyAsync(p->d_f1.p, p->fused1.data(), sizeof(int) * p->n_f1,
+                                 cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+            return fail(e, "fused1 upload");
+    }
+    if (p->n_f8) {
+        PLAN_RESERVE(p->d_f8, sizeof(int) * p->n_f8);
+        if ((e = cudaMemcpyAsync(p->d_f8.p, p->fused8.data(), sizeof(int) * p->n_f8,
+                                 cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+            return fail(e, "fused8 upload");
+    }
+#undef PLAN_RESERVE
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "plan sync");
+    *out = p;
+    return WC_OK;
+}
+
+int wc_plan_destroy(wc_plan* p) {
+    if (!p) return WC_OK;
+    wc_ctx* ctx = p->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = { &p->d_units, &p->d_states, &p->d_in, &p->d_out, &p->d_coef, &p->d_xtiles,
+                       &p->d_ctiles, &p->d_tile_i, &p->d_gkey, &p->d_offsets, &p->d_dense, &p->d_f1,
+                       &p->d_f8, &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
+                       &p->d_psum, &p->d_err, &p->d_rmse_units, &p->d_rmse_sum, &p->d_rmse,
+                       &p->d_stage_out };
+    for (DevBuf* b : bufs) b->release();
+    p->h_states.release();
+    p->h_dense.release();
+    p->h_misc.release();
+    cudaGetLastError();
+    if (ctx->batch_plan == p) ctx->batch_plan = nullptr;
+    delete p;
+    return WC_OK;
+}
+
+int wc_plan_set_inputs(wc_plan* p, const wc_box_desc* units) {
+    if (!p || (p->n_units > 0 && !units)) return WC_ERR_INVALID_ARG;
+    wc_ctx* ctx = p->ctx;
+    for (int i = 0; i < p->n_units; ++i) {
+        const wc_box_desc& a = p->units[i];
+        if (units[i].nx != a.nx || units[i].ny != a.ny || units[i].nz != a.nz ||
+            units[i].dtype != a.dtype)
+            return WC_ERR_INVALID_ARG;
+    }
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < p->n_units; ++i) {
+        p->units[i].data = units[i].data;
+        if (p->in_space == WC_DEVICE) p->h_units[i].in = units[i].data;
+    }
+    if (p->in_space == WC_DEVICE) {
+        CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int rc = plan_upload_units(p);
+        if (rc != WC_OK) return rc;
+        CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return WC_OK;
+}
+
+static int plan_stage_inputs(wc_plan* p) {
+    wc_ctx* ctx = p->ctx;
+    if (p->in_space != WC_HOST) return WC_OK;
+    CopyList cl;
+    for (int i = 0; i < p->n_units; ++i) {
+        size_t bytes = (size_t)p->h_units[i].n * dtype_size(p->units[i].dtype);
+        cl.add(p->d_in.as<char>() + p->in_dev_off[i], p->units[i].data, bytes);
+    }
+    for (const CopyRange& r : cl.r) {
+        CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d += r.bytes;
+    }
+    return WC_OK;
+}
+
+// forward transform (+ arg-max keys) of every unit; the fused classes only run here when the
+// threshold is batch-wide (they otherwise do everything in one kernel in plan_pack)
+static int plan_forward(wc_plan* p, bool global_mode) {
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaMemsetAsync(p->d_states.p, 0, sizeof(UnitState) * std::max(p->n_units, 1),
+                                  ctx->stream));
+    CTX_CUDA(ctx, launch_forward_generic(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
+                                         p->d_xtiles.as<int2>(), p->n_xtiles, ctx->stream,
+                                         &ctx->ls));
+    if (global_mode) {
+        if (p->n_f1)
+            CTX_CUDA(ctx, launch_fused_compress(1, FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
+                                                p->d_states.as<UnitState>(), p->d_f1.as<int>(),
+                                                p->n_f1, 0.0, nullptr, ctx->sm_count, ctx->stream,
+                                                &ctx->ls));
+        if (p->n_f8)
+            CTX_CUDA(ctx, launch_fused_compress(8, FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
+                                                p->d_states.as<UnitState>(), p->d_f8.as<int>(),
+                                                p->n_f8, 0.0, nullptr, ctx->sm_count, ctx->stream,
+                                                &ctx->ls));
+    }
+    return WC_OK;
+}
+
+static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
+    wc_ctx* ctx = p->ctx;
+    // 1 - keep evaluated in double exactly as `(1 - keep)` at src/compressor.cpp:216
+    volatile double one = 1.0;
+    double omk = one - keep;
+    if (!p->generic.empty() || global_key_dev) {
+        CTX_CUDA(ctx, launch_finalize_thresh(p->d_states.as<UnitState>(), p->n_units, omk,
+                                             global_key_dev, ctx->stream, &ctx->ls));
+    }
+    if (!p->generic.empty()) {
+        int* ti = p->d_tile_i.as<int>();
+        size_t nt = (size_t)p->n_ctiles;
+        CTX_CUDA(ctx, launch_pack_generic(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
+                                          p->n_units, p->d_ctiles.as<int2>(), p->n_ctiles, ti,
+                                          ti + nt, ti + 2 * nt, ti + 3 * nt, ctx->stream,
+                                          &ctx->ls));
+    }
+    int mode = global_key_dev ? FUSED_GIVEN_THRESH : FUSED_FULL;
+    if (p->n_f1)
+        CTX_CUDA(ctx, launch_fused_compress(1, mode, p->d_units.as<UnitDev>(),
+                                            p->d_states.as<UnitState>(), p->d_f1.as<int>(), p->n_f1,
+                                            omk, global_key_dev, ctx->sm_count, ctx->stream,
+                                            &ctx->ls));
+    if (p->n_f8)
+        CTX_CUDA(ctx, launch_fused_compress(8, mode, p->d_units.as<UnitDev>(),
+                                            p->d_states.as<UnitState>(), p->d_f8.as<int>(), p->n_f8,
+                                            omk, global_key_dev, ctx->sm_count, ctx->stream,
+                                            &ctx->ls));
+    p->compressed = true;
+    return WC_OK;
+}
+
+int wc_plan_compress(wc_plan* p, double keep, int thresh_mode) {
+    if (!p || (thresh_mode != WC_THRESH_PER_UNIT && thresh_mode != WC_THRESH_GLOBAL))
+        return WC_ERR_INVALID_ARG;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = plan_stage_inputs(p);
+    if (rc != WC_OK) return rc;
+    bool global_mode = thresh_mode == WC_THRESH_GLOBAL;
+    rc = plan_forward(p, global_mode);
+    if (rc != WC_OK) return rc;
+    const u64* gk = nullptr;
+    if (global_mode) {
+        CTX_CUDA(ctx, launch_global_key(p->d_states.as<UnitState>(), p->n_units, p->d_gkey.as<u64>(),
+                                        ctx->stream, &ctx->ls));
+        gk = p->d_gkey.as<u64>();
+    }
+    return plan_pack(p, keep, gk);
+}
+
+int wc_plan_transform(wc_plan* p, uint64_t** key_dev) {
+    if (!p || !key_dev) return WC_ERR_INVALID_ARG;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = plan_stage_inputs(p);
+    if (rc != WC_OK) return rc;
+    rc = plan_forward(p, true);
+    if (rc != WC_OK) return rc;
+    CTX_CUDA(ctx, launch_global_key(p->d_states.as<UnitState>(), p->n_units, p->d_gkey.as<u64>(),
+                                    ctx->stream, &ctx->ls));
+    *key_dev       = reinterpret_cast<uint64_t*>(p->d_gkey.p);
+    p->transformed = true;
+    return WC_OK;
+}
+
+int wc_plan_pack_with_key(wc_plan* p, double keep, const uint64_t* key_dev) {
+    if (!p || !key_dev) return WC_ERR_INVALID_ARG;
+    if (!p->transformed) return WC_ERR_STATE;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return plan_pack(p, keep, reinterpret_cast<const u64*>(key_dev));
+}
+
+static int plan_read_states(wc_plan* p) {
+    wc_ctx* ctx = p->ctx;
+    if (p->n_units == 0) return WC_OK;
+    CTX_CUDA(ctx, cudaMemcpyAsync(p->h_states.p, p->d_states.p, sizeof(UnitState) * p->n_units,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h += sizeof(UnitState) * p->n_units;
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return WC_OK;
+}
+
+int wc_plan_total_pairs(wc_plan* p, int64_t* total) {
+    if (!p || !total) return WC_ERR_INVALID_ARG;
+    if (!p->compressed) return WC_ERR_STATE;
+    CTX_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    int rc = plan_read_states(p);
+    if (rc != WC_OK) return rc;
+    int64_t t = 0;
+    const UnitState* hs = p->h_states.as<UnitState>();
+    for (int i = 0; i < p->n_units; ++i) t += hs[i].npairs;
+    *total = t;
+    return WC_OK;
+}
+
+int wc_plan_fetch(wc_plan* p, wc_packed* out, int out_space) {
+    if (!p || (p->n_units > 0 && !out) || (out_space != WC_HOST && out_space != WC_DEVICE))
+        return WC_ERR_INVALID_ARG;
+    if (!p->compressed) return WC_ERR_STATE;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (out_space == WC_HOST && p->n_units > 0) {
+        cudaError_t e = p->d_offsets.reserve(sizeof(long long) * (p->n_units + 1));
+        CTX_CUDA(ctx, e);
+        CTX_CUDA(ctx, launch_gather_dense(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
+                                          p->n_units, p->d_offsets.as<long long>(), nullptr, true,
+                                          ctx->stream, &ctx->ls));
+    }
+    int rc = plan_read_states(p);
+    if (rc != WC_OK) return rc;
+    const UnitState* hs = p->h_states.as<UnitState>();
+    size_t total = 0;
+    for (int i = 0; i < p->n_units; ++i) {
+        const UnitDev& u = p->h_units[i];
+        out[i].shape[0] = u.nx; out[i].shape[1] = u.ny; out[i].shape[2] = u.nz;
+        out[i].ncoef    = u.n;
+        out[i].npairs   = hs[i].npairs;
+        out[i].reserved = 0;
+        out[i].pairs    = u.out;
+        total += (size_t)hs[i].npairs;
+    }
+    if (out_space == WC_DEVICE || p->n_units == 0) return WC_OK;
+    CTX_CUDA(ctx, p->d_dense.reserve(sizeof(wc_pair) * std::max<size_t>(total, 1)));
+    CTX_CUDA(ctx, p->h_dense.reserve(sizeof(wc_pair) * std::max<size_t>(total, 1)));
+    CTX_CUDA(ctx, launch_gather_dense(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
+                                      p->n_units, p->d_offsets.as<long long>(),
+                                      p->d_dense.as<wc_pair>(), false, ctx->stream, &ctx->ls));
+    if (total) {
+        CTX_CUDA(ctx, cudaMemcpyAsync(p->h_dense.p, p->d_dense.p, sizeof(wc_pair) * total,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h += sizeof(wc_pair) * total;
+    }
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    size_t off = 0;
+    for (int i = 0; i < p->n_units; ++i) {
+        out[i].pairs = p->h_dense.as<wc_pair>() + off;
+        off += (size_t)hs[i].npairs;
+    }
+    return WC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decompression
+// ---------------------------------------------------------------------------------------------
+// Common engine: units described by (pairs on device, K or a device pointer to K, dims, output).
+struct DecJob {
+    const wc_pair* pairs_dev;
+    const int32_t* npairs_dev; // optional: K read on the device (plan round trip)
+    int32_t        npairs;     // K (host known) or capacity bound when npairs_dev is set
+    int32_t        nx, ny, nz;
+    void*          out_dev;
+    int32_t        out_dtype;
+};
+
+static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& d_coef,
+                          DevBuf& d_dec_units, DevBuf& d_inv_units, DevBuf& d_inv_tiles,
+                          DevBuf& d_ptiles, DevBuf& d_psum, DevBuf& d_err, DevBuf& d_fused_list) {
+    int n = (int)jobs.size();
+    if (n == 0) return WC_OK;
+    std::vector<DecUnitDev> du(n);
+    std::vector<InvUnitDev> iu(n);
+    std::vector<int2> ptiles, xtiles;
+    std::vector<int> f1, f8;
+    size_t coef_floats = 0;
+    std::vector<size_t> coef_off(n);
+    for (int i = 0; i < n; ++i) {
+        long long total = (long long)jobs[i].nx * jobs[i].ny * jobs[i].nz;
+        int cls = total > 0 ? fused_class(jobs[i].nx, jobs[i].ny, jobs[i].nz) : -1;
+        if (ctx->opt_path == 1 && cls > 0) cls = 0;
+        if (!fused_decode_available()) cls = cls > 0 ? 0 : cls;
+        coef_off[i] = coef_floats;
+        if (cls == 0) coef_floats += align_up((size_t)total, 4);
+        du[i].pairs      = jobs[i].pairs_dev;
+        du[i].npairs_dev = jobs[i].npairs_dev;
+        du[i].npairs     = jobs[i].npairs;
+        du[i].total      = (int32_t)total;
+        du[i].ptile0     = (int32_t)ptiles.size();
+        du[i].nptiles    = 0;
+        iu[i].nx = jobs[i].nx; iu[i].ny = jobs[i].ny; iu[i].nz = jobs[i].nz;
+        iu[i].out = jobs[i].out_dev;
+        iu[i].dtype = jobs[i].out_dtype;
+        if (cls == 0) {
+            du[i].nptiles = ptile_count(jobs[i].npairs);
+            for (int t = 0; t < du[i].nptiles; ++t) ptiles.push_back(make_int2(i, t));
+            int nt = xtile_count(jobs[i].nx, jobs[i].ny, jobs[i].nz);
+            for (int t = 0; t < nt; ++t) xtiles.push_back(make_int2(i, t));
+        } else if (cls == 1) f1.push_back(i);
+        else if (cls == 8) f8.push_back(i);
+    }
+    CTX_CUDA(ctx, d_coef.reserve(sizeof(float) * std::max<size_t>(coef_floats, 4)));
+    for (int i = 0; i < n; ++i) {
+        du[i].coef = d_coef.as<float>() + coef_off[i];
+        iu[i].coef = du[i].coef;
+    }
+    CTX_CUDA(ctx, d_dec_units.reserve(sizeof(DecUnitDev) * n));
+    CTX_CUDA(ctx, d_inv_units.reserve(sizeof(InvUnitDev) * n));
+    CTX_CUDA(ctx, d_inv_tiles.reserve(sizeof(int2) * std::max<size_t>(xtiles.size(), 1)));
+    CTX_CUDA(ctx, d_ptiles.reserve(sizeof(int2) * std::max<size_t>(ptiles.size(), 1)));
+    CTX_CUDA(ctx, d_psum.reserve(sizeof(long long) * std::max<size_t>(ptiles.size(), 1)));
+    CTX_CUDA(ctx, d_err.reserve(64));
+    CTX_CUDA(ctx, cudaMemcpyAsync(d_dec_units.p, du.data(), sizeof(DecUnitDev) * n,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemcpyAsync(d_inv_units.p, iu.data(), sizeof(InvUnitDev) * n,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    if (!xtiles.empty())
+        CTX_CUDA(ctx, cudaMemcpyAsync(d_inv_tiles.p, xtiles.data(), sizeof(int2) * xtiles.size(),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    if (!ptiles.empty())
+        CTX_CUDA(ctx, cudaMemcpyAsync(d_ptiles.p, ptiles.data(), sizeof(int2) * ptiles.size(),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 64, ctx->stream));
+    if (coef_floats) CTX_CUDA(ctx, cudaMemsetAsync(d_coef.p, 0, sizeof(float) * coef_floats, ctx->stream));
+    CTX_CUDA(ctx, launch_rle_decode_generic(d_dec_units.as<DecUnitDev>(), n, d_ptiles.as<int2>(),
+                                            (int)ptiles.size(), d_psum.as<long long>(),
+                                            d_err.as<int>(), ctx->stream, &ctx->ls));
+    CTX_CUDA(ctx, launch_inverse_generic(d_inv_units.as<InvUnitDev>(), d_inv_tiles.as<int2>(),
+                                         (int)xtiles.size(), ctx->stream, &ctx->ls));
+    if (!f1.empty() || !f8.empty()) {
+        CTX_CUDA(ctx, d_fused_list.reserve(sizeof(int) * (f1.size() + f8.size())));
+        int* dl = d_fused_list.as<int>();
+        if (!f1.empty())
+            CTX_CUDA(ctx, cudaMemcpyAsync(dl, f1.data(), sizeof(int) * f1.size(),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        if (!f8.empty())
+            CTX_CUDA(ctx, cudaMemcpyAsync(dl + f1.size(), f8.data(), sizeof(int) * f8.size(),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        if (!f1.empty())
+            CTX_CUDA(ctx, launch_fused_decompress(1, d_dec_units.as<DecUnitDev>(),
+                                                  d_inv_units.as<InvUnitDev>(), dl, (int)f1.size(),
+                                                  d_err.as<int>(), ctx->sm_count, ctx->stream,
+                                                  &ctx->ls));
+        if (!f8.empty())
+            CTX_CUDA(ctx, launch_fused_decompress(8, d_dec_units.as<DecUnitDev>(),
+                                                  d_inv_units.as<InvUnitDev>(), dl + f1.size(),
+                                                  (int)f8.size(), d_err.as<int>(), ctx->sm_count,
+                                                  ctx->stream, &ctx->ls));
+    }
+    return WC_OK;
+}
+
+int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
+    if (!p || (p->n_units > 0 && !out) || (out_space != WC_HOST && out_space != WC_DEVICE))
+        return WC_ERR_INVALID_ARG;
+    if (!p->compressed) return WC_ERR_STATE;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int n = p->n_units;
+    std::vector<DecJob> jobs(n);
+    size_t stage = 0;
+    std::vector<size_t> stage_off(n);
+    for (int i = 0; i < n; ++i) {
+        const UnitDev& u = p->h_units[i];
+        if (out[i].nx != u.nx || out[i].ny != u.ny || out[i].nz != u.nz) return WC_ERR_INVALID_ARG;
+        if (out[i].dtype != WC_F32 && out[i].dtype != WC_F64) return WC_ERR_INVALID_ARG;
+        if (u.n > 0 && !out[i].data) return WC_ERR_INVALID_ARG;
+        stage_off[i] = stage;
+        stage += align_up((size_t)u.n * dtype_size(out[i].dtype), 256);
+    }
+    if (out_space == WC_HOST) CTX_CUDA(ctx, p->d_stage_out.reserve(std::max<size_t>(stage, 256)));
+    for (int i = 0; i < n; ++i) {
+        const UnitDev& u = p->h_units[i];
+        jobs[i].pairs_dev  = u.out;
+        jobs[i].npairs_dev = &p->d_states.as<UnitState>()[i].npairs;
+        jobs[i].npairs     = u.n; // bound
+        jobs[i].nx = u.nx; jobs[i].ny = u.ny; jobs[i].nz = u.nz;
+        jobs[i].out_dev   = out_space == WC_HOST ? (void*)(p->d_stage_out.as<char>() + stage_off[i]) : out[i].data;
+        jobs[i].out_dtype = out[i].dtype;
+    }
+    int rc = run_decompress(ctx, jobs, ctx->ws_coef, p->d_dec_units,
+                            p->d_inv_units, p->d_inv_tiles, p->d_ptiles, p->d_psum, p->d_err,
+                            ctx->ws_misc);
+    if (rc != WC_OK) return rc;
+    if (out_space == WC_HOST) {
+        CopyList cl;
+        for (int i = 0; i < n; ++i)
+            cl.add(out[i].data, p->d_stage_out.as<char>() + stage_off[i],
+                   (size_t)p->h_units[i].n * dtype_size(out[i].dtype));
+        for (const CopyRange& r : cl.r) {
+            CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h += r.bytes;
+        }
+    }
+    return WC_OK;
+}
+
+int wc_decompress_batch(wc_ctx* ctx, const wc_packed* in, int n_units, int in_space,
+                        const wc_box_out* out, int out_space) {
+    if (!ctx || n_units < 0 || (n_units > 0 && (!in || !out)) ||
+        (in_space != WC_HOST && in_space != WC_DEVICE) ||
+        (out_space != WC_HOST && out_space != WC_DEVICE))
+        return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<DecJob> jobs(n_units);
+    size_t pair_total = 0, stage = 0;
+    std::vector<size_t> pair_off(n_units), stage_off(n_units);
+    for (int i = 0; i < n_units; ++i) {
+        int rc = check_dims(in[i].shape[0], in[i].shape[1], in[i].shape[2]);
+        if (rc != WC_OK) return rc;
+        long long n = (long long)in[i].shape[0] * in[i].shape[1] * in[i].shape[2];
+        if (in[i].npairs < 0 || in[i].ncoef < 0) return WC_ERR_CORRUPT;
+        // The reference decodes into coeff_shape[0] floats and then reads shape[0]*shape[1]*shape[2]
+        // of them (src/decompressor.cpp:245-251); a mismatch is out-of-bounds there, an error here.
+        if ((long long)in[i].ncoef != n) return WC_ERR_CORRUPT;
+        if (in[i].npairs > 0 && !in[i].pairs) return WC_ERR_INVALID_ARG;
+        if (out[i].nx != in[i].shape[0] || out[i].ny != in[i].shape[1] || out[i].nz != in[i].shape[2])
+            return WC_ERR_INVALID_ARG;
+        if (out[i].dtype != WC_F32 && out[i].dtype != WC_F64) return WC_ERR_INVALID_ARG;
+        if (n > 0 && !out[i].data) return WC_ERR_INVALID_ARG;
+        pair_off[i] = pair_total;
+        pair_total += (size_t)in[i].npairs;
+        stage_off[i] = stage;
+        stage += align_up((size_t)n * dtype_size(out[i].dtype), 256);
+    }
+    if (in_space == WC_HOST) {
+        CTX_CUDA(ctx, ctx->ws_pairs.reserve(sizeof(wc_pair) * std::max<size_t>(pair_total, 1)));
+        CopyList cl;
+        for (int i = 0; i < n_units; ++i)
+            cl.add(ctx->ws_pairs.as<wc_pair>() + pair_off[i], in[i].pairs, sizeof(wc_pair) * (size_t)in[i].npairs);
+        for (const CopyRange& r : cl.r) {
+            CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d += r.bytes;
+        }
+    }
+    if (out_space == WC_HOST) CTX_CUDA(ctx, ctx->ws_boxes.reserve(std::max<size_t>(stage, 256)));
+    for (int i = 0; i < n_units; ++i) {
+        jobs[i].pairs_dev  = in_space == WC_HOST ? ctx->ws_pairs.as<wc_pair>() + pair_off[i] : in[i].pairs;
+        jobs[i].npairs_dev = nullptr;
+        jobs[i].npairs     = in[i].npairs;
+        jobs[i].nx = in[i].shape[0]; jobs[i].ny = in[i].shape[1]; jobs[i].nz = in[i].shape[2];
+        jobs[i].out_dev   = out_space == WC_HOST ? (void*)(ctx->ws_boxes.as<char>() + stage_off[i]) : out[i].data;
+        jobs[i].out_dtype = out[i].dtype;
+    }
+    int rc = run_decompress(ctx, jobs, ctx->ws_coef, ctx->ws_tbl0, ctx->ws_tbl1, ctx->ws_tiles0,
+                            ctx->ws_tiles1, ctx->ws_sum, ctx->ws_tbl2, ctx->ws_misc);
+    if (rc != WC_OK) return rc;
+    if (out_space == WC_HOST) {
+        CopyList cl;
+        for (int i = 0; i < n_units; ++i) {
+            long long n = (long long)in[i].shape[0] * in[i].shape[1] * in[i].shape[2];
+            cl.add(out[i].data, ctx->ws_boxes.as<char>() + stage_off[i], (size_t)n * dtype_size(out[i].dtype));
+        }
+        for (const CopyRange& r : cl.r) {
+            CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h += r.bytes;
+        }
+    }
+    int h_err = 0;
+    CTX_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->ws_tbl2.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return h_err ? WC_ERR_CORRUPT : WC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSE
+// ---------------------------------------------------------------------------------------------
+struct RmseJob {
+    const void* a;
+    const void* b;
+    int32_t a_dtype, b_dtype;
+    int32_t n;
+};
+
+static int run_rmse(wc_ctx* ctx, const std::vector<RmseJob>& jobs, DevBuf& d_units, DevBuf& d_tiles,
+                    DevBuf& d_sum, DevBuf& d_rmse, double* rmse_host) {
+    int n = (int)jobs.size();
+    if (n == 0) return WC_OK;
+    std::vector<RmseUnitDev> ru(n);
+    std::vector<int2> tiles;
+    for (int i = 0; i < n; ++i) {
+        ru[i].a = jobs[i].a; ru[i].b = jobs[i].b;
+        ru[i].a_dtype = jobs[i].a_dtype; ru[i].b_dtype = jobs[i].b_dtype;
+        ru[i].n = jobs[i].n;
+        ru[i].ctile0  = (int32_t)tiles.size();
+        ru[i].nctiles = ctile_count(jobs[i].n);
+        for (int t = 0; t < ru[i].nctiles; ++t) tiles.push_back(make_int2(i, t));
+    }
+    CTX_CUDA(ctx, d_units.reserve(sizeof(RmseUnitDev) * n));
+    CTX_CUDA(ctx, d_tiles.reserve(sizeof(int2) * std::max<size_t>(tiles.size(), 1)));
+    CTX_CUDA(ctx, d_sum.reserve(sizeof(double) * std::max<size_t>(tiles.size(), 1)));
+    CTX_CUDA(ctx, d_rmse.reserve(sizeof(double) * n));
+    CTX_CUDA(ctx, cudaMemcpyAsync(d_units.p, ru.data(), sizeof(RmseUnitDev) * n,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    if (!tiles.empty())
+        CTX_CUDA(ctx, cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, launch_rmse_generic(d_units.as<RmseUnitDev>(), n, d_tiles.as<int2>(),
+                                      (int)tiles.size(), d_sum.as<double>(), d_rmse.as<double>(),
+                                      ctx->stream, &ctx->ls));
+    CTX_CUDA(ctx, cudaMemcpyAsync(rmse_host, d_rmse.p, sizeof(double) * n, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    ctx->d2h += sizeof(double) * n;
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return WC_OK;
+}
+
+int wc_plan_rmse(wc_plan* p, const wc_box_desc* recon, double* rmse) {
+    if (!p || (p->n_units > 0 && (!recon || !rmse))) return WC_ERR_INVALID_ARG;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<RmseJob> jobs(p->n_units);
+    for (int i = 0; i < p->n_units; ++i) {
+        const UnitDev& u = p->h_units[i];
+        if (recon[i].nx != u.nx || recon[i].ny != u.ny || recon[i].nz != u.nz) return WC_ERR_INVALID_ARG;
+        if (recon[i].dtype != WC_F32 && recon[i].dtype != WC_F64) return WC_ERR_INVALID_ARG;
+        jobs[i] = { u.in, recon[i].data, u.dtype, recon[i].dtype, u.n };
+    }
+    return run_rmse(ctx, jobs, p->d_rmse_units, p->d_inv_tiles, p->d_rmse_sum, p->d_rmse, rmse);
+}
+
+int wc_rmse_batch(wc_ctx* ctx, const wc_box_desc* actual, const wc_box_desc* pred, int n_units,
+                  int space, double* rmse) {
+    if (!ctx || n_units < 0 || (n_units > 0 && (!actual || !pred || !rmse)) ||
+        (space != WC_HOST && space != WC_DEVICE))
+        return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<RmseJob> jobs(n_units);
+    std::vector<size_t> off_a(n_units), off_b(n_units);
+    size_t ta = 0, tb = 0;
+    for (int i = 0; i < n_units; ++i) {
+        int rc = check_dims(actual[i].nx, actual[i].ny, actual[i].nz);
+        if (rc != WC_OK) return rc;
+        if (pred[i].nx != actual[i].nx || pred[i].ny != actual[i].ny || pred[i].nz != actual[i].nz)
+            return WC_ERR_INVALID_ARG;
+        if ((actual[i].dtype != WC_F32 && actual[i].dtype != WC_F64) ||
+            (pred[i].dtype != WC_F32 && pred[i].dtype != WC_F64))
+            return WC_ERR_INVALID_ARG;
+        size_t n = (size_t)actual[i].nx * actual[i].ny * actual[i].nz;
+        if (n > 0 && (!actual[i].data || !pred[i].data)) return WC_ERR_INVALID_ARG;
+        off_a[i] = ta; ta += align_up(n * dtype_size(actual[i].dtype), 256);
+        off_b[i] = tb; tb += align_up(n * dtype_size(pred[i].dtype), 256);
+    }
+    if (space == WC_HOST) {
+        CTX_CUDA(ctx, ctx->ws_a.reserve(std::max<size_t>(ta, 256)));
+        CTX_CUDA(ctx, ctx->ws_b.reserve(std::max<size_t>(tb, 256)));
+        CopyList ca, cb;
+        for (int i = 0; i < n_units; ++i) {
+            size_t n = (size_t)actual[i].nx * actual[i].ny * actual[i].nz;
+            ca.add(ctx->ws_a.as<char>() + off_a[i], actual[i].data, n * dtype_size(actual[i].dtype));
+            cb.add(ctx->ws_b.as<char>() + off_b[i], pred[i].data, n * dtype_size(pred[i].dtype));
+        }
+        for (const CopyList* cl : { &ca, &cb })
+            for (const CopyRange& r : cl->r) {
+                CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyHostToDevice, ctx->stream));
+                ctx->h2d += r.bytes;
+            }
+    }
+    for (int i = 0; i < n_units; ++i) {
+        size_t n = (size_t)actual[i].nx * actual[i].ny * actual[i].nz;
+        jobs[i].a = space == WC_HOST ? (const void*)(ctx->ws_a.as<char>() + off_a[i]) : actual[i].data;
+        jobs[i].b = space == WC_HOST ? (const void*)(ctx->ws_b.as<char>() + off_b[i]) : pred[i].data;
+        jobs[i].a_dtype = actual[i].dtype;
+        jobs[i].b_dtype = pred[i].dtype;
+        jobs[i].n = (int32_t)n;
+    }
+    return run_rmse(ctx, jobs, ctx->ws_tbl0, ctx->ws_tiles0, ctx->ws_sum, ctx->ws_misc, rmse);
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocking compress
+// ---------------------------------------------------------------------------------------------
+int wc_compress_batch(wc_ctx* ctx, const wc_box_desc* in, int n_units, int in_space, double keep,
+                      int thresh_mode, wc_packed* out, int out_space) {
+    if (!ctx || n_units < 0 || (n_units > 0 && (!in || !out))) return WC_ERR_INVALID_ARG;
+    if (ctx->batch_plan) {
+        wc_plan_destroy(ctx->batch_plan);
+        ctx->batch_plan = nullptr;
+    }
+    wc_plan* p = nullptr;
+    int rc = wc_plan_create(ctx, in, n_units, in_space, &p);
+    if (rc != WC_OK) return rc;
+    ctx->batch_plan = p;
+    rc = wc_plan_compress(p, keep, thresh_mode);
+    if (rc != WC_OK) return rc;
+    return wc_plan_fetch(p, out, out_space);
+}
+
+// ---------------------------------------------------------------------------------------------
+// un-fused primitives (always the generic kernels)
+// ---------------------------------------------------------------------------------------------
+static int stage_in(wc_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, int space, const void** dev) {
+    // always staged into an aligned internal buffer, so caller alignment never matters
+    CTX_CUDA(ctx, buf.reserve(std::max<size_t>(bytes, 16)));
+    if (bytes) {
+        CTX_CUDA(ctx, cudaMemcpyAsync(buf.p, src, bytes,
+                                      space == WC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+        if (space == WC_HOST) ctx->h2d += bytes;
+    }
+    *dev = buf.p;
+    return WC_OK;
+}
+
+static int stage_out(wc_ctx* ctx, void* dst, const void* dev, size_t bytes, int space) {
+    if (bytes) {
+        CTX_CUDA(ctx, cudaMemcpyAsync(dst, dev, bytes,
+                                      space == WC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+        if (space == WC_HOST) ctx->d2h += bytes;
+    }
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return WC_OK;
+}
+
+int wc_haar_forward(wc_ctx* ctx, const wc_box_desc* in, int space, float* coef_out) {
+    if (!ctx || !in || (space != WC_HOST && space != WC_DEVICE)) return WC_ERR_INVALID_ARG;
+    int rc = check_dims(in->nx, in->ny, in->nz);
+    if (rc != WC_OK) return rc;
+    if (in->dtype != WC_F32 && in->dtype != WC_F64) return WC_ERR_INVALID_ARG;
+    size_t n = (size_t)in->nx * in->ny * in->nz;
+    if (n == 0) return WC_OK;
+    if (!in->data || !coef_out) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_in;
+    rc = stage_in(ctx, ctx->ws_a, in->data, n * dtype_size(in->dtype), space, &d_in);
+    if (rc != WC_OK) return rc;
+    CTX_CUDA(ctx, ctx->ws_coef.reserve(sizeof(float) * n));
+    CTX_CUDA(ctx, ctx->ws_tbl0.reserve(sizeof(UnitDev)));
+    CTX_CUDA(ctx, ctx->ws_tbl1.reserve(sizeof(UnitState)));
+    UnitDev u;
+    std::memset(&u, 0, sizeof(u));
+    u.in = d_in; u.coef = ctx->ws_coef.as<float>(); u.nx = in->nx; u.ny = in->ny; u.nz = in->nz;
+    u.n = (int32_t)n; u.dtype = in->dtype;
+    int nt = xtile_count(in->nx, in->ny, in->nz);
+    std::vector<int2> tiles(nt);
+    for (int t = 0; t < nt; ++t) tiles[t] = make_int2(0, t);
+    CTX_CUDA(ctx, ctx->ws_tiles0.reserve(sizeof(int2) * nt));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tbl0.p, &u, sizeof(u), cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tiles0.p, tiles.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemsetAsync(ctx->ws_tbl1.p, 0, sizeof(UnitState), ctx->stream));
+    CTX_CUDA(ctx, launch_forward_generic(ctx->ws_tbl0.as<UnitDev>(), ctx->ws_tbl1.as<UnitState>(),
+                                         ctx->ws_tiles0.as<int2>(), nt, ctx->stream, &ctx->ls));
+    return stage_out(ctx, coef_out, ctx->ws_coef.p, sizeof(float) * n, space);
+}
+
+int wc_haar_inverse(wc_ctx* ctx, const float* coef, int nx, int ny, int nz, int space,
+                    float* box_out) {
+    if (!ctx || (space != WC_HOST && space != WC_DEVICE)) return WC_ERR_INVALID_ARG;
+    int rc = check_dims(nx, ny, nz);
+    if (rc != WC_OK) return rc;
+    size_t n = (size_t)nx * ny * nz;
+    if (n == 0) return WC_OK;
+    if (!coef || !box_out) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_coef;
+    rc = stage_in(ctx, ctx->ws_coef, coef, sizeof(float) * n, space, &d_coef);
+    if (rc != WC_OK) return rc;
+    CTX_CUDA(ctx, ctx->ws_boxes.reserve(sizeof(float) * n));
+    CTX_CUDA(ctx, ctx->ws_tbl0.reserve(sizeof(InvUnitDev)));
+    InvUnitDev iu;
+    iu.coef = static_cast<const float*>(d_coef); iu.out = ctx->ws_boxes.p;
+    iu.nx = nx; iu.ny = ny; iu.nz = nz; iu.dtype = WC_F32;
+    int nt = xtile_count(nx, ny, nz);
+    std::vector<int2> tiles(nt);
+    for (int t = 0; t < nt; ++t) tiles[t] = make_int2(0, t);
+    CTX_CUDA(ctx, ctx->ws_tiles0.reserve(sizeof(int2) * nt));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tbl0.p, &iu, sizeof(iu), cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tiles0.p, tiles.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, launch_inverse_generic(ctx->ws_tbl0.as<InvUnitDev>(), ctx->ws_tiles0.as<int2>(), nt,
+                                         ctx->stream, &ctx->ls));
+    return stage_out(ctx, box_out, ctx->ws_boxes.p, sizeof(float) * n, space);
+}
+
+int wc_threshold_pack(wc_ctx* ctx, const float* coef, int n, double keep, int space,
+                      wc_pair* pairs_out, int32_t* npairs_out) {
+    if (!ctx || n < 0 || !npairs_out || (space != WC_HOST && space != WC_DEVICE)) return WC_ERR_INVALID_ARG;
+    *npairs_out = 0;
+    if (n == 0) return WC_OK;
+    if (!coef || !pairs_out) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_coef;
+    int rc = stage_in(ctx, ctx->ws_coef, coef, sizeof(float) * (size_t)n, space, &d_coef);
+    if (rc != WC_OK) return rc;
+    int nct = ctile_count(n);
+    CTX_CUDA(ctx, ctx->ws_pairs.reserve(sizeof(wc_pair) * (size_t)n));
+    CTX_CUDA(ctx, ctx->ws_tbl0.reserve(sizeof(UnitDev)));
+    CTX_CUDA(ctx, ctx->ws_tbl1.reserve(sizeof(UnitState)));
+    CTX_CUDA(ctx, ctx->ws_tiles0.reserve(sizeof(int2) * nct));
+    CTX_CUDA(ctx, ctx->ws_sum.reserve(sizeof(int) * 4 * (size_t)nct));
+    UnitDev u;
+    std::memset(&u, 0, sizeof(u));
+    u.coef = const_cast<float*>(static_cast<const float*>(d_coef));
+    u.out  = ctx->ws_pairs.as<wc_pair>();
+    u.nx = n; u.ny = 1; u.nz = 1; u.n = n; u.ctile0 = 0; u.nctiles = nct;
+    std::vector<int2> tiles(nct);
+    for (int t = 0; t < nct; ++t) tiles[t] = make_int2(0, t);
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tbl0.p, &u, sizeof(u), cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tiles0.p, tiles.data(), sizeof(int2) * nct, cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemsetAsync(ctx->ws_tbl1.p, 0, sizeof(UnitState), ctx->stream));
+    CTX_CUDA(ctx, launch_argmax_flat(ctx->ws_tbl0.as<UnitDev>(), ctx->ws_tbl1.as<UnitState>(),
+                                     ctx->ws_tiles0.as<int2>(), nct, ctx->stream, &ctx->ls));
+    volatile double one = 1.0;
+    CTX_CUDA(ctx, launch_finalize_thresh(ctx->ws_tbl1.as<UnitState>(), 1, one - keep, nullptr,
+                                         ctx->stream, &ctx->ls));
+    int* ti = ctx->ws_sum.as<int>();
+    CTX_CUDA(ctx, launch_pack_generic(ctx->ws_tbl0.as<UnitDev>(), ctx->ws_tbl1.as<UnitState>(), 1,
+                                      ctx->ws_tiles0.as<int2>(), nct, ti, ti + nct, ti + 2 * nct,
+                                      ti + 3 * nct, ctx->stream, &ctx->ls));
+    UnitState hs;
+    CTX_CUDA(ctx, cudaMemcpyAsync(&hs, ctx->ws_tbl1.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *npairs_out = hs.npairs;
+    return stage_out(ctx, pairs_out, ctx->ws_pairs.p, sizeof(wc_pair) * (size_t)hs.npairs, space);
+}
+
+int wc_rle_decode(wc_ctx* ctx, const wc_pair* pairs, int npairs, int total, int space,
+                  float* coef_out) {
+    if (!ctx || npairs < 0 || total < 0 || (space != WC_HOST && space != WC_DEVICE)) return WC_ERR_INVALID_ARG;
+    if (total == 0) return WC_OK;
+    if (!coef_out || (npairs > 0 && !pairs)) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_pairs = nullptr;
+    int rc = stage_in(ctx, ctx->ws_pairs, pairs, sizeof(wc_pair) * (size_t)npairs, space, &d_pairs);
+    if (rc != WC_OK) return rc;
+    int npt = ptile_count(npairs);
+    CTX_CUDA(ctx, ctx->ws_coef.reserve(sizeof(float) * (size_t)total));
+    CTX_CUDA(ctx, ctx->ws_tbl0.reserve(sizeof(DecUnitDev)));
+    CTX_CUDA(ctx, ctx->ws_tiles0.reserve(sizeof(int2) * std::max(npt, 1)));
+    CTX_CUDA(ctx, ctx->ws_sum.reserve(sizeof(long long) * std::max(npt, 1)));
+    CTX_CUDA(ctx, ctx->ws_tbl2.reserve(64));
+    DecUnitDev du;
+    du.pairs = static_cast<const wc_pair*>(d_pairs); du.npairs_dev = nullptr;
+    du.coef = ctx->ws_coef.as<float>(); du.npairs = npairs; du.total = total; du.ptile0 = 0; du.nptiles = npt;
+    std::vector<int2> tiles(std::max(npt, 1));
+    for (int t = 0; t < npt; ++t) tiles[t] = make_int2(0, t);
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tbl0.p, &du, sizeof(du), cudaMemcpyHostToDevice, ctx->stream));
+    if (npt) CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tiles0.p, tiles.data(), sizeof(int2) * npt, cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemsetAsync(ctx->ws_tbl2.p, 0, 64, ctx->stream));
+    CTX_CUDA(ctx, cudaMemsetAsync(ctx->ws_coef.p, 0, sizeof(float) * (size_t)total, ctx->stream));
+    CTX_CUDA(ctx, launch_rle_decode_generic(ctx->ws_tbl0.as<DecUnitDev>(), 1, ctx->ws_tiles0.as<int2>(), npt,
+                                            ctx->ws_sum.as<long long>(), ctx->ws_tbl2.as<int>(),
+                                            ctx->stream, &ctx->ls));
+    int h_err = 0;
+    CTX_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->ws_tbl2.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = stage_out(ctx, coef_out, ctx->ws_coef.p, sizeof(float) * (size_t)total, space);
+    if (rc != WC_OK) return rc;
+    return h_err ? WC_ERR_CORRUPT : WC_OK;
+}
+
+} // extern "C"
