@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py — compress throughput of the B200 numeric core on the AMR-256-L4 workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path (forward Haar + threshold + (run,value) packing,
+src/compressor.cpp:203-247) over one synthetic AMReX timestep: 256^3 level 0 (64 boxes of 64^3) +
+3 refinement levels (512 boxes of 32^3 each), 8 float64 components = 12 800 units, 4.29 GB of input
+field data, keep = 0.999f (BASELINE.json configs[2]).  At N > 1 every rank holds its own timestep
+(t = rank) of the same shape — the timestep-sharded series of configs[3] — and there is no
+data-path collective (units are independent); scaling is weak.
+
+value   : GB/s of float64 input field data, whole job, inputs resident in HBM, outputs left in HBM.
+e2e     : the same metric through the C-ABI plan with HOST (pinned) input boxes and the packed
+          stream fetched back to pinned host memory: H2D + kernels + dense gather + D2H inside the
+          timed region.
+roofline: the dominant kernel's algorithmic bytes (8N + 8K + 20 per unit) / its
+          average launch duration measured with CUDA events on the launch stream (WC_OPT_PROFILE)
+          against MEASURED_PEAKS.json's hbm_gbs.
+cpu_baseline / --impl reference: the reference's own compress() (oracle/_ref, unmodified sources)
+          on the host cores over a bounded sample of the same units.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KEEP = float(np.float32(0.999))
+N_COMP = 8
+WORKLOAD = ("AMR-256-L4: 256^3 level 0 (64 boxes of 64^3) + 3 refinement levels (512 boxes of 32^3 each), "
+            "8 float64 components, 12800 units, 4.29 GB per timestep, keep=0.999f")
+
+
+def load_pkg():
+    import __graft_entry__ as g
+    return g.package()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (NVML in a thread; nvidia-smi has too coarse a period for millisecond steps)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), threading.Event()
+        self.ok, self.max_mhz = False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10,
+                 "applications_clocks_setting": 0x2, "display_clock_setting": 0x100}
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.ok:
+            self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.ok:
+            self.th.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def build_timestep_device(pkg, t, device):
+    """One AMR-256-L4 timestep generated on the device, FAB order.  Returns (tensors, descs, dims)."""
+    synth = pkg.amr_synth
+    levels = synth.amr_levels()
+    tensors, ptrs, dims = [], [], []
+    for lev in levels:
+        fab = synth.generate_level_torch(lev, N_COMP, t=t, device=device)  # (boxes, comp, z, y, x) f64
+        tensors.append(fab)
+        n = lev.box ** 3
+        base = fab.data_ptr()
+        for b in range(lev.n_boxes):
+            for c in range(N_COMP):
+                ptrs.append(base + 8 * n * (b * N_COMP + c))
+                dims.append((lev.box,) * 3)
+    descs = pkg.capi.box_descs(ptrs, [pkg.WC_F64] * len(ptrs), dims)
+    return tensors, descs, dims
+
+
+def cpu_sample_units(pkg, t=0, l0_boxes=8, fine_boxes=32):
+    """Bounded sample of the same workload on the host: (float32 box, dims) per unit."""
+    synth = pkg.amr_synth
+    units = []
+    for lev in synth.amr_levels():
+        fab = synth.generate_level_numpy(lev, N_COMP, t=t)
+        nb = l0_boxes if lev.level == 0 else fine_boxes
+        step = max(1, lev.n_boxes // nb)
+        for b in list(range(0, lev.n_boxes, step))[:nb]:
+            for c in range(N_COMP):
+                units.append((fab[b, c].astype(np.float32), (lev.box,) * 3))  # src/preprocess.cpp:78
+        del fab
+    return units
+
+
+def time_reference_cpu(units, steps, warmup, stub_lzma, threads):
+    """Reference compress() (oracle/_ref when present, else the C port) over `units`, `threads`
+    host threads over disjoint units.  Returns (seconds per step list, kind)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.have_ref() else "port"
+    if kind == "reference":
+        ref = pyoracle.Ref()
+        ref.set_lzma_mode(1 if stub_lzma else 0)
+    else:
+        orc = pyoracle.Oracle()
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    times = []
+    with tempfile.TemporaryDirectory(dir=shm) as d, ThreadPoolExecutor(threads) as pool:
+        def work(i):
+            box, dims = units[i]
+            if kind == "reference":
+                ref.compress(box.reshape(1, -1), dims, KEEP, d, t=0, lev=0, box_idx=i, want_pairs=False)
+            else:
+                orc.compress_unit(box, dims, KEEP)
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            list(pool.map(work, range(len(units)), chunksize=max(1, len(units) // (threads * 8))))
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    if kind == "reference":
+        ref.set_lzma_mode(0)
+    return times, kind
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    pkg = load_pkg()
+    threads = os.cpu_count() or 1
+    units = cpu_sample_units(pkg)
+    field_bytes = sum(8 * b.size for b, _ in units)  # float64 field data the units came from
+    steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    times, kind = time_reference_cpu(units, steps, warmup, stub_lzma=True, threads=threads)
+    sec = statistics.median(times)
+    value = field_bytes / sec / 1e9
+    full_times, _ = time_reference_cpu(units[::16], 1, 0, stub_lzma=False, threads=threads)
+    full_value = sum(8 * b.size for b, _ in units[::16]) / full_times[0] / 1e9
+    sample = (f"{len(units)} units of timestep 0 (8 of 64 level-0 boxes, 32 of 512 boxes per fine level, 8 comps; "
+              f"{field_bytes / 1e6:.0f} MB of f64 field data) per step; reference compress() "
+              f"(src/compressor.cpp:192-297) with the LZMA stage stubbed out and files on tmpfs = numeric core + "
+              f"serialisation only; with LZMA (xz preset 6) it drops to {full_value:.4f} GB/s")
+    line = {"impl": "reference", "metric": "compress GB/s of input field data", "value": value, "unit": "GB/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "keep": KEEP},
+            "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample,
+                             "with_lzma_value": full_value},
+            "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# main arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic kernels only, 2 fused only")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    pkg = load_pkg()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libwcgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+
+    stream = torch.cuda.Stream(device=device)
+    ctx = pkg.Context(local, stream=stream.cuda_stream)
+    ctx.set_path(args.path)
+    tensors, descs, dims = build_timestep_device(pkg, t=rank, device=device)
+    torch.cuda.synchronize()
+    n_units = len(descs)
+    field_bytes = sum(8 * d[0] * d[1] * d[2] for d in dims)
+    plan = ctx.plan(descs, pkg.WC_DEVICE)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- timed region: device resident -------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(W):
+            plan.compress(KEEP)
+        barrier()
+        ctx.reset_counters()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            barrier()
+            ev0.record(stream)
+            for _ in range(K):
+                plan.compress(KEEP)
+            ev1.record(stream)
+            barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        launches = ctx.counter(pkg.capi.WC_CTR_KERNEL_LAUNCHES)
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    ms_per_step = ms_total / K
+    value = world * field_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # per-unit K for the algorithmic-bytes accounting
+    rec = plan.fetch_records(pkg.WC_DEVICE)
+    npairs = rec["npairs"].astype(np.int64)
+    ncoef = rec["ncoef"].astype(np.int64)
+    total_pairs = int(npairs.sum())
+
+    # ---- roofline: per-kernel device time with CUDA events on the launch stream ------------------------
+    ctx.set_profile(True)
+    ctx.reset_counters()
+    prof_steps = 5
+    for _ in range(prof_steps):
+        plan.compress(KEEP)
+    ctx.sync()
+    stats = ctx.kernel_stats()
+    ctx.set_profile(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)")
+    step_kernel_ms = sum(ms for _, ms in stats.values()) / prof_steps
+    dom = max(stats.items(), key=lambda kv: kv[1][1]) if stats else ("none", (1, 0.0))
+    dom_name, (dom_n, dom_ms) = dom
+    is32 = ncoef == 32 ** 3
+    is64 = ncoef == 64 ** 3
+    alg_all = int((8 * ncoef + 8 * npairs + 20).sum())
+    alg_by_kernel = {
+        "k_fused_compress<1>": int((8 * ncoef[is32] + 8 * npairs[is32] + 20).sum()),
+        "k_fused_compress<8>": int((8 * ncoef[is64] + 8 * npairs[is64] + 20).sum()),
+        "k_forward_generic": int((8 * ncoef).sum()),          # reads the f64 input once (writes 4N scratch)
+        "k_emit_tiles": int((8 * npairs).sum()),
+        "k_count_tiles": 0,
+    }
+    dom_alg = alg_by_kernel.get(dom_name, alg_all)
+    dom_avg_ms = dom_ms / max(dom_n, 1)
+    launches_per_step_of_dom = dom_n / prof_steps
+    dom_alg_per_launch = dom_alg / max(launches_per_step_of_dom, 1)
+    achieved = dom_alg_per_launch / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": dom_alg_per_launch, "avg_launch_ms": dom_avg_ms,
+                "kernel_share_of_step": (dom_ms / prof_steps) / step_kernel_ms if step_kernel_ms else None,
+                "whole_step": {"alg_bytes": alg_all, "achieved": alg_all / (ms_per_step * 1e-3) / 1e9,
+                               "frac": alg_all / (ms_per_step * 1e-3) / 1e9 / peak},
+                "kernels_ms_per_step": {k: ms / prof_steps for k, (n, ms) in stats.items()}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(dom_name)
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- decompress + RMSE on the device (reported, not the headline) ----------------------------------
+    outs = [torch.empty_like(tn, dtype=torch.float32) for tn in tensors]
+    optrs = []
+    for tn, lev in zip(outs, pkg.amr_synth.amr_levels()):
+        n = lev.box ** 3
+        optrs += [tn.data_ptr() + 4 * n * i for i in range(lev.n_boxes * N_COMP)]
+    odescs = pkg.capi.box_descs(optrs, [pkg.WC_F32] * n_units, dims)
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            plan.decompress(odescs, pkg.WC_DEVICE)
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dsteps = max(3, min(K, 20))
+        d0.record(stream)
+        for _ in range(dsteps):
+            plan.decompress(odescs, pkg.WC_DEVICE)
+        d1.record(stream)
+        torch.cuda.synchronize()
+        dec_ms = d0.elapsed_time(d1) / dsteps
+    rm = plan.rmse(odescs)
+    dec_alg = int((8 * npairs + 4 * ncoef).sum())
+    decompress = {"ms_per_step": dec_ms, "value": (4 * int(ncoef.sum())) / (dec_ms * 1e-3) / 1e9,
+                  "unit": "GB/s of float32 output field data", "alg_bytes": dec_alg,
+                  "achieved": dec_alg / (dec_ms * 1e-3) / 1e9, "frac": dec_alg / (dec_ms * 1e-3) / 1e9 / peak}
+
+    # ---- parity spot check of this very run against the oracle (not timed) -----------------------------
+    parity = None
+    cpu_baseline = None
+    if rank == 0:
+        from oracle.pyoracle import Oracle
+        orc = Oracle()
+        packed_rec = plan.fetch_records(pkg.WC_DEVICE)
+        checked, ok, worst = 0, True, 0.0
+        flat_in = [tn.reshape(-1) for tn in tensors]
+        unit_level = np.repeat(np.arange(4), [64 * N_COMP] + [512 * N_COMP] * 3)
+        first = np.concatenate([[0], np.cumsum([64 * N_COMP] + [512 * N_COMP] * 3)])
+        for u in list(range(0, n_units, 997)) + [n_units - 1]:
+            lv = int(unit_level[u])
+            n = int(ncoef[u])
+            off = (u - int(first[lv])) * n
+            box = flat_in[lv][off:off + n].cpu().numpy()
+            runs, vals, _ = orc.compress_unit(box, dims[u], KEEP)
+            k = int(packed_rec[u]["npairs"])
+            got = np.empty(max(k, 1), pkg.capi.PAIR)
+            if k:
+                pkg.capi.check(ctx.lib.wc_memcpy(ctx.h, got.ctypes.data, int(packed_rec[u]["pairs"]), 8 * k, 1), "wc_memcpy", ctx.h)
+            ok &= (k == runs.size and got["run"][:k].tobytes() == runs.tobytes() and got["val"][:k].tobytes() == vals.tobytes())
+            ob = orc.decompress_unit(runs, vals, dims[u])
+            rec_box = outs[lv].reshape(-1)[off:off + n].cpu().numpy()
+            ok &= rec_box.tobytes() == ob.reshape(-1).tobytes()
+            oe = orc.rmse(box.astype(np.float32), ob, dims[u])
+            rel = abs(rm[u] - oe) / max(abs(oe), 1e-300)
+            worst = max(worst, rel)
+            checked += 1
+        parity = {"units_checked": checked, "pairs_and_recon_bit_exact": bool(ok), "rmse_max_rel_err": worst,
+                  "rmse_tolerance": 1e-12, "mean_rmse_per_component": [float(np.mean(rm[c::N_COMP])) for c in range(N_COMP)]}
+
+    # ---- e2e: host boxes in, packed stream out, through the C ABI -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        lib = ctx.lib
+        hptr = ctypes.c_void_p()
+        pkg.capi.check(lib.wc_host_alloc(ctypes.byref(hptr), field_bytes), "wc_host_alloc")
+        off = 0
+        hptrs = []
+        for tn in tensors:  # fill the pinned host copy from the device data (same values), untimed
+            nb = tn.numel() * 8
+            pkg.capi.check(lib.wc_memcpy(ctx.h, hptr.value + off, tn.data_ptr(), nb, 1), "wc_memcpy", ctx.h)
+            off += nb
+        off = 0
+        for d in dims:
+            hptrs.append(hptr.value + off)
+            off += 8 * d[0] * d[1] * d[2]
+        hdescs = pkg.capi.box_descs(hptrs, [pkg.WC_F64] * n_units, dims)
+        hplan = ctx.plan(hdescs, pkg.WC_HOST)
+        hplan.compress(KEEP)
+        hplan.fetch_records(pkg.WC_HOST)  # warm-up (allocates the dense buffers)
+        barrier()
+        ctx.reset_counters()
+        es = max(1, args.e2e_steps)
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(es):
+            hplan.compress(KEEP)
+            hrec = hplan.fetch_records(pkg.WC_HOST)
+        e1.record(stream)
+        barrier()
+        e_ms = e0.elapsed_time(e1) / es
+        wall_ms = (time.perf_counter() - t0) * 1e3 / es
+        tm = torch.tensor([max(e_ms, wall_ms)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e_ms = float(tm.item())
+        h2d = ctx.counter(pkg.capi.WC_CTR_H2D_BYTES) // es
+        d2h = ctx.counter(pkg.capi.WC_CTR_D2H_BYTES) // es
+        same = bool(np.array_equal(hrec["npairs"], rec["npairs"]))
+        e2e = {"value": world * field_bytes / (e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": es,
+               "api": "wc_plan_compress + wc_plan_fetch(WC_HOST) on pinned host boxes",
+               "same_pair_counts_as_device_run": same}
+        hplan.close()
+        lib.wc_host_free(hptr)
+
+    # ---- CPU baseline: the reference's own code on this box's host cores ---------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        units = cpu_sample_units(pkg)
+        fb = sum(8 * b.size for b, _ in units)
+        times, kind = time_reference_cpu(units, 2, 1, stub_lzma=True, threads=threads)
+        sec = min(times)
+        sub = units[::16]
+        full_times, _ = time_reference_cpu(sub, 1, 0, stub_lzma=False, threads=threads)
+        cpu_baseline = {"value": fb / sec / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
+                        "sample": (f"{len(units)} units of timestep 0 (8 level-0 boxes + 32 boxes per fine level, 8 comps, "
+                                   f"{fb / 1e6:.0f} MB f64 field data), reference compress() with LZMA stubbed + tmpfs files "
+                                   f"(numeric core + serialisation)"),
+                        "with_lzma_value": sum(8 * b.size for b, _ in sub) / full_times[0] / 1e9,
+                        "with_lzma_sample": f"{len(sub)} of those units, full compress() incl. xz preset 6"}
+
+    if rank == 0:
+        line = {"metric": "compress GB/s of input field data", "value": value, "unit": "GB/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "keep": KEEP, "units_per_gpu": n_units,
+                           "kept_fraction": total_pairs / float(ncoef.sum()),
+                           "l2": "inputs (4.29 GB per step) larger than L2; no flush needed",
+                           "timestep_per_rank": "t = rank", "path": args.path},
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "decompress": decompress, "parity": parity}
+        print(json.dumps(line))
+    plan.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

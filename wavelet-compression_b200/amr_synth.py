@@ -70,7 +70,10 @@ def _field(xp, lev: LevelSpec, comp: int, t: int, dtype, noise):
     """The (region, region, region) [z][y][x] float64 field of one level / component."""
     A, B, sigma = COMPONENTS[comp % len(COMPONENTS)][1:]
     n = lev.region
-    g = xp.arange(n, dtype=dtype) + float(lev.origin)
+    if hasattr(noise, "device"):  # torch: build the coordinates where the noise lives
+        g = xp.arange(n, dtype=dtype, device=noise.device) + float(lev.origin)
+    else:
+        g = xp.arange(n, dtype=dtype) + float(lev.origin)
     p = (g + 0.5) / float(lev.domain)
     px = p.reshape(1, 1, n)
     py = p.reshape(1, n, 1)
