@@ -1,0 +1,98 @@
+"""GPU: the fused on-chip kernels (k_fused_compress<1>, <8>) forced with WC_OPT_PATH=2, against the
+oracle.  Covers the geometries the chunking / padding logic branches on, the +M/-M tie slow path,
+NaN at f = 0, both input dtypes, and many units per launch (persistent loop, producer run-ahead)."""
+import numpy as np
+import pytest
+
+from conftest import same_bits, smooth_box
+
+pytestmark = pytest.mark.gpu
+F999 = float(np.float32(0.999))
+
+FUSED1 = [(32, 32, 32), (16, 32, 64), (64, 16, 32), (8, 8, 8), (4, 4, 4), (2, 2, 2), (8, 4, 2), (24, 40, 12),
+          (48, 16, 16), (32, 16, 64), (64, 64, 8), (4, 64, 128), (12, 20, 28), (2, 2, 4096), (64, 2, 2)]
+FUSED8 = [(64, 64, 64), (32, 64, 64), (64, 32, 64), (64, 64, 32), (48, 48, 48), (16, 128, 64), (40, 48, 56)]
+
+
+def check(ctx, oracle, boxes, dims, keep, mode=0):
+    packed = ctx.compress_batch(boxes, keep, thresh_mode=mode, dims=dims)
+    for b, d, p in zip(boxes, dims, packed):
+        runs, vals, _ = oracle.compress_unit(b, d, keep)
+        assert p.npairs == runs.size, (d, p.npairs, runs.size)
+        assert same_bits(p.runs, runs) and same_bits(p.vals, vals), d
+    return packed
+
+
+@pytest.fixture()
+def fused_ctx(ctx):
+    ctx.set_path(2)
+    yield ctx
+    ctx.set_path(0)
+
+
+@pytest.mark.parametrize("dims", FUSED1 + FUSED8)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_fused_single_unit_shapes(fused_ctx, oracle, dims, dt):
+    if dt == np.float32 and dims[0] % 4:
+        pytest.skip("float32 rows must be 16-byte multiples for the TMA path (falls back to generic)")
+    rng = np.random.default_rng(abs(hash((dims, str(dt)))) % 2**32)
+    for sym in (False, True):
+        b = smooth_box(dims, rng, dtype=dt, sym=sym)
+        for keep in (F999, float(np.float32(0.99))):
+            check(fused_ctx, oracle, [b], [dims], keep)
+
+
+def test_fused_many_units_mixed(fused_ctx, oracle):
+    rng = np.random.default_rng(2024)
+    dims = ([(32, 32, 32)] * 40 + [(64, 64, 64)] * 5 + [(16, 32, 64)] * 7 + [(8, 8, 8)] * 20) * 2
+    boxes = [smooth_box(d, rng, dtype=np.float64 if i % 3 else np.float32, sym=(i % 2 == 0), noise=10.0 ** -(i % 5))
+             for i, d in enumerate(dims)]
+    for keep in (F999, float(np.float32(0.9999))):
+        check(fused_ctx, oracle, boxes, dims, keep)
+
+
+def test_fused_tie_and_special_values(fused_ctx, oracle):
+    cases = []
+    for dims in [(4, 4, 4), (32, 32, 32), (64, 64, 64)]:
+        n = dims[0] * dims[1] * dims[2]
+        rng = np.random.default_rng(n)
+        z = np.zeros(n, np.float32); z[5] = 8; z[n - 3] = -8            # +M first
+        cases.append((dims, z))
+        z = np.zeros(n, np.float32); z[5] = -8; z[n - 3] = 8            # -M first -> everything kept
+        cases.append((dims, z))
+        z = np.zeros(n, np.float32); z[n // 2 + 1] = -8                 # negative max
+        cases.append((dims, z))
+        cases.append((dims, np.zeros(n, np.float32)))                   # all zero -> K = 0
+        z = rng.standard_normal(n).astype(np.float32); z[:8] = np.nan   # NaN at f = 0 -> nothing kept
+        cases.append((dims, z))
+        z = rng.standard_normal(n).astype(np.float32); z[n // 3] = np.nan
+        cases.append((dims, z))
+        z = rng.standard_normal(n).astype(np.float32); z[7] = np.inf; z[n - 9] = -np.inf
+        cases.append((dims, z))
+        z = np.full(n, 3902.4, np.float32)                              # constant box (the bundled fixtures)
+        cases.append((dims, z))
+        z = np.full(n, -16.0, np.float32)
+        cases.append((dims, z))
+    boxes = [c[1].reshape(c[0][2], c[0][1], c[0][0]) for c in cases]
+    dims = [c[0] for c in cases]
+    check(fused_ctx, oracle, boxes, dims, F999)
+    check(fused_ctx, oracle, boxes, dims, 0.5)
+
+
+def test_fused_global_threshold(fused_ctx, oracle, wc):
+    rng = np.random.default_rng(8)
+    dims = [(32, 32, 32)] * 6 + [(64, 64, 64)] * 2
+    boxes = [smooth_box(d, rng, sym=bool(i % 2)) * (1 + i) for i, d in enumerate(dims)]
+    keep = float(np.float32(0.99))
+    packed = fused_ctx.compress_batch(boxes, keep, thresh_mode=wc.WC_THRESH_GLOBAL)
+    flats = [oracle.haar_forward(b, d) for b, d in zip(boxes, dims)]
+    t = oracle.select_threshold_global(flats, keep)
+    for f, p in zip(flats, packed):
+        runs, vals = oracle.threshold_pack(f, t)
+        assert same_bits(p.runs, runs) and same_bits(p.vals, vals)
+
+
+def test_fused_rejects_what_it_cannot_hold(fused_ctx, wc):
+    with pytest.raises(wc.WcError) as e:
+        fused_ctx.compress_batch([np.zeros((7, 5, 3), np.float32)], 0.9)   # odd dims -> generic only
+    assert e.value.status == 2

@@ -405,7 +405,8 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
         slot_off[i] = slot_pairs;
         slot_pairs += align_up((size_t)n, 2); // keep every slot 16-byte aligned
 
-        int cls = fused_class(b.nx, b.ny, b.nz);
+        const void* cls_ptr = in_space == WC_HOST ? reinterpret_cast<const void*>(p->in_dev_off[i]) : b.data;
+        int cls = fused_class(b.nx, b.ny, b.nz, b.dtype, cls_ptr);
         if (ctx->opt_path == 1) cls = 0;
         if (ctx->opt_path == 2 && cls == 0 && n > 0) {
             delete p;
@@ -515,6 +516,11 @@ int wc_plan_set_inputs(wc_plan* p, const wc_box_desc* units) {
         const wc_box_desc& a = p->units[i];
         if (units[i].nx != a.nx || units[i].ny != a.ny || units[i].nz != a.nz ||
             units[i].dtype != a.dtype)
+            return WC_ERR_INVALID_ARG;
+        // the fused kernels read their input with 16-byte TMA bulk copies: the kernel class chosen at
+        // plan creation must still fit the new address
+        if (p->in_space == WC_DEVICE && ((reinterpret_cast<uintptr_t>(a.data) & 15u) == 0) &&
+            (reinterpret_cast<uintptr_t>(units[i].data) & 15u) != 0)
             return WC_ERR_INVALID_ARG;
     }
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -739,7 +745,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
     std::vector<size_t> coef_off(n);
     for (int i = 0; i < n; ++i) {
         long long total = (long long)jobs[i].nx * jobs[i].ny * jobs[i].nz;
-        int cls = total > 0 ? fused_class(jobs[i].nx, jobs[i].ny, jobs[i].nz) : -1;
+        int cls = total > 0 ? fused_class(jobs[i].nx, jobs[i].ny, jobs[i].nz, WC_F32, nullptr) : -1;
         if (ctx->opt_path == 1 && cls > 0) cls = 0;
         if (!fused_decode_available()) cls = cls > 0 ? 0 : cls;
         coef_off[i] = coef_floats;

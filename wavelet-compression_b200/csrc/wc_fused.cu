@@ -1,12 +1,620 @@
-// placeholder until the fused kernels land: everything goes through the generic path
+// Fused on-chip compress kernel for sm_100a: one unit's coefficients never leave the SM(s).
+//
+//   k_fused_compress<R>: a unit (box, component) is owned by a cluster of R CTAs (R = 1 or 8).
+//   CTA r takes the block-rows b in [r*nb, (r+1)*nb) (a y-slab), so
+//     - its input is, per z-plane, ONE contiguous piece of 2*nb rows  -> TMA bulk copies
+//       (cp.async.bulk.shared::cluster.global.mbarrier) issued by a dedicated producer warp into a
+//       4-stage shared-memory ring, running ahead of the consumers across unit boundaries;
+//     - its coefficients are the rows j' in {b, hy+b} of every i': 2*X "segments" of nb*Z values that
+//       are contiguous both in the CTA's shared-memory array C and in the global f order, so the
+//       ordered (run,value) packing only needs per-segment counts from the other CTAs (DSMEM push
+//       + cluster-scope mbarrier), never their coefficients.
+//   16 consumer warps: (A) 2x2x2 Haar blocks from the staged float64/float32 rows -> C (f order,
+//   padded against bank conflicts) + running max of +c and -c; (B) threshold of
+//   src/compressor.cpp:212-216; (C1) per-segment count / last-kept; (C2) ballot-ranked emission of
+//   (run, value) pairs straight to the unit's slot in HBM.
+//   HBM traffic per unit = 8N (or 4N) in + 8K out: the algorithmic minimum of SURVEY.md §8d.
 #include "wc_common.cuh"
 #include "wc_fused.h"
 
 namespace wc {
-int  fused_class(int, int, int) { return 0; }
+
+// ---- compile-time geometry ---------------------------------------------------------------------
+constexpr int F_CWARPS      = 16;                 // consumer warps
+constexpr int F_CONSUMERS   = F_CWARPS * 32;      // 512
+constexpr int F_THREADS     = F_CONSUMERS + 32;   // + producer warp
+constexpr int F_GROUP       = F_CONSUMERS / 2;    // two consumer groups alternate over the stages
+constexpr int F_CAP         = 32768;              // coefficients per CTA
+constexpr int F_CPAD        = 256;                // padding words of C (PAD * X <= 256)
+constexpr int F_STAGE       = 16384;              // payload bytes per stage
+constexpr int F_STAGE_ALLOC = F_STAGE + 2048;     // + piece padding
+constexpr int F_NSTAGES     = 4;
+constexpr int F_MAXSEG      = 128;                // segments (2*X) per CTA
+constexpr int F_MAXG        = 1024;               // gathered segment entries (2*X*R)
+
+constexpr int SM_C      = 0;
+constexpr int SM_STAGE  = SM_C + (F_CAP + F_CPAD) * 4;
+constexpr int SM_GCNT   = SM_STAGE + F_NSTAGES * F_STAGE_ALLOC;   // [2][F_MAXG] int
+constexpr int SM_GLAST  = SM_GCNT + 2 * F_MAXG * 4;               // [2][F_MAXG] int
+constexpr int SM_BASE   = SM_GLAST + 2 * F_MAXG * 4;              // [F_MAXSEG] int
+constexpr int SM_PREV   = SM_BASE + F_MAXSEG * 4;                 // [F_MAXSEG] int
+constexpr int SM_RED    = SM_PREV + F_MAXSEG * 4;                 // scratch: 64 x 8 bytes
+constexpr int SM_XS1    = SM_RED + 64 * 8;                        // [2][8] u64 exchange slots
+constexpr int SM_XS2    = SM_XS1 + 16 * 8;                        // [2][8] u64
+constexpr int SM_BARS   = SM_XS2 + 16 * 8;                        // full[4] empty[4] x1 x2 x3
+constexpr int SM_TOTAL  = SM_BARS + 16 * 8;
+static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
+
+struct FGeom {
+    int X, Y, Z, hx, hy, hz, es;
+    int nb;        // block-rows (y) per CTA
+    int LC, PAD;   // c-lanes per warp-row and padding words per i' slab of C
+    int CB, CZ;    // chunk extents in blocks
+    int ncb, ncz;  // chunks along b and c
+    int padp;      // bytes between consecutive plane pieces in a stage, beyond the payload
+    int seglen;    // nb * Z
+    int nseg;      // 2 * X
+    int nlocal;    // X * 2 * nb * Z
+};
+
+__host__ __device__ inline bool fused_geom(int X, int Y, int Z, int dtype, int R, FGeom& g) {
+    if (X < 2 || Y < 2 || Z < 2 || (X & 1) || (Y & 1) || (Z & 1)) return false;
+    g.X = X; g.Y = Y; g.Z = Z;
+    g.hx = X / 2; g.hy = Y / 2; g.hz = Z / 2;
+    g.es = dtype == WC_F64 ? 8 : 4;
+    if ((X * g.es) % 16) return false;
+    if (2 * X > F_MAXSEG) return false;
+    long long n = (long long)X * Y * Z;
+    if (g.hy % R) return false;
+    if (n / R > F_CAP) return false;
+    g.nb = g.hy / R;
+    int lc = g.hx >= 32 ? 1 : (g.hx >= 16 ? 2 : 4);
+    while (g.hz % lc) lc >>= 1;
+    g.LC  = lc;
+    g.PAD = lc;
+    if (g.PAD * X > F_CPAD) return false;
+    int row_pair = 2 * X * g.es;               // bytes of one block-row (2 y rows) of one plane
+    int min_chunk = 2 * lc * row_pair;
+    if (min_chunk > F_STAGE) return false;
+    int cb = F_STAGE / min_chunk;
+    if (cb >= g.nb) {
+        g.CB = g.nb;
+        int cz = F_STAGE / (2 * g.nb * row_pair);
+        cz -= cz % lc;
+        if (cz > g.hz) cz = g.hz;
+        if (cz > 32) cz = 32 - (32 % lc);
+        g.CZ = cz;
+    } else {
+        g.CB = cb;
+        g.CZ = lc;
+    }
+    g.ncb  = (g.nb + g.CB - 1) / g.CB;
+    g.ncz  = (g.hz + g.CZ - 1) / g.CZ;
+    g.padp = lc == 1 ? 0 : (lc == 2 ? 32 : 16);
+    g.seglen = g.nb * Z;
+    g.nseg   = 2 * X;
+    g.nlocal = g.nseg * g.seglen;
+    return true;
+}
+
+int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
+    if (reinterpret_cast<uintptr_t>(ptr) & 15u) return 0;
+    FGeom g;
+    if (fused_geom(nx, ny, nz, dtype, 1, g)) return 1;
+    if (fused_geom(nx, ny, nz, dtype, 8, g)) return 8;
+    return 0;
+}
 bool fused_decode_available() { return false; }
-cudaError_t launch_fused_compress(int, int, const UnitDev*, UnitState*, const int*, int, double,
-                                  const u64*, int, cudaStream_t, LaunchStats*) { return cudaSuccess; }
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_cluster(bar, parity)) { }
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t addr, u64 v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t nclusters_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(F_CONSUMERS) : "memory"); }
+
+// exact q / d for q < 65536, d < 65536 (m = ceil(2^32 / d); d == 1 handled by the caller's m == 0)
+__device__ __forceinline__ uint32_t fdiv(uint32_t q, uint32_t m) { return m ? __umulhi(q, m) : q; }
+__device__ __forceinline__ uint32_t fdiv_magic(uint32_t d) { return d <= 1 ? 0u : (0xffffffffu / d) + 1u; }
+
+// ---- the kernel -----------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(F_THREADS, 1)
+k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
+                 const int* __restrict__ unit_list, int n_list, double one_minus_keep,
+                 const u64* __restrict__ global_key, int mode) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* const  C      = reinterpret_cast<float*>(smem + SM_C);
+    int* const    g_cnt  = reinterpret_cast<int*>(smem + SM_GCNT);
+    int* const    g_last = reinterpret_cast<int*>(smem + SM_GLAST);
+    int* const    s_base = reinterpret_cast<int*>(smem + SM_BASE);
+    int* const    s_prev = reinterpret_cast<int*>(smem + SM_PREV);
+    u64* const    s_red  = reinterpret_cast<u64*>(smem + SM_RED);
+    u64* const    xs1    = reinterpret_cast<u64*>(smem + SM_XS1);
+    u64* const    xs2    = reinterpret_cast<u64*>(smem + SM_XS2);
+    const uint32_t bars  = smem_u32(smem + SM_BARS);
+    const uint32_t full0 = bars, empty0 = bars + 8 * F_NSTAGES;
+    const uint32_t xb1 = bars + 8 * (2 * F_NSTAGES), xb2 = xb1 + 8, xb3 = xb2 + 8;
+    const uint32_t stage0 = smem_u32(smem + SM_STAGE);
+
+    const int tid  = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = R > 1 ? cluster_ctarank() : 0u;
+    const uint32_t cid  = R > 1 ? cluster_id_x() : blockIdx.x;
+    const uint32_t ncl  = R > 1 ? nclusters_x() : gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < F_NSTAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, F_CWARPS / 2);
+        }
+        mbar_init(xb1, R);
+        mbar_init(xb2, R);
+        mbar_init(xb3, R);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (R > 1) cluster_sync_all();
+
+    if (warp == F_CWARPS) {
+        // =============================== producer warp ===============================
+        uint32_t kg = 0;
+        for (int ui = cid; ui < n_list; ui += ncl) {
+            const UnitDev u = units[unit_list[ui]];
+            FGeom g;
+            fused_geom(u.nx, u.ny, u.nz, u.dtype, R, g);
+            const char* in  = static_cast<const char*>(u.in);
+            const int   b0  = rank * g.nb;
+            const size_t row_bytes   = (size_t)g.X * g.es;
+            const size_t plane_bytes = row_bytes * g.Y;
+            for (int icb = 0; icb < g.ncb; ++icb) {
+                const int bc0 = icb * g.CB;
+                const int cbc = min(g.CB, g.nb - bc0);
+                const uint32_t piece_bytes = (uint32_t)(2 * cbc * row_bytes);
+                const uint32_t pstride     = piece_bytes + g.padp;
+                for (int icz = 0; icz < g.ncz; ++icz, ++kg) {
+                    const int cc0 = icz * g.CZ;
+                    const int czc = min(g.CZ, g.hz - cc0);
+                    const int npieces = 2 * czc;
+                    const uint32_t s = kg % F_NSTAGES;
+                    mbar_wait(empty0 + 8 * s, ((kg / F_NSTAGES) & 1) ^ 1);
+                    if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * s, piece_bytes * npieces);
+                    __syncwarp();
+                    const char* src0 = in + (size_t)(2 * cc0) * plane_bytes + (size_t)(2 * (b0 + bc0)) * row_bytes;
+                    for (int p = lane; p < npieces; p += 32)
+                        tma_load_1d(stage0 + s * F_STAGE_ALLOC + p * pstride, src0 + (size_t)p * plane_bytes,
+                                    piece_bytes, full0 + 8 * s);
+                }
+            }
+        }
+    } else {
+        // =============================== consumer warps ===============================
+        const int group = warp >> 3;          // 0 or 1: which stages this warp consumes
+        const int tig   = tid & (F_GROUP - 1);
+        const uint32_t lt = lanemask_lt();
+        uint32_t kg = 0, xph1 = 0, xph2 = 0, xph3 = 0;
+        for (int ui = cid; ui < n_list; ui += ncl) {
+            const int     uid = unit_list[ui];
+            const UnitDev u   = units[uid];
+            FGeom g;
+            fused_geom(u.nx, u.ny, u.nz, u.dtype, R, g);
+            const int b0 = rank * g.nb;
+            const uint32_t m_lc = fdiv_magic(g.LC), m_hx = fdiv_magic(g.hx);
+            const int slab = 2 * g.nb * g.Z + g.PAD;   // padded words per i'
+            float bp = 0.f, bn = 0.f;                  // running max of +c and of -c
+            bool  nan0 = false;
+
+            // ---------------- phase A: transform the staged rows into C ----------------
+            for (int icb = 0; icb < g.ncb; ++icb) {
+                const int bc0 = icb * g.CB;
+                const int cbc = min(g.CB, g.nb - bc0);
+                const uint32_t row_bytes   = (uint32_t)g.X * g.es;
+                const uint32_t piece_bytes = 2 * cbc * row_bytes;
+                const uint32_t pstride     = piece_bytes + g.padp;
+                for (int icz = 0; icz < g.ncz; ++icz, ++kg) {
+                    if ((int)(kg & 1) != group) continue;
+                    const int cc0 = icz * g.CZ;
+                    const int czc = min(g.CZ, g.hz - cc0);
+                    const uint32_t s = kg % F_NSTAGES;
+                    mbar_wait(full0 + 8 * s, (kg / F_NSTAGES) & 1);
+                    const unsigned char* st = smem + SM_STAGE + s * F_STAGE_ALLOC;
+                    const int nblk = czc * cbc * g.hx;
+                    const uint32_t chn = (uint32_t)czc / g.LC;       // c-groups of LC in this chunk
+                    const uint32_t m_chn = fdiv_magic(chn);
+                    for (int q = tig; q < nblk; q += F_GROUP) {
+                        // q -> (cl fastest, a, ch, bl)
+                        uint32_t t1 = fdiv(q, m_lc), cl = q - t1 * g.LC;
+                        uint32_t t2 = fdiv(t1, m_hx), a = t1 - t2 * g.hx;
+                        uint32_t bl = fdiv(t2, m_chn), ch = t2 - bl * chn;
+                        const int cz = ch * g.LC + cl;               // c within chunk
+                        float v[8];
+                        const unsigned char* p0 = st + (2 * cz) * pstride + (2 * bl) * row_bytes + a * 2 * g.es;
+                        if (g.es == 8) {
+#pragma unroll
+                            for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+                                for (int yi = 0; yi < 2; ++yi) {
+                                    double2 d = *reinterpret_cast<const double2*>(p0 + zi * pstride + yi * row_bytes);
+                                    v[zi * 4 + yi * 2]     = __double2float_rn(d.x);   // src/preprocess.cpp:78
+                                    v[zi * 4 + yi * 2 + 1] = __double2float_rn(d.y);
+                                }
+                        } else {
+#pragma unroll
+                            for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+                                for (int yi = 0; yi < 2; ++yi) {
+                                    float2 d = *reinterpret_cast<const float2*>(p0 + zi * pstride + yi * row_bytes);
+                                    v[zi * 4 + yi * 2]     = d.x;
+                                    v[zi * 4 + yi * 2 + 1] = d.y;
+                                }
+                        }
+                        haar_block_forward_full(v);
+                        const int c  = cc0 + cz;
+                        const int bb = bc0 + bl;                     // block-row within the CTA slab
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int sx = o & 1, sy = (o >> 1) & 1, sz = o >> 2;
+                            const int ip = a + sx * g.hx;
+                            const int idx = ip * slab + (sy * g.nb + bb) * g.Z + c + sz * g.hz;
+                            C[idx] = v[o];
+                            bp = fmaxf(bp, v[o]);
+                            bn = fmaxf(bn, -v[o]);
+                        }
+                        if (R == 1 || rank == 0) {
+                            if (a == 0 && bb == 0 && c == 0) nan0 = isnan(v[0]);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8 * s);
+                }
+            }
+
+            // ---------------- phase B: the threshold ----------------
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
+                bn = fmaxf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
+            }
+            const bool any_nan0 = __any_sync(0xffffffffu, nan0);
+            if (lane == 0) {
+                // bn >= 0, so its sign bit is free: it carries "the coefficient at f = 0 is NaN"
+                s_red[warp] = ((u64)__float_as_uint(bp) << 32) |
+                              (u64)((__float_as_uint(bn) & 0x7fffffffu) | (any_nan0 ? 0x80000000u : 0u));
+            }
+            consumer_bar();
+            float Mp = 0.f, Mn = 0.f;
+            bool  first_nan = false;
+            {
+                u64 x = s_red[lane & (F_CWARPS - 1)];
+                float p = __uint_as_float((uint32_t)(x >> 32));
+                float n = __uint_as_float((uint32_t)x & 0x7fffffffu);
+                first_nan = __any_sync(0xffffffffu, ((uint32_t)x >> 31) != 0);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
+                    n = fmaxf(n, __shfl_xor_sync(0xffffffffu, n, o));
+                }
+                Mp = p; Mn = n;
+            }
+            if (R > 1) {
+                // all-gather (Mp | Mn) over the cluster
+                const uint32_t par = xph1 & 1;
+                if (tid < R) {
+                    u64 pay = ((u64)__float_as_uint(Mp) << 32) |
+                              (u64)((__float_as_uint(Mn) & 0x7fffffffu) | (first_nan ? 0x80000000u : 0u));
+                    st_cluster_u64(mapa(smem_u32(&xs1[par * 8 + rank]), tid), pay);
+                    mbar_arrive_remote(mapa(xb1, tid));
+                }
+                mbar_wait_cluster(xb1, par);
+                ++xph1;
+                float p = 0.f, n = 0.f;
+                bool fn = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    u64 x = xs1[par * 8 + r];
+                    fn = fn || (((uint32_t)x >> 31) != 0);
+                    p  = fmaxf(p, __uint_as_float((uint32_t)(x >> 32)));
+                    n  = fmaxf(n, __uint_as_float((uint32_t)x & 0x7fffffffu));
+                }
+                Mp = p; Mn = n; first_nan = fn;
+            }
+            float M = fmaxf(Mp, Mn);
+            uint32_t sign = Mn > Mp ? 1u : 0u;
+            if (Mp == Mn && M != 0.f && !first_nan && mode != FUSED_GIVEN_THRESH) {
+                // +M and -M tie: the FIRST one in f order decides (std::max_element) -> find min f
+                u64 best = ~0ull;
+                const uint32_t m_sl = fdiv_magic(g.seglen);
+                for (int l = tid; l < g.nlocal; l += F_CONSUMERS) {
+                    uint32_t sg = fdiv(l, m_sl), w = l - sg * g.seglen;
+                    float c = C[l + g.PAD * (sg >> 1)];
+                    if (fabsf(c) == M) {
+                        uint32_t f = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z + w;
+                        u64 cand = ((u64)f << 1) | (u64)(__float_as_uint(c) >> 31);
+                        best = cand < best ? cand : best;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    u64 x = __shfl_xor_sync(0xffffffffu, best, o);
+                    best = x < best ? x : best;
+                }
+                consumer_bar();   // s_red reuse
+                if (lane == 0) s_red[warp] = best;
+                consumer_bar();
+                best = s_red[lane & (F_CWARPS - 1)];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    u64 x = __shfl_xor_sync(0xffffffffu, best, o);
+                    best = x < best ? x : best;
+                }
+                if (R > 1) {
+                    const uint32_t par = xph3 & 1;
+                    if (tid < R) {
+                        st_cluster_u64(mapa(smem_u32(&xs2[par * 8 + rank]), tid), best);
+                        mbar_arrive_remote(mapa(xb3, tid));
+                    }
+                    mbar_wait_cluster(xb3, par);
+                    ++xph3;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        u64 x = xs2[par * 8 + r];
+                        best = x < best ? x : best;
+                    }
+                }
+                sign = (uint32_t)(best & 1ull);
+            }
+            float tf;
+            {
+                u64 key = ((u64)__float_as_uint(M) << 32) | 2ull | (u64)sign;
+                if (mode == FUSED_GIVEN_THRESH) {
+                    u64 gk = *global_key;
+                    tf = threshold_float(gk & ~(1ull << 63), (gk >> 63) != 0, one_minus_keep);
+                } else {
+                    tf = threshold_float(key, first_nan, one_minus_keep);
+                }
+                if (tid == 0 && rank == 0) {
+                    states[uid].key      = key;
+                    states[uid].flags    = first_nan ? 1 : 0;
+                    states[uid].thresh_f = tf;
+                }
+            }
+            if (mode == FUSED_KEYS_ONLY) {
+                consumer_bar();   // C is rewritten by the next unit
+                continue;
+            }
+
+            // ---------------- phase C1: per-segment count and last kept ----------------
+            const int gpar = R > 1 ? (int)(xph2 & 1) : 0;
+            int* const my_cnt  = g_cnt + gpar * F_MAXG;
+            int* const my_last = g_last + gpar * F_MAXG;
+            for (int sg = warp; sg < g.nseg; sg += F_CWARPS) {
+                const float* cs = C + sg * g.seglen + g.PAD * (sg >> 1);
+                int cnt = 0, last = -1;
+                for (int w0 = 0; w0 < g.seglen; w0 += 32) {
+                    int w = w0 + lane;
+                    bool kf = w < g.seglen && keep_coef(cs[w], tf);
+                    uint32_t bal = __ballot_sync(0xffffffffu, kf);
+                    cnt += __popc(bal);
+                    if (bal) last = w0 + 31 - __clz(bal);
+                }
+                if (lane == 0) {
+                    int fstart = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z;
+                    int lastf  = last >= 0 ? fstart + last : -1;
+                    if (R == 1) {
+                        my_cnt[sg]  = cnt;
+                        my_last[sg] = lastf;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            st_cluster_u32(mapa(smem_u32(&my_cnt[sg * R + rank]), r), (uint32_t)cnt);
+                            st_cluster_u32(mapa(smem_u32(&my_last[sg * R + rank]), r), (uint32_t)lastf);
+                        }
+                    }
+                }
+            }
+            if (R > 1) {
+                fence_cluster();
+                consumer_bar();
+                if (tid < R) mbar_arrive_remote(mapa(xb2, tid));
+                mbar_wait_cluster(xb2, gpar);
+                ++xph2;
+            } else {
+                consumer_bar();
+            }
+
+            // ---------------- scan over the segments in global order ----------------
+            {
+                const int NG = g.nseg * R;   // <= 1024, entry e = sg * R + r
+                const int e0 = tid * 2;
+                int c0 = e0 < NG ? my_cnt[e0] : 0, c1 = e0 + 1 < NG ? my_cnt[e0 + 1] : 0;
+                int l0 = e0 < NG ? my_last[e0] : -1, l1 = e0 + 1 < NG ? my_last[e0 + 1] : -1;
+                int isum = c0 + c1, imax = max(l0, l1);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int ps = __shfl_up_sync(0xffffffffu, isum, o);
+                    int pm = __shfl_up_sync(0xffffffffu, imax, o);
+                    if (lane >= o) { isum += ps; imax = max(imax, pm); }
+                }
+                int* sr = reinterpret_cast<int*>(s_red);
+                if (lane == 31) { sr[warp] = isum; sr[32 + warp] = imax; }
+                consumer_bar();
+                int wsum = 0, wmax = -1, total = 0;
+#pragma unroll
+                for (int i = 0; i < F_CWARPS; ++i) {
+                    int xs = sr[i], xm = sr[32 + i];
+                    if (i < warp) { wsum += xs; wmax = max(wmax, xm); }
+                    total += xs;
+                }
+                int es = __shfl_up_sync(0xffffffffu, isum, 1);
+                int em = __shfl_up_sync(0xffffffffu, imax, 1);
+                if (lane == 0) { es = 0; em = -1; }
+                es += wsum;
+                em = max(em, wmax);
+                // entry e0: exclusive = (es, em); entry e0+1: (es + c0, max(em, l0))
+                if (e0 < NG && (R == 1 || (e0 % R) == (int)rank)) { s_base[e0 / R] = es; s_prev[e0 / R] = em; }
+                if (e0 + 1 < NG && (R == 1 || ((e0 + 1) % R) == (int)rank)) {
+                    s_base[(e0 + 1) / R] = es + c0;
+                    s_prev[(e0 + 1) / R] = max(em, l0);
+                }
+                if (tid == 0 && rank == 0) states[uid].npairs = total;
+                consumer_bar();
+            }
+
+            // ---------------- phase C2: emit (run, value) pairs ----------------
+            for (int sg = warp; sg < g.nseg; sg += F_CWARPS) {
+                const float* cs = C + sg * g.seglen + g.PAD * (sg >> 1);
+                const int fstart = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z;
+                int pos = s_base[sg], prev = s_prev[sg];
+                int2* out = reinterpret_cast<int2*>(u.out);
+                for (int w0 = 0; w0 < g.seglen; w0 += 32) {
+                    int w = w0 + lane;
+                    float c = w < g.seglen ? cs[w] : 0.f;
+                    bool kf = w < g.seglen && keep_coef(c, tf);
+                    uint32_t bal = __ballot_sync(0xffffffffu, kf);
+                    if (kf) {
+                        uint32_t lower = bal & lt;
+                        int pf = lower ? fstart + w0 + 31 - __clz(lower) : prev;
+                        out[pos + __popc(lower)] = make_int2(fstart + w - pf - 1, __float_as_int(c));
+                    }
+                    if (bal) {
+                        pos += __popc(bal);
+                        prev = fstart + w0 + 31 - __clz(bal);
+                    }
+                }
+            }
+            consumer_bar();   // C and the segment arrays are rewritten by the next unit
+        }
+    }
+    if (R > 1) cluster_sync_all();   // no CTA may exit while peers can still write into its smem
+}
+
+// ---- launchers --------------------------------------------------------------------------------------
+template <int R>
+static cudaError_t launch_fc(int mode, const UnitDev* units, UnitState* states, const int* list, int n,
+                             double omk, const u64* gkey, int sm_count, cudaStream_t st, LaunchStats* ls) {
+    static int n_clusters_cached = 0;
+    auto kern = k_fused_compress<R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim         = dim3(F_THREADS);
+    cfg.dynamicSmemBytes = SM_TOTAL;
+    cfg.stream           = st;
+    cudaLaunchAttribute attr[1];
+    int grid;
+    if (R > 1) {
+        attr[0].id               = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = R;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs    = attr;
+        cfg.numAttrs = 1;
+        if (n_clusters_cached == 0) {
+            cfg.gridDim = dim3(R * (sm_count / R));
+            int nc = 0;
+            e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+            if (e != cudaSuccess) return e;
+            if (nc < 1) return cudaErrorLaunchOutOfResources;
+            n_clusters_cached = nc;
+        }
+        int nc = n_clusters_cached < n ? n_clusters_cached : n;
+        grid = nc * R;
+    } else {
+        grid = sm_count < n ? sm_count : n;
+    }
+    cfg.gridDim = dim3(grid);
+    ls->begin(R == 1 ? KID_FUSED_C1 : KID_FUSED_C8, st);
+    e = cudaLaunchKernelEx(&cfg, kern, units, states, list, n, omk, gkey, mode);
+    ls->end(st);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, UnitState* states,
+                                  const int* unit_list, int n_list, double one_minus_keep,
+                                  const u64* global_key, int sm_count, cudaStream_t st,
+                                  LaunchStats* ls) {
+    if (n_list <= 0) return cudaSuccess;
+    if (cluster == 1)
+        return launch_fc<1>(mode, units, states, unit_list, n_list, one_minus_keep, global_key, sm_count, st, ls);
+    if (cluster == 8)
+        return launch_fc<8>(mode, units, states, unit_list, n_list, one_minus_keep, global_key, sm_count, st, ls);
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_fused_decompress(int, const DecUnitDev*, const InvUnitDev*, const int*, int, int*,
-                                    int, cudaStream_t, LaunchStats*) { return cudaSuccess; }
+                                    int, cudaStream_t, LaunchStats*) {
+    return cudaSuccess;
+}
+
 } // namespace wc

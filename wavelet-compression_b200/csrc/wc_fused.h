@@ -13,7 +13,7 @@ enum { FUSED_FULL = 0, FUSED_KEYS_ONLY = 1, FUSED_GIVEN_THRESH = 2 };
 
 // Which fused kernel handles a box: 0 = none (generic path), 1 = one CTA per unit,
 // 8 = one 8-CTA cluster per unit.
-int  fused_class(int nx, int ny, int nz);
+int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 bool fused_decode_available();
 
 cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, UnitState* states,
