@@ -9,8 +9,9 @@ from conftest import same_bits, smooth_box
 pytestmark = pytest.mark.gpu
 F999 = float(np.float32(0.999))
 
-FUSED1 = [(32, 32, 32), (16, 32, 64), (64, 16, 32), (8, 8, 8), (4, 4, 4), (2, 2, 2), (8, 4, 2), (24, 40, 12),
-          (48, 16, 16), (32, 16, 64), (64, 64, 8), (4, 64, 128), (12, 20, 28), (2, 2, 4096), (64, 2, 2)]
+FUSED1 = [(32, 32, 32), (16, 32, 64), (64, 16, 32), (8, 8, 8), (4, 4, 4), (2, 2, 4), (8, 4, 4), (24, 40, 12),
+          (48, 16, 16), (32, 16, 64), (64, 64, 8), (4, 64, 128), (12, 20, 28), (2, 2, 4096), (64, 2, 4),
+          (16, 16, 24), (8, 8, 40)]
 FUSED8 = [(64, 64, 64), (32, 64, 64), (64, 32, 64), (64, 64, 32), (48, 48, 48), (16, 128, 64), (40, 48, 56)]
 
 
@@ -44,7 +45,7 @@ def test_fused_single_unit_shapes(fused_ctx, oracle, dims, dt):
 
 def test_fused_many_units_mixed(fused_ctx, oracle):
     rng = np.random.default_rng(2024)
-    dims = ([(32, 32, 32)] * 40 + [(64, 64, 64)] * 5 + [(16, 32, 64)] * 7 + [(8, 8, 8)] * 20) * 2
+    dims = ([(32, 32, 32)] * 40 + [(64, 64, 64)] * 5 + [(16, 32, 64)] * 7 + [(8, 8, 8)] * 20 + [(24, 40, 12)] * 3) * 2
     boxes = [smooth_box(d, rng, dtype=np.float64 if i % 3 else np.float32, sym=(i % 2 == 0), noise=10.0 ** -(i % 5))
              for i, d in enumerate(dims)]
     for keep in (F999, float(np.float32(0.9999))):
@@ -93,6 +94,21 @@ def test_fused_global_threshold(fused_ctx, oracle, wc):
 
 
 def test_fused_rejects_what_it_cannot_hold(fused_ctx, wc):
-    with pytest.raises(wc.WcError) as e:
-        fused_ctx.compress_batch([np.zeros((7, 5, 3), np.float32)], 0.9)   # odd dims -> generic only
-    assert e.value.status == 2
+    for shape in [(7, 5, 3), (2, 4, 8), (128, 128, 128)]:   # odd dims, nz % 4 != 0, too large -> generic only
+        with pytest.raises(wc.WcError) as e:
+            fused_ctx.compress_batch([np.zeros(shape, np.float32)], 0.9)
+        assert e.value.status == 2
+
+
+def test_fused_persistent_loop_many_units_per_cta(fused_ctx, oracle):
+    """More units than CTAs / clusters: every CTA runs its persistent loop several times, the producer
+    warp prefetches across unit boundaries and the stage ring wraps many times."""
+    rng = np.random.default_rng(77)
+    dims = [(32, 32, 32)] * 620 + [(64, 64, 64)] * 50
+    base32 = [smooth_box((32, 32, 32), rng, dtype=np.float64, sym=bool(i % 2), noise=10.0 ** -(i % 4)) for i in range(8)]
+    base64 = [smooth_box((64, 64, 64), rng, dtype=np.float64, sym=bool(i % 2)) for i in range(3)]
+    boxes = [base32[i % 8] * (1.0 + 0.001 * i) for i in range(620)] + [base64[i % 3] * (1.0 + 0.01 * i) for i in range(50)]
+    packed = fused_ctx.compress_batch(boxes, F999, dims=dims)
+    for i in list(range(0, 620, 37)) + list(range(620, 670, 7)) + [619, 669]:
+        runs, vals, _ = oracle.compress_unit(boxes[i], dims[i], F999)
+        assert same_bits(packed[i].runs, runs) and same_bits(packed[i].vals, vals), i

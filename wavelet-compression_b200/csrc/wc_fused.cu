@@ -23,42 +23,45 @@ namespace wc {
 constexpr int F_CWARPS      = 16;                 // consumer warps
 constexpr int F_CONSUMERS   = F_CWARPS * 32;      // 512
 constexpr int F_THREADS     = F_CONSUMERS + 32;   // + producer warp
-constexpr int F_GROUP       = F_CONSUMERS / 2;    // two consumer groups alternate over the stages
+constexpr int F_NGROUPS     = 4;                  // consumer groups; chunk k is consumed by group k % 4
+constexpr int F_GROUP       = F_CONSUMERS / F_NGROUPS;   // 128 threads = one warp per SM sub-partition
 constexpr int F_CAP         = 32768;              // coefficients per CTA
-constexpr int F_CPAD        = 256;                // padding words of C (PAD * X <= 256)
+constexpr int F_PAD         = 4;                  // padding words per i' slab of C (keeps float4/float2
+                                                  // alignment, makes a-lanes hit banks 4a + ...)
+constexpr int F_CPAD        = 256;                // total padding words of C (F_PAD * X, X <= 64)
 constexpr int F_STAGE       = 16384;              // payload bytes per stage
-constexpr int F_STAGE_ALLOC = F_STAGE + 2048;     // + piece padding
-constexpr int F_NSTAGES     = 4;
+constexpr int F_PADP        = 16;                 // bytes between plane pieces in a stage (LDS.128 banks)
+constexpr int F_STAGE_ALLOC = F_STAGE + 64 * F_PADP;
+constexpr int F_NSTAGES     = 5;
 constexpr int F_MAXSEG      = 128;                // segments (2*X) per CTA
 constexpr int F_MAXG        = 1024;               // gathered segment entries (2*X*R)
 
 constexpr int SM_C      = 0;
 constexpr int SM_STAGE  = SM_C + (F_CAP + F_CPAD) * 4;
-constexpr int SM_GCNT   = SM_STAGE + F_NSTAGES * F_STAGE_ALLOC;   // [2][F_MAXG] int
-constexpr int SM_GLAST  = SM_GCNT + 2 * F_MAXG * 4;               // [2][F_MAXG] int
-constexpr int SM_BASE   = SM_GLAST + 2 * F_MAXG * 4;              // [F_MAXSEG] int
+constexpr int SM_G      = SM_STAGE + F_NSTAGES * F_STAGE_ALLOC;   // [2][F_MAXG] u32: cnt << 16 | last
+constexpr int SM_BASE   = SM_G + 2 * F_MAXG * 4;                  // [F_MAXSEG] int
 constexpr int SM_PREV   = SM_BASE + F_MAXSEG * 4;                 // [F_MAXSEG] int
 constexpr int SM_RED    = SM_PREV + F_MAXSEG * 4;                 // scratch: 64 x 8 bytes
 constexpr int SM_XS1    = SM_RED + 64 * 8;                        // [2][8] u64 exchange slots
 constexpr int SM_XS2    = SM_XS1 + 16 * 8;                        // [2][8] u64
-constexpr int SM_BARS   = SM_XS2 + 16 * 8;                        // full[4] empty[4] x1 x2 x3
-constexpr int SM_TOTAL  = SM_BARS + 16 * 8;
+constexpr int SM_BARS   = SM_XS2 + 16 * 8;                        // full[5] empty[5] x1 x2 x3
+constexpr int SM_TOTAL  = SM_BARS + 20 * 8;                       // + gen[5] u32
 static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
+static_assert(SM_STAGE % 128 == 0 && F_STAGE_ALLOC % 128 == 0, "stage alignment");
 
 struct FGeom {
     int X, Y, Z, hx, hy, hz, es;
     int nb;        // block-rows (y) per CTA
-    int LC, PAD;   // c-lanes per warp-row and padding words per i' slab of C
-    int CB, CZ;    // chunk extents in blocks
+    int CB, CZ;    // chunk extents in blocks (CZ even: a thread transforms two c-adjacent blocks at once)
     int ncb, ncz;  // chunks along b and c
-    int padp;      // bytes between consecutive plane pieces in a stage, beyond the payload
     int seglen;    // nb * Z
     int nseg;      // 2 * X
     int nlocal;    // X * 2 * nb * Z
+    int slab;      // padded words of C per i'
 };
 
 __host__ __device__ inline bool fused_geom(int X, int Y, int Z, int dtype, int R, FGeom& g) {
-    if (X < 2 || Y < 2 || Z < 2 || (X & 1) || (Y & 1) || (Z & 1)) return false;
+    if (X < 2 || Y < 2 || Z < 4 || (X & 1) || (Y & 1) || (Z & 3)) return false;
     g.X = X; g.Y = Y; g.Z = Z;
     g.hx = X / 2; g.hy = Y / 2; g.hz = Z / 2;
     g.es = dtype == WC_F64 ? 8 : 4;
@@ -68,32 +71,29 @@ __host__ __device__ inline bool fused_geom(int X, int Y, int Z, int dtype, int R
     if (g.hy % R) return false;
     if (n / R > F_CAP) return false;
     g.nb = g.hy / R;
-    int lc = g.hx >= 32 ? 1 : (g.hx >= 16 ? 2 : 4);
-    while (g.hz % lc) lc >>= 1;
-    g.LC  = lc;
-    g.PAD = lc;
-    if (g.PAD * X > F_CPAD) return false;
-    int row_pair = 2 * X * g.es;               // bytes of one block-row (2 y rows) of one plane
-    int min_chunk = 2 * lc * row_pair;
-    if (min_chunk > F_STAGE) return false;
-    int cb = F_STAGE / min_chunk;
+    int cz0 = (g.hz % 4 == 0) ? 4 : 2;
+    int row_pair = 2 * X * g.es;                 // bytes of one block-row (2 y rows) of one z-plane
+    if (2 * cz0 * row_pair > F_STAGE) cz0 = 2;
+    int per_b = 2 * cz0 * row_pair;              // bytes of one block-row for cz0 block-planes
+    if (per_b > F_STAGE) return false;
+    int cb = F_STAGE / per_b;
     if (cb >= g.nb) {
         g.CB = g.nb;
         int cz = F_STAGE / (2 * g.nb * row_pair);
-        cz -= cz % lc;
+        cz -= cz % cz0;
         if (cz > g.hz) cz = g.hz;
-        if (cz > 32) cz = 32 - (32 % lc);
+        if (cz > 32) cz = 32;
         g.CZ = cz;
     } else {
         g.CB = cb;
-        g.CZ = lc;
+        g.CZ = cz0;
     }
     g.ncb  = (g.nb + g.CB - 1) / g.CB;
     g.ncz  = (g.hz + g.CZ - 1) / g.CZ;
-    g.padp = lc == 1 ? 0 : (lc == 2 ? 32 : 16);
     g.seglen = g.nb * Z;
     g.nseg   = 2 * X;
     g.nlocal = g.nseg * g.seglen;
+    g.slab   = 2 * g.nb * Z + F_PAD;
     return true;
 }
 
@@ -148,6 +148,14 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_volatile_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -188,23 +196,85 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t q, uint32_t m) { return m ? __
 __device__ __forceinline__ uint32_t fdiv_magic(uint32_t d) { return d <= 1 ? 0u : (0xffffffffu / d) + 1u; }
 
 // ---- the kernel -----------------------------------------------------------------------------------
+__device__ __forceinline__ void st_pair_pred(bool p, int2* addr, int run, float val) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.u32 q, %0, 0;\n\t"
+        "@q st.global.v2.b32 [%1], {%2, %3};\n\t}"
+        ::"r"((uint32_t)p), "l"(addr), "r"(run), "r"(__float_as_int(val)) : "memory");
+}
+
+// One 1-D Haar step on two independent blocks at once (packed f32x2): lo = (lo+hi)*0.5, hi = (lo-hi)*0.5,
+// each rounded exactly like the scalar __fadd_rn / __fsub_rn / __fmul_rn sequence: hi*(-1)+lo is the
+// correctly rounded difference, and the *0.5 is a separate rounding step as in the reference.
+__device__ __forceinline__ void haar_pair2(float2& lo, float2& hi) {
+    const float2 half = make_float2(0.5f, 0.5f), neg1 = make_float2(-1.f, -1.f);
+    float2 s = __fadd2_rn(lo, hi);
+    float2 d = __ffma2_rn(hi, neg1, lo);
+    lo = __fmul2_rn(s, half);
+    hi = __fmul2_rn(d, half);
+}
+
+// Transforms the two c-adjacent blocks whose 4 z-planes start at `p0` in the stage and stores the 8 x 2
+// coefficients into C.  v[zi*4+yi*2+xi] = (block c, block c+1).
+template <int ES>
+__device__ __forceinline__ float transform_pair(const unsigned char* p0, uint32_t pstride, uint32_t row_bytes,
+                                                float* cdst, int o1, int o2, int o3, float& bp, float& bn) {
+    float2 v[8];
+#pragma unroll
+    for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+        for (int yi = 0; yi < 2; ++yi) {
+            const unsigned char* pa = p0 + zi * pstride + yi * row_bytes;
+            const unsigned char* pb = pa + 2 * pstride;
+            if (ES == 8) {
+                double2 da = *reinterpret_cast<const double2*>(pa);
+                double2 db = *reinterpret_cast<const double2*>(pb);
+                v[zi * 4 + yi * 2]     = make_float2(__double2float_rn(da.x), __double2float_rn(db.x)); // src/preprocess.cpp:78
+                v[zi * 4 + yi * 2 + 1] = make_float2(__double2float_rn(da.y), __double2float_rn(db.y));
+            } else {
+                float2 fa = *reinterpret_cast<const float2*>(pa);
+                float2 fb = *reinterpret_cast<const float2*>(pb);
+                v[zi * 4 + yi * 2]     = make_float2(fa.x, fb.x);
+                v[zi * 4 + yi * 2 + 1] = make_float2(fa.y, fb.y);
+            }
+        }
+    // Z, then Y, then X (src/compressor.cpp:98-175)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) haar_pair2(v[q], v[4 + q]);
+#pragma unroll
+    for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+        for (int xi = 0; xi < 2; ++xi) haar_pair2(v[zi * 4 + xi], v[zi * 4 + 2 + xi]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) haar_pair2(v[2 * q], v[2 * q + 1]);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        const int idx = (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3;
+        *reinterpret_cast<float2*>(cdst + idx) = v[o];
+        bp = fmaxf(fmaxf(bp, v[o].x), v[o].y);
+        bn = fmaxf(fmaxf(bn, -v[o].x), -v[o].y);
+    }
+    return v[0].x;
+}
+
 template <int R>
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                  const int* __restrict__ unit_list, int n_list, double one_minus_keep,
                  const u64* __restrict__ global_key, int mode) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float* const  C      = reinterpret_cast<float*>(smem + SM_C);
-    int* const    g_cnt  = reinterpret_cast<int*>(smem + SM_GCNT);
-    int* const    g_last = reinterpret_cast<int*>(smem + SM_GLAST);
-    int* const    s_base = reinterpret_cast<int*>(smem + SM_BASE);
-    int* const    s_prev = reinterpret_cast<int*>(smem + SM_PREV);
-    u64* const    s_red  = reinterpret_cast<u64*>(smem + SM_RED);
-    u64* const    xs1    = reinterpret_cast<u64*>(smem + SM_XS1);
-    u64* const    xs2    = reinterpret_cast<u64*>(smem + SM_XS2);
+    float* const    C      = reinterpret_cast<float*>(smem + SM_C);
+    uint32_t* const g_pk   = reinterpret_cast<uint32_t*>(smem + SM_G);
+    int* const      s_base = reinterpret_cast<int*>(smem + SM_BASE);
+    int* const      s_prev = reinterpret_cast<int*>(smem + SM_PREV);
+    u64* const      s_red  = reinterpret_cast<u64*>(smem + SM_RED);
+    u64* const      xs1    = reinterpret_cast<u64*>(smem + SM_XS1);
+    u64* const      xs2    = reinterpret_cast<u64*>(smem + SM_XS2);
     const uint32_t bars  = smem_u32(smem + SM_BARS);
     const uint32_t full0 = bars, empty0 = bars + 8 * F_NSTAGES;
     const uint32_t xb1 = bars + 8 * (2 * F_NSTAGES), xb2 = xb1 + 8, xb3 = xb2 + 8;
+    const uint32_t gen0 = xb3 + 8;   // [F_NSTAGES] u32: chunk number each stage currently holds
     const uint32_t stage0 = smem_u32(smem + SM_STAGE);
 
     const int tid  = threadIdx.x;
@@ -216,11 +286,12 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
     if (tid == 0) {
         for (int s = 0; s < F_NSTAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, F_CWARPS / 2);
+            mbar_init(empty0 + 8 * s, F_GROUP / 32);
         }
         mbar_init(xb1, R);
         mbar_init(xb2, R);
         mbar_init(xb3, R);
+        for (int s = 0; s < F_NSTAGES; ++s) st_volatile_shared_u32(gen0 + 4 * s, 0xffffffffu);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -241,14 +312,17 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                 const int bc0 = icb * g.CB;
                 const int cbc = min(g.CB, g.nb - bc0);
                 const uint32_t piece_bytes = (uint32_t)(2 * cbc * row_bytes);
-                const uint32_t pstride     = piece_bytes + g.padp;
+                const uint32_t pstride     = piece_bytes + F_PADP;
                 for (int icz = 0; icz < g.ncz; ++icz, ++kg) {
                     const int cc0 = icz * g.CZ;
                     const int czc = min(g.CZ, g.hz - cc0);
                     const int npieces = 2 * czc;
                     const uint32_t s = kg % F_NSTAGES;
                     mbar_wait(empty0 + 8 * s, ((kg / F_NSTAGES) & 1) ^ 1);
-                    if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * s, piece_bytes * npieces);
+                    if (lane == 0) {
+                        st_volatile_shared_u32(gen0 + 4 * s, kg);   // stage s now belongs to chunk kg
+                        mbar_arrive_expect_tx(full0 + 8 * s, piece_bytes * npieces);
+                    }
                     __syncwarp();
                     const char* src0 = in + (size_t)(2 * cc0) * plane_bytes + (size_t)(2 * (b0 + bc0)) * row_bytes;
                     for (int p = lane; p < npieces; p += 32)
@@ -259,7 +333,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
         }
     } else {
         // =============================== consumer warps ===============================
-        const int group = warp >> 3;          // 0 or 1: which stages this warp consumes
+        const int group = warp >> 2;              // chunk k belongs to group k % 4
         const int tig   = tid & (F_GROUP - 1);
         const uint32_t lt = lanemask_lt();
         uint32_t kg = 0, xph1 = 0, xph2 = 0, xph3 = 0;
@@ -269,70 +343,63 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
             FGeom g;
             fused_geom(u.nx, u.ny, u.nz, u.dtype, R, g);
             const int b0 = rank * g.nb;
-            const uint32_t m_lc = fdiv_magic(g.LC), m_hx = fdiv_magic(g.hx);
-            const int slab = 2 * g.nb * g.Z + g.PAD;   // padded words per i'
-            float bp = 0.f, bn = 0.f;                  // running max of +c and of -c
+            const uint32_t m_hx = fdiv_magic(g.hx);
+            const uint32_t row_bytes = (uint32_t)g.X * g.es;
+            const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
+            float bp = 0.f, bn = 0.f;             // running max of +c and of -c
             bool  nan0 = false;
 
             // ---------------- phase A: transform the staged rows into C ----------------
+            int c_czc = -1, c_cbc = -1, c_npairs = 0;     // cached decomposition of pair index `tig`
+            uint32_t c_mnpc = 0, c_src = 0;
+            int c_crel = 0;
+            bool c_first = false;
             for (int icb = 0; icb < g.ncb; ++icb) {
                 const int bc0 = icb * g.CB;
                 const int cbc = min(g.CB, g.nb - bc0);
-                const uint32_t row_bytes   = (uint32_t)g.X * g.es;
-                const uint32_t piece_bytes = 2 * cbc * row_bytes;
-                const uint32_t pstride     = piece_bytes + g.padp;
+                const uint32_t pstride = 2 * cbc * row_bytes + F_PADP;
                 for (int icz = 0; icz < g.ncz; ++icz, ++kg) {
-                    if ((int)(kg & 1) != group) continue;
+                    if ((int)(kg & (F_NGROUPS - 1)) != group) continue;
                     const int cc0 = icz * g.CZ;
                     const int czc = min(g.CZ, g.hz - cc0);
+                    const int npc = czc >> 1;                    // c-pairs in this chunk
+                    if (czc != c_czc || cbc != c_cbc) {
+                        c_czc = czc; c_cbc = cbc;
+                        c_npairs = npc * cbc * g.hx;
+                        c_mnpc   = fdiv_magic(npc);
+                        // pair q -> (cp fastest, a, bl)
+                        uint32_t t1 = fdiv(tig, c_mnpc), cp = tig - t1 * npc;
+                        uint32_t bl = fdiv(t1, m_hx), a = t1 - bl * g.hx;
+                        c_src   = (4 * cp) * pstride + (2 * bl) * row_bytes + a * 2 * g.es;
+                        c_crel  = a * g.slab + bl * g.Z + 2 * cp;
+                        c_first = (a == 0 && bl == 0 && cp == 0);
+                    }
                     const uint32_t s = kg % F_NSTAGES;
+                    // The groups run independently, so this group may get here before the PREVIOUS use of
+                    // stage s (chunk kg - NSTAGES, another group's) has even landed.
+                    // A parity wait alone is ambiguous here: it cannot tell "the previous use of the stage has
+                    // not landed yet" from "this use has landed".  The producer therefore publishes the chunk
+                    // number it is filling stage s with (after the stage was released), and the group waits
+                    // for that first.
+                    while (ld_volatile_shared_u32(gen0 + 4 * s) != kg) { }
                     mbar_wait(full0 + 8 * s, (kg / F_NSTAGES) & 1);
                     const unsigned char* st = smem + SM_STAGE + s * F_STAGE_ALLOC;
-                    const int nblk = czc * cbc * g.hx;
-                    const uint32_t chn = (uint32_t)czc / g.LC;       // c-groups of LC in this chunk
-                    const uint32_t m_chn = fdiv_magic(chn);
-                    for (int q = tig; q < nblk; q += F_GROUP) {
-                        // q -> (cl fastest, a, ch, bl)
-                        uint32_t t1 = fdiv(q, m_lc), cl = q - t1 * g.LC;
-                        uint32_t t2 = fdiv(t1, m_hx), a = t1 - t2 * g.hx;
-                        uint32_t bl = fdiv(t2, m_chn), ch = t2 - bl * chn;
-                        const int cz = ch * g.LC + cl;               // c within chunk
-                        float v[8];
-                        const unsigned char* p0 = st + (2 * cz) * pstride + (2 * bl) * row_bytes + a * 2 * g.es;
-                        if (g.es == 8) {
-#pragma unroll
-                            for (int zi = 0; zi < 2; ++zi)
-#pragma unroll
-                                for (int yi = 0; yi < 2; ++yi) {
-                                    double2 d = *reinterpret_cast<const double2*>(p0 + zi * pstride + yi * row_bytes);
-                                    v[zi * 4 + yi * 2]     = __double2float_rn(d.x);   // src/preprocess.cpp:78
-                                    v[zi * 4 + yi * 2 + 1] = __double2float_rn(d.y);
-                                }
-                        } else {
-#pragma unroll
-                            for (int zi = 0; zi < 2; ++zi)
-#pragma unroll
-                                for (int yi = 0; yi < 2; ++yi) {
-                                    float2 d = *reinterpret_cast<const float2*>(p0 + zi * pstride + yi * row_bytes);
-                                    v[zi * 4 + yi * 2]     = d.x;
-                                    v[zi * 4 + yi * 2 + 1] = d.y;
-                                }
+                    float* const cbase = C + bc0 * g.Z + cc0;
+                    for (int q = tig; q < c_npairs; q += F_GROUP) {
+                        uint32_t src = c_src;
+                        int crel = c_crel;
+                        bool first = c_first;
+                        if (q != tig) {
+                            uint32_t t1 = fdiv(q, c_mnpc), cp = q - t1 * npc;
+                            uint32_t bl = fdiv(t1, m_hx), a = t1 - bl * g.hx;
+                            src   = (4 * cp) * pstride + (2 * bl) * row_bytes + a * 2 * g.es;
+                            crel  = a * g.slab + bl * g.Z + 2 * cp;
+                            first = false;
                         }
-                        haar_block_forward_full(v);
-                        const int c  = cc0 + cz;
-                        const int bb = bc0 + bl;                     // block-row within the CTA slab
-#pragma unroll
-                        for (int o = 0; o < 8; ++o) {
-                            const int sx = o & 1, sy = (o >> 1) & 1, sz = o >> 2;
-                            const int ip = a + sx * g.hx;
-                            const int idx = ip * slab + (sy * g.nb + bb) * g.Z + c + sz * g.hz;
-                            C[idx] = v[o];
-                            bp = fmaxf(bp, v[o]);
-                            bn = fmaxf(bn, -v[o]);
-                        }
-                        if (R == 1 || rank == 0) {
-                            if (a == 0 && bb == 0 && c == 0) nan0 = isnan(v[0]);
-                        }
+                        float v0 = g.es == 8
+                            ? transform_pair<8>(st + src, pstride, row_bytes, cbase + crel, o1, o2, o3, bp, bn)
+                            : transform_pair<4>(st + src, pstride, row_bytes, cbase + crel, o1, o2, o3, bp, bn);
+                        if (first && rank == 0 && bc0 == 0 && cc0 == 0) nan0 = isnan(v0);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty0 + 8 * s);
@@ -396,7 +463,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                 const uint32_t m_sl = fdiv_magic(g.seglen);
                 for (int l = tid; l < g.nlocal; l += F_CONSUMERS) {
                     uint32_t sg = fdiv(l, m_sl), w = l - sg * g.seglen;
-                    float c = C[l + g.PAD * (sg >> 1)];
+                    float c = C[l + F_PAD * (sg >> 1)];
                     if (fabsf(c) == M) {
                         uint32_t f = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z + w;
                         u64 cand = ((u64)f << 1) | (u64)(__float_as_uint(c) >> 31);
@@ -455,31 +522,26 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
 
             // ---------------- phase C1: per-segment count and last kept ----------------
             const int gpar = R > 1 ? (int)(xph2 & 1) : 0;
-            int* const my_cnt  = g_cnt + gpar * F_MAXG;
-            int* const my_last = g_last + gpar * F_MAXG;
+            uint32_t* const my_pk = g_pk + gpar * F_MAXG;
             for (int sg = warp; sg < g.nseg; sg += F_CWARPS) {
-                const float* cs = C + sg * g.seglen + g.PAD * (sg >> 1);
-                int cnt = 0, last = -1;
-                for (int w0 = 0; w0 < g.seglen; w0 += 32) {
-                    int w = w0 + lane;
-                    bool kf = w < g.seglen && keep_coef(cs[w], tf);
-                    uint32_t bal = __ballot_sync(0xffffffffu, kf);
-                    cnt += __popc(bal);
-                    if (bal) last = w0 + 31 - __clz(bal);
+                const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);   // 16-byte aligned
+                int cnt = 0, lb = 0;
+                uint32_t lm = 0;
+                for (int w = lane * 4; w < g.seglen; w += 128) {           // seglen % 4 == 0
+                    const float4 c = *reinterpret_cast<const float4*>(cs + w);
+                    uint32_t m = (keep_coef(c.x, tf) ? 1u : 0u) | (keep_coef(c.y, tf) ? 2u : 0u) |
+                                 (keep_coef(c.z, tf) ? 4u : 0u) | (keep_coef(c.w, tf) ? 8u : 0u);
+                    cnt += __popc(m);
+                    if (m) { lb = w; lm = m; }
                 }
-                if (lane == 0) {
-                    int fstart = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z;
-                    int lastf  = last >= 0 ? fstart + last : -1;
-                    if (R == 1) {
-                        my_cnt[sg]  = cnt;
-                        my_last[sg] = lastf;
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            st_cluster_u32(mapa(smem_u32(&my_cnt[sg * R + rank]), r), (uint32_t)cnt);
-                            st_cluster_u32(mapa(smem_u32(&my_last[sg * R + rank]), r), (uint32_t)lastf);
-                        }
-                    }
+                int last = lm ? lb + 31 - __clz(lm) : -1;
+                cnt  = __reduce_add_sync(0xffffffffu, cnt);
+                last = __reduce_max_sync(0xffffffffu, last);
+                const uint32_t pk = ((uint32_t)cnt << 16) | ((uint32_t)last & 0xffffu);
+                if (R == 1) {
+                    if (lane == 0) my_pk[sg] = pk;
+                } else if (lane < R) {
+                    st_cluster_u32(mapa(smem_u32(&my_pk[sg * R + rank]), lane), pk);
                 }
             }
             if (R > 1) {
@@ -495,10 +557,20 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
             // ---------------- scan over the segments in global order ----------------
             {
                 const int NG = g.nseg * R;   // <= 1024, entry e = sg * R + r
-                const int e0 = tid * 2;
-                int c0 = e0 < NG ? my_cnt[e0] : 0, c1 = e0 + 1 < NG ? my_cnt[e0 + 1] : 0;
-                int l0 = e0 < NG ? my_last[e0] : -1, l1 = e0 + 1 < NG ? my_last[e0 + 1] : -1;
-                int isum = c0 + c1, imax = max(l0, l1);
+                int cv[2], lv[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int e = tid * 2 + j;
+                    cv[j] = 0; lv[j] = -1;
+                    if (e < NG) {
+                        const uint32_t pk = my_pk[e];
+                        const int sg = e / R, r = e % R;
+                        cv[j] = (int)(pk >> 16);
+                        if ((pk & 0xffffu) != 0xffffu)
+                            lv[j] = ((sg >> 1) * g.Y + (sg & 1) * g.hy + r * g.nb) * g.Z + (int)(pk & 0xffffu);
+                    }
+                }
+                int isum = cv[0] + cv[1], imax = max(lv[0], lv[1]);
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     int ps = __shfl_up_sync(0xffffffffu, isum, o);
@@ -520,11 +592,11 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                 if (lane == 0) { es = 0; em = -1; }
                 es += wsum;
                 em = max(em, wmax);
-                // entry e0: exclusive = (es, em); entry e0+1: (es + c0, max(em, l0))
+                const int e0 = tid * 2;
                 if (e0 < NG && (R == 1 || (e0 % R) == (int)rank)) { s_base[e0 / R] = es; s_prev[e0 / R] = em; }
                 if (e0 + 1 < NG && (R == 1 || ((e0 + 1) % R) == (int)rank)) {
-                    s_base[(e0 + 1) / R] = es + c0;
-                    s_prev[(e0 + 1) / R] = max(em, l0);
+                    s_base[(e0 + 1) / R] = es + cv[0];
+                    s_prev[(e0 + 1) / R] = max(em, lv[0]);
                 }
                 if (tid == 0 && rank == 0) states[uid].npairs = total;
                 consumer_bar();
@@ -532,23 +604,31 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
 
             // ---------------- phase C2: emit (run, value) pairs ----------------
             for (int sg = warp; sg < g.nseg; sg += F_CWARPS) {
-                const float* cs = C + sg * g.seglen + g.PAD * (sg >> 1);
+                const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);
                 const int fstart = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z;
                 int pos = s_base[sg], prev = s_prev[sg];
-                int2* out = reinterpret_cast<int2*>(u.out);
-                for (int w0 = 0; w0 < g.seglen; w0 += 32) {
-                    int w = w0 + lane;
-                    float c = w < g.seglen ? cs[w] : 0.f;
-                    bool kf = w < g.seglen && keep_coef(c, tf);
-                    uint32_t bal = __ballot_sync(0xffffffffu, kf);
-                    if (kf) {
-                        uint32_t lower = bal & lt;
-                        int pf = lower ? fstart + w0 + 31 - __clz(lower) : prev;
-                        out[pos + __popc(lower)] = make_int2(fstart + w - pf - 1, __float_as_int(c));
+                int2* const out = reinterpret_cast<int2*>(u.out);
+                for (int w0 = 0; w0 < g.seglen; w0 += 128) {
+                    float    c[4];
+                    uint32_t bal[4];
+                    bool     kf[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int w = w0 + 32 * j + lane;
+                        const bool ok = w < g.seglen;
+                        c[j]   = ok ? cs[w] : 0.f;
+                        kf[j]  = ok && keep_coef(c[j], tf);
+                        bal[j] = __ballot_sync(0xffffffffu, kf[j]);
                     }
-                    if (bal) {
-                        pos += __popc(bal);
-                        prev = fstart + w0 + 31 - __clz(bal);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (bal[j] == 0u) continue;                      // warp-uniform
+                        const int f0 = fstart + w0 + 32 * j;
+                        const uint32_t lower = bal[j] & lt;
+                        const int pf = lower ? f0 + 31 - __clz(lower) : prev;
+                        st_pair_pred(kf[j], out + pos + __popc(lower), f0 + lane - pf - 1, c[j]);
+                        pos += __popc(bal[j]);
+                        prev = f0 + 31 - __clz(bal[j]);
                     }
                 }
             }
