@@ -289,6 +289,16 @@ int wc_kernel_stats(wc_ctx* ctx, int index, const char** name, double* total_ms,
     return WC_OK;
 }
 
+// Undeclared debug hook (not part of include/wcgpu.h): per-phase SM cycles of the fused compress
+// kernel summed over CTAs since the last reset: A, B, C1, scan, C2, units.
+__attribute__((visibility("default"))) int wc_debug_phase_cycles(wc_ctx* ctx, unsigned long long* out6, int reset) {
+    if (!ctx || !out6) return WC_ERR_INVALID_ARG;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CTX_CUDA(ctx, debug_phase_cycles(out6, reset != 0));
+    return WC_OK;
+}
+
 int wc_reset_counters(wc_ctx* ctx) {
     if (!ctx) return WC_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);

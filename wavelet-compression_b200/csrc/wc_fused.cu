@@ -14,6 +14,8 @@
 //   src/compressor.cpp:212-216; (C1) per-segment count / last-kept; (C2) ballot-ranked emission of
 //   (run, value) pairs straight to the unit's slot in HBM.
 //   HBM traffic per unit = 8N (or 4N) in + 8K out: the algorithmic minimum of SURVEY.md §8d.
+#include <cstdio>
+
 #include "wc_common.cuh"
 #include "wc_fused.h"
 
@@ -148,6 +150,11 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// Hint: pull [src, src+bytes) into L2 (no destination).  Used one unit ahead of the TMA ring so the
+// ring refills at L2 latency instead of HBM latency.
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_volatile_shared_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -196,6 +203,13 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t q, uint32_t m) { return m ? __
 __device__ __forceinline__ uint32_t fdiv_magic(uint32_t d) { return d <= 1 ? 0u : (0xffffffffu / d) + 1u; }
 
 // ---- the kernel -----------------------------------------------------------------------------------
+// Per-CTA phase cycle counters (clock64 by consumer thread 0 at the phase boundaries): a built-in
+// light-weight profile, read back with wc_debug_phase_cycles().  [cta][phase], phases: 0 = A (transform,
+// includes waiting for TMA data), 1 = B (threshold), 2 = C1 (count), 3 = scan (+ cluster exchange),
+// 4 = C2 (emit), 5 = units processed.
+__device__ unsigned long long g_phase_cycles[1024][6];
+__device__ unsigned long long g_a_cycles[1024][4];   // debug: gen spin, full wait, transform, chunks
+
 __device__ __forceinline__ void st_pair_pred(bool p, int2* addr, int run, float val) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
@@ -308,6 +322,23 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
             const int   b0  = rank * g.nb;
             const size_t row_bytes   = (size_t)g.X * g.es;
             const size_t plane_bytes = row_bytes * g.Y;
+            // L2 prefetch of this CTA's whole slab of the NEXT unit: one contiguous piece per z-plane
+            if (ui + (int)ncl < n_list) {
+                const UnitDev un = units[unit_list[ui + ncl]];
+                FGeom gn;
+                fused_geom(un.nx, un.ny, un.nz, un.dtype, R, gn);
+                const size_t rb = (size_t)gn.X * gn.es, pb = rb * gn.Y;
+                const char* base = static_cast<const char*>(un.in) + (size_t)(2 * rank * gn.nb) * rb;
+                const uint32_t slab_bytes = (uint32_t)(2 * gn.nb * rb);
+                if (R == 1) {
+                    // the slab is the whole box: contiguous, prefetch in 16 KB pieces
+                    const size_t total = pb * gn.Z;
+                    for (size_t off = (size_t)lane * 16384; off < total; off += 32 * 16384)
+                        l2_prefetch(base + off, (uint32_t)min((size_t)16384, total - off));
+                } else {
+                    for (int z = lane; z < gn.Z; z += 32) l2_prefetch(base + (size_t)z * pb, slab_bytes);
+                }
+            }
             for (int icb = 0; icb < g.ncb; ++icb) {
                 const int bc0 = icb * g.CB;
                 const int cbc = min(g.CB, g.nb - bc0);
@@ -348,6 +379,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
             const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
             float bp = 0.f, bn = 0.f;             // running max of +c and of -c
             bool  nan0 = false;
+            long long t0 = clock64();
 
             // ---------------- phase A: transform the staged rows into C ----------------
             int c_czc = -1, c_cbc = -1, c_npairs = 0;     // cached decomposition of pair index `tig`
@@ -381,8 +413,11 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                     // not landed yet" from "this use has landed".  The producer therefore publishes the chunk
                     // number it is filling stage s with (after the stage was released), and the group waits
                     // for that first.
+                    long long ta = clock64();
                     while (ld_volatile_shared_u32(gen0 + 4 * s) != kg) { }
+                    long long tb = clock64();
                     mbar_wait(full0 + 8 * s, (kg / F_NSTAGES) & 1);
+                    long long tc = clock64();
                     const unsigned char* st = smem + SM_STAGE + s * F_STAGE_ALLOC;
                     float* const cbase = C + bc0 * g.Z + cc0;
                     for (int q = tig; q < c_npairs; q += F_GROUP) {
@@ -403,10 +438,16 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty0 + 8 * s);
+                    if (tid == 0 && blockIdx.x < 1024) {
+                        long long td = clock64();
+                        unsigned long long* pa = g_a_cycles[blockIdx.x];
+                        pa[0] += tb - ta; pa[1] += tc - tb; pa[2] += td - tc; pa[3] += 1;
+                    }
                 }
             }
 
             // ---------------- phase B: the threshold ----------------
+            long long t1 = clock64();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
@@ -521,6 +562,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
             }
 
             // ---------------- phase C1: per-segment count and last kept ----------------
+            long long t2 = clock64();
             const int gpar = R > 1 ? (int)(xph2 & 1) : 0;
             uint32_t* const my_pk = g_pk + gpar * F_MAXG;
             for (int sg = warp; sg < g.nseg; sg += F_CWARPS) {
@@ -544,6 +586,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                     st_cluster_u32(mapa(smem_u32(&my_pk[sg * R + rank]), lane), pk);
                 }
             }
+            long long t3 = clock64();
             if (R > 1) {
                 fence_cluster();
                 consumer_bar();
@@ -603,11 +646,21 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
             }
 
             // ---------------- phase C2: emit (run, value) pairs ----------------
+            long long t4 = clock64();
             for (int sg = warp; sg < g.nseg; sg += F_CWARPS) {
+                const int scnt = (int)(my_pk[sg * R + rank] >> 16);
+                if (scnt == 0) continue;                                   // nothing kept in this segment
                 const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);
                 const int fstart = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z;
-                int pos = s_base[sg], prev = s_prev[sg];
+                uint32_t pos = (uint32_t)s_base[sg];
+                int prev = s_prev[sg];
                 int2* const out = reinterpret_cast<int2*>(u.out);
+                if (scnt == g.seglen) {
+                    // every coefficient kept (e.g. a negative max, SURVEY.md D3'): runs are 0, ranks are w
+                    for (int w = lane; w < g.seglen; w += 32)
+                        out[pos + (uint32_t)w] = make_int2(w == 0 ? fstart - prev - 1 : 0, __float_as_int(cs[w]));
+                    continue;
+                }
                 for (int w0 = 0; w0 < g.seglen; w0 += 128) {
                     float    c[4];
                     uint32_t bal[4];
@@ -626,13 +679,18 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                         const int f0 = fstart + w0 + 32 * j;
                         const uint32_t lower = bal[j] & lt;
                         const int pf = lower ? f0 + 31 - __clz(lower) : prev;
-                        st_pair_pred(kf[j], out + pos + __popc(lower), f0 + lane - pf - 1, c[j]);
+                        st_pair_pred(kf[j], out + (pos + __popc(lower)), f0 + lane - pf - 1, c[j]);
                         pos += __popc(bal[j]);
                         prev = f0 + 31 - __clz(bal[j]);
                     }
                 }
             }
             consumer_bar();   // C and the segment arrays are rewritten by the next unit
+            if (tid == 0 && blockIdx.x < 1024) {
+                long long t5 = clock64();
+                unsigned long long* pc = g_phase_cycles[blockIdx.x];
+                pc[0] += t1 - t0; pc[1] += t2 - t1; pc[2] += t3 - t2; pc[3] += t4 - t3; pc[4] += t5 - t4; pc[5] += 1;
+            }
         }
     }
     if (R > 1) cluster_sync_all();   // no CTA may exit while peers can still write into its smem
@@ -690,6 +748,31 @@ cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, U
     if (cluster == 8)
         return launch_fc<8>(mode, units, states, unit_list, n_list, one_minus_keep, global_key, sm_count, st, ls);
     return cudaErrorInvalidValue;
+}
+
+// debug: sums over CTAs of the phase cycle counters; reset = zero them afterwards
+cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset) {
+    static unsigned long long h[1024][6];
+    cudaError_t e = cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h));
+    if (e != cudaSuccess) return e;
+    for (int p = 0; p < 6; ++p) out[p] = 0;
+    for (int c = 0; c < 1024; ++c)
+        for (int p = 0; p < 6; ++p) out[p] += h[c][p];
+    {
+        static unsigned long long ha[1024][4];
+        cudaMemcpyFromSymbol(ha, g_a_cycles, sizeof(ha));
+        unsigned long long t[4] = {0, 0, 0, 0};
+        for (int c = 0; c < 1024; ++c) for (int p = 0; p < 4; ++p) t[p] += ha[c][p];
+        if (t[3]) fprintf(stderr, "[phaseA warp0] per chunk: gen spin %.0f, full wait %.0f, transform %.0f cycles (%llu chunks)\n",
+                          (double)t[0] / t[3], (double)t[1] / t[3], (double)t[2] / t[3], t[3]);
+        static unsigned long long za[1024][4];
+        if (reset) cudaMemcpyToSymbol(g_a_cycles, za, sizeof(za));
+    }
+    if (reset) {
+        static unsigned long long z[1024][6];
+        e = cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+    }
+    return e;
 }
 
 cudaError_t launch_fused_decompress(int, const DecUnitDev*, const InvUnitDev*, const int*, int, int*,

@@ -24,4 +24,6 @@ cudaError_t launch_fused_decompress(int cluster, const DecUnitDev* dec, const In
                                     const int* unit_list, int n_list, int* err, int sm_count,
                                     cudaStream_t st, LaunchStats* ls);
 
+cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset);
+
 } // namespace wc
