@@ -111,16 +111,16 @@ struct wc_plan {
     int     in_space = WC_DEVICE;
     std::vector<wc_box_desc> units;
     std::vector<UnitDev>     h_units;
-    std::vector<int>         fused1, fused8, generic; // unit ids per path
+    std::vector<int>         fused1, fused2, fused8, generic; // unit ids per path
     long long total_n = 0;     // sum of ncoef
     size_t    in_bytes = 0;    // sum of input bytes
     // device memory
     DevBuf d_units, d_states, d_in, d_out, d_coef, d_xtiles, d_ctiles, d_tile_i, d_gkey,
-        d_offsets, d_dense, d_f1, d_f8, d_dec_units, d_inv_units, d_inv_tiles, d_ptiles, d_psum,
+        d_offsets, d_dense, d_f1, d_f2, d_f8, d_dec_units, d_inv_units, d_inv_tiles, d_ptiles, d_psum,
         d_err, d_rmse_units, d_rmse_sum, d_rmse, d_stage_out;
     PinBuf h_states, h_dense, h_misc;
     int    n_xtiles = 0, n_ctiles = 0;
-    int    n_f1 = 0, n_f8 = 0;
+    int    n_f1 = 0, n_f2 = 0, n_f8 = 0;
     bool   compressed = false;
     bool   transformed = false;
     std::vector<size_t> in_dev_off; // per unit offset in d_in (host inputs)
@@ -424,6 +424,7 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
         }
         if (n == 0) cls = -1; // nothing to do: K = 0
         if (cls == 1) p->fused1.push_back(i);
+        else if (cls == 2) p->fused2.push_back(i);
         else if (cls == 8) p->fused8.push_back(i);
         else if (cls == 0) {
             p->generic.push_back(i);
@@ -481,6 +482,13 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
     // fused work lists
     p->n_f1 = (int)p->fused1.size();
     p->n_f8 = (int)p->fused8.size();
+    p->n_f2 = (int)p->fused2.size();
+    if (p->n_f2) {
+        PLAN_RESERVE(p->d_f2, sizeof(int) * p->n_f2);
+        if ((e = cudaMemcpyAsync(p->d_f2.p, p->fused2.data(), sizeof(int) * p->n_f2,
+                                 cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+            return fail(e, "fused2 upload");
+    }
     if (p->n_f1) {
         PLAN_RESERVE(p->d_f1, sizeof(int) * p->n_f1);
         if ((e = cudaMemcpyAsync(p->d_f1.p, p->fused1.data(), sizeof(int) * p->n_f1,
@@ -506,7 +514,7 @@ int wc_plan_destroy(wc_plan* p) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &p->d_units, &p->d_states, &p->d_in, &p->d_out, &p->d_coef, &p->d_xtiles,
                        &p->d_ctiles, &p->d_tile_i, &p->d_gkey, &p->d_offsets, &p->d_dense, &p->d_f1,
-                       &p->d_f8, &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
+                       &p->d_f2, &p->d_f8, &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
                        &p->d_psum, &p->d_err, &p->d_rmse_units, &p->d_rmse_sum, &p->d_rmse,
                        &p->d_stage_out };
     for (DevBuf* b : bufs) b->release();
@@ -577,6 +585,11 @@ static int plan_forward(wc_plan* p, bool global_mode) {
                                                 p->d_states.as<UnitState>(), p->d_f1.as<int>(),
                                                 p->n_f1, 0.0, nullptr, ctx->sm_count, ctx->stream,
                                                 &ctx->ls));
+        if (p->n_f2)
+            CTX_CUDA(ctx, launch_fused_compress(2, FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
+                                                p->d_states.as<UnitState>(), p->d_f2.as<int>(),
+                                                p->n_f2, 0.0, nullptr, ctx->sm_count, ctx->stream,
+                                                &ctx->ls));
         if (p->n_f8)
             CTX_CUDA(ctx, launch_fused_compress(8, FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
                                                 p->d_states.as<UnitState>(), p->d_f8.as<int>(),
@@ -607,6 +620,11 @@ static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
     if (p->n_f1)
         CTX_CUDA(ctx, launch_fused_compress(1, mode, p->d_units.as<UnitDev>(),
                                             p->d_states.as<UnitState>(), p->d_f1.as<int>(), p->n_f1,
+                                            omk, global_key_dev, ctx->sm_count, ctx->stream,
+                                            &ctx->ls));
+    if (p->n_f2)
+        CTX_CUDA(ctx, launch_fused_compress(2, mode, p->d_units.as<UnitDev>(),
+                                            p->d_states.as<UnitState>(), p->d_f2.as<int>(), p->n_f2,
                                             omk, global_key_dev, ctx->sm_count, ctx->stream,
                                             &ctx->ls));
     if (p->n_f8)
@@ -774,7 +792,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             for (int t = 0; t < du[i].nptiles; ++t) ptiles.push_back(make_int2(i, t));
             int nt = xtile_count(jobs[i].nx, jobs[i].ny, jobs[i].nz);
             for (int t = 0; t < nt; ++t) xtiles.push_back(make_int2(i, t));
-        } else if (cls == 1) f1.push_back(i);
+        } else if (cls == 1 || cls == 2) f1.push_back(i);
         else if (cls == 8) f8.push_back(i);
     }
     CTX_CUDA(ctx, d_coef.reserve(sizeof(float) * std::max<size_t>(coef_floats, 4)));
