@@ -33,6 +33,10 @@ def build(ref: bool | None = None) -> None:
     if ref and have_ref:
         subprocess.check_call(
             ["make", "-s", "-C", HERE, "ref", "REF=" + os.environ.get("WC_REF", "/root/reference")])
+        # the drop-in test links libwcgpu.so: only once the product library has been built
+        if os.path.exists(os.path.join(HERE, "..", "wavelet-compression_b200", "libwcgpu.so")):
+            subprocess.check_call(
+                ["make", "-s", "-C", HERE, "dropin", "REF=" + os.environ.get("WC_REF", "/root/reference")])
 
 
 def _c(a, dt):

@@ -214,3 +214,15 @@ def test_error_codes(wc, ctx):
     with pytest.raises(wc.WcError) as e:
         ctx.decompress_batch([neg])
     assert e.value.status == 7
+
+
+def test_cpp_dropin_runs_the_reference_doctests_on_the_gpu():
+    """oracle/_ref/dropin_test = wavelet-compression_b200/host/dropin_test.cpp compiled against the
+    REFERENCE's own grid.h / box-structs.h (types + signatures of src/compressor.h, decompressor.h,
+    calc-loss.h), linked to libwcgpu.so: the reference's doctest cases + a batched run."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "dropin_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_test not built (needs /root/reference headers at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "dropin ok" in r.stdout, r.stdout + r.stderr

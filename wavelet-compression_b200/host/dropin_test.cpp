@@ -1,0 +1,123 @@
+// Drop-in evidence: the reference's own doctest cases for this path (src/compressor.cpp:369-406,
+// src/calc-loss.cpp:68-86), re-expressed against namespace wcgpu, compiled with the REFERENCE's
+// own headers (grid.h / box-structs.h from $(REF)/src — see oracle/Makefile target `dropin`), so the
+// types and signatures are the reference's, and every number comes from the GPU through the C ABI.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <filesystem>
+#include <string>
+#include <unistd.h>
+
+#include "box-structs.h"   // the reference's: Grid3D, Box3D, multiBox3D, CompressedWavelet
+
+#include "wc_dropin.hpp"
+
+static int g_fail = 0;
+#define REQUIRE(x)                                                                  \
+    do {                                                                            \
+        if (!(x)) {                                                                 \
+            ++g_fail;                                                               \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #x);     \
+        }                                                                           \
+    } while (0)
+
+static std::string scratch_dir() {
+    std::string t = (std::filesystem::temp_directory_path() / "wcgpu_dropin.XXXXXX").string();
+    if (!mkdtemp(t.data())) { std::perror("mkdtemp"); std::exit(2); }
+    return t;
+}
+
+int main() {
+    using namespace wcgpu;
+
+    {   // "Wavelet decomposition" (src/compressor.cpp:369-384)
+        Box3D test(4, 8, 16, 5.0f);
+        test.set(1, 2, 3, 8.5f);
+        test.set(2, 5, 6, 5.44f);
+        test.set(1, 1, 1, 3.3999932f);
+        test.set(2, 2, 2, 3.19229f);
+        test.set(3, 5, 12, 199.39029f);
+        std::vector<float> wavelet = wavelet_decompose(test);
+        Box3D result = inverse_wavelet_decompose(wavelet, 4, 8, 16);
+        REQUIRE(test.equals(result, 1e-6));
+        REQUIRE(wavelet.size() == 512);
+        REQUIRE(wavelet[0] == 4.79999924f);   // SURVEY.md §8c known answer
+    }
+    {   // "File writing/compression" (src/compressor.cpp:387-406)
+        Box3D box(4, 8, 16, 5.0f);
+        multiBox3D test;
+        test.push_back(std::move(box));
+        std::vector<int> components = { 0 };
+        std::string dir = scratch_dir();
+        auto cw = compress(test, components, 0.999, 0, 0, 0, dir);
+        REQUIRE(cw.size() == 1);
+        REQUIRE(cw[0].rle_encoded.size() == 64);
+        Box3D result = decompress(dir + "/compressed-wavelet-0-0-0-0.xz", 0, 0, 0, 0);
+        REQUIRE(test[0].equals(result, 0));
+        std::filesystem::remove_all(dir);
+    }
+    {   // "Calc RMSE" (src/calc-loss.cpp:68-86)
+        Box3D b1(2, 2, 2, 0.0f), b2(2, 2, 2, 3.5f);
+        multiBox3D t1, t2;
+        t1.push_back(b1.clone()); t2.push_back(b2.clone());
+        t1.push_back(b1.clone()); t2.push_back(b2.clone());
+        std::vector<double> rmses = calc_rmse_per_box(t1, t2, 2);
+        std::vector<double> truth = { 3.5, 3.5 };
+        REQUIRE(rmses == truth);
+    }
+    {   // batched run: same files as the per-box calls, and a lossless-enough round trip
+        const int T = 2, L = 2, NB = 3, NC = 2;
+        std::vector<int> comp_idxs = { 0, 3 };
+        std::vector<std::vector<std::vector<multiBox3D>>> boxes(T);
+        std::vector<std::vector<int>> counts(T, std::vector<int>(L, NB));
+        for (int t = 0; t < T; ++t) {
+            boxes[t].resize(L);
+            for (int l = 0; l < L; ++l)
+                for (int b = 0; b < NB; ++b) {
+                    multiBox3D mb;
+                    for (int c = 0; c < NC; ++c) {
+                        int X = l ? 32 : 16, Y = l ? 32 : 8, Z = l ? 32 : 12;
+                        Box3D bx(X, Y, Z);
+                        for (int k = 0; k < Z; ++k)
+                            for (int j = 0; j < Y; ++j)
+                                for (int i = 0; i < X; ++i)
+                                    bx(i, j, k) = (c ? 0.f : 300.f) + 50.f * std::sin(0.1f * i + t) * std::cos(0.07f * j + b) *
+                                                                      std::sin(0.05f * k + l);
+                        mb.push_back(std::move(bx));
+                    }
+                    boxes[t][l].push_back(std::move(mb));
+                }
+        }
+        std::string d1 = scratch_dir(), d2 = scratch_dir();
+        double keep = (double)0.9999f;
+        compress_all(boxes, comp_idxs, keep, d1, 4);
+        for (int t = 0; t < T; ++t)
+            for (int l = 0; l < L; ++l)
+                for (int b = 0; b < NB; ++b) compress(boxes[t][l][b], comp_idxs, keep, t, l, b, d2);
+        size_t nfiles = 0;
+        for (auto& e : std::filesystem::directory_iterator(d1)) {
+            std::string name = e.path().filename().string();
+            std::ifstream fa(e.path(), std::ios::binary), fb(std::filesystem::path(d2) / name, std::ios::binary);
+            std::string a((std::istreambuf_iterator<char>(fa)), {}), bb((std::istreambuf_iterator<char>(fb)), {});
+            REQUIRE(!a.empty() && a == bb);
+            ++nfiles;
+        }
+        REQUIRE(nfiles == (size_t)T * L * NB * NC);
+        auto regen = decompress_all(d1 + "/", counts, comp_idxs, 4);
+        for (int t = 0; t < T; ++t)
+            for (int l = 0; l < L; ++l)
+                for (int b = 0; b < NB; ++b) {
+                    std::vector<double> r = calc_rmse_per_box(boxes[t][l][b], regen[t][l][b], NC);
+                    for (int c = 0; c < NC; ++c) {
+                        Box3D one = decompress(detail::unit_path(d1, t, l, comp_idxs[c], b), t, l, comp_idxs[c], b);
+                        REQUIRE(one.equals(regen[t][l][b][c], 0));
+                        REQUIRE(r[c] < 0.05);
+                    }
+                }
+        std::filesystem::remove_all(d1);
+        std::filesystem::remove_all(d2);
+    }
+    std::printf(g_fail ? "dropin FAILED (%d)\n" : "dropin ok\n", g_fail);
+    return g_fail ? 1 : 0;
+}

@@ -1,0 +1,322 @@
+// wc_dropin.hpp — C++ drop-in for the reference's three hot-path entry points, on top of the C ABI.
+//
+// Include it AFTER the reference's own "box-structs.h" (Grid3D / Box3D / multiBox3D /
+// CompressedWavelet, src/grid.h + src/box-structs.h) and link libwcgpu.so + liblzma: the functions in
+// namespace wcgpu have exactly the signatures src/modes.cpp calls,
+//
+//   compress(multiBox3D&, std::vector<int>, double, int, int, int, std::string)   src/compressor.h:9-15
+//   decompress(std::string, int, int, int, int) -> Box3D                          src/decompressor.h:6-10
+//   calc_rmse_per_box(const multiBox3D&, const multiBox3D&, int)                  src/calc-loss.h:6-8
+//   inverse_wavelet_decompose(std::vector<float>, int, int, int) -> Box3D          src/decompressor.h:18
+//   deserialize_compressed_wavelet(const std::string&)                              src/decompressor.h:14
+//
+// so a host re-points its loops with `using namespace wcgpu;` or by swapping the two includes
+// (INTEGRATION.md).  What stays on the host is what the reference keeps on the host: the 20-byte
+// header, the .xz container (xz preset 6, CRC64, one lzma_code(FINISH)) and the file names.  Errors
+// keep the reference's behaviour: a message and exit(EXIT_FAILURE) (src/compressor.cpp:263-266,
+// src/decompressor.cpp:170-231) — the C ABI underneath never exits by itself.
+//
+// Beyond the per-box calls there are batched entry points (compress_all / decompress_all) that hand a
+// whole run to the GPU in one wc_compress_batch and spread the LZMA stage over host threads — the
+// per-box calls are correct but launch-bound, the batch calls are what a ported modes.cpp should use.
+#pragma once
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "../../include/wcgpu.h"
+#include "wc_lzma_abi.h"
+
+namespace wcgpu {
+
+namespace detail {
+
+[[noreturn]] inline void die(const std::string& what) {
+    std::fprintf(stderr, "[wcgpu] %s\n", what.c_str());
+    std::exit(EXIT_FAILURE);
+}
+
+inline void check(int status, wc_ctx* ctx, const char* what) {
+    if (status != WC_OK)
+        die(std::string(what) + ": " + wc_strerror(status) + (ctx ? std::string(" — ") + wc_last_error(ctx) : ""));
+}
+
+// one context per process and device, created on first use
+inline wc_ctx* context(int device = 0) {
+    static wc_ctx* ctx = nullptr;
+    if (!ctx) check(wc_create(&ctx, device), nullptr, "wc_create");
+    return ctx;
+}
+
+template <class Box>
+inline const float* box_data(const Box& b) {
+    return b.data_size() ? &b(0, 0, 0) : nullptr;   // Grid3D storage is one contiguous x-fastest vector
+}
+
+// serialize_compressed_wavelet, src/compressor.cpp:55-80: header from the C ABI + the pairs as they are
+inline std::string serialize(const wc_packed& p) {
+    std::string buf(20 + 8 * (size_t)p.npairs, '\0');
+    wc_serialize_header(&p, reinterpret_cast<uint8_t*>(&buf[0]));
+    if (p.npairs) std::memcpy(&buf[20], p.pairs, 8 * (size_t)p.npairs);
+    return buf;
+}
+
+// lzma_easy_encoder(6, CRC64) + one lzma_code(FINISH), src/compressor.cpp:260-285
+inline std::vector<uint8_t> xz_encode(const std::string& serialized) {
+    lzma_stream strm = LZMA_STREAM_INIT;
+    if (lzma_easy_encoder(&strm, 6, LZMA_CHECK_CRC64) != LZMA_OK) die("Failed to initialize LZMA encoder");
+    std::vector<uint8_t> out((size_t)(serialized.size() * 1.1) + 128);
+    strm.next_in   = reinterpret_cast<const uint8_t*>(serialized.data());
+    strm.avail_in  = serialized.size();
+    strm.next_out  = out.data();
+    strm.avail_out = out.size();
+    if (lzma_code(&strm, LZMA_FINISH) != LZMA_STREAM_END) die("LZMA compression failed");
+    out.resize(out.size() - strm.avail_out);
+    lzma_end(&strm);
+    return out;
+}
+
+// lzma_stream_decoder(LZMA_CONCATENATED) with a doubling buffer, src/decompressor.cpp:188-220
+inline std::string xz_decode_file(const std::string& filename) {
+    std::error_code ec;
+    auto size = std::filesystem::file_size(filename, ec);
+    if (ec) die("Error getting file size: " + ec.message() + " " + filename);
+    std::ifstream file(filename, std::ios::binary);
+    if (!file) die("Failed to open file: " + filename);
+    std::vector<uint8_t> in(size);
+    if (size && !file.read(reinterpret_cast<char*>(in.data()), (std::streamsize)size)) die("Failed to read file: " + filename);
+    lzma_stream strm = LZMA_STREAM_INIT;
+    if (lzma_stream_decoder(&strm, UINT64_MAX, LZMA_CONCATENATED) != LZMA_OK) die("Failed to initialize LZMA decoder.");
+    strm.next_in  = in.data();
+    strm.avail_in = in.size();
+    std::vector<uint8_t> out(4096);
+    strm.next_out  = out.data();
+    strm.avail_out = out.size();
+    for (;;) {
+        lzma_ret ret = lzma_code(&strm, LZMA_FINISH);
+        if (ret == LZMA_STREAM_END) break;
+        if (ret != LZMA_OK) die("LZMA decompression failed with code: " + std::to_string((int)ret));
+        size_t old = out.size();
+        out.resize(old * 2);
+        strm.next_out  = out.data() + old;
+        strm.avail_out = old;
+    }
+    size_t n = out.size() - strm.avail_out;
+    lzma_end(&strm);
+    return std::string(reinterpret_cast<char*>(out.data()), n);
+}
+
+inline std::string unit_path(const std::string& dir, int t, int lev, int comp, int box) {
+    return (std::filesystem::path(dir) / ("compressed-wavelet-" + std::to_string(t) + "-" + std::to_string(lev) + "-" +
+                                           std::to_string(comp) + "-" + std::to_string(box) + ".xz")).string();
+}
+
+inline void write_unit_file(const std::string& path, const wc_packed& p) {
+    std::ofstream file(path, std::ios::binary);
+    if (!file.is_open()) return;   // the reference silently skips a file it cannot open (src/compressor.cpp:256-257)
+    std::vector<uint8_t> xz = xz_encode(serialize(p));
+    file.write(reinterpret_cast<const char*>(xz.data()), (std::streamsize)xz.size());
+}
+
+inline CompressedWavelet to_compressed_wavelet(const wc_packed& p) {
+    CompressedWavelet cw;
+    cw.shape       = { p.shape[0], p.shape[1], p.shape[2] };
+    cw.coeff_shape = { p.ncoef };
+    cw.rle_encoded.resize((size_t)p.npairs);
+    bool need32 = false;
+    for (int i = 0; i < p.npairs; ++i) {
+        cw.rle_encoded[i] = { p.pairs[i].run, p.pairs[i].val };
+        double a = p.pairs[i].val < 0 ? -(double)p.pairs[i].val : (double)p.pairs[i].val;
+        if (a > INT16_MAX) need32 = true;   // src/compressor.cpp:229 (computed, never serialized)
+    }
+    cw.need32 = need32;
+    return cw;
+}
+
+template <class F>
+inline void parallel_for(size_t n, unsigned threads, F f) {
+    if (threads <= 1 || n <= 1) {
+        for (size_t i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::atomic<size_t> next { 0 };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; ++t)
+        pool.emplace_back([&] {
+            for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i);
+        });
+    for (auto& th : pool) th.join();
+}
+
+} // namespace detail
+
+// ---- compress(): src/compressor.cpp:192-297 ----------------------------------------------------------
+inline std::vector<CompressedWavelet> compress(multiBox3D& box, std::vector<int> components, double keep,
+                                               int time, int level, int box_index, std::string compressed_dir) {
+    wc_ctx* ctx = detail::context();
+    const int n = (int)components.size();
+    std::vector<wc_box_desc> in(n);
+    std::vector<wc_packed>   out(n);
+    for (int c = 0; c < n; ++c)
+        in[c] = { detail::box_data(box[c]), WC_F32, (int32_t)box[c].width(), (int32_t)box[c].height(), (int32_t)box[c].depth() };
+    detail::check(wc_compress_batch(ctx, in.data(), n, WC_HOST, keep, WC_THRESH_PER_UNIT, out.data(), WC_HOST), ctx,
+                  "wc_compress_batch");
+    std::vector<CompressedWavelet> ret;
+    for (int c = 0; c < n; ++c) {
+        detail::write_unit_file(detail::unit_path(compressed_dir, time, level, components[c], box_index), out[c]);
+        ret.push_back(detail::to_compressed_wavelet(out[c]));
+    }
+    return ret;
+}
+
+// ---- deserialize_compressed_wavelet(): src/decompressor.cpp:35-74 (host only) --------------------------
+inline CompressedWavelet deserialize_compressed_wavelet(const std::string& data) {
+    CompressedWavelet cw;
+    int32_t h[5];
+    std::memcpy(h, data.data(), 20);
+    cw.shape       = { h[0], h[1], h[2] };
+    cw.coeff_shape = { h[3] };
+    cw.rle_encoded.resize((size_t)h[4]);
+    for (int i = 0; i < h[4]; ++i) {
+        int   run;
+        float val;
+        std::memcpy(&run, data.data() + 20 + 8 * (size_t)i, 4);
+        std::memcpy(&val, data.data() + 24 + 8 * (size_t)i, 4);
+        cw.rle_encoded[i] = { run, val };
+    }
+    cw.need32 = false;
+    return cw;
+}
+
+// ---- decompress(): src/decompressor.cpp:238-255 -----------------------------------------------------------
+inline Box3D decompress(std::string file_path, int /*time*/, int /*level*/, int /*component*/, int /*box_idx*/) {
+    wc_ctx* ctx = detail::context();
+    std::string raw = detail::xz_decode_file(file_path);
+    if (raw.size() < 20) detail::die("Deserialization failed: short file " + file_path);
+    int32_t h[5];
+    std::memcpy(h, raw.data(), 20);
+    if (raw.size() < 20 + 8 * (size_t)h[4]) detail::die("Deserialization failed: truncated file " + file_path);
+    wc_packed p;
+    p.shape[0] = h[0]; p.shape[1] = h[1]; p.shape[2] = h[2];
+    p.ncoef = h[3]; p.npairs = h[4]; p.reserved = 0;
+    std::vector<wc_pair> pairs((size_t)h[4]);
+    if (h[4]) std::memcpy(pairs.data(), raw.data() + 20, 8 * (size_t)h[4]);
+    p.pairs = pairs.data();
+    Box3D box((size_t)h[0], (size_t)h[1], (size_t)h[2]);
+    wc_box_out o { box.data_size() ? &box(0, 0, 0) : nullptr, WC_F32, h[0], h[1], h[2] };
+    detail::check(wc_decompress_batch(ctx, &p, 1, WC_HOST, &o, WC_HOST), ctx, "wc_decompress_batch");
+    return box;
+}
+
+// ---- inverse_wavelet_decompose(): src/decompressor.cpp:79-159 ---------------------------------------------
+inline Box3D inverse_wavelet_decompose(std::vector<float> flat, int x, int y, int z) {
+    wc_ctx* ctx = detail::context();
+    Box3D box((size_t)x, (size_t)y, (size_t)z);
+    detail::check(wc_haar_inverse(ctx, flat.data(), x, y, z, WC_HOST, box.data_size() ? &box(0, 0, 0) : nullptr), ctx,
+                  "wc_haar_inverse");
+    return box;
+}
+
+// wavelet_decompose is `static` in the reference (src/compressor.cpp:85); exposed here for tests.
+inline std::vector<float> wavelet_decompose(const Box3D& box) {
+    wc_ctx* ctx = detail::context();
+    std::vector<float> flat(box.data_size());
+    wc_box_desc d { detail::box_data(box), WC_F32, (int32_t)box.width(), (int32_t)box.height(), (int32_t)box.depth() };
+    detail::check(wc_haar_forward(ctx, &d, WC_HOST, flat.data()), ctx, "wc_haar_forward");
+    return flat;
+}
+
+// ---- calc_rmse_per_box(): src/calc-loss.cpp:12-43 -----------------------------------------------------------
+inline std::vector<double> calc_rmse_per_box(const multiBox3D& actual, const multiBox3D& pred, int num_components) {
+    wc_ctx* ctx = detail::context();
+    std::vector<wc_box_desc> a(num_components), b(num_components);
+    for (int c = 0; c < num_components; ++c) {
+        a[c] = { detail::box_data(actual[c]), WC_F32, (int32_t)actual[c].width(), (int32_t)actual[c].height(), (int32_t)actual[c].depth() };
+        b[c] = { detail::box_data(pred[c]), WC_F32, (int32_t)pred[c].width(), (int32_t)pred[c].height(), (int32_t)pred[c].depth() };
+    }
+    std::vector<double> rmse(num_components, 0.0);
+    detail::check(wc_rmse_batch(ctx, a.data(), b.data(), num_components, WC_HOST, rmse.data()), ctx, "wc_rmse_batch");
+    return rmse;
+}
+
+inline double calc_adj_loss(double rmse, double range) { return rmse / range; }   // src/calc-loss.cpp:49-51
+
+// ---- batched: the whole (t, level, box) x component iteration of src/modes.cpp:100-103 in one call -----------
+// boxes[t][lev][box] is the reference's AllData::boxes.  One GPU batch, then the .xz files are written by
+// `lzma_threads` host threads (each file is independent; 0 = hardware_concurrency).
+inline void compress_all(std::vector<std::vector<std::vector<multiBox3D>>>& boxes, const std::vector<int>& comp_idxs,
+                         double keep, const std::string& compressed_dir, unsigned lzma_threads = 0) {
+    wc_ctx* ctx = detail::context();
+    struct Key { int t, l, b, c; };
+    std::vector<Key>         keys;
+    std::vector<wc_box_desc> in;
+    for (size_t t = 0; t < boxes.size(); ++t)
+        for (size_t l = 0; l < boxes[t].size(); ++l)
+            for (size_t b = 0; b < boxes[t][l].size(); ++b)
+                for (size_t c = 0; c < comp_idxs.size(); ++c) {
+                    const Box3D& bx = boxes[t][l][b][c];
+                    keys.push_back({ (int)t, (int)l, (int)b, comp_idxs[c] });
+                    in.push_back({ detail::box_data(bx), WC_F32, (int32_t)bx.width(), (int32_t)bx.height(), (int32_t)bx.depth() });
+                }
+    std::vector<wc_packed> out(in.size());
+    detail::check(wc_compress_batch(ctx, in.data(), (int)in.size(), WC_HOST, keep, WC_THRESH_PER_UNIT, out.data(), WC_HOST),
+                  ctx, "wc_compress_batch");
+    unsigned nt = lzma_threads ? lzma_threads : std::thread::hardware_concurrency();
+    detail::parallel_for(out.size(), nt, [&](size_t i) {
+        detail::write_unit_file(detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b), out[i]);
+    });
+}
+
+// Mirror of the decompress loop of src/modes.cpp:151-166: reads + xz-decodes every file with host threads, one
+// GPU batch for U + I, returns regen_boxes[t][lev][box] = multiBox3D.
+inline std::vector<std::vector<std::vector<multiBox3D>>>
+decompress_all(const std::string& compressed_dir, const std::vector<std::vector<int>>& box_counts,
+               const std::vector<int>& comp_idxs, unsigned lzma_threads = 0) {
+    wc_ctx* ctx = detail::context();
+    struct Key { int t, l, b, c; size_t ci; };
+    std::vector<Key> keys;
+    for (size_t t = 0; t < box_counts.size(); ++t)
+        for (size_t l = 0; l < box_counts[t].size(); ++l)
+            for (int b = 0; b < box_counts[t][l]; ++b)
+                for (size_t c = 0; c < comp_idxs.size(); ++c) keys.push_back({ (int)t, (int)l, b, comp_idxs[c], c });
+    std::vector<std::string> raw(keys.size());
+    unsigned nt = lzma_threads ? lzma_threads : std::thread::hardware_concurrency();
+    detail::parallel_for(keys.size(), nt, [&](size_t i) {
+        raw[i] = detail::xz_decode_file(detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b));
+        if (raw[i].size() < 20) detail::die("Deserialization failed: short file");
+    });
+    std::vector<std::vector<std::vector<multiBox3D>>> regen(box_counts.size());
+    for (size_t t = 0; t < box_counts.size(); ++t) {
+        regen[t].resize(box_counts[t].size());
+        for (size_t l = 0; l < box_counts[t].size(); ++l) regen[t][l].resize((size_t)box_counts[t][l]);
+    }
+    std::vector<wc_packed>  in(keys.size());
+    std::vector<wc_box_out> out(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i) {
+        int32_t h[5];
+        std::memcpy(h, raw[i].data(), 20);
+        in[i].shape[0] = h[0]; in[i].shape[1] = h[1]; in[i].shape[2] = h[2];
+        in[i].ncoef = h[3]; in[i].npairs = h[4]; in[i].reserved = 0;
+        // the pairs sit 4-byte aligned inside the decoded string (offset 20): wc_pair has 4-byte alignment
+        in[i].pairs = reinterpret_cast<wc_pair*>(&raw[i][0] + 20);
+        multiBox3D& mb = regen[keys[i].t][keys[i].l][keys[i].b];
+        if (mb.size() < comp_idxs.size()) mb.resize(comp_idxs.size());
+        mb[keys[i].ci] = Box3D((size_t)h[0], (size_t)h[1], (size_t)h[2]);
+        Box3D& bx = mb[keys[i].ci];
+        out[i] = { bx.data_size() ? &bx(0, 0, 0) : nullptr, WC_F32, h[0], h[1], h[2] };
+    }
+    detail::check(wc_decompress_batch(ctx, in.data(), (int)in.size(), WC_HOST, out.data(), WC_HOST), ctx,
+                  "wc_decompress_batch");
+    return regen;
+}
+
+} // namespace wcgpu
