@@ -112,3 +112,40 @@ def test_fused_persistent_loop_many_units_per_cta(fused_ctx, oracle):
     for i in list(range(0, 620, 37)) + list(range(620, 670, 7)) + [619, 669]:
         runs, vals, _ = oracle.compress_unit(boxes[i], dims[i], F999)
         assert same_bits(packed[i].runs, runs) and same_bits(packed[i].vals, vals), i
+
+
+# ---- fused decompress (k_fused_decompress<1>, <8>) ---------------------------------------------------
+@pytest.mark.parametrize("dims", FUSED1 + FUSED8)
+@pytest.mark.parametrize("out_dt", [np.float32, np.float64])
+def test_fused_decompress_shapes(fused_ctx, oracle, wc, dims, out_dt):
+    rng = np.random.default_rng(abs(hash((dims, "dec"))) % 2**32)
+    boxes = [smooth_box(dims, rng, sym=s) for s in (False, True)]
+    for keep in (F999, float(np.float32(0.99)), 1.0):
+        packed = []
+        for b in boxes:
+            runs, vals, _ = oracle.compress_unit(b, dims, keep)
+            packed.append(wc.PackedUnit(dims, dims[0] * dims[1] * dims[2], runs, vals))
+        recon = fused_ctx.decompress_batch(packed, out_dtype=out_dt)
+        for p, r in zip(packed, recon):
+            ob = oracle.decompress_unit(p.runs, p.vals, dims)
+            assert r.dtype == out_dt and same_bits(r.astype(np.float32), ob), (dims, keep)
+
+
+def test_fused_decompress_many_units_and_odd_streams(fused_ctx, oracle, wc):
+    rng = np.random.default_rng(4242)
+    dims = [(32, 32, 32)] * 400 + [(64, 64, 64)] * 30 + [(16, 32, 64)] * 20
+    packed = []
+    for i, d in enumerate(dims):
+        n = d[0] * d[1] * d[2]
+        k = int(rng.integers(0, n // 2))
+        if i % 50 == 0:
+            k = 0                                   # empty stream -> all zeros
+        runs = rng.integers(0, 3, k).astype(np.int32)
+        if i % 7 == 0 and k > 10:
+            runs[k // 2] = n                        # jumps past the end: this pair and all later ones are dropped
+        vals = rng.standard_normal(k).astype(np.float32)
+        packed.append(wc.PackedUnit(d, n, runs, vals))
+    recon = fused_ctx.decompress_batch(packed)
+    for i in list(range(0, 450, 13)) + [0, 399, 400, 429, 449]:
+        ob = oracle.decompress_unit(packed[i].runs, packed[i].vals, dims[i])
+        assert same_bits(recon[i], ob), i

@@ -773,8 +773,9 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
     std::vector<size_t> coef_off(n);
     for (int i = 0; i < n; ++i) {
         long long total = (long long)jobs[i].nx * jobs[i].ny * jobs[i].nz;
-        int cls = total > 0 ? fused_class(jobs[i].nx, jobs[i].ny, jobs[i].nz, WC_F32, nullptr) : -1;
+        int cls = total > 0 ? fused_decode_class(jobs[i].nx, jobs[i].ny, jobs[i].nz, jobs[i].out_dtype, jobs[i].out_dev) : -1;
         if (ctx->opt_path == 1 && cls > 0) cls = 0;
+        if (ctx->opt_path == 2 && cls == 0) return WC_ERR_BAD_DIMS;
         if (!fused_decode_available()) cls = cls > 0 ? 0 : cls;
         coef_off[i] = coef_floats;
         if (cls == 0) coef_floats += align_up((size_t)total, 4);
@@ -792,7 +793,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             for (int t = 0; t < du[i].nptiles; ++t) ptiles.push_back(make_int2(i, t));
             int nt = xtile_count(jobs[i].nx, jobs[i].ny, jobs[i].nz);
             for (int t = 0; t < nt; ++t) xtiles.push_back(make_int2(i, t));
-        } else if (cls == 1 || cls == 2) f1.push_back(i);
+        } else if (cls == 1) f1.push_back(i);
         else if (cls == 8) f8.push_back(i);
     }
     CTX_CUDA(ctx, d_coef.reserve(sizeof(float) * std::max<size_t>(coef_floats, 4)));

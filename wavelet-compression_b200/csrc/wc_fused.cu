@@ -92,7 +92,7 @@ int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
     if (fused_geom(nx, ny, nz, dtype, 8, 32768, g)) return 8;
     return 0;
 }
-bool fused_decode_available() { return false; }
+bool fused_decode_available() { return true; }
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -673,9 +673,293 @@ cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset) {
     return e;
 }
 
-cudaError_t launch_fused_decompress(int, const DecUnitDev*, const InvUnitDev*, const int*, int, int*,
-                                    int, cudaStream_t, LaunchStats*) {
-    return cudaSuccess;
+// =====================================================================================================
+// Fused decompress: rle_decode (src/decompressor.cpp:14-30) + inverse_wavelet_decompose (:79-159)
+// =====================================================================================================
+// Work item = (unit, y-slab r of S).  The CTA zero-fills its share C of the coefficient array in shared
+// memory, walks the unit's WHOLE pair list once (block-wide prefix sum of run+1 -> flat index of every
+// pair; the S slabs of a unit each do this — the list comes from L2 after the first — and keep only the
+// pairs that land in their own segments), then inverts two c-adjacent blocks per thread straight from C
+// and writes its slab of the box with coalesced 8/16-byte stores.  No coefficient scratch in HBM:
+// traffic = 8K (pairs, once from HBM) + 4N or 8N (box).
+struct FastDiv {     // q / d, exact: magic multiply when q_max * d < 2^32, plain division otherwise
+    uint32_t d, m;
+    __device__ __forceinline__ void init(uint32_t div, uint32_t qmax) {
+        d = div;
+        m = (div > 1 && (unsigned long long)qmax * div < (1ull << 32)) ? (0xffffffffu / div) + 1u : 0u;
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t q) const { return d == 1 ? q : (m ? __umulhi(q, m) : q / d); }
+};
+
+__device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) {   // saturating at 2^30 (> any ncoef)
+    uint32_t s = a + b;
+    return s > 0x40000000u ? 0x40000000u : s;
+}
+
+__device__ __forceinline__ void ihaar_pair2(float2& avg, float2& diff) {
+    const float2 neg1 = make_float2(-1.f, -1.f);
+    float2 p = __fadd2_rn(avg, diff);
+    float2 m = __ffma2_rn(diff, neg1, avg);     // avg - diff, correctly rounded
+    avg  = p;
+    diff = m;
+}
+
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// S = 1: one CTA per unit.  S = 8: an 8-CTA cluster per unit; CTA r owns the y-slab r of the box (and the
+// matching segments of C), walks 1/8 of the pair list, and scatters every value into the OWNER's shared
+// memory through DSMEM (st.shared::cluster) — the list is read from HBM exactly once.
+template <int S, int NT>
+__global__ void __launch_bounds__(NT, 1)
+k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
+                   const int* __restrict__ unit_list, int n_list, int* __restrict__ err) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NW = NT / 32;
+    constexpr int PPT = 8;                                     // pairs per thread per tile
+    float* const    C     = reinterpret_cast<float*>(smem);
+    uint32_t* const s_wt  = reinterpret_cast<uint32_t*>(smem + (32768 + F_CPAD) * 4);   // [32] warp totals
+    u64* const      xs    = reinterpret_cast<u64*>(smem + (32768 + F_CPAD) * 4 + 128);  // [2][8] exchange slots
+    const uint32_t  xb    = smem_u32(smem + (32768 + F_CPAD) * 4 + 128 + 128);          // mbarrier
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = S > 1 ? cluster_ctarank() : 0u;
+    const uint32_t cid  = S > 1 ? cluster_id_x() : blockIdx.x;
+    const uint32_t ncl  = S > 1 ? nclusters_x() : gridDim.x;
+    const uint32_t c_base = smem_u32(C);
+    uint32_t xph = 0;
+
+    if (S > 1) {
+        if (tid == 0) {
+            mbar_init(xb, S);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        cluster_sync_all();
+    }
+
+    for (int ui = cid; ui < n_list; ui += ncl) {
+        const int uid = unit_list[ui];
+        const DecUnitDev du = dec[uid];
+        const InvUnitDev iu = inv[uid];
+        FGeom g;
+        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, S, 32768, g);   // same rule as fused_decode_class
+        const int b0 = rank * g.nb;
+        const int K  = du.npairs_dev ? *du.npairs_dev : du.npairs;
+        const uint32_t total = (uint32_t)du.total;
+
+        // 1. zero-fill C (rle_decode starts from zeros, src/decompressor.cpp:17)
+        {
+            const int nwords = g.nlocal + F_PAD * g.X;
+            float4* c4 = reinterpret_cast<float4*>(C);
+            for (int i = tid; i < (nwords + 3) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // every CTA of the cluster has finished reading its previous C and zeroed the new one before
+        // anybody scatters into it
+        if (S > 1) cluster_sync_all(); else __syncthreads();
+
+        // 2. this CTA's share of the pair list: [k0, k1)
+        const int per = S > 1 ? (((K + S - 1) / S + PPT - 1) / PPT) * PPT : K;
+        const int k0 = min(K, (int)rank * per), k1 = min(K, k0 + per);
+        const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
+        bool bad = false;
+        uint32_t carry = 0;
+        if (S > 1) {
+            // 2a. sum of (run + 1) over the share, all-gathered -> where this share starts in f
+            uint32_t s = 0;
+            for (int p = k0 + tid; p < k1; p += NT) {
+                const int run = pairs[p].x;
+                if (run < 0) bad = true;
+                s = sat_add(s, (uint32_t)max(run, 0) + 1u);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s = sat_add(s, __shfl_xor_sync(0xffffffffu, s, o));
+            if (lane == 0) s_wt[warp] = s;
+            __syncthreads();
+            uint32_t tot = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) tot = sat_add(tot, s_wt[i]);
+            __syncthreads();
+            const uint32_t par = xph & 1;
+            if (tid < S) {
+                st_cluster_u64(mapa(smem_u32(&xs[par * 8 + rank]), tid), (u64)tot);
+                mbar_arrive_remote(mapa(xb, tid));
+            }
+            mbar_wait_cluster(xb, par);
+            ++xph;
+#pragma unroll
+            for (int r = 0; r < S; ++r)
+                if (r < (int)rank) carry = sat_add(carry, (uint32_t)xs[par * 8 + r]);
+        }
+        // 2b. flat index of every pair of the share; scatter into the owner's C
+        {
+            FastDiv dyz, dz, dnb;
+            dyz.init((uint32_t)(g.Y * g.Z), total);
+            dz.init((uint32_t)g.Z, (uint32_t)(g.Y * g.Z));
+            dnb.init((uint32_t)g.nb, (uint32_t)g.hy);
+            for (int p0 = k0; p0 < k1; p0 += NT * PPT) {
+                const int p = p0 + tid * PPT;
+                int2 pr[PPT];
+                uint32_t s = 0;
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) {
+                    pr[j] = (p + j < k1) ? pairs[p + j] : make_int2(-1, 0);
+                    if (p + j < k1) {
+                        if (pr[j].x < 0) bad = true;
+                        s = sat_add(s, (uint32_t)max(pr[j].x, 0) + 1u);
+                    }
+                }
+                uint32_t inc = s;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc = sat_add(inc, v);
+                }
+                if (lane == 31) s_wt[warp] = inc;
+                __syncthreads();
+                uint32_t wpre = 0, ttot = 0;
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    uint32_t x = s_wt[i];
+                    if (i < warp) wpre = sat_add(wpre, x);
+                    ttot = sat_add(ttot, x);
+                }
+                uint32_t exl = __shfl_up_sync(0xffffffffu, inc, 1);     // exclusive prefix inside the warp
+                if (lane == 0) exl = 0;
+                uint32_t pre = sat_add(sat_add(carry, wpre), exl);       // exclusive prefix of this thread
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) {
+                    if (p + j < k1 && pr[j].x >= 0) {
+                        const uint32_t f = sat_add(pre, (uint32_t)pr[j].x);
+                        if (f < total) {
+                            const uint32_t ip = dyz.div(f), rem = f - ip * (uint32_t)(g.Y * g.Z);
+                            const uint32_t jp = dz.div(rem), kp = rem - jp * (uint32_t)g.Z;
+                            const uint32_t sy = jp >= (uint32_t)g.hy ? 1u : 0u;
+                            const uint32_t b  = jp - sy * g.hy;                 // block-row 0..hy-1
+                            const uint32_t ro = S > 1 ? dnb.div(b) : 0u;       // owner slab
+                            const uint32_t bl = b - ro * g.nb;
+                            const uint32_t idx = ip * g.slab + (sy * g.nb + bl) * g.Z + kp;
+                            if (S > 1) st_cluster_f32(mapa(c_base + 4 * idx, ro), __int_as_float(pr[j].y));
+                            else C[idx] = __int_as_float(pr[j].y);
+                        }
+                        pre = sat_add(pre, (uint32_t)pr[j].x + 1u);
+                    }
+                }
+                carry = sat_add(carry, ttot);
+                __syncthreads();   // s_wt is reused by the next tile
+            }
+            if (bad) atomicOr(err, 1);
+        }
+        // all scatters (local and remote) are complete and visible before anybody reads its C
+        if (S > 1) cluster_sync_all(); else __syncthreads();
+
+        // 3. inverse transform (X, then Y, then Z), two c-adjacent blocks per thread, and store the slab
+        {
+            const uint32_t m_hx = fdiv_magic(g.hx), m_cq = fdiv_magic(g.ncq);
+            const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
+            const int npc = g.hz >> 1;
+            const size_t es = iu.dtype == WC_F64 ? 8 : 4;
+            const size_t row_bytes = (size_t)g.X * es, plane_bytes = row_bytes * g.Y;
+            char* out0 = static_cast<char*>(iu.out) + (size_t)(2 * b0) * row_bytes;
+            for (int q = tid; q < g.npairs; q += NT) {
+                const uint32_t cp2 = q & 1, t1 = q >> 1;
+                const uint32_t t2 = fdiv(t1, m_hx), a = t1 - t2 * g.hx;
+                const uint32_t bl = fdiv(t2, m_cq), cq = t2 - bl * g.ncq;
+                const int cpi = 2 * cq + cp2;
+                if (cpi >= npc) continue;
+                const float* csrc = C + a * g.slab + bl * g.Z + 2 * cpi;
+                float2 v[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o)
+                    v[o] = *reinterpret_cast<const float2*>(csrc + (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ihaar_pair2(v[2 * k], v[2 * k + 1]);                 // X
+#pragma unroll
+                for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+                    for (int xi = 0; xi < 2; ++xi) ihaar_pair2(v[zi * 4 + xi], v[zi * 4 + 2 + xi]);   // Y
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ihaar_pair2(v[k], v[4 + k]);                         // Z
+                char* p0 = out0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes + (size_t)a * 2 * es;
+#pragma unroll
+                for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+                    for (int yi = 0; yi < 2; ++yi) {
+                        const float2 lo = v[zi * 4 + yi * 2], hi = v[zi * 4 + yi * 2 + 1];   // xi = 0, 1
+                        char* pa = p0 + zi * plane_bytes + yi * row_bytes;        // block c:   planes 4cpi + zi
+                        char* pb = pa + 2 * plane_bytes;                          // block c+1: planes 4cpi + 2 + zi
+                        if (iu.dtype == WC_F64) {
+                            *reinterpret_cast<double2*>(pa) = make_double2((double)lo.x, (double)hi.x);
+                            *reinterpret_cast<double2*>(pb) = make_double2((double)lo.y, (double)hi.y);
+                        } else {
+                            *reinterpret_cast<float2*>(pa) = make_float2(lo.x, hi.x);
+                            *reinterpret_cast<float2*>(pb) = make_float2(lo.y, hi.y);
+                        }
+                    }
+            }
+        }
+        if (S == 1) __syncthreads();   // C is rewritten by the next unit (S > 1: the cluster barrier of step 1)
+    }
+    if (S > 1) cluster_sync_all();     // no CTA may exit while peers can still write into its smem
+}
+
+template <int S, int NT>
+static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
+                             int* err, int sm_count, cudaStream_t st, LaunchStats* ls) {
+    static int max_clusters = 0;
+    auto kern = k_fused_decompress<S, NT>;
+    constexpr int smem = (32768 + F_CPAD) * 4 + 512;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim         = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream           = st;
+    cudaLaunchAttribute attr[1];
+    if (S > 1) {
+        attr[0].id               = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = S;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs    = attr;
+        cfg.numAttrs = 1;
+        if (max_clusters == 0) {
+            cfg.gridDim = dim3(S * sm_count);
+            int nc = 0;
+            e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+            if (e != cudaSuccess) return e;
+            if (nc < 1) return cudaErrorLaunchOutOfResources;
+            max_clusters = nc;
+        }
+    } else {
+        max_clusters = sm_count;
+    }
+    const int nc = max_clusters < n ? max_clusters : n;
+    cfg.gridDim = dim3(nc * S);
+    ls->begin(kid, st);
+    e = cudaLaunchKernelEx(&cfg, kern, dec, inv, list, n, err);
+    ls->end(st);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+// Which fused-decompress class a unit belongs to (0 = generic): same geometry rules as compress, plus the
+// output pointer alignment for the vector stores.
+int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_ptr) {
+    if (reinterpret_cast<uintptr_t>(out_ptr) & (out_dtype == WC_F64 ? 15u : 7u)) return 0;
+    FGeom g;
+    if (fused_geom(nx, ny, nz, WC_F64, 1, 32768, g)) return 1;   // WC_F64: keeps the X*es % 16 rule valid for both
+    if (fused_geom(nx, ny, nz, WC_F64, 8, 32768, g)) return 8;
+    return 0;
+}
+
+cudaError_t launch_fused_decompress(int cluster, const DecUnitDev* dec, const InvUnitDev* inv,
+                                    const int* unit_list, int n_list, int* err, int sm_count,
+                                    cudaStream_t st, LaunchStats* ls) {
+    if (n_list <= 0) return cudaSuccess;
+    if (cluster == 1) return launch_fd<1, 512>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls);
+    if (cluster == 8) return launch_fd<8, 512>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls);
+    return cudaErrorInvalidValue;
 }
 
 } // namespace wc

@@ -15,6 +15,7 @@ enum { FUSED_FULL = 0, FUSED_KEYS_ONLY = 1, FUSED_GIVEN_THRESH = 2 };
 // 8 = one 8-CTA cluster per unit.
 int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 bool fused_decode_available();
+int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
 
 cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, UnitState* states,
                                   const int* unit_list, int n_list, double one_minus_keep,
