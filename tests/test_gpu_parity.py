@@ -226,3 +226,19 @@ def test_cpp_dropin_runs_the_reference_doctests_on_the_gpu():
         pytest.skip("oracle/_ref/dropin_test not built (needs /root/reference headers at build time)")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "dropin ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_multi_gpu_sharding_and_nccl_global_threshold():
+    """One rank per GPU under torchrun (needs >= 2 GPUs; the 1-GPU box skips): tests/mgpu_check.py."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -11,6 +11,11 @@ The directory name contains a hyphen (it mirrors the reference's repository name
 importlib.import_module("wavelet-compression_b200") or through __graft_entry__.package().
 """
 from . import amr_synth, capi  # noqa: F401
+
+try:  # torch is only needed for the multi-process helpers
+    from . import distributed  # noqa: F401
+except ImportError:  # pragma: no cover
+    distributed = None
 from .capi import (WC_DEVICE, WC_F32, WC_F64, WC_HOST, WC_THRESH_GLOBAL,  # noqa: F401
                    WC_THRESH_PER_UNIT, WcError)
 from .core import Context, PackedUnit, Plan  # noqa: F401
