@@ -200,6 +200,11 @@ WC_API int wc_plan_compress(wc_plan* plan, double keep, int thresh_mode);
  * plan-owned device memory.  WC_HOST: the kept pairs of all units are gathered densely on the device,
  * copied D2H once into plan-owned pinned memory, and out[u].pairs points into it. */
 WC_API int wc_plan_fetch(wc_plan* plan, wc_packed* out, int out_space);
+/* compress + fetch(WC_HOST) for host-resident inputs in ONE pipelined call: the unit list is cut into
+ * chunks and the H2D copy of chunk c overlaps the kernels of chunk c-1 and the gather + D2H of chunk
+ * c-2 (three streams; PCIe is full duplex).  Per-unit thresholds only.  Falls back to
+ * wc_plan_compress + wc_plan_fetch when the plan's inputs are device-resident. */
+WC_API int wc_plan_compress_to_host(wc_plan* plan, double keep, wc_packed* out);
 /* Total kept pairs of the last compress (waits for it). */
 WC_API int wc_plan_total_pairs(wc_plan* plan, int64_t* total);
 /* Enqueue decompression of the plan's current packed result into out[u] (device memory, or host

@@ -61,6 +61,7 @@ SIGNATURES = {
     "wc_plan_set_inputs": (_i, [_vp, _vp]),
     "wc_plan_compress": (_i, [_vp, _d, _i]),
     "wc_plan_fetch": (_i, [_vp, _vp, _i]),
+    "wc_plan_compress_to_host": (_i, [_vp, _d, _vp]),
     "wc_plan_total_pairs": (_i, [_vp, C.POINTER(C.c_int64)]),
     "wc_plan_decompress": (_i, [_vp, _vp, _i]),
     "wc_plan_rmse": (_i, [_vp, _vp, _vp]),

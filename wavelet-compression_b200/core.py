@@ -293,6 +293,12 @@ class Plan:
               self.ctx.h)
         return self._packed[:self.n]
 
+    def compress_to_host_records(self, keep: float) -> np.ndarray:
+        """Pipelined H2D / kernels / D2H (host-resident inputs): wc_packed records with pinned-host pairs."""
+        check(self.lib.wc_plan_compress_to_host(self.h, float(keep), self._packed.ctypes.data),
+              "wc_plan_compress_to_host", self.ctx.h)
+        return self._packed[:self.n]
+
     def fetch_host(self) -> list[PackedUnit]:
         rec = self.fetch_records(WC_HOST)
         return [Context._packed_to_host(rec[i]) for i in range(self.n)]

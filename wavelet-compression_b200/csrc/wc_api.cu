@@ -124,6 +124,10 @@ struct wc_plan {
     bool   compressed = false;
     bool   transformed = false;
     std::vector<size_t> in_dev_off; // per unit offset in d_in (host inputs)
+    // pipelined host path (wc_plan_compress_to_host)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev;
+    DevBuf d_running;
 };
 
 #define CTX_CUDA(ctx, call)                                                                        \
@@ -223,6 +227,7 @@ int wc_create_on_stream(wc_ctx** ctx, int device_id, void* cuda_stream) {
 }
 
 int wc_plan_destroy(wc_plan* plan);
+int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out);
 
 int wc_destroy(wc_ctx* ctx) {
     if (!ctx) return WC_OK;
@@ -518,6 +523,10 @@ int wc_plan_destroy(wc_plan* p) {
                        &p->d_psum, &p->d_err, &p->d_rmse_units, &p->d_rmse_sum, &p->d_rmse,
                        &p->d_stage_out };
     for (DevBuf* b : bufs) b->release();
+    p->d_running.release();
+    for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+    if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
+    if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
     p->h_states.release();
     p->h_dense.release();
     p->h_misc.release();
@@ -742,6 +751,140 @@ int wc_plan_fetch(wc_plan* p, wc_packed* out, int out_space) {
     size_t off = 0;
     for (int i = 0; i < p->n_units; ++i) {
         out[i].pairs = p->h_dense.as<wc_pair>() + off;
+        off += (size_t)hs[i].npairs;
+    }
+    return WC_OK;
+}
+
+
+// Pipelined host path: the unit list is cut into chunks; chunk c's boxes are copied H2D on one stream
+// while chunk c-1 is compressed on the ctx stream and chunk c-2's pairs are gathered densely and copied
+// D2H on a third stream (PCIe is full duplex), so the call costs about max(H2D, D2H) instead of their
+// sum.  Same result as wc_plan_compress + wc_plan_fetch(WC_HOST).
+int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
+    if (!p || (p->n_units > 0 && !out)) return WC_ERR_INVALID_ARG;
+    wc_ctx* ctx = p->ctx;
+    if (p->in_space != WC_HOST || !p->generic.empty() || p->n_units == 0) {
+        int rc = wc_plan_compress(p, keep, WC_THRESH_PER_UNIT);
+        if (rc != WC_OK) return rc;
+        return wc_plan_fetch(p, out, WC_HOST);
+    }
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int NCH = 8;
+    if (!p->s_h2d) {
+        CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+        CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+        p->ev.resize(3 * NCH + 1);
+        for (cudaEvent_t& e : p->ev) CTX_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CTX_CUDA(ctx, p->d_running.reserve(64));
+        CTX_CUDA(ctx, p->h_misc.reserve(sizeof(long long) * (NCH + 1)));
+        CTX_CUDA(ctx, p->d_offsets.reserve(sizeof(long long) * (p->n_units + NCH + 1)));
+    }
+    // worst case: every coefficient kept
+    CTX_CUDA(ctx, p->d_dense.reserve(sizeof(wc_pair) * std::max<size_t>((size_t)p->total_n, 1)));
+    volatile double one = 1.0;
+    const double omk = one - keep;
+    // chunk boundaries by input bytes
+    std::vector<int> cut(NCH + 1, p->n_units);
+    cut[0] = 0;
+    {
+        size_t acc = 0, per = p->in_bytes / NCH + 1;
+        int c = 1;
+        for (int i = 0; i < p->n_units && c < NCH; ++i) {
+            acc += (size_t)p->h_units[i].n * dtype_size(p->units[i].dtype);
+            if (acc >= per * c) cut[c++] = i + 1;
+        }
+    }
+    long long* h_run = p->h_misc.as<long long>();
+    CTX_CUDA(ctx, cudaMemsetAsync(p->d_running.p, 0, 8, ctx->stream));
+    CTX_CUDA(ctx, cudaMemsetAsync(p->d_states.p, 0, sizeof(UnitState) * p->n_units, ctx->stream));
+    CTX_CUDA(ctx, cudaEventRecord(p->ev[3 * NCH], ctx->stream));
+    CTX_CUDA(ctx, cudaStreamWaitEvent(p->s_h2d, p->ev[3 * NCH], 0));
+    size_t i1 = 0, i8 = 0;
+    long long done_total = 0;
+    auto finish_chunk = [&](int c, long long& prev_total) -> int {
+        // host learns the running total of chunk c, then enqueues its D2H
+        CTX_CUDA(ctx, cudaEventSynchronize(p->ev[NCH + c]));
+        long long tot = h_run[c];
+        size_t need = sizeof(wc_pair) * (size_t)std::max<long long>(tot, 1);
+        if (need > p->h_dense.cap) {
+            // grow the pinned buffer; earlier chunks' copies must land first, then move them over
+            CTX_CUDA(ctx, cudaStreamSynchronize(p->s_d2h));
+            PinBuf bigger;
+            CTX_CUDA(ctx, bigger.reserve(std::max(need, sizeof(wc_pair) * (size_t)p->total_n / 2 + 4096)));
+            if (p->h_dense.p && prev_total > 0) std::memcpy(bigger.p, p->h_dense.p, sizeof(wc_pair) * (size_t)prev_total);
+            p->h_dense.release();
+            p->h_dense = bigger;
+        }
+        if (tot > prev_total) {
+            CTX_CUDA(ctx, cudaStreamWaitEvent(p->s_d2h, p->ev[2 * NCH + c], 0));
+            CTX_CUDA(ctx, cudaMemcpyAsync(p->h_dense.as<wc_pair>() + prev_total, p->d_dense.as<wc_pair>() + prev_total,
+                                          sizeof(wc_pair) * (size_t)(tot - prev_total), cudaMemcpyDeviceToHost, p->s_d2h));
+            ctx->d2h += sizeof(wc_pair) * (size_t)(tot - prev_total);
+        }
+        prev_total = tot;
+        return WC_OK;
+    };
+    for (int c = 0; c < NCH; ++c) {
+        const int u0 = cut[c], u1 = cut[c + 1];
+        // H2D of the chunk
+        CopyList cl;
+        for (int i = u0; i < u1; ++i)
+            cl.add(p->d_in.as<char>() + p->in_dev_off[i], p->units[i].data, (size_t)p->h_units[i].n * dtype_size(p->units[i].dtype));
+        for (const CopyRange& r : cl.r) {
+            CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyHostToDevice, p->s_h2d));
+            ctx->h2d += r.bytes;
+        }
+        CTX_CUDA(ctx, cudaEventRecord(p->ev[c], p->s_h2d));
+        // compute on the ctx stream
+        CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->ev[c], 0));
+        size_t j1 = i1, j8 = i8;
+        while (j1 < p->fused1.size() && p->fused1[j1] < u1) ++j1;
+        while (j8 < p->fused8.size() && p->fused8[j8] < u1) ++j8;
+        if (j1 > i1)
+            CTX_CUDA(ctx, launch_fused_compress(1, FUSED_FULL, p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
+                                                p->d_f1.as<int>() + i1, (int)(j1 - i1), omk, nullptr, ctx->sm_count,
+                                                ctx->stream, &ctx->ls));
+        if (j8 > i8)
+            CTX_CUDA(ctx, launch_fused_compress(8, FUSED_FULL, p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
+                                                p->d_f8.as<int>() + i8, (int)(j8 - i8), omk, nullptr, ctx->sm_count,
+                                                ctx->stream, &ctx->ls));
+        i1 = j1; i8 = j8;
+        if (u1 > u0) {
+            CTX_CUDA(ctx, launch_gather_dense(p->d_units.as<UnitDev>() + u0, p->d_states.as<UnitState>() + u0, u1 - u0,
+                                              p->d_offsets.as<long long>() + u0 + c, nullptr, true, ctx->stream, &ctx->ls,
+                                              p->d_running.as<long long>()));
+        }
+        CTX_CUDA(ctx, cudaMemcpyAsync(&h_run[c], p->d_running.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CUDA(ctx, cudaEventRecord(p->ev[NCH + c], ctx->stream));
+        if (u1 > u0)
+            CTX_CUDA(ctx, launch_gather_dense(p->d_units.as<UnitDev>() + u0, p->d_states.as<UnitState>() + u0, u1 - u0,
+                                              p->d_offsets.as<long long>() + u0 + c, p->d_dense.as<wc_pair>(), false,
+                                              ctx->stream, &ctx->ls));
+        CTX_CUDA(ctx, cudaEventRecord(p->ev[2 * NCH + c], ctx->stream));
+        // while chunk c computes, hand chunk c-1's pairs to the D2H stream
+        if (c > 0) {
+            int rc = finish_chunk(c - 1, done_total);
+            if (rc != WC_OK) return rc;
+        }
+    }
+    {
+        int rc = finish_chunk(NCH - 1, done_total);
+        if (rc != WC_OK) return rc;
+    }
+    p->compressed = true;
+    int rc = plan_read_states(p);
+    if (rc != WC_OK) return rc;
+    CTX_CUDA(ctx, cudaStreamSynchronize(p->s_d2h));
+    const UnitState* hs = p->h_states.as<UnitState>();
+    size_t off = 0;
+    for (int i = 0; i < p->n_units; ++i) {
+        const UnitDev& u = p->h_units[i];
+        out[i].shape[0] = u.nx; out[i].shape[1] = u.ny; out[i].shape[2] = u.nz;
+        out[i].ncoef    = u.n;
+        out[i].npairs   = hs[i].npairs;
+        out[i].reserved = 0;
+        out[i].pairs    = p->h_dense.as<wc_pair>() + off;
         off += (size_t)hs[i].npairs;
     }
     return WC_OK;
@@ -1078,6 +1221,8 @@ int wc_compress_batch(wc_ctx* ctx, const wc_box_desc* in, int n_units, int in_sp
     int rc = wc_plan_create(ctx, in, n_units, in_space, &p);
     if (rc != WC_OK) return rc;
     ctx->batch_plan = p;
+    if (in_space == WC_HOST && out_space == WC_HOST && thresh_mode == WC_THRESH_PER_UNIT)
+        return wc_plan_compress_to_host(p, keep, out);
     rc = wc_plan_compress(p, keep, thresh_mode);
     if (rc != WC_OK) return rc;
     return wc_plan_fetch(p, out, out_space);

@@ -664,11 +664,12 @@ __global__ void k_rmse_final(const RmseUnitDev* __restrict__ units, int n_units,
 // dense gather of the packed slots (for the single D2H of wc_plan_fetch(WC_HOST))
 // ============================================================================================
 __global__ void k_unit_offsets(const UnitState* __restrict__ states, int n_units,
-                               long long* __restrict__ offsets /* n_units+1 */) {
+                               long long* __restrict__ offsets /* n_units+1 */,
+                               long long* __restrict__ running /* optional: in = base, out = base + total */) {
     // single CTA exclusive scan over units
     __shared__ long long s_w[32];
     __shared__ long long s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) s_carry = running ? *running : 0;
     __syncthreads();
     for (int i0 = 0; i0 < n_units; i0 += blockDim.x) {
         int i = i0 + threadIdx.x;
@@ -680,7 +681,10 @@ __global__ void k_unit_offsets(const UnitState* __restrict__ states, int n_units
         if (threadIdx.x == 0) s_carry += tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) offsets[n_units] = s_carry;
+    if (threadIdx.x == 0) {
+        offsets[n_units] = s_carry;
+        if (running) *running = s_carry;
+    }
 }
 
 __global__ void k_gather_dense(const UnitDev* __restrict__ units, const UnitState* __restrict__ states,
@@ -833,11 +837,11 @@ cudaError_t launch_rmse_generic(const RmseUnitDev* units, int n_units, const int
 
 cudaError_t launch_gather_dense(const UnitDev* units, const UnitState* states, int n_units,
                                 long long* offsets, wc_pair* dense, bool offsets_only,
-                                cudaStream_t st, LaunchStats* ls) {
+                                cudaStream_t st, LaunchStats* ls, long long* running) {
     if (n_units <= 0) return cudaSuccess;
     if (offsets_only) {
         ls->begin(KID_OFFSETS, st);
-        k_unit_offsets<<<1, 1024, 0, st>>>(states, n_units, offsets);
+        k_unit_offsets<<<1, 1024, 0, st>>>(states, n_units, offsets, running);
         ls->end(st);
         WC_LAUNCH_CHECK();
         return cudaSuccess;

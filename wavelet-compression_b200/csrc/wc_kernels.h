@@ -142,6 +142,6 @@ cudaError_t launch_rmse_generic(const RmseUnitDev* units, int n_units, const int
                                 LaunchStats* ls);
 cudaError_t launch_gather_dense(const UnitDev* units, const UnitState* states, int n_units,
                                 long long* offsets, wc_pair* dense, bool offsets_only,
-                                cudaStream_t st, LaunchStats* ls);
+                                cudaStream_t st, LaunchStats* ls, long long* running = nullptr);
 
 } // namespace wc
