@@ -269,6 +269,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
     u64* const      s_red  = reinterpret_cast<u64*>(smem + SM::RED);
     u64* const      xs1    = reinterpret_cast<u64*>(smem + SM::XS1);
     u64* const      xs2    = reinterpret_cast<u64*>(smem + SM::XS2);
+    int* const      s_next = reinterpret_cast<int*>(smem + SM::RED + 48 * 8);   // C2 work counter
     const uint32_t bars = smem_u32(smem + SM::BARS);
     const uint32_t xb1 = bars, xb2 = xb1 + 8, xb3 = xb2 + 8;
 
@@ -544,12 +545,20 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                 em = max(em, lv[j]);
             }
             if (tid == 0 && rank == 0) states[uid].npairs = total;
+            if (tid == 0) *s_next = 0;
             __syncthreads();
         }
 
         // ---------------- phase C2: emit (run, value) pairs ----------------
+        // Segments are handed out dynamically (shared-memory counter): their cost ranges from nothing
+        // (detail bands below the threshold) to a full copy, and a static round-robin left half of the
+        // warps idle at the closing barrier.
         long long t4 = clock64();
-        for (int sg = warp; sg < g.nseg; sg += NW) {
+        for (;;) {
+            int sg = 0;
+            if (lane == 0) sg = atomicAdd(s_next, 1);
+            sg = __shfl_sync(0xffffffffu, sg, 0);
+            if (sg >= g.nseg) break;
             const int scnt = (int)(my_pk[sg * R + rank] >> 16);
             if (scnt == 0) continue;                                   // nothing kept in this segment
             const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);
