@@ -168,6 +168,12 @@ WC_API int wc_decompress_batch(wc_ctx* ctx, const wc_packed* in, int n_units, in
 WC_API int wc_rmse_batch(wc_ctx* ctx, const wc_box_desc* actual, const wc_box_desc* pred, int n_units,
                   int space, double* rmse);
 
+/* Ingest statistics: per-unit minimum and maximum of the (narrowed) float32 values, the quantities
+ * src/preprocess.cpp:82-88 accumulates per component for the adjusted loss (src/modes.cpp:289).  A unit
+ * without any comparable value (empty, all NaN) reports +inf / -inf.  mins / maxs are HOST arrays. */
+WC_API int wc_minmax_batch(wc_ctx* ctx, const wc_box_desc* boxes, int n_units, int space, float* mins,
+                           float* maxs);
+
 /* ---- un-fused primitives (one unit, blocking) for parity tests -------------------------------- */
 /* wavelet_decompose, src/compressor.cpp:85-185: coef_out gets nx*ny*nz float32 in f order. */
 WC_API int wc_haar_forward(wc_ctx* ctx, const wc_box_desc* in, int space, float* coef_out);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "wc_compress_batch": (_i, [_vp, _vp, _i, _i, _d, _i, _vp, _i]),
     "wc_decompress_batch": (_i, [_vp, _vp, _i, _i, _vp, _i]),
     "wc_rmse_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "wc_minmax_batch": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "wc_haar_forward": (_i, [_vp, _vp, _i, _vp]),
     "wc_haar_inverse": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "wc_threshold_pack": (_i, [_vp, _vp, _i, _d, _i, _vp, C.POINTER(C.c_int32)]),

@@ -191,6 +191,15 @@ class Context:
                                      out.ctypes.data), "wc_rmse_batch", self.h)
         return out[:n]
 
+    def minmax_batch(self, boxes, dims=None):
+        """Per-unit (min, max) of the narrowed float32 values (src/preprocess.cpp:82-88)."""
+        d, hold = _host_descs(boxes, dims)
+        n = len(d)
+        lo, hi = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
+        check(self.lib.wc_minmax_batch(self.h, d.ctypes.data, n, WC_HOST, lo.ctypes.data, hi.ctypes.data),
+              "wc_minmax_batch", self.h)
+        return lo[:n], hi[:n]
+
     # -- un-fused primitives -------------------------------------------------------------------
     def haar_forward(self, box: np.ndarray) -> np.ndarray:
         d, hold = _host_descs([box])

@@ -1207,6 +1207,68 @@ int wc_rmse_batch(wc_ctx* ctx, const wc_box_desc* actual, const wc_box_desc* pre
     return run_rmse(ctx, jobs, ctx->ws_tbl0, ctx->ws_tiles0, ctx->ws_sum, ctx->ws_misc, rmse);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// ingest statistics: per-unit min / max of the narrowed values
+// ---------------------------------------------------------------------------------------------
+int wc_minmax_batch(wc_ctx* ctx, const wc_box_desc* boxes, int n_units, int space, float* mins, float* maxs) {
+    if (!ctx || n_units < 0 || (n_units > 0 && (!boxes || !mins || !maxs)) ||
+        (space != WC_HOST && space != WC_DEVICE))
+        return WC_ERR_INVALID_ARG;
+    if (n_units == 0) return WC_OK;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<RmseUnitDev> ru(n_units);
+    std::vector<int2> tiles;
+    std::vector<size_t> off(n_units);
+    size_t total = 0;
+    for (int i = 0; i < n_units; ++i) {
+        int rc = check_dims(boxes[i].nx, boxes[i].ny, boxes[i].nz);
+        if (rc != WC_OK) return rc;
+        if (boxes[i].dtype != WC_F32 && boxes[i].dtype != WC_F64) return WC_ERR_INVALID_ARG;
+        size_t n = (size_t)boxes[i].nx * boxes[i].ny * boxes[i].nz;
+        if (n > 0 && !boxes[i].data) return WC_ERR_INVALID_ARG;
+        off[i] = total;
+        total += align_up(n * dtype_size(boxes[i].dtype), 256);
+    }
+    if (space == WC_HOST) {
+        CTX_CUDA(ctx, ctx->ws_a.reserve(std::max<size_t>(total, 256)));
+        CopyList cl;
+        for (int i = 0; i < n_units; ++i) {
+            size_t n = (size_t)boxes[i].nx * boxes[i].ny * boxes[i].nz;
+            cl.add(ctx->ws_a.as<char>() + off[i], boxes[i].data, n * dtype_size(boxes[i].dtype));
+        }
+        for (const CopyRange& r : cl.r) {
+            CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d += r.bytes;
+        }
+    }
+    for (int i = 0; i < n_units; ++i) {
+        size_t n = (size_t)boxes[i].nx * boxes[i].ny * boxes[i].nz;
+        ru[i].a = space == WC_HOST ? (const void*)(ctx->ws_a.as<char>() + off[i]) : boxes[i].data;
+        ru[i].b = nullptr;
+        ru[i].a_dtype = boxes[i].dtype; ru[i].b_dtype = WC_F32;
+        ru[i].n = (int32_t)n;
+        ru[i].ctile0  = (int32_t)tiles.size();
+        ru[i].nctiles = ctile_count((long long)n);
+        for (int t = 0; t < ru[i].nctiles; ++t) tiles.push_back(make_int2(i, t));
+    }
+    CTX_CUDA(ctx, ctx->ws_tbl0.reserve(sizeof(RmseUnitDev) * n_units));
+    CTX_CUDA(ctx, ctx->ws_tiles0.reserve(sizeof(int2) * std::max<size_t>(tiles.size(), 1)));
+    CTX_CUDA(ctx, ctx->ws_sum.reserve(sizeof(float2) * std::max<size_t>(tiles.size(), 1)));
+    CTX_CUDA(ctx, ctx->ws_misc.reserve(sizeof(float2) * n_units));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tbl0.p, ru.data(), sizeof(RmseUnitDev) * n_units, cudaMemcpyHostToDevice, ctx->stream));
+    if (!tiles.empty())
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_tiles0.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, launch_minmax_generic(ctx->ws_tbl0.as<RmseUnitDev>(), n_units, ctx->ws_tiles0.as<int2>(), (int)tiles.size(),
+                                        ctx->ws_sum.as<float2>(), ctx->ws_misc.as<float2>(), ctx->stream, &ctx->ls));
+    std::vector<float2> mm(n_units);
+    CTX_CUDA(ctx, cudaMemcpyAsync(mm.data(), ctx->ws_misc.p, sizeof(float2) * n_units, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h += sizeof(float2) * n_units;
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n_units; ++i) { mins[i] = mm[i].x; maxs[i] = mm[i].y; }
+    return WC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // blocking compress
 // ---------------------------------------------------------------------------------------------

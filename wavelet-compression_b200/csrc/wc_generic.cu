@@ -661,6 +661,61 @@ __global__ void k_rmse_final(const RmseUnitDev* __restrict__ units, int n_units,
 }
 
 // ============================================================================================
+// per-unit min / max of the narrowed values (ingest statistics, src/preprocess.cpp:82-88)
+// ============================================================================================
+// `if (value < min) min = value; if (value > max) max = value;` — NaN never updates either.
+__global__ void __launch_bounds__(CT_THREADS)
+k_minmax_tiles(const RmseUnitDev* __restrict__ units, const int2* __restrict__ tiles,
+               float2* __restrict__ tile_mm) {
+    __shared__ float s_lo[CT_THREADS / 32], s_hi[CT_THREADS / 32];
+    const int2        tl = tiles[blockIdx.x];
+    const RmseUnitDev u  = units[tl.x];
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);   // +inf / -inf = "no value yet"
+    for (int j = threadIdx.x; j < CT_ELEMS; j += CT_THREADS) {
+        int f = tl.y * CT_ELEMS + j;
+        if (f < u.n) {
+            float v = u.a_dtype == WC_F64 ? __double2float_rn(static_cast<const double*>(u.a)[f])
+                                          : static_cast<const float*>(u.a)[f];
+            if (v < lo) lo = v;
+            if (v > hi) hi = v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_lo[w] = lo; s_hi[w] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < CT_THREADS / 32; ++i) { lo = fminf(lo, s_lo[i]); hi = fmaxf(hi, s_hi[i]); }
+        tile_mm[u.ctile0 + tl.y] = make_float2(lo, hi);
+    }
+}
+
+__global__ void k_minmax_final(const RmseUnitDev* __restrict__ units, int n_units,
+                               const float2* __restrict__ tile_mm, float2* __restrict__ out) {
+    int unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int l    = threadIdx.x & 31;
+    if (unit >= n_units) return;
+    const RmseUnitDev u = units[unit];
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    for (int t = l; t < u.nctiles; t += 32) {
+        float2 m = tile_mm[u.ctile0 + t];
+        lo = fminf(lo, m.x);
+        hi = fmaxf(hi, m.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (l == 0) out[unit] = make_float2(lo, hi);
+}
+
+// ============================================================================================
 // dense gather of the packed slots (for the single D2H of wc_plan_fetch(WC_HOST))
 // ============================================================================================
 __global__ void k_unit_offsets(const UnitState* __restrict__ states, int n_units,
@@ -830,6 +885,22 @@ cudaError_t launch_rmse_generic(const RmseUnitDev* units, int n_units, const int
     }
     ls->begin(KID_RMSE_FINAL, st);
     k_rmse_final<<<(n_units + 7) / 8, 256, 0, st>>>(units, n_units, tile_sum, rmse);
+    ls->end(st);
+    WC_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_minmax_generic(const RmseUnitDev* units, int n_units, const int2* ctiles, int n_ctiles,
+                                  float2* tile_mm, float2* out, cudaStream_t st, LaunchStats* ls) {
+    if (n_units <= 0) return cudaSuccess;
+    if (n_ctiles > 0) {
+        ls->begin(KID_MINMAX_TILES, st);
+        k_minmax_tiles<<<n_ctiles, CT_THREADS, 0, st>>>(units, ctiles, tile_mm);
+        ls->end(st);
+        WC_LAUNCH_CHECK();
+    }
+    ls->begin(KID_MINMAX_FINAL, st);
+    k_minmax_final<<<(n_units + 7) / 8, 256, 0, st>>>(units, n_units, tile_mm, out);
     ls->end(st);
     WC_LAUNCH_CHECK();
     return cudaSuccess;

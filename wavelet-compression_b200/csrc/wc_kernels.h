@@ -18,7 +18,7 @@ struct UnitState;
 enum KernelId {
     KID_FORWARD_GENERIC, KID_ARGMAX_FLAT, KID_FINALIZE, KID_GLOBAL_KEY, KID_COUNT, KID_SCAN, KID_EMIT,
     KID_RLE_SUMS, KID_RLE_SCAN, KID_RLE_SCATTER, KID_INVERSE_GENERIC, KID_RMSE_TILES, KID_RMSE_FINAL,
-    KID_OFFSETS, KID_GATHER, KID_FUSED_C1, KID_FUSED_C2, KID_FUSED_C8, KID_FUSED_D1, KID_FUSED_D8, KID_N
+    KID_OFFSETS, KID_GATHER, KID_FUSED_C1, KID_FUSED_C2, KID_FUSED_C8, KID_FUSED_D1, KID_FUSED_D8, KID_MINMAX_TILES, KID_MINMAX_FINAL, KID_N
 };
 inline const char* kernel_name(int id) {
     static const char* n[KID_N] = {
@@ -26,7 +26,7 @@ inline const char* kernel_name(int id) {
         "k_scan_tiles", "k_emit_tiles", "k_rle_tile_sums", "k_rle_scan", "k_rle_scatter",
         "k_inverse_generic", "k_rmse_tiles", "k_rmse_final", "k_unit_offsets", "k_gather_dense",
         "k_fused_compress<1>", "k_fused_compress<2>", "k_fused_compress<8>", "k_fused_decompress<1>",
-        "k_fused_decompress<8>" };
+        "k_fused_decompress<8>", "k_minmax_tiles", "k_minmax_final" };
     return (id >= 0 && id < KID_N) ? n[id] : "?";
 }
 struct LaunchStats {
@@ -140,6 +140,8 @@ cudaError_t launch_inverse_generic(const InvUnitDev* units, const int2* tiles, i
 cudaError_t launch_rmse_generic(const RmseUnitDev* units, int n_units, const int2* ctiles,
                                 int n_ctiles, double* tile_sum, double* rmse, cudaStream_t st,
                                 LaunchStats* ls);
+cudaError_t launch_minmax_generic(const RmseUnitDev* units, int n_units, const int2* ctiles, int n_ctiles,
+                                  float2* tile_mm, float2* out, cudaStream_t st, LaunchStats* ls);
 cudaError_t launch_gather_dense(const UnitDev* units, const UnitState* states, int n_units,
                                 long long* offsets, wc_pair* dense, bool offsets_only,
                                 cudaStream_t st, LaunchStats* ls, long long* running = nullptr);
