@@ -120,8 +120,10 @@ typedef enum {
     WC_OPT_PATH = 0,   /* 0 = auto (fused on-chip kernels when a unit fits, generic otherwise),
                           1 = force the generic multi-kernel path, 2 = force fused (error if a unit
                           does not fit) */
-    WC_OPT_PROFILE = 1 /* 1 = bracket every kernel launch with CUDA events on the ctx stream and
-                          accumulate per-kernel device time (read with wc_kernel_stats) */
+    WC_OPT_PROFILE = 1, /* 1 = bracket every kernel launch with CUDA events on the ctx stream and
+                           accumulate per-kernel device time (read with wc_kernel_stats) */
+    WC_OPT_OVERLAP = 2  /* 1 (default) = run the single-CTA and the cluster compress kernels of a step
+                           concurrently (second stream, dynamic unit hand-out); 0 = back to back */
 } wc_option;
 WC_API int wc_set_option(wc_ctx* ctx, int option, int64_t value);
 

@@ -17,7 +17,7 @@ WC_OK = 0
 WC_F32, WC_F64 = 0, 1
 WC_HOST, WC_DEVICE = 0, 1
 WC_THRESH_PER_UNIT, WC_THRESH_GLOBAL = 0, 1
-WC_OPT_PATH, WC_OPT_PROFILE = 0, 1
+WC_OPT_PATH, WC_OPT_PROFILE, WC_OPT_OVERLAP = 0, 1, 2
 WC_CTR_KERNEL_LAUNCHES, WC_CTR_H2D_BYTES, WC_CTR_D2H_BYTES = 0, 1, 2
 
 # numpy mirrors of the POD structs (layout checked against sizeof in tests/test_abi.py)

@@ -97,6 +97,7 @@ struct wc_ctx {
     LaunchStats  ls;
     uint64_t     h2d = 0, d2h = 0;
     int          opt_path = 0;
+    int          opt_overlap = 1;
     int          sm_count = 0;
     wc_plan*     batch_plan = nullptr; // owner of the memory handed out by wc_compress_batch
     // workspace of the blocking decompress / rmse / primitive calls (grow-only)
@@ -125,7 +126,9 @@ struct wc_plan {
     bool   transformed = false;
     std::vector<size_t> in_dev_off; // per unit offset in d_in (host inputs)
     // pipelined host path (wc_plan_compress_to_host)
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;
+    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
+    DevBuf d_counter;
     std::vector<cudaEvent_t> ev;
     DevBuf d_running;
 };
@@ -261,6 +264,9 @@ int wc_set_option(wc_ctx* ctx, int option, int64_t value) {
     case WC_OPT_PATH:
         if (value < 0 || value > 2) return WC_ERR_INVALID_ARG;
         ctx->opt_path = (int)value;
+        return WC_OK;
+    case WC_OPT_OVERLAP:
+        ctx->opt_overlap = value != 0;
         return WC_OK;
     case WC_OPT_PROFILE:
         cudaSetDevice(ctx->device);
@@ -524,6 +530,10 @@ int wc_plan_destroy(wc_plan* p) {
                        &p->d_stage_out };
     for (DevBuf* b : bufs) b->release();
     p->d_running.release();
+    p->d_counter.release();
+    if (p->s_aux) cudaStreamDestroy(p->s_aux);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
     if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
     if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
@@ -626,6 +636,33 @@ static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
                                           &ctx->ls));
     }
     int mode = global_key_dev ? FUSED_GIVEN_THRESH : FUSED_FULL;
+    // The cluster kernel cannot use every SM (clusters of 8 must fit inside a GPC: 15 clusters = 120 of 148
+    // SMs on B200).  When a step has both classes, the single-CTA kernel runs concurrently on a second
+    // stream with dynamic unit hand-out and back-fills the idle SMs.  (Serialised while per-kernel event
+    // profiling is on, so each kernel is timed alone.)
+    const bool overlap = p->n_f1 > 0 && p->n_f8 > 0 && !ctx->ls.profile && ctx->opt_overlap;
+    if (overlap) {
+        if (!p->s_aux) {
+            CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
+            CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+            CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+            CTX_CUDA(ctx, p->d_counter.reserve(64));
+        }
+        CTX_CUDA(ctx, cudaMemsetAsync(p->d_counter.p, 0, 4, ctx->stream));
+        CTX_CUDA(ctx, cudaEventRecord(p->ev_fork, ctx->stream));
+        CTX_CUDA(ctx, cudaStreamWaitEvent(p->s_aux, p->ev_fork, 0));
+        CTX_CUDA(ctx, launch_fused_compress(8, mode, p->d_units.as<UnitDev>(),
+                                            p->d_states.as<UnitState>(), p->d_f8.as<int>(), p->n_f8,
+                                            omk, global_key_dev, ctx->sm_count, ctx->stream, &ctx->ls));
+        CTX_CUDA(ctx, launch_fused_compress(1, mode, p->d_units.as<UnitDev>(),
+                                            p->d_states.as<UnitState>(), p->d_f1.as<int>(), p->n_f1,
+                                            omk, global_key_dev, ctx->sm_count, p->s_aux, &ctx->ls,
+                                            p->d_counter.as<int>()));
+        CTX_CUDA(ctx, cudaEventRecord(p->ev_join, p->s_aux));
+        CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->ev_join, 0));
+        p->compressed = true;
+        return WC_OK;
+    }
     if (p->n_f1)
         CTX_CUDA(ctx, launch_fused_compress(1, mode, p->d_units.as<UnitDev>(),
                                             p->d_states.as<UnitState>(), p->d_f1.as<int>(), p->n_f1,

@@ -258,7 +258,7 @@ template <int R, int CAP, int NT>
 __global__ void __launch_bounds__(NT, 1)
 k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                  const int* __restrict__ unit_list, int n_list, double one_minus_keep,
-                 const u64* __restrict__ global_key, int mode) {
+                 const u64* __restrict__ global_key, int mode, int* __restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
     typedef FSmem<R, CAP> SM;
     constexpr int NW = NT / 32;                   // warps per CTA
@@ -293,7 +293,21 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
     const uint32_t lt = lanemask_lt();
     const u64 pol = l2_policy_evict_first();
     uint32_t xph1 = 0, xph2 = 0, xph3 = 0;
-    for (int ui = cid; ui < n_list; ui += ncl) {
+    // Unit hand-out: static round-robin over the clusters, or (R = 1, work_counter given) a global atomic
+    // counter, so that CTAs that become resident late — e.g. on SMs the 8-CTA-cluster kernel of the same
+    // step is still using — simply take fewer units.  `ui_next` is known one unit ahead for the L2 prefetch.
+    const bool dynamic = (R == 1) && work_counter != nullptr;
+    int* const s_fetch = reinterpret_cast<int*>(smem + SM::RED + 50 * 8);
+    auto fetch = [&](int after) -> int {
+        if (!dynamic) return after + (int)ncl;
+        __syncthreads();
+        if (tid == 0) *s_fetch = atomicAdd(work_counter, 1);
+        __syncthreads();
+        return *s_fetch;
+    };
+    int ui = dynamic ? fetch(0) : (int)cid;
+    int ui_next = ui < n_list ? fetch(ui) : n_list;
+    for (; ui < n_list; ui = ui_next, ui_next = (ui < n_list ? fetch(ui) : n_list)) {
         const int     uid = unit_list[ui];
         const UnitDev u   = units[uid];
         FGeom g;
@@ -330,8 +344,8 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
 
         // L2 prefetch of this CTA's slab of its NEXT unit (one contiguous piece per z-plane), issued after
         // this unit's own loads: the HBM reads of unit u+1 overlap the packing phases of unit u.
-        if (ui + (int)ncl < n_list) {
-            const UnitDev un = units[unit_list[ui + ncl]];
+        if (ui_next < n_list) {
+            const UnitDev un = units[unit_list[ui_next]];
             FGeom gn;
             fused_geom(un.nx, un.ny, un.nz, un.dtype, R, CAP, gn);
             const size_t rb = (size_t)gn.X * gn.es, pb = rb * gn.Y;
@@ -610,7 +624,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
 template <int R, int CAP, int NT>
 static cudaError_t launch_fc(int kid, int mode, const UnitDev* units, UnitState* states, const int* list,
                              int n, double omk, const u64* gkey, int sm_count, cudaStream_t st,
-                             LaunchStats* ls) {
+                             LaunchStats* ls, int* work_counter) {
     static int max_clusters = 0;   // resident clusters (CTAs for R = 1) on this device
     auto kern = k_fused_compress<R, CAP, NT>;
     constexpr int smem = FSmem<R, CAP>::TOTAL;
@@ -647,7 +661,7 @@ static cudaError_t launch_fc(int kid, int mode, const UnitDev* units, UnitState*
     const int nc = max_clusters < n ? max_clusters : n;
     cfg.gridDim = dim3(nc * R);
     ls->begin(kid, st);
-    e = cudaLaunchKernelEx(&cfg, kern, units, states, list, n, omk, gkey, mode);
+    e = cudaLaunchKernelEx(&cfg, kern, units, states, list, n, omk, gkey, mode, work_counter);
     ls->end(st);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
@@ -656,14 +670,14 @@ static cudaError_t launch_fc(int kid, int mode, const UnitDev* units, UnitState*
 cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, UnitState* states,
                                   const int* unit_list, int n_list, double one_minus_keep,
                                   const u64* global_key, int sm_count, cudaStream_t st,
-                                  LaunchStats* ls) {
+                                  LaunchStats* ls, int* work_counter) {
     if (n_list <= 0) return cudaSuccess;
     if (cluster == 1)
         return launch_fc<1, 32768, WC_NT1>(KID_FUSED_C1, mode, units, states, unit_list, n_list, one_minus_keep,
-                                           global_key, sm_count, st, ls);
+                                           global_key, sm_count, st, ls, work_counter);
     if (cluster == 8)
         return launch_fc<8, 32768, 512>(KID_FUSED_C8, mode, units, states, unit_list, n_list, one_minus_keep,
-                                        global_key, sm_count, st, ls);
+                                        global_key, sm_count, st, ls, nullptr);
     return cudaErrorInvalidValue;
 }
 

@@ -20,7 +20,7 @@ int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_d
 cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, UnitState* states,
                                   const int* unit_list, int n_list, double one_minus_keep,
                                   const u64* global_key, int sm_count, cudaStream_t st,
-                                  LaunchStats* ls);
+                                  LaunchStats* ls, int* work_counter = nullptr);
 cudaError_t launch_fused_decompress(int cluster, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
                                     cudaStream_t st, LaunchStats* ls);
