@@ -104,6 +104,10 @@ struct wc_ctx {
     DevBuf ws_pairs, ws_coef, ws_boxes, ws_tbl0, ws_tbl1, ws_tbl2, ws_tiles0, ws_tiles1, ws_sum,
         ws_misc, ws_a, ws_b;
     PinBuf ws_pin;
+    // second stream for running the single-CTA and cluster kernels of one step concurrently
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
+    DevBuf       d_counter;
 };
 
 struct wc_plan {
@@ -243,6 +247,10 @@ int wc_destroy(wc_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     ctx->ws_pin.release();
     ctx->ls.destroy();
+    ctx->d_counter.release();
+    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
@@ -1013,16 +1021,33 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
         if (!f8.empty())
             CTX_CUDA(ctx, cudaMemcpyAsync(dl + f1.size(), f8.data(), sizeof(int) * f8.size(),
                                           cudaMemcpyHostToDevice, ctx->stream));
-        if (!f1.empty())
-            CTX_CUDA(ctx, launch_fused_decompress(1, d_dec_units.as<DecUnitDev>(),
-                                                  d_inv_units.as<InvUnitDev>(), dl, (int)f1.size(),
-                                                  d_err.as<int>(), ctx->sm_count, ctx->stream,
-                                                  &ctx->ls));
+        const bool overlap = !f1.empty() && !f8.empty() && !ctx->ls.profile && ctx->opt_overlap;
+        if (overlap) {
+            if (!ctx->s_aux) {
+                CTX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+                CTX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+                CTX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+                CTX_CUDA(ctx, ctx->d_counter.reserve(64));
+            }
+            CTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
+            CTX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
+        }
         if (!f8.empty())
             CTX_CUDA(ctx, launch_fused_decompress(8, d_dec_units.as<DecUnitDev>(),
                                                   d_inv_units.as<InvUnitDev>(), dl + f1.size(),
                                                   (int)f8.size(), d_err.as<int>(), ctx->sm_count,
                                                   ctx->stream, &ctx->ls));
+        if (!f1.empty())
+            CTX_CUDA(ctx, launch_fused_decompress(1, d_dec_units.as<DecUnitDev>(),
+                                                  d_inv_units.as<InvUnitDev>(), dl, (int)f1.size(),
+                                                  d_err.as<int>(), ctx->sm_count,
+                                                  overlap ? ctx->s_aux : ctx->stream, &ctx->ls,
+                                                  overlap ? ctx->d_counter.as<int>() : nullptr));
+        if (overlap) {
+            CTX_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->s_aux));
+            CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        }
     }
     return WC_OK;
 }

@@ -737,7 +737,8 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
 template <int S, int NT>
 __global__ void __launch_bounds__(NT, 1)
 k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
-                   const int* __restrict__ unit_list, int n_list, int* __restrict__ err) {
+                   const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
+                   int* __restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NW = NT / 32;
     constexpr int PPT = 8;                                     // pairs per thread per tile
@@ -761,7 +762,17 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         cluster_sync_all();
     }
 
-    for (int ui = cid; ui < n_list; ui += ncl) {
+    // static round-robin, or (S = 1 with a work counter) dynamic hand-out — see k_fused_compress
+    const bool dynamic = (S == 1) && work_counter != nullptr;
+    int* const s_fetch = reinterpret_cast<int*>(smem + (32768 + F_CPAD) * 4 + 128 + 128 + 16);
+    auto fetch = [&](int after) -> int {
+        if (!dynamic) return after + (int)ncl;
+        __syncthreads();
+        if (tid == 0) *s_fetch = atomicAdd(work_counter, 1);
+        __syncthreads();
+        return *s_fetch;
+    };
+    for (int ui = dynamic ? fetch(0) : (int)cid; ui < n_list; ui = fetch(ui)) {
         const int uid = unit_list[ui];
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
@@ -928,7 +939,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
 
 template <int S, int NT>
 static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
-                             int* err, int sm_count, cudaStream_t st, LaunchStats* ls) {
+                             int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter) {
     static int max_clusters = 0;
     auto kern = k_fused_decompress<S, NT>;
     constexpr int smem = (32768 + F_CPAD) * 4 + 512;
@@ -960,7 +971,7 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
     const int nc = max_clusters < n ? max_clusters : n;
     cfg.gridDim = dim3(nc * S);
     ls->begin(kid, st);
-    e = cudaLaunchKernelEx(&cfg, kern, dec, inv, list, n, err);
+    e = cudaLaunchKernelEx(&cfg, kern, dec, inv, list, n, err, work_counter);
     ls->end(st);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
@@ -978,10 +989,10 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
 
 cudaError_t launch_fused_decompress(int cluster, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
-                                    cudaStream_t st, LaunchStats* ls) {
+                                    cudaStream_t st, LaunchStats* ls, int* work_counter) {
     if (n_list <= 0) return cudaSuccess;
-    if (cluster == 1) return launch_fd<1, 512>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls);
-    if (cluster == 8) return launch_fd<8, 512>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls);
+    if (cluster == 1) return launch_fd<1, 512>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    if (cluster == 8) return launch_fd<8, 512>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, nullptr);
     return cudaErrorInvalidValue;
 }
 

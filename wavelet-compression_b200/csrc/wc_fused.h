@@ -23,7 +23,7 @@ cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, U
                                   LaunchStats* ls, int* work_counter = nullptr);
 cudaError_t launch_fused_decompress(int cluster, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
-                                    cudaStream_t st, LaunchStats* ls);
+                                    cudaStream_t st, LaunchStats* ls, int* work_counter = nullptr);
 
 cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset);
 
