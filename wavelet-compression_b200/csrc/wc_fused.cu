@@ -55,6 +55,7 @@ struct FSmem {
 static_assert(FSmem<8, 32768>::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 struct FGeom {
+    static constexpr bool is_static = false;
     int X, Y, Z, hx, hy, hz, es;
     int nb;        // block-rows (y) per CTA
     int ncq;       // c-quads: groups of two c-adjacent block pairs
@@ -63,6 +64,20 @@ struct FGeom {
     int nseg;      // 2 * X
     int nlocal;    // X * 2 * nb * Z
     int slab;      // padded words of C per i'
+};
+
+// The same quantities as literals, for the shapes AMR codes produce most (cubes of 32 and 64).
+template <int X_, int Y_, int Z_, int ES_, int R_>
+struct SGeom {
+    static constexpr bool is_static = true;
+    static constexpr int X = X_, Y = Y_, Z = Z_, hx = X_ / 2, hy = Y_ / 2, hz = Z_ / 2, es = ES_;
+    static constexpr int nb     = hy / R_;
+    static constexpr int ncq    = (hz / 2 + 1) / 2;
+    static constexpr int npairs = 2 * ncq * hx * nb;
+    static constexpr int seglen = nb * Z_;
+    static constexpr int nseg   = 2 * X_;
+    static constexpr int nlocal = nseg * seglen;
+    static constexpr int slab   = 2 * nb * Z_ + F_PAD;
 };
 
 __host__ __device__ inline bool fused_geom(int X, int Y, int Z, int dtype, int R, int cap, FGeom& g) {
@@ -149,6 +164,12 @@ __device__ __forceinline__ uint32_t nclusters_x() {
 
 // exact q / d for q < 65536, d < 65536 (m = ceil(2^32 / d); d == 1 is encoded as m == 0)
 __device__ __forceinline__ uint32_t fdiv(uint32_t q, uint32_t m) { return m ? __umulhi(q, m) : q; }
+// index of the most significant set bit, 0xffffffff for 0
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t x) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
 __device__ __forceinline__ uint32_t fdiv_magic(uint32_t d) { return d <= 1 ? 0u : (0xffffffffu / d) + 1u; }
 
 // Streaming accesses carry an L2 evict-first policy: the input is read once and the pairs are written
@@ -254,6 +275,358 @@ __device__ __forceinline__ float transform_pair(const char* p0, size_t plane_byt
     return v[0].x;
 }
 
+// Everything the per-unit body needs from the kernel frame (all scalarised after inlining).
+struct FShared {
+    float*    C;
+    uint32_t* g_pk;
+    int*      s_base;
+    int*      s_prev;
+    u64*      s_red;
+    u64*      xs1;
+    u64*      xs2;
+    int*      s_next;
+    uint32_t  xb1, xb2, xb3;
+};
+// This CTA's slab of its NEXT unit, for the L2 prefetch: `nplanes` pieces of `piece_lines` 128-byte lines,
+// `pitch` bytes apart (one piece of the whole unit when the CTA owns complete z-planes, R = 1).
+struct FPrefetch {
+    const char* base;
+    uint32_t    piece_lines, nplanes;
+    size_t      pitch;
+};
+
+// One unit, start to finish.  G is FGeom (geometry in registers, any admissible shape) or an SGeom<...>
+// (the common cubes: every stride, trip count and divisor is a literal).
+template <int R, int CAP, int NT, class G>
+__device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int uid, const FShared& S,
+                                        const FPrefetch& pf, const uint32_t rank, uint32_t& xph1,
+                                        uint32_t& xph2, uint32_t& xph3, UnitState* __restrict__ states,
+                                        const double one_minus_keep, const u64* __restrict__ global_key,
+                                        const int mode, const u64 pol, const uint32_t lt) {
+    typedef FSmem<R, CAP> SM;
+    constexpr int NW = NT / 32;
+    float* const C = S.C;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b0 = rank * g.nb;
+    const size_t row_bytes = (size_t)g.X * g.es, plane_bytes = row_bytes * g.Y;
+    const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
+    float bp = 0.f, bn = 0.f;                 // running max of +c and of -c
+    bool  nan0 = false;
+    long long t0 = clock64();
+
+    // ---------------- phase A: load, narrow, transform two blocks per thread, store into C -------
+    {
+        const uint32_t m_hx = G::is_static ? 0u : fdiv_magic(g.hx), m_cq = G::is_static ? 0u : fdiv_magic(g.ncq);
+        const char* in0 = static_cast<const char*>(u.in) + (size_t)(2 * b0) * row_bytes;
+        const int npc = g.hz >> 1;                         // c-pairs per (a, b)
+#pragma unroll 1
+        for (int q = tid; q < g.npairs; q += NT) {
+            // slot q -> (cp2 fastest, a, cq, bl): lanes = 2 c-pairs x 16 a  ->  coalesced rows, and
+            // conflict-free 8-byte stores into C (banks 4a + 2cp2 + {0,1})
+            const uint32_t cp2 = q & 1, t1 = q >> 1;
+            const uint32_t t2 = G::is_static ? t1 / (uint32_t)g.hx : fdiv(t1, m_hx), a = t1 - t2 * g.hx;
+            const uint32_t bl = G::is_static ? t2 / (uint32_t)g.ncq : fdiv(t2, m_cq), cq = t2 - bl * g.ncq;
+            const int cpi = 2 * cq + cp2;                  // c-pair index: blocks c = 2cpi, 2cpi+1
+            if ((npc & 1) && cpi >= npc) continue;         // hz/2 odd: the last quad has one pair
+            const char* p0 = in0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes +
+                             (size_t)a * 2 * g.es;
+            float* cdst = C + a * g.slab + bl * g.Z + 2 * cpi;
+            float v0 = g.es == 8
+                ? transform_pair<8>(p0, plane_bytes, row_bytes, cdst, o1, o2, o3, bp, bn, pol)
+                : transform_pair<4>(p0, plane_bytes, row_bytes, cdst, o1, o2, o3, bp, bn, pol);
+            if (q == 0 && rank == 0) nan0 = isnan(v0);     // slot 0 = block (0,0,0): coefficient f = 0
+        }
+    }
+
+    // L2 prefetch of this CTA's slab of its NEXT unit, issued after this unit's own loads: the HBM reads
+    // of unit u+1 overlap the packing phases of unit u.
+    if (pf.base) {
+        if (R == 1) {
+            for (uint32_t i = tid; i < pf.piece_lines; i += NT)
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pf.base + (size_t)i * 128));
+        } else {
+            const uint32_t nlines = pf.piece_lines * pf.nplanes;
+            for (uint32_t i = tid; i < nlines; i += NT) {
+                const uint32_t z = i / pf.piece_lines, l = i - z * pf.piece_lines;
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pf.base + (size_t)z * pf.pitch + (size_t)l * 128));
+            }
+        }
+    }
+
+    // ---------------- phase B: the threshold ----------------
+    long long t1 = clock64();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
+        bn = fmaxf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
+    }
+    const bool any_nan0 = __any_sync(0xffffffffu, nan0);
+    if (lane == 0) {
+        // bn >= 0, so its sign bit is free: it carries "the coefficient at f = 0 is NaN"
+        S.s_red[warp] = ((u64)__float_as_uint(bp) << 32) |
+                        (u64)((__float_as_uint(bn) & 0x7fffffffu) | (any_nan0 ? 0x80000000u : 0u));
+    }
+    __syncthreads();
+    float Mp = 0.f, Mn = 0.f;
+    bool  first_nan = false;
+    {
+        u64 x = lane < NW ? S.s_red[lane] : 0ull;
+        float p = __uint_as_float((uint32_t)(x >> 32));
+        float n = __uint_as_float((uint32_t)x & 0x7fffffffu);
+        first_nan = __any_sync(0xffffffffu, ((uint32_t)x >> 31) != 0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
+            n = fmaxf(n, __shfl_xor_sync(0xffffffffu, n, o));
+        }
+        Mp = p; Mn = n;
+    }
+    if (R > 1) {
+        // all-gather (Mp | Mn) over the cluster
+        const uint32_t par = xph1 & 1;
+        if (tid < R) {
+            u64 pay = ((u64)__float_as_uint(Mp) << 32) |
+                      (u64)((__float_as_uint(Mn) & 0x7fffffffu) | (first_nan ? 0x80000000u : 0u));
+            st_cluster_u64(mapa(smem_u32(&S.xs1[par * 8 + rank]), tid), pay);
+            mbar_arrive_remote(mapa(S.xb1, tid));
+        }
+        mbar_wait_cluster(S.xb1, par);
+        ++xph1;
+        float p = 0.f, n = 0.f;
+        bool fn = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            u64 x = S.xs1[par * 8 + r];
+            fn = fn || (((uint32_t)x >> 31) != 0);
+            p  = fmaxf(p, __uint_as_float((uint32_t)(x >> 32)));
+            n  = fmaxf(n, __uint_as_float((uint32_t)x & 0x7fffffffu));
+        }
+        Mp = p; Mn = n; first_nan = fn;
+    }
+    float M = fmaxf(Mp, Mn);
+    uint32_t sign = Mn > Mp ? 1u : 0u;
+    if (Mp == Mn && M != 0.f && !first_nan && mode != FUSED_GIVEN_THRESH) {
+        // +M and -M tie: the FIRST one in f order decides (std::max_element) -> find min f
+        u64 best = ~0ull;
+        const uint32_t m_sl = fdiv_magic(g.seglen);
+#pragma unroll 1
+        for (int l = tid; l < g.nlocal; l += NT) {
+            uint32_t sg = fdiv(l, m_sl), w = l - sg * g.seglen;
+            float c = C[l + F_PAD * (sg >> 1)];
+            if (fabsf(c) == M) {
+                uint32_t f = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z + w;
+                u64 cand = ((u64)f << 1) | (u64)(__float_as_uint(c) >> 31);
+                best = cand < best ? cand : best;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            u64 x = __shfl_xor_sync(0xffffffffu, best, o);
+            best = x < best ? x : best;
+        }
+        __syncthreads();   // s_red reuse
+        if (lane == 0) S.s_red[warp] = best;
+        __syncthreads();
+        best = lane < NW ? S.s_red[lane] : ~0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            u64 x = __shfl_xor_sync(0xffffffffu, best, o);
+            best = x < best ? x : best;
+        }
+        if (R > 1) {
+            const uint32_t par = xph3 & 1;
+            if (tid < R) {
+                st_cluster_u64(mapa(smem_u32(&S.xs2[par * 8 + rank]), tid), best);
+                mbar_arrive_remote(mapa(S.xb3, tid));
+            }
+            mbar_wait_cluster(S.xb3, par);
+            ++xph3;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                u64 x = S.xs2[par * 8 + r];
+                best = x < best ? x : best;
+            }
+        }
+        sign = (uint32_t)(best & 1ull);
+    }
+    float tf;
+    {
+        u64 key = ((u64)__float_as_uint(M) << 32) | 2ull | (u64)sign;
+        if (mode == FUSED_GIVEN_THRESH) {
+            u64 gk = *global_key;
+            tf = threshold_float(gk & ~(1ull << 63), (gk >> 63) != 0, one_minus_keep);
+        } else {
+            tf = threshold_float(key, first_nan, one_minus_keep);
+        }
+        if (tid == 0 && rank == 0) {
+            states[uid].key      = key;
+            states[uid].flags    = first_nan ? 1 : 0;
+            states[uid].thresh_f = tf;
+        }
+    }
+    if (mode == FUSED_KEYS_ONLY) {
+        __syncthreads();   // C is rewritten by the next unit
+        return;
+    }
+
+    // ---------------- phase C1: per-segment count and last kept ----------------
+    long long t2 = clock64();
+    const int gpar = R > 1 ? (int)(xph2 & 1) : 0;
+    uint32_t* const my_pk = S.g_pk + gpar * SM::MAXG;
+#pragma unroll 1
+    for (int sg = warp; sg < g.nseg; sg += NW) {
+        const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);   // 16-byte aligned
+        int cnt = 0, lb = 0;
+        uint32_t lm = 0;
+        for (int w = lane * 4; w < g.seglen; w += 128) {           // seglen % 4 == 0
+            const float4 c = *reinterpret_cast<const float4*>(cs + w);
+            uint32_t m = (keep_coef(c.x, tf) ? 1u : 0u) | (keep_coef(c.y, tf) ? 2u : 0u) |
+                         (keep_coef(c.z, tf) ? 4u : 0u) | (keep_coef(c.w, tf) ? 8u : 0u);
+            cnt += __popc(m);
+            if (m) { lb = w; lm = m; }
+        }
+        int last = lm ? lb + 31 - __clz(lm) : -1;
+        cnt  = __reduce_add_sync(0xffffffffu, cnt);
+        last = __reduce_max_sync(0xffffffffu, last);
+        const uint32_t pk = ((uint32_t)cnt << 16) | ((uint32_t)last & 0xffffu);
+        if (R == 1) {
+            if (lane == 0) my_pk[sg] = pk;
+        } else if (lane < R) {
+            st_cluster_u32(mapa(smem_u32(&my_pk[sg * R + rank]), lane), pk);
+        }
+    }
+    long long t3 = clock64();
+    if (R > 1) {
+        fence_cluster();
+        __syncthreads();
+        if (tid < R) mbar_arrive_remote(mapa(S.xb2, tid));
+        mbar_wait_cluster(S.xb2, gpar);
+        ++xph2;
+    } else {
+        __syncthreads();
+    }
+
+    // ---------------- scan over the segments in global order ----------------
+    {
+        constexpr int EPT = (SM::MAXG + NT - 1) / NT;   // entries per thread
+        const int NG = g.nseg * R;                      // <= MAXG, entry e = sg * R + r
+        int* sr = reinterpret_cast<int*>(S.s_red);
+        // only the warps that own entries work; the others (all but the first for R = 1) just publish
+        // neutral elements and meet the barriers
+        const bool active = warp * 32 * EPT < NG;
+        int cv[EPT], lv[EPT];
+        int isum = 0, imax = -1;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                const int e = tid * EPT + j;
+                cv[j] = 0; lv[j] = -1;
+                if (e < NG) {
+                    const uint32_t pk = my_pk[e];
+                    const int sg = e / R, r = e % R;
+                    cv[j] = (int)(pk >> 16);
+                    if ((pk & 0xffffu) != 0xffffu)
+                        lv[j] = ((sg >> 1) * g.Y + (sg & 1) * g.hy + r * g.nb) * g.Z + (int)(pk & 0xffffu);
+                }
+                isum += cv[j];
+                imax = max(imax, lv[j]);
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int ps = __shfl_up_sync(0xffffffffu, isum, o);
+                int pm = __shfl_up_sync(0xffffffffu, imax, o);
+                if (lane >= o) { isum += ps; imax = max(imax, pm); }
+            }
+        }
+        if (lane == 31) { sr[warp] = isum; sr[32 + warp] = imax; }
+        __syncthreads();
+        if (active) {
+            int wsum = 0, wmax = -1, total = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                int xs = sr[i], xm = sr[32 + i];
+                if (i < warp) { wsum += xs; wmax = max(wmax, xm); }
+                total += xs;
+            }
+            int es = __shfl_up_sync(0xffffffffu, isum, 1);
+            int em = __shfl_up_sync(0xffffffffu, imax, 1);
+            if (lane == 0) { es = 0; em = -1; }
+            es += wsum;
+            em = max(em, wmax);
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {                 // exclusive prefix in front of entry e
+                const int e = tid * EPT + j;
+                if (e < NG && (R == 1 || (e % R) == (int)rank)) { S.s_base[e / R] = es; S.s_prev[e / R] = em; }
+                es += cv[j];
+                em = max(em, lv[j]);
+            }
+            if (tid == 0 && rank == 0) states[uid].npairs = total;
+            if (tid == 0) *S.s_next = 0;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- phase C2: emit (run, value) pairs ----------------
+    // Segments are handed out dynamically (shared-memory counter): their cost ranges from nothing
+    // (detail bands below the threshold) to a full copy, and a static round-robin left half of the
+    // warps idle at the closing barrier.
+    long long t4 = clock64();
+    int2* const out = reinterpret_cast<int2*>(u.out);
+    for (;;) {
+        int sg = 0;
+        if (lane == 0) sg = atomicAdd(S.s_next, 1);
+        sg = __shfl_sync(0xffffffffu, sg, 0);
+        if (sg >= g.nseg) break;
+        const int scnt = (int)(my_pk[sg * R + rank] >> 16);
+        if (scnt == 0) continue;                                   // nothing kept in this segment
+        const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);
+        const int fstart = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z;
+        uint32_t pos = (uint32_t)S.s_base[sg];
+        int prev = S.s_prev[sg];
+        if (scnt == g.seglen) {
+            // every coefficient kept (e.g. a negative max, SURVEY.md D3'): runs are 0, ranks are w
+            for (int w = lane; w < g.seglen; w += 32)
+                st_pair_pred(true, out + (pos + (uint32_t)w), w == 0 ? fstart - prev - 1 : 0, cs[w], pol);
+            continue;
+        }
+        const bool whole = (g.seglen & 127) == 0;                  // no ragged last group
+#pragma unroll 1
+        for (int w0 = 0; w0 < g.seglen; w0 += 128) {
+            float    c[4];
+            uint32_t bal[4];
+            bool     kf[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int w = w0 + 32 * j + lane;
+                const bool ok = whole || w < g.seglen;
+                c[j]   = ok ? cs[w] : 0.f;
+                kf[j]  = ok && keep_coef(c[j], tf);
+                bal[j] = __ballot_sync(0xffffffffu, kf[j]);
+            }
+            // prel = (flat index of the previous kept coefficient) - (flat index of this group's lane 0)
+            int prel = prev - (fstart + w0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (bal[j] != 0u) {                                    // warp-uniform
+                    const uint32_t lower = bal[j] & lt;
+                    const int pl = lower ? (int)bfind_u32(lower) : prel;   // previous kept, lane units
+                    st_pair_pred(kf[j], out + (pos + __popc(lower)), lane - pl - 1, c[j], pol);
+                    pos += __popc(bal[j]);
+                    prel = (int)bfind_u32(bal[j]);
+                }
+                prel -= 32;
+            }
+            prev = prel + fstart + w0 + 128;
+        }
+    }
+    __syncthreads();   // C and the segment arrays are rewritten by the next unit
+    if (tid == 0 && blockIdx.x < 1024) {
+        long long t5 = clock64();
+        unsigned long long* pc = g_phase_cycles[blockIdx.x];
+        pc[0] += t1 - t0; pc[1] += t2 - t1; pc[2] += t3 - t2; pc[3] += t4 - t3; pc[4] += t5 - t4; pc[5] += 1;
+    }
+}
+
 template <int R, int CAP, int NT>
 __global__ void __launch_bounds__(NT, 1)
 k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
@@ -261,29 +634,28 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                  const u64* __restrict__ global_key, int mode, int* __restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
     typedef FSmem<R, CAP> SM;
-    constexpr int NW = NT / 32;                   // warps per CTA
-    float* const    C      = reinterpret_cast<float*>(smem + SM::C);
-    uint32_t* const g_pk   = reinterpret_cast<uint32_t*>(smem + SM::G);
-    int* const      s_base = reinterpret_cast<int*>(smem + SM::BASE);
-    int* const      s_prev = reinterpret_cast<int*>(smem + SM::PREV);
-    u64* const      s_red  = reinterpret_cast<u64*>(smem + SM::RED);
-    u64* const      xs1    = reinterpret_cast<u64*>(smem + SM::XS1);
-    u64* const      xs2    = reinterpret_cast<u64*>(smem + SM::XS2);
-    int* const      s_next = reinterpret_cast<int*>(smem + SM::RED + 48 * 8);   // C2 work counter
+    FShared S;
+    S.C      = reinterpret_cast<float*>(smem + SM::C);
+    S.g_pk   = reinterpret_cast<uint32_t*>(smem + SM::G);
+    S.s_base = reinterpret_cast<int*>(smem + SM::BASE);
+    S.s_prev = reinterpret_cast<int*>(smem + SM::PREV);
+    S.s_red  = reinterpret_cast<u64*>(smem + SM::RED);
+    S.xs1    = reinterpret_cast<u64*>(smem + SM::XS1);
+    S.xs2    = reinterpret_cast<u64*>(smem + SM::XS2);
+    S.s_next = reinterpret_cast<int*>(smem + SM::RED + 48 * 8);   // C2 work counter
     const uint32_t bars = smem_u32(smem + SM::BARS);
-    const uint32_t xb1 = bars, xb2 = xb1 + 8, xb3 = xb2 + 8;
+    S.xb1 = bars; S.xb2 = bars + 8; S.xb3 = bars + 16;
 
-    const int tid  = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const uint32_t rank = R > 1 ? cluster_ctarank() : 0u;
     const uint32_t cid  = R > 1 ? cluster_id_x() : blockIdx.x;
     const uint32_t ncl  = R > 1 ? nclusters_x() : gridDim.x;
 
     if (R > 1) {
         if (tid == 0) {
-            mbar_init(xb1, R);
-            mbar_init(xb2, R);
-            mbar_init(xb3, R);
+            mbar_init(S.xb1, R);
+            mbar_init(S.xb2, R);
+            mbar_init(S.xb3, R);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
@@ -310,312 +682,34 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
     for (; ui < n_list; ui = ui_next, ui_next = (ui < n_list ? fetch(ui) : n_list)) {
         const int     uid = unit_list[ui];
         const UnitDev u   = units[uid];
-        FGeom g;
-        fused_geom(u.nx, u.ny, u.nz, u.dtype, R, CAP, g);
-        const int b0 = rank * g.nb;
-        const size_t row_bytes = (size_t)g.X * g.es, plane_bytes = row_bytes * g.Y;
-        const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
-        float bp = 0.f, bn = 0.f;                 // running max of +c and of -c
-        bool  nan0 = false;
-        long long t0 = clock64();
-
-        // ---------------- phase A: load, narrow, transform two blocks per thread, store into C -------
-        {
-            const uint32_t m_hx = fdiv_magic(g.hx), m_cq = fdiv_magic(g.ncq);
-            const char* in0 = static_cast<const char*>(u.in) + (size_t)(2 * b0) * row_bytes;
-            const int npc = g.hz >> 1;                         // c-pairs per (a, b)
-            for (int q = tid; q < g.npairs; q += NT) {
-                // slot q -> (cp2 fastest, a, cq, bl): lanes = 2 c-pairs x 16 a  ->  coalesced rows, and
-                // conflict-free 8-byte stores into C (banks 4a + 2cp2 + {0,1})
-                const uint32_t cp2 = q & 1, t1 = q >> 1;
-                const uint32_t t2 = fdiv(t1, m_hx), a = t1 - t2 * g.hx;
-                const uint32_t bl = fdiv(t2, m_cq), cq = t2 - bl * g.ncq;
-                const int cpi = 2 * cq + cp2;                  // c-pair index: blocks c = 2cpi, 2cpi+1
-                if (cpi >= npc) continue;                      // hz/2 odd: the last quad has one pair
-                const char* p0 = in0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes +
-                                 (size_t)a * 2 * g.es;
-                float* cdst = C + a * g.slab + bl * g.Z + 2 * cpi;
-                float v0 = g.es == 8
-                    ? transform_pair<8>(p0, plane_bytes, row_bytes, cdst, o1, o2, o3, bp, bn, pol)
-                    : transform_pair<4>(p0, plane_bytes, row_bytes, cdst, o1, o2, o3, bp, bn, pol);
-                if (q == 0 && rank == 0) nan0 = isnan(v0);     // slot 0 = block (0,0,0): coefficient f = 0
-            }
-        }
-
-        // L2 prefetch of this CTA's slab of its NEXT unit (one contiguous piece per z-plane), issued after
-        // this unit's own loads: the HBM reads of unit u+1 overlap the packing phases of unit u.
+        FPrefetch pf = {nullptr, 0u, 0u, 0};
         if (ui_next < n_list) {
             const UnitDev un = units[unit_list[ui_next]];
-            FGeom gn;
-            fused_geom(un.nx, un.ny, un.nz, un.dtype, R, CAP, gn);
-            const size_t rb = (size_t)gn.X * gn.es, pb = rb * gn.Y;
-            const char* base = static_cast<const char*>(un.in) + (size_t)(2 * rank * gn.nb) * rb;
-            const uint32_t piece = (uint32_t)(2 * gn.nb * rb);              // bytes per z-plane piece
-            const uint32_t lines_per_piece = (piece + 127) / 128;
-            const uint32_t nlines = lines_per_piece * gn.Z;
-            for (uint32_t i = tid; i < nlines; i += NT) {
-                const uint32_t z = i / lines_per_piece, l = i - z * lines_per_piece;
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)z * pb + (size_t)l * 128));
-            }
-        }
-
-        // ---------------- phase B: the threshold ----------------
-        long long t1 = clock64();
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
-            bn = fmaxf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
-        }
-        const bool any_nan0 = __any_sync(0xffffffffu, nan0);
-        if (lane == 0) {
-            // bn >= 0, so its sign bit is free: it carries "the coefficient at f = 0 is NaN"
-            s_red[warp] = ((u64)__float_as_uint(bp) << 32) |
-                          (u64)((__float_as_uint(bn) & 0x7fffffffu) | (any_nan0 ? 0x80000000u : 0u));
-        }
-        __syncthreads();
-        float Mp = 0.f, Mn = 0.f;
-        bool  first_nan = false;
-        {
-            u64 x = lane < NW ? s_red[lane] : 0ull;
-            float p = __uint_as_float((uint32_t)(x >> 32));
-            float n = __uint_as_float((uint32_t)x & 0x7fffffffu);
-            first_nan = __any_sync(0xffffffffu, ((uint32_t)x >> 31) != 0);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
-                n = fmaxf(n, __shfl_xor_sync(0xffffffffu, n, o));
-            }
-            Mp = p; Mn = n;
-        }
-        if (R > 1) {
-            // all-gather (Mp | Mn) over the cluster
-            const uint32_t par = xph1 & 1;
-            if (tid < R) {
-                u64 pay = ((u64)__float_as_uint(Mp) << 32) |
-                          (u64)((__float_as_uint(Mn) & 0x7fffffffu) | (first_nan ? 0x80000000u : 0u));
-                st_cluster_u64(mapa(smem_u32(&xs1[par * 8 + rank]), tid), pay);
-                mbar_arrive_remote(mapa(xb1, tid));
-            }
-            mbar_wait_cluster(xb1, par);
-            ++xph1;
-            float p = 0.f, n = 0.f;
-            bool fn = false;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                u64 x = xs1[par * 8 + r];
-                fn = fn || (((uint32_t)x >> 31) != 0);
-                p  = fmaxf(p, __uint_as_float((uint32_t)(x >> 32)));
-                n  = fmaxf(n, __uint_as_float((uint32_t)x & 0x7fffffffu));
-            }
-            Mp = p; Mn = n; first_nan = fn;
-        }
-        float M = fmaxf(Mp, Mn);
-        uint32_t sign = Mn > Mp ? 1u : 0u;
-        if (Mp == Mn && M != 0.f && !first_nan && mode != FUSED_GIVEN_THRESH) {
-            // +M and -M tie: the FIRST one in f order decides (std::max_element) -> find min f
-            u64 best = ~0ull;
-            const uint32_t m_sl = fdiv_magic(g.seglen);
-            for (int l = tid; l < g.nlocal; l += NT) {
-                uint32_t sg = fdiv(l, m_sl), w = l - sg * g.seglen;
-                float c = C[l + F_PAD * (sg >> 1)];
-                if (fabsf(c) == M) {
-                    uint32_t f = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z + w;
-                    u64 cand = ((u64)f << 1) | (u64)(__float_as_uint(c) >> 31);
-                    best = cand < best ? cand : best;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                u64 x = __shfl_xor_sync(0xffffffffu, best, o);
-                best = x < best ? x : best;
-            }
-            __syncthreads();   // s_red reuse
-            if (lane == 0) s_red[warp] = best;
-            __syncthreads();
-            best = lane < NW ? s_red[lane] : ~0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                u64 x = __shfl_xor_sync(0xffffffffu, best, o);
-                best = x < best ? x : best;
-            }
-            if (R > 1) {
-                const uint32_t par = xph3 & 1;
-                if (tid < R) {
-                    st_cluster_u64(mapa(smem_u32(&xs2[par * 8 + rank]), tid), best);
-                    mbar_arrive_remote(mapa(xb3, tid));
-                }
-                mbar_wait_cluster(xb3, par);
-                ++xph3;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    u64 x = xs2[par * 8 + r];
-                    best = x < best ? x : best;
-                }
-            }
-            sign = (uint32_t)(best & 1ull);
-        }
-        float tf;
-        {
-            u64 key = ((u64)__float_as_uint(M) << 32) | 2ull | (u64)sign;
-            if (mode == FUSED_GIVEN_THRESH) {
-                u64 gk = *global_key;
-                tf = threshold_float(gk & ~(1ull << 63), (gk >> 63) != 0, one_minus_keep);
-            } else {
-                tf = threshold_float(key, first_nan, one_minus_keep);
-            }
-            if (tid == 0 && rank == 0) {
-                states[uid].key      = key;
-                states[uid].flags    = first_nan ? 1 : 0;
-                states[uid].thresh_f = tf;
-            }
-        }
-        if (mode == FUSED_KEYS_ONLY) {
-            __syncthreads();   // C is rewritten by the next unit
-            continue;
-        }
-
-        // ---------------- phase C1: per-segment count and last kept ----------------
-        long long t2 = clock64();
-        const int gpar = R > 1 ? (int)(xph2 & 1) : 0;
-        uint32_t* const my_pk = g_pk + gpar * SM::MAXG;
-        for (int sg = warp; sg < g.nseg; sg += NW) {
-            const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);   // 16-byte aligned
-            int cnt = 0, lb = 0;
-            uint32_t lm = 0;
-            for (int w = lane * 4; w < g.seglen; w += 128) {           // seglen % 4 == 0
-                const float4 c = *reinterpret_cast<const float4*>(cs + w);
-                uint32_t m = (keep_coef(c.x, tf) ? 1u : 0u) | (keep_coef(c.y, tf) ? 2u : 0u) |
-                             (keep_coef(c.z, tf) ? 4u : 0u) | (keep_coef(c.w, tf) ? 8u : 0u);
-                cnt += __popc(m);
-                if (m) { lb = w; lm = m; }
-            }
-            int last = lm ? lb + 31 - __clz(lm) : -1;
-            cnt  = __reduce_add_sync(0xffffffffu, cnt);
-            last = __reduce_max_sync(0xffffffffu, last);
-            const uint32_t pk = ((uint32_t)cnt << 16) | ((uint32_t)last & 0xffffu);
+            const size_t rb = (size_t)un.nx * (un.dtype == WC_F64 ? 8 : 4), pb = rb * un.ny;
             if (R == 1) {
-                if (lane == 0) my_pk[sg] = pk;
-            } else if (lane < R) {
-                st_cluster_u32(mapa(smem_u32(&my_pk[sg * R + rank]), lane), pk);
+                pf.base = static_cast<const char*>(un.in);
+                pf.piece_lines = (uint32_t)((pb * un.nz + 127) / 128);
+                pf.nplanes = 1;
+            } else {
+                const int nbn = (un.ny / 2) / R;
+                pf.base = static_cast<const char*>(un.in) + (size_t)(2 * rank * nbn) * rb;
+                pf.piece_lines = (uint32_t)((2 * nbn * rb + 127) / 128);
+                pf.nplanes = un.nz;
+                pf.pitch = pb;
             }
         }
-        long long t3 = clock64();
-        if (R > 1) {
-            fence_cluster();
-            __syncthreads();
-            if (tid < R) mbar_arrive_remote(mapa(xb2, tid));
-            mbar_wait_cluster(xb2, gpar);
-            ++xph2;
+#define WC_FC_UNIT(GEOM) fc_unit<R, CAP, NT>(GEOM, u, uid, S, pf, rank, xph1, xph2, xph3, states, \
+                                             one_minus_keep, global_key, mode, pol, lt)
+        constexpr int CUBE = R == 1 ? 32 : 64;     // the cube this variant is specialised for
+        if (u.nx == CUBE && u.ny == CUBE && u.nz == CUBE) {
+            if (u.dtype == WC_F64) WC_FC_UNIT((SGeom<CUBE, CUBE, CUBE, 8, R>()));
+            else                   WC_FC_UNIT((SGeom<CUBE, CUBE, CUBE, 4, R>()));
         } else {
-            __syncthreads();
+            FGeom g;
+            fused_geom(u.nx, u.ny, u.nz, u.dtype, R, CAP, g);
+            WC_FC_UNIT(g);
         }
-
-        // ---------------- scan over the segments in global order ----------------
-        {
-            constexpr int EPT = (SM::MAXG + NT - 1) / NT;   // entries per thread
-            const int NG = g.nseg * R;                      // <= MAXG, entry e = sg * R + r
-            int cv[EPT], lv[EPT];
-            int isum = 0, imax = -1;
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                const int e = tid * EPT + j;
-                cv[j] = 0; lv[j] = -1;
-                if (e < NG) {
-                    const uint32_t pk = my_pk[e];
-                    const int sg = e / R, r = e % R;
-                    cv[j] = (int)(pk >> 16);
-                    if ((pk & 0xffffu) != 0xffffu)
-                        lv[j] = ((sg >> 1) * g.Y + (sg & 1) * g.hy + r * g.nb) * g.Z + (int)(pk & 0xffffu);
-                }
-                isum += cv[j];
-                imax = max(imax, lv[j]);
-            }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int ps = __shfl_up_sync(0xffffffffu, isum, o);
-                int pm = __shfl_up_sync(0xffffffffu, imax, o);
-                if (lane >= o) { isum += ps; imax = max(imax, pm); }
-            }
-            int* sr = reinterpret_cast<int*>(s_red);
-            if (lane == 31) { sr[warp] = isum; sr[32 + warp] = imax; }
-            __syncthreads();
-            int wsum = 0, wmax = -1, total = 0;
-#pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                int xs = sr[i], xm = sr[32 + i];
-                if (i < warp) { wsum += xs; wmax = max(wmax, xm); }
-                total += xs;
-            }
-            int es = __shfl_up_sync(0xffffffffu, isum, 1);
-            int em = __shfl_up_sync(0xffffffffu, imax, 1);
-            if (lane == 0) { es = 0; em = -1; }
-            es += wsum;
-            em = max(em, wmax);
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {                 // exclusive prefix in front of entry e
-                const int e = tid * EPT + j;
-                if (e < NG && (R == 1 || (e % R) == (int)rank)) { s_base[e / R] = es; s_prev[e / R] = em; }
-                es += cv[j];
-                em = max(em, lv[j]);
-            }
-            if (tid == 0 && rank == 0) states[uid].npairs = total;
-            if (tid == 0) *s_next = 0;
-            __syncthreads();
-        }
-
-        // ---------------- phase C2: emit (run, value) pairs ----------------
-        // Segments are handed out dynamically (shared-memory counter): their cost ranges from nothing
-        // (detail bands below the threshold) to a full copy, and a static round-robin left half of the
-        // warps idle at the closing barrier.
-        long long t4 = clock64();
-        for (;;) {
-            int sg = 0;
-            if (lane == 0) sg = atomicAdd(s_next, 1);
-            sg = __shfl_sync(0xffffffffu, sg, 0);
-            if (sg >= g.nseg) break;
-            const int scnt = (int)(my_pk[sg * R + rank] >> 16);
-            if (scnt == 0) continue;                                   // nothing kept in this segment
-            const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);
-            const int fstart = ((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z;
-            uint32_t pos = (uint32_t)s_base[sg];
-            int prev = s_prev[sg];
-            int2* const out = reinterpret_cast<int2*>(u.out);
-            if (scnt == g.seglen) {
-                // every coefficient kept (e.g. a negative max, SURVEY.md D3'): runs are 0, ranks are w
-                for (int w = lane; w < g.seglen; w += 32)
-                    st_pair_pred(true, out + (pos + (uint32_t)w), w == 0 ? fstart - prev - 1 : 0, cs[w], pol);
-                continue;
-            }
-            for (int w0 = 0; w0 < g.seglen; w0 += 128) {
-                float    c[4];
-                uint32_t bal[4];
-                bool     kf[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int w = w0 + 32 * j + lane;
-                    const bool ok = w < g.seglen;
-                    c[j]   = ok ? cs[w] : 0.f;
-                    kf[j]  = ok && keep_coef(c[j], tf);
-                    bal[j] = __ballot_sync(0xffffffffu, kf[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (bal[j] == 0u) continue;                        // warp-uniform
-                    const int f0 = fstart + w0 + 32 * j;
-                    const uint32_t lower = bal[j] & lt;
-                    const int pf = lower ? f0 + 31 - __clz(lower) : prev;
-                    st_pair_pred(kf[j], out + (pos + __popc(lower)), f0 + lane - pf - 1, c[j], pol);
-                    pos += __popc(bal[j]);
-                    prev = f0 + 31 - __clz(bal[j]);
-                }
-            }
-        }
-        __syncthreads();   // C and the segment arrays are rewritten by the next unit
-        if (tid == 0 && blockIdx.x < 1024) {
-            long long t5 = clock64();
-            unsigned long long* pc = g_phase_cycles[blockIdx.x];
-            pc[0] += t1 - t0; pc[1] += t2 - t1; pc[2] += t3 - t2; pc[3] += t4 - t3; pc[4] += t5 - t4; pc[5] += 1;
-        }
+#undef WC_FC_UNIT
     }
     if (R > 1) cluster_sync_all();   // no CTA may exit while peers can still write into its smem
 }
