@@ -298,8 +298,8 @@ def main():
     is64 = ncoef == 64 ** 3
     alg_all = int((8 * ncoef + 8 * npairs + 20).sum())
     alg_by_kernel = {
-        "k_fused_compress<1>": int((8 * ncoef[is32] + 8 * npairs[is32] + 20).sum()),
-        "k_fused_compress<8>": int((8 * ncoef[is64] + 8 * npairs[is64] + 20).sum()),
+        "k_fused_compress<1,cube32>": int((8 * ncoef[is32] + 8 * npairs[is32] + 20).sum()),
+        "k_fused_compress<8,cube64>": int((8 * ncoef[is64] + 8 * npairs[is64] + 20).sum()),
         "k_forward_generic": int((8 * ncoef).sum()),          # reads the f64 input once (writes 4N scratch)
         "k_emit_tiles": int((8 * npairs).sum()),
         "k_count_tiles": 0,

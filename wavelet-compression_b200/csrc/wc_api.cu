@@ -110,22 +110,28 @@ struct wc_ctx {
     DevBuf       d_counter;
 };
 
+// Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
+// stream), then the single-CTA kernels (second stream when both kinds are present).
+enum { FL_N = 4 };
+static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_CUBE32, FUSED_CLS_R1};
+static inline bool fl_is_cluster(int k) { return k < 2; }
+
 struct wc_plan {
     wc_ctx* ctx      = nullptr;
     int     n_units  = 0;
     int     in_space = WC_DEVICE;
     std::vector<wc_box_desc> units;
     std::vector<UnitDev>     h_units;
-    std::vector<int>         fused1, fused2, fused8, generic; // unit ids per path
+    // unit ids per path: fl[k] = the fused class FL_CLASS[k] (ascending ids), generic = the rest
+    std::vector<int>         fl[FL_N], generic;
     long long total_n = 0;     // sum of ncoef
     size_t    in_bytes = 0;    // sum of input bytes
     // device memory
     DevBuf d_units, d_states, d_in, d_out, d_coef, d_xtiles, d_ctiles, d_tile_i, d_gkey,
-        d_offsets, d_dense, d_f1, d_f2, d_f8, d_dec_units, d_inv_units, d_inv_tiles, d_ptiles, d_psum,
+        d_offsets, d_dense, d_fl[FL_N], d_dec_units, d_inv_units, d_inv_tiles, d_ptiles, d_psum,
         d_err, d_rmse_units, d_rmse_sum, d_rmse, d_stage_out;
     PinBuf h_states, h_dense, h_misc;
     int    n_xtiles = 0, n_ctiles = 0;
-    int    n_f1 = 0, n_f2 = 0, n_f8 = 0;
     bool   compressed = false;
     bool   transformed = false;
     std::vector<size_t> in_dev_off; // per unit offset in d_in (host inputs)
@@ -442,9 +448,10 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
             return WC_ERR_BAD_DIMS;
         }
         if (n == 0) cls = -1; // nothing to do: K = 0
-        if (cls == 1) p->fused1.push_back(i);
-        else if (cls == 2) p->fused2.push_back(i);
-        else if (cls == 8) p->fused8.push_back(i);
+        int fk = -1;
+        for (int k = 0; k < FL_N; ++k)
+            if (cls == FL_CLASS[k]) fk = k;
+        if (fk >= 0) p->fl[fk].push_back(i);
         else if (cls == 0) {
             p->generic.push_back(i);
             coef_off[i] = coef_floats;
@@ -499,26 +506,12 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
                                  cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
             return fail(e, "ctiles upload");
     // fused work lists
-    p->n_f1 = (int)p->fused1.size();
-    p->n_f8 = (int)p->fused8.size();
-    p->n_f2 = (int)p->fused2.size();
-    if (p->n_f2) {
-        PLAN_RESERVE(p->d_f2, sizeof(int) * p->n_f2);
-        if ((e = cudaMemcpyAsync(p->d_f2.p, p->fused2.data(), sizeof(int) * p->n_f2,
+    for (int k = 0; k < FL_N; ++k) {
+        if (p->fl[k].empty()) continue;
+        PLAN_RESERVE(p->d_fl[k], sizeof(int) * p->fl[k].size());
+        if ((e = cudaMemcpyAsync(p->d_fl[k].p, p->fl[k].data(), sizeof(int) * p->fl[k].size(),
                                  cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
-            return fail(e, "fused2 upload");
-    }
-    if (p->n_f1) {
-        PLAN_RESERVE(p->d_f1, sizeof(int) * p->n_f1);
-        if ((e = cudaMemcpyAsync(p->d_f1.p, p->fused1.data(), sizeof(int) * p->n_f1,
-                                 cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
-            return fail(e, "fused1 upload");
-    }
-    if (p->n_f8) {
-        PLAN_RESERVE(p->d_f8, sizeof(int) * p->n_f8);
-        if ((e = cudaMemcpyAsync(p->d_f8.p, p->fused8.data(), sizeof(int) * p->n_f8,
-                                 cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
-            return fail(e, "fused8 upload");
+            return fail(e, "fused list upload");
     }
 #undef PLAN_RESERVE
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "plan sync");
@@ -532,8 +525,8 @@ int wc_plan_destroy(wc_plan* p) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &p->d_units, &p->d_states, &p->d_in, &p->d_out, &p->d_coef, &p->d_xtiles,
-                       &p->d_ctiles, &p->d_tile_i, &p->d_gkey, &p->d_offsets, &p->d_dense, &p->d_f1,
-                       &p->d_f2, &p->d_f8, &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
+                       &p->d_ctiles, &p->d_tile_i, &p->d_gkey, &p->d_offsets, &p->d_dense, &p->d_fl[0],
+                       &p->d_fl[1], &p->d_fl[2], &p->d_fl[3], &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
                        &p->d_psum, &p->d_err, &p->d_rmse_units, &p->d_rmse_sum, &p->d_rmse,
                        &p->d_stage_out };
     for (DevBuf* b : bufs) b->release();
@@ -607,21 +600,12 @@ static int plan_forward(wc_plan* p, bool global_mode) {
                                          p->d_xtiles.as<int2>(), p->n_xtiles, ctx->stream,
                                          &ctx->ls));
     if (global_mode) {
-        if (p->n_f1)
-            CTX_CUDA(ctx, launch_fused_compress(1, FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
-                                                p->d_states.as<UnitState>(), p->d_f1.as<int>(),
-                                                p->n_f1, 0.0, nullptr, ctx->sm_count, ctx->stream,
-                                                &ctx->ls));
-        if (p->n_f2)
-            CTX_CUDA(ctx, launch_fused_compress(2, FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
-                                                p->d_states.as<UnitState>(), p->d_f2.as<int>(),
-                                                p->n_f2, 0.0, nullptr, ctx->sm_count, ctx->stream,
-                                                &ctx->ls));
-        if (p->n_f8)
-            CTX_CUDA(ctx, launch_fused_compress(8, FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
-                                                p->d_states.as<UnitState>(), p->d_f8.as<int>(),
-                                                p->n_f8, 0.0, nullptr, ctx->sm_count, ctx->stream,
-                                                &ctx->ls));
+        for (int k = 0; k < FL_N; ++k)
+            if (!p->fl[k].empty())
+                CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
+                                                    p->d_states.as<UnitState>(), p->d_fl[k].as<int>(),
+                                                    (int)p->fl[k].size(), 0.0, nullptr, ctx->sm_count,
+                                                    ctx->stream, &ctx->ls));
     }
     return WC_OK;
 }
@@ -648,7 +632,10 @@ static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
     // SMs on B200).  When a step has both classes, the single-CTA kernel runs concurrently on a second
     // stream with dynamic unit hand-out and back-fills the idle SMs.  (Serialised while per-kernel event
     // profiling is on, so each kernel is timed alone.)
-    const bool overlap = p->n_f1 > 0 && p->n_f8 > 0 && !ctx->ls.profile && ctx->opt_overlap;
+    bool any_cluster = false, any_single = false;
+    for (int k = 0; k < FL_N; ++k)
+        if (!p->fl[k].empty()) (fl_is_cluster(k) ? any_cluster : any_single) = true;
+    const bool overlap = any_cluster && any_single && !ctx->ls.profile && ctx->opt_overlap;
     if (overlap) {
         if (!p->s_aux) {
             CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
@@ -656,36 +643,23 @@ static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
             CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
             CTX_CUDA(ctx, p->d_counter.reserve(64));
         }
-        CTX_CUDA(ctx, cudaMemsetAsync(p->d_counter.p, 0, 4, ctx->stream));
+        CTX_CUDA(ctx, cudaMemsetAsync(p->d_counter.p, 0, 4 * FL_N, ctx->stream));
         CTX_CUDA(ctx, cudaEventRecord(p->ev_fork, ctx->stream));
         CTX_CUDA(ctx, cudaStreamWaitEvent(p->s_aux, p->ev_fork, 0));
-        CTX_CUDA(ctx, launch_fused_compress(8, mode, p->d_units.as<UnitDev>(),
-                                            p->d_states.as<UnitState>(), p->d_f8.as<int>(), p->n_f8,
-                                            omk, global_key_dev, ctx->sm_count, ctx->stream, &ctx->ls));
-        CTX_CUDA(ctx, launch_fused_compress(1, mode, p->d_units.as<UnitDev>(),
-                                            p->d_states.as<UnitState>(), p->d_f1.as<int>(), p->n_f1,
-                                            omk, global_key_dev, ctx->sm_count, p->s_aux, &ctx->ls,
-                                            p->d_counter.as<int>()));
+    }
+    for (int k = 0; k < FL_N; ++k) {
+        if (p->fl[k].empty()) continue;
+        const bool aux = overlap && !fl_is_cluster(k);
+        CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], mode, p->d_units.as<UnitDev>(),
+                                            p->d_states.as<UnitState>(), p->d_fl[k].as<int>(),
+                                            (int)p->fl[k].size(), omk, global_key_dev, ctx->sm_count,
+                                            aux ? p->s_aux : ctx->stream, &ctx->ls,
+                                            aux ? p->d_counter.as<int>() + k : nullptr));
+    }
+    if (overlap) {
         CTX_CUDA(ctx, cudaEventRecord(p->ev_join, p->s_aux));
         CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->ev_join, 0));
-        p->compressed = true;
-        return WC_OK;
     }
-    if (p->n_f1)
-        CTX_CUDA(ctx, launch_fused_compress(1, mode, p->d_units.as<UnitDev>(),
-                                            p->d_states.as<UnitState>(), p->d_f1.as<int>(), p->n_f1,
-                                            omk, global_key_dev, ctx->sm_count, ctx->stream,
-                                            &ctx->ls));
-    if (p->n_f2)
-        CTX_CUDA(ctx, launch_fused_compress(2, mode, p->d_units.as<UnitDev>(),
-                                            p->d_states.as<UnitState>(), p->d_f2.as<int>(), p->n_f2,
-                                            omk, global_key_dev, ctx->sm_count, ctx->stream,
-                                            &ctx->ls));
-    if (p->n_f8)
-        CTX_CUDA(ctx, launch_fused_compress(8, mode, p->d_units.as<UnitDev>(),
-                                            p->d_states.as<UnitState>(), p->d_f8.as<int>(), p->n_f8,
-                                            omk, global_key_dev, ctx->sm_count, ctx->stream,
-                                            &ctx->ls));
     p->compressed = true;
     return WC_OK;
 }
@@ -845,7 +819,7 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
     CTX_CUDA(ctx, cudaMemsetAsync(p->d_states.p, 0, sizeof(UnitState) * p->n_units, ctx->stream));
     CTX_CUDA(ctx, cudaEventRecord(p->ev[3 * NCH], ctx->stream));
     CTX_CUDA(ctx, cudaStreamWaitEvent(p->s_h2d, p->ev[3 * NCH], 0));
-    size_t i1 = 0, i8 = 0;
+    size_t fi[FL_N] = {};
     long long done_total = 0;
     auto finish_chunk = [&](int c, long long& prev_total) -> int {
         // host learns the running total of chunk c, then enqueues its D2H
@@ -883,18 +857,16 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
         CTX_CUDA(ctx, cudaEventRecord(p->ev[c], p->s_h2d));
         // compute on the ctx stream
         CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->ev[c], 0));
-        size_t j1 = i1, j8 = i8;
-        while (j1 < p->fused1.size() && p->fused1[j1] < u1) ++j1;
-        while (j8 < p->fused8.size() && p->fused8[j8] < u1) ++j8;
-        if (j1 > i1)
-            CTX_CUDA(ctx, launch_fused_compress(1, FUSED_FULL, p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
-                                                p->d_f1.as<int>() + i1, (int)(j1 - i1), omk, nullptr, ctx->sm_count,
-                                                ctx->stream, &ctx->ls));
-        if (j8 > i8)
-            CTX_CUDA(ctx, launch_fused_compress(8, FUSED_FULL, p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
-                                                p->d_f8.as<int>() + i8, (int)(j8 - i8), omk, nullptr, ctx->sm_count,
-                                                ctx->stream, &ctx->ls));
-        i1 = j1; i8 = j8;
+        for (int k = 0; k < FL_N; ++k) {
+            size_t j = fi[k];
+            while (j < p->fl[k].size() && p->fl[k][j] < u1) ++j;
+            if (j > fi[k])
+                CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], FUSED_FULL, p->d_units.as<UnitDev>(),
+                                                    p->d_states.as<UnitState>(), p->d_fl[k].as<int>() + fi[k],
+                                                    (int)(j - fi[k]), omk, nullptr, ctx->sm_count, ctx->stream,
+                                                    &ctx->ls));
+            fi[k] = j;
+        }
         if (u1 > u0) {
             CTX_CUDA(ctx, launch_gather_dense(p->d_units.as<UnitDev>() + u0, p->d_states.as<UnitState>() + u0, u1 - u0,
                                               p->d_offsets.as<long long>() + u0 + c, nullptr, true, ctx->stream, &ctx->ls,

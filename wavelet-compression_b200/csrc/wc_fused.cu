@@ -21,6 +21,7 @@
 //   "Fused compress v2"); with C taking 128 KB of the SM's shared memory the ring was too shallow to
 //   cover the TMA round trip and it measured slower than direct loads + L2 prefetch.
 #include <cstdio>
+#include <type_traits>
 
 #include "wc_common.cuh"
 #include "wc_fused.h"
@@ -35,9 +36,6 @@ constexpr int F_PAD    = 4;      // padding words per i' slab of C (keeps float4
                                  // the a-lanes of a warp hit banks 4a + 2cp + {0,1})
 constexpr int F_CPAD   = 256;    // total padding words of C (F_PAD * X, X <= 64)
 constexpr int F_MAXSEG = 128;    // segments (2*X) per CTA
-#ifndef WC_NT1
-#define WC_NT1 512
-#endif
 
 template <int R, int CAP>
 struct FSmem {
@@ -103,9 +101,11 @@ __host__ __device__ inline bool fused_geom(int X, int Y, int Z, int dtype, int R
 int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
     if (reinterpret_cast<uintptr_t>(ptr) & 15u) return 0;
     FGeom g;
-    if (fused_geom(nx, ny, nz, dtype, 1, 32768, g)) return 1;
-    if (fused_geom(nx, ny, nz, dtype, 8, 32768, g)) return 8;
-    return 0;
+    if (nx == 32 && ny == 32 && nz == 32) return FUSED_CLS_CUBE32;
+    if (nx == 64 && ny == 64 && nz == 64) return FUSED_CLS_CUBE64;
+    if (fused_geom(nx, ny, nz, dtype, 1, 32768, g)) return FUSED_CLS_R1;
+    if (fused_geom(nx, ny, nz, dtype, 8, 32768, g)) return FUSED_CLS_R8;
+    return FUSED_CLS_NONE;
 }
 bool fused_decode_available() { return true; }
 
@@ -191,6 +191,9 @@ __device__ __forceinline__ float2 ldg_stream_f32x2(const void* p, u64 pol) {
                  : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
     return v;
 }
+template <class T> __device__ __forceinline__ T ldg_stream(const void* p, u64 pol);
+template <> __device__ __forceinline__ double2 ldg_stream<double2>(const void* p, u64 pol) { return ldg_stream_f64x2(p, pol); }
+template <> __device__ __forceinline__ float2  ldg_stream<float2>(const void* p, u64 pol) { return ldg_stream_f32x2(p, pol); }
 __device__ __forceinline__ void st_pair_pred(bool p, int2* addr, int run, float val, u64 pol) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
@@ -217,45 +220,48 @@ __device__ __forceinline__ void haar_pair2(float2& lo, float2& hi) {
     hi = __fmul2_rn(d, half);
 }
 
-// Loads the two c-adjacent 2x2x2 blocks whose first cell is at `p0` (4 z-planes x 2 rows x one (x,x+1)
-// pair each, straight from global memory / L2, 16-byte vector loads), transforms both at once and stores
-// the 8 x 2 coefficients into C.  v[zi*4+yi*2+xi] = (block c, block c+1).
+// Phase A works on the two c-adjacent 2x2x2 blocks whose first cell is at `p0`: 4 z-planes x 2 rows x one
+// (x,x+1) pair each, straight from global memory / L2 with 16-byte (f64) or 8-byte (f32) vector loads.
+// It is split in two so that the loop can issue the loads of slot q+NT right after narrowing slot q
+// (the raw registers are free from that point on) and run the transform of slot q under their latency.
+template <int ES> struct RawPair;
+template <> struct RawPair<8> { double2 d[8]; };
+template <> struct RawPair<4> { float2 d[8]; };
+
 template <int ES>
-__device__ __forceinline__ float transform_pair(const char* p0, size_t plane_bytes, size_t row_bytes,
-                                                float* cdst, int o1, int o2, int o3, float& bp, float& bn,
-                                                u64 pol) {
-    float2 v[8];
-    if (ES == 8) {
-        double2 d[8];
+__device__ __forceinline__ void load_pair(RawPair<ES>& r, const char* p0, size_t plane_bytes, size_t row_bytes,
+                                          u64 pol) {
 #pragma unroll
-        for (int pl = 0; pl < 4; ++pl)
+    for (int pl = 0; pl < 4; ++pl)
 #pragma unroll
-            for (int yi = 0; yi < 2; ++yi)
-                d[pl * 2 + yi] = ldg_stream_f64x2(p0 + pl * plane_bytes + yi * row_bytes, pol);
+        for (int yi = 0; yi < 2; ++yi) {
+            if (ES == 8) r.d[pl * 2 + yi] = ldg_stream<typename std::remove_reference<decltype(r.d[0])>::type>(p0 + pl * plane_bytes + yi * row_bytes, pol);
+            else         r.d[pl * 2 + yi] = ldg_stream<typename std::remove_reference<decltype(r.d[0])>::type>(p0 + pl * plane_bytes + yi * row_bytes, pol);
+        }
+}
+// v[zi*4+yi*2+xi] = (block c, block c+1), narrowed as src/preprocess.cpp:78 does
+__device__ __forceinline__ void narrow_pair(const RawPair<8>& r, float2 v[8]) {
 #pragma unroll
-        for (int zi = 0; zi < 2; ++zi)
+    for (int zi = 0; zi < 2; ++zi)
 #pragma unroll
-            for (int yi = 0; yi < 2; ++yi) {
-                const double2 da = d[zi * 2 + yi], db = d[(zi + 2) * 2 + yi];
-                v[zi * 4 + yi * 2]     = make_float2(__double2float_rn(da.x), __double2float_rn(db.x)); // src/preprocess.cpp:78
-                v[zi * 4 + yi * 2 + 1] = make_float2(__double2float_rn(da.y), __double2float_rn(db.y));
-            }
-    } else {
-        float2 d[8];
+        for (int yi = 0; yi < 2; ++yi) {
+            const double2 da = r.d[zi * 2 + yi], db = r.d[(zi + 2) * 2 + yi];
+            v[zi * 4 + yi * 2]     = make_float2(__double2float_rn(da.x), __double2float_rn(db.x));
+            v[zi * 4 + yi * 2 + 1] = make_float2(__double2float_rn(da.y), __double2float_rn(db.y));
+        }
+}
+__device__ __forceinline__ void narrow_pair(const RawPair<4>& r, float2 v[8]) {
 #pragma unroll
-        for (int pl = 0; pl < 4; ++pl)
+    for (int zi = 0; zi < 2; ++zi)
 #pragma unroll
-            for (int yi = 0; yi < 2; ++yi)
-                d[pl * 2 + yi] = ldg_stream_f32x2(p0 + pl * plane_bytes + yi * row_bytes, pol);
-#pragma unroll
-        for (int zi = 0; zi < 2; ++zi)
-#pragma unroll
-            for (int yi = 0; yi < 2; ++yi) {
-                const float2 fa = d[zi * 2 + yi], fb = d[(zi + 2) * 2 + yi];
-                v[zi * 4 + yi * 2]     = make_float2(fa.x, fb.x);
-                v[zi * 4 + yi * 2 + 1] = make_float2(fa.y, fb.y);
-            }
-    }
+        for (int yi = 0; yi < 2; ++yi) {
+            const float2 fa = r.d[zi * 2 + yi], fb = r.d[(zi + 2) * 2 + yi];
+            v[zi * 4 + yi * 2]     = make_float2(fa.x, fb.x);
+            v[zi * 4 + yi * 2 + 1] = make_float2(fa.y, fb.y);
+        }
+}
+// Transforms both blocks at once and stores the 8 x 2 coefficients into C.
+__device__ __forceinline__ void finish_pair(float2 v[8], float* cdst, int o1, int o2, int o3, float& bp, float& bn) {
     // Z, then Y, then X (src/compressor.cpp:98-175)
 #pragma unroll
     for (int q = 0; q < 4; ++q) haar_pair2(v[q], v[4 + q]);
@@ -272,7 +278,62 @@ __device__ __forceinline__ float transform_pair(const char* p0, size_t plane_byt
         bp = fmaxf(fmaxf(bp, v[o].x), v[o].y);
         bn = fmaxf(fmaxf(bn, -v[o].x), -v[o].y);
     }
-    return v[0].x;
+}
+
+// Phase A of one CTA: every thread takes the slots q = tid, tid + NT, ... of its y-slab.
+//   slot q -> (cp2 fastest, a, cq, bl): the lanes of a warp are 2 c-pairs x 16 a  ->  coalesced rows, and
+//   conflict-free 8-byte stores into C (banks 4a + 2cp2 + {0,1}).
+// With literal geometry the trip count is a constant: the loop is fully unrolled and the loads of slot
+// i+1 are issued between the narrowing and the transform of slot i (software pipeline without extra
+// registers, and without a branch ptxas could hoist the math over).
+template <int NT, int ES, class G>
+__device__ __forceinline__ void phase_a(const G& g, const char* in0, float* C, uint32_t rank, u64 pol,
+                                        float& bp, float& bn, bool& nan0) {
+    const int tid = threadIdx.x;
+    const size_t row_bytes = (size_t)g.X * g.es, plane_bytes = row_bytes * g.Y;
+    const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
+    const uint32_t m_hx = G::is_static ? 0u : fdiv_magic(g.hx), m_cq = G::is_static ? 0u : fdiv_magic(g.ncq);
+    const int npc = g.hz >> 1;                         // c-pairs per (a, b)
+    auto decode = [&](int q, const char*& p0, float*& cdst) -> bool {
+        const uint32_t cp2 = q & 1, t1 = q >> 1;
+        const uint32_t t2 = G::is_static ? t1 / (uint32_t)g.hx : fdiv(t1, m_hx), a = t1 - t2 * g.hx;
+        const uint32_t bl = G::is_static ? t2 / (uint32_t)g.ncq : fdiv(t2, m_cq), cq = t2 - bl * g.ncq;
+        const int cpi = 2 * cq + cp2;                  // c-pair index: blocks c = 2cpi, 2cpi+1
+        p0   = in0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes + (size_t)a * 2 * g.es;
+        cdst = C + a * g.slab + bl * g.Z + 2 * cpi;
+        return !(npc & 1) || cpi < npc;                // hz/2 odd: the last quad has one pair
+    };
+    RawPair<ES> raw;
+    const char* p0;
+    float*      cdst;
+    if constexpr (G::is_static) {
+        static_assert(G::npairs % NT == 0 && (G::hz / 2) % 2 == 0, "literal geometries fill every slot");
+        constexpr int NIT = G::npairs / NT;
+        decode(tid, p0, cdst);
+        load_pair<ES>(raw, p0, plane_bytes, row_bytes, pol);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            float2 v[8];
+            narrow_pair(raw, v);
+            float* const cd = cdst;
+            if (it + 1 < NIT) {
+                decode(tid + (it + 1) * NT, p0, cdst);
+                load_pair<ES>(raw, p0, plane_bytes, row_bytes, pol);
+            }
+            finish_pair(v, cd, o1, o2, o3, bp, bn);
+            if (it == 0 && tid == 0 && rank == 0) nan0 = isnan(v[0].x);   // block (0,0,0): coefficient f = 0
+        }
+    } else {
+#pragma unroll 1
+        for (int q = tid; q < g.npairs; q += NT) {
+            if (!decode(q, p0, cdst)) continue;
+            float2 v[8];
+            load_pair<ES>(raw, p0, plane_bytes, row_bytes, pol);
+            narrow_pair(raw, v);
+            finish_pair(v, cdst, o1, o2, o3, bp, bn);
+            if (q == 0 && rank == 0) nan0 = isnan(v[0].x);
+        }
+    }
 }
 
 // Everything the per-unit body needs from the kernel frame (all scalarised after inlining).
@@ -308,34 +369,16 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     float* const C = S.C;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b0 = rank * g.nb;
-    const size_t row_bytes = (size_t)g.X * g.es, plane_bytes = row_bytes * g.Y;
-    const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
+    const size_t row_bytes = (size_t)g.X * g.es;
     float bp = 0.f, bn = 0.f;                 // running max of +c and of -c
     bool  nan0 = false;
     long long t0 = clock64();
 
     // ---------------- phase A: load, narrow, transform two blocks per thread, store into C -------
     {
-        const uint32_t m_hx = G::is_static ? 0u : fdiv_magic(g.hx), m_cq = G::is_static ? 0u : fdiv_magic(g.ncq);
         const char* in0 = static_cast<const char*>(u.in) + (size_t)(2 * b0) * row_bytes;
-        const int npc = g.hz >> 1;                         // c-pairs per (a, b)
-#pragma unroll 1
-        for (int q = tid; q < g.npairs; q += NT) {
-            // slot q -> (cp2 fastest, a, cq, bl): lanes = 2 c-pairs x 16 a  ->  coalesced rows, and
-            // conflict-free 8-byte stores into C (banks 4a + 2cp2 + {0,1})
-            const uint32_t cp2 = q & 1, t1 = q >> 1;
-            const uint32_t t2 = G::is_static ? t1 / (uint32_t)g.hx : fdiv(t1, m_hx), a = t1 - t2 * g.hx;
-            const uint32_t bl = G::is_static ? t2 / (uint32_t)g.ncq : fdiv(t2, m_cq), cq = t2 - bl * g.ncq;
-            const int cpi = 2 * cq + cp2;                  // c-pair index: blocks c = 2cpi, 2cpi+1
-            if ((npc & 1) && cpi >= npc) continue;         // hz/2 odd: the last quad has one pair
-            const char* p0 = in0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes +
-                             (size_t)a * 2 * g.es;
-            float* cdst = C + a * g.slab + bl * g.Z + 2 * cpi;
-            float v0 = g.es == 8
-                ? transform_pair<8>(p0, plane_bytes, row_bytes, cdst, o1, o2, o3, bp, bn, pol)
-                : transform_pair<4>(p0, plane_bytes, row_bytes, cdst, o1, o2, o3, bp, bn, pol);
-            if (q == 0 && rank == 0) nan0 = isnan(v0);     // slot 0 = block (0,0,0): coefficient f = 0
-        }
+        if (g.es == 8) phase_a<NT, 8>(g, in0, C, rank, pol, bp, bn, nan0);
+        else           phase_a<NT, 4>(g, in0, C, rank, pol, bp, bn, nan0);
     }
 
     // L2 prefetch of this CTA's slab of its NEXT unit, issued after this unit's own loads: the HBM reads
@@ -476,16 +519,30 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
 #pragma unroll 1
     for (int sg = warp; sg < g.nseg; sg += NW) {
         const float* cs = C + sg * g.seglen + F_PAD * (sg >> 1);   // 16-byte aligned
-        int cnt = 0, lb = 0;
+        // 512 coefficients per round: four float4 per lane, one 16-bit keep mask, one POPC
+        const bool whole512 = (g.seglen & 511) == 0;
+        int cnt = 0, lw = 0;
         uint32_t lm = 0;
-        for (int w = lane * 4; w < g.seglen; w += 128) {           // seglen % 4 == 0
-            const float4 c = *reinterpret_cast<const float4*>(cs + w);
-            uint32_t m = (keep_coef(c.x, tf) ? 1u : 0u) | (keep_coef(c.y, tf) ? 2u : 0u) |
-                         (keep_coef(c.z, tf) ? 4u : 0u) | (keep_coef(c.w, tf) ? 8u : 0u);
+#pragma unroll 1
+        for (int w0 = lane * 4; w0 < g.seglen; w0 += 512) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int w = w0 + 128 * it;
+                if (whole512 || w < g.seglen) {                      // seglen % 4 == 0
+                    const float4 c = *reinterpret_cast<const float4*>(cs + w);
+                    m |= ((keep_coef(c.x, tf) ? 1u : 0u) | (keep_coef(c.y, tf) ? 2u : 0u) |
+                          (keep_coef(c.z, tf) ? 4u : 0u) | (keep_coef(c.w, tf) ? 8u : 0u)) << (4 * it);
+                }
+            }
             cnt += __popc(m);
-            if (m) { lb = w; lm = m; }
+            if (m) { lw = w0; lm = m; }
         }
-        int last = lm ? lb + 31 - __clz(lm) : -1;
+        int last = -1;
+        if (lm) {
+            const int hb = (int)bfind_u32(lm);                       // bit 4*it + k  ->  w = lw + 128*it + k
+            last = lw + 128 * (hb >> 2) + (hb & 3);
+        }
         cnt  = __reduce_add_sync(0xffffffffu, cnt);
         last = __reduce_max_sync(0xffffffffu, last);
         const uint32_t pk = ((uint32_t)cnt << 16) | ((uint32_t)last & 0xffffu);
@@ -627,7 +684,8 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     }
 }
 
-template <int R, int CAP, int NT>
+// STATIC: every unit of the list is the cube this variant is specialised for (32^3 for R = 1, 64^3 for R = 8).
+template <int R, int CAP, int NT, bool STATIC>
 __global__ void __launch_bounds__(NT, 1)
 k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                  const int* __restrict__ unit_list, int n_list, double one_minus_keep,
@@ -700,8 +758,8 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
         }
 #define WC_FC_UNIT(GEOM) fc_unit<R, CAP, NT>(GEOM, u, uid, S, pf, rank, xph1, xph2, xph3, states, \
                                              one_minus_keep, global_key, mode, pol, lt)
-        constexpr int CUBE = R == 1 ? 32 : 64;     // the cube this variant is specialised for
-        if (u.nx == CUBE && u.ny == CUBE && u.nz == CUBE) {
+        if constexpr (STATIC) {
+            constexpr int CUBE = R == 1 ? 32 : 64;
             if (u.dtype == WC_F64) WC_FC_UNIT((SGeom<CUBE, CUBE, CUBE, 8, R>()));
             else                   WC_FC_UNIT((SGeom<CUBE, CUBE, CUBE, 4, R>()));
         } else {
@@ -715,12 +773,12 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
 }
 
 // ---- launchers --------------------------------------------------------------------------------------
-template <int R, int CAP, int NT>
+template <int R, int CAP, int NT, bool STATIC>
 static cudaError_t launch_fc(int kid, int mode, const UnitDev* units, UnitState* states, const int* list,
                              int n, double omk, const u64* gkey, int sm_count, cudaStream_t st,
                              LaunchStats* ls, int* work_counter) {
     static int max_clusters = 0;   // resident clusters (CTAs for R = 1) on this device
-    auto kern = k_fused_compress<R, CAP, NT>;
+    auto kern = k_fused_compress<R, CAP, NT, STATIC>;
     constexpr int smem = FSmem<R, CAP>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -761,17 +819,25 @@ static cudaError_t launch_fc(int kid, int mode, const UnitDev* units, UnitState*
     return cudaGetLastError();
 }
 
-cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, UnitState* states,
+cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states,
                                   const int* unit_list, int n_list, double one_minus_keep,
                                   const u64* global_key, int sm_count, cudaStream_t st,
                                   LaunchStats* ls, int* work_counter) {
     if (n_list <= 0) return cudaSuccess;
-    if (cluster == 1)
-        return launch_fc<1, 32768, WC_NT1>(KID_FUSED_C1, mode, units, states, unit_list, n_list, one_minus_keep,
-                                           global_key, sm_count, st, ls, work_counter);
-    if (cluster == 8)
-        return launch_fc<8, 32768, 512>(KID_FUSED_C8, mode, units, states, unit_list, n_list, one_minus_keep,
-                                        global_key, sm_count, st, ls, nullptr);
+    switch (fused_cls) {
+    case FUSED_CLS_R1:
+        return launch_fc<1, 32768, 512, false>(KID_FUSED_C1, mode, units, states, unit_list, n_list,
+                                               one_minus_keep, global_key, sm_count, st, ls, work_counter);
+    case FUSED_CLS_R8:
+        return launch_fc<8, 32768, 512, false>(KID_FUSED_C8, mode, units, states, unit_list, n_list,
+                                               one_minus_keep, global_key, sm_count, st, ls, nullptr);
+    case FUSED_CLS_CUBE32:
+        return launch_fc<1, 32768, 1024, true>(KID_FUSED_C1S, mode, units, states, unit_list, n_list,
+                                               one_minus_keep, global_key, sm_count, st, ls, work_counter);
+    case FUSED_CLS_CUBE64:
+        return launch_fc<8, 32768, 1024, true>(KID_FUSED_C8S, mode, units, states, unit_list, n_list,
+                                               one_minus_keep, global_key, sm_count, st, ls, nullptr);
+    }
     return cudaErrorInvalidValue;
 }
 

@@ -11,13 +11,16 @@ namespace wc {
 
 enum { FUSED_FULL = 0, FUSED_KEYS_ONLY = 1, FUSED_GIVEN_THRESH = 2 };
 
-// Which fused kernel handles a box: 0 = none (generic path), 1 = one CTA per unit,
-// 8 = one 8-CTA cluster per unit.
+// Which fused compress kernel handles a box: 0 = none (generic path); one CTA per unit (<= 32768 cells) or
+// one 8-CTA cluster per unit (<= 262144 cells), each as a runtime-geometry kernel (512 threads) and as a
+// literal-geometry kernel for the most common AMR box (1024 threads: the literal strides and trip counts
+// bring it under 64 registers).
+enum { FUSED_CLS_NONE = 0, FUSED_CLS_R1 = 1, FUSED_CLS_R8 = 8, FUSED_CLS_CUBE32 = 101, FUSED_CLS_CUBE64 = 108 };
 int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 bool fused_decode_available();
 int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
 
-cudaError_t launch_fused_compress(int cluster, int mode, const UnitDev* units, UnitState* states,
+cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states,
                                   const int* unit_list, int n_list, double one_minus_keep,
                                   const u64* global_key, int sm_count, cudaStream_t st,
                                   LaunchStats* ls, int* work_counter = nullptr);
