@@ -170,6 +170,11 @@ __device__ __forceinline__ uint32_t bfind_u32(uint32_t x) {
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
     return r;
 }
+// the same through the float exponent: I2FP + shift + add on the ALU/FMA pipes instead of one FLO on the
+// (16 lanes/clk) XU pipe, which the emission phase otherwise loads with four ops per 32 coefficients
+__device__ __forceinline__ int bfind_alu(uint32_t x) {
+    return (int)(__float_as_uint(__uint2float_rz(x)) >> 23) - 127;     // x == 0 -> -127 (callers test x first)
+}
 __device__ __forceinline__ uint32_t fdiv_magic(uint32_t d) { return d <= 1 ? 0u : (0xffffffffu / d) + 1u; }
 
 // Streaming accesses carry an L2 evict-first policy: the input is read once and the pairs are written
@@ -666,10 +671,10 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
             for (int j = 0; j < 4; ++j) {
                 if (bal[j] != 0u) {                                    // warp-uniform
                     const uint32_t lower = bal[j] & lt;
-                    const int pl = lower ? (int)bfind_u32(lower) : prel;   // previous kept, lane units
+                    const int pl = lower ? bfind_alu(lower) : prel;        // previous kept, lane units
                     st_pair_pred(kf[j], out + (pos + __popc(lower)), lane - pl - 1, c[j], pol);
                     pos += __popc(bal[j]);
-                    prel = (int)bfind_u32(bal[j]);
+                    prel = bfind_alu(bal[j]);
                 }
                 prel -= 32;
             }
