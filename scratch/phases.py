@@ -13,6 +13,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else 'all'
 if which == '32': sel = [i for i, d in enumerate(dims) if d[0] == 32]
 elif which == '64': sel = [i for i, d in enumerate(dims) if d[0] == 64]
 else: sel = list(range(len(dims)))
+if len(sys.argv) > 2 and sys.argv[2].isdigit(): sel = sel[:int(sys.argv[2])]   # few units: the input stays in L2 (hot-input diagnostic)
 plan = ctx.plan(descs[sel], pkg.WC_DEVICE)
 lib = ctx.lib
 lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]

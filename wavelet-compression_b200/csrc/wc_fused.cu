@@ -48,7 +48,8 @@ struct FSmem {
     static constexpr int XS1   = RED + 64 * 8;                       // [2][8] u64 exchange slots
     static constexpr int XS2   = XS1 + 16 * 8;                       // [2][8] u64
     static constexpr int BARS  = XS2 + 16 * 8;                       // x1 x2 x3
-    static constexpr int TOTAL = BARS + 4 * 8;
+    static constexpr int DESC  = BARS + 4 * 8;                       // [2] FDesc: unit descriptors, one unit ahead
+    static constexpr int TOTAL = DESC + 2 * 64;
 };
 static_assert(FSmem<8, 32768>::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
@@ -341,6 +342,46 @@ __device__ __forceinline__ void phase_a(const G& g, const char* in0, float* C, u
     }
 }
 
+// Unit descriptors travel through shared memory one unit ahead: while unit k is processed, thread 0
+// fetches (index ->) unit id -> UnitDev of unit k+2 in stages placed at the phase boundaries, so that the
+// dependent global loads (and the work-counter atomic of the dynamic hand-out) never sit on the critical
+// path at the top of a unit.  Slot k&1 holds unit k; unit k+1 (slot (k+1)&1) is the L2-prefetch target.
+struct __align__(8) FDesc {
+    UnitDev u;      // 56 bytes
+    int     uid;    // index into units[] / states[]
+    int     ui;     // position in the work list; >= n_list: no more work
+};
+static_assert(sizeof(FDesc) == 64, "FDesc layout");
+struct FLookahead {
+    const UnitDev* units;
+    const int*     unit_list;
+    int*           work_counter;   // dynamic hand-out, or nullptr: static stride
+    int            n_list, stride;
+    FDesc*         slot;           // where unit k+2 goes (= the slot of unit k)
+    int            ui_prev;        // static: list position of unit k+1
+    int            idx, uid;       // thread 0 only
+    __device__ __forceinline__ void stage1() {          // top of the unit
+        idx = work_counter ? atomicAdd(work_counter, 1) : ui_prev + stride;
+    }
+    __device__ __forceinline__ void stage2() {          // after the first barrier: slot k&1 is free now
+        uid = idx < n_list ? __ldg(unit_list + idx) : -1;
+    }
+    __device__ __forceinline__ void stage3() {
+        slot->ui  = idx;
+        slot->uid = uid;
+        if (uid >= 0) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&slot->u);
+            const char*    src = reinterpret_cast<const char*>(units + uid);
+#pragma unroll
+            for (int b = 0; b < 56; b += 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + b), "l"(src + b) : "memory");
+        }
+    }
+    __device__ __forceinline__ void stage4() {          // before the unit's last barrier
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+};
+
 // Everything the per-unit body needs from the kernel frame (all scalarised after inlining).
 struct FShared {
     float*    C;
@@ -365,7 +406,7 @@ struct FPrefetch {
 // (the common cubes: every stride, trip count and divisor is a literal).
 template <int R, int CAP, int NT, class G>
 __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int uid, const FShared& S,
-                                        const FPrefetch& pf, const uint32_t rank, uint32_t& xph1,
+                                        const FPrefetch& pf, FLookahead& la, const uint32_t rank, uint32_t& xph1,
                                         uint32_t& xph2, uint32_t& xph3, UnitState* __restrict__ states,
                                         const double one_minus_keep, const u64* __restrict__ global_key,
                                         const int mode, const u64 pol, const uint32_t lt) {
@@ -378,6 +419,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     float bp = 0.f, bn = 0.f;                 // running max of +c and of -c
     bool  nan0 = false;
     long long t0 = clock64();
+    if (tid == 0) la.stage1();
 
     // ---------------- phase A: load, narrow, transform two blocks per thread, store into C -------
     {
@@ -415,6 +457,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
                         (u64)((__float_as_uint(bn) & 0x7fffffffu) | (any_nan0 ? 0x80000000u : 0u));
     }
     __syncthreads();
+    if (tid == 0) la.stage2();
     float Mp = 0.f, Mn = 0.f;
     bool  first_nan = false;
     {
@@ -513,6 +556,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
         }
     }
     if (mode == FUSED_KEYS_ONLY) {
+        if (tid == 0) { la.stage3(); la.stage4(); }
         __syncthreads();   // C is rewritten by the next unit
         return;
     }
@@ -567,6 +611,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     } else {
         __syncthreads();
     }
+    if (tid == 0) la.stage3();
 
     // ---------------- scan over the segments in global order ----------------
     {
@@ -681,6 +726,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
             prev = prel + fstart + w0 + 128;
         }
     }
+    if (tid == 0) la.stage4();
     __syncthreads();   // C and the segment arrays are rewritten by the next unit
     if (tid == 0 && blockIdx.x < 1024) {
         long long t5 = clock64();
@@ -730,38 +776,48 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
     uint32_t xph1 = 0, xph2 = 0, xph3 = 0;
     // Unit hand-out: static round-robin over the clusters, or (R = 1, work_counter given) a global atomic
     // counter, so that CTAs that become resident late — e.g. on SMs the 8-CTA-cluster kernel of the same
-    // step is still using — simply take fewer units.  `ui_next` is known one unit ahead for the L2 prefetch.
+    // step is still using — simply take fewer units.  Descriptors are staged two units ahead (FLookahead).
     const bool dynamic = (R == 1) && work_counter != nullptr;
-    int* const s_fetch = reinterpret_cast<int*>(smem + SM::RED + 50 * 8);
-    auto fetch = [&](int after) -> int {
-        if (!dynamic) return after + (int)ncl;
-        __syncthreads();
-        if (tid == 0) *s_fetch = atomicAdd(work_counter, 1);
-        __syncthreads();
-        return *s_fetch;
-    };
-    int ui = dynamic ? fetch(0) : (int)cid;
-    int ui_next = ui < n_list ? fetch(ui) : n_list;
-    for (; ui < n_list; ui = ui_next, ui_next = (ui < n_list ? fetch(ui) : n_list)) {
-        const int     uid = unit_list[ui];
-        const UnitDev u   = units[uid];
+    FDesc* const s_desc = reinterpret_cast<FDesc*>(smem + SM::DESC);
+    FLookahead la;
+    la.units = units; la.unit_list = unit_list; la.work_counter = dynamic ? work_counter : nullptr;
+    la.n_list = n_list; la.stride = (int)ncl;
+    la.idx = 0; la.uid = -1;
+    if (tid == 0) {
+        // prologue: units 0 and 1 of this CTA
+        la.ui_prev = (int)cid - (int)ncl;
+        for (int k = 0; k < 2; ++k) {
+            la.slot = &s_desc[k];
+            la.stage1(); la.stage2(); la.stage3();
+            la.ui_prev = la.idx;
+        }
+        la.stage4();
+    }
+    __syncthreads();
+    for (int k = 0;; ++k) {
+        const FDesc& d  = s_desc[k & 1];
+        const FDesc& dn = s_desc[(k + 1) & 1];
+        if (d.ui >= n_list) break;
+        const int     uid = d.uid;
+        const UnitDev u   = d.u;
+        la.slot    = &s_desc[k & 1];
+        la.ui_prev = dn.ui;
         FPrefetch pf = {nullptr, 0u, 0u, 0};
-        if (ui_next < n_list) {
-            const UnitDev un = units[unit_list[ui_next]];
-            const size_t rb = (size_t)un.nx * (un.dtype == WC_F64 ? 8 : 4), pb = rb * un.ny;
+        if (dn.ui < n_list) {
+            const size_t rb = (size_t)dn.u.nx * (dn.u.dtype == WC_F64 ? 8 : 4), pb = rb * dn.u.ny;
             if (R == 1) {
-                pf.base = static_cast<const char*>(un.in);
-                pf.piece_lines = (uint32_t)((pb * un.nz + 127) / 128);
+                pf.base = static_cast<const char*>(dn.u.in);
+                pf.piece_lines = (uint32_t)((pb * dn.u.nz + 127) / 128);
                 pf.nplanes = 1;
             } else {
-                const int nbn = (un.ny / 2) / R;
-                pf.base = static_cast<const char*>(un.in) + (size_t)(2 * rank * nbn) * rb;
+                const int nbn = (dn.u.ny / 2) / R;
+                pf.base = static_cast<const char*>(dn.u.in) + (size_t)(2 * rank * nbn) * rb;
                 pf.piece_lines = (uint32_t)((2 * nbn * rb + 127) / 128);
-                pf.nplanes = un.nz;
+                pf.nplanes = dn.u.nz;
                 pf.pitch = pb;
             }
         }
-#define WC_FC_UNIT(GEOM) fc_unit<R, CAP, NT>(GEOM, u, uid, S, pf, rank, xph1, xph2, xph3, states, \
+#define WC_FC_UNIT(GEOM) fc_unit<R, CAP, NT>(GEOM, u, uid, S, pf, la, rank, xph1, xph2, xph3, states, \
                                              one_minus_keep, global_key, mode, pol, lt)
         if constexpr (STATIC) {
             constexpr int CUBE = R == 1 ? 32 : 64;
