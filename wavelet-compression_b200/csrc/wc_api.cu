@@ -139,6 +139,7 @@ struct wc_plan {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;
     cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
     DevBuf d_counter;
+    unsigned counter_next = 0;
     std::vector<cudaEvent_t> ev;
     DevBuf d_running;
 };
@@ -590,6 +591,18 @@ static int plan_stage_inputs(wc_plan* p) {
     return WC_OK;
 }
 
+// A zeroed work counter for one single-CTA-class launch on `st` (dynamic unit hand-out: evens out the
+// ~10 % speed spread between SMs and lets late CTAs take less).  Ring of 64: launches that could still be
+// running 64 launches later are ordered before the reuse by the streams' own ordering / the fork-join events.
+static int plan_counter(wc_plan* p, cudaStream_t st, int** out) {
+    wc_ctx* ctx = p->ctx;
+    if (!p->d_counter.p) CTX_CUDA(ctx, p->d_counter.reserve(64 * sizeof(int)));
+    int* c = p->d_counter.as<int>() + (p->counter_next++ & 63);
+    CTX_CUDA(ctx, cudaMemsetAsync(c, 0, sizeof(int), st));
+    *out = c;
+    return WC_OK;
+}
+
 // forward transform (+ arg-max keys) of every unit; the fused classes only run here when the
 // threshold is batch-wide (they otherwise do everything in one kernel in plan_pack)
 static int plan_forward(wc_plan* p, bool global_mode) {
@@ -601,11 +614,17 @@ static int plan_forward(wc_plan* p, bool global_mode) {
                                          &ctx->ls));
     if (global_mode) {
         for (int k = 0; k < FL_N; ++k)
-            if (!p->fl[k].empty())
+            if (!p->fl[k].empty()) {
+                int* counter = nullptr;
+                if (!fl_is_cluster(k)) {
+                    int rc = plan_counter(p, ctx->stream, &counter);
+                    if (rc != WC_OK) return rc;
+                }
                 CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
                                                     p->d_states.as<UnitState>(), p->d_fl[k].as<int>(),
                                                     (int)p->fl[k].size(), 0.0, nullptr, ctx->sm_count,
-                                                    ctx->stream, &ctx->ls));
+                                                    ctx->stream, &ctx->ls, counter));
+            }
     }
     return WC_OK;
 }
@@ -641,20 +660,22 @@ static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
             CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
             CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
             CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-            CTX_CUDA(ctx, p->d_counter.reserve(64));
         }
-        CTX_CUDA(ctx, cudaMemsetAsync(p->d_counter.p, 0, 4 * FL_N, ctx->stream));
         CTX_CUDA(ctx, cudaEventRecord(p->ev_fork, ctx->stream));
         CTX_CUDA(ctx, cudaStreamWaitEvent(p->s_aux, p->ev_fork, 0));
     }
     for (int k = 0; k < FL_N; ++k) {
         if (p->fl[k].empty()) continue;
-        const bool aux = overlap && !fl_is_cluster(k);
+        cudaStream_t st = (overlap && !fl_is_cluster(k)) ? p->s_aux : ctx->stream;
+        int* counter = nullptr;
+        if (!fl_is_cluster(k)) {
+            int rc = plan_counter(p, st, &counter);
+            if (rc != WC_OK) return rc;
+        }
         CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], mode, p->d_units.as<UnitDev>(),
                                             p->d_states.as<UnitState>(), p->d_fl[k].as<int>(),
                                             (int)p->fl[k].size(), omk, global_key_dev, ctx->sm_count,
-                                            aux ? p->s_aux : ctx->stream, &ctx->ls,
-                                            aux ? p->d_counter.as<int>() + k : nullptr));
+                                            st, &ctx->ls, counter));
     }
     if (overlap) {
         CTX_CUDA(ctx, cudaEventRecord(p->ev_join, p->s_aux));
@@ -860,11 +881,17 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
         for (int k = 0; k < FL_N; ++k) {
             size_t j = fi[k];
             while (j < p->fl[k].size() && p->fl[k][j] < u1) ++j;
-            if (j > fi[k])
+            if (j > fi[k]) {
+                int* counter = nullptr;
+                if (!fl_is_cluster(k)) {
+                    int rc = plan_counter(p, ctx->stream, &counter);
+                    if (rc != WC_OK) return rc;
+                }
                 CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], FUSED_FULL, p->d_units.as<UnitDev>(),
                                                     p->d_states.as<UnitState>(), p->d_fl[k].as<int>() + fi[k],
                                                     (int)(j - fi[k]), omk, nullptr, ctx->sm_count, ctx->stream,
-                                                    &ctx->ls));
+                                                    &ctx->ls, counter));
+            }
             fi[k] = j;
         }
         if (u1 > u0) {

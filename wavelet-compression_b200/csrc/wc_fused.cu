@@ -213,7 +213,14 @@ __device__ __forceinline__ void st_pair_pred(bool p, int2* addr, int run, float 
 // profile, read back with wc_debug_phase_cycles().  [cta][phase], phases: 0 = A (load + transform),
 // 1 = B (threshold, includes waiting for the slowest warp of A), 2 = C1 (count), 3 = scan (+ cluster
 // exchange), 4 = C2 (emit), 5 = units processed.
+// Only in builds with -DWC_PHASE_PROFILE (make PHASE_PROFILE=1): the read-modify-writes cost thread 0 some
+// 600 cycles per unit.
 __device__ unsigned long long g_phase_cycles[1024][6];
+#ifdef WC_PHASE_PROFILE
+#define WC_PHASE_CLOCK(t) long long t = clock64()
+#else
+#define WC_PHASE_CLOCK(t) do { } while (0)
+#endif
 
 // One 1-D Haar step on two independent blocks at once (packed f32x2): lo = (lo+hi)*0.5, hi = (lo-hi)*0.5,
 // each rounded exactly like the scalar __fadd_rn / __fsub_rn / __fmul_rn sequence: hi*(-1)+lo is the
@@ -364,7 +371,8 @@ struct FLookahead {
         idx = work_counter ? atomicAdd(work_counter, 1) : ui_prev + stride;
     }
     __device__ __forceinline__ void stage2() {          // after the first barrier: slot k&1 is free now
-        uid = idx < n_list ? __ldg(unit_list + idx) : -1;
+        uid = -1;          // volatile: issued HERE (the compiler would otherwise sink the load to its first use)
+        if (idx < n_list) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(uid) : "l"(unit_list + idx));
     }
     __device__ __forceinline__ void stage3() {
         slot->ui  = idx;
@@ -418,7 +426,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     const size_t row_bytes = (size_t)g.X * g.es;
     float bp = 0.f, bn = 0.f;                 // running max of +c and of -c
     bool  nan0 = false;
-    long long t0 = clock64();
+    WC_PHASE_CLOCK(t0);
     if (tid == 0) la.stage1();
 
     // ---------------- phase A: load, narrow, transform two blocks per thread, store into C -------
@@ -444,7 +452,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     }
 
     // ---------------- phase B: the threshold ----------------
-    long long t1 = clock64();
+    WC_PHASE_CLOCK(t1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
@@ -562,7 +570,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     }
 
     // ---------------- phase C1: per-segment count and last kept ----------------
-    long long t2 = clock64();
+    WC_PHASE_CLOCK(t2);
     const int gpar = R > 1 ? (int)(xph2 & 1) : 0;
     uint32_t* const my_pk = S.g_pk + gpar * SM::MAXG;
 #pragma unroll 1
@@ -601,7 +609,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
             st_cluster_u32(mapa(smem_u32(&my_pk[sg * R + rank]), lane), pk);
         }
     }
-    long long t3 = clock64();
+    WC_PHASE_CLOCK(t3);
     if (R > 1) {
         fence_cluster();
         __syncthreads();
@@ -611,7 +619,6 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     } else {
         __syncthreads();
     }
-    if (tid == 0) la.stage3();
 
     // ---------------- scan over the segments in global order ----------------
     {
@@ -677,7 +684,8 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     // Segments are handed out dynamically (shared-memory counter): their cost ranges from nothing
     // (detail bands below the threshold) to a full copy, and a static round-robin left half of the
     // warps idle at the closing barrier.
-    long long t4 = clock64();
+    WC_PHASE_CLOCK(t4);
+    if (tid == 0) la.stage3();
     int2* const out = reinterpret_cast<int2*>(u.out);
     for (;;) {
         int sg = 0;
@@ -728,11 +736,13 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     }
     if (tid == 0) la.stage4();
     __syncthreads();   // C and the segment arrays are rewritten by the next unit
+#ifdef WC_PHASE_PROFILE
     if (tid == 0 && blockIdx.x < 1024) {
         long long t5 = clock64();
         unsigned long long* pc = g_phase_cycles[blockIdx.x];
         pc[0] += t1 - t0; pc[1] += t2 - t1; pc[2] += t3 - t2; pc[3] += t4 - t3; pc[4] += t5 - t4; pc[5] += 1;
     }
+#endif
 }
 
 // STATIC: every unit of the list is the cube this variant is specialised for (32^3 for R = 1, 64^3 for R = 8).
