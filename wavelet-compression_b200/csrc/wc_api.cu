@@ -108,6 +108,7 @@ struct wc_ctx {
     cudaStream_t s_aux = nullptr;
     cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
     DevBuf       d_counter;
+    unsigned     counter_next = 0;
 };
 
 // Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
@@ -955,7 +956,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
     std::vector<DecUnitDev> du(n);
     std::vector<InvUnitDev> iu(n);
     std::vector<int2> ptiles, xtiles;
-    std::vector<int> f1, f8;
+    std::vector<int> fl[FL_N];   // fused classes, FL_CLASS order (cluster kernels first)
     size_t coef_floats = 0;
     std::vector<size_t> coef_off(n);
     for (int i = 0; i < n; ++i) {
@@ -980,8 +981,10 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             for (int t = 0; t < du[i].nptiles; ++t) ptiles.push_back(make_int2(i, t));
             int nt = xtile_count(jobs[i].nx, jobs[i].ny, jobs[i].nz);
             for (int t = 0; t < nt; ++t) xtiles.push_back(make_int2(i, t));
-        } else if (cls == 1) f1.push_back(i);
-        else if (cls == 8) f8.push_back(i);
+        } else {
+            for (int k = 0; k < FL_N; ++k)
+                if (cls == FL_CLASS[k]) fl[k].push_back(i);
+        }
     }
     CTX_CUDA(ctx, d_coef.reserve(sizeof(float) * std::max<size_t>(coef_floats, 4)));
     for (int i = 0; i < n; ++i) {
@@ -1011,38 +1014,49 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
                                             d_err.as<int>(), ctx->stream, &ctx->ls));
     CTX_CUDA(ctx, launch_inverse_generic(d_inv_units.as<InvUnitDev>(), d_inv_tiles.as<int2>(),
                                          (int)xtiles.size(), ctx->stream, &ctx->ls));
-    if (!f1.empty() || !f8.empty()) {
-        CTX_CUDA(ctx, d_fused_list.reserve(sizeof(int) * (f1.size() + f8.size())));
+    size_t n_fused = 0;
+    bool any_cluster = false, any_single = false;
+    for (int k = 0; k < FL_N; ++k) {
+        n_fused += fl[k].size();
+        if (!fl[k].empty()) (fl_is_cluster(k) ? any_cluster : any_single) = true;
+    }
+    if (n_fused) {
+        CTX_CUDA(ctx, d_fused_list.reserve(sizeof(int) * n_fused));
         int* dl = d_fused_list.as<int>();
-        if (!f1.empty())
-            CTX_CUDA(ctx, cudaMemcpyAsync(dl, f1.data(), sizeof(int) * f1.size(),
-                                          cudaMemcpyHostToDevice, ctx->stream));
-        if (!f8.empty())
-            CTX_CUDA(ctx, cudaMemcpyAsync(dl + f1.size(), f8.data(), sizeof(int) * f8.size(),
-                                          cudaMemcpyHostToDevice, ctx->stream));
-        const bool overlap = !f1.empty() && !f8.empty() && !ctx->ls.profile && ctx->opt_overlap;
+        size_t off[FL_N], o = 0;
+        for (int k = 0; k < FL_N; ++k) {
+            off[k] = o;
+            if (!fl[k].empty())
+                CTX_CUDA(ctx, cudaMemcpyAsync(dl + o, fl[k].data(), sizeof(int) * fl[k].size(),
+                                              cudaMemcpyHostToDevice, ctx->stream));
+            o += fl[k].size();
+        }
+        if (!ctx->s_aux) {
+            CTX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+            CTX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            CTX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
+        }
+        // cluster kernels on the ctx stream, single-CTA kernels (dynamic unit hand-out) on the second stream
+        // when both kinds are present — see plan_pack
+        const bool overlap = any_cluster && any_single && !ctx->ls.profile && ctx->opt_overlap;
         if (overlap) {
-            if (!ctx->s_aux) {
-                CTX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
-                CTX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-                CTX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-                CTX_CUDA(ctx, ctx->d_counter.reserve(64));
-            }
-            CTX_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
             CTX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
             CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
         }
-        if (!f8.empty())
-            CTX_CUDA(ctx, launch_fused_decompress(8, d_dec_units.as<DecUnitDev>(),
-                                                  d_inv_units.as<InvUnitDev>(), dl + f1.size(),
-                                                  (int)f8.size(), d_err.as<int>(), ctx->sm_count,
-                                                  ctx->stream, &ctx->ls));
-        if (!f1.empty())
-            CTX_CUDA(ctx, launch_fused_decompress(1, d_dec_units.as<DecUnitDev>(),
-                                                  d_inv_units.as<InvUnitDev>(), dl, (int)f1.size(),
-                                                  d_err.as<int>(), ctx->sm_count,
-                                                  overlap ? ctx->s_aux : ctx->stream, &ctx->ls,
-                                                  overlap ? ctx->d_counter.as<int>() : nullptr));
+        for (int k = 0; k < FL_N; ++k) {
+            if (fl[k].empty()) continue;
+            cudaStream_t st = (overlap && !fl_is_cluster(k)) ? ctx->s_aux : ctx->stream;
+            int* counter = nullptr;
+            if (!fl_is_cluster(k)) {
+                counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
+                CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
+            }
+            CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
+                                                  d_inv_units.as<InvUnitDev>(), dl + off[k],
+                                                  (int)fl[k].size(), d_err.as<int>(), ctx->sm_count, st,
+                                                  &ctx->ls, counter));
+        }
         if (overlap) {
             CTX_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->s_aux));
             CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));

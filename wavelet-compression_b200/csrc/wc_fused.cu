@@ -962,218 +962,366 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
-// S = 1: one CTA per unit.  S = 8: an 8-CTA cluster per unit; CTA r owns the y-slab r of the box (and the
-// matching segments of C), walks 1/8 of the pair list, and scatters every value into the OWNER's shared
-// memory through DSMEM (st.shared::cluster) — the list is read from HBM exactly once.
-template <int S, int NT>
+// Unit descriptors are staged two units ahead through shared memory, like FLookahead of the compress
+// kernels; K (which may live on the device after a plan round trip) is resolved one unit ahead, in time
+// for the L2 prefetch of the next unit's pair list.
+struct __align__(8) FDDesc {
+    DecUnitDev du;      // 40 bytes
+    InvUnitDev iu;      // 32 bytes
+    int        K;       // resolved pair count
+    int        uid, ui; // index into dec[] / inv[]; position in the work list (>= n_list: no more work)
+    int        pad;
+};
+static_assert(sizeof(DecUnitDev) == 40 && sizeof(InvUnitDev) == 32 && sizeof(FDDesc) == 88, "FDDesc layout");
+struct FDLookahead {
+    const DecUnitDev* dec;
+    const InvUnitDev* inv;
+    const int*        unit_list;
+    int*              work_counter;
+    int               n_list, stride;
+    FDDesc*           slot;        // unit k's slot: receives unit k+2
+    FDDesc*           next_slot;   // unit k+1: descriptor present, K still to be resolved
+    int               ui_prev;
+    int               idx, uid, kreg;   // thread 0 only
+    __device__ __forceinline__ void resolve_k_issue() {
+        kreg = 0;
+        if (next_slot->uid >= 0) {
+            kreg = next_slot->du.npairs;
+            const int32_t* kp = next_slot->du.npairs_dev;
+            if (kp) asm volatile("ld.global.s32 %0, [%1];" : "=r"(kreg) : "l"(kp));
+        }
+    }
+    __device__ __forceinline__ void stage1() {          // top of the unit
+        idx = work_counter ? atomicAdd(work_counter, 1) : ui_prev + stride;
+    }
+    __device__ __forceinline__ void stage2() {          // after the first barrier: slot k&1 is free now
+        uid = -1;
+        if (idx < n_list) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(uid) : "l"(unit_list + idx));
+    }
+    __device__ __forceinline__ void resolve_k_store() { next_slot->K = kreg; }   // before the post-scatter barrier
+    __device__ __forceinline__ void stage3() {
+        slot->ui  = idx;
+        slot->uid = uid;
+        if (uid >= 0) {
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&slot->du);
+            const char*    s0 = reinterpret_cast<const char*>(dec + uid);
+#pragma unroll
+            for (int b = 0; b < 40; b += 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + b), "l"(s0 + b) : "memory");
+            const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(&slot->iu);
+            const char*    s1 = reinterpret_cast<const char*>(inv + uid);
+#pragma unroll
+            for (int b = 0; b < 32; b += 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1 + b), "l"(s1 + b) : "memory");
+        }
+    }
+    __device__ __forceinline__ void stage4() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+};
+
+struct FDShared {
+    float*    C;
+    uint32_t* s_wt;     // [2][32] warp totals (double-buffered per tile)
+    u64*      xs;       // [2][8] exchange slots
+    uint32_t  xb;       // mbarrier
+    uint32_t  c_base;
+};
+
+// One unit of the fused decompress.  S = 1: one CTA per unit.  S = 8: an 8-CTA cluster per unit; CTA r owns
+// the y-slab r of the box (and the matching segments of C), walks 1/8 of the pair list, and scatters every
+// value into the OWNER's shared memory through DSMEM (st.shared::cluster) — the list is read from HBM once.
+template <int S, int NT, class G>
+__device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const InvUnitDev& iu, const int K,
+                                        const FDShared& Sh, FDLookahead& la, const uint32_t rank,
+                                        uint32_t& xph, int* __restrict__ err, const bool have_next) {
+    constexpr int NW  = NT / 32;
+    constexpr int PPT = 8;                                     // pairs per thread per tile
+    float* const C = Sh.C;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b0 = rank * g.nb;
+    const uint32_t total = (uint32_t)du.total;
+    if (tid == 0) { la.stage1(); la.resolve_k_issue(); }
+
+    // this CTA's share of the pair list: [k0, k1)
+    const int per = S > 1 ? (((K + S - 1) / S + PPT - 1) / PPT) * PPT : K;
+    const int k0 = min(K, (int)rank * per), k1 = min(K, k0 + per);
+    const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
+    const bool vec16 = (reinterpret_cast<uintptr_t>(pairs) & 15u) == 0;   // k0 is a multiple of 8
+    auto load_tile = [&](int p, int2 (&pr)[PPT]) {
+        if (vec16 && p + PPT <= k1) {
+#pragma unroll
+            for (int j = 0; j < PPT; j += 2) {
+                const int4 v = *reinterpret_cast<const int4*>(pairs + p + j);
+                pr[j] = make_int2(v.x, v.y); pr[j + 1] = make_int2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) pr[j] = (p + j < k1) ? pairs[p + j] : make_int2(0, 0);
+        }
+    };
+    int2 pr[PPT];
+    if (S == 1) load_tile(k0 + tid * PPT, pr);                  // in flight during the zero-fill
+
+    // 1. zero-fill C (rle_decode starts from zeros, src/decompressor.cpp:17)
+    {
+        const int nwords = g.nlocal + F_PAD * g.X;
+        float4* c4 = reinterpret_cast<float4*>(C);
+#pragma unroll 4
+        for (int i = tid; i < (nwords + 3) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // every CTA of the cluster has finished reading its previous C and zeroed the new one before
+    // anybody scatters into it
+    if (S > 1) cluster_sync_all(); else __syncthreads();
+    if (tid == 0) la.stage2();
+
+    bool bad = false;
+    uint32_t carry = 0;
+    if (S > 1) {
+        // 2a. sum of (run + 1) over the share, all-gathered -> where this share starts in f
+        uint32_t s = 0;
+        for (int p = k0 + tid; p < k1; p += NT) {
+            const int run = pairs[p].x;
+            if (run < 0) bad = true;
+            s = sat_add(s, (uint32_t)max(run, 0) + 1u);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s = sat_add(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (lane == 0) Sh.s_wt[warp] = s;
+        __syncthreads();
+        uint32_t tot = lane < NW ? Sh.s_wt[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot = sat_add(tot, __shfl_xor_sync(0xffffffffu, tot, o));
+        __syncthreads();
+        const uint32_t par = xph & 1;
+        if (tid < S) {
+            st_cluster_u64(mapa(smem_u32(&Sh.xs[par * 8 + rank]), tid), (u64)tot);
+            mbar_arrive_remote(mapa(Sh.xb, tid));
+        }
+        mbar_wait_cluster(Sh.xb, par);
+        ++xph;
+#pragma unroll
+        for (int r = 0; r < S; ++r)
+            if (r < (int)rank) carry = sat_add(carry, (uint32_t)Sh.xs[par * 8 + r]);
+    }
+    // 2b. flat index of every pair of the share; scatter into the owner's C
+    {
+        FastDiv dyz, dz, dnb;
+        if (!G::is_static) {
+            dyz.init((uint32_t)(g.Y * g.Z), total);
+            dz.init((uint32_t)g.Z, (uint32_t)(g.Y * g.Z));
+            dnb.init((uint32_t)g.nb, (uint32_t)g.hy);
+        }
+        int tile = 0;
+#pragma unroll 1
+        for (int p0 = k0; p0 < k1; p0 += NT * PPT, ++tile) {
+            const int p = p0 + tid * PPT;
+            if (S > 1 || tile > 0) load_tile(p, pr);
+            uint32_t s = 0;
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+                if (p + j < k1) {
+                    if (pr[j].x < 0) bad = true;
+                    s = sat_add(s, (uint32_t)max(pr[j].x, 0) + 1u);
+                }
+            }
+            uint32_t inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc = sat_add(inc, v);
+            }
+            uint32_t* const wt = Sh.s_wt + (tile & 1) * 32;     // double-buffered: one barrier per tile
+            if (lane == 31) wt[warp] = inc;
+            __syncthreads();
+            // prefix over the warp totals: one warp-scan instead of NW shared loads per thread
+            uint32_t wv = lane < NW ? wt[lane] : 0u, winc = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc = sat_add(winc, v);
+            }
+            const uint32_t ttot = __shfl_sync(0xffffffffu, winc, 31);
+            uint32_t wpre = __shfl_sync(0xffffffffu, winc, (warp + 31) & 31);   // inclusive up to warp-1
+            if (warp == 0) wpre = 0;
+            uint32_t exl = __shfl_up_sync(0xffffffffu, inc, 1);     // exclusive prefix inside the warp
+            if (lane == 0) exl = 0;
+            uint32_t pre = sat_add(sat_add(carry, wpre), exl);       // exclusive prefix of this thread
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+                if (p + j < k1 && pr[j].x >= 0) {
+                    const uint32_t f = sat_add(pre, (uint32_t)pr[j].x);
+                    if (f < total) {
+                        const uint32_t YZ = (uint32_t)(g.Y * g.Z);
+                        const uint32_t ip = G::is_static ? f / YZ : dyz.div(f), rem = f - ip * YZ;
+                        const uint32_t jp = G::is_static ? rem / (uint32_t)g.Z : dz.div(rem), kp = rem - jp * (uint32_t)g.Z;
+                        const uint32_t sy = jp >= (uint32_t)g.hy ? 1u : 0u;
+                        const uint32_t b  = jp - sy * g.hy;                 // block-row 0..hy-1
+                        const uint32_t ro = S > 1 ? (G::is_static ? b / (uint32_t)g.nb : dnb.div(b)) : 0u;   // owner slab
+                        const uint32_t bl = b - ro * g.nb;
+                        const uint32_t idx = ip * g.slab + (sy * g.nb + bl) * g.Z + kp;
+                        if (S > 1) st_cluster_f32(mapa(Sh.c_base + 4 * idx, ro), __int_as_float(pr[j].y));
+                        else C[idx] = __int_as_float(pr[j].y);
+                    }
+                    pre = sat_add(pre, (uint32_t)pr[j].x + 1u);
+                }
+            }
+            carry = sat_add(carry, ttot);
+        }
+        if (bad) atomicOr(err, 1);
+    }
+    if (tid == 0) la.resolve_k_store();
+    // all scatters (local and remote) are complete and visible before anybody reads its C
+    if (S > 1) cluster_sync_all(); else __syncthreads();
+
+    // L2 prefetch of this CTA's share of the NEXT unit's pair list: lands while this unit is inverted
+    if (have_next) {
+        const int Kn = la.next_slot->K;
+        const int pern = S > 1 ? (((Kn + S - 1) / S + PPT - 1) / PPT) * PPT : Kn;
+        const int n0 = min(Kn, (int)rank * pern), n1 = min(Kn, n0 + pern);
+        const char* base = reinterpret_cast<const char*>(la.next_slot->du.pairs) + (size_t)n0 * 8;
+        const int nlines = ((n1 - n0) * 8 + 127) / 128;
+        for (int i = tid; i < nlines; i += NT)
+            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)i * 128));
+    }
+    if (tid == 0) la.stage3();
+
+    // 3. inverse transform (X, then Y, then Z), two c-adjacent blocks per thread, and store the slab
+    {
+        const uint32_t m_hx = G::is_static ? 0u : fdiv_magic(g.hx), m_cq = G::is_static ? 0u : fdiv_magic(g.ncq);
+        const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
+        const int npc = g.hz >> 1;
+        const size_t es = iu.dtype == WC_F64 ? 8 : 4;
+        const size_t row_bytes = (size_t)g.X * es, plane_bytes = row_bytes * g.Y;
+        char* out0 = static_cast<char*>(iu.out) + (size_t)(2 * b0) * row_bytes;
+        auto one = [&](int q) {
+            const uint32_t cp2 = q & 1, t1 = q >> 1;
+            const uint32_t t2 = G::is_static ? t1 / (uint32_t)g.hx : fdiv(t1, m_hx), a = t1 - t2 * g.hx;
+            const uint32_t bl = G::is_static ? t2 / (uint32_t)g.ncq : fdiv(t2, m_cq), cq = t2 - bl * g.ncq;
+            const int cpi = 2 * cq + cp2;
+            if ((npc & 1) && cpi >= npc) return;
+            const float* csrc = C + a * g.slab + bl * g.Z + 2 * cpi;
+            float2 v[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+                v[o] = *reinterpret_cast<const float2*>(csrc + (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ihaar_pair2(v[2 * k], v[2 * k + 1]);                 // X
+#pragma unroll
+            for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+                for (int xi = 0; xi < 2; ++xi) ihaar_pair2(v[zi * 4 + xi], v[zi * 4 + 2 + xi]);   // Y
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ihaar_pair2(v[k], v[4 + k]);                         // Z
+            char* p0 = out0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes + (size_t)a * 2 * es;
+#pragma unroll
+            for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+                for (int yi = 0; yi < 2; ++yi) {
+                    const float2 lo = v[zi * 4 + yi * 2], hi = v[zi * 4 + yi * 2 + 1];   // xi = 0, 1
+                    char* pa = p0 + zi * plane_bytes + yi * row_bytes;        // block c:   planes 4cpi + zi
+                    char* pb = pa + 2 * plane_bytes;                          // block c+1: planes 4cpi + 2 + zi
+                    if (iu.dtype == WC_F64) {
+                        *reinterpret_cast<double2*>(pa) = make_double2((double)lo.x, (double)hi.x);
+                        *reinterpret_cast<double2*>(pb) = make_double2((double)lo.y, (double)hi.y);
+                    } else {
+                        *reinterpret_cast<float2*>(pa) = make_float2(lo.x, hi.x);
+                        *reinterpret_cast<float2*>(pb) = make_float2(lo.y, hi.y);
+                    }
+                }
+        };
+        if constexpr (G::is_static) {
+            static_assert(G::npairs % NT == 0, "literal geometries fill every slot");
+#pragma unroll
+            for (int it = 0; it < G::npairs / NT; ++it) one(tid + it * NT);
+        } else {
+#pragma unroll 1
+            for (int q = tid; q < g.npairs; q += NT) one(q);
+        }
+    }
+    if (tid == 0) la.stage4();
+    // C is zero-filled again by the next unit (the cluster barrier of step 1 comes AFTER the zero-fill, so the
+    // cluster variant needs this CTA barrier too), and the staged descriptor becomes visible to the CTA
+    __syncthreads();
+}
+
+template <int S, int NT, bool STATIC>
 __global__ void __launch_bounds__(NT, 1)
 k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
                    const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
                    int* __restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int NW = NT / 32;
-    constexpr int PPT = 8;                                     // pairs per thread per tile
-    float* const    C     = reinterpret_cast<float*>(smem);
-    uint32_t* const s_wt  = reinterpret_cast<uint32_t*>(smem + (32768 + F_CPAD) * 4);   // [32] warp totals
-    u64* const      xs    = reinterpret_cast<u64*>(smem + (32768 + F_CPAD) * 4 + 128);  // [2][8] exchange slots
-    const uint32_t  xb    = smem_u32(smem + (32768 + F_CPAD) * 4 + 128 + 128);          // mbarrier
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int BASE = (32768 + F_CPAD) * 4;
+    FDShared Sh;
+    Sh.C      = reinterpret_cast<float*>(smem);
+    Sh.s_wt   = reinterpret_cast<uint32_t*>(smem + BASE);          // [2][32]
+    Sh.xs     = reinterpret_cast<u64*>(smem + BASE + 256);         // [2][8]
+    Sh.xb     = smem_u32(smem + BASE + 256 + 128);
+    Sh.c_base = smem_u32(Sh.C);
+    FDDesc* const s_desc = reinterpret_cast<FDDesc*>(smem + BASE + 256 + 128 + 16);   // [2] x 88 bytes
+    const int tid = threadIdx.x;
     const uint32_t rank = S > 1 ? cluster_ctarank() : 0u;
     const uint32_t cid  = S > 1 ? cluster_id_x() : blockIdx.x;
     const uint32_t ncl  = S > 1 ? nclusters_x() : gridDim.x;
-    const uint32_t c_base = smem_u32(C);
     uint32_t xph = 0;
 
     if (S > 1) {
         if (tid == 0) {
-            mbar_init(xb, S);
+            mbar_init(Sh.xb, S);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         cluster_sync_all();
     }
 
-    // static round-robin, or (S = 1 with a work counter) dynamic hand-out — see k_fused_compress
-    const bool dynamic = (S == 1) && work_counter != nullptr;
-    int* const s_fetch = reinterpret_cast<int*>(smem + (32768 + F_CPAD) * 4 + 128 + 128 + 16);
-    auto fetch = [&](int after) -> int {
-        if (!dynamic) return after + (int)ncl;
-        __syncthreads();
-        if (tid == 0) *s_fetch = atomicAdd(work_counter, 1);
-        __syncthreads();
-        return *s_fetch;
-    };
-    for (int ui = dynamic ? fetch(0) : (int)cid; ui < n_list; ui = fetch(ui)) {
-        const int uid = unit_list[ui];
-        const DecUnitDev du = dec[uid];
-        const InvUnitDev iu = inv[uid];
-        FGeom g;
-        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, S, 32768, g);   // same rule as fused_decode_class
-        const int b0 = rank * g.nb;
-        const int K  = du.npairs_dev ? *du.npairs_dev : du.npairs;
-        const uint32_t total = (uint32_t)du.total;
-
-        // 1. zero-fill C (rle_decode starts from zeros, src/decompressor.cpp:17)
-        {
-            const int nwords = g.nlocal + F_PAD * g.X;
-            float4* c4 = reinterpret_cast<float4*>(C);
-            for (int i = tid; i < (nwords + 3) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // static round-robin over the clusters, or (S = 1 with a work counter) dynamic hand-out
+    FDLookahead la;
+    la.dec = dec; la.inv = inv; la.unit_list = unit_list;
+    la.work_counter = (S == 1) ? work_counter : nullptr;
+    la.n_list = n_list; la.stride = (int)ncl;
+    la.idx = 0; la.uid = -1; la.kreg = 0;
+    if (tid == 0) {
+        la.ui_prev = (int)cid - (int)ncl;
+        for (int k = 0; k < 2; ++k) {
+            la.slot = &s_desc[k];
+            la.stage1(); la.stage2(); la.stage3();
+            la.ui_prev = la.idx;
         }
-        // every CTA of the cluster has finished reading its previous C and zeroed the new one before
-        // anybody scatters into it
-        if (S > 1) cluster_sync_all(); else __syncthreads();
-
-        // 2. this CTA's share of the pair list: [k0, k1)
-        const int per = S > 1 ? (((K + S - 1) / S + PPT - 1) / PPT) * PPT : K;
-        const int k0 = min(K, (int)rank * per), k1 = min(K, k0 + per);
-        const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
-        bool bad = false;
-        uint32_t carry = 0;
-        if (S > 1) {
-            // 2a. sum of (run + 1) over the share, all-gathered -> where this share starts in f
-            uint32_t s = 0;
-            for (int p = k0 + tid; p < k1; p += NT) {
-                const int run = pairs[p].x;
-                if (run < 0) bad = true;
-                s = sat_add(s, (uint32_t)max(run, 0) + 1u);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s = sat_add(s, __shfl_xor_sync(0xffffffffu, s, o));
-            if (lane == 0) s_wt[warp] = s;
-            __syncthreads();
-            uint32_t tot = 0;
-#pragma unroll
-            for (int i = 0; i < NW; ++i) tot = sat_add(tot, s_wt[i]);
-            __syncthreads();
-            const uint32_t par = xph & 1;
-            if (tid < S) {
-                st_cluster_u64(mapa(smem_u32(&xs[par * 8 + rank]), tid), (u64)tot);
-                mbar_arrive_remote(mapa(xb, tid));
-            }
-            mbar_wait_cluster(xb, par);
-            ++xph;
-#pragma unroll
-            for (int r = 0; r < S; ++r)
-                if (r < (int)rank) carry = sat_add(carry, (uint32_t)xs[par * 8 + r]);
+        la.stage4();
+        for (int k = 0; k < 2; ++k) {
+            la.next_slot = &s_desc[k];
+            la.resolve_k_issue(); la.resolve_k_store();
         }
-        // 2b. flat index of every pair of the share; scatter into the owner's C
-        {
-            FastDiv dyz, dz, dnb;
-            dyz.init((uint32_t)(g.Y * g.Z), total);
-            dz.init((uint32_t)g.Z, (uint32_t)(g.Y * g.Z));
-            dnb.init((uint32_t)g.nb, (uint32_t)g.hy);
-            for (int p0 = k0; p0 < k1; p0 += NT * PPT) {
-                const int p = p0 + tid * PPT;
-                int2 pr[PPT];
-                uint32_t s = 0;
-#pragma unroll
-                for (int j = 0; j < PPT; ++j) {
-                    pr[j] = (p + j < k1) ? pairs[p + j] : make_int2(-1, 0);
-                    if (p + j < k1) {
-                        if (pr[j].x < 0) bad = true;
-                        s = sat_add(s, (uint32_t)max(pr[j].x, 0) + 1u);
-                    }
-                }
-                uint32_t inc = s;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc = sat_add(inc, v);
-                }
-                if (lane == 31) s_wt[warp] = inc;
-                __syncthreads();
-                uint32_t wpre = 0, ttot = 0;
-#pragma unroll
-                for (int i = 0; i < NW; ++i) {
-                    uint32_t x = s_wt[i];
-                    if (i < warp) wpre = sat_add(wpre, x);
-                    ttot = sat_add(ttot, x);
-                }
-                uint32_t exl = __shfl_up_sync(0xffffffffu, inc, 1);     // exclusive prefix inside the warp
-                if (lane == 0) exl = 0;
-                uint32_t pre = sat_add(sat_add(carry, wpre), exl);       // exclusive prefix of this thread
-#pragma unroll
-                for (int j = 0; j < PPT; ++j) {
-                    if (p + j < k1 && pr[j].x >= 0) {
-                        const uint32_t f = sat_add(pre, (uint32_t)pr[j].x);
-                        if (f < total) {
-                            const uint32_t ip = dyz.div(f), rem = f - ip * (uint32_t)(g.Y * g.Z);
-                            const uint32_t jp = dz.div(rem), kp = rem - jp * (uint32_t)g.Z;
-                            const uint32_t sy = jp >= (uint32_t)g.hy ? 1u : 0u;
-                            const uint32_t b  = jp - sy * g.hy;                 // block-row 0..hy-1
-                            const uint32_t ro = S > 1 ? dnb.div(b) : 0u;       // owner slab
-                            const uint32_t bl = b - ro * g.nb;
-                            const uint32_t idx = ip * g.slab + (sy * g.nb + bl) * g.Z + kp;
-                            if (S > 1) st_cluster_f32(mapa(c_base + 4 * idx, ro), __int_as_float(pr[j].y));
-                            else C[idx] = __int_as_float(pr[j].y);
-                        }
-                        pre = sat_add(pre, (uint32_t)pr[j].x + 1u);
-                    }
-                }
-                carry = sat_add(carry, ttot);
-                __syncthreads();   // s_wt is reused by the next tile
-            }
-            if (bad) atomicOr(err, 1);
+    }
+    __syncthreads();
+    for (int k = 0;; ++k) {
+        const FDDesc& d = s_desc[k & 1];
+        if (d.ui >= n_list) break;
+        const DecUnitDev du = d.du;
+        const InvUnitDev iu = d.iu;
+        const int K = d.K;
+        la.slot      = &s_desc[k & 1];
+        la.next_slot = &s_desc[(k + 1) & 1];
+        la.ui_prev   = la.next_slot->ui;
+        const bool have_next = la.next_slot->ui < n_list;
+#define WC_FD_UNIT(GEOM) fd_unit<S, NT>(GEOM, du, iu, K, Sh, la, rank, xph, err, have_next)
+        if constexpr (STATIC) {
+            constexpr int CUBE = S == 1 ? 32 : 64;
+            WC_FD_UNIT((SGeom<CUBE, CUBE, CUBE, 8, S>()));
+        } else {
+            FGeom g;
+            fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, S, 32768, g);   // same rule as fused_decode_class
+            WC_FD_UNIT(g);
         }
-        // all scatters (local and remote) are complete and visible before anybody reads its C
-        if (S > 1) cluster_sync_all(); else __syncthreads();
-
-        // 3. inverse transform (X, then Y, then Z), two c-adjacent blocks per thread, and store the slab
-        {
-            const uint32_t m_hx = fdiv_magic(g.hx), m_cq = fdiv_magic(g.ncq);
-            const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
-            const int npc = g.hz >> 1;
-            const size_t es = iu.dtype == WC_F64 ? 8 : 4;
-            const size_t row_bytes = (size_t)g.X * es, plane_bytes = row_bytes * g.Y;
-            char* out0 = static_cast<char*>(iu.out) + (size_t)(2 * b0) * row_bytes;
-            for (int q = tid; q < g.npairs; q += NT) {
-                const uint32_t cp2 = q & 1, t1 = q >> 1;
-                const uint32_t t2 = fdiv(t1, m_hx), a = t1 - t2 * g.hx;
-                const uint32_t bl = fdiv(t2, m_cq), cq = t2 - bl * g.ncq;
-                const int cpi = 2 * cq + cp2;
-                if (cpi >= npc) continue;
-                const float* csrc = C + a * g.slab + bl * g.Z + 2 * cpi;
-                float2 v[8];
-#pragma unroll
-                for (int o = 0; o < 8; ++o)
-                    v[o] = *reinterpret_cast<const float2*>(csrc + (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) ihaar_pair2(v[2 * k], v[2 * k + 1]);                 // X
-#pragma unroll
-                for (int zi = 0; zi < 2; ++zi)
-#pragma unroll
-                    for (int xi = 0; xi < 2; ++xi) ihaar_pair2(v[zi * 4 + xi], v[zi * 4 + 2 + xi]);   // Y
-#pragma unroll
-                for (int k = 0; k < 4; ++k) ihaar_pair2(v[k], v[4 + k]);                         // Z
-                char* p0 = out0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes + (size_t)a * 2 * es;
-#pragma unroll
-                for (int zi = 0; zi < 2; ++zi)
-#pragma unroll
-                    for (int yi = 0; yi < 2; ++yi) {
-                        const float2 lo = v[zi * 4 + yi * 2], hi = v[zi * 4 + yi * 2 + 1];   // xi = 0, 1
-                        char* pa = p0 + zi * plane_bytes + yi * row_bytes;        // block c:   planes 4cpi + zi
-                        char* pb = pa + 2 * plane_bytes;                          // block c+1: planes 4cpi + 2 + zi
-                        if (iu.dtype == WC_F64) {
-                            *reinterpret_cast<double2*>(pa) = make_double2((double)lo.x, (double)hi.x);
-                            *reinterpret_cast<double2*>(pb) = make_double2((double)lo.y, (double)hi.y);
-                        } else {
-                            *reinterpret_cast<float2*>(pa) = make_float2(lo.x, hi.x);
-                            *reinterpret_cast<float2*>(pb) = make_float2(lo.y, hi.y);
-                        }
-                    }
-            }
-        }
-        if (S == 1) __syncthreads();   // C is rewritten by the next unit (S > 1: the cluster barrier of step 1)
+#undef WC_FD_UNIT
     }
     if (S > 1) cluster_sync_all();     // no CTA may exit while peers can still write into its smem
 }
 
-template <int S, int NT>
+template <int S, int NT, bool STATIC>
 static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                              int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter) {
     static int max_clusters = 0;
-    auto kern = k_fused_decompress<S, NT>;
-    constexpr int smem = (32768 + F_CPAD) * 4 + 512;
+    auto kern = k_fused_decompress<S, NT, STATIC>;
+    constexpr int smem = (32768 + F_CPAD) * 4 + 1024;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -1208,22 +1356,32 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
     return cudaGetLastError();
 }
 
-// Which fused-decompress class a unit belongs to (0 = generic): same geometry rules as compress, plus the
-// output pointer alignment for the vector stores.
+// Which fused-decompress class a unit belongs to (FUSED_CLS_*, 0 = generic): same geometry rules as compress,
+// plus the output pointer alignment for the vector stores.
 int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_ptr) {
-    if (reinterpret_cast<uintptr_t>(out_ptr) & (out_dtype == WC_F64 ? 15u : 7u)) return 0;
+    if (reinterpret_cast<uintptr_t>(out_ptr) & (out_dtype == WC_F64 ? 15u : 7u)) return FUSED_CLS_NONE;
+    if (nx == 32 && ny == 32 && nz == 32) return FUSED_CLS_CUBE32;
+    if (nx == 64 && ny == 64 && nz == 64) return FUSED_CLS_CUBE64;
     FGeom g;
-    if (fused_geom(nx, ny, nz, WC_F64, 1, 32768, g)) return 1;   // WC_F64: keeps the X*es % 16 rule valid for both
-    if (fused_geom(nx, ny, nz, WC_F64, 8, 32768, g)) return 8;
-    return 0;
+    if (fused_geom(nx, ny, nz, WC_F64, 1, 32768, g)) return FUSED_CLS_R1;   // WC_F64: keeps the X*es % 16 rule valid for both
+    if (fused_geom(nx, ny, nz, WC_F64, 8, 32768, g)) return FUSED_CLS_R8;
+    return FUSED_CLS_NONE;
 }
 
-cudaError_t launch_fused_decompress(int cluster, const DecUnitDev* dec, const InvUnitDev* inv,
+cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
                                     cudaStream_t st, LaunchStats* ls, int* work_counter) {
     if (n_list <= 0) return cudaSuccess;
-    if (cluster == 1) return launch_fd<1, 512>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
-    if (cluster == 8) return launch_fd<8, 512>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, nullptr);
+    switch (fused_cls) {
+    case FUSED_CLS_R1:
+        return launch_fd<1, 512, false>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    case FUSED_CLS_R8:
+        return launch_fd<8, 512, false>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, nullptr);
+    case FUSED_CLS_CUBE32:
+        return launch_fd<1, 1024, true>(KID_FUSED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    case FUSED_CLS_CUBE64:
+        return launch_fd<8, 1024, true>(KID_FUSED_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, nullptr);
+    }
     return cudaErrorInvalidValue;
 }
 

@@ -24,7 +24,7 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
                                   const int* unit_list, int n_list, double one_minus_keep,
                                   const u64* global_key, int sm_count, cudaStream_t st,
                                   LaunchStats* ls, int* work_counter = nullptr);
-cudaError_t launch_fused_decompress(int cluster, const DecUnitDev* dec, const InvUnitDev* inv,
+cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
                                     cudaStream_t st, LaunchStats* ls, int* work_counter = nullptr);
 
