@@ -967,6 +967,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
         if (!fused_decode_available()) cls = cls > 0 ? 0 : cls;
         coef_off[i] = coef_floats;
         if (cls == 0) coef_floats += align_up((size_t)total, 4);
+        else if (cls > 0) coef_floats += align_up(2 * fused_decode_table_entries(cls, jobs[i].nx), 4);   // int2 segment table
         du[i].pairs      = jobs[i].pairs_dev;
         du[i].npairs_dev = jobs[i].npairs_dev;
         du[i].npairs     = jobs[i].npairs;
@@ -1015,51 +1016,24 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
     CTX_CUDA(ctx, launch_inverse_generic(d_inv_units.as<InvUnitDev>(), d_inv_tiles.as<int2>(),
                                          (int)xtiles.size(), ctx->stream, &ctx->ls));
     size_t n_fused = 0;
-    bool any_cluster = false, any_single = false;
-    for (int k = 0; k < FL_N; ++k) {
-        n_fused += fl[k].size();
-        if (!fl[k].empty()) (fl_is_cluster(k) ? any_cluster : any_single) = true;
-    }
+    for (int k = 0; k < FL_N; ++k) n_fused += fl[k].size();
     if (n_fused) {
         CTX_CUDA(ctx, d_fused_list.reserve(sizeof(int) * n_fused));
+        CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
         int* dl = d_fused_list.as<int>();
-        size_t off[FL_N], o = 0;
-        for (int k = 0; k < FL_N; ++k) {
-            off[k] = o;
-            if (!fl[k].empty())
-                CTX_CUDA(ctx, cudaMemcpyAsync(dl + o, fl[k].data(), sizeof(int) * fl[k].size(),
-                                              cudaMemcpyHostToDevice, ctx->stream));
-            o += fl[k].size();
-        }
-        if (!ctx->s_aux) {
-            CTX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
-            CTX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-            CTX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-            CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
-        }
-        // cluster kernels on the ctx stream, single-CTA kernels (dynamic unit hand-out) on the second stream
-        // when both kinds are present — see plan_pack
-        const bool overlap = any_cluster && any_single && !ctx->ls.profile && ctx->opt_overlap;
-        if (overlap) {
-            CTX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-            CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
-        }
+        size_t o = 0;
+        // every fused decode kernel is a persistent one-CTA-per-SM kernel with dynamic item hand-out
         for (int k = 0; k < FL_N; ++k) {
             if (fl[k].empty()) continue;
-            cudaStream_t st = (overlap && !fl_is_cluster(k)) ? ctx->s_aux : ctx->stream;
-            int* counter = nullptr;
-            if (!fl_is_cluster(k)) {
-                counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
-                CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
-            }
+            CTX_CUDA(ctx, cudaMemcpyAsync(dl + o, fl[k].data(), sizeof(int) * fl[k].size(),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+            int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
+            CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
             CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
-                                                  d_inv_units.as<InvUnitDev>(), dl + off[k],
-                                                  (int)fl[k].size(), d_err.as<int>(), ctx->sm_count, st,
-                                                  &ctx->ls, counter));
-        }
-        if (overlap) {
-            CTX_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->s_aux));
-            CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+                                                  d_inv_units.as<InvUnitDev>(), dl + o,
+                                                  (int)fl[k].size(), d_err.as<int>(), ctx->sm_count,
+                                                  ctx->stream, &ctx->ls, counter));
+            o += fl[k].size();
         }
     }
     return WC_OK;

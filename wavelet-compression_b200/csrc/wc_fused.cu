@@ -930,12 +930,18 @@ cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset) {
 // =====================================================================================================
 // Fused decompress: rle_decode (src/decompressor.cpp:14-30) + inverse_wavelet_decompose (:79-159)
 // =====================================================================================================
-// Work item = (unit, y-slab r of S).  The CTA zero-fills its share C of the coefficient array in shared
-// memory, walks the unit's WHOLE pair list once (block-wide prefix sum of run+1 -> flat index of every
-// pair; the S slabs of a unit each do this — the list comes from L2 after the first — and keep only the
-// pairs that land in their own segments), then inverts two c-adjacent blocks per thread straight from C
-// and writes its slab of the box with coalesced 8/16-byte stores.  No coefficient scratch in HBM:
-// traffic = 8K (pairs, once from HBM) + 4N or 8N (box).
+// Work item = (unit, y-slab r of S), one CTA per item, no clusters.  The CTA zero-fills its share C of the
+// coefficient array in shared memory, decodes the pairs that land in its segments, then inverts two
+// c-adjacent blocks per thread straight from C and writes its slab of the box with coalesced 8/16-byte
+// stores.  No coefficient scratch in HBM.
+//   S = 1 (<= 32768 cells): the item is the whole unit; its pair list is walked once with a block-wide
+//          prefix sum of run+1 (flat index of every pair).  Traffic = 8K + 4N (or 8N).
+//   S = 8 (<= 262144 cells): a slab's coefficients are 2*X segments of nb*Z consecutive flat indices.  A
+//          small index kernel (k_seg_index) first walks each unit's list once and records, for every
+//          segment boundary, the first pair at/after it and that pair's flat index; the 8 slab items of a
+//          unit are then independent: a warp decodes one segment at a time from its own sub-range of the
+//          list.  Traffic = 16K + 4N: the list is read twice, which costs less than the cluster-wide
+//          barriers and the DSMEM scatter of the previous design (3x faster on 64^3 boxes).
 struct FastDiv {     // q / d, exact: magic multiply when q_max * d < 2^32, plain division otherwise
     uint32_t d, m;
     __device__ __forceinline__ void init(uint32_t div, uint32_t qmax) {
@@ -958,29 +964,163 @@ __device__ __forceinline__ void ihaar_pair2(float2& avg, float2& diff) {
     diff = m;
 }
 
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+constexpr int FD_PPT = 8;        // pairs per thread per tile of the block-wide scan
+
+// Loads FD_PPT consecutive pairs starting at p (a multiple of FD_PPT); pairs past k1 read as (0, 0).
+__device__ __forceinline__ void fd_load_tile(const int2* pairs, bool vec16, int p, int k1, int2 (&pr)[FD_PPT]) {
+    if (vec16 && p + FD_PPT <= k1) {
+#pragma unroll
+        for (int j = 0; j < FD_PPT; j += 2) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(pairs + p + j));
+            pr[j] = make_int2(v.x, v.y); pr[j + 1] = make_int2(v.z, v.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < FD_PPT; ++j) pr[j] = (p + j < k1) ? __ldg(pairs + p + j) : make_int2(0, 0);
+    }
 }
 
-// Unit descriptors are staged two units ahead through shared memory, like FLookahead of the compress
-// kernels; K (which may live on the device after a plan round trip) is resolved one unit ahead, in time
-// for the L2 prefetch of the next unit's pair list.
+// Block-wide exclusive prefix of run+1 over one tile (saturating; negative runs are flagged, count as 0 and
+// are skipped by the callers).  wt = 32 words of shared memory, alternating between two buffers per tile so
+// that one barrier per tile suffices.  Returns this thread's exclusive prefix (tile-relative) and the tile total.
+template <int NT>
+__device__ __forceinline__ uint32_t fd_tile_scan(const int2 (&pr)[FD_PPT], int nvalid, uint32_t* wt, bool& bad,
+                                                 uint32_t& ttot) {
+    constexpr int NW = NT / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < FD_PPT; ++j) {
+        const bool in = j < nvalid;
+        if (in && pr[j].x < 0) bad = true;
+        s = sat_add(s, (in && pr[j].x >= 0) ? (uint32_t)pr[j].x + 1u : 0u);
+    }
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = sat_add(inc, v);
+    }
+    if (lane == 31) wt[warp] = inc;
+    __syncthreads();
+    // prefix over the warp totals: one warp-scan instead of NW shared loads per thread
+    uint32_t winc = lane < NW ? wt[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc = sat_add(winc, v);
+    }
+    ttot = __shfl_sync(0xffffffffu, winc, 31);
+    uint32_t wpre = __shfl_sync(0xffffffffu, winc, (warp + 31) & 31);   // inclusive up to warp-1
+    if (warp == 0) wpre = 0;
+    uint32_t exl = __shfl_up_sync(0xffffffffu, inc, 1);                 // exclusive prefix inside the warp
+    if (lane == 0) exl = 0;
+    return sat_add(wpre, exl);
+}
+
+// ---- segment index of the slab-decoded units --------------------------------------------------------
+// tab[m] = (first pair p whose flat index F_p >= m * seglen, F_p), m = 0 .. nseg; pairs at or past `total`
+// (and everything after them) are dropped as rle_decode does: tab[m >= first uncovered] = (Kend, total).
+// The table lives where the generic path keeps its coefficient scratch pointer (DecUnitDev::coef).
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
+k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
+            const int* __restrict__ unit_list, int n_list, int* __restrict__ err) {
+    __shared__ uint32_t s_wt[2][32];
+    __shared__ int s_kend, s_flast;
+    const int tid = threadIdx.x;
+    for (int ui = blockIdx.x; ui < n_list; ui += gridDim.x) {
+        const int uid = unit_list[ui];
+        const DecUnitDev du = dec[uid];
+        const InvUnitDev iu = inv[uid];
+        FGeom g;
+        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, 8, 32768, g);
+        const uint32_t seglen = (uint32_t)g.seglen, total = (uint32_t)du.total;
+        const int nseg = g.nseg * 8;                       // == total / seglen
+        int2* const tab = reinterpret_cast<int2*>(du.coef);
+        const int K = du.npairs_dev ? *du.npairs_dev : du.npairs;
+        const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
+        const bool vec16 = (reinterpret_cast<uintptr_t>(pairs) & 15u) == 0;
+        FastDiv dsl;
+        dsl.init(seglen, total);
+        if (tid == 0) { s_kend = 0; s_flast = -1; }
+        __syncthreads();
+        bool bad = false;
+        uint32_t carry = 0;
+        int kend = 0, flast = -1;
+        int tile = 0;
+        int2 pr[FD_PPT], nxt[FD_PPT];
+        fd_load_tile(pairs, vec16, tid * FD_PPT, K, nxt);
+#pragma unroll 1
+        for (int p0 = 0; p0 < K; p0 += NT * FD_PPT, ++tile) {
+            const int p = p0 + tid * FD_PPT;
+#pragma unroll
+            for (int j = 0; j < FD_PPT; ++j) pr[j] = nxt[j];
+            if (p0 + NT * FD_PPT < K) fd_load_tile(pairs, vec16, p + NT * FD_PPT, K, nxt);   // next tile in flight
+            uint32_t ttot;
+            uint32_t pre = sat_add(carry, fd_tile_scan<NT>(pr, K - p, s_wt[tile & 1], bad, ttot));
+            // last pair of this thread's group that is still inside the box (flat indices only grow)
+            int gl = -1, gk = 0;
+            {
+                uint32_t rp = pre;
+#pragma unroll
+                for (int j = 0; j < FD_PPT; ++j) {
+                    if (p + j < K && pr[j].x >= 0) {
+                        const uint32_t f = sat_add(rp, (uint32_t)pr[j].x);
+                        if (f < total) { gl = (int)f; gk = p + j + 1; }
+                        rp = sat_add(rp, (uint32_t)pr[j].x + 1u);
+                    }
+                }
+            }
+            if (gl >= 0) { flast = gl; kend = gk; }
+            // the group covers the flat indices (pre - 1, gl]: most groups cross no segment boundary
+            if (gl >= 0) {
+                uint32_t m = pre == 0 ? 0u : dsl.div(pre - 1u) + 1u;     // next boundary to assign ...
+                uint32_t fb = m * seglen;                                 // ... and its flat index
+                if ((uint32_t)gl >= fb) {
+#pragma unroll
+                    for (int j = 0; j < FD_PPT; ++j) {
+                        if (p + j < K && pr[j].x >= 0) {
+                            const uint32_t f = sat_add(pre, (uint32_t)pr[j].x);
+                            if (f < total)
+                                for (; fb <= f; fb += seglen, ++m) tab[m] = make_int2(p + j, (int)f);
+                            pre = sat_add(pre, (uint32_t)pr[j].x + 1u);
+                        }
+                    }
+                }
+            }
+            carry = sat_add(carry, ttot);
+        }
+        if (bad) atomicOr(err, 1);
+        if (kend > 0) { atomicMax(&s_kend, kend); atomicMax(&s_flast, flast); }
+        __syncthreads();
+        const int ke = s_kend, fl = s_flast;
+        for (int m = (fl < 0 ? 0 : (int)dsl.div((uint32_t)fl) + 1) + tid; m <= nseg; m += NT)
+            tab[m] = make_int2(ke, (int)total);
+        __syncthreads();
+    }
+}
+
+// Unit descriptors are staged two items ahead through shared memory, like FLookahead of the compress
+// kernels; K (which may live on the device after a plan round trip) is resolved one item ahead, in time
+// for the L2 prefetch of the next unit's pair list (S = 1).
 struct __align__(8) FDDesc {
     DecUnitDev du;      // 40 bytes
     InvUnitDev iu;      // 32 bytes
     int        K;       // resolved pair count
-    int        uid, ui; // index into dec[] / inv[]; position in the work list (>= n_list: no more work)
+    int        uid, ui; // index into dec[] / inv[]; position in the item list (>= n_items: no more work)
     int        pad;
 };
 static_assert(sizeof(DecUnitDev) == 40 && sizeof(InvUnitDev) == 32 && sizeof(FDDesc) == 88, "FDDesc layout");
+template <int S>
 struct FDLookahead {
     const DecUnitDev* dec;
     const InvUnitDev* inv;
     const int*        unit_list;
     int*              work_counter;
-    int               n_list, stride;
-    FDDesc*           slot;        // unit k's slot: receives unit k+2
-    FDDesc*           next_slot;   // unit k+1: descriptor present, K still to be resolved
+    int               n_items, stride;    // items = S per listed unit: item i -> unit_list[i / S], slab i % S
+    FDDesc*           slot;        // item k's slot: receives item k+2
+    FDDesc*           next_slot;   // item k+1: descriptor present, K still to be resolved
     int               ui_prev;
     int               idx, uid, kreg;   // thread 0 only
     __device__ __forceinline__ void resolve_k_issue() {
@@ -991,12 +1131,12 @@ struct FDLookahead {
             if (kp) asm volatile("ld.global.s32 %0, [%1];" : "=r"(kreg) : "l"(kp));
         }
     }
-    __device__ __forceinline__ void stage1() {          // top of the unit
+    __device__ __forceinline__ void stage1() {          // top of the item
         idx = work_counter ? atomicAdd(work_counter, 1) : ui_prev + stride;
     }
     __device__ __forceinline__ void stage2() {          // after the first barrier: slot k&1 is free now
         uid = -1;
-        if (idx < n_list) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(uid) : "l"(unit_list + idx));
+        if (idx < n_items) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(uid) : "l"(unit_list + idx / S));
     }
     __device__ __forceinline__ void resolve_k_store() { next_slot->K = kreg; }   // before the post-scatter barrier
     __device__ __forceinline__ void stage3() {
@@ -1018,48 +1158,30 @@ struct FDLookahead {
     __device__ __forceinline__ void stage4() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 };
 
-struct FDShared {
-    float*    C;
-    uint32_t* s_wt;     // [2][32] warp totals (double-buffered per tile)
-    u64*      xs;       // [2][8] exchange slots
-    uint32_t  xb;       // mbarrier
-    uint32_t  c_base;
-};
-
-// One unit of the fused decompress.  S = 1: one CTA per unit.  S = 8: an 8-CTA cluster per unit; CTA r owns
-// the y-slab r of the box (and the matching segments of C), walks 1/8 of the pair list, and scatters every
-// value into the OWNER's shared memory through DSMEM (st.shared::cluster) — the list is read from HBM once.
+// One work item (unit, slab `rank`) of the fused decompress.  G: FGeom or SGeom<..., S>.
 template <int S, int NT, class G>
 __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const InvUnitDev& iu, const int K,
-                                        const FDShared& Sh, FDLookahead& la, const uint32_t rank,
-                                        uint32_t& xph, int* __restrict__ err, const bool have_next) {
-    constexpr int NW  = NT / 32;
-    constexpr int PPT = 8;                                     // pairs per thread per tile
-    float* const C = Sh.C;
+                                        float* const C, uint32_t* const s_wt, FDLookahead<S>& la,
+                                        const uint32_t rank, int* __restrict__ err, const bool have_next) {
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b0 = rank * g.nb;
     const uint32_t total = (uint32_t)du.total;
+    WC_PHASE_CLOCK(t0);
     if (tid == 0) { la.stage1(); la.resolve_k_issue(); }
 
-    // this CTA's share of the pair list: [k0, k1)
-    const int per = S > 1 ? (((K + S - 1) / S + PPT - 1) / PPT) * PPT : K;
-    const int k0 = min(K, (int)rank * per), k1 = min(K, k0 + per);
     const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
-    const bool vec16 = (reinterpret_cast<uintptr_t>(pairs) & 15u) == 0;   // k0 is a multiple of 8
-    auto load_tile = [&](int p, int2 (&pr)[PPT]) {
-        if (vec16 && p + PPT <= k1) {
-#pragma unroll
-            for (int j = 0; j < PPT; j += 2) {
-                const int4 v = *reinterpret_cast<const int4*>(pairs + p + j);
-                pr[j] = make_int2(v.x, v.y); pr[j + 1] = make_int2(v.z, v.w);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < PPT; ++j) pr[j] = (p + j < k1) ? pairs[p + j] : make_int2(0, 0);
-        }
-    };
-    int2 pr[PPT];
-    if (S == 1) load_tile(k0 + tid * PPT, pr);                  // in flight during the zero-fill
+    const bool vec16 = (reinterpret_cast<uintptr_t>(pairs) & 15u) == 0;
+    int2 pr[FD_PPT];
+    int2 te = make_int2(0, 0);
+    if (S == 1) {
+        fd_load_tile(pairs, vec16, tid * FD_PPT, K, pr);           // in flight during the zero-fill
+    } else {
+        // segment table entries of this warp's segments (<= 16 per warp): lane 2q + e <- tab[m(q) + e]
+        const int sg = warp + (lane >> 1) * NW;
+        if (sg < g.nseg)
+            te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sg >> 1) * (2 * S) + (sg & 1) * S + (int)rank + (lane & 1));
+    }
 
     // 1. zero-fill C (rle_decode starts from zeros, src/decompressor.cpp:17)
     {
@@ -1068,120 +1190,98 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
 #pragma unroll 4
         for (int i = tid; i < (nwords + 3) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // every CTA of the cluster has finished reading its previous C and zeroed the new one before
-    // anybody scatters into it
-    if (S > 1) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
+    WC_PHASE_CLOCK(t1);
     if (tid == 0) la.stage2();
+    WC_PHASE_CLOCK(t2);
 
-    bool bad = false;
-    uint32_t carry = 0;
-    if (S > 1) {
-        // 2a. sum of (run + 1) over the share, all-gathered -> where this share starts in f
-        uint32_t s = 0;
-        for (int p = k0 + tid; p < k1; p += NT) {
-            const int run = pairs[p].x;
-            if (run < 0) bad = true;
-            s = sat_add(s, (uint32_t)max(run, 0) + 1u);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s = sat_add(s, __shfl_xor_sync(0xffffffffu, s, o));
-        if (lane == 0) Sh.s_wt[warp] = s;
-        __syncthreads();
-        uint32_t tot = lane < NW ? Sh.s_wt[lane] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot = sat_add(tot, __shfl_xor_sync(0xffffffffu, tot, o));
-        __syncthreads();
-        const uint32_t par = xph & 1;
-        if (tid < S) {
-            st_cluster_u64(mapa(smem_u32(&Sh.xs[par * 8 + rank]), tid), (u64)tot);
-            mbar_arrive_remote(mapa(Sh.xb, tid));
-        }
-        mbar_wait_cluster(Sh.xb, par);
-        ++xph;
-#pragma unroll
-        for (int r = 0; r < S; ++r)
-            if (r < (int)rank) carry = sat_add(carry, (uint32_t)Sh.xs[par * 8 + r]);
-    }
-    // 2b. flat index of every pair of the share; scatter into the owner's C
-    {
-        FastDiv dyz, dz, dnb;
-        if (!G::is_static) {
-            dyz.init((uint32_t)(g.Y * g.Z), total);
-            dz.init((uint32_t)g.Z, (uint32_t)(g.Y * g.Z));
-            dnb.init((uint32_t)g.nb, (uint32_t)g.hy);
-        }
+    // 2. decode the pairs that land in this item's segments
+    if (S == 1) {
+        // block-wide scan over the whole list; flat index -> (i', j', k') -> padded index in C
+        FastDiv dyz;
+        if (!G::is_static) dyz.init((uint32_t)(g.Y * g.Z), total);
+        bool bad = false;
+        uint32_t carry = 0;
         int tile = 0;
 #pragma unroll 1
-        for (int p0 = k0; p0 < k1; p0 += NT * PPT, ++tile) {
-            const int p = p0 + tid * PPT;
-            if (S > 1 || tile > 0) load_tile(p, pr);
-            uint32_t s = 0;
-#pragma unroll
-            for (int j = 0; j < PPT; ++j) {
-                if (p + j < k1) {
-                    if (pr[j].x < 0) bad = true;
-                    s = sat_add(s, (uint32_t)max(pr[j].x, 0) + 1u);
-                }
-            }
-            uint32_t inc = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc = sat_add(inc, v);
-            }
-            uint32_t* const wt = Sh.s_wt + (tile & 1) * 32;     // double-buffered: one barrier per tile
-            if (lane == 31) wt[warp] = inc;
-            __syncthreads();
-            // prefix over the warp totals: one warp-scan instead of NW shared loads per thread
-            uint32_t wv = lane < NW ? wt[lane] : 0u, winc = wv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc = sat_add(winc, v);
-            }
-            const uint32_t ttot = __shfl_sync(0xffffffffu, winc, 31);
-            uint32_t wpre = __shfl_sync(0xffffffffu, winc, (warp + 31) & 31);   // inclusive up to warp-1
-            if (warp == 0) wpre = 0;
-            uint32_t exl = __shfl_up_sync(0xffffffffu, inc, 1);     // exclusive prefix inside the warp
-            if (lane == 0) exl = 0;
-            uint32_t pre = sat_add(sat_add(carry, wpre), exl);       // exclusive prefix of this thread
-#pragma unroll
-            for (int j = 0; j < PPT; ++j) {
-                if (p + j < k1 && pr[j].x >= 0) {
-                    const uint32_t f = sat_add(pre, (uint32_t)pr[j].x);
-                    if (f < total) {
-                        const uint32_t YZ = (uint32_t)(g.Y * g.Z);
-                        const uint32_t ip = G::is_static ? f / YZ : dyz.div(f), rem = f - ip * YZ;
-                        const uint32_t jp = G::is_static ? rem / (uint32_t)g.Z : dz.div(rem), kp = rem - jp * (uint32_t)g.Z;
-                        const uint32_t sy = jp >= (uint32_t)g.hy ? 1u : 0u;
-                        const uint32_t b  = jp - sy * g.hy;                 // block-row 0..hy-1
-                        const uint32_t ro = S > 1 ? (G::is_static ? b / (uint32_t)g.nb : dnb.div(b)) : 0u;   // owner slab
-                        const uint32_t bl = b - ro * g.nb;
-                        const uint32_t idx = ip * g.slab + (sy * g.nb + bl) * g.Z + kp;
-                        if (S > 1) st_cluster_f32(mapa(Sh.c_base + 4 * idx, ro), __int_as_float(pr[j].y));
-                        else C[idx] = __int_as_float(pr[j].y);
-                    }
-                    pre = sat_add(pre, (uint32_t)pr[j].x + 1u);
-                }
-            }
+        for (int p0 = 0; p0 < K; p0 += NT * FD_PPT, ++tile) {
+            const int p = p0 + tid * FD_PPT;
+            if (tile > 0) fd_load_tile(pairs, vec16, p, K, pr);
+            uint32_t ttot;
+            uint32_t pre = sat_add(carry, fd_tile_scan<NT>(pr, K - p, s_wt + (tile & 1) * 32, bad, ttot));
             carry = sat_add(carry, ttot);
+            // carry < 2^30: nothing saturated up to and including this tile -> plain adds are exact
+            const bool plain = carry < 0x40000000u;
+#pragma unroll
+            for (int j = 0; j < FD_PPT; ++j) {
+                const int  run  = pr[j].x;
+                const bool live = (p + j < K) && run >= 0;
+                const uint32_t f = plain ? pre + (uint32_t)run : sat_add(pre, (uint32_t)max(run, 0));
+                // S == 1: the CTA owns every segment; C is the flat array with F_PAD words after every i' slab
+                const uint32_t ip  = G::is_static ? f / (uint32_t)(g.Y * g.Z) : dyz.div(f);
+                if (live && f < total) C[f + F_PAD * ip] = __int_as_float(pr[j].y);
+                const uint32_t nx = plain ? pre + (uint32_t)run + 1u : sat_add(pre, (uint32_t)max(run, 0) + 1u);
+                pre = live ? nx : pre;
+            }
         }
         if (bad) atomicOr(err, 1);
+    } else {
+        // one warp per segment: the pairs [tab[m].x, tab[m+1].x) start at flat index tab[m].y >= m * seglen.
+        // Lanes 2q, 2q+1 hold the table entries of the warp's q-th segment (loaded before the zero-fill);
+        // up to 8 chunks of 32 pairs are in flight per segment before the first one is decoded.
+        const uint32_t seglen = (uint32_t)g.seglen;
+        int q = 0;
+#pragma unroll 1
+        for (int sg = warp; sg < g.nseg; sg += NW, ++q) {
+            const int i = sg >> 1, half = sg & 1;
+            const int m = i * (2 * S) + half * S + (int)rank;
+            const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * q), e0y = __shfl_sync(0xffffffffu, te.y, 2 * q);
+            const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * q + 1);
+            float* const cseg = C + i * g.slab + half * g.seglen;    // C index of flat index m * seglen
+            const uint32_t fseg = (uint32_t)m * seglen;
+            uint32_t base = (uint32_t)e0y;                           // flat index of the first pair
+#pragma unroll 1
+            for (int c0 = e0x; c0 < e1x; c0 += 256) {
+                int2 pv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int p = c0 + 32 * c + lane;
+                    pv[c] = make_int2(-1, 0);
+                    if (p < e1x) pv[c] = __ldg(pairs + p);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c0 + 32 * c < e1x) {                         // warp-uniform
+                        const int p = c0 + 32 * c + lane;
+                        const bool live = pv[c].x >= 0;
+                        // the segment's first pair sits at `base` itself; every later one adds run + 1
+                        uint32_t inc = (live && p != e0x) ? (uint32_t)pv[c].x + 1u : 0u;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += v;
+                        }
+                        const uint32_t f = base + inc;
+                        if (live && f - fseg < seglen && f < total) cseg[f - fseg] = __int_as_float(pv[c].y);
+                        base += __shfl_sync(0xffffffffu, inc, 31);
+                    }
+                }
+            }
+        }
     }
+    WC_PHASE_CLOCK(t3);
     if (tid == 0) la.resolve_k_store();
-    // all scatters (local and remote) are complete and visible before anybody reads its C
-    if (S > 1) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
 
-    // L2 prefetch of this CTA's share of the NEXT unit's pair list: lands while this unit is inverted
-    if (have_next) {
+    // L2 prefetch of the NEXT unit's pair list (S = 1): lands while this unit is inverted
+    if (S == 1 && have_next) {
         const int Kn = la.next_slot->K;
-        const int pern = S > 1 ? (((Kn + S - 1) / S + PPT - 1) / PPT) * PPT : Kn;
-        const int n0 = min(Kn, (int)rank * pern), n1 = min(Kn, n0 + pern);
-        const char* base = reinterpret_cast<const char*>(la.next_slot->du.pairs) + (size_t)n0 * 8;
-        const int nlines = ((n1 - n0) * 8 + 127) / 128;
+        const char* base = reinterpret_cast<const char*>(la.next_slot->du.pairs);
+        const int nlines = (Kn * 8 + 127) / 128;
         for (int i = tid; i < nlines; i += NT)
             asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)i * 128));
     }
+    WC_PHASE_CLOCK(t4);
     if (tid == 0) la.stage3();
 
     // 3. inverse transform (X, then Y, then Z), two c-adjacent blocks per thread, and store the slab
@@ -1220,11 +1320,11 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
                     char* pa = p0 + zi * plane_bytes + yi * row_bytes;        // block c:   planes 4cpi + zi
                     char* pb = pa + 2 * plane_bytes;                          // block c+1: planes 4cpi + 2 + zi
                     if (iu.dtype == WC_F64) {
-                        *reinterpret_cast<double2*>(pa) = make_double2((double)lo.x, (double)hi.x);
-                        *reinterpret_cast<double2*>(pb) = make_double2((double)lo.y, (double)hi.y);
+                        __stcs(reinterpret_cast<double2*>(pa), make_double2((double)lo.x, (double)hi.x));
+                        __stcs(reinterpret_cast<double2*>(pb), make_double2((double)lo.y, (double)hi.y));
                     } else {
-                        *reinterpret_cast<float2*>(pa) = make_float2(lo.x, hi.x);
-                        *reinterpret_cast<float2*>(pb) = make_float2(lo.y, hi.y);
+                        __stcs(reinterpret_cast<float2*>(pa), make_float2(lo.x, hi.x));
+                        __stcs(reinterpret_cast<float2*>(pb), make_float2(lo.y, hi.y));
                     }
                 }
         };
@@ -1238,11 +1338,18 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         }
     }
     if (tid == 0) la.stage4();
-    // C is zero-filled again by the next unit (the cluster barrier of step 1 comes AFTER the zero-fill, so the
-    // cluster variant needs this CTA barrier too), and the staged descriptor becomes visible to the CTA
+    // C is zero-filled again by the next item, and the staged descriptor becomes visible to the CTA
     __syncthreads();
+#ifdef WC_PHASE_PROFILE
+    if (tid == 0 && blockIdx.x < 1024) {   // 0 zero-fill, 1 -, 2 decode, 3 barrier + prefetch, 4 inverse + store
+        long long t5 = clock64();
+        unsigned long long* pc = g_phase_cycles[blockIdx.x];
+        pc[0] += t1 - t0; pc[1] += t2 - t1; pc[2] += t3 - t2; pc[3] += t4 - t3; pc[4] += t5 - t4; pc[5] += 1;
+    }
+#endif
 }
 
+// STATIC: every unit of the list is the cube this variant is specialised for (32^3 for S = 1, 64^3 for S = 8).
 template <int S, int NT, bool STATIC>
 __global__ void __launch_bounds__(NT, 1)
 k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
@@ -1250,36 +1357,20 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
                    int* __restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int BASE = (32768 + F_CPAD) * 4;
-    FDShared Sh;
-    Sh.C      = reinterpret_cast<float*>(smem);
-    Sh.s_wt   = reinterpret_cast<uint32_t*>(smem + BASE);          // [2][32]
-    Sh.xs     = reinterpret_cast<u64*>(smem + BASE + 256);         // [2][8]
-    Sh.xb     = smem_u32(smem + BASE + 256 + 128);
-    Sh.c_base = smem_u32(Sh.C);
-    FDDesc* const s_desc = reinterpret_cast<FDDesc*>(smem + BASE + 256 + 128 + 16);   // [2] x 88 bytes
+    float* const    C    = reinterpret_cast<float*>(smem);
+    uint32_t* const s_wt = reinterpret_cast<uint32_t*>(smem + BASE);               // [2][32]
+    FDDesc* const s_desc = reinterpret_cast<FDDesc*>(smem + BASE + 256);          // [2] x 88 bytes
     const int tid = threadIdx.x;
-    const uint32_t rank = S > 1 ? cluster_ctarank() : 0u;
-    const uint32_t cid  = S > 1 ? cluster_id_x() : blockIdx.x;
-    const uint32_t ncl  = S > 1 ? nclusters_x() : gridDim.x;
-    uint32_t xph = 0;
+    const int n_items = n_list * S;
 
-    if (S > 1) {
-        if (tid == 0) {
-            mbar_init(Sh.xb, S);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        cluster_sync_all();
-    }
-
-    // static round-robin over the clusters, or (S = 1 with a work counter) dynamic hand-out
-    FDLookahead la;
+    // dynamic hand-out of the items through a global counter (or a static stride without one)
+    FDLookahead<S> la;
     la.dec = dec; la.inv = inv; la.unit_list = unit_list;
-    la.work_counter = (S == 1) ? work_counter : nullptr;
-    la.n_list = n_list; la.stride = (int)ncl;
+    la.work_counter = work_counter;
+    la.n_items = n_items; la.stride = (int)gridDim.x;
     la.idx = 0; la.uid = -1; la.kreg = 0;
     if (tid == 0) {
-        la.ui_prev = (int)cid - (int)ncl;
+        la.ui_prev = (int)blockIdx.x - (int)gridDim.x;
         for (int k = 0; k < 2; ++k) {
             la.slot = &s_desc[k];
             la.stage1(); la.stage2(); la.stage3();
@@ -1294,15 +1385,16 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
     __syncthreads();
     for (int k = 0;; ++k) {
         const FDDesc& d = s_desc[k & 1];
-        if (d.ui >= n_list) break;
+        if (d.ui >= n_items) break;
         const DecUnitDev du = d.du;
         const InvUnitDev iu = d.iu;
         const int K = d.K;
+        const uint32_t rank = (uint32_t)(d.ui % S);
         la.slot      = &s_desc[k & 1];
         la.next_slot = &s_desc[(k + 1) & 1];
         la.ui_prev   = la.next_slot->ui;
-        const bool have_next = la.next_slot->ui < n_list;
-#define WC_FD_UNIT(GEOM) fd_unit<S, NT>(GEOM, du, iu, K, Sh, la, rank, xph, err, have_next)
+        const bool have_next = la.next_slot->ui < n_items;
+#define WC_FD_UNIT(GEOM) fd_unit<S, NT>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next)
         if constexpr (STATIC) {
             constexpr int CUBE = S == 1 ? 32 : 64;
             WC_FD_UNIT((SGeom<CUBE, CUBE, CUBE, 8, S>()));
@@ -1313,46 +1405,29 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         }
 #undef WC_FD_UNIT
     }
-    if (S > 1) cluster_sync_all();     // no CTA may exit while peers can still write into its smem
 }
 
 template <int S, int NT, bool STATIC>
 static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                              int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter) {
-    static int max_clusters = 0;
     auto kern = k_fused_decompress<S, NT, STATIC>;
     constexpr int smem = (32768 + F_CPAD) * 4 + 1024;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim         = dim3(NT);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream           = st;
-    cudaLaunchAttribute attr[1];
     if (S > 1) {
-        attr[0].id               = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = S;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs    = attr;
-        cfg.numAttrs = 1;
-        if (max_clusters == 0) {
-            cfg.gridDim = dim3(S * sm_count);
-            int nc = 0;
-            e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
-            if (e != cudaSuccess) return e;
-            if (nc < 1) return cudaErrorLaunchOutOfResources;
-            max_clusters = nc;
-        }
-    } else {
-        max_clusters = sm_count;
+        // segment tables first: one CTA per unit, a few units per SM
+        const int nb = n < 2 * sm_count ? n : 2 * sm_count;
+        ls->begin(KID_SEG_INDEX, st);
+        k_seg_index<512><<<nb, 512, 0, st>>>(dec, inv, list, n, err);
+        ls->end(st);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
     }
-    const int nc = max_clusters < n ? max_clusters : n;
-    cfg.gridDim = dim3(nc * S);
+    const long long items = (long long)n * S;
+    const int nc = (int)(sm_count < items ? sm_count : items);
     ls->begin(kid, st);
-    e = cudaLaunchKernelEx(&cfg, kern, dec, inv, list, n, err, work_counter);
+    kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter);
     ls->end(st);
-    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
@@ -1367,6 +1442,10 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
     if (fused_geom(nx, ny, nz, WC_F64, 8, 32768, g)) return FUSED_CLS_R8;
     return FUSED_CLS_NONE;
 }
+// int2 entries of the segment table a slab-decoded unit needs (0 for the other classes)
+size_t fused_decode_table_entries(int fused_cls, int nx) {
+    return (fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64) ? (size_t)(2 * nx * 8 + 1) : 0;
+}
 
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
@@ -1376,11 +1455,11 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
     case FUSED_CLS_R1:
         return launch_fd<1, 512, false>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
     case FUSED_CLS_R8:
-        return launch_fd<8, 512, false>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, nullptr);
+        return launch_fd<8, 512, false>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
     case FUSED_CLS_CUBE32:
         return launch_fd<1, 1024, true>(KID_FUSED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
     case FUSED_CLS_CUBE64:
-        return launch_fd<8, 1024, true>(KID_FUSED_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, nullptr);
+        return launch_fd<8, 1024, true>(KID_FUSED_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
     }
     return cudaErrorInvalidValue;
 }

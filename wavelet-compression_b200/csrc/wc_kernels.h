@@ -18,7 +18,7 @@ struct UnitState;
 enum KernelId {
     KID_FORWARD_GENERIC, KID_ARGMAX_FLAT, KID_FINALIZE, KID_GLOBAL_KEY, KID_COUNT, KID_SCAN, KID_EMIT,
     KID_RLE_SUMS, KID_RLE_SCAN, KID_RLE_SCATTER, KID_INVERSE_GENERIC, KID_RMSE_TILES, KID_RMSE_FINAL,
-    KID_OFFSETS, KID_GATHER, KID_FUSED_C1, KID_FUSED_C8, KID_FUSED_C1S, KID_FUSED_C8S, KID_FUSED_D1, KID_FUSED_D8, KID_FUSED_D1S, KID_FUSED_D8S, KID_MINMAX_TILES, KID_MINMAX_FINAL, KID_N
+    KID_OFFSETS, KID_GATHER, KID_FUSED_C1, KID_FUSED_C8, KID_FUSED_C1S, KID_FUSED_C8S, KID_FUSED_D1, KID_FUSED_D8, KID_FUSED_D1S, KID_FUSED_D8S, KID_SEG_INDEX, KID_MINMAX_TILES, KID_MINMAX_FINAL, KID_N
 };
 inline const char* kernel_name(int id) {
     static const char* n[KID_N] = {
@@ -27,7 +27,7 @@ inline const char* kernel_name(int id) {
         "k_inverse_generic", "k_rmse_tiles", "k_rmse_final", "k_unit_offsets", "k_gather_dense",
         "k_fused_compress<1>", "k_fused_compress<8>", "k_fused_compress<1,cube32>", "k_fused_compress<8,cube64>",
         "k_fused_decompress<1>",
-        "k_fused_decompress<8>", "k_fused_decompress<1,cube32>", "k_fused_decompress<8,cube64>", "k_minmax_tiles", "k_minmax_final" };
+        "k_fused_decompress<8>", "k_fused_decompress<1,cube32>", "k_fused_decompress<8,cube64>", "k_seg_index", "k_minmax_tiles", "k_minmax_final" };
     return (id >= 0 && id < KID_N) ? n[id] : "?";
 }
 struct LaunchStats {
@@ -96,7 +96,8 @@ struct DecUnitDev {
     const wc_pair* pairs;
     const int32_t* npairs_dev; // when set, K is read from the device (plan round trip) and
                                // `npairs` is only the bound the tile table was sized for
-    float*         coef;       // zero-filled scratch, `total` floats (generic path)
+    float*         coef;       // zero-filled scratch, `total` floats (generic path); for the slab-decoded
+                               // fused classes (R8 / CUBE64): the unit's segment table, int2[2*nx*8 + 1]
     int32_t        npairs;
     int32_t        total;      // ncoef
     int32_t        ptile0;
