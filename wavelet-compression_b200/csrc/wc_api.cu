@@ -125,6 +125,7 @@ struct wc_plan {
     std::vector<UnitDev>     h_units;
     // unit ids per path: fl[k] = the fused class FL_CLASS[k] (ascending ids), generic = the rest
     std::vector<int>         fl[FL_N], generic;
+    std::vector<char>        has_segtab;                     // per unit: UnitDev::coef is a segment table
     long long total_n = 0;     // sum of ncoef
     size_t    in_bytes = 0;    // sum of input bytes
     // device memory
@@ -423,6 +424,8 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
     p->units.assign(units, units + n_units);
     p->h_units.resize(n_units);
     p->in_dev_off.resize(n_units);
+    p->has_segtab.assign(n_units, 0);
+    std::vector<char> is_generic(n_units, 0);
 
     // classify + lay out
     size_t slot_pairs = 0, coef_floats = 0, in_off = 0;
@@ -453,9 +456,18 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
         int fk = -1;
         for (int k = 0; k < FL_N; ++k)
             if (cls == FL_CLASS[k]) fk = k;
-        if (fk >= 0) p->fl[fk].push_back(i);
-        else if (cls == 0) {
+        if (fk >= 0) {
+            p->fl[fk].push_back(i);
+            // cluster classes: room for the decode-side segment table the compress kernel fills for free
+            const size_t te = fused_decode_table_entries(cls, b.nx);
+            if (te) {
+                coef_off[i] = coef_floats;
+                coef_floats += align_up(2 * te, 4);
+                p->has_segtab[i] = 1;
+            }
+        } else if (cls == 0) {
             p->generic.push_back(i);
+            is_generic[i] = 1;
             coef_off[i] = coef_floats;
             coef_floats += align_up((size_t)n, 4);
             int nt = xtile_count(b.nx, b.ny, b.nz);
@@ -495,7 +507,9 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
         UnitDev& u = p->h_units[i];
         u.in   = in_space == WC_HOST ? (const void*)(p->d_in.as<char>() + p->in_dev_off[i]) : units[i].data;
         u.out  = p->d_out.as<wc_pair>() + slot_off[i];
-        u.coef = p->d_coef.p ? p->d_coef.as<float>() + coef_off[i] : nullptr;
+        // generic units: coefficient scratch; cluster-class fused units: segment table; other fused units: none
+        const bool uses = p->has_segtab[i] || is_generic[i];
+        u.coef = (uses && p->d_coef.p) ? p->d_coef.as<float>() + coef_off[i] : nullptr;
     }
     int rc = plan_upload_units(p);
     if (rc != WC_OK) { wc_plan_destroy(p); return rc; }
@@ -946,6 +960,7 @@ struct DecJob {
     int32_t        nx, ny, nz;
     void*          out_dev;
     int32_t        out_dtype;
+    const int2*    segtab = nullptr; // optional: segment table already on the device (plan round trip)
 };
 
 static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& d_coef,
@@ -959,6 +974,8 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
     std::vector<int> fl[FL_N];   // fused classes, FL_CLASS order (cluster kernels first)
     size_t coef_floats = 0;
     std::vector<size_t> coef_off(n);
+    std::vector<char> slab_tab(n, 0);      // slab-decoded unit whose segment table came with the job
+    bool build_tables[FL_N] = {};
     for (int i = 0; i < n; ++i) {
         long long total = (long long)jobs[i].nx * jobs[i].ny * jobs[i].nz;
         int cls = total > 0 ? fused_decode_class(jobs[i].nx, jobs[i].ny, jobs[i].nz, jobs[i].out_dtype, jobs[i].out_dev) : -1;
@@ -967,7 +984,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
         if (!fused_decode_available()) cls = cls > 0 ? 0 : cls;
         coef_off[i] = coef_floats;
         if (cls == 0) coef_floats += align_up((size_t)total, 4);
-        else if (cls > 0) coef_floats += align_up(2 * fused_decode_table_entries(cls, jobs[i].nx), 4);   // int2 segment table
+        else if (cls > 0 && !jobs[i].segtab) coef_floats += align_up(2 * fused_decode_table_entries(cls, jobs[i].nx), 4);   // int2 segment table
         du[i].pairs      = jobs[i].pairs_dev;
         du[i].npairs_dev = jobs[i].npairs_dev;
         du[i].npairs     = jobs[i].npairs;
@@ -984,12 +1001,19 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             for (int t = 0; t < nt; ++t) xtiles.push_back(make_int2(i, t));
         } else {
             for (int k = 0; k < FL_N; ++k)
-                if (cls == FL_CLASS[k]) fl[k].push_back(i);
+                if (cls == FL_CLASS[k]) {
+                    fl[k].push_back(i);
+                    if (fused_decode_table_entries(cls, jobs[i].nx)) {
+                        if (jobs[i].segtab) slab_tab[i] = 1;
+                        else build_tables[k] = true;
+                    }
+                }
         }
     }
     CTX_CUDA(ctx, d_coef.reserve(sizeof(float) * std::max<size_t>(coef_floats, 4)));
     for (int i = 0; i < n; ++i) {
         du[i].coef = d_coef.as<float>() + coef_off[i];
+        if (slab_tab[i]) du[i].coef = reinterpret_cast<float*>(const_cast<int2*>(jobs[i].segtab));
         iu[i].coef = du[i].coef;
     }
     CTX_CUDA(ctx, d_dec_units.reserve(sizeof(DecUnitDev) * n));
@@ -1032,7 +1056,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
                                                   d_inv_units.as<InvUnitDev>(), dl + o,
                                                   (int)fl[k].size(), d_err.as<int>(), ctx->sm_count,
-                                                  ctx->stream, &ctx->ls, counter));
+                                                  ctx->stream, &ctx->ls, counter, build_tables[k]));
             o += fl[k].size();
         }
     }
@@ -1066,6 +1090,7 @@ int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
         jobs[i].nx = u.nx; jobs[i].ny = u.ny; jobs[i].nz = u.nz;
         jobs[i].out_dev   = out_space == WC_HOST ? (void*)(p->d_stage_out.as<char>() + stage_off[i]) : out[i].data;
         jobs[i].out_dtype = out[i].dtype;
+        if (p->has_segtab[i] && u.coef) jobs[i].segtab = reinterpret_cast<const int2*>(u.coef);
     }
     int rc = run_decompress(ctx, jobs, ctx->ws_coef, p->d_dec_units,
                             p->d_inv_units, p->d_inv_tiles, p->d_ptiles, p->d_psum, p->d_err,

@@ -670,11 +670,18 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {                 // exclusive prefix in front of entry e
                 const int e = tid * EPT + j;
-                if (e < NG && (R == 1 || (e % R) == (int)rank)) { S.s_base[e / R] = es; S.s_prev[e / R] = em; }
+                if (e < NG && (R == 1 || (e % R) == (int)rank)) {
+                    S.s_base[e / R] = es; S.s_prev[e / R] = em;
+                    // decode-side segment table (k_seg_index): first pair of the segment, last kept before it
+                    if (R > 1 && u.coef) reinterpret_cast<int2*>(u.coef)[e] = make_int2(es, em);
+                }
                 es += cv[j];
                 em = max(em, lv[j]);
             }
-            if (tid == 0 && rank == 0) states[uid].npairs = total;
+            if (tid == 0 && rank == 0) {
+                states[uid].npairs = total;
+                if (R > 1 && u.coef) reinterpret_cast<int2*>(u.coef)[NG] = make_int2(total, -1);   // sentinel
+            }
             if (tid == 0) *S.s_next = 0;
         }
         __syncthreads();
@@ -966,6 +973,11 @@ __device__ __forceinline__ void ihaar_pair2(float2& avg, float2& diff) {
 
 constexpr int FD_PPT = 8;        // pairs per thread per tile of the block-wide scan
 
+// q-th segment of a warp (slab decode): round-robin, with the parity flipped every other round — odd
+// segments are the high-j' (detail, sparse) halves, so a fixed parity would give half the warps all the work.
+// NW is even and nseg = 2X is even, so q * NW + (warp ^ 1) stays below nseg whenever q * NW + warp does.
+__device__ __forceinline__ int fd_seg_of(int q, int warp, int NW) { return q * NW + (warp ^ (q & 1)); }
+
 // Loads FD_PPT consecutive pairs starting at p (a multiple of FD_PPT); pairs past k1 read as (0, 0).
 __device__ __forceinline__ void fd_load_tile(const int2* pairs, bool vec16, int p, int k1, int2 (&pr)[FD_PPT]) {
     if (vec16 && p + FD_PPT <= k1) {
@@ -1019,8 +1031,10 @@ __device__ __forceinline__ uint32_t fd_tile_scan(const int2 (&pr)[FD_PPT], int n
 }
 
 // ---- segment index of the slab-decoded units --------------------------------------------------------
-// tab[m] = (first pair p whose flat index F_p >= m * seglen, F_p), m = 0 .. nseg; pairs at or past `total`
-// (and everything after them) are dropped as rle_decode does: tab[m >= first uncovered] = (Kend, total).
+// tab[m] = (first pair p whose flat index F_p >= m * seglen, flat index of the pair before it or -1),
+// m = 0 .. nseg; pairs at or past `total` (and everything after them) are dropped as rle_decode does:
+// tab[m >= first uncovered] = (Kend, .).  The fused compress kernels of the same classes write the same
+// table for free (their segment scan holds exactly these two numbers), so a plan round trip skips this kernel.
 // The table lives where the generic path keeps its coefficient scratch pointer (DecUnitDev::coef).
 template <int NT>
 __global__ void __launch_bounds__(NT, 2)
@@ -1083,7 +1097,7 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
                         if (p + j < K && pr[j].x >= 0) {
                             const uint32_t f = sat_add(pre, (uint32_t)pr[j].x);
                             if (f < total)
-                                for (; fb <= f; fb += seglen, ++m) tab[m] = make_int2(p + j, (int)f);
+                                for (; fb <= f; fb += seglen, ++m) tab[m] = make_int2(p + j, (int)pre - 1);
                             pre = sat_add(pre, (uint32_t)pr[j].x + 1u);
                         }
                     }
@@ -1096,7 +1110,7 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
         __syncthreads();
         const int ke = s_kend, fl = s_flast;
         for (int m = (fl < 0 ? 0 : (int)dsl.div((uint32_t)fl) + 1) + tid; m <= nseg; m += NT)
-            tab[m] = make_int2(ke, (int)total);
+            tab[m] = make_int2(ke, fl);
         __syncthreads();
     }
 }
@@ -1178,8 +1192,8 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         fd_load_tile(pairs, vec16, tid * FD_PPT, K, pr);           // in flight during the zero-fill
     } else {
         // segment table entries of this warp's segments (<= 16 per warp): lane 2q + e <- tab[m(q) + e]
-        const int sg = warp + (lane >> 1) * NW;
-        if (sg < g.nseg)
+        const int sg = fd_seg_of(lane >> 1, warp, NW);
+        if ((lane >> 1) * NW + warp < g.nseg)
             te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sg >> 1) * (2 * S) + (sg & 1) * S + (int)rank + (lane & 1));
     }
 
@@ -1230,16 +1244,16 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         // Lanes 2q, 2q+1 hold the table entries of the warp's q-th segment (loaded before the zero-fill);
         // up to 8 chunks of 32 pairs are in flight per segment before the first one is decoded.
         const uint32_t seglen = (uint32_t)g.seglen;
-        int q = 0;
 #pragma unroll 1
-        for (int sg = warp; sg < g.nseg; sg += NW, ++q) {
+        for (int q = 0; q * NW + warp < g.nseg; ++q) {
+            const int sg = fd_seg_of(q, warp, NW);
             const int i = sg >> 1, half = sg & 1;
             const int m = i * (2 * S) + half * S + (int)rank;
             const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * q), e0y = __shfl_sync(0xffffffffu, te.y, 2 * q);
             const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * q + 1);
             float* const cseg = C + i * g.slab + half * g.seglen;    // C index of flat index m * seglen
             const uint32_t fseg = (uint32_t)m * seglen;
-            uint32_t base = (uint32_t)e0y;                           // flat index of the first pair
+            uint32_t base = (uint32_t)e0y;                           // flat index of the pair before the first (or -1)
 #pragma unroll 1
             for (int c0 = e0x; c0 < e1x; c0 += 256) {
                 int2 pv[8];
@@ -1252,10 +1266,8 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c0 + 32 * c < e1x) {                         // warp-uniform
-                        const int p = c0 + 32 * c + lane;
                         const bool live = pv[c].x >= 0;
-                        // the segment's first pair sits at `base` itself; every later one adds run + 1
-                        uint32_t inc = (live && p != e0x) ? (uint32_t)pv[c].x + 1u : 0u;
+                        uint32_t inc = live ? (uint32_t)pv[c].x + 1u : 0u;   // every pair advances by run + 1
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) {
                             uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
@@ -1409,12 +1421,13 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
 
 template <int S, int NT, bool STATIC>
 static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
-                             int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter) {
+                             int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter,
+                             bool build_tables) {
     auto kern = k_fused_decompress<S, NT, STATIC>;
     constexpr int smem = (32768 + F_CPAD) * 4 + 1024;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    if (S > 1) {
+    if (S > 1 && build_tables) {
         // segment tables first: one CTA per unit, a few units per SM
         const int nb = n < 2 * sm_count ? n : 2 * sm_count;
         ls->begin(KID_SEG_INDEX, st);
@@ -1449,17 +1462,17 @@ size_t fused_decode_table_entries(int fused_cls, int nx) {
 
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
-                                    cudaStream_t st, LaunchStats* ls, int* work_counter) {
+                                    cudaStream_t st, LaunchStats* ls, int* work_counter, bool build_tables) {
     if (n_list <= 0) return cudaSuccess;
     switch (fused_cls) {
     case FUSED_CLS_R1:
-        return launch_fd<1, 512, false>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+        return launch_fd<1, 512, false>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     case FUSED_CLS_R8:
-        return launch_fd<8, 512, false>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+        return launch_fd<8, 512, false>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
     case FUSED_CLS_CUBE32:
-        return launch_fd<1, 1024, true>(KID_FUSED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+        return launch_fd<1, 1024, true>(KID_FUSED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     case FUSED_CLS_CUBE64:
-        return launch_fd<8, 1024, true>(KID_FUSED_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+        return launch_fd<8, 1024, true>(KID_FUSED_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
     }
     return cudaErrorInvalidValue;
 }

@@ -27,7 +27,8 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
                                   LaunchStats* ls, int* work_counter = nullptr);
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
-                                    cudaStream_t st, LaunchStats* ls, int* work_counter = nullptr);
+                                    cudaStream_t st, LaunchStats* ls, int* work_counter = nullptr,
+                                    bool build_tables = true);
 
 cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset);
 
