@@ -984,7 +984,8 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
         if (!fused_decode_available()) cls = cls > 0 ? 0 : cls;
         coef_off[i] = coef_floats;
         if (cls == 0) coef_floats += align_up((size_t)total, 4);
-        else if (cls > 0 && !jobs[i].segtab) coef_floats += align_up(2 * fused_decode_table_entries(cls, jobs[i].nx), 4);   // int2 segment table
+        else if (cls > 0 && !jobs[i].segtab && fused_decode_needs_table(cls))
+            coef_floats += align_up(2 * fused_decode_table_entries(cls, jobs[i].nx), 4);   // int2 segment table
         du[i].pairs      = jobs[i].pairs_dev;
         du[i].npairs_dev = jobs[i].npairs_dev;
         du[i].npairs     = jobs[i].npairs;
@@ -1003,17 +1004,16 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             for (int k = 0; k < FL_N; ++k)
                 if (cls == FL_CLASS[k]) {
                     fl[k].push_back(i);
-                    if (fused_decode_table_entries(cls, jobs[i].nx)) {
-                        if (jobs[i].segtab) slab_tab[i] = 1;
-                        else build_tables[k] = true;
-                    }
+                    if (jobs[i].segtab) slab_tab[i] = 1;                       // table came with the job
+                    else if (fused_decode_needs_table(cls)) build_tables[k] = true;
+                    else slab_tab[i] = 2;                                      // block-wide scan: no table
                 }
         }
     }
     CTX_CUDA(ctx, d_coef.reserve(sizeof(float) * std::max<size_t>(coef_floats, 4)));
     for (int i = 0; i < n; ++i) {
         du[i].coef = d_coef.as<float>() + coef_off[i];
-        if (slab_tab[i]) du[i].coef = reinterpret_cast<float*>(const_cast<int2*>(jobs[i].segtab));
+        if (slab_tab[i]) du[i].coef = reinterpret_cast<float*>(const_cast<int2*>(jobs[i].segtab));   // nullptr for 2
         iu[i].coef = du[i].coef;
     }
     CTX_CUDA(ctx, d_dec_units.reserve(sizeof(DecUnitDev) * n));

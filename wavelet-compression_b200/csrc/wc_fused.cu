@@ -673,14 +673,14 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
                 if (e < NG && (R == 1 || (e % R) == (int)rank)) {
                     S.s_base[e / R] = es; S.s_prev[e / R] = em;
                     // decode-side segment table (k_seg_index): first pair of the segment, last kept before it
-                    if (R > 1 && u.coef) reinterpret_cast<int2*>(u.coef)[e] = make_int2(es, em);
+                    if (u.coef) reinterpret_cast<int2*>(u.coef)[e] = make_int2(es, em);
                 }
                 es += cv[j];
                 em = max(em, lv[j]);
             }
             if (tid == 0 && rank == 0) {
                 states[uid].npairs = total;
-                if (R > 1 && u.coef) reinterpret_cast<int2*>(u.coef)[NG] = make_int2(total, -1);   // sentinel
+                if (u.coef) reinterpret_cast<int2*>(u.coef)[NG] = make_int2(total, -1);   // sentinel
             }
             if (tid == 0) *S.s_next = 0;
         }
@@ -1188,7 +1188,10 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
     const bool vec16 = (reinterpret_cast<uintptr_t>(pairs) & 15u) == 0;
     int2 pr[FD_PPT];
     int2 te = make_int2(0, 0);
-    if (S == 1) {
+    // S = 1 units decode by segments too when a table came with them (plan round trip: the compress kernel
+    // wrote it); without one they take the block-wide scan, which needs no second pass over the list
+    const bool use_tab = S > 1 || du.coef != nullptr;
+    if (!use_tab) {
         fd_load_tile(pairs, vec16, tid * FD_PPT, K, pr);           // in flight during the zero-fill
     } else {
         // segment table entries of this warp's segments (<= 16 per warp): lane 2q + e <- tab[m(q) + e]
@@ -1210,7 +1213,7 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
     WC_PHASE_CLOCK(t2);
 
     // 2. decode the pairs that land in this item's segments
-    if (S == 1) {
+    if (!use_tab) {
         // block-wide scan over the whole list; flat index -> (i', j', k') -> padded index in C
         FastDiv dyz;
         if (!G::is_static) dyz.init((uint32_t)(g.Y * g.Z), total);
@@ -1457,8 +1460,11 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
 }
 // int2 entries of the segment table a slab-decoded unit needs (0 for the other classes)
 size_t fused_decode_table_entries(int fused_cls, int nx) {
-    return (fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64) ? (size_t)(2 * nx * 8 + 1) : 0;
+    if (fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64) return (size_t)(2 * nx * 8 + 1);
+    if (fused_cls == FUSED_CLS_R1 || fused_cls == FUSED_CLS_CUBE32) return (size_t)(2 * nx + 1);
+    return 0;
 }
+bool fused_decode_needs_table(int fused_cls) { return fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64; }
 
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,

@@ -19,7 +19,8 @@ enum { FUSED_CLS_NONE = 0, FUSED_CLS_R1 = 1, FUSED_CLS_R8 = 8, FUSED_CLS_CUBE32 
 int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 bool fused_decode_available();
 int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
-size_t fused_decode_table_entries(int fused_cls, int nx);
+size_t fused_decode_table_entries(int fused_cls, int nx);   // int2 entries of a unit's segment table
+bool fused_decode_needs_table(int fused_cls);               // slab-decoded classes cannot decode without one
 
 cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states,
                                   const int* unit_list, int n_list, double one_minus_keep,
