@@ -1115,6 +1115,43 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
     }
 }
 
+// Decodes the pairs [c0, min(c0 + 32 * NCH, e1x)) of one segment: pair p sits at flat index
+// base + sum of (run + 1) over the pairs c0 .. p; `base` is advanced past the last one.
+template <int NCH>
+__device__ __forceinline__ void fd_decode_chunks(const int2* __restrict__ pairs, int c0, int e1x, int lane,
+                                                 uint32_t& base, uint32_t fseg, uint32_t seglen, uint32_t total,
+                                                 float* cseg) {
+    int2     pv[NCH];
+    uint32_t inc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int p = c0 + 32 * c + lane;
+        pv[c] = make_int2(-1, 0);
+        if (p < e1x) pv[c] = __ldg(pairs + p);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) inc[c] = pv[c].x >= 0 ? (uint32_t)pv[c].x + 1u : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc[c], o);
+            if (lane >= o) inc[c] += v;
+        }
+    }
+    uint32_t tot[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tot[c] = __shfl_sync(0xffffffffu, inc[c], 31);
+    uint32_t b = base;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const uint32_t f = b + inc[c];
+        if (pv[c].x >= 0 && f - fseg < seglen && f < total) cseg[f - fseg] = __int_as_float(pv[c].y);
+        b += tot[c];
+    }
+    base = b;
+}
+
 // Unit descriptors are staged two items ahead through shared memory, like FLookahead of the compress
 // kernels; K (which may live on the device after a plan round trip) is resolved one item ahead, in time
 // for the L2 prefetch of the next unit's pair list (S = 1).
@@ -1259,28 +1296,10 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
             uint32_t base = (uint32_t)e0y;                           // flat index of the pair before the first (or -1)
 #pragma unroll 1
             for (int c0 = e0x; c0 < e1x; c0 += 256) {
-                int2 pv[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int p = c0 + 32 * c + lane;
-                    pv[c] = make_int2(-1, 0);
-                    if (p < e1x) pv[c] = __ldg(pairs + p);
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c0 + 32 * c < e1x) {                         // warp-uniform
-                        const bool live = pv[c].x >= 0;
-                        uint32_t inc = live ? (uint32_t)pv[c].x + 1u : 0u;   // every pair advances by run + 1
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                            if (lane >= o) inc += v;
-                        }
-                        const uint32_t f = base + inc;
-                        if (live && f - fseg < seglen && f < total) cseg[f - fseg] = __int_as_float(pv[c].y);
-                        base += __shfl_sync(0xffffffffu, inc, 31);
-                    }
-                }
+                // 4 or 8 chunks of 32 pairs at once: the loads are all in flight together, and the chunks'
+                // shuffle scans are independent chains the scheduler interleaves (no branch between them)
+                if (e1x - c0 <= 128) fd_decode_chunks<4>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
+                else                 fd_decode_chunks<8>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
             }
         }
     }
