@@ -27,3 +27,7 @@ with torch.cuda.stream(stream):
     t2 = time.perf_counter()
     print("host enqueue ms/step", (t1 - t0) * 200, "total ms/step", (t2 - t0) * 200)
     for k, (n, ms) in ctx.kernel_stats().items(): print(k, n, ms / 5)
+    ctx.reset_counters()
+    for _ in range(5): rm = plan.rmse(odescs)
+    ctx.sync()
+    for k, (n, ms) in ctx.kernel_stats().items(): print(k, n, ms / 5)

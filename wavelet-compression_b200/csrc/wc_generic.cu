@@ -618,19 +618,52 @@ k_rmse_tiles(const RmseUnitDev* __restrict__ units, const int2* __restrict__ til
     __shared__ double s_w[CT_THREADS / 32];
     const int2        tl = tiles[blockIdx.x];
     const RmseUnitDev u  = units[tl.x];
-    int f0 = tl.y * CT_ELEMS + threadIdx.x * (CT_ELEMS / CT_THREADS);
+    // thread t takes the element pairs (2t, 2t+1) + 2 * CT_THREADS * j: a warp reads whole 512-byte (f64) /
+    // 256-byte (f32) runs with 16- / 8-byte vector loads; the order of the additions is fixed
+    const int tile0 = tl.y * CT_ELEMS;
     double s = 0.0;
+    auto term = [&](float av, float bv) {
+        float  df = __fsub_rn(av, bv); // float subtraction, src/calc-loss.cpp:33
+        double d  = (double)df;
+        s = __dadd_rn(s, __dmul_rn(d, d));
+    };
+    const bool a64 = u.a_dtype == WC_F64, b64 = u.b_dtype == WC_F64;
+    const bool vec = tile0 + CT_ELEMS <= u.n &&
+                     (reinterpret_cast<uintptr_t>(u.a) & (a64 ? 15u : 7u)) == 0 &&
+                     (reinterpret_cast<uintptr_t>(u.b) & (b64 ? 15u : 7u)) == 0;
+    if (vec) {
+        float2 av[CT_ELEMS / CT_THREADS / 2], bv[CT_ELEMS / CT_THREADS / 2];
 #pragma unroll
-    for (int j = 0; j < CT_ELEMS / CT_THREADS; ++j) {
-        int f = f0 + j;
-        if (f < u.n) {
-            float av = u.a_dtype == WC_F64 ? __double2float_rn(static_cast<const double*>(u.a)[f])
-                                           : static_cast<const float*>(u.a)[f];
-            float bv = u.b_dtype == WC_F64 ? __double2float_rn(static_cast<const double*>(u.b)[f])
-                                           : static_cast<const float*>(u.b)[f];
-            float  df = __fsub_rn(av, bv); // float subtraction, src/calc-loss.cpp:33
-            double d  = (double)df;
-            s = __dadd_rn(s, __dmul_rn(d, d));
+        for (int j = 0; j < CT_ELEMS / CT_THREADS / 2; ++j) {
+            const int f = tile0 + 2 * (threadIdx.x + CT_THREADS * j);
+            if (a64) {
+                const double2 v = __ldcs(reinterpret_cast<const double2*>(static_cast<const double*>(u.a) + f));
+                av[j] = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));   // src/preprocess.cpp:78
+            } else {
+                av[j] = __ldcs(reinterpret_cast<const float2*>(static_cast<const float*>(u.a) + f));
+            }
+            if (b64) {
+                const double2 v = __ldcs(reinterpret_cast<const double2*>(static_cast<const double*>(u.b) + f));
+                bv[j] = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+            } else {
+                bv[j] = __ldcs(reinterpret_cast<const float2*>(static_cast<const float*>(u.b) + f));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CT_ELEMS / CT_THREADS / 2; ++j) { term(av[j].x, bv[j].x); term(av[j].y, bv[j].y); }
+    } else {
+        // ragged last tile / unaligned boxes: same element-to-thread map, scalar loads
+#pragma unroll
+        for (int j = 0; j < CT_ELEMS / CT_THREADS / 2; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int f = tile0 + 2 * (threadIdx.x + CT_THREADS * j) + e;
+                if (f < u.n) {
+                    float av = a64 ? __double2float_rn(static_cast<const double*>(u.a)[f]) : static_cast<const float*>(u.a)[f];
+                    float bv = b64 ? __double2float_rn(static_cast<const double*>(u.b)[f]) : static_cast<const float*>(u.b)[f];
+                    term(av, bv);
+                }
+            }
         }
     }
 #pragma unroll
