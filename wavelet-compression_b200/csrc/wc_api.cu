@@ -142,6 +142,8 @@ struct wc_plan {
     cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
     DevBuf d_counter;
     unsigned counter_next = 0;
+    DevBuf d_rmse_tiles;
+    long long rmse_tiles = -1;   // tiles resident in d_rmse_tiles (-1: not built yet)
     std::vector<cudaEvent_t> ev;
     DevBuf d_running;
 };
@@ -548,6 +550,7 @@ int wc_plan_destroy(wc_plan* p) {
     for (DevBuf* b : bufs) b->release();
     p->d_running.release();
     p->d_counter.release();
+    p->d_rmse_tiles.release();
     if (p->s_aux) cudaStreamDestroy(p->s_aux);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
@@ -1186,31 +1189,38 @@ struct RmseJob {
     int32_t n;
 };
 
+// `cached_tiles`: in/out, the number of tiles already resident in d_tiles from an earlier call with the same
+// unit sizes (a plan), or nullptr / -1 to build and upload the (unit, tile) table now.
 static int run_rmse(wc_ctx* ctx, const std::vector<RmseJob>& jobs, DevBuf& d_units, DevBuf& d_tiles,
-                    DevBuf& d_sum, DevBuf& d_rmse, double* rmse_host) {
+                    DevBuf& d_sum, DevBuf& d_rmse, double* rmse_host, long long* cached_tiles = nullptr) {
     int n = (int)jobs.size();
     if (n == 0) return WC_OK;
+    const bool have_tiles = cached_tiles && *cached_tiles >= 0;
     std::vector<RmseUnitDev> ru(n);
     std::vector<int2> tiles;
+    size_t n_tiles = 0;
     for (int i = 0; i < n; ++i) {
         ru[i].a = jobs[i].a; ru[i].b = jobs[i].b;
         ru[i].a_dtype = jobs[i].a_dtype; ru[i].b_dtype = jobs[i].b_dtype;
         ru[i].n = jobs[i].n;
-        ru[i].ctile0  = (int32_t)tiles.size();
+        ru[i].ctile0  = (int32_t)n_tiles;
         ru[i].nctiles = ctile_count(jobs[i].n);
-        for (int t = 0; t < ru[i].nctiles; ++t) tiles.push_back(make_int2(i, t));
+        if (!have_tiles)
+            for (int t = 0; t < ru[i].nctiles; ++t) tiles.push_back(make_int2(i, t));
+        n_tiles += (size_t)ru[i].nctiles;
     }
     CTX_CUDA(ctx, d_units.reserve(sizeof(RmseUnitDev) * n));
-    CTX_CUDA(ctx, d_tiles.reserve(sizeof(int2) * std::max<size_t>(tiles.size(), 1)));
-    CTX_CUDA(ctx, d_sum.reserve(sizeof(double) * std::max<size_t>(tiles.size(), 1)));
+    CTX_CUDA(ctx, d_tiles.reserve(sizeof(int2) * std::max<size_t>(n_tiles, 1)));
+    CTX_CUDA(ctx, d_sum.reserve(sizeof(double) * std::max<size_t>(n_tiles, 1)));
     CTX_CUDA(ctx, d_rmse.reserve(sizeof(double) * n));
     CTX_CUDA(ctx, cudaMemcpyAsync(d_units.p, ru.data(), sizeof(RmseUnitDev) * n,
                                   cudaMemcpyHostToDevice, ctx->stream));
-    if (!tiles.empty())
-        CTX_CUDA(ctx, cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(),
+    if (!have_tiles && n_tiles)
+        CTX_CUDA(ctx, cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * n_tiles,
                                       cudaMemcpyHostToDevice, ctx->stream));
+    if (cached_tiles) *cached_tiles = (long long)n_tiles;
     CTX_CUDA(ctx, launch_rmse_generic(d_units.as<RmseUnitDev>(), n, d_tiles.as<int2>(),
-                                      (int)tiles.size(), d_sum.as<double>(), d_rmse.as<double>(),
+                                      (int)n_tiles, d_sum.as<double>(), d_rmse.as<double>(),
                                       ctx->stream, &ctx->ls));
     CTX_CUDA(ctx, cudaMemcpyAsync(rmse_host, d_rmse.p, sizeof(double) * n, cudaMemcpyDeviceToHost,
                                   ctx->stream));
@@ -1230,7 +1240,8 @@ int wc_plan_rmse(wc_plan* p, const wc_box_desc* recon, double* rmse) {
         if (recon[i].dtype != WC_F32 && recon[i].dtype != WC_F64) return WC_ERR_INVALID_ARG;
         jobs[i] = { u.in, recon[i].data, u.dtype, recon[i].dtype, u.n };
     }
-    return run_rmse(ctx, jobs, p->d_rmse_units, p->d_inv_tiles, p->d_rmse_sum, p->d_rmse, rmse);
+    // the (unit, tile) table only depends on the unit sizes: uploaded once per plan
+    return run_rmse(ctx, jobs, p->d_rmse_units, p->d_rmse_tiles, p->d_rmse_sum, p->d_rmse, rmse, &p->rmse_tiles);
 }
 
 int wc_rmse_batch(wc_ctx* ctx, const wc_box_desc* actual, const wc_box_desc* pred, int n_units,
