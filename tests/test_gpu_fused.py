@@ -149,3 +149,58 @@ def test_fused_decompress_many_units_and_odd_streams(fused_ctx, oracle, wc):
     for i in list(range(0, 450, 13)) + [0, 399, 400, 429, 449]:
         ob = oracle.decompress_unit(packed[i].runs, packed[i].vals, dims[i])
         assert same_bits(recon[i], ob), i
+
+
+# ---- plan round trip: the decoder runs from the segment tables the compress kernels wrote ---------------
+def test_plan_roundtrip_segment_tables_all_fused_classes(fused_ctx, oracle, wc):
+    """compress -> decompress -> rmse inside one plan for every fused class (literal-geometry cubes and
+    runtime-geometry shapes, one CTA or 8 slabs per unit), both ingest dtypes, float32 and float64 outputs,
+    sparse / dense / all-kept / empty units: the decompress kernels take the per-segment (first pair, last
+    kept index) tables written by the compress kernels instead of scanning the pair lists."""
+    import torch
+    rng = np.random.default_rng(90210)
+    shapes = [(32, 32, 32)] * 150 + [(64, 64, 64)] * 20 + [(16, 32, 64)] * 12 + [(24, 40, 12)] * 6 + \
+             [(48, 48, 48)] * 6 + [(32, 64, 64)] * 5 + [(8, 8, 8)] * 9 + [(2, 2, 4)] * 3
+    host, dts = [], []
+    for i, d in enumerate(shapes):
+        dt = np.float32 if (i % 4 == 1 and d[0] % 4 == 0) else np.float64
+        b = smooth_box(d, rng, dtype=dt, sym=(i % 2 == 0), noise=10.0 ** -(i % 6))
+        if i % 17 == 3:
+            b = -np.abs(b) - 1.0                       # negative max: every coefficient kept (SURVEY.md D3')
+        if i % 19 == 5:
+            b = np.zeros_like(b)                       # nothing kept
+        host.append(b)
+        dts.append(dt)
+    dev = [torch.from_numpy(h).cuda() for h in host]
+    code = lambda dt: wc.WC_F64 if dt == np.float64 else wc.WC_F32
+    descs = wc.capi.box_descs([t.data_ptr() for t in dev], [code(dt) for dt in dts], shapes)
+    plan = fused_ctx.plan(descs, wc.WC_DEVICE)
+    for out_dt, tdt in ((np.float32, torch.float32), (np.float64, torch.float64)):
+        outs = [torch.full(h.shape, 7.0, dtype=tdt, device="cuda") for h in host]
+        torch.cuda.synchronize()
+        odescs = wc.capi.box_descs([t.data_ptr() for t in outs], [code(out_dt)] * len(outs), shapes)
+        for keep in (F999, float(np.float32(0.9)), 1.0):
+            plan.compress(keep)
+            plan.decompress(odescs, wc.WC_DEVICE)
+            rm = plan.rmse(odescs)
+            fused_ctx.sync()
+            packed = plan.fetch_host()
+            for i in list(range(0, len(shapes), 7)) + [149, 150, 169, 170, len(shapes) - 1]:
+                runs, vals, _ = oracle.compress_unit(host[i], shapes[i], keep)
+                assert same_bits(packed[i].runs, runs) and same_bits(packed[i].vals, vals), (i, shapes[i], keep)
+                ob = oracle.decompress_unit(runs, vals, shapes[i])
+                got = outs[i].cpu().numpy().astype(np.float32)
+                assert same_bits(got.reshape(ob.shape), ob), (i, shapes[i], keep, out_dt)
+                oe = oracle.rmse(host[i].astype(np.float32), ob, shapes[i])
+                assert abs(rm[i] - oe) <= 1e-12 * max(abs(oe), 1e-300), (i, rm[i], oe)
+    # global threshold (extension): one key for the whole batch, same tables
+    plan.compress(F999, thresh_mode=wc.WC_THRESH_GLOBAL)
+    outs = [torch.empty(h.shape, dtype=torch.float32, device="cuda") for h in host]
+    odescs = wc.capi.box_descs([t.data_ptr() for t in outs], [wc.WC_F32] * len(outs), shapes)
+    plan.decompress(odescs, wc.WC_DEVICE)
+    fused_ctx.sync()
+    packed = plan.fetch_host()
+    for i in (0, 150, 170, 185, len(shapes) - 1):
+        ob = oracle.decompress_unit(packed[i].runs, packed[i].vals, shapes[i])
+        assert same_bits(outs[i].cpu().numpy().reshape(ob.shape), ob), i
+    plan.close()

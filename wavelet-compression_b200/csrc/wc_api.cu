@@ -828,7 +828,7 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
         return wc_plan_fetch(p, out, WC_HOST);
     }
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int NCH = 8;
+    const int NCH = 16;
     if (!p->s_h2d) {
         CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
         CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
