@@ -144,6 +144,8 @@ struct wc_plan {
     unsigned counter_next = 0;
     DevBuf d_rmse_tiles;
     long long rmse_tiles = -1;   // tiles resident in d_rmse_tiles (-1: not built yet)
+    DevBuf d_dec_list;           // fused work lists of the last wc_plan_decompress (re-used on a cache hit)
+    struct DecCache* dec_cache = nullptr;
     std::vector<cudaEvent_t> ev;
     DevBuf d_running;
 };
@@ -551,6 +553,8 @@ int wc_plan_destroy(wc_plan* p) {
     p->d_running.release();
     p->d_counter.release();
     p->d_rmse_tiles.release();
+    p->d_dec_list.release();
+    delete p->dec_cache;
     if (p->s_aux) cudaStreamDestroy(p->s_aux);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
@@ -966,11 +970,48 @@ struct DecJob {
     const int2*    segtab = nullptr; // optional: segment table already on the device (plan round trip)
 };
 
+struct DecCache {
+    std::vector<uint64_t> key;
+    bool   valid = false;
+    size_t fl_n[4] = {};
+};
+
 static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& d_coef,
                           DevBuf& d_dec_units, DevBuf& d_inv_units, DevBuf& d_inv_tiles,
-                          DevBuf& d_ptiles, DevBuf& d_psum, DevBuf& d_err, DevBuf& d_fused_list) {
+                          DevBuf& d_ptiles, DevBuf& d_psum, DevBuf& d_err, DevBuf& d_fused_list,
+                          DecCache* cache = nullptr) {
     int n = (int)jobs.size();
     if (n == 0) return WC_OK;
+    // A plan that decodes into the same boxes again (keep sweeps of the estimate mode) re-launches from the
+    // device tables of the previous call; only all-fused batches without scratch are cached.
+    if (cache) {
+        std::vector<uint64_t> key(4 * (size_t)n);
+        for (int i = 0; i < n; ++i) {
+            key[4 * i]     = (uint64_t)(uintptr_t)jobs[i].pairs_dev;
+            key[4 * i + 1] = (uint64_t)(uintptr_t)jobs[i].out_dev;
+            key[4 * i + 2] = (uint64_t)(uintptr_t)jobs[i].segtab;
+            key[4 * i + 3] = ((uint64_t)(uint32_t)jobs[i].out_dtype << 32) | (uint32_t)jobs[i].npairs;
+        }
+        if (cache->valid && cache->key == key) {
+            CTX_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 64, ctx->stream));
+            CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
+            int* dl = d_fused_list.as<int>();
+            size_t o = 0;
+            for (int k = 0; k < FL_N; ++k) {
+                if (!cache->fl_n[k]) continue;
+                int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
+                CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+                CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
+                                                      d_inv_units.as<InvUnitDev>(), dl + o, (int)cache->fl_n[k],
+                                                      d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls,
+                                                      counter, false));
+                o += cache->fl_n[k];
+            }
+            return WC_OK;
+        }
+        cache->valid = false;
+        cache->key.swap(key);
+    }
     std::vector<DecUnitDev> du(n);
     std::vector<InvUnitDev> iu(n);
     std::vector<int2> ptiles, xtiles;
@@ -1063,6 +1104,14 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             o += fl[k].size();
         }
     }
+    if (cache) {
+        bool ok = coef_floats == 0 && ptiles.empty() && xtiles.empty();
+        for (int k = 0; k < FL_N; ++k) {
+            cache->fl_n[k] = fl[k].size();
+            ok = ok && !build_tables[k];
+        }
+        cache->valid = ok;
+    }
     return WC_OK;
 }
 
@@ -1095,9 +1144,10 @@ int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
         jobs[i].out_dtype = out[i].dtype;
         if (p->has_segtab[i] && u.coef) jobs[i].segtab = reinterpret_cast<const int2*>(u.coef);
     }
+    if (!p->dec_cache) p->dec_cache = new DecCache();
     int rc = run_decompress(ctx, jobs, ctx->ws_coef, p->d_dec_units,
                             p->d_inv_units, p->d_inv_tiles, p->d_ptiles, p->d_psum, p->d_err,
-                            ctx->ws_misc);
+                            p->d_dec_list, p->dec_cache);
     if (rc != WC_OK) return rc;
     if (out_space == WC_HOST) {
         CopyList cl;
