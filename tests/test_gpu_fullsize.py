@@ -93,3 +93,48 @@ def test_amr_level_properties(wc, ctx, oracle, level):
         oe = oracle.rmse(box.astype(np.float32), ob, dims[i])
         assert abs(rmse[i] - oe) <= 1e-12 * max(abs(oe), 1e-300), (i, rmse[i], oe)
     plan.close()
+
+
+def test_config5_keep_sweep_global_threshold(wc, ctx, oracle):
+    """BASELINE config 5 (EXTENSION, parity defined by the oracle's max rule over the concatenation): a 512^3
+    level-0 box set = 512 boxes of 64^3, one float64 component (1.07 GB), keep in {0.99, 0.999, 0.9999} with ONE
+    threshold for all boxes.  The shared threshold is the oracle's (first-max rule over all 512 boxes' coefficients);
+    sampled units: pairs, reconstruction and RMSE equal the oracle's; every 16th unit: pair count; the kept count
+    grows with keep."""
+    import torch
+    lev = wc.amr_synth.LevelSpec(0, 512, 64, 512)
+    assert lev.n_boxes == 512
+    fab = wc.amr_synth.generate_level_torch(lev, 1, t=0, device="cuda")      # (512, 1, 64, 64, 64) float64
+    n = 64 ** 3
+    dims = [(64, 64, 64)] * 512
+    descs = wc.capi.box_descs([fab.data_ptr() + 8 * n * i for i in range(512)], [wc.WC_F64] * 512, dims)
+    rec = torch.empty(512 * n, dtype=torch.float32, device="cuda")
+    odescs = wc.capi.box_descs([rec.data_ptr() + 4 * n * i for i in range(512)], [wc.WC_F32] * 512, dims)
+    torch.cuda.synchronize()
+    plan = ctx.plan(descs, wc.WC_DEVICE)
+    # the oracle's coefficients of every box (C restatement, ~10 ms per 64^3 box) -> its shared threshold
+    host = fab.cpu().numpy()
+    flats = [oracle.haar_forward(host[i, 0].reshape(-1).astype(np.float32), dims[i]) for i in range(512)]
+    sample = [0, 63, 200, 317, 511]
+    totals = []
+    for keep in (float(np.float32(0.99)), KEEP, float(np.float32(0.9999))):
+        plan.compress(keep, thresh_mode=wc.WC_THRESH_GLOBAL)
+        plan.decompress(odescs, wc.WC_DEVICE)
+        rm = plan.rmse(odescs)
+        ctx.sync()
+        assert np.all(np.isfinite(rm))
+        packed = plan.fetch_host()
+        totals.append(sum(p.npairs for p in packed))
+        t = oracle.select_threshold_global(flats, keep)
+        for i in sample:
+            runs, vals = oracle.threshold_pack(flats[i], t)
+            assert same_bits(packed[i].runs, runs) and same_bits(packed[i].vals, vals), (keep, i)
+            ob = oracle.decompress_unit(runs, vals, dims[i])
+            assert same_bits(rec[i * n:(i + 1) * n].cpu().numpy().reshape(ob.shape), ob), (keep, i)
+            oe = oracle.rmse(host[i, 0].reshape(-1).astype(np.float32), ob, dims[i])
+            assert abs(rm[i] - oe) <= 1e-12 * max(abs(oe), 1e-300), (keep, i, rm[i], oe)
+        # every unit's pair count equals the oracle's count for the shared threshold
+        for i in range(0, 512, 16):
+            assert packed[i].npairs == int(np.count_nonzero(np.abs(flats[i].astype(np.float64)) > t)), (keep, i)
+    assert totals[0] <= totals[1] <= totals[2], totals
+    plan.close()
