@@ -1025,7 +1025,6 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
         int cls = total > 0 ? fused_decode_class(jobs[i].nx, jobs[i].ny, jobs[i].nz, jobs[i].out_dtype, jobs[i].out_dev) : -1;
         if (ctx->opt_path == 1 && cls > 0) cls = 0;
         if (ctx->opt_path == 2 && cls == 0) return WC_ERR_BAD_DIMS;
-        if (!fused_decode_available()) cls = cls > 0 ? 0 : cls;
         coef_off[i] = coef_floats;
         if (cls == 0) coef_floats += align_up((size_t)total, 4);
         else if (cls > 0 && !jobs[i].segtab && fused_decode_needs_table(cls))

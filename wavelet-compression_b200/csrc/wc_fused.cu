@@ -1,8 +1,8 @@
-// Fused on-chip compress kernel for sm_100a: one unit's coefficients never leave the SM(s).
+// Fused on-chip kernels for sm_100a: one unit's coefficients never leave the SM(s).
 //
-//   k_fused_compress<R, CAP, NT>: a unit (box, component) is owned by a cluster of R CTAs (R = 1 or 8),
-//   each holding CAP coefficients in shared memory.  CTA r takes the block-rows b in [r*nb, (r+1)*nb)
-//   (a y-slab), so
+// COMPRESS  k_fused_compress<R, CAP, NT, STATIC>: a unit (box, component) is owned by a cluster of R CTAs
+//   (R = 1 or 8), each holding CAP coefficients in shared memory.  CTA r takes the block-rows b in
+//   [r*nb, (r+1)*nb) (a y-slab), so
 //     - its input is, per z-plane, ONE contiguous piece of 2*nb rows, read once with coalesced 16-byte
 //       streaming loads (L2 evict-first), while the same slab of the CTA's NEXT unit is prefetched into
 //       L2 (evict-last) so that HBM keeps streaming during the packing phases;
@@ -14,12 +14,21 @@
 //   f32x2 add/fma/mul) and stores the 16 coefficients into C in f order (padded: conflict-free 8-byte
 //   stores), keeping a running max of +c and -c; (B) threshold of src/compressor.cpp:212-216;
 //   (C1) per-segment count / last-kept with float4 reads; scan of the segment table (cluster-wide for
-//   R = 8); (C2) ballot-ranked emission of (run, value) pairs straight to the unit's slot in HBM.
+//   R = 8), also written out as the decoder's segment table; (C2) ballot-ranked emission of (run, value)
+//   pairs straight to the unit's slot in HBM.
 //   HBM traffic per unit = 8N (or 4N) in + 8K out: the algorithmic minimum of SURVEY.md §8d.
+//   The per-unit body (fc_unit) is a template over the geometry: FGeom (registers, 512 threads) or an
+//   SGeom<...> of literals for the 32^3 / 64^3 cubes (STATIC kernels: < 64 registers, 1024 threads).
+//   Unit descriptors are staged two units ahead through shared memory (FLookahead); single-CTA kernels
+//   take their units from a global counter (dynamic hand-out).
 //
-//   An earlier version fed phase A from a warp-specialised TMA ring (cp.async.bulk + mbarriers, commit
-//   "Fused compress v2"); with C taking 128 KB of the SM's shared memory the ring was too shallow to
-//   cover the TMA round trip and it measured slower than direct loads + L2 prefetch.
+// DECOMPRESS  k_fused_decompress<S, NT, STATIC> (+ k_seg_index): one CTA per (unit, y-slab), no clusters;
+//   see the comment block in front of FastDiv below.
+//
+//   History: a warp-specialised TMA ring (cp.async.bulk + mbarriers) fed phase A at
+//   first; with C taking 128 KB of the SM's shared memory the ring was too shallow to cover the TMA round
+//   trip and it measured slower than direct loads + L2 prefetch.  The first decompress used 8-CTA clusters
+//   with a DSMEM scatter; the segment-table design replaced it.
 #include <cstdio>
 #include <type_traits>
 
@@ -108,7 +117,6 @@ int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
     if (fused_geom(nx, ny, nz, dtype, 8, 32768, g)) return FUSED_CLS_R8;
     return FUSED_CLS_NONE;
 }
-bool fused_decode_available() { return true; }
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

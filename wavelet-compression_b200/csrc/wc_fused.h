@@ -17,7 +17,6 @@ enum { FUSED_FULL = 0, FUSED_KEYS_ONLY = 1, FUSED_GIVEN_THRESH = 2 };
 // bring it under 64 registers).
 enum { FUSED_CLS_NONE = 0, FUSED_CLS_R1 = 1, FUSED_CLS_R8 = 8, FUSED_CLS_CUBE32 = 101, FUSED_CLS_CUBE64 = 108 };
 int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
-bool fused_decode_available();
 int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
 size_t fused_decode_table_entries(int fused_cls, int nx);   // int2 entries of a unit's segment table
 bool fused_decode_needs_table(int fused_cls);               // slab-decoded classes cannot decode without one
