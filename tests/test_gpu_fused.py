@@ -1,4 +1,4 @@
-"""GPU: the fused on-chip kernels (k_fused_compress<1>, <8>) forced with WC_OPT_PATH=2, against the
+"""GPU: the fused on-chip kernels (every class: cube16 / small / cube32 / R1 / cube64 / R8) forced with WC_OPT_PATH=2, against the
 oracle.  Covers the geometries the chunking / padding logic branches on, the +M/-M tie slow path,
 NaN at f = 0, both input dtypes, and many units per launch (persistent loop, producer run-ahead)."""
 import numpy as np
@@ -9,7 +9,7 @@ from conftest import same_bits, smooth_box
 pytestmark = pytest.mark.gpu
 F999 = float(np.float32(0.999))
 
-FUSED1 = [(32, 32, 32), (16, 32, 64), (64, 16, 32), (8, 8, 8), (4, 4, 4), (2, 2, 4), (8, 4, 4), (24, 40, 12),
+FUSED1 = [(32, 32, 32), (16, 16, 16), (16, 32, 64), (64, 16, 32), (8, 8, 8), (4, 4, 4), (2, 2, 4), (8, 4, 4), (24, 40, 12),
           (48, 16, 16), (32, 16, 64), (64, 64, 8), (4, 64, 128), (12, 20, 28), (2, 2, 4096), (64, 2, 4),
           (16, 16, 24), (8, 8, 40)]
 FUSED8 = [(64, 64, 64), (32, 64, 64), (64, 32, 64), (64, 64, 32), (48, 48, 48), (16, 128, 64), (40, 48, 56)]
@@ -160,7 +160,8 @@ def test_plan_roundtrip_segment_tables_all_fused_classes(fused_ctx, oracle, wc):
     import torch
     rng = np.random.default_rng(90210)
     shapes = [(32, 32, 32)] * 150 + [(64, 64, 64)] * 20 + [(16, 32, 64)] * 12 + [(24, 40, 12)] * 6 + \
-             [(48, 48, 48)] * 6 + [(32, 64, 64)] * 5 + [(8, 8, 8)] * 9 + [(2, 2, 4)] * 3
+             [(48, 48, 48)] * 6 + [(32, 64, 64)] * 5 + [(8, 8, 8)] * 9 + [(2, 2, 4)] * 3 + [(16, 16, 16)] * 700 + \
+             [(8, 16, 8)] * 650
     host, dts = [], []
     for i, d in enumerate(shapes):
         dt = np.float32 if (i % 4 == 1 and d[0] % 4 == 0) else np.float64
@@ -185,7 +186,7 @@ def test_plan_roundtrip_segment_tables_all_fused_classes(fused_ctx, oracle, wc):
             rm = plan.rmse(odescs)
             fused_ctx.sync()
             packed = plan.fetch_host()
-            for i in list(range(0, len(shapes), 7)) + [149, 150, 169, 170, len(shapes) - 1]:
+            for i in list(range(0, 211, 7)) + list(range(211, len(shapes), 53)) + [149, 150, 169, 170, len(shapes) - 1]:
                 runs, vals, _ = oracle.compress_unit(host[i], shapes[i], keep)
                 assert same_bits(packed[i].runs, runs) and same_bits(packed[i].vals, vals), (i, shapes[i], keep)
                 ob = oracle.decompress_unit(runs, vals, shapes[i])
@@ -200,7 +201,7 @@ def test_plan_roundtrip_segment_tables_all_fused_classes(fused_ctx, oracle, wc):
     plan.decompress(odescs, wc.WC_DEVICE)
     fused_ctx.sync()
     packed = plan.fetch_host()
-    for i in (0, 150, 170, 185, len(shapes) - 1):
+    for i in (0, 150, 170, 185, 300, 1000, len(shapes) - 1):
         ob = oracle.decompress_unit(packed[i].runs, packed[i].vals, shapes[i])
         assert same_bits(outs[i].cpu().numpy().reshape(ob.shape), ob), i
     plan.close()

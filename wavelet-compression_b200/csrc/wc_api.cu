@@ -113,8 +113,9 @@ struct wc_ctx {
 
 // Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
 // stream), then the single-CTA kernels (second stream when both kinds are present).
-enum { FL_N = 4 };
-static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_CUBE32, FUSED_CLS_R1};
+enum { FL_N = 6 };
+static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_CUBE32, FUSED_CLS_R1,
+                                    FUSED_CLS_CUBE16, FUSED_CLS_R1S};
 static inline bool fl_is_cluster(int k) { return k < 2; }
 
 struct wc_plan {
@@ -546,7 +547,7 @@ int wc_plan_destroy(wc_plan* p) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &p->d_units, &p->d_states, &p->d_in, &p->d_out, &p->d_coef, &p->d_xtiles,
                        &p->d_ctiles, &p->d_tile_i, &p->d_gkey, &p->d_offsets, &p->d_dense, &p->d_fl[0],
-                       &p->d_fl[1], &p->d_fl[2], &p->d_fl[3], &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
+                       &p->d_fl[1], &p->d_fl[2], &p->d_fl[3], &p->d_fl[4], &p->d_fl[5], &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
                        &p->d_psum, &p->d_err, &p->d_rmse_units, &p->d_rmse_sum, &p->d_rmse,
                        &p->d_stage_out };
     for (DevBuf* b : bufs) b->release();
@@ -973,7 +974,7 @@ struct DecJob {
 struct DecCache {
     std::vector<uint64_t> key;
     bool   valid = false;
-    size_t fl_n[4] = {};
+    size_t fl_n[8] = {};
 };
 
 static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& d_coef,

@@ -113,6 +113,8 @@ int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
     FGeom g;
     if (nx == 32 && ny == 32 && nz == 32) return FUSED_CLS_CUBE32;
     if (nx == 64 && ny == 64 && nz == 64) return FUSED_CLS_CUBE64;
+    if (nx == 16 && ny == 16 && nz == 16) return FUSED_CLS_CUBE16;
+    if (fused_geom(nx, ny, nz, dtype, 1, 4096, g)) return FUSED_CLS_R1S;
     if (fused_geom(nx, ny, nz, dtype, 1, 32768, g)) return FUSED_CLS_R1;
     if (fused_geom(nx, ny, nz, dtype, 8, 32768, g)) return FUSED_CLS_R8;
     return FUSED_CLS_NONE;
@@ -375,8 +377,14 @@ struct FLookahead {
     FDesc*         slot;           // where unit k+2 goes (= the slot of unit k)
     int            ui_prev;        // static: list position of unit k+1
     int            idx, uid;       // thread 0 only
+    int            batch, batch_next, batch_left;
     __device__ __forceinline__ void stage1() {          // top of the unit
-        idx = work_counter ? atomicAdd(work_counter, 1) : ui_prev + stride;
+        if (!work_counter) { idx = ui_prev + stride; return; }
+        // dynamic hand-out, `batch` consecutive units per atomic: hundreds of CTAs hitting one address cost
+        // ~15-30 cycles per atomic chip-wide, which would bound the small-unit kernels
+        if (batch_left == 0) { batch_next = atomicAdd(work_counter, batch); batch_left = batch; }
+        idx = batch_next++;
+        --batch_left;
     }
     __device__ __forceinline__ void stage2() {          // after the first barrier: slot k&1 is free now
         uid = -1;          // volatile: issued HERE (the compiler would otherwise sink the load to its first use)
@@ -762,7 +770,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
 
 // STATIC: every unit of the list is the cube this variant is specialised for (32^3 for R = 1, 64^3 for R = 8).
 template <int R, int CAP, int NT, bool STATIC>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, (CAP <= 4096 ? 4 : 1))
 k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                  const int* __restrict__ unit_list, int n_list, double one_minus_keep,
                  const u64* __restrict__ global_key, int mode, int* __restrict__ work_counter) {
@@ -808,6 +816,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
     la.units = units; la.unit_list = unit_list; la.work_counter = dynamic ? work_counter : nullptr;
     la.n_list = n_list; la.stride = (int)ncl;
     la.idx = 0; la.uid = -1;
+    la.batch = CAP <= 4096 ? 16 : 1; la.batch_next = 0; la.batch_left = 0;
     if (tid == 0) {
         // prologue: units 0 and 1 of this CTA
         la.ui_prev = (int)cid - (int)ncl;
@@ -845,7 +854,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
 #define WC_FC_UNIT(GEOM) fc_unit<R, CAP, NT>(GEOM, u, uid, S, pf, la, rank, xph1, xph2, xph3, states, \
                                              one_minus_keep, global_key, mode, pol, lt)
         if constexpr (STATIC) {
-            constexpr int CUBE = R == 1 ? 32 : 64;
+            constexpr int CUBE = R == 1 ? (CAP <= 4096 ? 16 : 32) : 64;
             if (u.dtype == WC_F64) WC_FC_UNIT((SGeom<CUBE, CUBE, CUBE, 8, R>()));
             else                   WC_FC_UNIT((SGeom<CUBE, CUBE, CUBE, 4, R>()));
         } else {
@@ -920,6 +929,12 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
     case FUSED_CLS_CUBE32:
         return launch_fc<1, 32768, 1024, true>(KID_FUSED_C1S, mode, units, states, unit_list, n_list,
                                                one_minus_keep, global_key, sm_count, st, ls, work_counter);
+    case FUSED_CLS_R1S:
+        return launch_fc<1, 4096, 128, false>(KID_FUSED_C1T, mode, units, states, unit_list, n_list,
+                                              one_minus_keep, global_key, sm_count, st, ls, work_counter);
+    case FUSED_CLS_CUBE16:
+        return launch_fc<1, 4096, 256, true>(KID_FUSED_C16, mode, units, states, unit_list, n_list,
+                                             one_minus_keep, global_key, sm_count, st, ls, work_counter);
     case FUSED_CLS_CUBE64:
         return launch_fc<8, 32768, 1024, true>(KID_FUSED_C8S, mode, units, states, unit_list, n_list,
                                                one_minus_keep, global_key, sm_count, st, ls, nullptr);
@@ -1182,6 +1197,7 @@ struct FDLookahead {
     FDDesc*           next_slot;   // item k+1: descriptor present, K still to be resolved
     int               ui_prev;
     int               idx, uid, kreg;   // thread 0 only
+    int               batch, batch_next, batch_left;
     __device__ __forceinline__ void resolve_k_issue() {
         kreg = 0;
         if (next_slot->uid >= 0) {
@@ -1191,7 +1207,12 @@ struct FDLookahead {
         }
     }
     __device__ __forceinline__ void stage1() {          // top of the item
-        idx = work_counter ? atomicAdd(work_counter, 1) : ui_prev + stride;
+        if (!work_counter) { idx = ui_prev + stride; return; }
+        // dynamic hand-out, `batch` consecutive units per atomic: hundreds of CTAs hitting one address cost
+        // ~15-30 cycles per atomic chip-wide, which would bound the small-unit kernels
+        if (batch_left == 0) { batch_next = atomicAdd(work_counter, batch); batch_left = batch; }
+        idx = batch_next++;
+        --batch_left;
     }
     __device__ __forceinline__ void stage2() {          // after the first barrier: slot k&1 is free now
         uid = -1;
@@ -1392,13 +1413,13 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
 }
 
 // STATIC: every unit of the list is the cube this variant is specialised for (32^3 for S = 1, 64^3 for S = 8).
-template <int S, int NT, bool STATIC>
-__global__ void __launch_bounds__(NT, 1)
+template <int S, int CAP, int NT, bool STATIC>
+__global__ void __launch_bounds__(NT, (CAP <= 4096 ? 4 : 1))
 k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
                    const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
                    int* __restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int BASE = (32768 + F_CPAD) * 4;
+    constexpr int BASE = (CAP + F_CPAD) * 4;
     float* const    C    = reinterpret_cast<float*>(smem);
     uint32_t* const s_wt = reinterpret_cast<uint32_t*>(smem + BASE);               // [2][32]
     FDDesc* const s_desc = reinterpret_cast<FDDesc*>(smem + BASE + 256);          // [2] x 88 bytes
@@ -1411,6 +1432,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
     la.work_counter = work_counter;
     la.n_items = n_items; la.stride = (int)gridDim.x;
     la.idx = 0; la.uid = -1; la.kreg = 0;
+    la.batch = CAP <= 4096 ? 16 : 1; la.batch_next = 0; la.batch_left = 0;
     if (tid == 0) {
         la.ui_prev = (int)blockIdx.x - (int)gridDim.x;
         for (int k = 0; k < 2; ++k) {
@@ -1438,23 +1460,23 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         const bool have_next = la.next_slot->ui < n_items;
 #define WC_FD_UNIT(GEOM) fd_unit<S, NT>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next)
         if constexpr (STATIC) {
-            constexpr int CUBE = S == 1 ? 32 : 64;
+            constexpr int CUBE = S == 1 ? (CAP <= 4096 ? 16 : 32) : 64;
             WC_FD_UNIT((SGeom<CUBE, CUBE, CUBE, 8, S>()));
         } else {
             FGeom g;
-            fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, S, 32768, g);   // same rule as fused_decode_class
+            fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, S, CAP, g);   // same rule as fused_decode_class
             WC_FD_UNIT(g);
         }
 #undef WC_FD_UNIT
     }
 }
 
-template <int S, int NT, bool STATIC>
+template <int S, int CAP, int NT, bool STATIC>
 static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                              int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter,
                              bool build_tables) {
-    auto kern = k_fused_decompress<S, NT, STATIC>;
-    constexpr int smem = (32768 + F_CPAD) * 4 + 1024;
+    auto kern = k_fused_decompress<S, CAP, NT, STATIC>;
+    constexpr int smem = (CAP + F_CPAD) * 4 + 1024;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     if (S > 1 && build_tables) {
@@ -1466,8 +1488,14 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    const long long items = (long long)n * S;
-    const int nc = (int)(sm_count < items ? sm_count : items);
+    static int per_sm = 0;           // resident CTAs per SM (4 for the small-unit variants)
+    if (per_sm == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    }
+    const long long items = (long long)n * S, slots = (long long)per_sm * sm_count;
+    const int nc = (int)(slots < items ? slots : items);
     ls->begin(kid, st);
     kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter);
     ls->end(st);
@@ -1480,7 +1508,9 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
     if (reinterpret_cast<uintptr_t>(out_ptr) & (out_dtype == WC_F64 ? 15u : 7u)) return FUSED_CLS_NONE;
     if (nx == 32 && ny == 32 && nz == 32) return FUSED_CLS_CUBE32;
     if (nx == 64 && ny == 64 && nz == 64) return FUSED_CLS_CUBE64;
+    if (nx == 16 && ny == 16 && nz == 16) return FUSED_CLS_CUBE16;
     FGeom g;
+    if (fused_geom(nx, ny, nz, WC_F64, 1, 4096, g)) return FUSED_CLS_R1S;
     if (fused_geom(nx, ny, nz, WC_F64, 1, 32768, g)) return FUSED_CLS_R1;   // WC_F64: keeps the X*es % 16 rule valid for both
     if (fused_geom(nx, ny, nz, WC_F64, 8, 32768, g)) return FUSED_CLS_R8;
     return FUSED_CLS_NONE;
@@ -1488,7 +1518,9 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
 // int2 entries of the segment table a slab-decoded unit needs (0 for the other classes)
 size_t fused_decode_table_entries(int fused_cls, int nx) {
     if (fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64) return (size_t)(2 * nx * 8 + 1);
-    if (fused_cls == FUSED_CLS_R1 || fused_cls == FUSED_CLS_CUBE32) return (size_t)(2 * nx + 1);
+    if (fused_cls == FUSED_CLS_R1 || fused_cls == FUSED_CLS_CUBE32 || fused_cls == FUSED_CLS_R1S ||
+        fused_cls == FUSED_CLS_CUBE16)
+        return (size_t)(2 * nx + 1);
     return 0;
 }
 bool fused_decode_needs_table(int fused_cls) { return fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64; }
@@ -1499,13 +1531,17 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
     if (n_list <= 0) return cudaSuccess;
     switch (fused_cls) {
     case FUSED_CLS_R1:
-        return launch_fd<1, 512, false>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
+        return launch_fd<1, 32768, 512, false>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     case FUSED_CLS_R8:
-        return launch_fd<8, 512, false>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
+        return launch_fd<8, 32768, 512, false>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
     case FUSED_CLS_CUBE32:
-        return launch_fd<1, 1024, true>(KID_FUSED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
+        return launch_fd<1, 32768, 1024, true>(KID_FUSED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     case FUSED_CLS_CUBE64:
-        return launch_fd<8, 1024, true>(KID_FUSED_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
+        return launch_fd<8, 32768, 1024, true>(KID_FUSED_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
+    case FUSED_CLS_R1S:
+        return launch_fd<1, 4096, 128, false>(KID_FUSED_D1T, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
+    case FUSED_CLS_CUBE16:
+        return launch_fd<1, 4096, 256, true>(KID_FUSED_D16, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     }
     return cudaErrorInvalidValue;
 }
