@@ -161,7 +161,7 @@ def test_plan_roundtrip_segment_tables_all_fused_classes(fused_ctx, oracle, wc):
     rng = np.random.default_rng(90210)
     shapes = [(32, 32, 32)] * 150 + [(64, 64, 64)] * 20 + [(16, 32, 64)] * 12 + [(24, 40, 12)] * 6 + \
              [(48, 48, 48)] * 6 + [(32, 64, 64)] * 5 + [(8, 8, 8)] * 9 + [(2, 2, 4)] * 3 + [(16, 16, 16)] * 700 + \
-             [(8, 16, 8)] * 650
+             [(8, 16, 8)] * 650 + [(8, 8, 8)] * 5000
     host, dts = [], []
     for i, d in enumerate(shapes):
         dt = np.float32 if (i % 4 == 1 and d[0] % 4 == 0) else np.float64
@@ -201,7 +201,7 @@ def test_plan_roundtrip_segment_tables_all_fused_classes(fused_ctx, oracle, wc):
     plan.decompress(odescs, wc.WC_DEVICE)
     fused_ctx.sync()
     packed = plan.fetch_host()
-    for i in (0, 150, 170, 185, 300, 1000, len(shapes) - 1):
+    for i in (0, 150, 170, 185, 300, 1000, 3000, 6000, len(shapes) - 1):
         ob = oracle.decompress_unit(packed[i].runs, packed[i].vals, shapes[i])
         assert same_bits(outs[i].cpu().numpy().reshape(ob.shape), ob), i
     plan.close()

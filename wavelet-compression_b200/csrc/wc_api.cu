@@ -113,9 +113,9 @@ struct wc_ctx {
 
 // Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
 // stream), then the single-CTA kernels (second stream when both kinds are present).
-enum { FL_N = 6 };
+enum { FL_N = 7 };
 static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_CUBE32, FUSED_CLS_R1,
-                                    FUSED_CLS_CUBE16, FUSED_CLS_R1S};
+                                    FUSED_CLS_CUBE16, FUSED_CLS_R1S, FUSED_CLS_CUBE8};
 static inline bool fl_is_cluster(int k) { return k < 2; }
 
 struct wc_plan {
@@ -547,7 +547,7 @@ int wc_plan_destroy(wc_plan* p) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &p->d_units, &p->d_states, &p->d_in, &p->d_out, &p->d_coef, &p->d_xtiles,
                        &p->d_ctiles, &p->d_tile_i, &p->d_gkey, &p->d_offsets, &p->d_dense, &p->d_fl[0],
-                       &p->d_fl[1], &p->d_fl[2], &p->d_fl[3], &p->d_fl[4], &p->d_fl[5], &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
+                       &p->d_fl[1], &p->d_fl[2], &p->d_fl[3], &p->d_fl[4], &p->d_fl[5], &p->d_fl[6], &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
                        &p->d_psum, &p->d_err, &p->d_rmse_units, &p->d_rmse_sum, &p->d_rmse,
                        &p->d_stage_out };
     for (DevBuf* b : bufs) b->release();
@@ -972,10 +972,35 @@ struct DecJob {
 };
 
 struct DecCache {
-    std::vector<uint64_t> key;
-    bool   valid = false;
-    size_t fl_n[8] = {};
+    uint64_t h1 = 0, h2 = 0;      // 128-bit hash of (output space, pointers, dtypes) of the cached call
+    bool     valid = false;
+    size_t   fl_n[8] = {};
 };
+static inline void dec_hash(uint64_t& h1, uint64_t& h2, uint64_t v) {
+    h1 = (h1 ^ v) * 0x9E3779B97F4A7C15ull; h1 ^= h1 >> 29;
+    h2 = (h2 + v) * 0xC2B2AE3D27D4EB4Full; h2 ^= h2 >> 31;
+}
+
+// A plan that decodes into the same boxes again (keep sweeps of the estimate mode) re-launches from the
+// device tables of the previous call; only all-fused batches without scratch are cached.
+static int relaunch_decompress(wc_ctx* ctx, const DecCache* cache, DevBuf& d_dec_units, DevBuf& d_inv_units,
+                               DevBuf& d_err, DevBuf& d_fused_list) {
+    CTX_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 64, ctx->stream));
+    CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
+    int* dl = d_fused_list.as<int>();
+    size_t o = 0;
+    for (int k = 0; k < FL_N; ++k) {
+        if (!cache->fl_n[k]) continue;
+        int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
+        CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+        CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
+                                              d_inv_units.as<InvUnitDev>(), dl + o, (int)cache->fl_n[k],
+                                              d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls,
+                                              counter, false));
+        o += cache->fl_n[k];
+    }
+    return WC_OK;
+}
 
 static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& d_coef,
                           DevBuf& d_dec_units, DevBuf& d_inv_units, DevBuf& d_inv_tiles,
@@ -983,36 +1008,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
                           DecCache* cache = nullptr) {
     int n = (int)jobs.size();
     if (n == 0) return WC_OK;
-    // A plan that decodes into the same boxes again (keep sweeps of the estimate mode) re-launches from the
-    // device tables of the previous call; only all-fused batches without scratch are cached.
-    if (cache) {
-        std::vector<uint64_t> key(4 * (size_t)n);
-        for (int i = 0; i < n; ++i) {
-            key[4 * i]     = (uint64_t)(uintptr_t)jobs[i].pairs_dev;
-            key[4 * i + 1] = (uint64_t)(uintptr_t)jobs[i].out_dev;
-            key[4 * i + 2] = (uint64_t)(uintptr_t)jobs[i].segtab;
-            key[4 * i + 3] = ((uint64_t)(uint32_t)jobs[i].out_dtype << 32) | (uint32_t)jobs[i].npairs;
-        }
-        if (cache->valid && cache->key == key) {
-            CTX_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 64, ctx->stream));
-            CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
-            int* dl = d_fused_list.as<int>();
-            size_t o = 0;
-            for (int k = 0; k < FL_N; ++k) {
-                if (!cache->fl_n[k]) continue;
-                int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
-                CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-                CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
-                                                      d_inv_units.as<InvUnitDev>(), dl + o, (int)cache->fl_n[k],
-                                                      d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls,
-                                                      counter, false));
-                o += cache->fl_n[k];
-            }
-            return WC_OK;
-        }
-        cache->valid = false;
-        cache->key.swap(key);
-    }
+    if (cache) cache->valid = false;
     std::vector<DecUnitDev> du(n);
     std::vector<InvUnitDev> iu(n);
     std::vector<int2> ptiles, xtiles;
@@ -1122,9 +1118,9 @@ int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
     wc_ctx* ctx = p->ctx;
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
     int n = p->n_units;
-    std::vector<DecJob> jobs(n);
     size_t stage = 0;
     std::vector<size_t> stage_off(n);
+    uint64_t h1 = 0x243F6A8885A308D3ull ^ (uint64_t)out_space, h2 = 0x13198A2E03707344ull + (uint64_t)n;
     for (int i = 0; i < n; ++i) {
         const UnitDev& u = p->h_units[i];
         if (out[i].nx != u.nx || out[i].ny != u.ny || out[i].nz != u.nz) return WC_ERR_INVALID_ARG;
@@ -1132,8 +1128,15 @@ int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
         if (u.n > 0 && !out[i].data) return WC_ERR_INVALID_ARG;
         stage_off[i] = stage;
         stage += align_up((size_t)u.n * dtype_size(out[i].dtype), 256);
+        dec_hash(h1, h2, out_space == WC_DEVICE ? (uint64_t)(uintptr_t)out[i].data : 0);
+        dec_hash(h1, h2, (uint64_t)out[i].dtype);
     }
     if (out_space == WC_HOST) CTX_CUDA(ctx, p->d_stage_out.reserve(std::max<size_t>(stage, 256)));
+    dec_hash(h1, h2, (uint64_t)(uintptr_t)p->d_stage_out.p);
+    if (!p->dec_cache) p->dec_cache = new DecCache();
+    const bool hit = p->dec_cache->valid && p->dec_cache->h1 == h1 && p->dec_cache->h2 == h2;
+    std::vector<DecJob> jobs(hit ? 0 : n);
+    if (!hit)
     for (int i = 0; i < n; ++i) {
         const UnitDev& u = p->h_units[i];
         jobs[i].pairs_dev  = u.out;
@@ -1144,11 +1147,11 @@ int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
         jobs[i].out_dtype = out[i].dtype;
         if (p->has_segtab[i] && u.coef) jobs[i].segtab = reinterpret_cast<const int2*>(u.coef);
     }
-    if (!p->dec_cache) p->dec_cache = new DecCache();
-    int rc = run_decompress(ctx, jobs, ctx->ws_coef, p->d_dec_units,
-                            p->d_inv_units, p->d_inv_tiles, p->d_ptiles, p->d_psum, p->d_err,
-                            p->d_dec_list, p->dec_cache);
+    int rc = hit ? relaunch_decompress(ctx, p->dec_cache, p->d_dec_units, p->d_inv_units, p->d_err, p->d_dec_list)
+                 : run_decompress(ctx, jobs, ctx->ws_coef, p->d_dec_units, p->d_inv_units, p->d_inv_tiles,
+                                  p->d_ptiles, p->d_psum, p->d_err, p->d_dec_list, p->dec_cache);
     if (rc != WC_OK) return rc;
+    p->dec_cache->h1 = h1; p->dec_cache->h2 = h2;
     if (out_space == WC_HOST) {
         CopyList cl;
         for (int i = 0; i < n; ++i)

@@ -114,6 +114,7 @@ int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
     if (nx == 32 && ny == 32 && nz == 32) return FUSED_CLS_CUBE32;
     if (nx == 64 && ny == 64 && nz == 64) return FUSED_CLS_CUBE64;
     if (nx == 16 && ny == 16 && nz == 16) return FUSED_CLS_CUBE16;
+    if (nx == 8 && ny == 8 && nz == 8) return FUSED_CLS_CUBE8;
     if (fused_geom(nx, ny, nz, dtype, 1, 4096, g)) return FUSED_CLS_R1S;
     if (fused_geom(nx, ny, nz, dtype, 1, 32768, g)) return FUSED_CLS_R1;
     if (fused_geom(nx, ny, nz, dtype, 8, 32768, g)) return FUSED_CLS_R8;
@@ -770,7 +771,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
 
 // STATIC: every unit of the list is the cube this variant is specialised for (32^3 for R = 1, 64^3 for R = 8).
 template <int R, int CAP, int NT, bool STATIC>
-__global__ void __launch_bounds__(NT, (CAP <= 4096 ? 4 : 1))
+__global__ void __launch_bounds__(NT, (CAP <= 512 ? 32 : CAP <= 4096 ? 4 : 1))
 k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                  const int* __restrict__ unit_list, int n_list, double one_minus_keep,
                  const u64* __restrict__ global_key, int mode, int* __restrict__ work_counter) {
@@ -854,7 +855,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
 #define WC_FC_UNIT(GEOM) fc_unit<R, CAP, NT>(GEOM, u, uid, S, pf, la, rank, xph1, xph2, xph3, states, \
                                              one_minus_keep, global_key, mode, pol, lt)
         if constexpr (STATIC) {
-            constexpr int CUBE = R == 1 ? (CAP <= 4096 ? 16 : 32) : 64;
+            constexpr int CUBE = R == 1 ? (CAP <= 512 ? 8 : CAP <= 4096 ? 16 : 32) : 64;
             if (u.dtype == WC_F64) WC_FC_UNIT((SGeom<CUBE, CUBE, CUBE, 8, R>()));
             else                   WC_FC_UNIT((SGeom<CUBE, CUBE, CUBE, 4, R>()));
         } else {
@@ -935,6 +936,9 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
     case FUSED_CLS_CUBE16:
         return launch_fc<1, 4096, 256, true>(KID_FUSED_C16, mode, units, states, unit_list, n_list,
                                              one_minus_keep, global_key, sm_count, st, ls, work_counter);
+    case FUSED_CLS_CUBE8:    // one warp per CTA, up to 32 CTAs per SM
+        return launch_fc<1, 512, 32, true>(KID_FUSED_C8C, mode, units, states, unit_list, n_list,
+                                           one_minus_keep, global_key, sm_count, st, ls, work_counter);
     case FUSED_CLS_CUBE64:
         return launch_fc<8, 32768, 1024, true>(KID_FUSED_C8S, mode, units, states, unit_list, n_list,
                                                one_minus_keep, global_key, sm_count, st, ls, nullptr);
@@ -999,7 +1003,7 @@ constexpr int FD_PPT = 8;        // pairs per thread per tile of the block-wide 
 // q-th segment of a warp (slab decode): round-robin, with the parity flipped every other round — odd
 // segments are the high-j' (detail, sparse) halves, so a fixed parity would give half the warps all the work.
 // NW is even and nseg = 2X is even, so q * NW + (warp ^ 1) stays below nseg whenever q * NW + warp does.
-__device__ __forceinline__ int fd_seg_of(int q, int warp, int NW) { return q * NW + (warp ^ (q & 1)); }
+__device__ __forceinline__ int fd_seg_of(int q, int warp, int NW) { return NW > 1 ? q * NW + (warp ^ (q & 1)) : q; }
 
 // Loads FD_PPT consecutive pairs starting at p (a multiple of FD_PPT); pairs past k1 read as (0, 0).
 __device__ __forceinline__ void fd_load_tile(const int2* pairs, bool vec16, int p, int k1, int2 (&pr)[FD_PPT]) {
@@ -1414,7 +1418,7 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
 
 // STATIC: every unit of the list is the cube this variant is specialised for (32^3 for S = 1, 64^3 for S = 8).
 template <int S, int CAP, int NT, bool STATIC>
-__global__ void __launch_bounds__(NT, (CAP <= 4096 ? 4 : 1))
+__global__ void __launch_bounds__(NT, (CAP <= 512 ? 32 : CAP <= 4096 ? 4 : 1))
 k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
                    const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
                    int* __restrict__ work_counter) {
@@ -1460,7 +1464,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         const bool have_next = la.next_slot->ui < n_items;
 #define WC_FD_UNIT(GEOM) fd_unit<S, NT>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next)
         if constexpr (STATIC) {
-            constexpr int CUBE = S == 1 ? (CAP <= 4096 ? 16 : 32) : 64;
+            constexpr int CUBE = S == 1 ? (CAP <= 512 ? 8 : CAP <= 4096 ? 16 : 32) : 64;
             WC_FD_UNIT((SGeom<CUBE, CUBE, CUBE, 8, S>()));
         } else {
             FGeom g;
@@ -1509,6 +1513,7 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
     if (nx == 32 && ny == 32 && nz == 32) return FUSED_CLS_CUBE32;
     if (nx == 64 && ny == 64 && nz == 64) return FUSED_CLS_CUBE64;
     if (nx == 16 && ny == 16 && nz == 16) return FUSED_CLS_CUBE16;
+    if (nx == 8 && ny == 8 && nz == 8) return FUSED_CLS_CUBE8;
     FGeom g;
     if (fused_geom(nx, ny, nz, WC_F64, 1, 4096, g)) return FUSED_CLS_R1S;
     if (fused_geom(nx, ny, nz, WC_F64, 1, 32768, g)) return FUSED_CLS_R1;   // WC_F64: keeps the X*es % 16 rule valid for both
@@ -1519,7 +1524,7 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
 size_t fused_decode_table_entries(int fused_cls, int nx) {
     if (fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64) return (size_t)(2 * nx * 8 + 1);
     if (fused_cls == FUSED_CLS_R1 || fused_cls == FUSED_CLS_CUBE32 || fused_cls == FUSED_CLS_R1S ||
-        fused_cls == FUSED_CLS_CUBE16)
+        fused_cls == FUSED_CLS_CUBE16 || fused_cls == FUSED_CLS_CUBE8)
         return (size_t)(2 * nx + 1);
     return 0;
 }
@@ -1542,6 +1547,8 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
         return launch_fd<1, 4096, 128, false>(KID_FUSED_D1T, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     case FUSED_CLS_CUBE16:
         return launch_fd<1, 4096, 256, true>(KID_FUSED_D16, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
+    case FUSED_CLS_CUBE8:
+        return launch_fd<1, 512, 32, true>(KID_FUSED_D8C, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     }
     return cudaErrorInvalidValue;
 }
