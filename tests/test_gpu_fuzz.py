@@ -1,0 +1,70 @@
+"""GPU: randomised shapes across every kernel class boundary (<= 512, <= 4096, <= 32768, <= 262144 cells; even
+and odd dims -> fused and generic paths), random keep values, both dtypes: packed pairs, reconstructions and
+RMSE against the oracle, for the one-shot batch API and for the plan round trip (segment tables)."""
+import numpy as np
+import pytest
+
+from conftest import same_bits, smooth_box
+
+pytestmark = pytest.mark.gpu
+
+
+def _shapes(rng, n):
+    out = []
+    pools = [[2, 4, 6, 8, 10, 12, 16, 20, 24, 32, 40, 48, 64], [1, 3, 5, 7, 9, 15, 17, 31, 33]]
+    while len(out) < n:
+        odd = rng.random() < 0.25
+        d = tuple(int(rng.choice(pools[1] if (odd and rng.random() < 0.5) else pools[0])) for _ in range(3))
+        if d[0] * d[1] * d[2] <= 262144:
+            out.append(d)
+    return out
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16, 17, 18, 19, 20])
+def test_fuzz_batch_and_plan_roundtrip(wc, ctx, oracle, seed):
+    import torch
+    rng = np.random.default_rng(seed)
+    shapes = _shapes(rng, 70)
+    # make sure every literal-geometry class and its neighbours are present
+    shapes += [(8, 8, 8)] * 3 + [(16, 16, 16)] * 3 + [(32, 32, 32)] * 2 + [(64, 64, 64)] + [(8, 8, 4), (16, 16, 12), (32, 32, 28), (64, 64, 60), (48, 4, 8), (64, 2, 4), (64, 4, 16), (2, 64, 64), (64, 64, 2)]
+    boxes, dts = [], []
+    for i, d in enumerate(shapes):
+        dt = np.float32 if rng.random() < 0.3 else np.float64
+        b = smooth_box(d, rng, dtype=dt, sym=bool(i % 2), noise=10.0 ** -int(rng.integers(0, 6)))
+        if rng.random() < 0.08:
+            b = -np.abs(b) - 0.5                     # negative max: everything kept
+        if rng.random() < 0.05:
+            b = np.zeros_like(b)
+        boxes.append(b); dts.append(dt)
+    keep = float(np.float32(rng.choice([0.9, 0.99, 0.999, 0.9999])))
+    # one-shot batch API (host boxes in, host pairs out; foreign-stream decode on the way back)
+    packed = ctx.compress_batch(boxes, keep, dims=shapes)
+    recon = ctx.decompress_batch(packed)
+    for b, d, p, r in zip(boxes, shapes, packed, recon):
+        runs, vals, _ = oracle.compress_unit(b, d, keep)
+        assert same_bits(p.runs, runs) and same_bits(p.vals, vals), (seed, d, b.dtype)
+        ob = oracle.decompress_unit(runs, vals, d)
+        assert same_bits(r.reshape(ob.shape), ob), (seed, d)
+    # plan round trip on the device
+    dev = [torch.from_numpy(np.ascontiguousarray(b)).cuda() for b in boxes]
+    outs = [torch.full((int(np.prod(d)),), 3.0, dtype=torch.float32, device="cuda") for d in shapes]
+    torch.cuda.synchronize()
+    code = lambda dt: wc.WC_F64 if dt == np.float64 else wc.WC_F32
+    descs = wc.capi.box_descs([t.data_ptr() for t in dev], [code(dt) for dt in dts], shapes)
+    odescs = wc.capi.box_descs([t.data_ptr() for t in outs], [wc.WC_F32] * len(outs), shapes)
+    plan = ctx.plan(descs, wc.WC_DEVICE)
+    for k2 in (keep, float(np.float32(0.95))):
+        plan.compress(k2)
+        plan.decompress(odescs, wc.WC_DEVICE)
+        rm = plan.rmse(odescs)
+        ctx.sync()
+        got = plan.fetch_host()
+        for i, (b, d) in enumerate(zip(boxes, shapes)):
+            runs, vals, _ = oracle.compress_unit(b, d, k2)
+            assert same_bits(got[i].runs, runs) and same_bits(got[i].vals, vals), (seed, i, d, k2)
+            ob = oracle.decompress_unit(runs, vals, d)
+            assert same_bits(outs[i].cpu().numpy().reshape(ob.shape), ob), (seed, i, d, k2)
+            oe = oracle.rmse(b.astype(np.float32), ob, d)
+            n = d[0] * d[1] * d[2]
+            assert abs(rm[i] - oe) <= max(1e-12, n * 2.0 ** -54) * max(abs(oe), 1e-300), (seed, i, d, rm[i], oe)
+    plan.close()

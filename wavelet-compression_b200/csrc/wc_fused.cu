@@ -1264,7 +1264,7 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
     if (!use_tab) {
         fd_load_tile(pairs, vec16, tid * FD_PPT, K, pr);           // in flight during the zero-fill
     } else {
-        // segment table entries of this warp's segments (<= 16 per warp): lane 2q + e <- tab[m(q) + e]
+        // segment table entries of this warp's first 16 segments: lane 2q + e <- tab[m(q) + e]
         const int sg = fd_seg_of(lane >> 1, warp, NW);
         if ((lane >> 1) * NW + warp < g.nseg)
             te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sg >> 1) * (2 * S) + (sg & 1) * S + (int)rank + (lane & 1));
@@ -1322,8 +1322,17 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
             const int sg = fd_seg_of(q, warp, NW);
             const int i = sg >> 1, half = sg & 1;
             const int m = i * (2 * S) + half * S + (int)rank;
-            const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * q), e0y = __shfl_sync(0xffffffffu, te.y, 2 * q);
-            const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * q + 1);
+            if (q && (q & 15) == 0) {
+                // a warp holds the entries of 16 segments at a time: next round (more than 16 segments per
+                // warp only happens with few warps and a long x axis, e.g. 48 x 4 x 8 boxes)
+                const int qq = q + (lane >> 1), sq = fd_seg_of(qq, warp, NW);
+                te = make_int2(0, 0);
+                if (qq * NW + warp < g.nseg)
+                    te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sq >> 1) * (2 * S) + (sq & 1) * S + (int)rank + (lane & 1));
+            }
+            const int ql = q & 15;
+            const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * ql), e0y = __shfl_sync(0xffffffffu, te.y, 2 * ql);
+            const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * ql + 1);
             float* const cseg = C + i * g.slab + half * g.seglen;    // C index of flat index m * seglen
             const uint32_t fseg = (uint32_t)m * seglen;
             uint32_t base = (uint32_t)e0y;                           // flat index of the pair before the first (or -1)
