@@ -111,6 +111,12 @@ struct wc_ctx {
     unsigned     counter_next = 0;
 };
 
+// Device tables of a plan's last wc_plan_decompress call (see run_decompress / relaunch_decompress).
+struct DecCache {
+    uint64_t h1 = 0, h2 = 0;      // 128-bit hash of (output space, pointers, dtypes) of the cached call
+    bool     valid = false;
+    size_t   fl_n[8] = {};
+};
 // Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
 // stream), then the single-CTA kernels (second stream when both kinds are present).
 enum { FL_N = 7 };
@@ -146,7 +152,7 @@ struct wc_plan {
     DevBuf d_rmse_tiles;
     long long rmse_tiles = -1;   // tiles resident in d_rmse_tiles (-1: not built yet)
     DevBuf d_dec_list;           // fused work lists of the last wc_plan_decompress (re-used on a cache hit)
-    struct DecCache* dec_cache = nullptr;
+    DecCache* dec_cache = nullptr;
     std::vector<cudaEvent_t> ev;
     DevBuf d_running;
 };
@@ -971,11 +977,6 @@ struct DecJob {
     const int2*    segtab = nullptr; // optional: segment table already on the device (plan round trip)
 };
 
-struct DecCache {
-    uint64_t h1 = 0, h2 = 0;      // 128-bit hash of (output space, pointers, dtypes) of the cached call
-    bool     valid = false;
-    size_t   fl_n[8] = {};
-};
 static inline void dec_hash(uint64_t& h1, uint64_t& h2, uint64_t v) {
     h1 = (h1 ^ v) * 0x9E3779B97F4A7C15ull; h1 ^= h1 >> 29;
     h2 = (h2 + v) * 0xC2B2AE3D27D4EB4Full; h2 ^= h2 >> 31;
