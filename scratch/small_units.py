@@ -8,7 +8,8 @@ pkg = g.package()
 stream = torch.cuda.Stream()
 ctx = pkg.Context(0, stream=stream.cuda_stream)
 KEEP = 0.9990000128746033
-for dims, n_units in (((16, 16, 16), 262144), ((8, 8, 8), 1048576), ((16, 32, 64), 32768), ((32, 32, 32), 32768)):
+for dims, n_units in (((16, 16, 16), 262144), ((8, 8, 8), 1048576), ((16, 32, 64), 32768), ((32, 32, 32), 32768),
+                      ((40, 40, 40), 16384), ((56, 56, 40), 8192), ((40, 40, 42), 16384)):
     n = dims[0] * dims[1] * dims[2]
     gen = torch.Generator(device='cuda'); gen.manual_seed(1)
     x = torch.linspace(0, 50, n_units * n, device='cuda', dtype=torch.float64).sin_() * 100 + \

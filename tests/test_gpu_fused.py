@@ -12,7 +12,8 @@ F999 = float(np.float32(0.999))
 FUSED1 = [(32, 32, 32), (16, 16, 16), (16, 32, 64), (64, 16, 32), (8, 8, 8), (4, 4, 4), (2, 2, 4), (8, 4, 4), (24, 40, 12),
           (48, 16, 16), (32, 16, 64), (64, 64, 8), (4, 64, 128), (12, 20, 28), (2, 2, 4096), (64, 2, 4),
           (16, 16, 24), (8, 8, 40)]
-FUSED8 = [(64, 64, 64), (32, 64, 64), (64, 32, 64), (64, 64, 32), (48, 48, 48), (16, 128, 64), (40, 48, 56)]
+FUSED8 = [(64, 64, 64), (32, 64, 64), (64, 32, 64), (64, 64, 32), (48, 48, 48), (16, 128, 64), (40, 48, 56),
+          (40, 40, 40), (36, 36, 36), (56, 56, 40), (48, 40, 64)]      # the last four: clusters of 2 / 4
 
 
 def check(ctx, oracle, boxes, dims, keep, mode=0):
@@ -161,7 +162,8 @@ def test_plan_roundtrip_segment_tables_all_fused_classes(fused_ctx, oracle, wc):
     rng = np.random.default_rng(90210)
     shapes = [(32, 32, 32)] * 150 + [(64, 64, 64)] * 20 + [(16, 32, 64)] * 12 + [(24, 40, 12)] * 6 + \
              [(48, 48, 48)] * 6 + [(32, 64, 64)] * 5 + [(8, 8, 8)] * 9 + [(2, 2, 4)] * 3 + [(16, 16, 16)] * 700 + \
-             [(8, 16, 8)] * 650 + [(8, 8, 8)] * 5000
+             [(8, 16, 8)] * 650 + [(8, 8, 8)] * 5000 + [(40, 40, 40)] * 9 + \
+             [(56, 56, 40)] * 5
     host, dts = [], []
     for i, d in enumerate(shapes):
         dt = np.float32 if (i % 4 == 1 and d[0] % 4 == 0) else np.float64

@@ -115,14 +115,14 @@ struct wc_ctx {
 struct DecCache {
     uint64_t h1 = 0, h2 = 0;      // 128-bit hash of (output space, pointers, dtypes) of the cached call
     bool     valid = false;
-    size_t   fl_n[8] = {};
+    size_t   fl_n[12] = {};
 };
 // Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
 // stream), then the single-CTA kernels (second stream when both kinds are present).
-enum { FL_N = 7 };
-static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_CUBE32, FUSED_CLS_R1,
-                                    FUSED_CLS_CUBE16, FUSED_CLS_R1S, FUSED_CLS_CUBE8};
-static inline bool fl_is_cluster(int k) { return k < 2; }
+enum { FL_N = 9 };
+static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_R4, FUSED_CLS_R2, FUSED_CLS_CUBE32,
+                                    FUSED_CLS_R1, FUSED_CLS_CUBE16, FUSED_CLS_R1S, FUSED_CLS_CUBE8};
+static inline bool fl_is_cluster(int k) { return k < 4; }
 
 struct wc_plan {
     wc_ctx* ctx      = nullptr;
@@ -552,11 +552,11 @@ int wc_plan_destroy(wc_plan* p) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &p->d_units, &p->d_states, &p->d_in, &p->d_out, &p->d_coef, &p->d_xtiles,
-                       &p->d_ctiles, &p->d_tile_i, &p->d_gkey, &p->d_offsets, &p->d_dense, &p->d_fl[0],
-                       &p->d_fl[1], &p->d_fl[2], &p->d_fl[3], &p->d_fl[4], &p->d_fl[5], &p->d_fl[6], &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
+                       &p->d_ctiles, &p->d_tile_i, &p->d_gkey, &p->d_offsets, &p->d_dense, &p->d_dec_units, &p->d_inv_units, &p->d_inv_tiles, &p->d_ptiles,
                        &p->d_psum, &p->d_err, &p->d_rmse_units, &p->d_rmse_sum, &p->d_rmse,
                        &p->d_stage_out };
     for (DevBuf* b : bufs) b->release();
+    for (int k = 0; k < FL_N; ++k) p->d_fl[k].release();
     p->d_running.release();
     p->d_counter.release();
     p->d_rmse_tiles.release();

@@ -117,6 +117,8 @@ int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
     if (nx == 8 && ny == 8 && nz == 8) return FUSED_CLS_CUBE8;
     if (fused_geom(nx, ny, nz, dtype, 1, 4096, g)) return FUSED_CLS_R1S;
     if (fused_geom(nx, ny, nz, dtype, 1, 32768, g)) return FUSED_CLS_R1;
+    if (fused_geom(nx, ny, nz, dtype, 2, 32768, g)) return FUSED_CLS_R2;
+    if (fused_geom(nx, ny, nz, dtype, 4, 32768, g)) return FUSED_CLS_R4;
     if (fused_geom(nx, ny, nz, dtype, 8, 32768, g)) return FUSED_CLS_R8;
     return FUSED_CLS_NONE;
 }
@@ -927,6 +929,12 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
     case FUSED_CLS_R8:
         return launch_fc<8, 32768, 512, false>(KID_FUSED_C8, mode, units, states, unit_list, n_list,
                                                one_minus_keep, global_key, sm_count, st, ls, nullptr);
+    case FUSED_CLS_R4:
+        return launch_fc<4, 32768, 512, false>(KID_FUSED_C4, mode, units, states, unit_list, n_list,
+                                               one_minus_keep, global_key, sm_count, st, ls, nullptr);
+    case FUSED_CLS_R2:
+        return launch_fc<2, 32768, 512, false>(KID_FUSED_C2, mode, units, states, unit_list, n_list,
+                                               one_minus_keep, global_key, sm_count, st, ls, nullptr);
     case FUSED_CLS_CUBE32:
         return launch_fc<1, 32768, 1024, true>(KID_FUSED_C1S, mode, units, states, unit_list, n_list,
                                                one_minus_keep, global_key, sm_count, st, ls, work_counter);
@@ -1066,7 +1074,7 @@ __device__ __forceinline__ uint32_t fd_tile_scan(const int2 (&pr)[FD_PPT], int n
 template <int NT>
 __global__ void __launch_bounds__(NT, 2)
 k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
-            const int* __restrict__ unit_list, int n_list, int* __restrict__ err) {
+            const int* __restrict__ unit_list, int n_list, int* __restrict__ err, int slabs) {
     __shared__ uint32_t s_wt[2][32];
     __shared__ int s_kend, s_flast;
     const int tid = threadIdx.x;
@@ -1075,9 +1083,9 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
         FGeom g;
-        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, 8, 32768, g);
+        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g);
         const uint32_t seglen = (uint32_t)g.seglen, total = (uint32_t)du.total;
-        const int nseg = g.nseg * 8;                       // == total / seglen
+        const int nseg = g.nseg * slabs;                   // == total / seglen
         int2* const tab = reinterpret_cast<int2*>(du.coef);
         const int K = du.npairs_dev ? *du.npairs_dev : du.npairs;
         const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
@@ -1496,7 +1504,7 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
         // segment tables first: one CTA per unit, a few units per SM
         const int nb = n < 2 * sm_count ? n : 2 * sm_count;
         ls->begin(KID_SEG_INDEX, st);
-        k_seg_index<512><<<nb, 512, 0, st>>>(dec, inv, list, n, err);
+        k_seg_index<512><<<nb, 512, 0, st>>>(dec, inv, list, n, err, S);
         ls->end(st);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -1526,18 +1534,24 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
     FGeom g;
     if (fused_geom(nx, ny, nz, WC_F64, 1, 4096, g)) return FUSED_CLS_R1S;
     if (fused_geom(nx, ny, nz, WC_F64, 1, 32768, g)) return FUSED_CLS_R1;   // WC_F64: keeps the X*es % 16 rule valid for both
+    if (fused_geom(nx, ny, nz, WC_F64, 2, 32768, g)) return FUSED_CLS_R2;
+    if (fused_geom(nx, ny, nz, WC_F64, 4, 32768, g)) return FUSED_CLS_R4;
     if (fused_geom(nx, ny, nz, WC_F64, 8, 32768, g)) return FUSED_CLS_R8;
     return FUSED_CLS_NONE;
 }
 // int2 entries of the segment table a slab-decoded unit needs (0 for the other classes)
 size_t fused_decode_table_entries(int fused_cls, int nx) {
     if (fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64) return (size_t)(2 * nx * 8 + 1);
+    if (fused_cls == FUSED_CLS_R4) return (size_t)(2 * nx * 4 + 1);
+    if (fused_cls == FUSED_CLS_R2) return (size_t)(2 * nx * 2 + 1);
     if (fused_cls == FUSED_CLS_R1 || fused_cls == FUSED_CLS_CUBE32 || fused_cls == FUSED_CLS_R1S ||
         fused_cls == FUSED_CLS_CUBE16 || fused_cls == FUSED_CLS_CUBE8)
         return (size_t)(2 * nx + 1);
     return 0;
 }
-bool fused_decode_needs_table(int fused_cls) { return fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64; }
+bool fused_decode_needs_table(int fused_cls) {
+    return fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64 || fused_cls == FUSED_CLS_R4 || fused_cls == FUSED_CLS_R2;
+}
 
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
@@ -1548,6 +1562,10 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
         return launch_fd<1, 32768, 512, false>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     case FUSED_CLS_R8:
         return launch_fd<8, 32768, 512, false>(KID_FUSED_D8, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
+    case FUSED_CLS_R4:
+        return launch_fd<4, 32768, 512, false>(KID_FUSED_D4, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
+    case FUSED_CLS_R2:
+        return launch_fd<2, 32768, 512, false>(KID_FUSED_D2, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, build_tables);
     case FUSED_CLS_CUBE32:
         return launch_fd<1, 32768, 1024, true>(KID_FUSED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);
     case FUSED_CLS_CUBE64:

@@ -18,7 +18,9 @@ enum { FUSED_FULL = 0, FUSED_KEYS_ONLY = 1, FUSED_GIVEN_THRESH = 2 };
 // Units of at most 4096 cells (16^3 and smaller) go to variants with a 16 KB coefficient array, so that
 // four CTAs share an SM and overlap each other's barriers and load latencies; 8^3 boxes get one-warp CTAs,
 // 32 per SM.
-enum { FUSED_CLS_NONE = 0, FUSED_CLS_R1 = 1, FUSED_CLS_R1S = 2, FUSED_CLS_R8 = 8, FUSED_CLS_CUBE32 = 101,
+enum { FUSED_CLS_NONE = 0, FUSED_CLS_R1 = 1, FUSED_CLS_R1S = 2, FUSED_CLS_R8 = 8, FUSED_CLS_R4 = 24,
+       FUSED_CLS_R2 = 22,      // clusters of 4 / 2: boxes whose half-height is not a multiple of 8 (40^3 ...)
+       FUSED_CLS_CUBE32 = 101,
        FUSED_CLS_CUBE64 = 108, FUSED_CLS_CUBE16 = 116, FUSED_CLS_CUBE8 = 117 };
 int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
