@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WCGPU_VERSION 100 /* 0.1.0 */
+#define WCGPU_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define WC_API __attribute__((visibility("default")))
@@ -97,9 +97,13 @@ typedef struct {
     int32_t  shape[3]; /* nx, ny, nz            -> serialized bytes [0,12)  */
     int32_t  ncoef;    /* nx*ny*nz              -> bytes [12,16)            */
     int32_t  npairs;   /* K                     -> bytes [16,20)            */
-    int32_t  reserved;
+    int32_t  flags;    /* WC_PACKED_* bits, set by the compress calls; not serialized */
     wc_pair* pairs;    /* K pairs               -> bytes [20,20+8K)         */
 } wc_packed;
+/* CompressedWavelet::need32 (src/compressor.cpp:224-229, src/box-structs.h:69): some kept value has
+ * |v| > INT16_MAX, i.e. the TODO'd 16-bit value stream (TODO.txt:1-2) could not hold this unit.  Computed on
+ * the device, never part of the byte stream (the reference does not serialize it either). */
+#define WC_PACKED_NEED32 1
 
 /* ---- library / context ---------------------------------------------------------------------- */
 WC_API int         wc_version(void);
@@ -122,8 +126,15 @@ typedef enum {
                           does not fit) */
     WC_OPT_PROFILE = 1, /* 1 = bracket every kernel launch with CUDA events on the ctx stream and
                            accumulate per-kernel device time (read with wc_kernel_stats) */
-    WC_OPT_OVERLAP = 2  /* 1 (default) = run the single-CTA and the cluster compress kernels of a step
+    WC_OPT_OVERLAP = 2, /* 1 (default) = run the single-CTA and the cluster compress kernels of a step
                            concurrently (second stream, dynamic unit hand-out); 0 = back to back */
+    WC_OPT_SEG_INDEX = 3, /* segment index of table-less packed streams: 0 (default) = chunk-parallel
+                             single-pass scan (k_seg_index2), 1 = one CTA per unit (k_seg_index) */
+    WC_OPT_COPY_ONLY = 4, /* measurement probe: 1 = wc_plan_compress_to_host issues its H2D / D2H copies with
+                             the same chunking but launches no compress kernel (the pair counts of the previous
+                             real call size the D2H) -> the host-link ceiling of that call */
+    WC_OPT_INGEST_STATS = 5 /* 1 = the compress kernels also record each unit's min / max of the narrowed
+                               input values (src/preprocess.cpp:82-88), read with wc_plan_unit_stats */
 } wc_option;
 WC_API int wc_set_option(wc_ctx* ctx, int option, int64_t value);
 
@@ -199,7 +210,9 @@ WC_API int wc_serialize_header(const wc_packed* unit, uint8_t header_out[20]);
 WC_API int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_space,
                    wc_plan** plan);
 WC_API int wc_plan_destroy(wc_plan* plan);
-/* New input addresses for the same dims/dtypes (e.g. the next timestep on the same grids). */
+/* New input addresses for the same dims/dtypes (e.g. the next timestep on the same grids).  Device inputs:
+ * stream-ordered, no host synchronisation (pinned pointer table + a patch kernel), so a timestep series
+ * alternates wc_plan_set_inputs / wc_plan_compress without draining the GPU. */
 WC_API int wc_plan_set_inputs(wc_plan* plan, const wc_box_desc* units);
 /* Enqueue compression of every unit.  Returns after enqueueing when the inputs are on the device;
  * host inputs are first staged with (asynchronous, if pinned) H2D copies on the same stream. */
@@ -213,6 +226,19 @@ WC_API int wc_plan_fetch(wc_plan* plan, wc_packed* out, int out_space);
  * c-2 (three streams; PCIe is full duplex).  Per-unit thresholds only.  Falls back to
  * wc_plan_compress + wc_plan_fetch when the plan's inputs are device-resident. */
 WC_API int wc_plan_compress_to_host(wc_plan* plan, double keep, wc_packed* out);
+/* The same, handing finished chunks to the host while later chunks are still on the GPU, so that the host's
+ * LZMA stage (src/compressor.cpp:256-291) overlaps the GPU work: on_chunk(user, first_unit, n_units, units) is
+ * called on the calling thread, in unit order, as soon as the pairs of units [first_unit, first_unit + n_units)
+ * have landed in pinned host memory; `units` = &out[first_unit], filled in.  The pointers stay valid until the
+ * next compress call on this plan.  on_chunk may be NULL (= wc_plan_compress_to_host). */
+typedef void (*wc_chunk_fn)(void* user, int first_unit, int n_units, const wc_packed* units);
+WC_API int wc_plan_compress_to_host_chunked(wc_plan* plan, double keep, wc_packed* out, wc_chunk_fn on_chunk,
+                                            void* user);
+/* Per-unit by-products of the last compress (HOST arrays of n_units entries, any of them may be NULL):
+ * mins / maxs = min / max of the unit's narrowed float32 input values, NaNs skipped, +inf / -inf when no value
+ * is comparable (what src/preprocess.cpp:82-88 folds into the per-component range of the adjusted loss;
+ * needs WC_OPT_INGEST_STATS = 1 at compress time, else WC_ERR_STATE); need32 = CompressedWavelet::need32. */
+WC_API int wc_plan_unit_stats(wc_plan* plan, float* mins, float* maxs, int32_t* need32);
 /* Total kept pairs of the last compress (waits for it). */
 WC_API int wc_plan_total_pairs(wc_plan* plan, int64_t* total);
 /* Enqueue decompression of the plan's current packed result into out[u] (device memory, or host
@@ -227,6 +253,23 @@ WC_API int wc_plan_rmse(wc_plan* plan, const wc_box_desc* recon, double* rmse);
  *   wc_plan_pack_with_key   : threshold from *key_dev (device) + mask + pack                     */
 WC_API int wc_plan_transform(wc_plan* plan, uint64_t** key_dev);
 WC_API int wc_plan_pack_with_key(wc_plan* plan, double keep, const uint64_t* key_dev);
+
+/* ---- decode plans: decompress() (src/decompressor.cpp:238-255) for a batch, stream-in ------------------ *
+ * A decode plan fixes the output boxes (dims, dtype, addresses) of a batch and owns the device tables; each
+ * wc_dplan_decode then takes the batch's packed units as ONE dense pair stream — the units' pairs back to back
+ * in unit order, i.e. the concatenation of bytes [20, 20+8K) of the reference's files, which is also what
+ * wc_plan_fetch(WC_HOST) / wc_plan_compress_to_host return — plus the K of every unit.  Nothing but the two
+ * arrays is needed from the host: per-unit offsets, the segment index of the large units and the inverse
+ * transform all run on the device.  Host streams are pipelined (H2D of chunk c | kernels of c-1 | D2H of the
+ * boxes of c-2). */
+typedef struct wc_dplan wc_dplan;
+WC_API int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_space, wc_dplan** dplan);
+WC_API int wc_dplan_destroy(wc_dplan* dplan);
+/* Enqueue: pairs (sum of npairs entries) and npairs (n_units entries) both in `in_space`.  Asynchronous for
+ * device streams; results are complete after wc_dplan_finish. */
+WC_API int wc_dplan_decode(wc_dplan* dplan, const wc_pair* pairs, const int32_t* npairs, int in_space);
+/* Wait for the last decode; WC_ERR_CORRUPT if a unit's stream was inconsistent (negative run, K > ncoef). */
+WC_API int wc_dplan_finish(wc_dplan* dplan);
 
 #ifdef __cplusplus
 }

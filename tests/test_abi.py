@@ -25,7 +25,7 @@ def test_header_symbols_all_exported_and_bound(wc):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/wcgpu.h but not exported by libwcgpu.so"
     assert set(syms) == set(wc.capi.SIGNATURES), set(syms) ^ set(wc.capi.SIGNATURES)
-    assert lib.wc_version() == 100
+    assert lib.wc_version() == 200
     assert wc.capi.strerror(0) == "ok" and "fallback" in wc.capi.strerror(3)
 
 

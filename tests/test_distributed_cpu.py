@@ -32,7 +32,8 @@ def np_plan_key(flats):
             continue
         g = (k & 0xFFFFFFFF00000000) | ((0x7FFFFFFF - i) << 1) | (k & 1)
         best = max(best, g)
-    if flats and flats[0].size and np.isnan(flats[0][0]):
+    first = next((fl for fl in flats if fl.size), None)     # first NON-EMPTY unit (k_global_key)
+    if first is not None and np.isnan(first[0]):
         best |= 1 << 63
     return best
 
@@ -55,7 +56,7 @@ def _worker(rank, world, port, tmp):
     orc = Oracle()
     rng = np.random.default_rng(1234)           # same data on every rank
     dims = (8, 8, 8)
-    for case in range(4):
+    for case in range(6):
         boxes = [rng.standard_normal(512).astype(np.float32) * (1 + (i % 3)) for i in range(11)]
         if case == 1:
             boxes[7][:] = 0; boxes[7][3] = -50.0       # the winner is negative and sits on rank 1
@@ -66,9 +67,17 @@ def _worker(rank, world, port, tmp):
         flats = [orc.haar_forward(b, dims) for b in boxes]
         sizes = [b.size for b in boxes]
         lo, hi = wc.amr_synth.shard_units(sizes, world, rank)
+        if case >= 4:
+            # rank 0 owns only EMPTY units: the first coefficient of the concatenation is rank 1's; in case 5
+            # it is NaN, and a stale NaN flag on rank 0 must not leak into the batch key
+            empty = np.zeros(0, np.float32)
+            lo, hi = (0, 5) if rank == 0 else (5, 16)
+            flats = [empty] * 5 + flats
+            if case == 5:
+                flats[5] = flats[5].copy(); flats[5][0] = np.nan
         local_key = np_plan_key(flats[lo:hi])
         t = torch.tensor([local_key - (1 << 64) if local_key >> 63 else local_key], dtype=torch.int64)
-        g = wc.distributed.allreduce_key(t, lo)
+        g = wc.distributed.allreduce_key(t, lo, has_nonempty=any(f.size for f in flats[lo:hi]))
         gk = int(g.item()) & 0xFFFFFFFFFFFFFFFF
         keep = float(np.float32(0.99))
         want = orc.select_threshold_global(flats, keep)
@@ -81,7 +90,7 @@ def _worker(rank, world, port, tmp):
         stats = torch.tensor([float(i) for i in range(lo, hi)], dtype=torch.float64)
         allv = wc.distributed.gather_unit_stats(stats)
         if rank == 0:
-            assert allv.tolist() == [float(i) for i in range(len(boxes))]
+            assert allv.tolist() == [float(i) for i in range(len(flats))]
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 

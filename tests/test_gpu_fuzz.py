@@ -66,5 +66,6 @@ def test_fuzz_batch_and_plan_roundtrip(wc, ctx, oracle, seed):
             assert same_bits(outs[i].cpu().numpy().reshape(ob.shape), ob), (seed, i, d, k2)
             oe = oracle.rmse(b.astype(np.float32), ob, d)
             n = d[0] * d[1] * d[2]
-            assert abs(rm[i] - oe) <= max(1e-12, n * 2.0 ** -54) * max(abs(oe), 1e-300), (seed, i, d, rm[i], oe)
+            tol = 1e-12 if n <= (1 << 18) else max(1e-12, n * 2.0 ** -54)   # strict at every BASELINE size (test_gpu_parity.rmse_tol)
+            assert abs(rm[i] - oe) <= tol * max(abs(oe), 1e-300), (seed, i, d, rm[i], oe)
     plan.close()

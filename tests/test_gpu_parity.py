@@ -15,19 +15,23 @@ RMSE_RTOL = 1e-12
 F999 = float(np.float32(0.999))
 
 
+def rmse_tol(n):
+    """RMSE parity bound (relative).  STRICT 1e-12 (north_star) for every unit of at most 2^18 cells —
+    which covers every BASELINE box (64^3 = 2^18, 32^3, 16x32x64, 8x4x2).  The reference sums N squared
+    float differences SEQUENTIALLY in float64 (src/calc-loss.cpp:30-35), itself only accurate to
+    (N-1)*2^-53 relative on the sum; the GPU uses a fixed pairwise tree (~log2(N)*2^-53).  The two may
+    differ by N*2^-53 on the sum = N*2^-54 on the root.  N*2^-54 reaches 1e-12 at N = 18 014 cells already,
+    so it is NOT used as a bound for the BASELINE sizes: only beyond 2^18 cells (96^3 was observed at
+    1.1e-12) does the scaled bound N*2^-54 apply (1.46e-11 * N/2^18)."""
+    return RMSE_RTOL if n <= (1 << 18) else max(RMSE_RTOL, n * 2.0 ** -54)
+
+
 def rmse_close(a, b, n=0):
-    """RMSE parity: 1e-12 relative (north_star) for every BASELINE size.  The reference sums N squared
-    float differences SEQUENTIALLY in float64 (src/calc-loss.cpp:30-35), which is itself only accurate
-    to (N-1)*2^-53 relative (small terms are absorbed once the partial sum is large); the GPU uses a
-    fixed pairwise tree (error ~log2(N)*2^-53).  The two can therefore differ by up to N*2^-53 on the
-    sum = N*2^-54 on the root; the bound below only exceeds 1e-12 for boxes beyond ~2^20 cells... it
-    is written out so the tolerance is explicit rather than tuned."""
     if np.isnan(a) or np.isnan(b):
         return np.isnan(a) and np.isnan(b)
     if np.isinf(a) or np.isinf(b):
         return a == b
-    tol = max(RMSE_RTOL, n * 2.0 ** -54)
-    return abs(a - b) <= tol * max(abs(b), np.finfo(np.float64).tiny)
+    return abs(a - b) <= rmse_tol(n) * max(abs(b), np.finfo(np.float64).tiny)
 
 
 def test_library_is_the_cuda_one(wc, ctx):

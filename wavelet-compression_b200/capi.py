@@ -11,19 +11,22 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libwcgpu.so")
+# WCGPU_LIB: developer hook for instrumented builds of the SAME library (make PHASE_PROFILE=1 OUT=...); it names
+# another libwcgpu, never another implementation
+LIB_PATH = os.environ.get("WCGPU_LIB") or os.path.join(PKG_DIR, "libwcgpu.so")
 
 WC_OK = 0
 WC_F32, WC_F64 = 0, 1
 WC_HOST, WC_DEVICE = 0, 1
 WC_THRESH_PER_UNIT, WC_THRESH_GLOBAL = 0, 1
-WC_OPT_PATH, WC_OPT_PROFILE, WC_OPT_OVERLAP = 0, 1, 2
+WC_OPT_PATH, WC_OPT_PROFILE, WC_OPT_OVERLAP, WC_OPT_SEG_INDEX, WC_OPT_COPY_ONLY, WC_OPT_INGEST_STATS = 0, 1, 2, 3, 4, 5
+WC_PACKED_NEED32 = 1
 WC_CTR_KERNEL_LAUNCHES, WC_CTR_H2D_BYTES, WC_CTR_D2H_BYTES = 0, 1, 2
 
 # numpy mirrors of the POD structs (layout checked against sizeof in tests/test_abi.py)
 BOX_DESC = np.dtype([("data", "<u8"), ("dtype", "<i4"), ("nx", "<i4"), ("ny", "<i4"), ("nz", "<i4")],
                     align=True)
-PACKED = np.dtype([("shape", "<i4", (3,)), ("ncoef", "<i4"), ("npairs", "<i4"), ("reserved", "<i4"),
+PACKED = np.dtype([("shape", "<i4", (3,)), ("ncoef", "<i4"), ("npairs", "<i4"), ("flags", "<i4"),
                    ("pairs", "<u8")], align=True)
 PAIR = np.dtype([("run", "<i4"), ("val", "<f4")])
 assert BOX_DESC.itemsize == 24 and PACKED.itemsize == 32 and PAIR.itemsize == 8
@@ -63,12 +66,21 @@ SIGNATURES = {
     "wc_plan_compress": (_i, [_vp, _d, _i]),
     "wc_plan_fetch": (_i, [_vp, _vp, _i]),
     "wc_plan_compress_to_host": (_i, [_vp, _d, _vp]),
+    "wc_plan_compress_to_host_chunked": (_i, [_vp, _d, _vp, _vp, _vp]),
+    "wc_plan_unit_stats": (_i, [_vp, _vp, _vp, _vp]),
+    "wc_dplan_create": (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
+    "wc_dplan_destroy": (_i, [_vp]),
+    "wc_dplan_decode": (_i, [_vp, _vp, _vp, _i]),
+    "wc_dplan_finish": (_i, [_vp]),
     "wc_plan_total_pairs": (_i, [_vp, C.POINTER(C.c_int64)]),
     "wc_plan_decompress": (_i, [_vp, _vp, _i]),
     "wc_plan_rmse": (_i, [_vp, _vp, _vp]),
     "wc_plan_transform": (_i, [_vp, C.POINTER(_vp)]),
     "wc_plan_pack_with_key": (_i, [_vp, _d, _vp]),
 }
+
+
+CHUNK_FN = C.CFUNCTYPE(None, _vp, _i, _i, _vp)   # wc_chunk_fn
 
 
 class WcError(RuntimeError):

@@ -120,6 +120,9 @@ class Context:
         check(self.lib.wc_get_counter(self.h, which, C.byref(v)), "wc_get_counter", self.h)
         return v.value
 
+    def set_option(self, option: int, value: int):
+        check(self.lib.wc_set_option(self.h, option, int(value)), "wc_set_option", self.h)
+
     def set_profile(self, on: bool):
         check(self.lib.wc_set_option(self.h, capi.WC_OPT_PROFILE, 1 if on else 0), "wc_set_option", self.h)
 
@@ -237,6 +240,9 @@ class Context:
     def plan(self, descs: np.ndarray, in_space: int) -> "Plan":
         return Plan(self, descs, in_space)
 
+    def decode_plan(self, out_descs: np.ndarray, out_space: int) -> "DecodePlan":
+        return DecodePlan(self, out_descs, out_space)
+
     def plan_host(self, boxes, dims=None) -> "Plan":
         descs, hold = _host_descs(boxes, dims)
         p = Plan(self, descs, WC_HOST)
@@ -308,6 +314,26 @@ class Plan:
               "wc_plan_compress_to_host", self.ctx.h)
         return self._packed[:self.n]
 
+    def compress_to_host_chunked(self, keep: float, on_chunk) -> np.ndarray:
+        """wc_plan_compress_to_host_chunked: on_chunk(first_unit, n_units, records) is called on this thread as soon
+        as the pairs of those units are in pinned host memory, while later chunks are still on the GPU."""
+        recs = self._packed
+
+        def tramp(_user, first, n, _units):
+            on_chunk(first, n, recs[first:first + n])
+        cb = capi.CHUNK_FN(tramp)
+        check(self.lib.wc_plan_compress_to_host_chunked(self.h, float(keep), self._packed.ctypes.data, cb, None),
+              "wc_plan_compress_to_host_chunked", self.ctx.h)
+        return self._packed[:self.n]
+
+    def unit_stats(self, minmax: bool = True):
+        """(mins, maxs, need32) of the last compress; mins / maxs need WC_OPT_INGEST_STATS at compress time."""
+        n = max(self.n, 1)
+        lo, hi, n32 = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        check(self.lib.wc_plan_unit_stats(self.h, lo.ctypes.data if minmax else None, hi.ctypes.data if minmax else None,
+                                          n32.ctypes.data), "wc_plan_unit_stats", self.ctx.h)
+        return lo[:self.n], hi[:self.n], n32[:self.n]
+
     def fetch_host(self) -> list[PackedUnit]:
         rec = self.fetch_records(WC_HOST)
         return [Context._packed_to_host(rec[i]) for i in range(self.n)]
@@ -322,3 +348,35 @@ class Plan:
         check(self.lib.wc_plan_rmse(self.h, recon_descs.ctypes.data, out.ctypes.data),
               "wc_plan_rmse", self.ctx.h)
         return out[:self.n]
+
+
+class DecodePlan:
+    """wc_dplan: fixed output boxes; every decode() takes the batch as one dense pair stream + per-unit counts."""
+
+    def __init__(self, ctx: Context, out_descs: np.ndarray, out_space: int):
+        assert out_descs.dtype == BOX_DESC
+        self.ctx, self.lib = ctx, ctx.lib
+        self.n = len(out_descs)
+        self.descs = out_descs.copy()
+        h = C.c_void_p()
+        check(self.lib.wc_dplan_create(ctx.h, self.descs.ctypes.data, self.n, out_space, C.byref(h)),
+              "wc_dplan_create", ctx.h)
+        self.h = h
+
+    def decode(self, pairs_addr: int, npairs_addr: int, in_space: int):
+        check(self.lib.wc_dplan_decode(self.h, C.c_void_p(pairs_addr), C.c_void_p(npairs_addr), in_space),
+              "wc_dplan_decode", self.ctx.h)
+
+    def finish(self):
+        check(self.lib.wc_dplan_finish(self.h), "wc_dplan_finish", self.ctx.h)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.lib.wc_dplan_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -98,11 +98,15 @@ struct wc_ctx {
     uint64_t     h2d = 0, d2h = 0;
     int          opt_path = 0;
     int          opt_overlap = 1;
+    int          opt_seg_index = 0;   // 0 = chunk-parallel k_seg_index2, 1 = one CTA per unit (k_seg_index)
+    int          opt_copy_only = 0;   // probe: wc_plan_compress_to_host moves the bytes but skips the kernels
+    int          opt_ingest_stats = 0; // compress also records per-unit min / max of the narrowed inputs
     int          sm_count = 0;
     wc_plan*     batch_plan = nullptr; // owner of the memory handed out by wc_compress_batch
     // workspace of the blocking decompress / rmse / primitive calls (grow-only)
     DevBuf ws_pairs, ws_coef, ws_boxes, ws_tbl0, ws_tbl1, ws_tbl2, ws_tiles0, ws_tiles1, ws_sum,
         ws_misc, ws_a, ws_b;
+    DevBuf ws_chunk, ws_status;   // chunk-parallel segment index: chunk_start and look-back status words
     PinBuf ws_pin;
     // second stream for running the single-CTA and cluster kernels of one step concurrently
     cudaStream_t s_aux = nullptr;
@@ -153,8 +157,14 @@ struct wc_plan {
     long long rmse_tiles = -1;   // tiles resident in d_rmse_tiles (-1: not built yet)
     DevBuf d_dec_list;           // fused work lists of the last wc_plan_decompress (re-used on a cache hit)
     DecCache* dec_cache = nullptr;
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> ev, ev_d2h;
     DevBuf d_running;
+    // wc_plan_set_inputs: ring of pinned pointer tables (host) + one device table, patched by k_patch_inputs
+    enum { IN_RING = 4 };
+    PinBuf      h_inptr[IN_RING];
+    cudaEvent_t ev_inptr[IN_RING] = {};
+    DevBuf      d_inptr;
+    unsigned    inptr_next = 0;
 };
 
 #define CTX_CUDA(ctx, call)                                                                        \
@@ -254,7 +264,9 @@ int wc_create_on_stream(wc_ctx** ctx, int device_id, void* cuda_stream) {
 }
 
 int wc_plan_destroy(wc_plan* plan);
+int wc_minmax_batch(wc_ctx* ctx, const wc_box_desc* boxes, int n_units, int space, float* mins, float* maxs);
 int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out);
+int wc_plan_compress_to_host_chunked(wc_plan* p, double keep, wc_packed* out, wc_chunk_fn on_chunk, void* user);
 
 int wc_destroy(wc_ctx* ctx) {
     if (!ctx) return WC_OK;
@@ -265,6 +277,8 @@ int wc_destroy(wc_ctx* ctx) {
                        &ctx->ws_tbl2, &ctx->ws_tiles0, &ctx->ws_tiles1, &ctx->ws_sum, &ctx->ws_misc,
                        &ctx->ws_a, &ctx->ws_b };
     for (DevBuf* b : bufs) b->release();
+    ctx->ws_chunk.release();
+    ctx->ws_status.release();
     ctx->ws_pin.release();
     ctx->ls.destroy();
     ctx->d_counter.release();
@@ -295,6 +309,16 @@ int wc_set_option(wc_ctx* ctx, int option, int64_t value) {
         return WC_OK;
     case WC_OPT_OVERLAP:
         ctx->opt_overlap = value != 0;
+        return WC_OK;
+    case WC_OPT_SEG_INDEX:
+        if (value < 0 || value > 1) return WC_ERR_INVALID_ARG;
+        ctx->opt_seg_index = (int)value;
+        return WC_OK;
+    case WC_OPT_COPY_ONLY:
+        ctx->opt_copy_only = value != 0;
+        return WC_OK;
+    case WC_OPT_INGEST_STATS:
+        ctx->opt_ingest_stats = value != 0;
         return WC_OK;
     case WC_OPT_PROFILE:
         cudaSetDevice(ctx->device);
@@ -328,7 +352,8 @@ int wc_kernel_stats(wc_ctx* ctx, int index, const char** name, double* total_ms,
     return WC_OK;
 }
 
-// Undeclared debug hook (not part of include/wcgpu.h): per-phase SM cycles of the fused compress
+#ifdef WC_PHASE_PROFILE
+// Debug hook of PHASE_PROFILE builds only (not part of include/wcgpu.h, absent from the product build): per-phase SM cycles of the fused compress
 // kernel summed over CTAs since the last reset: A, B, C1, scan, C2, units.
 __attribute__((visibility("default"))) int wc_debug_phase_cycles(wc_ctx* ctx, unsigned long long* out6, int reset) {
     if (!ctx || !out6) return WC_ERR_INVALID_ARG;
@@ -337,6 +362,7 @@ __attribute__((visibility("default"))) int wc_debug_phase_cycles(wc_ctx* ctx, un
     CTX_CUDA(ctx, debug_phase_cycles(out6, reset != 0));
     return WC_OK;
 }
+#endif
 
 int wc_reset_counters(wc_ctx* ctx) {
     if (!ctx) return WC_ERR_INVALID_ARG;
@@ -561,11 +587,17 @@ int wc_plan_destroy(wc_plan* p) {
     p->d_counter.release();
     p->d_rmse_tiles.release();
     p->d_dec_list.release();
+    p->d_inptr.release();
+    for (int i = 0; i < wc_plan::IN_RING; ++i) {
+        p->h_inptr[i].release();
+        if (p->ev_inptr[i]) cudaEventDestroy(p->ev_inptr[i]);
+    }
     delete p->dec_cache;
     if (p->s_aux) cudaStreamDestroy(p->s_aux);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->ev_d2h) cudaEventDestroy(e);
     if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
     if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
     p->h_states.release();
@@ -596,11 +628,24 @@ int wc_plan_set_inputs(wc_plan* p, const wc_box_desc* units) {
         p->units[i].data = units[i].data;
         if (p->in_space == WC_DEVICE) p->h_units[i].in = units[i].data;
     }
-    if (p->in_space == WC_DEVICE) {
-        CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        int rc = plan_upload_units(p);
-        if (rc != WC_OK) return rc;
-        CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (p->in_space == WC_DEVICE && p->n_units > 0) {
+        // Stream-ordered and without a host synchronisation: the new addresses go through a ring of pinned
+        // tables (one H2D of 8 bytes per unit) and a kernel patches UnitDev::in, so a timestep series can call
+        // this between two wc_plan_compress without draining the GPU.  A ring slot is reused only after the
+        // copy that read it has completed (event).
+        const int slot = (int)(p->inptr_next++ % wc_plan::IN_RING);
+        const size_t bytes = sizeof(void*) * (size_t)p->n_units;
+        CTX_CUDA(ctx, p->h_inptr[slot].reserve(bytes));
+        CTX_CUDA(ctx, p->d_inptr.reserve(bytes));
+        if (!p->ev_inptr[slot]) CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_inptr[slot], cudaEventDisableTiming));
+        else CTX_CUDA(ctx, cudaEventSynchronize(p->ev_inptr[slot]));
+        const void** hp = p->h_inptr[slot].as<const void*>();
+        for (int i = 0; i < p->n_units; ++i) hp[i] = units[i].data;
+        CTX_CUDA(ctx, cudaMemcpyAsync(p->d_inptr.p, hp, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CTX_CUDA(ctx, cudaEventRecord(p->ev_inptr[slot], ctx->stream));
+        ctx->h2d += bytes;
+        CTX_CUDA(ctx, launch_patch_inputs(p->d_units.as<UnitDev>(), p->d_inptr.as<const void*>(), p->n_units,
+                                          ctx->stream, &ctx->ls));
     }
     return WC_OK;
 }
@@ -649,7 +694,8 @@ static int plan_forward(wc_plan* p, bool global_mode) {
                     int rc = plan_counter(p, ctx->stream, &counter);
                     if (rc != WC_OK) return rc;
                 }
-                CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], FUSED_KEYS_ONLY, p->d_units.as<UnitDev>(),
+                CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], FUSED_KEYS_ONLY | (ctx->opt_ingest_stats ? FUSED_MINMAX : 0),
+                                                    p->d_units.as<UnitDev>(),
                                                     p->d_states.as<UnitState>(), p->d_fl[k].as<int>(),
                                                     (int)p->fl[k].size(), 0.0, nullptr, ctx->sm_count,
                                                     ctx->stream, &ctx->ls, counter));
@@ -675,7 +721,7 @@ static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
                                           ti + nt, ti + 2 * nt, ti + 3 * nt, ctx->stream,
                                           &ctx->ls));
     }
-    int mode = global_key_dev ? FUSED_GIVEN_THRESH : FUSED_FULL;
+    int mode = global_key_dev ? FUSED_GIVEN_THRESH : (FUSED_FULL | (ctx->opt_ingest_stats ? FUSED_MINMAX : 0));
     // The cluster kernel cannot use every SM (clusters of 8 must fit inside a GPC: 15 clusters = 120 of 148
     // SMs on B200).  When a step has both classes, the single-CTA kernel runs concurrently on a second
     // stream with dynamic unit hand-out and back-fills the idle SMs.  (Serialised while per-kernel event
@@ -726,7 +772,7 @@ int wc_plan_compress(wc_plan* p, double keep, int thresh_mode) {
     if (rc != WC_OK) return rc;
     const u64* gk = nullptr;
     if (global_mode) {
-        CTX_CUDA(ctx, launch_global_key(p->d_states.as<UnitState>(), p->n_units, p->d_gkey.as<u64>(),
+        CTX_CUDA(ctx, launch_global_key(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(), p->n_units, p->d_gkey.as<u64>(),
                                         ctx->stream, &ctx->ls));
         gk = p->d_gkey.as<u64>();
     }
@@ -741,7 +787,7 @@ int wc_plan_transform(wc_plan* p, uint64_t** key_dev) {
     if (rc != WC_OK) return rc;
     rc = plan_forward(p, true);
     if (rc != WC_OK) return rc;
-    CTX_CUDA(ctx, launch_global_key(p->d_states.as<UnitState>(), p->n_units, p->d_gkey.as<u64>(),
+    CTX_CUDA(ctx, launch_global_key(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(), p->n_units, p->d_gkey.as<u64>(),
                                     ctx->stream, &ctx->ls));
     *key_dev       = reinterpret_cast<uint64_t*>(p->d_gkey.p);
     p->transformed = true;
@@ -801,7 +847,7 @@ int wc_plan_fetch(wc_plan* p, wc_packed* out, int out_space) {
         out[i].shape[0] = u.nx; out[i].shape[1] = u.ny; out[i].shape[2] = u.nz;
         out[i].ncoef    = u.n;
         out[i].npairs   = hs[i].npairs;
-        out[i].reserved = 0;
+        out[i].flags    = (hs[i].flags & UNIT_FLAG_NEED32) ? WC_PACKED_NEED32 : 0;
         out[i].pairs    = u.out;
         total += (size_t)hs[i].npairs;
     }
@@ -831,12 +877,18 @@ int wc_plan_fetch(wc_plan* p, wc_packed* out, int out_space) {
 // D2H on a third stream (PCIe is full duplex), so the call costs about max(H2D, D2H) instead of their
 // sum.  Same result as wc_plan_compress + wc_plan_fetch(WC_HOST).
 int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
+    return wc_plan_compress_to_host_chunked(p, keep, out, nullptr, nullptr);
+}
+
+int wc_plan_compress_to_host_chunked(wc_plan* p, double keep, wc_packed* out, wc_chunk_fn on_chunk, void* user) {
     if (!p || (p->n_units > 0 && !out)) return WC_ERR_INVALID_ARG;
     wc_ctx* ctx = p->ctx;
     if (p->in_space != WC_HOST || !p->generic.empty() || p->n_units == 0) {
         int rc = wc_plan_compress(p, keep, WC_THRESH_PER_UNIT);
         if (rc != WC_OK) return rc;
-        return wc_plan_fetch(p, out, WC_HOST);
+        rc = wc_plan_fetch(p, out, WC_HOST);
+        if (rc == WC_OK && on_chunk && p->n_units > 0) on_chunk(user, 0, p->n_units, out);
+        return rc;
     }
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
     const int NCH = 16;
@@ -849,8 +901,12 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
         CTX_CUDA(ctx, p->h_misc.reserve(sizeof(long long) * (NCH + 1)));
         CTX_CUDA(ctx, p->d_offsets.reserve(sizeof(long long) * (p->n_units + NCH + 1)));
     }
-    // worst case: every coefficient kept
+    // worst case: every coefficient kept.  The pinned destination is sized for the worst case up front
+    // as well: the chunk callback hands out pointers into it while later chunks are still in flight, so it
+    // must never move.
     CTX_CUDA(ctx, p->d_dense.reserve(sizeof(wc_pair) * std::max<size_t>((size_t)p->total_n, 1)));
+    if (on_chunk) CTX_CUDA(ctx, p->h_dense.reserve(sizeof(wc_pair) * std::max<size_t>((size_t)p->total_n, 1)));
+    const bool copy_only = ctx->opt_copy_only != 0;      // probe: same copies, no kernels (previous counts stand)
     volatile double one = 1.0;
     const double omk = one - keep;
     // chunk boundaries by input bytes
@@ -866,11 +922,43 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
     }
     long long* h_run = p->h_misc.as<long long>();
     CTX_CUDA(ctx, cudaMemsetAsync(p->d_running.p, 0, 8, ctx->stream));
-    CTX_CUDA(ctx, cudaMemsetAsync(p->d_states.p, 0, sizeof(UnitState) * p->n_units, ctx->stream));
+    if (!copy_only) CTX_CUDA(ctx, cudaMemsetAsync(p->d_states.p, 0, sizeof(UnitState) * p->n_units, ctx->stream));
     CTX_CUDA(ctx, cudaEventRecord(p->ev[3 * NCH], ctx->stream));
     CTX_CUDA(ctx, cudaStreamWaitEvent(p->s_h2d, p->ev[3 * NCH], 0));
     size_t fi[FL_N] = {};
     long long done_total = 0;
+    UnitState* const hs_all = p->h_states.as<UnitState>();
+    std::vector<long long> chunk_off(NCH + 1, 0);     // running pair total in front of each chunk
+    std::vector<cudaEvent_t>& ev_done = p->ev_d2h;    // D2H of a chunk's pairs has landed (callback mode)
+    if (on_chunk && ev_done.empty()) {
+        ev_done.resize(NCH);
+        for (cudaEvent_t& e : ev_done) CTX_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    int delivered = 0;                                // chunks already handed to the callback
+    auto fill_out = [&](int c) {
+        size_t off = (size_t)chunk_off[c];
+        for (int i = cut[c]; i < cut[c + 1]; ++i) {
+            const UnitDev& u = p->h_units[i];
+            out[i].shape[0] = u.nx; out[i].shape[1] = u.ny; out[i].shape[2] = u.nz;
+            out[i].ncoef    = u.n;
+            out[i].npairs   = hs_all[i].npairs;
+            out[i].flags    = (hs_all[i].flags & UNIT_FLAG_NEED32) ? WC_PACKED_NEED32 : 0;
+            out[i].pairs    = p->h_dense.as<wc_pair>() + off;
+            off += (size_t)hs_all[i].npairs;
+        }
+    };
+    // hands every chunk whose D2H has completed to the callback, in order; `block`: wait for all up to `upto`
+    auto deliver = [&](int upto, bool block) -> int {
+        while (on_chunk && delivered < upto) {
+            if (block) CTX_CUDA(ctx, cudaEventSynchronize(ev_done[delivered]));
+            else if (cudaEventQuery(ev_done[delivered]) != cudaSuccess) { cudaGetLastError(); break; }
+            fill_out(delivered);
+            if (cut[delivered + 1] > cut[delivered])
+                on_chunk(user, cut[delivered], cut[delivered + 1] - cut[delivered], out + cut[delivered]);
+            ++delivered;
+        }
+        return WC_OK;
+    };
     auto finish_chunk = [&](int c, long long& prev_total) -> int {
         // host learns the running total of chunk c, then enqueues its D2H
         CTX_CUDA(ctx, cudaEventSynchronize(p->ev[NCH + c]));
@@ -891,8 +979,11 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
                                           sizeof(wc_pair) * (size_t)(tot - prev_total), cudaMemcpyDeviceToHost, p->s_d2h));
             ctx->d2h += sizeof(wc_pair) * (size_t)(tot - prev_total);
         }
+        chunk_off[c]     = prev_total;
+        chunk_off[c + 1] = tot;
+        if (on_chunk) CTX_CUDA(ctx, cudaEventRecord(ev_done[c], p->s_d2h));
         prev_total = tot;
-        return WC_OK;
+        return deliver(c, false);
     };
     for (int c = 0; c < NCH; ++c) {
         const int u0 = cut[c], u1 = cut[c + 1];
@@ -910,13 +1001,14 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
         for (int k = 0; k < FL_N; ++k) {
             size_t j = fi[k];
             while (j < p->fl[k].size() && p->fl[k][j] < u1) ++j;
-            if (j > fi[k]) {
+            if (j > fi[k] && !copy_only) {
                 int* counter = nullptr;
                 if (!fl_is_cluster(k)) {
                     int rc = plan_counter(p, ctx->stream, &counter);
                     if (rc != WC_OK) return rc;
                 }
-                CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], FUSED_FULL, p->d_units.as<UnitDev>(),
+                CTX_CUDA(ctx, launch_fused_compress(FL_CLASS[k], FUSED_FULL | (ctx->opt_ingest_stats ? FUSED_MINMAX : 0),
+                                                    p->d_units.as<UnitDev>(),
                                                     p->d_states.as<UnitState>(), p->d_fl[k].as<int>() + fi[k],
                                                     (int)(j - fi[k]), omk, nullptr, ctx->sm_count, ctx->stream,
                                                     &ctx->ls, counter));
@@ -929,8 +1021,13 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
                                               p->d_running.as<long long>()));
         }
         CTX_CUDA(ctx, cudaMemcpyAsync(&h_run[c], p->d_running.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (u1 > u0) {   // the chunk's unit records travel with its running total (callback mode needs them early)
+            CTX_CUDA(ctx, cudaMemcpyAsync(hs_all + u0, p->d_states.as<UnitState>() + u0, sizeof(UnitState) * (size_t)(u1 - u0),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h += sizeof(UnitState) * (size_t)(u1 - u0);
+        }
         CTX_CUDA(ctx, cudaEventRecord(p->ev[NCH + c], ctx->stream));
-        if (u1 > u0)
+        if (u1 > u0 && !copy_only)
             CTX_CUDA(ctx, launch_gather_dense(p->d_units.as<UnitDev>() + u0, p->d_states.as<UnitState>() + u0, u1 - u0,
                                               p->d_offsets.as<long long>() + u0 + c, p->d_dense.as<wc_pair>(), false,
                                               ctx->stream, &ctx->ls));
@@ -946,20 +1043,13 @@ int wc_plan_compress_to_host(wc_plan* p, double keep, wc_packed* out) {
         if (rc != WC_OK) return rc;
     }
     p->compressed = true;
-    int rc = plan_read_states(p);
-    if (rc != WC_OK) return rc;
-    CTX_CUDA(ctx, cudaStreamSynchronize(p->s_d2h));
-    const UnitState* hs = p->h_states.as<UnitState>();
-    size_t off = 0;
-    for (int i = 0; i < p->n_units; ++i) {
-        const UnitDev& u = p->h_units[i];
-        out[i].shape[0] = u.nx; out[i].shape[1] = u.ny; out[i].shape[2] = u.nz;
-        out[i].ncoef    = u.n;
-        out[i].npairs   = hs[i].npairs;
-        out[i].reserved = 0;
-        out[i].pairs    = p->h_dense.as<wc_pair>() + off;
-        off += (size_t)hs[i].npairs;
+    if (on_chunk) {
+        int rc = deliver(NCH, true);
+        if (rc != WC_OK) return rc;
     }
+    CTX_CUDA(ctx, cudaStreamSynchronize(p->s_d2h));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int c = delivered; c < NCH; ++c) fill_out(c);
     return WC_OK;
 }
 
@@ -1000,6 +1090,31 @@ static int relaunch_decompress(wc_ctx* ctx, const DecCache* cache, DevBuf& d_dec
                                               counter, false));
         o += cache->fl_n[k];
     }
+    return WC_OK;
+}
+
+// Segment tables of one slab-decoded class list with the chunk-parallel index kernel.  K is known on the
+// host here (blocking API): chunk_start is built on the host and uploaded.
+static int build_tables_chunked(wc_ctx* ctx, int fused_cls, const std::vector<DecUnitDev>& du, const std::vector<int>& list,
+                                const DecUnitDev* d_dec, const InvUnitDev* d_inv, const int* d_list, int* d_err) {
+    const int n = (int)list.size();
+    std::vector<int> cs(n + 1);
+    long long items = 0;
+    for (int j = 0; j < n; ++j) {
+        cs[j] = (int)items;
+        const int k = du[list[j]].npairs;
+        items += k > 0 ? (k + SEG_INDEX_CHUNK - 1) / SEG_INDEX_CHUNK : 1;
+    }
+    cs[n] = (int)items;
+    CTX_CUDA(ctx, ctx->ws_chunk.reserve(sizeof(int) * (size_t)(n + 1)));
+    CTX_CUDA(ctx, ctx->ws_status.reserve(sizeof(u64) * (size_t)std::max<long long>(items, 1)));
+    CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_chunk.p, cs.data(), sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemsetAsync(ctx->ws_status.p, 0, sizeof(u64) * (size_t)std::max<long long>(items, 1), ctx->stream));
+    int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
+    CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+    CTX_CUDA(ctx, launch_seg_index2(fused_cls, d_dec, d_inv, d_list, n, ctx->ws_chunk.as<int>(), items,
+                                    ctx->ws_status.as<u64>(), counter, d_err, ctx->sm_count, ctx->stream, &ctx->ls));
     return WC_OK;
 }
 
@@ -1092,12 +1207,25 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             if (fl[k].empty()) continue;
             CTX_CUDA(ctx, cudaMemcpyAsync(dl + o, fl[k].data(), sizeof(int) * fl[k].size(),
                                           cudaMemcpyHostToDevice, ctx->stream));
+            bool v1_tables = build_tables[k];
+            if (build_tables[k] && ctx->opt_seg_index == 0) {
+                // every unit of a slab-decoded class arrives either with or without its table; the chunk-parallel
+                // index only handles lists where all do without (mixed lists keep the one-CTA-per-unit kernel)
+                bool all_without = true;
+                for (int i : fl[k]) all_without = all_without && !slab_tab[i];
+                if (all_without) {
+                    int rc = build_tables_chunked(ctx, FL_CLASS[k], du, fl[k], d_dec_units.as<DecUnitDev>(),
+                                                  d_inv_units.as<InvUnitDev>(), dl + o, d_err.as<int>());
+                    if (rc != WC_OK) return rc;
+                    v1_tables = false;
+                }
+            }
             int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
             CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
             CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
                                                   d_inv_units.as<InvUnitDev>(), dl + o,
                                                   (int)fl[k].size(), d_err.as<int>(), ctx->sm_count,
-                                                  ctx->stream, &ctx->ls, counter, build_tables[k]));
+                                                  ctx->stream, &ctx->ls, counter, v1_tables));
             o += fl[k].size();
         }
     }
@@ -1181,6 +1309,9 @@ int wc_decompress_batch(wc_ctx* ctx, const wc_packed* in, int n_units, int in_sp
         if (rc != WC_OK) return rc;
         long long n = (long long)in[i].shape[0] * in[i].shape[1] * in[i].shape[2];
         if (in[i].npairs < 0 || in[i].ncoef < 0) return WC_ERR_CORRUPT;
+        // more pairs than coefficients cannot come from the encoder (every pair is one kept coefficient):
+        // reject it here, before its size drives an allocation or a copy (hostile / truncated headers)
+        if (in[i].npairs > in[i].ncoef) return WC_ERR_CORRUPT;
         // The reference decodes into coeff_shape[0] floats and then reads shape[0]*shape[1]*shape[2]
         // of them (src/decompressor.cpp:245-251); a mismatch is out-of-bounds there, an error here.
         if ((long long)in[i].ncoef != n) return WC_ERR_CORRUPT;
@@ -1231,6 +1362,416 @@ int wc_decompress_batch(wc_ctx* ctx, const wc_packed* in, int n_units, int in_sp
     CTX_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->ws_tbl2.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return h_err ? WC_ERR_CORRUPT : WC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode plans: the `-d` path (src/decompressor.cpp:238-255) for a whole batch of packed units that arrive
+// as ONE dense pair stream — the concatenation of the files' bytes [20, 20+8K), which is also what
+// wc_plan_fetch(WC_HOST) / wc_plan_compress_to_host deliver — plus the per-unit pair counts.
+// ---------------------------------------------------------------------------------------------
+struct wc_dplan {
+    wc_ctx* ctx       = nullptr;
+    int     n         = 0;
+    int     out_space = WC_DEVICE;
+    std::vector<wc_box_out> outs;
+    std::vector<size_t>     stage_off;
+    size_t    stage_bytes = 0;
+    long long total_n     = 0;
+    std::vector<int> fl[FL_N];            // unit ids per fused class (ascending)
+    bool      has_generic = false;        // some unit needs the generic kernels: decode falls back to run_decompress
+    size_t    fl_off[FL_N] = {};          // offset of each class list inside d_lists
+    size_t    cs_off[FL_N] = {};          // offset of each slab-decoded class's chunk_start inside d_chunk
+    size_t    st_off[FL_N] = {};          // offset of its status words inside d_status
+    long long st_items[FL_N] = {};        // bound of its index items (K = ncoef)
+    std::vector<long long> st_prefix[FL_N];   // per listed unit: items bound in front of it (sub-list launches)
+    int       n_tab_lists = 0;
+    size_t    tab_floats = 0, status_items = 0, chunk_ints = 0;
+    DevBuf d_dec, d_inv, d_lists, d_tab, d_chunk, d_status, d_err, d_stage_out, d_pairs, d_npairs, d_tabn, d_counter;
+    PinBuf h_err;
+    unsigned counter_next = 0;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev;
+    bool decoded = false;
+    // generic fallback workspace
+    DevBuf g_coef, g_dec, g_inv, g_tiles, g_ptiles, g_psum, g_list;
+    std::vector<int32_t> h_npairs;
+};
+
+int wc_dplan_destroy(wc_dplan* dp);
+
+int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_space, wc_dplan** out) {
+    if (!ctx || !out || n_units < 0 || (n_units > 0 && !outs) || (out_space != WC_HOST && out_space != WC_DEVICE))
+        return WC_ERR_INVALID_ARG;
+    *out = nullptr;
+    for (int i = 0; i < n_units; ++i) {
+        int rc = check_dims(outs[i].nx, outs[i].ny, outs[i].nz);
+        if (rc != WC_OK) return rc;
+        if (outs[i].dtype != WC_F32 && outs[i].dtype != WC_F64) return WC_ERR_INVALID_ARG;
+        if ((long long)outs[i].nx * outs[i].ny * outs[i].nz > 0 && !outs[i].data) return WC_ERR_INVALID_ARG;
+    }
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    wc_dplan* dp = new (std::nothrow) wc_dplan();
+    if (!dp) return WC_ERR_OOM;
+    dp->ctx = ctx; dp->n = n_units; dp->out_space = out_space;
+    dp->outs.assign(outs, outs + n_units);
+    dp->stage_off.resize(n_units);
+    for (int i = 0; i < n_units; ++i) {
+        const long long n = (long long)outs[i].nx * outs[i].ny * outs[i].nz;
+        dp->total_n += n;
+        dp->stage_off[i] = dp->stage_bytes;
+        dp->stage_bytes += align_up((size_t)n * dtype_size(outs[i].dtype), 256);
+    }
+    auto fail = [&](cudaError_t e, const char* what) {
+        ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        cudaGetLastError();
+        wc_dplan_destroy(dp);
+        return e == cudaErrorMemoryAllocation ? WC_ERR_OOM : WC_ERR_CUDA;
+    };
+    cudaError_t e;
+#define DP_RESERVE(buf, bytes) if ((e = (buf).reserve(bytes)) != cudaSuccess) return fail(e, "dplan alloc " #buf)
+    if (out_space == WC_HOST) DP_RESERVE(dp->d_stage_out, std::max<size_t>(dp->stage_bytes, 256));
+    std::vector<DecUnitDev> du(std::max(n_units, 1));
+    std::vector<InvUnitDev> iu(std::max(n_units, 1));
+    std::vector<size_t> tab_off(n_units, 0);
+    std::vector<int> cls_of(n_units, -1);
+    for (int i = 0; i < n_units; ++i) {
+        const wc_box_out& o = outs[i];
+        const long long n = (long long)o.nx * o.ny * o.nz;
+        void* dev_out = out_space == WC_HOST ? (void*)(dp->d_stage_out.as<char>() + dp->stage_off[i]) : o.data;
+        int cls = n > 0 ? fused_decode_class(o.nx, o.ny, o.nz, o.dtype, dev_out) : -1;
+        if (ctx->opt_path == 1 && cls > 0) cls = 0;
+        if (ctx->opt_path == 2 && cls == 0) { wc_dplan_destroy(dp); return WC_ERR_BAD_DIMS; }
+        cls_of[i] = cls;
+        std::memset(&du[i], 0, sizeof(DecUnitDev));
+        du[i].total = (int32_t)n;
+        iu[i].coef = nullptr; iu[i].out = dev_out;
+        iu[i].nx = o.nx; iu[i].ny = o.ny; iu[i].nz = o.nz; iu[i].dtype = o.dtype;
+        if (cls == 0) dp->has_generic = true;
+        for (int k = 0; k < FL_N; ++k)
+            if (cls == FL_CLASS[k]) {
+                dp->fl[k].push_back(i);
+                if (fused_decode_needs_table(cls)) {
+                    tab_off[i] = dp->tab_floats;
+                    dp->tab_floats += align_up(2 * fused_decode_table_entries(cls, o.nx), 4);
+                }
+            }
+    }
+    DP_RESERVE(dp->d_dec, sizeof(DecUnitDev) * std::max(n_units, 1));
+    DP_RESERVE(dp->d_inv, sizeof(InvUnitDev) * std::max(n_units, 1));
+    DP_RESERVE(dp->d_tab, sizeof(float) * std::max<size_t>(dp->tab_floats, 4));
+    DP_RESERVE(dp->d_err, 64);
+    DP_RESERVE(dp->d_npairs, sizeof(int32_t) * std::max(n_units, 1));
+    DP_RESERVE(dp->d_counter, 64 * sizeof(int));
+    if ((e = dp->h_err.reserve(64)) != cudaSuccess) return fail(e, "dplan pinned alloc");
+    size_t n_fused = 0;
+    std::vector<int> lists, tabn;
+    for (int k = 0; k < FL_N; ++k) {
+        dp->fl_off[k] = n_fused;
+        n_fused += dp->fl[k].size();
+        lists.insert(lists.end(), dp->fl[k].begin(), dp->fl[k].end());
+    }
+    // slab-decoded classes come first in FL_CLASS order, so their lists are a prefix of `lists`: exactly the
+    // layout k_dec_prepare walks (tab_list + tab_n)
+    for (int k = 0; k < FL_N; ++k) {
+        if (dp->fl[k].empty() || !fused_decode_needs_table(FL_CLASS[k])) continue;
+        tabn.push_back((int)dp->fl[k].size());
+        dp->cs_off[k] = dp->chunk_ints;
+        dp->chunk_ints += dp->fl[k].size() + 1;
+        dp->st_off[k] = dp->status_items;
+        dp->st_prefix[k].resize(dp->fl[k].size() + 1);
+        long long items = 0;
+        for (size_t j = 0; j < dp->fl[k].size(); ++j) {
+            dp->st_prefix[k][j] = items;
+            const long long n = du[dp->fl[k][j]].total;
+            items += std::max<long long>(1, (n + SEG_INDEX_CHUNK - 1) / SEG_INDEX_CHUNK);
+        }
+        dp->st_prefix[k][dp->fl[k].size()] = items;
+        dp->st_items[k] = items;
+        dp->status_items += (size_t)items;
+        ++dp->n_tab_lists;
+    }
+    for (int i = 0; i < n_units; ++i)
+        if (cls_of[i] > 0 && fused_decode_needs_table(cls_of[i])) {
+            du[i].coef = dp->d_tab.as<float>() + tab_off[i];
+            iu[i].coef = du[i].coef;
+        }
+    DP_RESERVE(dp->d_lists, sizeof(int) * std::max<size_t>(n_fused, 1));
+    DP_RESERVE(dp->d_tabn, sizeof(int) * std::max<size_t>(tabn.size(), 1));
+    DP_RESERVE(dp->d_chunk, sizeof(int) * std::max<size_t>(dp->chunk_ints, 1));
+    DP_RESERVE(dp->d_status, sizeof(u64) * std::max<size_t>(dp->status_items, 1));
+#undef DP_RESERVE
+    if (n_units) {
+        if ((e = cudaMemcpyAsync(dp->d_dec.p, du.data(), sizeof(DecUnitDev) * n_units, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
+        if ((e = cudaMemcpyAsync(dp->d_inv.p, iu.data(), sizeof(InvUnitDev) * n_units, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
+    }
+    if (n_fused)
+        if ((e = cudaMemcpyAsync(dp->d_lists.p, lists.data(), sizeof(int) * n_fused, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
+    if (!tabn.empty())
+        if ((e = cudaMemcpyAsync(dp->d_tabn.p, tabn.data(), sizeof(int) * tabn.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "dplan sync");
+    *out = dp;
+    return WC_OK;
+}
+
+int wc_dplan_destroy(wc_dplan* dp) {
+    if (!dp) return WC_OK;
+    wc_ctx* ctx = dp->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (dp->s_h2d) { cudaStreamSynchronize(dp->s_h2d); cudaStreamDestroy(dp->s_h2d); }
+    if (dp->s_d2h) { cudaStreamSynchronize(dp->s_d2h); cudaStreamDestroy(dp->s_d2h); }
+    for (cudaEvent_t e : dp->ev) cudaEventDestroy(e);
+    DevBuf* bufs[] = { &dp->d_dec, &dp->d_inv, &dp->d_lists, &dp->d_tab, &dp->d_chunk, &dp->d_status, &dp->d_err,
+                       &dp->d_stage_out, &dp->d_pairs, &dp->d_npairs, &dp->d_tabn, &dp->d_counter, &dp->g_coef,
+                       &dp->g_dec, &dp->g_inv, &dp->g_tiles, &dp->g_ptiles, &dp->g_psum, &dp->g_list };
+    for (DevBuf* b : bufs) b->release();
+    dp->h_err.release();
+    cudaGetLastError();
+    delete dp;
+    return WC_OK;
+}
+
+// kernels of the units [u0, u1) (all of them: 0, n) on the ctx stream; the dense stream and the counts are on
+// the device, k_dec_prepare has run
+static int dplan_launch_range(wc_dplan* dp, int u0, int u1, size_t fi[FL_N]) {
+    wc_ctx* ctx = dp->ctx;
+    int tl = 0;
+    for (int k = 0; k < FL_N; ++k) {
+        if (dp->fl[k].empty()) continue;
+        const bool tab = fused_decode_needs_table(FL_CLASS[k]);
+        size_t j = fi[k];
+        while (j < dp->fl[k].size() && dp->fl[k][j] < u1) ++j;
+        if (j > fi[k]) {
+            const int* list = dp->d_lists.as<int>() + dp->fl_off[k] + fi[k];
+            const int  nl   = (int)(j - fi[k]);
+            bool v1 = false;
+            if (tab) {
+                if (ctx->opt_seg_index == 0) {
+                    int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
+                    CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+                    CTX_CUDA(ctx, launch_seg_index2(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
+                                                    dp->d_chunk.as<int>() + dp->cs_off[k] + fi[k],
+                                                    dp->st_prefix[k][j] - dp->st_prefix[k][fi[k]],
+                                                    dp->d_status.as<u64>() + dp->st_off[k] + dp->st_prefix[k][fi[k]],
+                                                    counter, dp->d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls));
+                } else {
+                    v1 = true;
+                }
+            }
+            int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
+            CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+            CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
+                                                  dp->d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls, counter, v1));
+        }
+        fi[k] = j;
+        if (tab) ++tl;
+    }
+    (void)tl;
+    return WC_OK;
+}
+
+static int dplan_generic_fallback(wc_dplan* dp, const wc_pair* dense_dev, const int32_t* npairs_host) {
+    wc_ctx* ctx = dp->ctx;
+    std::vector<DecJob> jobs(dp->n);
+    size_t off = 0;
+    for (int i = 0; i < dp->n; ++i) {
+        const wc_box_out& o = dp->outs[i];
+        const long long n = (long long)o.nx * o.ny * o.nz;
+        if (npairs_host[i] < 0 || npairs_host[i] > n) return WC_ERR_CORRUPT;
+        jobs[i].pairs_dev = dense_dev + off;
+        jobs[i].npairs_dev = nullptr;
+        jobs[i].npairs = npairs_host[i];
+        jobs[i].nx = o.nx; jobs[i].ny = o.ny; jobs[i].nz = o.nz;
+        jobs[i].out_dev = dp->out_space == WC_HOST ? (void*)(dp->d_stage_out.as<char>() + dp->stage_off[i]) : o.data;
+        jobs[i].out_dtype = o.dtype;
+        off += (size_t)npairs_host[i];
+    }
+    return run_decompress(ctx, jobs, dp->g_coef, dp->g_dec, dp->g_inv, dp->g_tiles, dp->g_ptiles, dp->g_psum, dp->d_err, dp->g_list);
+}
+
+int wc_dplan_decode(wc_dplan* dp, const wc_pair* pairs, const int32_t* npairs, int in_space) {
+    if (!dp || (in_space != WC_HOST && in_space != WC_DEVICE) || (dp->n > 0 && !npairs)) return WC_ERR_INVALID_ARG;
+    wc_ctx* ctx = dp->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    dp->decoded = false;
+    const int n = dp->n;
+    if (n == 0) { dp->decoded = true; return WC_OK; }
+    const int NCH = 8;
+    if (!dp->s_h2d && (in_space == WC_HOST || dp->out_space == WC_HOST)) {
+        CTX_CUDA(ctx, cudaStreamCreateWithFlags(&dp->s_h2d, cudaStreamNonBlocking));
+        CTX_CUDA(ctx, cudaStreamCreateWithFlags(&dp->s_d2h, cudaStreamNonBlocking));
+        dp->ev.resize(2 * NCH + 2);
+        for (cudaEvent_t& e : dp->ev) CTX_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    CTX_CUDA(ctx, cudaMemsetAsync(dp->d_err.p, 0, 64, ctx->stream));
+    // host-side counts: needed to size the H2D of the stream (host input) and by the generic fallback
+    const int32_t* np_host = nullptr;
+    if (in_space == WC_HOST) np_host = npairs;
+    else if (dp->has_generic) {
+        dp->h_npairs.resize(n);
+        CTX_CUDA(ctx, cudaMemcpyAsync(dp->h_npairs.data(), npairs, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->d2h += sizeof(int32_t) * n;
+        np_host = dp->h_npairs.data();
+    }
+    std::vector<size_t> pair_off;
+    size_t total_pairs = 0;
+    if (np_host) {
+        pair_off.resize(n + 1);
+        for (int i = 0; i < n; ++i) {
+            pair_off[i] = total_pairs;
+            if (np_host[i] < 0 || (long long)np_host[i] > (long long)dp->outs[i].nx * dp->outs[i].ny * dp->outs[i].nz)
+                return WC_ERR_CORRUPT;
+            total_pairs += (size_t)np_host[i];
+        }
+        pair_off[n] = total_pairs;
+        if (total_pairs > 0 && !pairs) return WC_ERR_INVALID_ARG;
+    }
+    const wc_pair*  d_pairs  = pairs;
+    const int32_t*  d_npairs = npairs;
+    const bool pipelined = in_space == WC_HOST && !dp->has_generic;
+    if (in_space == WC_HOST) {
+        CTX_CUDA(ctx, dp->d_pairs.reserve(sizeof(wc_pair) * std::max<size_t>(total_pairs, 1)));
+        d_pairs  = dp->d_pairs.as<wc_pair>();
+        d_npairs = dp->d_npairs.as<int32_t>();
+        CTX_CUDA(ctx, cudaMemcpyAsync(dp->d_npairs.p, npairs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d += sizeof(int32_t) * n;
+        if (!pipelined && total_pairs) {
+            CTX_CUDA(ctx, cudaMemcpyAsync(dp->d_pairs.p, pairs, sizeof(wc_pair) * total_pairs, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d += sizeof(wc_pair) * total_pairs;
+        }
+    }
+    if (dp->has_generic) {
+        int rc = dplan_generic_fallback(dp, d_pairs, np_host);
+        if (rc != WC_OK) return rc;
+    } else {
+        if (dp->tab_floats) CTX_CUDA(ctx, cudaMemsetAsync(dp->d_tab.p, 0, sizeof(float) * dp->tab_floats, ctx->stream));
+        if (dp->status_items && ctx->opt_seg_index == 0)
+            CTX_CUDA(ctx, cudaMemsetAsync(dp->d_status.p, 0, sizeof(u64) * dp->status_items, ctx->stream));
+        CTX_CUDA(ctx, launch_dec_prepare(dp->d_dec.as<DecUnitDev>(), n, d_pairs, d_npairs, dp->d_lists.as<int>(),
+                                         dp->d_tabn.as<int>(), dp->n_tab_lists, dp->d_chunk.as<int>(), dp->d_err.as<int>(),
+                                         ctx->stream, &ctx->ls));
+    }
+    size_t fi[FL_N] = {};
+    if (!pipelined) {
+        if (!dp->has_generic) {
+            int rc = dplan_launch_range(dp, 0, n, fi);
+            if (rc != WC_OK) return rc;
+        }
+        if (dp->out_space == WC_HOST) {
+            CopyList cl;
+            for (int i = 0; i < n; ++i)
+                cl.add(dp->outs[i].data, dp->d_stage_out.as<char>() + dp->stage_off[i],
+                       (size_t)dp->outs[i].nx * dp->outs[i].ny * dp->outs[i].nz * dtype_size(dp->outs[i].dtype));
+            for (const CopyRange& r : cl.r) {
+                CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                ctx->d2h += r.bytes;
+            }
+        }
+    } else {
+        // host stream in (and usually host boxes out): chunk c's pairs go H2D on one stream while chunk c-1 is
+        // decoded on the ctx stream and chunk c-2's boxes go D2H on a third (PCIe is full duplex)
+        std::vector<int> cut(NCH + 1, n);
+        cut[0] = 0;
+        {
+            // chunk boundaries by output bytes (the larger direction)
+            size_t acc = 0, per = dp->stage_bytes / NCH + 1;
+            int c = 1;
+            for (int i = 0; i < n && c < NCH; ++i) {
+                acc += align_up((size_t)dp->outs[i].nx * dp->outs[i].ny * dp->outs[i].nz * dtype_size(dp->outs[i].dtype), 256);
+                if (acc >= per * c) cut[c++] = i + 1;
+            }
+        }
+        CTX_CUDA(ctx, cudaEventRecord(dp->ev[2 * NCH], ctx->stream));          // prepare done (needs only the counts)
+        CTX_CUDA(ctx, cudaStreamWaitEvent(dp->s_h2d, dp->ev[2 * NCH], 0));
+        for (int c = 0; c < NCH; ++c) {
+            const int u0 = cut[c], u1 = cut[c + 1];
+            const size_t p0 = pair_off[u0], p1 = pair_off[u1];
+            if (p1 > p0) {
+                CTX_CUDA(ctx, cudaMemcpyAsync(dp->d_pairs.as<wc_pair>() + p0, pairs + p0, sizeof(wc_pair) * (p1 - p0),
+                                              cudaMemcpyHostToDevice, dp->s_h2d));
+                ctx->h2d += sizeof(wc_pair) * (p1 - p0);
+            }
+            CTX_CUDA(ctx, cudaEventRecord(dp->ev[c], dp->s_h2d));
+            CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, dp->ev[c], 0));
+            int rc = dplan_launch_range(dp, u0, u1, fi);
+            if (rc != WC_OK) return rc;
+            CTX_CUDA(ctx, cudaEventRecord(dp->ev[NCH + c], ctx->stream));
+            if (dp->out_space == WC_HOST && u1 > u0) {
+                CTX_CUDA(ctx, cudaStreamWaitEvent(dp->s_d2h, dp->ev[NCH + c], 0));
+                CopyList cl;
+                for (int i = u0; i < u1; ++i)
+                    cl.add(dp->outs[i].data, dp->d_stage_out.as<char>() + dp->stage_off[i],
+                           (size_t)dp->outs[i].nx * dp->outs[i].ny * dp->outs[i].nz * dtype_size(dp->outs[i].dtype));
+                for (const CopyRange& r : cl.r) {
+                    CTX_CUDA(ctx, cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyDeviceToHost, dp->s_d2h));
+                    ctx->d2h += r.bytes;
+                }
+            }
+        }
+        if (dp->out_space == WC_HOST) {
+            CTX_CUDA(ctx, cudaEventRecord(dp->ev[2 * NCH + 1], dp->s_d2h));
+            CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, dp->ev[2 * NCH + 1], 0));   // ctx stream = everything done
+        }
+    }
+    CTX_CUDA(ctx, cudaMemcpyAsync(dp->h_err.p, dp->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    dp->decoded = true;
+    return WC_OK;
+}
+
+int wc_dplan_finish(wc_dplan* dp) {
+    if (!dp) return WC_ERR_INVALID_ARG;
+    if (!dp->decoded) return WC_ERR_STATE;
+    wc_ctx* ctx = dp->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dp->n == 0) return WC_OK;
+    return *dp->h_err.as<int>() ? WC_ERR_CORRUPT : WC_OK;
+}
+
+// per-unit results of the last compress that the reference derives on the host: min / max of the narrowed
+// values (src/preprocess.cpp:82-88; needs WC_OPT_INGEST_STATS = 1 before the compress) and need32
+// (src/compressor.cpp:224-229).  Any of the three arrays may be null.
+int wc_plan_unit_stats(wc_plan* p, float* mins, float* maxs, int32_t* need32) {
+    if (!p) return WC_ERR_INVALID_ARG;
+    if (!p->compressed) return WC_ERR_STATE;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((mins || maxs) && !ctx->opt_ingest_stats) return WC_ERR_STATE;
+    int rc = plan_read_states(p);
+    if (rc != WC_OK) return rc;
+    const UnitState* hs = p->h_states.as<UnitState>();
+    auto decode = [](uint32_t code) -> float {        // inverse of float_order_code
+        const uint32_t b = (code & 0x80000000u) ? (code & 0x7fffffffu) : ~code;
+        float f;
+        std::memcpy(&f, &b, 4);
+        return f;
+    };
+    const float inf = __builtin_inff();
+    for (int i = 0; i < p->n_units; ++i) {
+        uint32_t cmin, cmax;
+        std::memcpy(&cmin, &hs[i].vmin, 4);
+        std::memcpy(&cmax, &hs[i].vmax, 4);
+        if (mins) mins[i] = cmin ? decode(~cmin) : inf;
+        if (maxs) maxs[i] = cmax ? decode(cmax) : -inf;
+        if (need32) need32[i] = (hs[i].flags & UNIT_FLAG_NEED32) ? 1 : 0;
+    }
+    if ((mins || maxs) && !p->generic.empty()) {
+        // units on the generic kernels: their own min / max pass (shapes no fused class takes)
+        std::vector<wc_box_desc> b(p->generic.size());
+        std::vector<float> lo(b.size()), hi(b.size());
+        for (size_t j = 0; j < b.size(); ++j) {
+            const UnitDev& u = p->h_units[p->generic[j]];
+            b[j] = { u.in, u.dtype, u.nx, u.ny, u.nz };
+        }
+        rc = wc_minmax_batch(ctx, b.data(), (int)b.size(), WC_DEVICE, lo.data(), hi.data());
+        if (rc != WC_OK) return rc;
+        for (size_t j = 0; j < b.size(); ++j) {
+            if (mins) mins[p->generic[j]] = lo[j];
+            if (maxs) maxs[p->generic[j]] = hi[j];
+        }
+    }
+    return WC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

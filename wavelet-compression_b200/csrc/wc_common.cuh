@@ -34,9 +34,19 @@ struct UnitState {
     u64     key;      // arg-max key, see make_key
     float   thresh_f; // largest float <= thresh (see threshold_float)
     int32_t npairs;   // K
-    int32_t flags;    // bit0: coefficient f=0 is NaN
+    int32_t flags;    // bit0: coefficient f=0 is NaN; bit1: need32 (a kept |value| > INT16_MAX,
+                      // src/compressor.cpp:224-229)
+    float   vmin;     // with WC_OPT_INGEST_STATS: min / max of the narrowed input values, NaNs skipped
+    float   vmax;     //   (src/preprocess.cpp:82-88); +inf / -inf when nothing is comparable
     int32_t reserved;
 };
+static_assert(sizeof(UnitState) == 32, "UnitState layout");
+constexpr int UNIT_FLAG_NAN0 = 1, UNIT_FLAG_NEED32 = 2;
+
+// need32 of src/compressor.cpp:224-229: some KEPT coefficient has |value| > INT16_MAX.  The coefficient of
+// largest magnitude M is kept whenever anything above INT16_MAX is (|c| > tf is monotone in |c|), so the
+// flag is "M > 32767 and M passes the mask".
+__device__ __forceinline__ bool unit_need32(float M, float tf) { return M > 32767.0f && M > tf; }
 
 // ---- arg-max key -----------------------------------------------------------------------------------
 // std::max_element with comp(a,b) = |a| < |b| (src/compressor.cpp:212-215) returns the FIRST element

@@ -228,8 +228,8 @@ __device__ __forceinline__ void st_pair_pred(bool p, int2* addr, int run, float 
 // exchange), 4 = C2 (emit), 5 = units processed.
 // Only in builds with -DWC_PHASE_PROFILE (make PHASE_PROFILE=1): the read-modify-writes cost thread 0 some
 // 600 cycles per unit.
-__device__ unsigned long long g_phase_cycles[1024][6];
 #ifdef WC_PHASE_PROFILE
+__device__ unsigned long long g_phase_cycles[1024][6];
 #define WC_PHASE_CLOCK(t) long long t = clock64()
 #else
 #define WC_PHASE_CLOCK(t) do { } while (0)
@@ -312,9 +312,18 @@ __device__ __forceinline__ void finish_pair(float2 v[8], float* cdst, int o1, in
 // With literal geometry the trip count is a constant: the loop is fully unrolled and the loads of slot
 // i+1 are issued between the narrowing and the transform of slot i (software pipeline without extra
 // registers, and without a branch ptxas could hoist the math over).
-template <int NT, int ES, class G>
+// MM: also track min / max of the narrowed INPUT values (ingest statistics, src/preprocess.cpp:82-88; fminf /
+// fmaxf skip NaNs exactly like the reference's `value < min` / `value > max` updates).
+__device__ __forceinline__ void minmax_pair(const float2 v[8], float& mn, float& mx) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        mn = fminf(fminf(mn, v[o].x), v[o].y);
+        mx = fmaxf(fmaxf(mx, v[o].x), v[o].y);
+    }
+}
+template <int NT, int ES, bool MM, class G>
 __device__ __forceinline__ void phase_a(const G& g, const char* in0, float* C, uint32_t rank, u64 pol,
-                                        float& bp, float& bn, bool& nan0) {
+                                        float& bp, float& bn, bool& nan0, float& vmn, float& vmx) {
     const int tid = threadIdx.x;
     const size_t row_bytes = (size_t)g.X * g.es, plane_bytes = row_bytes * g.Y;
     const int o1 = g.hx * g.slab, o2 = g.nb * g.Z, o3 = g.hz;
@@ -341,6 +350,7 @@ __device__ __forceinline__ void phase_a(const G& g, const char* in0, float* C, u
         for (int it = 0; it < NIT; ++it) {
             float2 v[8];
             narrow_pair(raw, v);
+            if (MM) minmax_pair(v, vmn, vmx);
             float* const cd = cdst;
             if (it + 1 < NIT) {
                 decode(tid + (it + 1) * NT, p0, cdst);
@@ -356,6 +366,7 @@ __device__ __forceinline__ void phase_a(const G& g, const char* in0, float* C, u
             float2 v[8];
             load_pair<ES>(raw, p0, plane_bytes, row_bytes, pol);
             narrow_pair(raw, v);
+            if (MM) minmax_pair(v, vmn, vmx);
             finish_pair(v, cdst, o1, o2, o3, bp, bn);
             if (q == 0 && rank == 0) nan0 = isnan(v[0].x);
         }
@@ -431,7 +442,12 @@ struct FPrefetch {
 
 // One unit, start to finish.  G is FGeom (geometry in registers, any admissible shape) or an SGeom<...>
 // (the common cubes: every stride, trip count and divisor is a literal).
-template <int R, int CAP, int NT, class G>
+// order-preserving float -> uint32 (larger float = larger code; every code is > 0, so a zeroed word = unset)
+__device__ __forceinline__ uint32_t float_order_code(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+template <int R, int CAP, int NT, bool MM, class G>
 __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int uid, const FShared& S,
                                         const FPrefetch& pf, FLookahead& la, const uint32_t rank, uint32_t& xph1,
                                         uint32_t& xph2, uint32_t& xph3, UnitState* __restrict__ states,
@@ -444,6 +460,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     const int b0 = rank * g.nb;
     const size_t row_bytes = (size_t)g.X * g.es;
     float bp = 0.f, bn = 0.f;                 // running max of +c and of -c
+    float vmn = __int_as_float(0x7f800000), vmx = __int_as_float(0xff800000);   // MM: min / max of the inputs
     bool  nan0 = false;
     WC_PHASE_CLOCK(t0);
     if (tid == 0) la.stage1();
@@ -451,8 +468,8 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     // ---------------- phase A: load, narrow, transform two blocks per thread, store into C -------
     {
         const char* in0 = static_cast<const char*>(u.in) + (size_t)(2 * b0) * row_bytes;
-        if (g.es == 8) phase_a<NT, 8>(g, in0, C, rank, pol, bp, bn, nan0);
-        else           phase_a<NT, 4>(g, in0, C, rank, pol, bp, bn, nan0);
+        if (g.es == 8) phase_a<NT, 8, MM>(g, in0, C, rank, pol, bp, bn, nan0, vmn, vmx);
+        else           phase_a<NT, 4, MM>(g, in0, C, rank, pol, bp, bn, nan0, vmn, vmx);
     }
 
     // L2 prefetch of this CTA's slab of its NEXT unit, issued after this unit's own loads: the HBM reads
@@ -478,6 +495,14 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
         bn = fmaxf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
     }
     const bool any_nan0 = __any_sync(0xffffffffu, nan0);
+    if (MM) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmn = fminf(vmn, __shfl_xor_sync(0xffffffffu, vmn, o));
+            vmx = fmaxf(vmx, __shfl_xor_sync(0xffffffffu, vmx, o));
+        }
+        if (lane == 0) S.s_red[32 + warp] = ((u64)__float_as_uint(vmn) << 32) | (u64)__float_as_uint(vmx);
+    }
     if (lane == 0) {
         // bn >= 0, so its sign bit is free: it carries "the coefficient at f = 0 is NaN"
         S.s_red[warp] = ((u64)__float_as_uint(bp) << 32) |
@@ -485,6 +510,23 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     }
     __syncthreads();
     if (tid == 0) la.stage2();
+    if (MM && warp == 0) {
+        // one atomic pair per CTA and unit: vmax holds the order code of the max, vmin the INVERTED code of
+        // the min (both reduce with atomicMax over a zeroed word; wc_plan_unit_stats decodes them)
+        const u64 x = lane < NW ? S.s_red[32 + lane] : ((u64)0x7f800000u << 32) | 0xff800000u;
+        float a = __uint_as_float((uint32_t)(x >> 32)), b = __uint_as_float((uint32_t)x);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+            b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        }
+        if (lane == 0) {
+            if (a <= b) {     // at least one comparable value
+                atomicMax(reinterpret_cast<unsigned int*>(&states[uid].vmin), ~float_order_code(a));
+                atomicMax(reinterpret_cast<unsigned int*>(&states[uid].vmax), float_order_code(b));
+            }
+        }
+    }
     float Mp = 0.f, Mn = 0.f;
     bool  first_nan = false;
     {
@@ -699,6 +741,8 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
             }
             if (tid == 0 && rank == 0) {
                 states[uid].npairs = total;
+                states[uid].flags  = (first_nan ? UNIT_FLAG_NAN0 : 0) |
+                                     ((total > 0 && unit_need32(M, tf)) ? UNIT_FLAG_NEED32 : 0);
                 if (u.coef) reinterpret_cast<int2*>(u.coef)[NG] = make_int2(total, -1);   // sentinel
             }
             if (tid == 0) *S.s_next = 0;
@@ -772,7 +816,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
 }
 
 // STATIC: every unit of the list is the cube this variant is specialised for (32^3 for R = 1, 64^3 for R = 8).
-template <int R, int CAP, int NT, bool STATIC>
+template <int R, int CAP, int NT, bool STATIC, bool MM>
 __global__ void __launch_bounds__(NT, (CAP <= 512 ? 32 : CAP <= 4096 ? 4 : 1))
 k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                  const int* __restrict__ unit_list, int n_list, double one_minus_keep,
@@ -854,7 +898,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
                 pf.pitch = pb;
             }
         }
-#define WC_FC_UNIT(GEOM) fc_unit<R, CAP, NT>(GEOM, u, uid, S, pf, la, rank, xph1, xph2, xph3, states, \
+#define WC_FC_UNIT(GEOM) fc_unit<R, CAP, NT, MM>(GEOM, u, uid, S, pf, la, rank, xph1, xph2, xph3, states, \
                                              one_minus_keep, global_key, mode, pol, lt)
         if constexpr (STATIC) {
             constexpr int CUBE = R == 1 ? (CAP <= 512 ? 8 : CAP <= 4096 ? 16 : 32) : 64;
@@ -871,12 +915,12 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
 }
 
 // ---- launchers --------------------------------------------------------------------------------------
-template <int R, int CAP, int NT, bool STATIC>
-static cudaError_t launch_fc(int kid, int mode, const UnitDev* units, UnitState* states, const int* list,
+template <int R, int CAP, int NT, bool STATIC, bool MM>
+static cudaError_t launch_fc1(int kid, int mode, const UnitDev* units, UnitState* states, const int* list,
                              int n, double omk, const u64* gkey, int sm_count, cudaStream_t st,
                              LaunchStats* ls, int* work_counter) {
-    static int max_clusters = 0;   // resident clusters (CTAs for R = 1) on this device
-    auto kern = k_fused_compress<R, CAP, NT, STATIC>;
+    int& max_clusters = MM ? ls->occ_mm[kid] : ls->occ[kid];   // resident clusters (CTAs for R = 1) on this ctx's device
+    auto kern = k_fused_compress<R, CAP, NT, STATIC, MM>;
     constexpr int smem = FSmem<R, CAP>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -917,6 +961,19 @@ static cudaError_t launch_fc(int kid, int mode, const UnitDev* units, UnitState*
     return cudaGetLastError();
 }
 
+// MM (ingest statistics) is a separate instantiation: the min / max tracking costs two live registers in
+// phase A, which the 64-register literal kernels do not have to spare.
+template <int R, int CAP, int NT, bool STATIC>
+static cudaError_t launch_fc(int kid, int mode, const UnitDev* units, UnitState* states, const int* list,
+                             int n, double omk, const u64* gkey, int sm_count, cudaStream_t st,
+                             LaunchStats* ls, int* work_counter) {
+    if (mode & FUSED_MINMAX)
+        return launch_fc1<R, CAP, NT, STATIC, true>(kid, mode & ~FUSED_MINMAX, units, states, list, n, omk, gkey,
+                                                    sm_count, st, ls, work_counter);
+    return launch_fc1<R, CAP, NT, STATIC, false>(kid, mode, units, states, list, n, omk, gkey, sm_count, st, ls,
+                                                 work_counter);
+}
+
 cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states,
                                   const int* unit_list, int n_list, double one_minus_keep,
                                   const u64* global_key, int sm_count, cudaStream_t st,
@@ -954,6 +1011,7 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
     return cudaErrorInvalidValue;
 }
 
+#ifdef WC_PHASE_PROFILE
 // debug: sums over CTAs of the phase cycle counters; reset = zero them afterwards
 cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset) {
     static unsigned long long h[1024][6];
@@ -968,6 +1026,7 @@ cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset) {
     }
     return e;
 }
+#endif
 
 // =====================================================================================================
 // Fused decompress: rle_decode (src/decompressor.cpp:14-30) + inverse_wavelet_decompose (:79-159)
@@ -1146,6 +1205,216 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
         const int ke = s_kend, fl = s_flast;
         for (int m = (fl < 0 ? 0 : (int)dsl.div((uint32_t)fl) + 1) + tid; m <= nseg; m += NT)
             tab[m] = make_int2(ke, fl);
+        __syncthreads();
+    }
+}
+
+// ---- chunk-parallel segment index (packed streams that arrive without tables: files, wc_dplan) -------
+// Same table as k_seg_index, but a work item is one CHUNK of SEG_CHUNK consecutive pairs of one unit
+// instead of a whole unit, so the index pass streams at HBM speed (a CTA per unit walked its ~100 k pairs
+// tile after tile, latency-bound).  A chunk needs the flat index its first pair starts from = the sum of
+// run+1 over all earlier pairs of the unit: chunks publish their sums in a status word and look back over
+// their predecessors (single-pass "decoupled look-back" scan; items are handed out in increasing order
+// from a global counter, so a predecessor is always running or done — no deadlock).
+//   chunk_start[j]  = first item of the j-th listed unit (exclusive prefix of max(1, ceil(K / SEG_CHUNK)));
+//                     built on the host (wc_decompress_batch) or by k_dec_prepare (wc_dplan).
+//   status[item]    = 0 | (1 << 62 | chunk sum) | (2 << 62 | inclusive prefix), zeroed before the launch.
+//   The unit's table memory is zeroed before the launch as well: entries nobody assigns (corrupt streams
+//   with negative runs) then describe empty pair ranges instead of garbage.
+constexpr int SEG_CHUNK = 4096;                      // 512 threads x FD_PPT pairs
+__device__ __forceinline__ u64 ld_acquire_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(u64* p, u64 v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 3)
+k_seg_index2(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
+             const int* __restrict__ unit_list, int n_list, const int* __restrict__ chunk_start,
+             u64* __restrict__ status, int* __restrict__ work_counter, int* __restrict__ err, int slabs) {
+    static_assert(NT * FD_PPT == SEG_CHUNK, "one tile per chunk");
+    __shared__ uint32_t s_wt[32];
+    __shared__ int s_item;
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x;
+    const int cs0 = chunk_start[0];                      // sub-list launches: items are relative to the first unit
+    const int n_items = chunk_start[n_list] - cs0;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        // listed unit j with chunk_start[j] <= item < chunk_start[j + 1]
+        int lo = 0, hi = n_list;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(chunk_start + mid) - cs0 <= item) lo = mid; else hi = mid;
+        }
+        const int item0 = __ldg(chunk_start + lo) - cs0, nch = __ldg(chunk_start + lo + 1) - cs0 - item0;
+        const int c = item - item0;
+        const int uid = unit_list[lo];
+        const DecUnitDev du = dec[uid];
+        const InvUnitDev iu = inv[uid];
+        FGeom g;
+        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g);
+        const uint32_t seglen = (uint32_t)g.seglen, total = (uint32_t)du.total;
+        const int nseg = g.nseg * slabs;
+        int2* const tab = reinterpret_cast<int2*>(du.coef);
+        const int K = du.npairs_dev ? *du.npairs_dev : du.npairs;
+        const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
+        const bool vec16 = (reinterpret_cast<uintptr_t>(pairs) & 15u) == 0;
+        FastDiv dsl;
+        dsl.init(seglen, total);
+        const int p = c * SEG_CHUNK + tid * FD_PPT;
+        int2 pr[FD_PPT];
+        fd_load_tile(pairs, vec16, p, K, pr);
+        bool bad = false;
+        uint32_t ttot;
+        uint32_t pre = fd_tile_scan<NT>(pr, K - p, s_wt, bad, ttot);
+        // chunk base through the look-back
+        if (tid == 0) {
+            uint32_t base = 0;
+            if (c > 0) {
+                st_release_u64(status + item, (1ull << 62) | ttot);
+                for (int k = item - 1; k >= item0; --k) {
+                    u64 v;
+                    do { v = ld_acquire_u64(status + k); } while ((v >> 62) == 0);
+                    base = sat_add(base, (uint32_t)v);
+                    if ((v >> 62) == 2) break;
+                }
+            }
+            st_release_u64(status + item, (2ull << 62) | sat_add(base, ttot));
+            s_base = base;
+        }
+        __syncthreads();
+        const uint32_t base = s_base;
+        pre = sat_add(pre, base);
+        // last in-box pair of this thread's group, and the boundaries its group crosses (as k_seg_index)
+        int gl = -1, gk = 0;
+        {
+            uint32_t rp = pre;
+#pragma unroll
+            for (int j = 0; j < FD_PPT; ++j) {
+                if (p + j < K && pr[j].x >= 0) {
+                    const uint32_t f = sat_add(rp, (uint32_t)pr[j].x);
+                    if (f < total) { gl = (int)f; gk = p + j + 1; }
+                    rp = sat_add(rp, (uint32_t)pr[j].x + 1u);
+                }
+            }
+        }
+        if (gl >= 0) {
+            uint32_t m = pre == 0 ? 0u : dsl.div(pre - 1u) + 1u;
+            uint32_t fb = m * seglen;
+            if ((uint32_t)gl >= fb) {
+                uint32_t rp = pre;
+#pragma unroll
+                for (int j = 0; j < FD_PPT; ++j) {
+                    if (p + j < K && pr[j].x >= 0) {
+                        const uint32_t f = sat_add(rp, (uint32_t)pr[j].x);
+                        if (f < total)
+                            for (; fb <= f; fb += seglen, ++m) tab[m] = make_int2(p + j, (int)rp - 1);
+                        rp = sat_add(rp, (uint32_t)pr[j].x + 1u);
+                    }
+                }
+            }
+        }
+        if (bad) atomicOr(err, 1);
+        // The tail entries (segments that start after the unit's last in-box pair) are written by the group
+        // that holds that pair: its successor pair does not exist or lies outside the box.
+        if (gl >= 0) {
+            const int pn = p + FD_PPT;               // first pair after this thread's group
+            bool last = gk < pn || pn >= K;          // the group itself ends the in-box pairs / the list
+            if (!last) {
+                // successor = first later pair with a non-negative run (negative runs are skipped)
+                uint32_t rp = pre;
+#pragma unroll
+                for (int j = 0; j < FD_PPT; ++j) if (pr[j].x >= 0) rp = sat_add(rp, (uint32_t)pr[j].x + 1u);
+                int q = pn;
+                int2 nx = __ldg(pairs + q);
+                while (nx.x < 0 && ++q < K) nx = __ldg(pairs + q);
+                last = nx.x < 0 || sat_add(rp, (uint32_t)nx.x) >= total;
+            }
+            if (last)
+                for (int m = (int)dsl.div((uint32_t)gl) + 1; m <= nseg; ++m) tab[m] = make_int2(gk, gl);
+        }
+        (void)nch;
+        __syncthreads();     // s_item / s_wt / s_base are rewritten by the next item
+    }
+}
+
+// wc_dplan: the units' pairs arrive as ONE dense stream (unit after unit) plus the per-unit counts.  One CTA
+// turns the counts into per-unit pointers (exclusive scan) inside the DecUnitDev table, validates them
+// (0 <= K <= ncoef, else the corrupt flag) and, for the classes that decode by slabs, builds chunk_start
+// for k_seg_index2 — nothing of this touches the host.
+__global__ void __launch_bounds__(1024)
+k_dec_prepare(DecUnitDev* __restrict__ dec, int n_units, const wc_pair* __restrict__ dense,
+              const int32_t* __restrict__ npairs, const int* __restrict__ tab_list, const int* __restrict__ tab_n,
+              int n_tab_lists, int* __restrict__ chunk_start, int* __restrict__ err) {
+    __shared__ long long s_w[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto block_scan = [&](long long v, long long& tot) -> long long {     // exclusive
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        long long wpre = 0, t = 0;
+        for (int i = 0; i < 32; ++i) { const long long x = s_w[i]; if (i < warp) wpre += x; t += x; }
+        tot = t;
+        __syncthreads();
+        return wpre + inc - v;
+    };
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_units; i0 += 1024) {
+        const int i = i0 + tid;
+        int k = 0;
+        if (i < n_units) {
+            k = npairs[i];
+            if (k < 0 || k > dec[i].total) { atomicOr(err, 1); k = 0; }
+        }
+        long long tot;
+        const long long ex = block_scan((long long)k, tot);
+        if (i < n_units) {
+            dec[i].pairs      = dense + (s_carry + ex);
+            dec[i].npairs     = k;
+            dec[i].npairs_dev = nullptr;
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+        __syncthreads();
+    }
+    // chunk_start of every slab-decoded class list, back to back (each list has its own n + 1 entries)
+    int lo = 0, co = 0;
+    for (int l = 0; l < n_tab_lists; ++l) {
+        const int n = tab_n[l];
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (int j0 = 0; j0 < n; j0 += 1024) {
+            const int j = j0 + tid;
+            long long nch = 0;
+            if (j < n) {
+                const int k = dec[tab_list[lo + j]].npairs;      // written above by this CTA
+                nch = k > 0 ? (k + SEG_CHUNK - 1) / SEG_CHUNK : 1;
+            }
+            long long tot;
+            const long long ex = block_scan(nch, tot);
+            if (j < n) chunk_start[co + j] = (int)(s_carry + ex);
+            __syncthreads();
+            if (tid == 0) s_carry += tot;
+            __syncthreads();
+        }
+        if (tid == 0) chunk_start[co + n] = (int)s_carry;
+        lo += n;
+        co += n + 1;
         __syncthreads();
     }
 }
@@ -1509,7 +1778,7 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    static int per_sm = 0;           // resident CTAs per SM (4 for the small-unit variants)
+    int& per_sm = ls->occ[kid];      // resident CTAs per SM (4 for the small-unit variants), cached per ctx
     if (per_sm == 0) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
         if (e != cudaSuccess) return e;
@@ -1519,6 +1788,38 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
     const int nc = (int)(slots < items ? slots : items);
     ls->begin(kid, st);
     kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter);
+    ls->end(st);
+    return cudaGetLastError();
+}
+
+int fused_decode_slabs(int fused_cls) {
+    switch (fused_cls) {
+    case FUSED_CLS_R8: case FUSED_CLS_CUBE64: return 8;
+    case FUSED_CLS_R4: return 4;
+    case FUSED_CLS_R2: return 2;
+    }
+    return 1;
+}
+
+cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
+                              int n_list, const int* chunk_start, long long items_bound, u64* status,
+                              int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls) {
+    if (n_list <= 0) return cudaSuccess;
+    const long long slots = 3ll * sm_count;
+    const int nb = (int)(items_bound < slots ? (items_bound > 0 ? items_bound : 1) : slots);
+    ls->begin(KID_SEG_INDEX2, st);
+    k_seg_index2<512><<<nb, 512, 0, st>>>(dec, inv, unit_list, n_list, chunk_start, status, work_counter, err,
+                                          fused_decode_slabs(fused_cls));
+    ls->end(st);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
+                               const int* tab_list, const int* tab_n, int n_tab_lists, int* chunk_start, int* err,
+                               cudaStream_t st, LaunchStats* ls) {
+    if (n_units <= 0) return cudaSuccess;
+    ls->begin(KID_DEC_PREPARE, st);
+    k_dec_prepare<<<1, 1024, 0, st>>>(dec, n_units, dense, npairs, tab_list, tab_n, n_tab_lists, chunk_start, err);
     ls->end(st);
     return cudaGetLastError();
 }

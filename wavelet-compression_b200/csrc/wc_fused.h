@@ -9,7 +9,8 @@
 
 namespace wc {
 
-enum { FUSED_FULL = 0, FUSED_KEYS_ONLY = 1, FUSED_GIVEN_THRESH = 2 };
+enum { FUSED_FULL = 0, FUSED_KEYS_ONLY = 1, FUSED_GIVEN_THRESH = 2,
+       FUSED_MINMAX = 16 };   // flag, or-ed in: also record per-unit min / max of the narrowed inputs
 
 // Which fused compress kernel handles a box: 0 = none (generic path); one CTA per unit (<= 32768 cells) or
 // one 8-CTA cluster per unit (<= 262144 cells), each as a runtime-geometry kernel (512 threads) and as a
@@ -36,6 +37,19 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
                                     cudaStream_t st, LaunchStats* ls, int* work_counter = nullptr,
                                     bool build_tables = true);
 
+// Chunk-parallel segment index for packed streams without tables (see k_seg_index2), and the device-side
+// preparation of a dense stream (k_dec_prepare).  SEG_CHUNK pairs per work item.
+constexpr int SEG_INDEX_CHUNK = 4096;
+int fused_decode_slabs(int fused_cls);
+cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
+                              int n_list, const int* chunk_start, long long items_bound, u64* status,
+                              int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls);
+cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
+                               const int* tab_list, const int* tab_n, int n_tab_lists, int* chunk_start, int* err,
+                               cudaStream_t st, LaunchStats* ls);
+
+#ifdef WC_PHASE_PROFILE
 cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset);
+#endif
 
 } // namespace wc

@@ -232,10 +232,15 @@ __global__ void k_finalize_thresh(UnitState* __restrict__ states, int n_units,
 // EXTENSION: batch-wide key = the reference's sequential max rule over the concatenation of the
 // units in batch order.  Per-unit keys order by (|c|, lowest f); across units the lowest unit index
 // wins ties, so reduce (|c| bits, ~unit) and keep the sign of that unit's winner.
-__global__ void k_global_key(const UnitState* __restrict__ states, int n_units, u64* out) {
+__global__ void k_global_key(const UnitDev* __restrict__ units, const UnitState* __restrict__ states, int n_units,
+                             u64* out) {
     __shared__ u64 s_red[32];
+    __shared__ int s_first;
+    if (threadIdx.x == 0) s_first = n_units;
+    __syncthreads();
     u64 best = 0ull;
     for (int i = threadIdx.x; i < n_units; i += blockDim.x) {
+        if (units[i].n > 0) atomicMin(&s_first, i);     // the first coefficient of the concatenation lives here
         u64 k = states[i].key;
         if (k == 0ull) continue;
         u64 g = (k & 0xffffffff00000000ull) | ((u64)(0x7fffffffu - (uint32_t)i) << 1) | (k & 1ull);
@@ -243,8 +248,12 @@ __global__ void k_global_key(const UnitState* __restrict__ states, int n_units, 
     }
     best = block_max_u64(best, s_red);
     if (threadIdx.x == 0) {
-        bool first_nan = n_units > 0 && (states[0].flags & 1);
+        // empty units contribute no coefficient: the "first coefficient is NaN" flag is the one of the first
+        // NON-EMPTY unit (block_max_u64 has synchronised the CTA, s_first is final)
+        bool first_nan = s_first < n_units && (states[s_first].flags & 1);
         *out           = best | (first_nan ? (1ull << 63) : 0ull);
+        // a second word for multi-rank reductions: does this batch own a non-empty unit at all
+        out[1] = s_first < n_units ? 1ull : 0ull;
     }
 }
 
@@ -334,7 +343,12 @@ __global__ void k_scan_tiles(const UnitDev* __restrict__ units, UnitState* __res
         carry_cnt += __shfl_sync(0xffffffffu, ic, 31);
         carry_last = max(carry_last, __shfl_sync(0xffffffffu, im, 31));
     }
-    if (l == 0) states[unit].npairs = carry_cnt;
+    if (l == 0) {
+        states[unit].npairs = carry_cnt;
+        const UnitState st = states[unit];
+        if (carry_cnt > 0 && unit_need32(fabsf(key_value(st.key)), st.thresh_f))
+            states[unit].flags = st.flags | UNIT_FLAG_NEED32;
+    }
 }
 
 __global__ void __launch_bounds__(CT_THREADS)
@@ -796,17 +810,13 @@ __global__ void k_gather_dense(const UnitDev* __restrict__ units, const UnitStat
         if (e__ != cudaSuccess) return e__;      \
     } while (0)
 
+// Function attributes are per device: set on every launch (a cheap driver call) rather than cached in a
+// process-wide static, so that ctxs on different GPUs — and different host threads — stay independent.
 static cudaError_t ensure_xt_smem() {
-    static bool done = false;
-    if (!done) {
-        cudaError_t e;
-        e = cudaFuncSetAttribute(k_forward_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_inverse_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        done = true;
-    }
-    return cudaSuccess;
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_forward_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_inverse_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM_BYTES);
 }
 
 cudaError_t launch_forward_generic(const UnitDev* units, UnitState* states, const int2* tiles,
@@ -841,10 +851,10 @@ cudaError_t launch_finalize_thresh(UnitState* states, int n_units, double one_mi
     return cudaSuccess;
 }
 
-cudaError_t launch_global_key(const UnitState* states, int n_units, u64* out, cudaStream_t st,
-                              LaunchStats* ls) {
+cudaError_t launch_global_key(const UnitDev* units, const UnitState* states, int n_units, u64* out,
+                              cudaStream_t st, LaunchStats* ls) {
     ls->begin(KID_GLOBAL_KEY, st);
-    k_global_key<<<1, 1024, 0, st>>>(states, n_units, out);
+    k_global_key<<<1, 1024, 0, st>>>(units, states, n_units, out);
     ls->end(st);
     WC_LAUNCH_CHECK();
     return cudaSuccess;
@@ -953,6 +963,21 @@ cudaError_t launch_gather_dense(const UnitDev* units, const UnitState* states, i
     const int cpu = 4;
     ls->begin(KID_GATHER, st);
     k_gather_dense<<<n_units * cpu, 256, 0, st>>>(units, states, offsets, dense, n_units, cpu);
+    ls->end(st);
+    WC_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+// wc_plan_set_inputs: new input addresses for the same unit table, stream-ordered (no host synchronisation)
+__global__ void k_patch_inputs(UnitDev* __restrict__ units, const void* const* __restrict__ ptrs, int n_units) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_units) units[i].in = ptrs[i];
+}
+cudaError_t launch_patch_inputs(UnitDev* units, const void* const* ptrs, int n_units, cudaStream_t st,
+                                LaunchStats* ls) {
+    if (n_units <= 0) return cudaSuccess;
+    ls->begin(KID_PATCH_INPUTS, st);
+    k_patch_inputs<<<(n_units + 255) / 256, 256, 0, st>>>(units, ptrs, n_units);
     ls->end(st);
     WC_LAUNCH_CHECK();
     return cudaSuccess;

@@ -18,7 +18,7 @@ struct UnitState;
 enum KernelId {
     KID_FORWARD_GENERIC, KID_ARGMAX_FLAT, KID_FINALIZE, KID_GLOBAL_KEY, KID_COUNT, KID_SCAN, KID_EMIT,
     KID_RLE_SUMS, KID_RLE_SCAN, KID_RLE_SCATTER, KID_INVERSE_GENERIC, KID_RMSE_TILES, KID_RMSE_FINAL,
-    KID_OFFSETS, KID_GATHER, KID_FUSED_C1, KID_FUSED_C8, KID_FUSED_C1S, KID_FUSED_C8S, KID_FUSED_D1, KID_FUSED_D8, KID_FUSED_D1S, KID_FUSED_D8S, KID_SEG_INDEX, KID_FUSED_C1T, KID_FUSED_C16, KID_FUSED_D1T, KID_FUSED_D16, KID_FUSED_C8C, KID_FUSED_D8C, KID_FUSED_C4, KID_FUSED_C2, KID_FUSED_D4, KID_FUSED_D2, KID_MINMAX_TILES, KID_MINMAX_FINAL, KID_N
+    KID_OFFSETS, KID_GATHER, KID_FUSED_C1, KID_FUSED_C8, KID_FUSED_C1S, KID_FUSED_C8S, KID_FUSED_D1, KID_FUSED_D8, KID_FUSED_D1S, KID_FUSED_D8S, KID_SEG_INDEX, KID_FUSED_C1T, KID_FUSED_C16, KID_FUSED_D1T, KID_FUSED_D16, KID_FUSED_C8C, KID_FUSED_D8C, KID_FUSED_C4, KID_FUSED_C2, KID_FUSED_D4, KID_FUSED_D2, KID_MINMAX_TILES, KID_MINMAX_FINAL, KID_SEG_INDEX2, KID_DEC_PREPARE, KID_PATCH_INPUTS, KID_N
 };
 inline const char* kernel_name(int id) {
     static const char* n[KID_N] = {
@@ -30,7 +30,8 @@ inline const char* kernel_name(int id) {
         "k_fused_decompress<8>", "k_fused_decompress<1,cube32>", "k_fused_decompress<8,cube64>", "k_seg_index", "k_fused_compress<1,small>", "k_fused_compress<1,cube16>",
         "k_fused_decompress<1,small>", "k_fused_decompress<1,cube16>", "k_fused_compress<1,cube8>",
         "k_fused_decompress<1,cube8>", "k_fused_compress<4>", "k_fused_compress<2>", "k_fused_decompress<4>",
-        "k_fused_decompress<2>", "k_minmax_tiles", "k_minmax_final" };
+        "k_fused_decompress<2>", "k_minmax_tiles", "k_minmax_final", "k_seg_index2", "k_dec_prepare",
+        "k_patch_inputs" };
     return (id >= 0 && id < KID_N) ? n[id] : "?";
 }
 struct LaunchStats {
@@ -38,6 +39,8 @@ struct LaunchStats {
     bool     profile  = false;
     uint64_t count[KID_N] = {};
     double   ms[KID_N]    = {};
+    int      occ[KID_N]   = {};   // occupancy of each kernel on this ctx's device (0 = not queried yet)
+    int      occ_mm[KID_N] = {};  // same for the ingest-statistics instantiations of the compress kernels
     struct Pending { int id; cudaEvent_t a, b; };
     std::vector<Pending>     pending;
     std::vector<cudaEvent_t> pool;
@@ -131,8 +134,10 @@ cudaError_t launch_argmax_flat(const UnitDev* units, UnitState* states, const in
                                int n_ctiles, cudaStream_t st, LaunchStats* ls);
 cudaError_t launch_finalize_thresh(UnitState* states, int n_units, double one_minus_keep,
                                    const u64* global_key, cudaStream_t st, LaunchStats* ls);
-cudaError_t launch_global_key(const UnitState* states, int n_units, u64* out, cudaStream_t st,
-                              LaunchStats* ls);
+cudaError_t launch_global_key(const UnitDev* units, const UnitState* states, int n_units, u64* out,
+                              cudaStream_t st, LaunchStats* ls);
+cudaError_t launch_patch_inputs(UnitDev* units, const void* const* ptrs, int n_units, cudaStream_t st,
+                                LaunchStats* ls);
 cudaError_t launch_pack_generic(const UnitDev* units, UnitState* states, int n_units,
                                 const int2* ctiles, int n_ctiles, int* tile_cnt, int* tile_last,
                                 int* tile_base, int* tile_prev, cudaStream_t st,

@@ -50,11 +50,47 @@ inline void check(int status, wc_ctx* ctx, const char* what) {
         die(std::string(what) + ": " + wc_strerror(status) + (ctx ? std::string(" — ") + wc_last_error(ctx) : ""));
 }
 
-// one context per process and device, created on first use
-inline wc_ctx* context(int device = 0) {
-    static wc_ctx* ctx = nullptr;
-    if (!ctx) check(wc_create(&ctx, device), nullptr, "wc_create");
-    return ctx;
+// One context per (host thread, device), created on first use and destroyed with the thread.  A wc_ctx is not
+// thread-safe (include/wcgpu.h), so contexts are never shared between threads: a threaded multi-GPU host
+// (one thread per GPU) calls wcgpu::set_device(g) in each thread and then uses the same
+// free functions as the single-GPU host.  The default device is 0.
+struct ThreadContexts {
+    std::vector<wc_ctx*> by_device;
+    int                  current = 0;
+    ~ThreadContexts() {
+        for (wc_ctx* c : by_device)
+            if (c) wc_destroy(c);
+    }
+};
+inline ThreadContexts& thread_contexts() {
+    static thread_local ThreadContexts tc;
+    return tc;
+}
+inline wc_ctx* context(int device = -1) {
+    ThreadContexts& tc = thread_contexts();
+    if (device < 0) device = tc.current;
+    if ((size_t)device >= tc.by_device.size()) tc.by_device.resize((size_t)device + 1, nullptr);
+    if (!tc.by_device[device]) check(wc_create(&tc.by_device[device], device), nullptr, "wc_create");
+    return tc.by_device[device];
+}
+
+// Validated view of a decoded (xz-decompressed) unit: the 20-byte header of src/compressor.cpp:59-71 and the
+// K pairs behind it.  Rejects what the reference would read out of bounds on: a short buffer, negative
+// dims / counts, K > ncoef, ncoef != nx*ny*nz, fewer than 8K payload bytes (truncated or hostile file).
+inline wc_packed parse_unit(const std::string& raw, const std::string& what) {
+    if (raw.size() < 20) die("Deserialization failed: short file " + what);
+    int32_t h[5];
+    std::memcpy(h, raw.data(), 20);
+    if (h[0] < 0 || h[1] < 0 || h[2] < 0 || h[3] < 0 || h[4] < 0) die("Deserialization failed: negative header field " + what);
+    if ((long long)h[0] * h[1] * h[2] != (long long)h[3]) die("Deserialization failed: shape / coefficient count mismatch " + what);
+    if (h[4] > h[3]) die("Deserialization failed: more pairs than coefficients " + what);
+    if (raw.size() - 20 < 8 * (size_t)h[4]) die("Deserialization failed: truncated file " + what);
+    wc_packed p;
+    p.shape[0] = h[0]; p.shape[1] = h[1]; p.shape[2] = h[2];
+    p.ncoef = h[3]; p.npairs = h[4]; p.flags = 0;
+    // the pairs sit 4-byte aligned inside the decoded string (offset 20): wc_pair has 4-byte alignment
+    p.pairs = reinterpret_cast<wc_pair*>(const_cast<char*>(raw.data()) + 20);
+    return p;
 }
 
 template <class Box>
@@ -201,16 +237,8 @@ inline CompressedWavelet deserialize_compressed_wavelet(const std::string& data)
 inline Box3D decompress(std::string file_path, int /*time*/, int /*level*/, int /*component*/, int /*box_idx*/) {
     wc_ctx* ctx = detail::context();
     std::string raw = detail::xz_decode_file(file_path);
-    if (raw.size() < 20) detail::die("Deserialization failed: short file " + file_path);
-    int32_t h[5];
-    std::memcpy(h, raw.data(), 20);
-    if (raw.size() < 20 + 8 * (size_t)h[4]) detail::die("Deserialization failed: truncated file " + file_path);
-    wc_packed p;
-    p.shape[0] = h[0]; p.shape[1] = h[1]; p.shape[2] = h[2];
-    p.ncoef = h[3]; p.npairs = h[4]; p.reserved = 0;
-    std::vector<wc_pair> pairs((size_t)h[4]);
-    if (h[4]) std::memcpy(pairs.data(), raw.data() + 20, 8 * (size_t)h[4]);
-    p.pairs = pairs.data();
+    const wc_packed p = detail::parse_unit(raw, file_path);
+    const int32_t* h = p.shape;
     Box3D box((size_t)h[0], (size_t)h[1], (size_t)h[2]);
     wc_box_out o { box.data_size() ? &box(0, 0, 0) : nullptr, WC_F32, h[0], h[1], h[2] };
     detail::check(wc_decompress_batch(ctx, &p, 1, WC_HOST, &o, WC_HOST), ctx, "wc_decompress_batch");
@@ -292,7 +320,6 @@ decompress_all(const std::string& compressed_dir, const std::vector<std::vector<
     unsigned nt = lzma_threads ? lzma_threads : std::thread::hardware_concurrency();
     detail::parallel_for(keys.size(), nt, [&](size_t i) {
         raw[i] = detail::xz_decode_file(detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b));
-        if (raw[i].size() < 20) detail::die("Deserialization failed: short file");
     });
     std::vector<std::vector<std::vector<multiBox3D>>> regen(box_counts.size());
     for (size_t t = 0; t < box_counts.size(); ++t) {
@@ -302,12 +329,8 @@ decompress_all(const std::string& compressed_dir, const std::vector<std::vector<
     std::vector<wc_packed>  in(keys.size());
     std::vector<wc_box_out> out(keys.size());
     for (size_t i = 0; i < keys.size(); ++i) {
-        int32_t h[5];
-        std::memcpy(h, raw[i].data(), 20);
-        in[i].shape[0] = h[0]; in[i].shape[1] = h[1]; in[i].shape[2] = h[2];
-        in[i].ncoef = h[3]; in[i].npairs = h[4]; in[i].reserved = 0;
-        // the pairs sit 4-byte aligned inside the decoded string (offset 20): wc_pair has 4-byte alignment
-        in[i].pairs = reinterpret_cast<wc_pair*>(&raw[i][0] + 20);
+        in[i] = detail::parse_unit(raw[i], detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b));
+        const int32_t* h = in[i].shape;
         multiBox3D& mb = regen[keys[i].t][keys[i].l][keys[i].b];
         if (mb.size() < comp_idxs.size()) mb.resize(comp_idxs.size());
         mb[keys[i].ci] = Box3D((size_t)h[0], (size_t)h[1], (size_t)h[2]);
