@@ -1,8 +1,12 @@
-"""GPU: the -estimate / -c / -d drivers (modes.py) over AMReX-format plotfiles written by plotfile.py.
-BASELINE config 1 is reproduced from the bundled-fixture payloads stored in the golden file: 4096 + 8 pairs,
-RMSE 0, adjusted loss 0, predicted compressed size 0.09737 %."""
+"""GPU: the -estimate / -c / -d drivers (modes.py) over AMReX-format plotfiles.
+BASELINE config 1 is reproduced on the reference's own bundled plotfile (tests/golden/plt_fixtures.tar.xz, a copy of
+its test data): 4096 + 8 pairs, RMSE 0, adjusted loss 0, predicted compressed size 0.09737 %.
+BASELINE config 2 (-c then -d on plt00074..plt00075) must regenerate the reference's fixture DIRECTORIES byte for byte —
+Header, Cell_H and Cell_D — which is what the reference's writer test demands of AMReX (src/writeplotfile.cpp:400)."""
+import filecmp
 import lzma
 import os
+import tarfile
 
 import numpy as np
 import pytest
@@ -13,54 +17,68 @@ pytestmark = pytest.mark.gpu
 F999 = float(np.float32(0.999))
 
 
-def _fixture_plotfile(wc, golden, tmp, plt="plt00074"):
-    """Rebuilds Level_0 / Level_1 of the reference's bundled plotfile from the golden payloads."""
-    by = {c["name"]: i for i, c in enumerate(golden.cases)}
-    boxes = [((0, 0, 0), (15, 31, 63)), ((16, 32, 64), (23, 35, 65))]
-    out = os.path.join(tmp, plt)
-    for level in (0, 1):
-        data = []
-        for b in range(2):
-            comps = [golden.arrays(by[f"fixture_{plt}_L{level}_b{b}_{name}_k9999"])["in"] for name in ("temp", "pressure")]
-            data.append(np.stack(comps))
-        wc.plotfile.write_level(out, level, boxes, data, 2)
-    hdr = wc.plotfile.Header("HyperCLaw-V1.1", ["temp", "pressure"], 3, 0.2219392, 1, [0.6, 0.5, 0.4], [0.8, 0.9, 1.0], [2],
-                             [((0, 0, 0), (255, 511, 255)), ((0, 0, 0), (511, 1023, 511))], [1200, 1500],
-                             [[0.00078125] * 3, [0.000390625] * 3], 0, 0,
-                             [dict(level=l, ngrids=2, time=0.2219392, step=s, boxes_phys=[[(0.0, 1.0)] * 3] * 2, path=f"Level_{l}/Cell")
-                              for l, s in ((0, 1200), (1, 1500))])
-    wc.plotfile.write_header(out, hdr)
-    return out
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_baseline_config1_estimate(wc, ctx, golden, tmp_path):
-    plt = _fixture_plotfile(wc, golden, str(tmp_path))
+def _fixtures(tmp):
+    """The reference's bundled plotfiles plt00074 / plt00075 (copied test data, oracle/make_golden_side.py)."""
+    with tarfile.open(os.path.join(ROOT, "tests", "golden", "plt_fixtures.tar.xz")) as tar:
+        tar.extractall(tmp, filter="data")
+    return [os.path.join(tmp, p) for p in ("plt00074", "plt00075")]
+
+
+def _same_tree(a, b):
+    names = []
+    for dp, _, files in os.walk(a):
+        for f in files:
+            rel = os.path.relpath(os.path.join(dp, f), a)
+            names.append(rel)
+            assert filecmp.cmp(os.path.join(a, rel), os.path.join(b, rel), shallow=False), rel
+    return sorted(names)
+
+
+def test_baseline_config1_estimate(wc, ctx, tmp_path):
+    plt = _fixtures(str(tmp_path))[0]
     assert os.path.getsize(os.path.join(plt, "Level_0", "Cell_D_00000")) == 525493
     est = wc.modes.estimate(plt, 0, ["temp"], F999, ctx=ctx)
-    assert est["npairs"] == [4096, 8]
+    assert est["npairs"] == [4096, 8] and est["need32"] == [False, False]
     assert est["components"]["temp"]["rmse"] == 0.0 and est["components"]["temp"]["adjusted_loss"] == 0.0
     assert est["components"]["temp"]["max"] == np.float32(3902.4) and est["components"]["temp"]["min"] == 16.0
     assert abs(est["compressed_percent"] - 100.0 * 256 / 262913.5) < 1e-9       # 168 B + 88 B of .xz
+    # device-resident: the raw float64 slabs cross the bus ONCE (plus a few KB of descriptor tables)
+    assert est["input_bytes"] == 8 * (32768 + 64)
+    assert est["input_bytes"] <= est["h2d_bytes"] <= est["input_bytes"] + 4096
 
 
-def test_baseline_config2_roundtrip(wc, ctx, golden, tmp_path):
-    """-c then -d on plt00074..plt00075, both levels, components temp + pressure, keep = 0.9999f: 16 units,
-    4096 / 8 pairs each, regenerated Level files byte-identical to the inputs (constant boxes)."""
-    import filecmp
-    plts = [_fixture_plotfile(wc, golden, str(tmp_path / "in"), p) for p in ("plt00074", "plt00075")]
+def test_baseline_config2_roundtrip_regenerates_the_reference_fixture(wc, ctx, tmp_path):
+    """-c then -d on plt00074..plt00075, both levels, components temp + pressure, keep = 0.9999f: 16 units, 4096 / 8 pairs
+    each; the five side files are what the reference's own writers produce for this run (golden, masked long double
+    padding); the regenerated plotfile directories are byte-identical to the reference's fixtures, Header included."""
+    plts = _fixtures(str(tmp_path / "in"))
     cdir = str(tmp_path / "compressed")
-    man = wc.modes.compress_run(plts, [0, 1], ["temp", "pressure"], float(np.float32(0.9999)), cdir, ctx=ctx)
+    res = wc.modes.compress_run(plts, 0, 1, ["temp", "pressure"], float(np.float32(0.9999)), cdir, ctx=ctx)
+    assert res["units"] == 16 and not any(res["need32"])
     files = sorted(f for f in os.listdir(cdir) if f.endswith(".xz"))
     assert len(files) == 16
     for f in files:
         p = wc.PackedUnit.deserialize(lzma.decompress(open(os.path.join(cdir, f), "rb").read()))
         assert p.npairs == (4096 if p.dims == (16, 32, 64) else 8)
+    side = np.load(os.path.join(ROOT, "tests", "golden", "sidefiles_v1.npz"))
+    for name in wc.sidefiles.NAMES:
+        got = open(os.path.join(cdir, name), "rb").read()
+        want = side[f"config2_{name}"].tobytes()
+        if name == "runinfo.raw":        # the golden run names its inputs ../tests/plt0007x; only the paths differ
+            ri = wc.sidefiles.read_runinfo(cdir + "/")
+            assert [os.path.basename(f) for f in ri.files] == ["plt00074", "plt00075"]
+            assert (ri.min_level, ri.max_level, ri.components, ri.comp_idxs) == (0, 1, ["temp", "pressure"], [0, 1])
+        elif name == "amrexinfo.raw":
+            assert wc.sidefiles.mask_long_double_padding(got) == wc.sidefiles.mask_long_double_padding(want)
+        else:
+            assert got == want, name
     wc.modes.decompress_run(cdir, str(tmp_path / "out"), ctx=ctx)
     for p in ("plt00074", "plt00075"):
-        for level in (0, 1):
-            for name in ("Cell_H", "Cell_D_00000"):
-                assert filecmp.cmp(os.path.join(str(tmp_path / "out"), p, f"Level_{level}", name),
-                                   os.path.join(str(tmp_path / "in"), p, f"Level_{level}", name), shallow=False)
+        names = _same_tree(os.path.join(str(tmp_path / "in"), p), os.path.join(str(tmp_path / "out"), p))
+        assert names == ["Header", "Level_0/Cell_D_00000", "Level_0/Cell_H", "Level_1/Cell_D_00000", "Level_1/Cell_H"]
 
 
 def test_estimate_matches_oracle_on_nontrivial_plotfile(wc, ctx, oracle, tmp_path):
@@ -96,7 +114,9 @@ def test_estimate_matches_oracle_on_nontrivial_plotfile(wc, ctx, oracle, tmp_pat
     raw = sum(os.path.getsize(os.path.join(ldir, f)) for f in os.listdir(ldir)) / 3 * 2
     assert abs(est["compressed_percent"] - xz_total / raw * 100) < 1e-9
     for name in comps:
-        want = float(np.sum(per[name]) / len(per[name]))
+        want = wc.modes.sequential_mean(per[name])                      # std::accumulate, left to right
         assert abs(est["components"][name]["rmse"] - want) <= 1e-12 * want
         assert est["components"][name]["min"] == lo[name] and est["components"][name]["max"] == hi[name]
-        assert abs(est["components"][name]["adjusted_loss"] - want / (hi[name] - lo[name])) <= 1e-12 * want
+        rng32 = float(np.float32(hi[name]) - np.float32(lo[name]))      # max_values[c] - min_values[c] in float, src/modes.cpp:289
+        assert abs(est["components"][name]["adjusted_loss"] - want / rng32) <= 1e-12 * want / rng32
+    assert est["input_bytes"] <= est["h2d_bytes"] <= est["input_bytes"] + 4096

@@ -7,12 +7,13 @@
     refapi.py    Python mirror of the reference's three entry points (LZMA + files on the host)
     amr_synth.py synthetic AMReX-shaped workloads
     plotfile.py  AMReX plotfile reader / writer without AMReX (Header, Cell_H, Cell_D)
+    sidefiles.py the five .raw side files of a run, byte-compatible with src/readandwrite.cpp
     modes.py     -estimate / -c / -d drivers on top of the GPU path
 
 The directory name contains a hyphen (it mirrors the reference's repository name); import it with
 importlib.import_module("wavelet-compression_b200") or through __graft_entry__.package().
 """
-from . import amr_synth, capi, modes, plotfile  # noqa: F401
+from . import amr_synth, capi, modes, plotfile, sidefiles  # noqa: F401
 
 try:  # torch is only needed for the multi-process helpers
     from . import distributed  # noqa: F401

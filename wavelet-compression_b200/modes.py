@@ -1,19 +1,26 @@
-"""Host-side mode drivers on top of the GPU path: Python counterparts of the
-reference's `-estimate`, `-c` and `-d` loops (src/modes.cpp:209-328, :24-112, :115-204) that read AMReX
-plotfiles with plotfile.py instead of AMReX.  Everything numeric runs on the GPU through the C ABI; LZMA,
-file names and directory layout follow the reference (compressed-wavelet-{t}-{level}-{comp}-{box}.xz).
-The reference's five .raw side files are replaced by one JSON manifest (metadata, not on the hot path).
+"""Host-side mode drivers on top of the GPU path: Python counterparts of the reference's
+`-estimate`, `-c` and `-d` loops (src/modes.cpp:209-328, :24-112, :115-204) that read AMReX plotfiles with
+plotfile.py instead of AMReX.  Everything numeric runs on the GPU through the C ABI; what stays on the host is what
+the reference keeps there: LZMA, the file names (compressed-wavelet-{t}-{level}-{comp}-{box}.xz), the five .raw side
+files (sidefiles.py, byte-compatible with src/readandwrite.cpp) and the plotfile directory layout.
+
+  estimate       one H2D of the raw float64 FAB slabs; compress -> decompress -> RMSE -> min/max all stay in HBM
+                 (wc_plan_*); only the packed pairs come back, chunk by chunk, for the LZMA size estimate, which runs
+                 on host threads WHILE the GPU works on later chunks.
+  compress_run   same pipeline, the chunk callback feeds the .xz writers.
+  decompress_run the files' pair bytes are concatenated into one dense stream and decoded by a decode plan
+                 (wc_dplan_*), float64 out, then written as a complete plotfile (Header + Level_k/Cell_H + Cell_D).
 """
 from __future__ import annotations
 
-import json
+import ctypes as C
 import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from . import plotfile
-from .core import Context, PackedUnit
+from . import capi, plotfile, sidefiles
+from .core import Context, _host_descs
 from .refapi import unit_filename, xz_decode, xz_encode
 
 FLT_MAX = float(np.finfo(np.float32).max)
@@ -44,9 +51,49 @@ def fold_minmax(mins, maxs, n_comp):
     return lo, hi
 
 
+def sequential_mean(values) -> float:
+    """std::accumulate(begin, end, 0.0) / size (src/modes.cpp:284-285): a left-to-right float64 sum."""
+    s = 0.0
+    for v in values:
+        s += float(v)
+    return s / len(values)
+
+
+def _serialized(rec) -> bytes:
+    """serialize_compressed_wavelet (src/compressor.cpp:55-80) of one wc_packed record with host pairs."""
+    k = int(rec["npairs"])
+    head = np.array([*[int(s) for s in rec["shape"]], int(rec["ncoef"]), k], dtype="<i4").tobytes()
+    return head + (C.string_at(int(rec["pairs"]), 8 * k) if k else b"")
+
+
+def _compress_units(ctx: Context, boxes, dims, keep: float, per_unit, threads: int, ingest_stats: bool):
+    """One plan over host boxes: pipelined H2D / kernels / D2H; `per_unit(i, serialized_bytes)` runs on a host thread
+    pool fed by the chunk callback, i.e. while later chunks are still on the GPU.  Returns the plan (its packed result
+    stays in HBM for the round trip of estimate)."""
+    descs, hold = _host_descs(boxes, dims)
+    if ingest_stats:
+        ctx.set_option(capi.WC_OPT_INGEST_STATS, 1)
+    try:
+        plan = ctx.plan(descs, capi.WC_HOST)
+        plan._hold = hold
+        with ThreadPoolExecutor(threads or os.cpu_count() or 1) as pool:
+            futs = []
+
+            def on_chunk(first, n, recs):
+                for j in range(n):
+                    futs.append(pool.submit(per_unit, first + j, _serialized(recs[j])))
+            rec = plan.compress_to_host_chunked(keep, on_chunk).copy()
+            for f in futs:
+                f.result()
+    finally:
+        if ingest_stats:
+            ctx.set_option(capi.WC_OPT_INGEST_STATS, 0)
+    return plan, rec
+
+
 def estimate(plt_dir: str, level: int, components, keep: float, ctx: Context | None = None, threads: int = 0):
     """`-estimate` (src/modes.cpp:209-328): ONE file, ONE level, all requested components.
-    Returns {component: {rmse, adjusted_loss}}, compressed_percent and the per-unit pair counts."""
+    Returns {component: {rmse, adjusted_loss}}, compressed_percent, the per-unit pair counts and need32 flags."""
     ctx = ctx or Context(0)
     hdr = plotfile.read_header(plt_dir)
     comp_idxs = component_indices(hdr, components)
@@ -54,21 +101,35 @@ def estimate(plt_dir: str, level: int, components, keep: float, ctx: Context | N
     units = plotfile.level_units(lev, comp_idxs)
     boxes = [u[0] for u in units]
     dims = [u[1] for u in units]
-    nc = len(comp_idxs)
-    packed = ctx.compress_batch(boxes, keep, dims=dims)                  # F, T, M, P on the GPU (float64 ingest)
-    recon = ctx.decompress_batch(packed)                                 # U, I
-    rmse = ctx.rmse_batch(boxes, recon)                                  # R (narrowing of `actual` on the GPU)
-    mins, maxs = ctx.minmax_batch(boxes, dims)
+    nc, n = len(comp_idxs), len(units)
+    xz_sizes = [0] * n
+
+    def size_of(i, ser):
+        xz_sizes[i] = len(xz_encode(ser))                                  # LZMA stays on the host (threads)
+    h2d0 = ctx.counter(capi.WC_CTR_H2D_BYTES)
+    plan, rec = _compress_units(ctx, boxes, dims, keep, size_of, threads, ingest_stats=True)   # F, T, M, P (float64 ingest)
+    # U, I, R without leaving HBM: reconstruction into device boxes, RMSE against the plan's own inputs
+    ncoef = [d[0] * d[1] * d[2] for d in dims]
+    dbuf = C.c_void_p()
+    capi.check(ctx.lib.wc_device_alloc(ctx.h, C.byref(dbuf), 4 * max(sum(ncoef), 1)), "wc_device_alloc", ctx.h)
+    try:
+        offs = np.concatenate([[0], np.cumsum(ncoef)])[:-1]
+        od = capi.box_descs([dbuf.value + 4 * int(o) for o in offs], [capi.WC_F32] * n, dims)
+        plan.decompress(od, capi.WC_DEVICE)
+        rmse = plan.rmse(od)
+        mins, maxs, need32 = plan.unit_stats()
+    finally:
+        ctx.lib.wc_device_free(ctx.h, dbuf)
+    h2d = ctx.counter(capi.WC_CTR_H2D_BYTES) - h2d0
+    plan.close()
     lo, hi = fold_minmax(mins, maxs, nc)
-    with ThreadPoolExecutor(threads or os.cpu_count() or 1) as pool:     # LZMA stays on the host
-        xz_sizes = list(pool.map(lambda p: len(xz_encode(p.serialize())), packed))
-    out = {"components": {}, "npairs": [p.npairs for p in packed]}
+    out = {"components": {}, "npairs": [int(k) for k in rec["npairs"]], "need32": [bool(x) for x in need32],
+           "h2d_bytes": int(h2d), "input_bytes": int(sum(b.nbytes for b in boxes))}
     for c, name in enumerate(components):
-        per_box = rmse[c::nc]
-        mean_rmse = float(np.sum(per_box) / len(per_box))                # std::accumulate / size, src/modes.cpp:284-285
-        out["components"][name] = {"rmse": mean_rmse, "adjusted_loss": mean_rmse / (hi[c] - lo[c]) if hi[c] != lo[c] else
-                                   float(np.float64(mean_rmse) / np.float64(hi[c] - lo[c]) if mean_rmse else np.nan),
-                                   "min": lo[c], "max": hi[c]}
+        mean_rmse = sequential_mean(rmse[c::nc])                          # src/modes.cpp:284-285
+        with np.errstate(divide="ignore", invalid="ignore"):
+            adj = float(np.float64(mean_rmse) / np.float64(np.float32(hi[c]) - np.float32(lo[c])))   # :289, float range
+        out["components"][name] = {"rmse": mean_rmse, "adjusted_loss": adj, "min": lo[c], "max": hi[c]}
     ldir = os.path.join(plt_dir, f"Level_{level}")
     raw_size = float(sum(os.path.getsize(os.path.join(ldir, f)) for f in os.listdir(ldir)))
     raw_size = raw_size / len(hdr.names) * nc                             # src/modes.cpp:316-318
@@ -76,66 +137,90 @@ def estimate(plt_dir: str, level: int, components, keep: float, ctx: Context | N
     return out
 
 
-def compress_run(plt_dirs, levels, components, keep: float, compressed_dir: str, ctx: Context | None = None,
-                 threads: int = 0):
-    """`-c` (src/modes.cpp:24-112): every (file, level, box, component) in one GPU batch, one .xz per unit."""
+def _dir(d: str) -> str:
+    return d if d.endswith("/") else d + "/"      # the reference concatenates dir + name (src/readandwrite.cpp:200)
+
+
+def compress_run(plt_dirs, min_level: int, max_level: int, components, keep: float, compressed_dir: str,
+                 ctx: Context | None = None, threads: int = 0):
+    """`-c` (src/modes.cpp:24-112): the five side files, then every (file, level, box, component) in one GPU batch,
+    one .xz per unit written by host threads as the chunks come back."""
     ctx = ctx or Context(0)
+    compressed_dir = _dir(compressed_dir)
     os.makedirs(compressed_dir, exist_ok=True)
+    levels = list(range(min_level, max_level + 1))                         # format_levels
     keys, boxes, dims = [], [], []
-    manifest = {"files": [os.path.basename(os.path.normpath(p)) for p in plt_dirs], "levels": list(levels),
-                "components": list(components), "boxes": {}}
-    hdr0 = None
+    locations, dimensions, counts = [], [], []
+    comp_idxs = None
     for t, plt in enumerate(plt_dirs):
         hdr = plotfile.read_header(plt)
-        hdr0 = hdr0 or hdr
-        comp_idxs = component_indices(hdr, components)
+        comp_idxs = component_indices(hdr, components)                     # the last file's indices (src/preprocess.cpp:150)
+        locations.append([]); dimensions.append([]); counts.append([])
         for li, level in enumerate(levels):
             lev = plotfile.read_level(plt, level)
-            manifest["boxes"][f"{t}-{li}"] = [[list(f.lo), list(f.hi)] for f in lev.fabs]
+            locations[t].append([f.lo for f in lev.fabs])
+            dimensions[t].append([f.dims for f in lev.fabs])
+            counts[t].append(len(lev.fabs))
             for b, fab in enumerate(lev.fabs):
                 for c in comp_idxs:
                     keys.append((t, li, c, b))
                     boxes.append(fab.data[c])
                     dims.append(fab.dims)
-    manifest["comp_idxs"] = component_indices(hdr0, components)
-    packed = ctx.compress_batch(boxes, keep, dims=dims)
+    runinfo = sidefiles.RunInfo(list(plt_dirs), min_level, max_level, list(components), list(comp_idxs))
+    amrexinfo = sidefiles.amrexinfo_from_headers(plt_dirs, len(levels))
+    sidefiles.write_all(compressed_dir, runinfo, locations, dimensions, counts, amrexinfo)    # src/modes.cpp:71-89
 
-    def write(i):
-        t, li, c, b = keys[i]
-        with open(os.path.join(compressed_dir, unit_filename(t, li, c, b)), "wb") as f:
-            f.write(xz_encode(packed[i].serialize()))
-    with ThreadPoolExecutor(threads or os.cpu_count() or 1) as pool:
-        list(pool.map(write, range(len(keys))))
-    with open(os.path.join(compressed_dir, "wcgpu_manifest.json"), "w") as f:
-        json.dump(manifest, f)
-    return manifest
+    def write(i, ser):
+        with open(compressed_dir + unit_filename(*keys[i]), "wb") as f:
+            f.write(xz_encode(ser))
+    plan, rec = _compress_units(ctx, boxes, dims, keep, write, threads, ingest_stats=False)
+    plan.close()
+    return {"units": len(keys), "npairs": [int(k) for k in rec["npairs"]], "need32": [bool(int(f) & 1) for f in rec["flags"]]}
 
 
 def decompress_run(compressed_dir: str, out_dir: str, ctx: Context | None = None, threads: int = 0):
-    """`-d` (src/modes.cpp:115-204): reads every unit file, one GPU batch for U + I, writes Level_k/Cell_*
-    for each timestep (float32 results widened to float64 on the GPU, as src/writeplotfile.cpp:103)."""
+    """`-d` (src/modes.cpp:115-204): everything comes from the side files; the unit files are xz-decoded on host
+    threads, their pair bytes form one dense stream for a decode plan (float64 out, the widening of
+    src/writeplotfile.cpp:103 on the GPU), and each timestep is written as a complete plotfile — Header included."""
     ctx = ctx or Context(0)
-    m = json.load(open(os.path.join(compressed_dir, "wcgpu_manifest.json")))
-    keys = []
-    for key, bl in m["boxes"].items():
-        t, li = (int(v) for v in key.split("-"))
-        for b in range(len(bl)):
-            for c in m["comp_idxs"]:
-                keys.append((t, li, c, b))
+    compressed_dir, out_dir = _dir(compressed_dir), _dir(out_dir)
+    ri = sidefiles.read_runinfo(compressed_dir)
+    nt, nl, nc = len(ri.files), ri.max_level - ri.min_level + 1, len(ri.comp_idxs)
+    counts = sidefiles.read_box_counts(compressed_dir, nt, nl)
+    locs = sidefiles.read_loc_dim(compressed_dir, "locations.raw", counts)
+    dims_ld = sidefiles.read_loc_dim(compressed_dir, "dimensions.raw", counts)
+    info = sidefiles.read_amrexinfo(compressed_dir)
+    keys = [(t, l, c, b) for t in range(nt) for l in range(nl) for b in range(counts[t][l]) for c in ri.comp_idxs]
 
     def read(k):
-        with open(os.path.join(compressed_dir, unit_filename(*k)), "rb") as f:
-            return PackedUnit.deserialize(xz_decode(f.read()))
+        with open(compressed_dir + unit_filename(*k), "rb") as f:
+            raw = xz_decode(f.read())
+        h = np.frombuffer(raw, "<i4", 5)
+        if len(raw) < 20 or (h < 0).any() or int(h[0]) * int(h[1]) * int(h[2]) != int(h[3]) or h[4] > h[3] or len(raw) - 20 < 8 * int(h[4]):
+            raise ValueError(f"corrupt unit file {unit_filename(*k)}")
+        return (int(h[0]), int(h[1]), int(h[2])), int(h[4]), raw
     with ThreadPoolExecutor(threads or os.cpu_count() or 1) as pool:
-        packed = list(pool.map(read, keys))
-    recon = ctx.decompress_batch(packed, out_dtype=np.float64)
-    nc = len(m["comp_idxs"])
-    by = {}
-    for k, r in zip(keys, recon):
-        by.setdefault((k[0], k[1]), {}).setdefault(k[3], []).append(r)
-    for (t, li), boxes in by.items():
-        bl = m["boxes"][f"{t}-{li}"]
-        data = [np.stack(boxes[b]) for b in range(len(bl))]
-        plotfile.write_level(os.path.join(out_dir, m["files"][t]), m["levels"][li],
-                             [(tuple(lo), tuple(hi)) for lo, hi in bl], data, nc)
-    return m
+        units = list(pool.map(read, keys))
+    for k, (d, _, _) in zip(keys, units):
+        if tuple(dims_ld[k[0]][k[1]][k[3]]) != d:
+            raise ValueError(f"{unit_filename(*k)}: shape {d} disagrees with dimensions.raw {dims_ld[k[0]][k[1]][k[3]]}")
+    npairs = np.array([u[1] for u in units], np.int32)
+    stream = np.frombuffer(b"".join(u[2][20:20 + 8 * u[1]] for u in units) or b"\0" * 8, capi.PAIR)
+    udims = [u[0] for u in units]
+    outs = [np.empty((d[2], d[1], d[0]), np.float64) for d in udims]
+    od = capi.box_descs([o.ctypes.data for o in outs], [capi.WC_F64] * len(outs), udims)
+    dp = ctx.decode_plan(od, capi.WC_HOST)
+    dp.decode(stream.ctypes.data, npairs.ctypes.data, capi.WC_HOST)
+    dp.finish()
+    dp.close()
+    it = iter(outs)
+    for t in range(nt):
+        name = out_dir + os.path.basename(os.path.normpath(ri.files[t]))       # path.filename(), src/writeplotfile.cpp:132
+        level_boxes = []
+        for l in range(nl):
+            bl = [(tuple(lo), tuple(lo[k] + dm[k] - 1 for k in range(3))) for lo, dm in zip(locs[t][l], dims_ld[t][l])]
+            level_boxes.append(bl)
+            data = [np.stack([next(it) for _ in range(nc)]) for _ in bl]
+            plotfile.write_level(name, l, bl, data, nc)
+        plotfile.write_header(name, plotfile.header_from_amrexinfo(ri.components, info, t, level_boxes))
+    return ri

@@ -119,12 +119,53 @@ def write_header(plt_dir: str, h: Header) -> None:
         f.write("\n".join(out) + "\n")
 
 
+def header_from_amrexinfo(names, info, t: int, level_boxes, level_dirs=None) -> Header:
+    """The Header amrex::WriteMultiLevelPlotfile writes for timestep `t` of a decompressed run, from the quantities the
+    reference carries in amrexinfo.raw (src/writeplotfile.cpp:138-227 builds the Geometry objects, AMReX's
+    WriteGenericPlotfileHeader prints them).  Same arithmetic, in the same order, in float64:
+      domain of level l   = [0, dim * ref^l - 1]                                  (writeplotfile.cpp:166-172)
+      cell size           = (prob_hi - prob_lo) / n_cells                         (Geometry::define)
+      box extents         = prob_lo + dx * lo  ..  prob_lo + dx * (hi + 1)        (RealBox(box, dx, prob_lo))
+    level_boxes[l] = [(lo, hi)] in index space.  `info` is a sidefiles.AMReXInfo."""
+    nlev = len(level_boxes)
+    g = info.geomcellinfo[t]
+    prob_lo, prob_hi = [float(v) for v in g[:3]], [float(v) for v in g[3:6]]
+    time = float(np.longdouble(info.true_times[t]))       # amrex::Real time = long double -> double
+    dims0 = [info.xDim, info.yDim, info.zDim]
+    # DEVIATION (documented): the reference fills ref_ratios by reading `dim` ints off a Header line that holds one
+    # ratio per coarser LEVEL (src/preprocess.cpp:210-221), so a 2-level plotfile yields [2, 0, 0] and its own `-d` would
+    # build an empty domain for level 1 (yDim * pow(0, 1)).  The side file keeps the reference's bytes; here a zero
+    # entry falls back to the first ratio (AMReX plotfiles refine isotropically), which is what its writer test feeds
+    # in directly (src/writeplotfile.cpp:371: {2, 2, 2}).
+    ratios = [int(r) if int(r) > 0 else int(info.ref_ratios[0]) for r in info.ref_ratios]
+    domains, cell_size, levels = [], [], []
+    for l in range(nlev):
+        n = [int(dims0[k] * pow(float(ratios[k]), l)) for k in range(3)]               # int(xDim * pow(ref, l))
+        domains.append(((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1)))
+        dx = [(prob_hi[k] - prob_lo[k]) / float(n[k]) for k in range(3)]
+        cell_size.append(dx)
+        phys = [[(prob_lo[k] + dx[k] * float(lo[k]), prob_lo[k] + dx[k] * float(hi[k] + 1)) for k in range(3)]
+                for lo, hi in level_boxes[l]]
+        levels.append(dict(level=l, ngrids=len(level_boxes[l]), time=time, step=int(info.level_steps[t][l]),
+                           boxes_phys=phys, path=(level_dirs[l] if level_dirs else f"Level_{l}/Cell")))
+    # one ref_ratio entry per coarser level; AMReX prints ref_ratio[i][0]
+    return Header("HyperCLaw-V1.1", list(names), 3, time, nlev - 1, prob_lo, prob_hi,
+                  [ratios[0]] * (nlev - 1), domains, [int(v) for v in info.level_steps[t][:nlev]], cell_size,
+                  0, 0, levels)
+
+
 def read_level(plt_dir: str, level: int, alloc=None) -> Level:
     """Reads Level_<level>: Cell_H for the box list and FAB offsets, then the Cell_D file images.
     `alloc(nbytes) -> writable uint8 ndarray` lets the caller supply pinned memory (wc_host_alloc)."""
     ldir = os.path.join(plt_dir, f"Level_{level}")
     lines = open(os.path.join(ldir, "Cell_H")).read().split("\n")
     ncomp = int(lines[2])
+    nghost = int(lines[3].split()[0].strip("(),") or 0) if lines[3].strip() else 0
+    if nghost != 0:
+        # the on-disk FAB of a grown MultiFab covers the grown box; the reference reads the valid box out of it
+        # (mfi.validbox(), src/preprocess.cpp:43).  Plotfiles are written without ghost cells; refuse rather than
+        # hand mis-strided slabs to the GPU.
+        raise ValueError(f"{ldir}/Cell_H: nghost = {nghost}; only plotfiles without ghost cells are supported")
     nbox = int(re.match(r"\((\d+)", lines[4]).group(1))
     boxes = []
     for ln in lines[5:5 + nbox]:
@@ -143,7 +184,13 @@ def read_level(plt_dir: str, level: int, alloc=None) -> Level:
             images[fname] = buf
         img = images[fname]
         off = int(off)
-        nl = off + bytes(img[off:off + 256]).index(b"\n") + 1     # end of the ASCII "FAB ..." line
+        nl = off + bytes(img[off:off + 1024]).index(b"\n") + 1    # end of the ASCII "FAB ..." line
+        fab_line = bytes(img[off:nl]).decode("ascii", "replace")
+        fm = _BOX_RE.search(fab_line)
+        if not fm or (tuple(int(fm.group(i)) for i in (1, 2, 3)), tuple(int(fm.group(i)) for i in (4, 5, 6))) != (lo, hi):
+            raise ValueError(f"{ldir}/{fname}@{off}: FAB header box {fab_line.strip()!r} does not match the Cell_H box {lo}-{hi}")
+        if int(fab_line.split()[-1]) != ncomp:
+            raise ValueError(f"{ldir}/{fname}@{off}: FAB has {fab_line.split()[-1]} components, Cell_H says {ncomp}")
         dims = tuple(h - l + 1 for l, h in zip(lo, hi))
         n = dims[0] * dims[1] * dims[2]
         raw = img[nl:nl + 8 * n * ncomp]
