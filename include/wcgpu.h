@@ -133,8 +133,10 @@ typedef enum {
     WC_OPT_COPY_ONLY = 4, /* measurement probe: 1 = wc_plan_compress_to_host issues its H2D / D2H copies with
                              the same chunking but launches no compress kernel (the pair counts of the previous
                              real call size the D2H) -> the host-link ceiling of that call */
-    WC_OPT_INGEST_STATS = 5 /* 1 = the compress kernels also record each unit's min / max of the narrowed
-                               input values (src/preprocess.cpp:82-88), read with wc_plan_unit_stats */
+    WC_OPT_INGEST_STATS = 5, /* 1 = the compress kernels also record each unit's min / max of the narrowed
+                                input values (src/preprocess.cpp:82-88), read with wc_plan_unit_stats */
+    WC_OPT_DECODE_PIPE = 6   /* decompress kernel of the 32^3 / 64^3 cubes: 1 (default) = warp-specialised pipeline
+                                (decode of item k+1 overlaps the stores of item k), 0 = phase-by-phase kernel */
 } wc_option;
 WC_API int wc_set_option(wc_ctx* ctx, int option, int64_t value);
 

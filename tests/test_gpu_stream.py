@@ -98,8 +98,9 @@ def test_dplan_device_stream_from_a_compress_plan(wc, ctx, oracle):
         ctx2.close()
 
 
+@pytest.mark.parametrize("pipe", [1, 0])
 @pytest.mark.parametrize("seg_index", [0, 1])
-def test_dplan_overflow_drop_and_empty_streams(wc, ctx, oracle, seg_index):
+def test_dplan_overflow_drop_and_empty_streams(wc, ctx, oracle, seg_index, pipe):
     """rle_decode's `if (idx < N)` (src/decompressor.cpp:24-27): a pair that jumps past the end is dropped together
     with everything after it; empty streams decode to zeros.  Large units so the index kernels see many chunks."""
     rng = np.random.default_rng(99)
@@ -118,6 +119,7 @@ def test_dplan_overflow_drop_and_empty_streams(wc, ctx, oracle, seg_index):
     outs = [np.full((d[2], d[1], d[0]), 7.0, np.float32) for d in dims]
     od = wc.capi.box_descs([o.ctypes.data for o in outs], [wc.WC_F32] * len(outs), dims)
     ctx.set_option(wc.capi.WC_OPT_SEG_INDEX, seg_index)
+    ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, pipe)
     try:
         dp = ctx.decode_plan(od, wc.WC_HOST)
         dp.decode(pr.ctypes.data, k.ctypes.data, wc.WC_HOST)
@@ -126,6 +128,7 @@ def test_dplan_overflow_drop_and_empty_streams(wc, ctx, oracle, seg_index):
         recon = ctx.decompress_batch(packed)           # the blocking call takes the same index kernel
     finally:
         ctx.set_option(wc.capi.WC_OPT_SEG_INDEX, 0)
+        ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, 1)
     for i, (p, o, d) in enumerate(zip(packed, outs, dims)):
         ob = oracle.decompress_unit(p.runs, p.vals, d)
         assert same_bits(o, ob), (i, d)
@@ -269,3 +272,46 @@ def test_unit_stats_minmax_and_need32(wc, ctx, oracle):
         plan.unit_stats()
     plan.unit_stats(minmax=False)
     plan.close()
+
+
+@pytest.mark.parametrize("pipe", [1, 0])
+def test_decode_kernels_many_units_all_densities(wc, ctx, oracle, pipe):
+    """The cube decode kernels (pipelined and phase-by-phase) over many units per CTA — the pipeline's hand-over of the
+    coefficient array between items (clean-as-you-go, full / empty barriers, descriptor ring) only shows with more
+    units than SMs — at every density: empty, a single pair, sparse, the bench's ~40 %, all kept (K = N, 1024 chunks)."""
+    rng = np.random.default_rng(1234 + pipe)
+    dims = [(32, 32, 32)] * 700 + [(64, 64, 64)] * 45
+    packed = []
+    for i, d in enumerate(dims):
+        n = d[0] * d[1] * d[2]
+        mode = i % 7
+        if mode == 0:
+            k = 0
+        elif mode == 1:
+            k = 1
+        elif mode == 2:
+            k = n                                        # every coefficient kept: runs are all 0
+        else:
+            k = int(rng.integers(1, n // 2))
+        if k == n:
+            runs = np.zeros(k, np.int32)
+        else:
+            # runs with the right total: K kept positions drawn without replacement
+            pos = np.sort(rng.choice(n, size=k, replace=False)) if k else np.zeros(0, np.int64)
+            runs = np.diff(np.concatenate([[-1], pos])).astype(np.int32) - 1
+        packed.append(wc.PackedUnit(d, n, runs, rng.standard_normal(k).astype(np.float32)))
+    pr, kk = dense_stream(wc, packed)
+    outs = [np.full((d[2], d[1], d[0]), 7.0, np.float32) for d in dims]
+    od = wc.capi.box_descs([o.ctypes.data for o in outs], [wc.WC_F32] * len(outs), dims)
+    ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, pipe)
+    try:
+        dp = ctx.decode_plan(od, wc.WC_HOST)
+        for _ in range(2):
+            dp.decode(pr.ctypes.data, kk.ctypes.data, wc.WC_HOST)
+            dp.finish()
+        dp.close()
+    finally:
+        ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, 1)
+    for i in list(range(0, len(dims), 9)) + list(range(690, len(dims))):
+        ob = oracle.decompress_unit(packed[i].runs, packed[i].vals, dims[i])
+        assert same_bits(outs[i], ob), (i, dims[i], packed[i].npairs)

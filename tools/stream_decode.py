@@ -41,9 +41,10 @@ have_phase = hasattr(ctx.lib, "wc_debug_phase_cycles")
 if have_phase:
     ctx.lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 out = (ctypes.c_ulonglong * 6)()
-for seg in (0, 1):
+for seg, pipe in ((0, 1), (0, 0), (1, 1), (1, 0)):
     ctx2 = pkg.Context(0, stream=stream.cuda_stream)
     ctx2.set_option(capi.WC_OPT_SEG_INDEX, seg)
+    ctx2.set_option(capi.WC_OPT_DECODE_PIPE, pipe)
     dp = ctx2.decode_plan(odescs, pkg.WC_DEVICE)
     with torch.cuda.stream(stream):
         for _ in range(3):
@@ -67,9 +68,9 @@ for seg in (0, 1):
         dp.finish()
         st = ctx2.kernel_stats()
         ctx2.set_profile(False)
-    print(f"{which} seg_index={seg}: {ms:.4f} ms/step  {alg / ms / 1e6:.0f} GB/s algorithmic = {alg / ms / 1e6 / peak:.3f} of {peak}",
+    print(f"{which} seg_index={seg} pipe={pipe}: {ms:.4f} ms/step  {alg / ms / 1e6:.0f} GB/s algorithmic = {alg / ms / 1e6 / peak:.3f} of {peak}",
           {k: round(v[1] / 5, 4) for k, v in st.items()})
-    if have_phase:
+    if have_phase and not pipe:
         v = np.array(list(out), dtype=np.float64)
         units = max(v[5], 1)
         for n, c in zip(["zero-fill+barrier", "-", "decode (scan+scatter)", "barrier+prefetch", "inverse+store"], v[:5]):

@@ -20,6 +20,7 @@ WC_F32, WC_F64 = 0, 1
 WC_HOST, WC_DEVICE = 0, 1
 WC_THRESH_PER_UNIT, WC_THRESH_GLOBAL = 0, 1
 WC_OPT_PATH, WC_OPT_PROFILE, WC_OPT_OVERLAP, WC_OPT_SEG_INDEX, WC_OPT_COPY_ONLY, WC_OPT_INGEST_STATS = 0, 1, 2, 3, 4, 5
+WC_OPT_DECODE_PIPE = 6
 WC_PACKED_NEED32 = 1
 WC_CTR_KERNEL_LAUNCHES, WC_CTR_H2D_BYTES, WC_CTR_D2H_BYTES = 0, 1, 2
 

@@ -101,6 +101,7 @@ struct wc_ctx {
     int          opt_seg_index = 0;   // 0 = chunk-parallel k_seg_index2, 1 = one CTA per unit (k_seg_index)
     int          opt_copy_only = 0;   // probe: wc_plan_compress_to_host moves the bytes but skips the kernels
     int          opt_ingest_stats = 0; // compress also records per-unit min / max of the narrowed inputs
+    int          opt_decode_pipe = 1;  // 32^3 / 64^3 cubes decode with the warp-specialised pipeline kernel
     int          sm_count = 0;
     wc_plan*     batch_plan = nullptr; // owner of the memory handed out by wc_compress_batch
     // workspace of the blocking decompress / rmse / primitive calls (grow-only)
@@ -147,6 +148,7 @@ struct wc_plan {
     int    n_xtiles = 0, n_ctiles = 0;
     bool   compressed = false;
     bool   transformed = false;
+    bool   has_stats = false;    // the last compress ran with WC_OPT_INGEST_STATS: UnitState::vmin / vmax are valid
     std::vector<size_t> in_dev_off; // per unit offset in d_in (host inputs)
     // pipelined host path (wc_plan_compress_to_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;
@@ -319,6 +321,9 @@ int wc_set_option(wc_ctx* ctx, int option, int64_t value) {
         return WC_OK;
     case WC_OPT_INGEST_STATS:
         ctx->opt_ingest_stats = value != 0;
+        return WC_OK;
+    case WC_OPT_DECODE_PIPE:
+        ctx->opt_decode_pipe = value != 0;
         return WC_OK;
     case WC_OPT_PROFILE:
         cudaSetDevice(ctx->device);
@@ -767,6 +772,7 @@ int wc_plan_compress(wc_plan* p, double keep, int thresh_mode) {
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = plan_stage_inputs(p);
     if (rc != WC_OK) return rc;
+    p->has_stats = ctx->opt_ingest_stats != 0;
     bool global_mode = thresh_mode == WC_THRESH_GLOBAL;
     rc = plan_forward(p, global_mode);
     if (rc != WC_OK) return rc;
@@ -785,6 +791,7 @@ int wc_plan_transform(wc_plan* p, uint64_t** key_dev) {
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = plan_stage_inputs(p);
     if (rc != WC_OK) return rc;
+    p->has_stats = ctx->opt_ingest_stats != 0;
     rc = plan_forward(p, true);
     if (rc != WC_OK) return rc;
     CTX_CUDA(ctx, launch_global_key(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(), p->n_units, p->d_gkey.as<u64>(),
@@ -891,6 +898,7 @@ int wc_plan_compress_to_host_chunked(wc_plan* p, double keep, wc_packed* out, wc
         return rc;
     }
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    p->has_stats = ctx->opt_ingest_stats != 0;
     const int NCH = 16;
     if (!p->s_h2d) {
         CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
@@ -1072,6 +1080,19 @@ static inline void dec_hash(uint64_t& h1, uint64_t& h2, uint64_t v) {
     h2 = (h2 + v) * 0xC2B2AE3D27D4EB4Full; h2 ^= h2 >> 31;
 }
 
+// the decompress kernel of one fused class list: the pipelined kernel for the literal cubes (unless switched off)
+static cudaError_t launch_decode(wc_ctx* ctx, int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list,
+                                 int n, int* err, int* counter, bool v1_tables) {
+    if (ctx->opt_decode_pipe && pipe_decode_class(fused_cls)) {
+        if (v1_tables) {   // tables by the one-CTA-per-unit index kernel first (WC_OPT_SEG_INDEX = 1)
+            cudaError_t e = launch_seg_index1(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls);
+            if (e != cudaSuccess) return e;
+        }
+        return launch_pipe_decompress(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls, counter);
+    }
+    return launch_fused_decompress(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls, counter, v1_tables);
+}
+
 // A plan that decodes into the same boxes again (keep sweeps of the estimate mode) re-launches from the
 // device tables of the previous call; only all-fused batches without scratch are cached.
 static int relaunch_decompress(wc_ctx* ctx, const DecCache* cache, DevBuf& d_dec_units, DevBuf& d_inv_units,
@@ -1084,10 +1105,8 @@ static int relaunch_decompress(wc_ctx* ctx, const DecCache* cache, DevBuf& d_dec
         if (!cache->fl_n[k]) continue;
         int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
         CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-        CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
-                                              d_inv_units.as<InvUnitDev>(), dl + o, (int)cache->fl_n[k],
-                                              d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls,
-                                              counter, false));
+        CTX_CUDA(ctx, launch_decode(ctx, FL_CLASS[k], d_dec_units.as<DecUnitDev>(), d_inv_units.as<InvUnitDev>(), dl + o,
+                                    (int)cache->fl_n[k], d_err.as<int>(), counter, false));
         o += cache->fl_n[k];
     }
     return WC_OK;
@@ -1222,10 +1241,8 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             }
             int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
             CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-            CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], d_dec_units.as<DecUnitDev>(),
-                                                  d_inv_units.as<InvUnitDev>(), dl + o,
-                                                  (int)fl[k].size(), d_err.as<int>(), ctx->sm_count,
-                                                  ctx->stream, &ctx->ls, counter, v1_tables));
+            CTX_CUDA(ctx, launch_decode(ctx, FL_CLASS[k], d_dec_units.as<DecUnitDev>(), d_inv_units.as<InvUnitDev>(), dl + o,
+                                        (int)fl[k].size(), d_err.as<int>(), counter, v1_tables));
             o += fl[k].size();
         }
     }
@@ -1560,8 +1577,8 @@ static int dplan_launch_range(wc_dplan* dp, int u0, int u1, size_t fi[FL_N]) {
             }
             int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
             CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-            CTX_CUDA(ctx, launch_fused_decompress(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
-                                                  dp->d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls, counter, v1));
+            CTX_CUDA(ctx, launch_decode(ctx, FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
+                                        dp->d_err.as<int>(), counter, v1));
         }
         fi[k] = j;
         if (tab) ++tl;
@@ -1737,7 +1754,7 @@ int wc_plan_unit_stats(wc_plan* p, float* mins, float* maxs, int32_t* need32) {
     if (!p->compressed) return WC_ERR_STATE;
     wc_ctx* ctx = p->ctx;
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
-    if ((mins || maxs) && !ctx->opt_ingest_stats) return WC_ERR_STATE;
+    if ((mins || maxs) && !p->has_stats) return WC_ERR_STATE;
     int rc = plan_read_states(p);
     if (rc != WC_OK) return rc;
     const UnitState* hs = p->h_states.as<UnitState>();

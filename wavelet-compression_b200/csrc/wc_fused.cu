@@ -1275,20 +1275,31 @@ k_seg_index2(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
         bool bad = false;
         uint32_t ttot;
         uint32_t pre = fd_tile_scan<NT>(pr, K - p, s_wt, bad, ttot);
-        // chunk base through the look-back
-        if (tid == 0) {
+        // chunk base through the look-back: warp 0 inspects 32 predecessors per round (one L2 round trip for all
+        // of them instead of one per predecessor) and sums the aggregates in front of the nearest published prefix
+        if (tid < 32) {
             uint32_t base = 0;
             if (c > 0) {
-                st_release_u64(status + item, (1ull << 62) | ttot);
-                for (int k = item - 1; k >= item0; --k) {
-                    u64 v;
-                    do { v = ld_acquire_u64(status + k); } while ((v >> 62) == 0);
-                    base = sat_add(base, (uint32_t)v);
-                    if ((v >> 62) == 2) break;
+                if (tid == 0) st_release_u64(status + item, (1ull << 62) | ttot);
+                int hi = item - 1;                       // nearest predecessor not yet accounted for
+                for (;;) {
+                    const int k = hi - tid;              // lane 0 = nearest
+                    u64 v = 2ull << 62;                  // lanes in front of the unit's first chunk: prefix 0
+                    if (k >= item0) do { v = ld_acquire_u64(status + k); } while ((v >> 62) == 0);
+                    const uint32_t pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                    const int first = pm ? __ffs(pm) - 1 : 32;          // nearest lane holding an inclusive prefix
+                    uint32_t x = tid <= first ? (uint32_t)v : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) x = sat_add(x, __shfl_xor_sync(0xffffffffu, x, o));
+                    base = sat_add(base, x);
+                    if (pm) break;
+                    hi -= 32;
                 }
             }
-            st_release_u64(status + item, (2ull << 62) | sat_add(base, ttot));
-            s_base = base;
+            if (tid == 0) {
+                st_release_u64(status + item, (2ull << 62) | sat_add(base, ttot));
+                s_base = base;
+            }
         }
         __syncthreads();
         const uint32_t base = s_base;
@@ -1822,6 +1833,434 @@ cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dens
     k_dec_prepare<<<1, 1024, 0, st>>>(dec, n_units, dense, npairs, tab_list, tab_n, n_tab_lists, chunk_start, err);
     ls->end(st);
     return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Pipelined decompress for the literal cubes (32^3: S = 1, one item per unit; 64^3: S = 8 slab items)
+// =====================================================================================================
+// k_fused_decompress runs its phases back to back behind CTA-wide barriers: zero-fill, decode (latency bound:
+// dependent loads + shuffle scans + scattered shared-memory stores), inverse + store (bandwidth bound).  With one
+// 128 KB coefficient array per SM nothing overlaps, and a unit costs the SUM of the phases (measured 15-19 k cycles
+// against an HBM floor of ~10 k).  Here the CTA is split into two warp-specialised groups that run concurrently:
+//   DG  warps 0-15   decode: pairs -> coefficient array C
+//   IG  warps 16-31  inverse transform of C -> global stores, and zeroing C behind itself ("clean as you go":
+//                    the separate zero-fill pass and its barrier disappear)
+// C is handed over in NG groups of 4 consecutive x-blocks a (= the 16 segments i' in {4g..4g+3, hx+4g..hx+4g+3}):
+// full[g] (DG -> IG, 16 arrivals: one per DG warp) and empty[g] (IG -> DG, one arrival per IG warp of the group) are
+// CTA-scope mbarriers that complete exactly one phase per item, in strict alternation, so a parity wait is never
+// ambiguous.  DG therefore runs up to one whole item ahead of IG: the decode of item k+1 overlaps the stores of
+// item k, and a unit costs max(decode, inverse) instead of their sum.
+//   A group of 4 x-blocks is the pipeline's grain because it is the store side's coalescing grain: 4 blocks = 8
+//   cells = one 32-byte sector of a float32 row (64 bytes of a float64 row).
+// S = 1 (32^3): no segment table is needed or used.  DG first walks the unit's list once (P1: per-chunk sums of run+1,
+//   32 pairs per chunk; P2: their exclusive prefix in shared memory; P3: the chunk range of every group), then decodes
+//   group after group with the chunks dealt round-robin to its warps (P4): perfectly balanced, every chunk independent.
+//   The second read of the list comes from L1 / L2.  HBM traffic 8K + 4N.
+// S = 8 (64^3 slabs): a slab's pairs are 2X separate sub-ranges of the unit's list, found through the segment table
+//   (written by the compress kernels or by k_seg_index2); a DG warp decodes one segment per group, rotated from group
+//   to group so that the heavy low-pass segments land on different warps.
+// Unit descriptors travel through a ring of 4 slots, published two items ahead by DG's first thread (dfull barriers).
+constexpr int PD_NT   = 1024;   // threads per CTA
+constexpr int PD_NDG  = 512;    // decode group: threads [0, 512); inverse group: [512, 1024)
+constexpr int PD_NDW  = 16;     // warps per group
+constexpr int PD_PAD  = 8;      // padding words per i' slab of C: IG's LDS.64 hit banks 8*al + 4*cq0 + 2*cp2 + {0,1}
+constexpr int PD_RING = 4;
+constexpr int PD_CL   = 1 << 20; // clamp of one pair's run+1 and of a chunk sum (> any ncoef here; keeps u32 sums exact)
+
+template <int S, class G>
+struct PDSmem {
+    static constexpr int NG    = G::hx / 4;                       // groups per item
+    static constexpr int SLAB  = 2 * G::nb * G::Z + PD_PAD;       // words of C per i'
+    static constexpr int CW    = G::X * SLAB;
+    static constexpr int PPG   = G::npairs / NG;                  // IG pair-slots (threads) per group
+    static constexpr int GPP   = PD_NDG / PPG;                    // groups per IG pass
+    static constexpr int C     = 0;
+    static constexpr int CSUM  = C + CW * 4;                      // [2][1032] u32: chunk sums -> exclusive prefix (S = 1),
+                                                                  // double-buffered by item parity: P1 of item k + 1
+                                                                  // writes while slower warps still read item k's in P4
+    static constexpr int RANGE = CSUM + 2 * 1032 * 4;             // [NG][2] int2: chunk range of (group, x half)
+    static constexpr int WT    = RANGE + 16 * 8;                  // [32] u32 scan scratch
+    static constexpr int BARS  = WT + 32 * 4;                     // full[8] empty[8] dfull[4]
+    static constexpr int RINGO = BARS + 20 * 8;                   // [4] FDDesc (88 bytes, 8-byte aligned)
+    static constexpr int TOTAL = RINGO + PD_RING * 96;
+    static_assert(NG <= 8 && PPG * GPP == PD_NDG && NG % GPP == 0, "group geometry");
+    static_assert((G::hz / 2) % 2 == 0 && G::ncq % 2 == 0, "every pair-slot of the cube is a full c-pair");
+};
+
+__device__ __forceinline__ bool mbar_try_wait_cta(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_cta(bar, parity)) { }
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void dg_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(PD_NDG) : "memory"); }
+
+// the ring's producer (DG thread 0 only): item k + 2 is fetched in five stages spread over item k
+template <int S>
+struct PDFetch {
+    const DecUnitDev* dec;
+    const InvUnitDev* inv;
+    const int*        unit_list;
+    int*              work_counter;
+    int               n_items, stride, ui_prev;
+    int               idx, uid, kreg;
+    FDDesc*           slot;
+    __device__ __forceinline__ void a_index() {
+        idx = work_counter ? atomicAdd(work_counter, 1) : ui_prev + stride;
+        ui_prev = idx;
+    }
+    __device__ __forceinline__ void b_unit() {
+        uid = -1;
+        if (idx < n_items) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(uid) : "l"(unit_list + idx / S));
+    }
+    __device__ __forceinline__ void c_copy() {
+        slot->ui  = idx;
+        slot->uid = uid;
+        if (uid >= 0) {
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&slot->du);
+            const char*    s0 = reinterpret_cast<const char*>(dec + uid);
+#pragma unroll
+            for (int b = 0; b < 40; b += 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + b), "l"(s0 + b) : "memory");
+            const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(&slot->iu);
+            const char*    s1 = reinterpret_cast<const char*>(inv + uid);
+#pragma unroll
+            for (int b = 0; b < 32; b += 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1 + b), "l"(s1 + b) : "memory");
+        }
+    }
+    __device__ __forceinline__ void d_count() {          // descriptor has landed: resolve K (may live on the device)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        kreg = 0;
+        if (uid >= 0) {
+            kreg = slot->du.npairs;
+            const int32_t* kp = slot->du.npairs_dev;
+            if (kp) asm volatile("ld.global.s32 %0, [%1];" : "=r"(kreg) : "l"(kp));
+        }
+    }
+    __device__ __forceinline__ void e_publish(uint32_t bar) {
+        slot->K = kreg;
+        mbar_arrive_cta(bar);                              // release: the slot is visible to every waiter
+    }
+};
+
+template <int S, class G>
+__global__ void __launch_bounds__(PD_NT, 1)
+k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
+                  const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
+                  int* __restrict__ work_counter) {
+    typedef PDSmem<S, G> SM;
+    constexpr int NG = SM::NG, SLAB = SM::SLAB;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* const    C     = reinterpret_cast<float*>(smem + SM::C);
+    uint32_t* const csum2 = reinterpret_cast<uint32_t*>(smem + SM::CSUM);
+    int2* const     range = reinterpret_cast<int2*>(smem + SM::RANGE);
+    uint32_t* const wt    = reinterpret_cast<uint32_t*>(smem + SM::WT);
+    FDDesc* const   ring  = reinterpret_cast<FDDesc*>(smem + SM::RINGO);
+    const uint32_t  bars  = smem_u32(smem + SM::BARS);
+    auto full  = [&](int g) { return bars + 8u * (uint32_t)g; };
+    auto empty = [&](int g) { return bars + 64u + 8u * (uint32_t)g; };
+    auto dfull = [&](int r) { return bars + 128u + 8u * (uint32_t)r; };
+    const int tid = threadIdx.x, warp = (tid >> 5) & (PD_NDW - 1), lane = tid & 31;
+    const int n_items = n_list * S;
+
+    if (tid == 0) {
+        for (int g = 0; g < NG; ++g) {
+            mbar_init(full(g), PD_NDW);                 // one arrival per DG warp
+            mbar_init(empty(g), SM::PPG / 32);          // one arrival per IG warp of the group
+        }
+        for (int r = 0; r < PD_RING; ++r) mbar_init(dfull(r), 1);
+    }
+    {   // C starts out zeroed (rle_decode's zero fill, src/decompressor.cpp:17); IG keeps it that way
+        float4* c4 = reinterpret_cast<float4*>(C);
+        for (int i = tid; i < SM::CW / 4; i += PD_NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    if (tid < PD_NDG) {
+        // ================================ decode group ================================
+        PDFetch<S> fe;
+        fe.dec = dec; fe.inv = inv; fe.unit_list = unit_list; fe.work_counter = work_counter;
+        fe.n_items = n_items; fe.stride = (int)gridDim.x; fe.ui_prev = (int)blockIdx.x - (int)gridDim.x;
+        fe.idx = 0; fe.uid = -1; fe.kreg = 0; fe.slot = ring;
+        if (tid == 0) {
+            for (int j = 0; j < 2; ++j) {               // items 0 and 1 of this CTA
+                fe.slot = &ring[j];
+                fe.a_index(); fe.b_unit(); fe.c_copy(); fe.d_count(); fe.e_publish(dfull(j));
+            }
+        }
+        bool bad = false;
+        for (int k = 0;; ++k) {
+            mbar_wait_cta(dfull(k & 3), (uint32_t)(k >> 2) & 1u);
+            const FDDesc& d = ring[k & 3];
+            if (d.ui >= n_items) break;
+            const DecUnitDev du = d.du;
+            const int K = d.K;
+            const uint32_t total = (uint32_t)du.total;
+            const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
+            const uint32_t epar = (uint32_t)(k - 1) & 1u;          // parity of empty[] completed by item k - 1
+            if (tid == 0) { fe.slot = &ring[(k + 2) & 3]; fe.a_index(); }
+
+            if constexpr (S == 1) {
+                constexpr uint32_t YZ = G::Y * G::Z;
+                uint32_t* const csum = csum2 + (k & 1) * 1032;
+                // ---- P1: chunk sums (32 pairs per chunk, 4 chunks per warp and trip) ----
+                const int nch = (K + 31) >> 5;
+                for (int c0 = warp * 4; c0 < nch; c0 += PD_NDW * 4) {
+                    int2 pv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int p = (c0 + j) * 32 + lane;
+                        pv[j] = p < K ? __ldg(pairs + p) : make_int2(0, 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool in = (c0 + j) * 32 + lane < K;
+                        if (in && pv[j].x < 0) bad = true;                 // negative run: flagged, counts as 0, skipped
+                        uint32_t inc = (in && pv[j].x >= 0) ? min((uint32_t)pv[j].x + 1u, (uint32_t)PD_CL) : 0u;
+                        inc = __reduce_add_sync(0xffffffffu, inc);
+                        if (lane == 0 && c0 + j < nch) csum[c0 + j] = min(inc, (uint32_t)PD_CL);
+                    }
+                }
+                if (tid == 0) fe.b_unit();
+                {   // L2 prefetch of the NEXT item's list (its descriptor was published an item ago)
+                    const FDDesc& dn = ring[(k + 1) & 3];
+                    if (dn.ui < n_items) {
+                        const char* base = reinterpret_cast<const char*>(dn.du.pairs);
+                        const int nlines = (dn.K * 8 + 127) / 128;
+                        for (int i = tid; i < nlines; i += PD_NDG)
+                            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)i * 128));
+                    }
+                }
+                dg_barrier();
+                // ---- P2: exclusive prefix E[0 .. nch] of the chunk sums, in place ----
+                {
+                    const int e0 = 2 * tid;
+                    const uint32_t a = e0 < nch ? csum[e0] : 0u, b = e0 + 1 < nch ? csum[e0 + 1] : 0u;
+                    uint32_t inc = a + b;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    if (lane == 31) wt[warp] = inc;
+                    dg_barrier();
+                    uint32_t w = lane < PD_NDW ? wt[lane] : 0u;
+#pragma unroll
+                    for (int o = 1; o < PD_NDW; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+                        if (lane >= o) w += v;
+                    }
+                    const uint32_t wpre = warp ? __shfl_sync(0xffffffffu, w, warp - 1) : 0u;
+                    const uint32_t ex = wpre + inc - (a + b);
+                    if (e0 < nch) csum[e0] = ex;
+                    if (e0 + 1 < nch) csum[e0 + 1] = ex + a;
+                    if (e0 < nch && e0 + 2 >= nch) csum[nch] = ex + a + b;      // E[nch] = the whole list (nch <= 1024)
+                    if (nch == 0 && tid == 0) csum[0] = 0u;
+                }
+                dg_barrier();
+                // ---- P3: chunk range of every (group, x half): chunks that may hold a pair in [lo, lo + 4 YZ) ----
+                if (tid < 2 * NG) {
+                    const uint32_t lo = (uint32_t)((tid & 1) * G::hx + 4 * (tid >> 1)) * YZ, hi = lo + 4u * YZ;
+                    int l = 0, r = nch;                     // first c with E[c + 1] > lo
+                    while (l < r) { const int m = (l + r) >> 1; if (csum[m + 1] > lo) r = m; else l = m + 1; }
+                    const int clo = l;
+                    l = clo; r = nch;                       // first c with E[c] >= hi
+                    while (l < r) { const int m = (l + r) >> 1; if (csum[m] >= hi) r = m; else l = m + 1; }
+                    range[tid] = make_int2(clo, l);
+                }
+                if (tid == 0) fe.c_copy();
+                dg_barrier();
+                // ---- P4: decode group after group, chunks dealt round-robin to the warps ----
+#pragma unroll 1
+                for (int g = 0; g < NG; ++g) {
+                    if (k > 0) mbar_wait_cta(empty(g), epar);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int2 rg = range[2 * g + h];
+                        const uint32_t lo = (uint32_t)(h * G::hx + 4 * g) * YZ, hi = lo + 4u * YZ;
+#pragma unroll 1
+                        for (int c = rg.x + warp; c < rg.y; c += 2 * PD_NDW) {
+                            // two chunks per trip: independent load + scan chains
+                            const int c1 = c + PD_NDW;
+                            const int p0 = c * 32 + lane, p1 = c1 * 32 + lane;
+                            int2 v0 = make_int2(-1, 0), v1 = make_int2(-1, 0);
+                            if (p0 < K) v0 = __ldg(pairs + p0);
+                            if (c1 < rg.y && p1 < K) v1 = __ldg(pairs + p1);
+                            uint32_t i0 = v0.x >= 0 ? min((uint32_t)v0.x + 1u, (uint32_t)PD_CL) : 0u;
+                            uint32_t i1 = v1.x >= 0 ? min((uint32_t)v1.x + 1u, (uint32_t)PD_CL) : 0u;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t a0 = __shfl_up_sync(0xffffffffu, i0, o);
+                                const uint32_t a1 = __shfl_up_sync(0xffffffffu, i1, o);
+                                if (lane >= o) { i0 += a0; i1 += a1; }
+                            }
+                            const uint32_t f0 = csum[c] + i0 - 1u;
+                            if (v0.x >= 0 && f0 >= lo && f0 < hi && f0 < total)
+                                C[(f0 / YZ) * SLAB + (f0 % YZ)] = __int_as_float(v0.y);
+                            if (c1 < rg.y) {
+                                const uint32_t f1 = csum[c1] + i1 - 1u;
+                                if (v1.x >= 0 && f1 >= lo && f1 < hi && f1 < total)
+                                    C[(f1 / YZ) * SLAB + (f1 % YZ)] = __int_as_float(v1.y);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(full(g));
+                    if (tid == 0 && g == 1) fe.d_count();
+                }
+            } else {
+                // ---- slab item: one segment per warp and group, found through the unit's segment table ----
+                const uint32_t rank = (uint32_t)(d.ui % S);
+                const int2* tab = reinterpret_cast<const int2*>(du.coef);
+                constexpr uint32_t seglen = (uint32_t)G::seglen;
+                auto seg_of = [&](int g, int& ip, int& sy) {
+                    const int e = (warp + 5 * g) & 15;             // rotation: heavy segments move from warp to warp
+                    ip = (e >> 3) * G::hx + 4 * g + ((e >> 1) & 3);
+                    sy = e & 1;
+                    return ip * (2 * S) + sy * S + (int)rank;
+                };
+                int2 te = make_int2(0, 0);
+                if (lane < 2 * NG) {
+                    int ip, sy;
+                    const int m = seg_of(lane >> 1, ip, sy);
+                    te = __ldg(tab + m + (lane & 1));
+                }
+#pragma unroll 1
+                for (int g = 0; g < NG; ++g) {
+                    int ip, sy;
+                    const int m = seg_of(g, ip, sy);
+                    const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * g), e0y = __shfl_sync(0xffffffffu, te.y, 2 * g);
+                    const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * g + 1);
+                    if (k > 0) mbar_wait_cta(empty(g), epar);
+                    float* const cseg = C + ip * SLAB + sy * G::seglen;
+                    const uint32_t fseg = (uint32_t)m * seglen;
+                    uint32_t base = (uint32_t)e0y;
+#pragma unroll 1
+                    for (int c0 = e0x; c0 < e1x; c0 += 256) {
+                        if (e1x - c0 <= 128) fd_decode_chunks<4>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
+                        else                 fd_decode_chunks<8>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(full(g));
+                    if (tid == 0) {
+                        if (g == 1) fe.b_unit();
+                        if (g == 3) fe.c_copy();
+                        if (g == 5) fe.d_count();
+                    }
+                }
+            }
+            if (tid == 0) fe.e_publish(dfull((k + 2) & 3));
+        }
+        if (bad) atomicOr(err, 1);
+    } else {
+        // ================================ inverse group ================================
+        const int q = tid - PD_NDG;
+        constexpr int o1 = G::hx * SLAB, o2 = G::nb * G::Z, o3 = G::hz;
+        for (int k = 0;; ++k) {
+            mbar_wait_cta(dfull(k & 3), (uint32_t)(k >> 2) & 1u);
+            const FDDesc& d = ring[k & 3];
+            if (d.ui >= n_items) break;
+            const InvUnitDev iu = d.iu;
+            const int b0 = (d.ui % S) * G::nb;
+            const bool f64 = iu.dtype == WC_F64;
+            const size_t es = f64 ? 8 : 4;
+            const size_t row_bytes = (size_t)G::X * es, plane_bytes = row_bytes * G::Y;
+            char* const out0 = static_cast<char*>(iu.out) + (size_t)(2 * b0) * row_bytes;
+#pragma unroll 1
+            for (int pass = 0; pass < NG / SM::GPP; ++pass) {
+                const int g   = pass * SM::GPP + q / SM::PPG;
+                const int idx = q % SM::PPG;
+                // lanes: cp2 (1 bit), cq0 (1), al (2) -> conflict-free LDS.64 / STS.64; then the upper cq bits, then bl
+                const int cp2 = idx & 1, cq0 = (idx >> 1) & 1, al = (idx >> 2) & 3, rest = idx >> 4;
+                const int cqh = rest % (G::ncq / 2), bl = rest / (G::ncq / 2);
+                const int a = 4 * g + al, cpi = 2 * (cq0 + 2 * cqh) + cp2;
+                float* const csrc = C + a * SLAB + bl * G::Z + 2 * cpi;
+                mbar_wait_cta(full(g), (uint32_t)k & 1u);
+                float2 v[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    float2* const pc = reinterpret_cast<float2*>(csrc + (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3);
+                    v[o] = *pc;
+                    *pc  = make_float2(0.f, 0.f);                     // clean as you go
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ihaar_pair2(v[2 * j], v[2 * j + 1]);                 // X
+#pragma unroll
+                for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+                    for (int xi = 0; xi < 2; ++xi) ihaar_pair2(v[zi * 4 + xi], v[zi * 4 + 2 + xi]);   // Y
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ihaar_pair2(v[j], v[4 + j]);                         // Z
+                char* p0 = out0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes + (size_t)a * 2 * es;
+#pragma unroll
+                for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+                    for (int yi = 0; yi < 2; ++yi) {
+                        const float2 lo = v[zi * 4 + yi * 2], hi = v[zi * 4 + yi * 2 + 1];   // xi = 0, 1
+                        char* pa = p0 + zi * plane_bytes + yi * row_bytes;        // block c:   planes 4cpi + zi
+                        char* pb = pa + 2 * plane_bytes;                          // block c+1: planes 4cpi + 2 + zi
+                        if (f64) {
+                            __stcs(reinterpret_cast<double2*>(pa), make_double2((double)lo.x, (double)hi.x));
+                            __stcs(reinterpret_cast<double2*>(pb), make_double2((double)lo.y, (double)hi.y));
+                        } else {
+                            __stcs(reinterpret_cast<float2*>(pa), make_float2(lo.x, hi.x));
+                            __stcs(reinterpret_cast<float2*>(pb), make_float2(lo.y, hi.y));
+                        }
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cta(empty(g));
+            }
+        }
+    }
+}
+
+template <int S, class G>
+static cudaError_t launch_pd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n, int* err,
+                             int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter) {
+    auto kern = k_pipe_decompress<S, G>;
+    constexpr int smem = PDSmem<S, G>::TOTAL;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (long long)n * S;
+    const int nc = (int)(sm_count < items ? sm_count : items);
+    ls->begin(kid, st);
+    kern<<<nc, PD_NT, smem, st>>>(dec, inv, list, n, err, work_counter);
+    ls->end(st);
+    return cudaGetLastError();
+}
+
+// the one-CTA-per-unit index kernel on its own (WC_OPT_SEG_INDEX = 1 in front of the pipelined decode kernel)
+cudaError_t launch_seg_index1(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n, int* err,
+                              int sm_count, cudaStream_t st, LaunchStats* ls) {
+    if (n <= 0 || !fused_decode_needs_table(fused_cls)) return cudaSuccess;
+    const int nb = n < 2 * sm_count ? n : 2 * sm_count;
+    ls->begin(KID_SEG_INDEX, st);
+    k_seg_index<512><<<nb, 512, 0, st>>>(dec, inv, list, n, err, fused_decode_slabs(fused_cls));
+    ls->end(st);
+    return cudaGetLastError();
+}
+
+bool pipe_decode_class(int fused_cls) { return fused_cls == FUSED_CLS_CUBE32 || fused_cls == FUSED_CLS_CUBE64; }
+
+cudaError_t launch_pipe_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
+                                   int n_list, int* err, int sm_count, cudaStream_t st, LaunchStats* ls,
+                                   int* work_counter) {
+    if (n_list <= 0) return cudaSuccess;
+    if (fused_cls == FUSED_CLS_CUBE32)
+        return launch_pd<1, SGeom<32, 32, 32, 8, 1>>(KID_PIPE_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    if (fused_cls == FUSED_CLS_CUBE64)
+        return launch_pd<8, SGeom<64, 64, 64, 8, 8>>(KID_PIPE_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    return cudaErrorInvalidValue;
 }
 
 // Which fused-decompress class a unit belongs to (FUSED_CLS_*, 0 = generic): same geometry rules as compress,

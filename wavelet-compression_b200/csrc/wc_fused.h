@@ -48,6 +48,14 @@ cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dens
                                const int* tab_list, const int* tab_n, int n_tab_lists, int* chunk_start, int* err,
                                cudaStream_t st, LaunchStats* ls);
 
+// Warp-specialised, pipelined decompress of the literal cubes (32^3, 64^3): decode and inverse + store overlap.
+bool pipe_decode_class(int fused_cls);
+cudaError_t launch_seg_index1(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n, int* err,
+                              int sm_count, cudaStream_t st, LaunchStats* ls);
+cudaError_t launch_pipe_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
+                                   int n_list, int* err, int sm_count, cudaStream_t st, LaunchStats* ls,
+                                   int* work_counter);
+
 #ifdef WC_PHASE_PROFILE
 cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset);
 #endif

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <filesystem>
 #include <string>
+#include <thread>
 #include <unistd.h>
 
 #include "box-structs.h"   // the reference's: Grid3D, Box3D, multiBox3D, CompressedWavelet
@@ -117,6 +118,70 @@ int main() {
                 }
         std::filesystem::remove_all(d1);
         std::filesystem::remove_all(d2);
+    }
+    {   // estimate_all: the `-estimate` body on one plan (src/modes.cpp:236-324); BASELINE config 1 known answer
+        // (bundled plt00074, level 0, temp, keep = 0.999f: 4096 + 8 pairs, RMSE 0, 168 + 88 bytes of .xz)
+        std::vector<multiBox3D> boxes(2);
+        boxes[0].push_back(Box3D(16, 32, 64, 3902.4f));
+        boxes[1].push_back(Box3D(8, 4, 2, 16.0f));
+        Estimate e = estimate_all(boxes, 1, (double)0.999f, 2);
+        REQUIRE(e.npairs.size() == 2 && e.npairs[0] == 4096 && e.npairs[1] == 8);
+        REQUIRE(e.mean_rmse.size() == 1 && e.mean_rmse[0] == 0.0 && e.adjusted_loss[0] == 0.0);
+        REQUIRE(e.min_values[0] == 16.0f && e.max_values[0] == 3902.4f);
+        REQUIRE(e.xz_bytes == 168 + 88);
+        REQUIRE(!e.need32[0] && !e.need32[1]);
+        REQUIRE(e.h2d_bytes == sizeof(float) * (16 * 32 * 64 + 8 * 4 * 2));     // the boxes cross the bus exactly once
+        // a non-trivial level: per-box RMSE of estimate_all == the per-box calls, need32 on large values
+        std::vector<multiBox3D> lvl;
+        for (int b = 0; b < 5; ++b) {
+            multiBox3D mb;
+            for (int c = 0; c < 2; ++c) {
+                Box3D bx(32, 32, 32);
+                for (int k = 0; k < 32; ++k)
+                    for (int j = 0; j < 32; ++j)
+                        for (int i = 0; i < 32; ++i)
+                            bx(i, j, k) = (c ? 90000.f : -3.f) + 50.f * std::sin(0.1f * i + b) * std::cos(0.07f * j) * std::sin(0.05f * k + c);
+                mb.push_back(std::move(bx));
+            }
+            lvl.push_back(std::move(mb));
+        }
+        double keep = (double)0.999f;
+        Estimate f = estimate_all(lvl, 2, keep, 3);
+        std::string d = scratch_dir();
+        std::vector<int> comps = { 0, 1 };
+        std::vector<double> acc(2, 0.0);
+        size_t xz = 0;
+        for (int b = 0; b < 5; ++b) {
+            auto cw = compress(lvl[b], comps, keep, 0, 0, b, d);
+            multiBox3D regen;
+            for (int c = 0; c < 2; ++c) {
+                std::string path = detail::unit_path(d, 0, 0, c, b);
+                xz += (size_t)std::filesystem::file_size(path);
+                regen.push_back(decompress(path, 0, 0, c, b));
+                REQUIRE((int)cw[c].rle_encoded.size() == f.npairs[(size_t)b * 2 + c]);
+                REQUIRE(cw[c].need32 == (bool)f.need32[(size_t)b * 2 + c]);
+            }
+            std::vector<double> r = calc_rmse_per_box(lvl[b], regen, 2);
+            acc[0] += r[0]; acc[1] += r[1];
+        }
+        REQUIRE(f.need32[1] && !f.need32[0]);
+        REQUIRE(f.xz_bytes == xz);
+        for (int c = 0; c < 2; ++c) REQUIRE(std::fabs(f.mean_rmse[c] - acc[c] / 5.0) <= 1e-12 * (acc[c] / 5.0));
+        std::filesystem::remove_all(d);
+    }
+    {   // one host thread per GPU: contexts are per (thread, device) — two threads on device 0 must not share one
+        std::atomic<int> ok { 0 };
+        auto work = [&] {
+            set_device(0);
+            Box3D b1(2, 2, 2, 0.0f), b2(2, 2, 2, 3.5f);
+            multiBox3D t1, t2;
+            t1.push_back(b1.clone()); t2.push_back(b2.clone());
+            for (int i = 0; i < 20; ++i)
+                if (calc_rmse_per_box(t1, t2, 1)[0] == 3.5) ++ok;
+        };
+        std::thread a(work), b(work);
+        a.join(); b.join();
+        REQUIRE(ok == 40);
     }
     std::printf(g_fail ? "dropin FAILED (%d)\n" : "dropin ok\n", g_fail);
     return g_fail ? 1 : 0;

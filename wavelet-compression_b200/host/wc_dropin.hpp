@@ -16,18 +16,30 @@
 // keep the reference's behaviour: a message and exit(EXIT_FAILURE) (src/compressor.cpp:263-266,
 // src/decompressor.cpp:170-231) — the C ABI underneath never exits by itself.
 //
-// Beyond the per-box calls there are batched entry points (compress_all / decompress_all) that hand a
-// whole run to the GPU in one wc_compress_batch and spread the LZMA stage over host threads — the
-// per-box calls are correct but launch-bound, the batch calls are what a ported modes.cpp should use.
+// Beyond the per-box calls there are batched entry points that a ported modes.cpp should use (the per-box calls
+// are correct but launch-bound):
+//   compress_all    one plan for the whole run; the chunk callback of wc_plan_compress_to_host_chunked feeds a pool
+//                   of LZMA writer threads WHILE later chunks are still on the GPU (src/modes.cpp:100-103)
+//   decompress_all  host threads xz-decode the files, the pair bytes form one dense stream for a decode plan
+//                   (wc_dplan_*), one pipelined GPU pass (src/modes.cpp:151-166)
+//   estimate_all    the `-estimate` body (src/modes.cpp:236-291) on ONE plan: boxes cross the bus once, compress ->
+//                   decompress -> RMSE -> min/max -> need32 stay in HBM, only the packed pairs come back for the
+//                   LZMA size estimate (overlapped the same way)
+// A threaded multi-GPU host calls wcgpu::set_device(g) once per thread; contexts are per (thread, device).
 #pragma once
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
+#include <limits>
 #include <fstream>
+#include <functional>
+#include <mutex>
+#include <queue>
 #include <string>
 #include <thread>
 #include <utility>
@@ -178,6 +190,62 @@ inline CompressedWavelet to_compressed_wavelet(const wc_packed& p) {
     return cw;
 }
 
+// A small pool of worker threads for the LZMA stage: jobs are queued from the GPU thread (chunk callback) and run
+// concurrently with the rest of the GPU batch; wait() drains the queue.
+class WorkerPool {
+    std::vector<std::thread>          workers_;
+    std::queue<std::function<void()>> jobs_;
+    std::mutex                        mu_;
+    std::condition_variable           cv_, idle_;
+    size_t                            active_ = 0;
+    bool                              stop_   = false;
+
+public:
+    explicit WorkerPool(unsigned threads) {
+        if (threads == 0) threads = std::thread::hardware_concurrency();
+        if (threads == 0) threads = 1;
+        for (unsigned t = 0; t < threads; ++t)
+            workers_.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> job;
+                    {
+                        std::unique_lock<std::mutex> lk(mu_);
+                        cv_.wait(lk, [this] { return stop_ || !jobs_.empty(); });
+                        if (jobs_.empty()) return;
+                        job = std::move(jobs_.front());
+                        jobs_.pop();
+                        ++active_;
+                    }
+                    job();
+                    {
+                        std::lock_guard<std::mutex> lk(mu_);
+                        --active_;
+                    }
+                    idle_.notify_all();
+                }
+            });
+    }
+    void submit(std::function<void()> job) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            jobs_.push(std::move(job));
+        }
+        cv_.notify_one();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        idle_.wait(lk, [this] { return jobs_.empty() && active_ == 0; });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+};
+
 template <class F>
 inline void parallel_for(size_t n, unsigned threads, F f) {
     if (threads <= 1 || n <= 1) {
@@ -194,6 +262,9 @@ inline void parallel_for(size_t n, unsigned threads, F f) {
 }
 
 } // namespace detail
+
+// The device the calling thread's wcgpu:: calls run on (default 0).  One host thread per GPU.
+inline void set_device(int device) { detail::thread_contexts().current = device; }
 
 // ---- compress(): src/compressor.cpp:192-297 ----------------------------------------------------------
 inline std::vector<CompressedWavelet> compress(multiBox3D& box, std::vector<int> components, double keep,
@@ -279,57 +350,90 @@ inline std::vector<double> calc_rmse_per_box(const multiBox3D& actual, const mul
 inline double calc_adj_loss(double rmse, double range) { return rmse / range; }   // src/calc-loss.cpp:49-51
 
 // ---- batched: the whole (t, level, box) x component iteration of src/modes.cpp:100-103 in one call -----------
-// boxes[t][lev][box] is the reference's AllData::boxes.  One GPU batch, then the .xz files are written by
-// `lzma_threads` host threads (each file is independent; 0 = hardware_concurrency).
+namespace detail {
+struct UnitKey { int t, l, b, c; size_t ci; };
+
+// on_unit(unit index, packed unit with host pairs) runs on the pool's threads, fed chunk by chunk while the GPU is
+// still working on later chunks; returns after every job has finished.  The plan stays alive for the caller.
+template <class F>
+inline wc_plan* compress_units_overlapped(wc_ctx* ctx, const std::vector<wc_box_desc>& in, double keep,
+                                          std::vector<wc_packed>& out, unsigned lzma_threads, F on_unit) {
+    wc_plan* plan = nullptr;
+    check(wc_plan_create(ctx, in.data(), (int)in.size(), WC_HOST, &plan), ctx, "wc_plan_create");
+    out.resize(in.size());
+    WorkerPool pool(lzma_threads);
+    struct Ctx { WorkerPool* pool; F* f; } cb { &pool, &on_unit };
+    auto trampoline = [](void* user, int first, int n, const wc_packed* units) {
+        Ctx* c = static_cast<Ctx*>(user);
+        for (int j = 0; j < n; ++j) {
+            const wc_packed u = units[j];                 // pinned pairs stay valid until the next compress on the plan
+            const size_t    i = (size_t)first + j;
+            c->pool->submit([c, i, u] { (*c->f)(i, u); });
+        }
+    };
+    check(wc_plan_compress_to_host_chunked(plan, keep, out.data(), trampoline, &cb), ctx, "wc_plan_compress_to_host_chunked");
+    pool.wait();
+    return plan;
+}
+} // namespace detail
+
+// boxes[t][lev][box] is the reference's AllData::boxes.  The .xz files are written by `lzma_threads` host threads
+// (each file is independent; 0 = hardware_concurrency) while the GPU is still compressing later chunks.
 inline void compress_all(std::vector<std::vector<std::vector<multiBox3D>>>& boxes, const std::vector<int>& comp_idxs,
                          double keep, const std::string& compressed_dir, unsigned lzma_threads = 0) {
     wc_ctx* ctx = detail::context();
-    struct Key { int t, l, b, c; };
-    std::vector<Key>         keys;
-    std::vector<wc_box_desc> in;
+    std::vector<detail::UnitKey> keys;
+    std::vector<wc_box_desc>     in;
     for (size_t t = 0; t < boxes.size(); ++t)
         for (size_t l = 0; l < boxes[t].size(); ++l)
             for (size_t b = 0; b < boxes[t][l].size(); ++b)
                 for (size_t c = 0; c < comp_idxs.size(); ++c) {
                     const Box3D& bx = boxes[t][l][b][c];
-                    keys.push_back({ (int)t, (int)l, (int)b, comp_idxs[c] });
+                    keys.push_back({ (int)t, (int)l, (int)b, comp_idxs[c], c });
                     in.push_back({ detail::box_data(bx), WC_F32, (int32_t)bx.width(), (int32_t)bx.height(), (int32_t)bx.depth() });
                 }
-    std::vector<wc_packed> out(in.size());
-    detail::check(wc_compress_batch(ctx, in.data(), (int)in.size(), WC_HOST, keep, WC_THRESH_PER_UNIT, out.data(), WC_HOST),
-                  ctx, "wc_compress_batch");
-    unsigned nt = lzma_threads ? lzma_threads : std::thread::hardware_concurrency();
-    detail::parallel_for(out.size(), nt, [&](size_t i) {
-        detail::write_unit_file(detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b), out[i]);
+    std::vector<wc_packed> out;
+    wc_plan* plan = detail::compress_units_overlapped(ctx, in, keep, out, lzma_threads, [&](size_t i, const wc_packed& u) {
+        detail::write_unit_file(detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b), u);
     });
+    wc_plan_destroy(plan);
 }
 
 // Mirror of the decompress loop of src/modes.cpp:151-166: reads + xz-decodes every file with host threads, one
-// GPU batch for U + I, returns regen_boxes[t][lev][box] = multiBox3D.
+// pipelined GPU pass for U + I through a decode plan, returns regen_boxes[t][lev][box] = multiBox3D.
 inline std::vector<std::vector<std::vector<multiBox3D>>>
 decompress_all(const std::string& compressed_dir, const std::vector<std::vector<int>>& box_counts,
                const std::vector<int>& comp_idxs, unsigned lzma_threads = 0) {
     wc_ctx* ctx = detail::context();
-    struct Key { int t, l, b, c; size_t ci; };
-    std::vector<Key> keys;
+    std::vector<detail::UnitKey> keys;
     for (size_t t = 0; t < box_counts.size(); ++t)
         for (size_t l = 0; l < box_counts[t].size(); ++l)
             for (int b = 0; b < box_counts[t][l]; ++b)
                 for (size_t c = 0; c < comp_idxs.size(); ++c) keys.push_back({ (int)t, (int)l, b, comp_idxs[c], c });
     std::vector<std::string> raw(keys.size());
+    std::vector<wc_packed>   in(keys.size());
     unsigned nt = lzma_threads ? lzma_threads : std::thread::hardware_concurrency();
     detail::parallel_for(keys.size(), nt, [&](size_t i) {
-        raw[i] = detail::xz_decode_file(detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b));
+        const std::string path = detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b);
+        raw[i] = detail::xz_decode_file(path);
+        in[i]  = detail::parse_unit(raw[i], path);        // validated: sizes, counts, payload length
     });
     std::vector<std::vector<std::vector<multiBox3D>>> regen(box_counts.size());
     for (size_t t = 0; t < box_counts.size(); ++t) {
         regen[t].resize(box_counts[t].size());
         for (size_t l = 0; l < box_counts[t].size(); ++l) regen[t][l].resize((size_t)box_counts[t][l]);
     }
-    std::vector<wc_packed>  in(keys.size());
+    // one dense pair stream (the files' bytes [20, 20+8K) back to back) + the counts: what wc_dplan_decode takes
+    size_t total = 0;
+    for (auto const& p : in) total += (size_t)p.npairs;
+    std::vector<wc_pair>    stream(total ? total : 1);
+    std::vector<int32_t>    counts(keys.size());
     std::vector<wc_box_out> out(keys.size());
+    size_t off = 0;
     for (size_t i = 0; i < keys.size(); ++i) {
-        in[i] = detail::parse_unit(raw[i], detail::unit_path(compressed_dir, keys[i].t, keys[i].l, keys[i].c, keys[i].b));
+        if (in[i].npairs) std::memcpy(stream.data() + off, raw[i].data() + 20, 8 * (size_t)in[i].npairs);
+        off += (size_t)in[i].npairs;
+        counts[i] = in[i].npairs;
         const int32_t* h = in[i].shape;
         multiBox3D& mb = regen[keys[i].t][keys[i].l][keys[i].b];
         if (mb.size() < comp_idxs.size()) mb.resize(comp_idxs.size());
@@ -337,9 +441,86 @@ decompress_all(const std::string& compressed_dir, const std::vector<std::vector<
         Box3D& bx = mb[keys[i].ci];
         out[i] = { bx.data_size() ? &bx(0, 0, 0) : nullptr, WC_F32, h[0], h[1], h[2] };
     }
-    detail::check(wc_decompress_batch(ctx, in.data(), (int)in.size(), WC_HOST, out.data(), WC_HOST), ctx,
-                  "wc_decompress_batch");
+    wc_dplan* dp = nullptr;
+    detail::check(wc_dplan_create(ctx, out.data(), (int)out.size(), WC_HOST, &dp), ctx, "wc_dplan_create");
+    detail::check(wc_dplan_decode(dp, stream.data(), counts.data(), WC_HOST), ctx, "wc_dplan_decode");
+    detail::check(wc_dplan_finish(dp), ctx, "wc_dplan_finish");
+    wc_dplan_destroy(dp);
     return regen;
+}
+
+// ---- estimate: the body of `-estimate` (src/modes.cpp:236-324) on one plan, device-resident ------------------
+struct Estimate {
+    std::vector<double> mean_rmse;      // per component: std::accumulate(rmse) / size            src/modes.cpp:284-285
+    std::vector<double> adjusted_loss;  // per component: calc_adj_loss(mean_rmse, max - min)     src/modes.cpp:289
+    std::vector<float>  min_values, max_values;   // per component, the reference's running extrema incl. its initial
+                                                  // values FLT_MAX / FLT_MIN                      src/preprocess.cpp:30-31,82-88
+    std::vector<int>    npairs;         // per unit (box-major, component-minor)
+    std::vector<char>   need32;         // per unit: CompressedWavelet::need32                     src/compressor.cpp:224-229
+    size_t              xz_bytes = 0;   // total size of the .xz streams (what calc_size(scratch_dir) sums, :321)
+    uint64_t            h2d_bytes = 0;  // bytes the call moved host -> device (the boxes, once)
+};
+
+// boxes = AllData::boxes[0][0] (one file, one level: src/modes.cpp:215-233); num_components = boxes[b].size().
+inline Estimate estimate_all(const std::vector<multiBox3D>& boxes, int num_components, double keep, unsigned lzma_threads = 0) {
+    wc_ctx* ctx = detail::context();
+    std::vector<wc_box_desc> in;
+    for (auto const& mb : boxes)
+        for (int c = 0; c < num_components; ++c)
+            in.push_back({ detail::box_data(mb[c]), WC_F32, (int32_t)mb[c].width(), (int32_t)mb[c].height(), (int32_t)mb[c].depth() });
+    const size_t n = in.size();
+    Estimate est;
+    uint64_t h2d0 = 0, h2d1 = 0;
+    wc_get_counter(ctx, WC_CTR_H2D_BYTES, &h2d0);
+    detail::check(wc_set_option(ctx, WC_OPT_INGEST_STATS, 1), ctx, "wc_set_option");
+    std::vector<size_t>    xz(n, 0);
+    std::vector<wc_packed> out;
+    wc_plan* plan = detail::compress_units_overlapped(ctx, in, keep, out, lzma_threads, [&](size_t i, const wc_packed& u) {
+        xz[i] = detail::xz_encode(detail::serialize(u)).size();      // the size of the file compress() would write
+    });
+    wc_set_option(ctx, WC_OPT_INGEST_STATS, 0);
+    // U, I, R in HBM: reconstruct into device boxes, RMSE against the plan's own (device) inputs
+    size_t cells = 0;
+    for (auto const& d : in) cells += (size_t)d.nx * d.ny * d.nz;
+    void* dbuf = nullptr;
+    detail::check(wc_device_alloc(ctx, &dbuf, sizeof(float) * (cells ? cells : 1)), ctx, "wc_device_alloc");
+    std::vector<wc_box_out>  rec(n);
+    std::vector<wc_box_desc> recd(n);
+    size_t off = 0;
+    for (size_t i = 0; i < n; ++i) {
+        float* p = static_cast<float*>(dbuf) + off;
+        rec[i]  = { p, WC_F32, in[i].nx, in[i].ny, in[i].nz };
+        recd[i] = { p, WC_F32, in[i].nx, in[i].ny, in[i].nz };
+        off += (size_t)in[i].nx * in[i].ny * in[i].nz;
+    }
+    std::vector<double>  rmse(n ? n : 1);
+    std::vector<float>   lo(n ? n : 1), hi(n ? n : 1);
+    std::vector<int32_t> n32(n ? n : 1);
+    detail::check(wc_plan_decompress(plan, rec.data(), WC_DEVICE), ctx, "wc_plan_decompress");
+    detail::check(wc_plan_rmse(plan, recd.data(), rmse.data()), ctx, "wc_plan_rmse");
+    detail::check(wc_plan_unit_stats(plan, lo.data(), hi.data(), n32.data()), ctx, "wc_plan_unit_stats");
+    wc_device_free(ctx, dbuf);
+    wc_plan_destroy(plan);
+    wc_get_counter(ctx, WC_CTR_H2D_BYTES, &h2d1);
+    est.h2d_bytes = h2d1 - h2d0;
+    est.min_values.assign((size_t)num_components, std::numeric_limits<float>::max());
+    est.max_values.assign((size_t)num_components, std::numeric_limits<float>::min());   // sic: smallest POSITIVE float
+    std::vector<double> sum((size_t)num_components, 0.0);
+    for (size_t i = 0; i < n; ++i) {
+        const size_t c = i % (size_t)num_components;
+        if (lo[i] < est.min_values[c]) est.min_values[c] = lo[i];
+        if (hi[i] > est.max_values[c]) est.max_values[c] = hi[i];
+        sum[c] += rmse[i];                                   // left to right, as std::accumulate
+        est.npairs.push_back(out[i].npairs);
+        est.need32.push_back((char)(n32[i] != 0));
+        est.xz_bytes += xz[i];
+    }
+    for (int c = 0; c < num_components; ++c) {
+        const double mean = boxes.empty() ? 0.0 : sum[(size_t)c] / (double)boxes.size();
+        est.mean_rmse.push_back(mean);
+        est.adjusted_loss.push_back(calc_adj_loss(mean, est.max_values[(size_t)c] - est.min_values[(size_t)c]));
+    }
+    return est;
 }
 
 } // namespace wcgpu
