@@ -259,6 +259,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libwcgpu has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -544,7 +545,8 @@ def main():
                "same_pair_counts_as_device_run": same,
                "h2d_ceiling_gbs": world * field_bytes / (c_ms * 1e-3) / 1e9, "copy_only_ms_per_step": c_ms,
                "frac_of_ceiling": c_ms / e_ms,
-               "ceiling_note": "WC_OPT_COPY_ONLY: the same call, same pinned buffers and chunking, no kernels"}
+               "ceiling_note": "WC_OPT_COPY_ONLY: the same call, same pinned buffers and chunking, no kernels",
+               "cpu_affinity": affinity}
         hplan.close()
         lib.wc_host_free(hp64)
         # float32 host boxes: what the reference's host actually holds (multiBox3D, src/preprocess.cpp:78)
@@ -627,6 +629,19 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def pin_to_gpu_numa_node(index):
+    """Bind this rank's threads to the CPUs NVML reports as closest to its GPU BEFORE any pinned allocation, so that the
+    e2e legs' pinned buffers come from the GPU's own NUMA node (first-touch) and the copies do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cpus": len(os.sched_getaffinity(0)), "how": "nvmlDeviceSetCpuAffinity"}
+    except Exception as e:  # noqa: BLE001
+        return {"cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None, "how": "unchanged: " + repr(e)[:80]}
 
 
 def lzma_leg(pkg, ctx):

@@ -33,7 +33,8 @@ CASES = {
     "config2": dict(counts=[[2, 2], [2, 2]], locs=[[0, 0, 0], [16, 32, 64]] * 4, dims=[[16, 32, 64], [8, 4, 2]] * 4,
                     files=["../tests/plt00074", "../tests/plt00075"], min_level=0, max_level=1,
                     comps=["temp", "pressure"], comp_idxs=[0, 1],
-                    geom=[[0.6, 0.5, 0.4, 0.8, 0.9, 1.0]] * 2, ref=[2, 0, 0], times=["0.2219392", "0.3874982"],
+                    # the time lines exactly as the bundled Headers spell them (parsed to long double by operator>>)
+                    geom=[[0.6, 0.5, 0.4, 0.8, 0.9, 1.0]] * 2, ref=[2, 0, 0], times=["0.2219392", "0.38749820000000001"],
                     steps=[[1200, 1500], [1800, 2000]], xyz=[256, 512, 256]),
     "ragged": dict(counts=[[3, 1, 0], [2, 2, 5], [1, 0, 4]],
                    locs=[[i, 2 * i, 100 + i] for i in range(18)], dims=[[8 + i, 4, 2 * i + 2] for i in range(18)],

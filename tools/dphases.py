@@ -22,7 +22,7 @@ offs = np.concatenate([[0], np.cumsum(ncoef)])
 odescs = pkg.capi.box_descs([rec.data_ptr() + 4 * int(o) for o in offs[:-1]], [pkg.WC_F32] * len(sdims), sdims)
 lib = ctx.lib
 lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
-out = (ctypes.c_ulonglong * 6)()
+out = (ctypes.c_ulonglong * 8)()
 with torch.cuda.stream(stream):
     plan.compress(bench.KEEP)
     for _ in range(3): plan.decompress(odescs, pkg.WC_DEVICE)

@@ -17,7 +17,7 @@ if len(sys.argv) > 2 and sys.argv[2].isdigit(): sel = sel[:int(sys.argv[2])]   #
 plan = ctx.plan(descs[sel], pkg.WC_DEVICE)
 lib = ctx.lib
 lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
-out = (ctypes.c_ulonglong * 6)()
+out = (ctypes.c_ulonglong * 8)()
 with torch.cuda.stream(stream):
     for _ in range(3): plan.compress(bench.KEEP)
     torch.cuda.synchronize()

@@ -1115,25 +1115,30 @@ static int relaunch_decompress(wc_ctx* ctx, const DecCache* cache, DevBuf& d_dec
 // Segment tables of one slab-decoded class list with the chunk-parallel index kernel.  K is known on the
 // host here (blocking API): chunk_start is built on the host and uploaded.
 static int build_tables_chunked(wc_ctx* ctx, int fused_cls, const std::vector<DecUnitDev>& du, const std::vector<int>& list,
-                                const DecUnitDev* d_dec, const InvUnitDev* d_inv, const int* d_list, int* d_err) {
+                                const DecUnitDev* d_dec, const InvUnitDev* d_inv, int* d_err) {
     const int n = (int)list.size();
-    std::vector<int> cs(n + 1);
-    long long items = 0;
+    std::vector<int>  cs(n + 1);
+    std::vector<int2> rec;
     for (int j = 0; j < n; ++j) {
-        cs[j] = (int)items;
+        cs[j] = (int)rec.size();
         const int k = du[list[j]].npairs;
-        items += k > 0 ? (k + SEG_INDEX_CHUNK - 1) / SEG_INDEX_CHUNK : 1;
+        const int nch = k > 0 ? (k + SEG_INDEX_CHUNK - 1) / SEG_INDEX_CHUNK : 1;
+        for (int c = 0; c < nch; ++c) rec.push_back(make_int2(list[j], c));
     }
-    cs[n] = (int)items;
-    CTX_CUDA(ctx, ctx->ws_chunk.reserve(sizeof(int) * (size_t)(n + 1)));
-    CTX_CUDA(ctx, ctx->ws_status.reserve(sizeof(u64) * (size_t)std::max<long long>(items, 1)));
+    cs[n] = (int)rec.size();
+    const size_t items = rec.size();
+    CTX_CUDA(ctx, ctx->ws_chunk.reserve(sizeof(int) * (size_t)(n + 1) + 16 + sizeof(int2) * std::max<size_t>(items, 1)));
+    CTX_CUDA(ctx, ctx->ws_status.reserve(sizeof(u64) * std::max<size_t>(items, 1)));
     CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->ws_chunk.p, cs.data(), sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CTX_CUDA(ctx, cudaMemsetAsync(ctx->ws_status.p, 0, sizeof(u64) * (size_t)std::max<long long>(items, 1), ctx->stream));
+    int*  d_cs  = ctx->ws_chunk.as<int>();
+    int2* d_rec = reinterpret_cast<int2*>(ctx->ws_chunk.as<char>() + align_up(sizeof(int) * (size_t)(n + 1), 16));
+    CTX_CUDA(ctx, cudaMemcpyAsync(d_cs, cs.data(), sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (items) CTX_CUDA(ctx, cudaMemcpyAsync(d_rec, rec.data(), sizeof(int2) * items, cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaMemsetAsync(ctx->ws_status.p, 0, sizeof(u64) * std::max<size_t>(items, 1), ctx->stream));
     int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
     CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-    CTX_CUDA(ctx, launch_seg_index2(fused_cls, d_dec, d_inv, d_list, n, ctx->ws_chunk.as<int>(), items,
-                                    ctx->ws_status.as<u64>(), counter, d_err, ctx->sm_count, ctx->stream, &ctx->ls));
+    CTX_CUDA(ctx, launch_seg_index2(fused_cls, d_dec, d_inv, d_rec, d_cs, 0, n, (long long)items, ctx->ws_status.as<u64>(),
+                                    counter, d_err, ctx->sm_count, ctx->stream, &ctx->ls));
     return WC_OK;
 }
 
@@ -1234,7 +1239,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
                 for (int i : fl[k]) all_without = all_without && !slab_tab[i];
                 if (all_without) {
                     int rc = build_tables_chunked(ctx, FL_CLASS[k], du, fl[k], d_dec_units.as<DecUnitDev>(),
-                                                  d_inv_units.as<InvUnitDev>(), dl + o, d_err.as<int>());
+                                                  d_inv_units.as<InvUnitDev>(), d_err.as<int>());
                     if (rc != WC_OK) return rc;
                     v1_tables = false;
                 }
@@ -1403,7 +1408,8 @@ struct wc_dplan {
     std::vector<long long> st_prefix[FL_N];   // per listed unit: items bound in front of it (sub-list launches)
     int       n_tab_lists = 0;
     size_t    tab_floats = 0, status_items = 0, chunk_ints = 0;
-    DevBuf d_dec, d_inv, d_lists, d_tab, d_chunk, d_status, d_err, d_stage_out, d_pairs, d_npairs, d_tabn, d_counter;
+    DevBuf d_dec, d_inv, d_lists, d_tab, d_chunk, d_status, d_err, d_stage_out, d_pairs, d_npairs, d_tabn, d_counter,
+        d_items, d_itemoff;
     PinBuf h_err;
     unsigned counter_next = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -1516,6 +1522,17 @@ int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_sp
     DP_RESERVE(dp->d_tabn, sizeof(int) * std::max<size_t>(tabn.size(), 1));
     DP_RESERVE(dp->d_chunk, sizeof(int) * std::max<size_t>(dp->chunk_ints, 1));
     DP_RESERVE(dp->d_status, sizeof(u64) * std::max<size_t>(dp->status_items, 1));
+    DP_RESERVE(dp->d_items, sizeof(int2) * std::max<size_t>(dp->status_items, 1));
+    DP_RESERVE(dp->d_itemoff, sizeof(long long) * FL_N);
+    {
+        std::vector<long long> ioff;
+        for (int k = 0; k < FL_N; ++k)
+            if (!dp->fl[k].empty() && fused_decode_needs_table(FL_CLASS[k])) ioff.push_back((long long)dp->st_off[k]);
+        if (!ioff.empty())
+            if ((e = cudaMemcpyAsync(dp->d_itemoff.p, ioff.data(), sizeof(long long) * ioff.size(), cudaMemcpyHostToDevice,
+                                     ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "dplan sync");   // ioff is a local
+    }
 #undef DP_RESERVE
     if (n_units) {
         if ((e = cudaMemcpyAsync(dp->d_dec.p, du.data(), sizeof(DecUnitDev) * n_units, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
@@ -1538,6 +1555,8 @@ int wc_dplan_destroy(wc_dplan* dp) {
     if (dp->s_h2d) { cudaStreamSynchronize(dp->s_h2d); cudaStreamDestroy(dp->s_h2d); }
     if (dp->s_d2h) { cudaStreamSynchronize(dp->s_d2h); cudaStreamDestroy(dp->s_d2h); }
     for (cudaEvent_t e : dp->ev) cudaEventDestroy(e);
+    dp->d_items.release();
+    dp->d_itemoff.release();
     DevBuf* bufs[] = { &dp->d_dec, &dp->d_inv, &dp->d_lists, &dp->d_tab, &dp->d_chunk, &dp->d_status, &dp->d_err,
                        &dp->d_stage_out, &dp->d_pairs, &dp->d_npairs, &dp->d_tabn, &dp->d_counter, &dp->g_coef,
                        &dp->g_dec, &dp->g_inv, &dp->g_tiles, &dp->g_ptiles, &dp->g_psum, &dp->g_list };
@@ -1566,10 +1585,10 @@ static int dplan_launch_range(wc_dplan* dp, int u0, int u1, size_t fi[FL_N]) {
                 if (ctx->opt_seg_index == 0) {
                     int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
                     CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-                    CTX_CUDA(ctx, launch_seg_index2(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
-                                                    dp->d_chunk.as<int>() + dp->cs_off[k] + fi[k],
-                                                    dp->st_prefix[k][j] - dp->st_prefix[k][fi[k]],
-                                                    dp->d_status.as<u64>() + dp->st_off[k] + dp->st_prefix[k][fi[k]],
+                    CTX_CUDA(ctx, launch_seg_index2(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(),
+                                                    dp->d_items.as<int2>() + dp->st_off[k], dp->d_chunk.as<int>() + dp->cs_off[k],
+                                                    (int)fi[k], (int)j, dp->st_prefix[k][j] - dp->st_prefix[k][fi[k]],
+                                                    dp->d_status.as<u64>() + dp->st_off[k],
                                                     counter, dp->d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls));
                 } else {
                     v1 = true;
@@ -1666,7 +1685,8 @@ int wc_dplan_decode(wc_dplan* dp, const wc_pair* pairs, const int32_t* npairs, i
         if (dp->status_items && ctx->opt_seg_index == 0)
             CTX_CUDA(ctx, cudaMemsetAsync(dp->d_status.p, 0, sizeof(u64) * dp->status_items, ctx->stream));
         CTX_CUDA(ctx, launch_dec_prepare(dp->d_dec.as<DecUnitDev>(), n, d_pairs, d_npairs, dp->d_lists.as<int>(),
-                                         dp->d_tabn.as<int>(), dp->n_tab_lists, dp->d_chunk.as<int>(), dp->d_err.as<int>(),
+                                         dp->d_tabn.as<int>(), dp->n_tab_lists, dp->d_items.as<int2>(), dp->d_chunk.as<int>(),
+                                         dp->d_itemoff.as<long long>(), dp->d_err.as<int>(),
                                          ctx->stream, &ctx->ls));
     }
     size_t fi[FL_N] = {};

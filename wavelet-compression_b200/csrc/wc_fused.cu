@@ -229,7 +229,7 @@ __device__ __forceinline__ void st_pair_pred(bool p, int2* addr, int run, float 
 // Only in builds with -DWC_PHASE_PROFILE (make PHASE_PROFILE=1): the read-modify-writes cost thread 0 some
 // 600 cycles per unit.
 #ifdef WC_PHASE_PROFILE
-__device__ unsigned long long g_phase_cycles[1024][6];
+__device__ unsigned long long g_phase_cycles[1024][8];
 #define WC_PHASE_CLOCK(t) long long t = clock64()
 #else
 #define WC_PHASE_CLOCK(t) do { } while (0)
@@ -1013,15 +1013,15 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
 
 #ifdef WC_PHASE_PROFILE
 // debug: sums over CTAs of the phase cycle counters; reset = zero them afterwards
-cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset) {
-    static unsigned long long h[1024][6];
+cudaError_t debug_phase_cycles(unsigned long long out[8], bool reset) {
+    static unsigned long long h[1024][8];
     cudaError_t e = cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h));
     if (e != cudaSuccess) return e;
-    for (int p = 0; p < 6; ++p) out[p] = 0;
+    for (int p = 0; p < 8; ++p) out[p] = 0;
     for (int c = 0; c < 1024; ++c)
-        for (int p = 0; p < 6; ++p) out[p] += h[c][p];
+        for (int p = 0; p < 8; ++p) out[p] += h[c][p];
     if (reset) {
-        static unsigned long long z[1024][6];
+        static unsigned long long z[1024][8];
         e = cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
     }
     return e;
@@ -1234,29 +1234,22 @@ __device__ __forceinline__ void st_release_u64(u64* p, u64 v) {
 template <int NT>
 __global__ void __launch_bounds__(NT, 3)
 k_seg_index2(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
-             const int* __restrict__ unit_list, int n_list, const int* __restrict__ chunk_start,
+             const int2* __restrict__ items /* (unit id, chunk) per work item, unit-major, compact */,
+             const int* __restrict__ rec_start /* first item of every listed unit; [n] = total */, int j0, int j1,
              u64* __restrict__ status, int* __restrict__ work_counter, int* __restrict__ err, int slabs) {
     static_assert(NT * FD_PPT == SEG_CHUNK, "one tile per chunk");
     __shared__ uint32_t s_wt[32];
     __shared__ int s_item;
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x;
-    const int cs0 = chunk_start[0];                      // sub-list launches: items are relative to the first unit
-    const int n_items = chunk_start[n_list] - cs0;
+    const int first = rec_start[j0], n_items = rec_start[j1] - first;      // the listed units [j0, j1)
     for (;;) {
         if (tid == 0) s_item = atomicAdd(work_counter, 1);
         __syncthreads();
-        const int item = s_item;
-        if (item >= n_items) break;
-        // listed unit j with chunk_start[j] <= item < chunk_start[j + 1]
-        int lo = 0, hi = n_list;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(chunk_start + mid) - cs0 <= item) lo = mid; else hi = mid;
-        }
-        const int item0 = __ldg(chunk_start + lo) - cs0, nch = __ldg(chunk_start + lo + 1) - cs0 - item0;
-        const int c = item - item0;
-        const int uid = unit_list[lo];
+        if (s_item >= n_items) break;
+        const int item = first + s_item;
+        const int2 it = __ldg(items + item);
+        const int uid = it.x, c = it.y, item0 = item - c;     // the unit's chunks are consecutive items
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
         FGeom g;
@@ -1352,7 +1345,6 @@ k_seg_index2(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
             if (last)
                 for (int m = (int)dsl.div((uint32_t)gl) + 1; m <= nseg; ++m) tab[m] = make_int2(gk, gl);
         }
-        (void)nch;
         __syncthreads();     // s_item / s_wt / s_base are rewritten by the next item
     }
 }
@@ -1364,9 +1356,10 @@ k_seg_index2(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
 __global__ void __launch_bounds__(1024)
 k_dec_prepare(DecUnitDev* __restrict__ dec, int n_units, const wc_pair* __restrict__ dense,
               const int32_t* __restrict__ npairs, const int* __restrict__ tab_list, const int* __restrict__ tab_n,
-              int n_tab_lists, int* __restrict__ chunk_start, int* __restrict__ err) {
+              int n_tab_lists, int2* __restrict__ items, int* __restrict__ rec_start,
+              const long long* __restrict__ item_off /* per list: offset of its records / status words (host-known bound) */,
+              int* __restrict__ err) {
     __shared__ long long s_w[32];
-    __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto block_scan = [&](long long v, long long& tot) -> long long {     // exclusive
         long long inc = v;
@@ -1377,56 +1370,61 @@ k_dec_prepare(DecUnitDev* __restrict__ dec, int n_units, const wc_pair* __restri
         }
         if (lane == 31) s_w[warp] = inc;
         __syncthreads();
-        long long wpre = 0, t = 0;
-        for (int i = 0; i < 32; ++i) { const long long x = s_w[i]; if (i < warp) wpre += x; t += x; }
-        tot = t;
+        long long w = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long x = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += x;
+        }
+        tot = __shfl_sync(0xffffffffu, w, 31);
+        const long long wpre = warp ? __shfl_sync(0xffffffffu, w, warp - 1) : 0;
         __syncthreads();
         return wpre + inc - v;
     };
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < n_units; i0 += 1024) {
-        const int i = i0 + tid;
-        int k = 0;
-        if (i < n_units) {
-            k = npairs[i];
+    // every thread owns a contiguous run of units: independent loads, ONE block scan
+    {
+        const int per = (n_units + 1023) / 1024, i0 = tid * per, i1 = min(i0 + per, n_units);
+        long long mine = 0;
+        for (int i = i0; i < i1; ++i) {
+            int k = npairs[i];
             if (k < 0 || k > dec[i].total) { atomicOr(err, 1); k = 0; }
+            mine += k;
         }
         long long tot;
-        const long long ex = block_scan((long long)k, tot);
-        if (i < n_units) {
-            dec[i].pairs      = dense + (s_carry + ex);
+        long long off = block_scan(mine, tot);
+        for (int i = i0; i < i1; ++i) {
+            int k = npairs[i];
+            if (k < 0 || k > dec[i].total) k = 0;
+            dec[i].pairs      = dense + off;
             dec[i].npairs     = k;
             dec[i].npairs_dev = nullptr;
+            off += k;
         }
-        __syncthreads();
-        if (tid == 0) s_carry += tot;
-        __syncthreads();
     }
-    // chunk_start of every slab-decoded class list, back to back (each list has its own n + 1 entries)
-    int lo = 0, co = 0;
+    __syncthreads();
+    // index work items (unit id, chunk) of every slab-decoded class list
+    int lo = 0;
     for (int l = 0; l < n_tab_lists; ++l) {
         const int n = tab_n[l];
-        if (tid == 0) s_carry = 0;
-        __syncthreads();
-        for (int j0 = 0; j0 < n; j0 += 1024) {
-            const int j = j0 + tid;
-            long long nch = 0;
-            if (j < n) {
-                const int k = dec[tab_list[lo + j]].npairs;      // written above by this CTA
-                nch = k > 0 ? (k + SEG_CHUNK - 1) / SEG_CHUNK : 1;
-            }
-            long long tot;
-            const long long ex = block_scan(nch, tot);
-            if (j < n) chunk_start[co + j] = (int)(s_carry + ex);
-            __syncthreads();
-            if (tid == 0) s_carry += tot;
-            __syncthreads();
+        const int per = (n + 1023) / 1024, j0 = tid * per, j1 = min(j0 + per, n);
+        long long mine = 0;
+        for (int j = j0; j < j1; ++j) {
+            const int k = dec[tab_list[lo + j]].npairs;      // written above by this CTA
+            mine += k > 0 ? (k + SEG_CHUNK - 1) / SEG_CHUNK : 1;
         }
-        if (tid == 0) chunk_start[co + n] = (int)s_carry;
+        long long tot;
+        long long at = block_scan(mine, tot);
+        int2* const rec = items + item_off[l];
+        int* const  rs  = rec_start + lo + l;               // list l owns n + 1 entries
+        for (int j = j0; j < j1; ++j) {
+            const int uid = tab_list[lo + j], k = dec[uid].npairs;
+            const int nch = k > 0 ? (k + SEG_CHUNK - 1) / SEG_CHUNK : 1;
+            rs[j] = (int)at;
+            for (int c = 0; c < nch; ++c) rec[at + c] = make_int2(uid, c);
+            at += nch;
+        }
+        if (tid == 0) rs[n] = (int)tot;
         lo += n;
-        co += n + 1;
-        __syncthreads();
     }
 }
 
@@ -1812,25 +1810,25 @@ int fused_decode_slabs(int fused_cls) {
     return 1;
 }
 
-cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
-                              int n_list, const int* chunk_start, long long items_bound, u64* status,
+cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int2* items,
+                              const int* rec_start, int j0, int j1, long long items_bound, u64* status,
                               int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls) {
-    if (n_list <= 0) return cudaSuccess;
+    if (items_bound <= 0) return cudaSuccess;
     const long long slots = 3ll * sm_count;
-    const int nb = (int)(items_bound < slots ? (items_bound > 0 ? items_bound : 1) : slots);
+    const int nb = (int)(items_bound < slots ? items_bound : slots);
     ls->begin(KID_SEG_INDEX2, st);
-    k_seg_index2<512><<<nb, 512, 0, st>>>(dec, inv, unit_list, n_list, chunk_start, status, work_counter, err,
+    k_seg_index2<512><<<nb, 512, 0, st>>>(dec, inv, items, rec_start, j0, j1, status, work_counter, err,
                                           fused_decode_slabs(fused_cls));
     ls->end(st);
     return cudaGetLastError();
 }
 
 cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
-                               const int* tab_list, const int* tab_n, int n_tab_lists, int* chunk_start, int* err,
-                               cudaStream_t st, LaunchStats* ls) {
+                               const int* tab_list, const int* tab_n, int n_tab_lists, int2* items, int* rec_start,
+                               const long long* item_off, int* err, cudaStream_t st, LaunchStats* ls) {
     if (n_units <= 0) return cudaSuccess;
     ls->begin(KID_DEC_PREPARE, st);
-    k_dec_prepare<<<1, 1024, 0, st>>>(dec, n_units, dense, npairs, tab_list, tab_n, n_tab_lists, chunk_start, err);
+    k_dec_prepare<<<1, 1024, 0, st>>>(dec, n_units, dense, npairs, tab_list, tab_n, n_tab_lists, items, rec_start, item_off, err);
     ls->end(st);
     return cudaGetLastError();
 }
@@ -1852,10 +1850,11 @@ cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dens
 // item k, and a unit costs max(decode, inverse) instead of their sum.
 //   A group of 4 x-blocks is the pipeline's grain because it is the store side's coalescing grain: 4 blocks = 8
 //   cells = one 32-byte sector of a float32 row (64 bytes of a float64 row).
-// S = 1 (32^3): no segment table is needed or used.  DG first walks the unit's list once (P1: per-chunk sums of run+1,
-//   32 pairs per chunk; P2: their exclusive prefix in shared memory; P3: the chunk range of every group), then decodes
-//   group after group with the chunks dealt round-robin to its warps (P4): perfectly balanced, every chunk independent.
-//   The second read of the list comes from L1 / L2.  HBM traffic 8K + 4N.
+// S = 1 (32^3): no segment table is needed or used.  Every DG warp owns a contiguous run of the unit's 32-pair chunks
+//   and walks it twice, eight chunks per trip (eight 256-byte loads in flight per warp): P1 sums run+1 per chunk, P2
+//   (one warp-shuffle scan over <= 1024 sums) gives every chunk its starting flat index, P3 re-reads the chunks from
+//   L1 / L2, scans inside the chunk and scatters; before its first write into a group's rows a warp waits for IG to
+//   have handed that group back.  Perfectly balanced, every chunk independent.  HBM traffic 8K + 4N.
 // S = 8 (64^3 slabs): a slab's pairs are 2X separate sub-ranges of the unit's list, found through the segment table
 //   (written by the compress kernels or by k_seg_index2); a DG warp decodes one segment per group, rotated from group
 //   to group so that the heavy low-pass segments land on different warps.
@@ -2009,26 +2008,35 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
             const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
             const uint32_t epar = (uint32_t)(k - 1) & 1u;          // parity of empty[] completed by item k - 1
             if (tid == 0) { fe.slot = &ring[(k + 2) & 3]; fe.a_index(); }
+            WC_PHASE_CLOCK(tp0);
+#ifdef WC_PHASE_PROFILE
+            long long dg_wait = 0;
+#endif
 
             if constexpr (S == 1) {
                 constexpr uint32_t YZ = G::Y * G::Z;
                 uint32_t* const csum = csum2 + (k & 1) * 1032;
-                // ---- P1: chunk sums (32 pairs per chunk, 4 chunks per warp and trip) ----
+                // Every warp owns a CONTIGUOUS run of the unit's chunks (32 pairs each) and walks it twice, 8 chunks per
+                // trip so that eight 256-byte loads are in flight per warp: P1 sums run+1 per chunk, P2 turns the sums
+                // into every chunk's starting flat index, P3 re-reads the chunks (L1 / L2) and scatters.
                 const int nch = (K + 31) >> 5;
-                for (int c0 = warp * 4; c0 < nch; c0 += PD_NDW * 4) {
-                    int2 pv[4];
+                const int cpw = (nch + PD_NDW - 1) / PD_NDW, cw0 = warp * cpw, cw1 = min(cw0 + cpw, nch);
+                // ---- P1: chunk sums ----
+#pragma unroll 1
+                for (int c0 = cw0; c0 < cw1; c0 += 8) {
+                    int2 pv[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 8; ++j) {
                         const int p = (c0 + j) * 32 + lane;
-                        pv[j] = p < K ? __ldg(pairs + p) : make_int2(0, 0);
+                        pv[j] = (c0 + j < cw1 && p < K) ? __ldg(pairs + p) : make_int2(0, 0);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const bool in = (c0 + j) * 32 + lane < K;
+                    for (int j = 0; j < 8; ++j) {
+                        const bool in = c0 + j < cw1 && (c0 + j) * 32 + lane < K;
                         if (in && pv[j].x < 0) bad = true;                 // negative run: flagged, counts as 0, skipped
                         uint32_t inc = (in && pv[j].x >= 0) ? min((uint32_t)pv[j].x + 1u, (uint32_t)PD_CL) : 0u;
                         inc = __reduce_add_sync(0xffffffffu, inc);
-                        if (lane == 0 && c0 + j < nch) csum[c0 + j] = min(inc, (uint32_t)PD_CL);
+                        if (lane == 0 && c0 + j < cw1) csum[c0 + j] = min(inc, (uint32_t)PD_CL);
                     }
                 }
                 if (tid == 0) fe.b_unit();
@@ -2042,6 +2050,7 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                     }
                 }
                 dg_barrier();
+                WC_PHASE_CLOCK(tp1);
                 // ---- P2: exclusive prefix E[0 .. nch] of the chunk sums, in place ----
                 {
                     const int e0 = 2 * tid;
@@ -2067,57 +2076,67 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                     if (e0 < nch && e0 + 2 >= nch) csum[nch] = ex + a + b;      // E[nch] = the whole list (nch <= 1024)
                     if (nch == 0 && tid == 0) csum[0] = 0u;
                 }
-                dg_barrier();
-                // ---- P3: chunk range of every (group, x half): chunks that may hold a pair in [lo, lo + 4 YZ) ----
-                if (tid < 2 * NG) {
-                    const uint32_t lo = (uint32_t)((tid & 1) * G::hx + 4 * (tid >> 1)) * YZ, hi = lo + 4u * YZ;
-                    int l = 0, r = nch;                     // first c with E[c + 1] > lo
-                    while (l < r) { const int m = (l + r) >> 1; if (csum[m + 1] > lo) r = m; else l = m + 1; }
-                    const int clo = l;
-                    l = clo; r = nch;                       // first c with E[c] >= hi
-                    while (l < r) { const int m = (l + r) >> 1; if (csum[m] >= hi) r = m; else l = m + 1; }
-                    range[tid] = make_int2(clo, l);
-                }
                 if (tid == 0) fe.c_copy();
                 dg_barrier();
-                // ---- P4: decode group after group, chunks dealt round-robin to the warps ----
+                WC_PHASE_CLOCK(tp2);
+                // ---- P3: decode ----
+                uint32_t waited = k > 0 ? 0u : 0xffu;      // groups whose hand-back by IG (item k - 1) this warp has seen
 #pragma unroll 1
-                for (int g = 0; g < NG; ++g) {
-                    if (k > 0) mbar_wait_cta(empty(g), epar);
+                for (int c0 = cw0; c0 < cw1; c0 += 8) {
+                    int2     pv[8];
+                    uint32_t inc[8];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int2 rg = range[2 * g + h];
-                        const uint32_t lo = (uint32_t)(h * G::hx + 4 * g) * YZ, hi = lo + 4u * YZ;
-#pragma unroll 1
-                        for (int c = rg.x + warp; c < rg.y; c += 2 * PD_NDW) {
-                            // two chunks per trip: independent load + scan chains
-                            const int c1 = c + PD_NDW;
-                            const int p0 = c * 32 + lane, p1 = c1 * 32 + lane;
-                            int2 v0 = make_int2(-1, 0), v1 = make_int2(-1, 0);
-                            if (p0 < K) v0 = __ldg(pairs + p0);
-                            if (c1 < rg.y && p1 < K) v1 = __ldg(pairs + p1);
-                            uint32_t i0 = v0.x >= 0 ? min((uint32_t)v0.x + 1u, (uint32_t)PD_CL) : 0u;
-                            uint32_t i1 = v1.x >= 0 ? min((uint32_t)v1.x + 1u, (uint32_t)PD_CL) : 0u;
+                    for (int j = 0; j < 8; ++j) {
+                        const int p = (c0 + j) * 32 + lane;
+                        const bool in = c0 + j < cw1 && p < K;
+                        pv[j] = in ? __ldg(pairs + p) : make_int2(-1, 0);
+                        inc[j] = pv[j].x >= 0 ? min((uint32_t)pv[j].x + 1u, (uint32_t)PD_CL) : 0u;
+                    }
 #pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const uint32_t a0 = __shfl_up_sync(0xffffffffu, i0, o);
-                                const uint32_t a1 = __shfl_up_sync(0xffffffffu, i1, o);
-                                if (lane >= o) { i0 += a0; i1 += a1; }
-                            }
-                            const uint32_t f0 = csum[c] + i0 - 1u;
-                            if (v0.x >= 0 && f0 >= lo && f0 < hi && f0 < total)
-                                C[(f0 / YZ) * SLAB + (f0 % YZ)] = __int_as_float(v0.y);
-                            if (c1 < rg.y) {
-                                const uint32_t f1 = csum[c1] + i1 - 1u;
-                                if (v1.x >= 0 && f1 >= lo && f1 < hi && f1 < total)
-                                    C[(f1 / YZ) * SLAB + (f1 % YZ)] = __int_as_float(v1.y);
-                            }
+                    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t v = __shfl_up_sync(0xffffffffu, inc[j], o);
+                            if (lane >= o) inc[j] += v;
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cta(full(g));
-                    if (tid == 0 && g == 1) fe.d_count();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (c0 + j < cw1) {                                  // warp-uniform
+                            const uint32_t e0 = csum[c0 + j], e1 = csum[c0 + j + 1];
+                            if (e0 < total && e1 > e0) {
+                                // the groups this chunk writes into: rows e0 / YZ .. (e1 - 1) / YZ (clipped to the box)
+                                const uint32_t r0 = e0 / YZ, r1 = min(e1 - 1u, total - 1u) / YZ;
+                                uint32_t need = 0;
+                                for (uint32_t r = r0; r <= r1 && r < r0 + 2u * G::hx; ++r) need |= 1u << ((r % G::hx) >> 2);
+                                need &= ~waited;
+                                while (need) {
+                                    const int g = __ffs(need) - 1;
+                                    WC_PHASE_CLOCK(tw0);
+                                    mbar_wait_cta(empty(g), epar);
+#ifdef WC_PHASE_PROFILE
+                                    if (tid == 0) dg_wait += clock64() - tw0;
+#endif
+                                    waited |= 1u << g;
+                                    need &= need - 1u;
+                                }
+                            }
+                            const uint32_t f = e0 + inc[j] - 1u;
+                            if (pv[j].x >= 0 && f < total) C[(f / YZ) * SLAB + (f % YZ)] = __int_as_float(pv[j].y);
+                        }
+                    }
                 }
+                __syncwarp();
+                if (lane == 0)
+                    for (int g = 0; g < NG; ++g) mbar_arrive_cta(full(g));
+                if (tid == 0) fe.d_count();
+#ifdef WC_PHASE_PROFILE
+                if (tid == 0 && blockIdx.x < 1024) {
+                    const long long t3 = clock64();
+                    unsigned long long* pc = g_phase_cycles[blockIdx.x];
+                    pc[0] += tp1 - tp0; pc[1] += tp2 - tp1; pc[2] += t3 - tp2; pc[3] += dg_wait; pc[5] += 1;
+                }
+#endif
             } else {
                 // ---- slab item: one segment per warp and group, found through the unit's segment table ----
                 const uint32_t rank = (uint32_t)(d.ui % S);
@@ -2141,7 +2160,13 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                     const int m = seg_of(g, ip, sy);
                     const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * g), e0y = __shfl_sync(0xffffffffu, te.y, 2 * g);
                     const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * g + 1);
-                    if (k > 0) mbar_wait_cta(empty(g), epar);
+                    if (k > 0) {
+                        WC_PHASE_CLOCK(tw0);
+                        mbar_wait_cta(empty(g), epar);
+#ifdef WC_PHASE_PROFILE
+                        if (tid == 0) dg_wait += clock64() - tw0;
+#endif
+                    }
                     float* const cseg = C + ip * SLAB + sy * G::seglen;
                     const uint32_t fseg = (uint32_t)m * seglen;
                     uint32_t base = (uint32_t)e0y;
@@ -2158,6 +2183,12 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                         if (g == 5) fe.d_count();
                     }
                 }
+#ifdef WC_PHASE_PROFILE
+                if (tid == 0 && blockIdx.x < 1024) {
+                    unsigned long long* pc = g_phase_cycles[blockIdx.x];
+                    pc[2] += clock64() - tp0; pc[3] += dg_wait; pc[5] += 1;
+                }
+#endif
             }
             if (tid == 0) fe.e_publish(dfull((k + 2) & 3));
         }
@@ -2185,7 +2216,9 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                 const int cqh = rest % (G::ncq / 2), bl = rest / (G::ncq / 2);
                 const int a = 4 * g + al, cpi = 2 * (cq0 + 2 * cqh) + cp2;
                 float* const csrc = C + a * SLAB + bl * G::Z + 2 * cpi;
+                WC_PHASE_CLOCK(ti0);
                 mbar_wait_cta(full(g), (uint32_t)k & 1u);
+                WC_PHASE_CLOCK(ti1);
                 float2 v[8];
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
@@ -2219,6 +2252,12 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                     }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cta(empty(g));
+#ifdef WC_PHASE_PROFILE
+                if (q == 0 && blockIdx.x < 1024) {
+                    unsigned long long* pc = g_phase_cycles[blockIdx.x];
+                    pc[4] += ti1 - ti0; pc[6] += clock64() - ti1; pc[7] += 1;
+                }
+#endif
             }
         }
     }

@@ -41,12 +41,12 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
 // preparation of a dense stream (k_dec_prepare).  SEG_CHUNK pairs per work item.
 constexpr int SEG_INDEX_CHUNK = 4096;
 int fused_decode_slabs(int fused_cls);
-cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
-                              int n_list, const int* chunk_start, long long items_bound, u64* status,
+cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int2* items,
+                              const int* rec_start, int j0, int j1, long long items_bound, u64* status,
                               int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls);
 cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
-                               const int* tab_list, const int* tab_n, int n_tab_lists, int* chunk_start, int* err,
-                               cudaStream_t st, LaunchStats* ls);
+                               const int* tab_list, const int* tab_n, int n_tab_lists, int2* items, int* rec_start,
+                               const long long* item_off, int* err, cudaStream_t st, LaunchStats* ls);
 
 // Warp-specialised, pipelined decompress of the literal cubes (32^3, 64^3): decode and inverse + store overlap.
 bool pipe_decode_class(int fused_cls);
@@ -57,7 +57,7 @@ cudaError_t launch_pipe_decompress(int fused_cls, const DecUnitDev* dec, const I
                                    int* work_counter);
 
 #ifdef WC_PHASE_PROFILE
-cudaError_t debug_phase_cycles(unsigned long long out[6], bool reset);
+cudaError_t debug_phase_cycles(unsigned long long out[8], bool reset);
 #endif
 
 } // namespace wc
