@@ -135,8 +135,10 @@ typedef enum {
                              real call size the D2H) -> the host-link ceiling of that call */
     WC_OPT_INGEST_STATS = 5, /* 1 = the compress kernels also record each unit's min / max of the narrowed
                                 input values (src/preprocess.cpp:82-88), read with wc_plan_unit_stats */
-    WC_OPT_DECODE_PIPE = 6   /* decompress kernel of the 32^3 / 64^3 cubes: 1 (default) = warp-specialised pipeline
-                                (decode of item k+1 overlaps the stores of item k), 0 = phase-by-phase kernel */
+    WC_OPT_DECODE_PIPE = 6   /* decompress kernel of the cubes: 0 = phase-by-phase kernel, 1 (default) = warp-specialised
+                                pipeline for 32^3 (the decode of unit k+1 overlaps the stores of unit k; one hand-over
+                                group per unit, whole-row stores), 2 = pipeline with hand-over in groups of 4 x-blocks
+                                for 32^3 and 64^3 (finer overlap, 32-byte row pieces) */
 } wc_option;
 WC_API int wc_set_option(wc_ctx* ctx, int option, int64_t value);
 

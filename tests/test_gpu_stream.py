@@ -98,7 +98,7 @@ def test_dplan_device_stream_from_a_compress_plan(wc, ctx, oracle):
         ctx2.close()
 
 
-@pytest.mark.parametrize("pipe", [1, 0])
+@pytest.mark.parametrize("pipe", [1, 2, 0])
 @pytest.mark.parametrize("seg_index", [0, 1])
 def test_dplan_overflow_drop_and_empty_streams(wc, ctx, oracle, seg_index, pipe):
     """rle_decode's `if (idx < N)` (src/decompressor.cpp:24-27): a pair that jumps past the end is dropped together
@@ -274,7 +274,7 @@ def test_unit_stats_minmax_and_need32(wc, ctx, oracle):
     plan.close()
 
 
-@pytest.mark.parametrize("pipe", [1, 0])
+@pytest.mark.parametrize("pipe", [1, 2, 0])
 def test_decode_kernels_many_units_all_densities(wc, ctx, oracle, pipe):
     """The cube decode kernels (pipelined and phase-by-phase) over many units per CTA — the pipeline's hand-over of the
     coefficient array between items (clean-as-you-go, full / empty barriers, descriptor ring) only shows with more

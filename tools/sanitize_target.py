@@ -37,7 +37,7 @@ for i, (p, (runs, vals, _)) in enumerate(zip(got, want)):
     ok &= bool(lo[i] == np.nanmin(boxes[i].astype(np.float32)) and hi[i] == np.nanmax(boxes[i].astype(np.float32)))
 recon = [np.zeros((d[2], d[1], d[0]), np.float32) for d in dims]
 od = capi.box_descs([r.ctypes.data for r in recon], [capi.WC_F32] * len(dims), dims)
-for pipe in (1, 0):
+for pipe in (1, 2, 0):
     ctx.set_option(capi.WC_OPT_DECODE_PIPE, pipe)
     for r in recon:
         r[:] = 7
@@ -60,7 +60,7 @@ o = 0
 for runs, vals, _ in want:
     pr["run"][o:o + runs.size], pr["val"][o:o + runs.size] = runs, vals
     o += runs.size
-for seg, pipe in ((0, 1), (1, 0), (0, 0)):
+for seg, pipe in ((0, 1), (0, 2), (1, 0), (0, 0)):
     ctx.set_option(capi.WC_OPT_SEG_INDEX, seg)
     ctx.set_option(capi.WC_OPT_DECODE_PIPE, pipe)
     for r in recon:

@@ -41,7 +41,7 @@ have_phase = hasattr(ctx.lib, "wc_debug_phase_cycles")
 if have_phase:
     ctx.lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 out = (ctypes.c_ulonglong * 8)()
-for seg, pipe in ((0, 1), (0, 0), (1, 1), (1, 0)):
+for seg, pipe in ((0, 1), (0, 2), (0, 0), (1, 1)):
     ctx2 = pkg.Context(0, stream=stream.cuda_stream)
     ctx2.set_option(capi.WC_OPT_SEG_INDEX, seg)
     ctx2.set_option(capi.WC_OPT_DECODE_PIPE, pipe)

@@ -323,7 +323,8 @@ int wc_set_option(wc_ctx* ctx, int option, int64_t value) {
         ctx->opt_ingest_stats = value != 0;
         return WC_OK;
     case WC_OPT_DECODE_PIPE:
-        ctx->opt_decode_pipe = value != 0;
+        if (value < 0 || value > 2) return WC_ERR_INVALID_ARG;
+        ctx->opt_decode_pipe = (int)value;
         return WC_OK;
     case WC_OPT_PROFILE:
         cudaSetDevice(ctx->device);
@@ -1083,12 +1084,13 @@ static inline void dec_hash(uint64_t& h1, uint64_t& h2, uint64_t v) {
 // the decompress kernel of one fused class list: the pipelined kernel for the literal cubes (unless switched off)
 static cudaError_t launch_decode(wc_ctx* ctx, int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list,
                                  int n, int* err, int* counter, bool v1_tables) {
-    if (ctx->opt_decode_pipe && pipe_decode_class(fused_cls)) {
+    if (ctx->opt_decode_pipe && pipe_decode_class(fused_cls, ctx->opt_decode_pipe)) {
         if (v1_tables) {   // tables by the one-CTA-per-unit index kernel first (WC_OPT_SEG_INDEX = 1)
             cudaError_t e = launch_seg_index1(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls);
             if (e != cudaSuccess) return e;
         }
-        return launch_pipe_decompress(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls, counter);
+        return launch_pipe_decompress(fused_cls, ctx->opt_decode_pipe, dec, inv, list, n, err, ctx->sm_count, ctx->stream,
+                                      &ctx->ls, counter);
     }
     return launch_fused_decompress(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls, counter, v1_tables);
 }

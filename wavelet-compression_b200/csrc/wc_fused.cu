@@ -1866,13 +1866,17 @@ constexpr int PD_PAD  = 8;      // padding words per i' slab of C: IG's LDS.64 h
 constexpr int PD_RING = 4;
 constexpr int PD_CL   = 1 << 20; // clamp of one pair's run+1 and of a chunk sum (> any ncoef here; keeps u32 sums exact)
 
-template <int S, class G>
+// GA = x-blocks per hand-over group: 4 (NG = hx / 4 groups, IG stores 32-byte row pieces) or hx (ONE group per item:
+// DG and IG only overlap across items, but IG writes whole rows — 128-byte lines — exactly like k_fused_decompress).
+template <int S, class G, int GA>
 struct PDSmem {
-    static constexpr int NG    = G::hx / 4;                       // groups per item
-    static constexpr int SLAB  = 2 * G::nb * G::Z + PD_PAD;       // words of C per i'
+    static constexpr int NG    = G::hx / GA;                      // groups per item
+    static constexpr int PAD   = NG == 1 ? F_PAD : PD_PAD;        // NG = 1: lanes are (cp2, a) as in k_fused_decompress
+    static constexpr int SLAB  = 2 * G::nb * G::Z + PAD;          // words of C per i'
     static constexpr int CW    = G::X * SLAB;
-    static constexpr int PPG   = G::npairs / NG;                  // IG pair-slots (threads) per group
+    static constexpr int PPG   = NG == 1 ? PD_NDG : G::npairs / NG;   // IG pair-slots (threads) per group and pass
     static constexpr int GPP   = PD_NDG / PPG;                    // groups per IG pass
+    static constexpr int NPASS = NG == 1 ? G::npairs / PD_NDG : NG / GPP;
     static constexpr int C     = 0;
     static constexpr int CSUM  = C + CW * 4;                      // [2][1032] u32: chunk sums -> exclusive prefix (S = 1),
                                                                   // double-buffered by item parity: P1 of item k + 1
@@ -1882,7 +1886,7 @@ struct PDSmem {
     static constexpr int BARS  = WT + 32 * 4;                     // full[8] empty[8] dfull[4]
     static constexpr int RINGO = BARS + 20 * 8;                   // [4] FDDesc (88 bytes, 8-byte aligned)
     static constexpr int TOTAL = RINGO + PD_RING * 96;
-    static_assert(NG <= 8 && PPG * GPP == PD_NDG && NG % GPP == 0, "group geometry");
+    static_assert(NG <= 8 && PPG * GPP == PD_NDG && NG % GPP == 0 && G::npairs % PD_NDG == 0, "group geometry");
     static_assert((G::hz / 2) % 2 == 0 && G::ncq % 2 == 0, "every pair-slot of the cube is a full c-pair");
 };
 
@@ -1952,12 +1956,12 @@ struct PDFetch {
     }
 };
 
-template <int S, class G>
+template <int S, class G, int GA>
 __global__ void __launch_bounds__(PD_NT, 1)
 k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
                   const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
                   int* __restrict__ work_counter) {
-    typedef PDSmem<S, G> SM;
+    typedef PDSmem<S, G, GA> SM;
     constexpr int NG = SM::NG, SLAB = SM::SLAB;
     extern __shared__ __align__(128) unsigned char smem[];
     float* const    C     = reinterpret_cast<float*>(smem + SM::C);
@@ -1975,7 +1979,7 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
     if (tid == 0) {
         for (int g = 0; g < NG; ++g) {
             mbar_init(full(g), PD_NDW);                 // one arrival per DG warp
-            mbar_init(empty(g), SM::PPG / 32);          // one arrival per IG warp of the group
+            mbar_init(empty(g), SM::PPG / 32);          // one arrival per IG warp of the group (and item)
         }
         for (int r = 0; r < PD_RING; ++r) mbar_init(dfull(r), 1);
     }
@@ -2142,25 +2146,37 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                 const uint32_t rank = (uint32_t)(d.ui % S);
                 const int2* tab = reinterpret_cast<const int2*>(du.coef);
                 constexpr uint32_t seglen = (uint32_t)G::seglen;
-                auto seg_of = [&](int g, int& ip, int& sy) {
-                    const int e = (warp + 5 * g) & 15;             // rotation: heavy segments move from warp to warp
-                    ip = (e >> 3) * G::hx + 4 * g + ((e >> 1) & 3);
-                    sy = e & 1;
+                // round q of a warp: with x groups (NG > 1) the 16 segments of group q, rotated from group to group so that
+                // the heavy low-pass segments land on different warps; with one group per item (NG = 1) the segments
+                // warp, warp + 16, ... with the parity flipped every other round (fd_seg_of)
+                constexpr int NR = NG > 1 ? NG : G::nseg / PD_NDW;
+                static_assert(NR <= 16, "a warp holds the table entries of at most 16 segments");
+                auto seg_of = [&](int q, int& ip, int& sy) {
+                    if (NG > 1) {
+                        const int e = (warp + 5 * q) & 15;
+                        ip = (e >> 3) * G::hx + 4 * q + ((e >> 1) & 3);
+                        sy = e & 1;
+                    } else {
+                        const int sg = fd_seg_of(q, warp, PD_NDW);
+                        ip = sg >> 1;
+                        sy = sg & 1;
+                    }
                     return ip * (2 * S) + sy * S + (int)rank;
                 };
                 int2 te = make_int2(0, 0);
-                if (lane < 2 * NG) {
+                if (lane < 2 * NR) {
                     int ip, sy;
                     const int m = seg_of(lane >> 1, ip, sy);
                     te = __ldg(tab + m + (lane & 1));
                 }
 #pragma unroll 1
-                for (int g = 0; g < NG; ++g) {
+                for (int q = 0; q < NR; ++q) {
                     int ip, sy;
-                    const int m = seg_of(g, ip, sy);
-                    const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * g), e0y = __shfl_sync(0xffffffffu, te.y, 2 * g);
-                    const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * g + 1);
-                    if (k > 0) {
+                    const int m = seg_of(q, ip, sy);
+                    const int g = NG > 1 ? q : 0;
+                    const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * q), e0y = __shfl_sync(0xffffffffu, te.y, 2 * q);
+                    const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * q + 1);
+                    if (k > 0 && (NG > 1 || q == 0)) {
                         WC_PHASE_CLOCK(tw0);
                         mbar_wait_cta(empty(g), epar);
 #ifdef WC_PHASE_PROFILE
@@ -2175,12 +2191,14 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                         if (e1x - c0 <= 128) fd_decode_chunks<4>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
                         else                 fd_decode_chunks<8>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cta(full(g));
+                    if (NG > 1 || q == NR - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cta(full(g));
+                    }
                     if (tid == 0) {
-                        if (g == 1) fe.b_unit();
-                        if (g == 3) fe.c_copy();
-                        if (g == 5) fe.d_count();
+                        if (q == 1) fe.b_unit();
+                        if (q == 3) fe.c_copy();
+                        if (q == 5) fe.d_count();
                     }
                 }
 #ifdef WC_PHASE_PROFILE
@@ -2208,16 +2226,30 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
             const size_t row_bytes = (size_t)G::X * es, plane_bytes = row_bytes * G::Y;
             char* const out0 = static_cast<char*>(iu.out) + (size_t)(2 * b0) * row_bytes;
 #pragma unroll 1
-            for (int pass = 0; pass < NG / SM::GPP; ++pass) {
-                const int g   = pass * SM::GPP + q / SM::PPG;
-                const int idx = q % SM::PPG;
-                // lanes: cp2 (1 bit), cq0 (1), al (2) -> conflict-free LDS.64 / STS.64; then the upper cq bits, then bl
-                const int cp2 = idx & 1, cq0 = (idx >> 1) & 1, al = (idx >> 2) & 3, rest = idx >> 4;
-                const int cqh = rest % (G::ncq / 2), bl = rest / (G::ncq / 2);
-                const int a = 4 * g + al, cpi = 2 * (cq0 + 2 * cqh) + cp2;
+            for (int pass = 0; pass < SM::NPASS; ++pass) {
+                int g, a, bl, cpi;
+                if (NG > 1) {
+                    g = pass * SM::GPP + q / SM::PPG;
+                    const int idx = q % SM::PPG;
+                    // lanes: cp2 (1 bit), cq0 (1), al (2) -> conflict-free LDS.64 / STS.64; then the upper cq bits, then bl
+                    const int cp2 = idx & 1, cq0 = (idx >> 1) & 1, al = (idx >> 2) & 3, rest = idx >> 4;
+                    const int cqh = rest % (G::ncq / 2);
+                    bl = rest / (G::ncq / 2);
+                    a = 4 * g + al;
+                    cpi = 2 * (cq0 + 2 * cqh) + cp2;
+                } else {
+                    // one group: the pair-slot order of k_fused_decompress — a warp covers whole rows (2 c-pairs x 16 a)
+                    g = 0;
+                    const int qq = q + pass * PD_NDG;
+                    const int cp2 = qq & 1, t1 = qq >> 1;
+                    a = t1 % G::hx;
+                    const int t2 = t1 / G::hx;
+                    bl = t2 / G::ncq;
+                    cpi = 2 * (t2 % G::ncq) + cp2;
+                }
                 float* const csrc = C + a * SLAB + bl * G::Z + 2 * cpi;
                 WC_PHASE_CLOCK(ti0);
-                mbar_wait_cta(full(g), (uint32_t)k & 1u);
+                if (NG > 1 || pass == 0) mbar_wait_cta(full(g), (uint32_t)k & 1u);
                 WC_PHASE_CLOCK(ti1);
                 float2 v[8];
 #pragma unroll
@@ -2250,8 +2282,10 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                             __stcs(reinterpret_cast<float2*>(pb), make_float2(lo.y, hi.y));
                         }
                     }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cta(empty(g));
+                if (NG > 1 || pass == SM::NPASS - 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(empty(g));
+                }
 #ifdef WC_PHASE_PROFILE
                 if (q == 0 && blockIdx.x < 1024) {
                     unsigned long long* pc = g_phase_cycles[blockIdx.x];
@@ -2263,11 +2297,11 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
     }
 }
 
-template <int S, class G>
+template <int S, class G, int GA>
 static cudaError_t launch_pd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n, int* err,
                              int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter) {
-    auto kern = k_pipe_decompress<S, G>;
-    constexpr int smem = PDSmem<S, G>::TOTAL;
+    auto kern = k_pipe_decompress<S, G, GA>;
+    constexpr int smem = PDSmem<S, G, GA>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const long long items = (long long)n * S;
@@ -2289,16 +2323,26 @@ cudaError_t launch_seg_index1(int fused_cls, const DecUnitDev* dec, const InvUni
     return cudaGetLastError();
 }
 
-bool pipe_decode_class(int fused_cls) { return fused_cls == FUSED_CLS_CUBE32 || fused_cls == FUSED_CLS_CUBE64; }
+// variant 1: one hand-over group per item (whole-row stores); variant 2: groups of 4 x-blocks
+bool pipe_decode_class(int fused_cls, int variant) {
+    if (variant == 1) return fused_cls == FUSED_CLS_CUBE32;      // slab items gain nothing from one group (see DESIGN)
+    return variant == 2 && (fused_cls == FUSED_CLS_CUBE32 || fused_cls == FUSED_CLS_CUBE64);
+}
 
-cudaError_t launch_pipe_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
-                                   int n_list, int* err, int sm_count, cudaStream_t st, LaunchStats* ls,
-                                   int* work_counter) {
+cudaError_t launch_pipe_decompress(int fused_cls, int variant, const DecUnitDev* dec, const InvUnitDev* inv,
+                                   const int* unit_list, int n_list, int* err, int sm_count, cudaStream_t st,
+                                   LaunchStats* ls, int* work_counter) {
     if (n_list <= 0) return cudaSuccess;
-    if (fused_cls == FUSED_CLS_CUBE32)
-        return launch_pd<1, SGeom<32, 32, 32, 8, 1>>(KID_PIPE_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
-    if (fused_cls == FUSED_CLS_CUBE64)
-        return launch_pd<8, SGeom<64, 64, 64, 8, 8>>(KID_PIPE_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    typedef SGeom<32, 32, 32, 8, 1> G32;
+    typedef SGeom<64, 64, 64, 8, 8> G64;
+    if (fused_cls == FUSED_CLS_CUBE32 && variant == 1)
+        return launch_pd<1, G32, G32::hx>(KID_PIPE_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    if (fused_cls == FUSED_CLS_CUBE32 && variant == 2)
+        return launch_pd<1, G32, 4>(KID_PIPE_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    if (fused_cls == FUSED_CLS_CUBE64 && variant == 1)
+        return launch_pd<8, G64, G64::hx>(KID_PIPE_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    if (fused_cls == FUSED_CLS_CUBE64 && variant == 2)
+        return launch_pd<8, G64, 4>(KID_PIPE_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
     return cudaErrorInvalidValue;
 }
 

@@ -49,12 +49,12 @@ cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dens
                                const long long* item_off, int* err, cudaStream_t st, LaunchStats* ls);
 
 // Warp-specialised, pipelined decompress of the literal cubes (32^3, 64^3): decode and inverse + store overlap.
-bool pipe_decode_class(int fused_cls);
+bool pipe_decode_class(int fused_cls, int variant);
 cudaError_t launch_seg_index1(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n, int* err,
                               int sm_count, cudaStream_t st, LaunchStats* ls);
-cudaError_t launch_pipe_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
-                                   int n_list, int* err, int sm_count, cudaStream_t st, LaunchStats* ls,
-                                   int* work_counter);
+cudaError_t launch_pipe_decompress(int fused_cls, int variant, const DecUnitDev* dec, const InvUnitDev* inv,
+                                   const int* unit_list, int n_list, int* err, int sm_count, cudaStream_t st,
+                                   LaunchStats* ls, int* work_counter);
 
 #ifdef WC_PHASE_PROFILE
 cudaError_t debug_phase_cycles(unsigned long long out[8], bool reset);
