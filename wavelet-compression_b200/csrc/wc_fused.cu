@@ -2112,7 +2112,7 @@ k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restri
                                 // the groups this chunk writes into: rows e0 / YZ .. (e1 - 1) / YZ (clipped to the box)
                                 const uint32_t r0 = e0 / YZ, r1 = min(e1 - 1u, total - 1u) / YZ;
                                 uint32_t need = 0;
-                                for (uint32_t r = r0; r <= r1 && r < r0 + 2u * G::hx; ++r) need |= 1u << ((r % G::hx) >> 2);
+                                for (uint32_t r = r0; r <= r1 && r < r0 + 2u * G::hx; ++r) need |= 1u << ((r % G::hx) / GA);
                                 need &= ~waited;
                                 while (need) {
                                     const int g = __ffs(need) - 1;
