@@ -135,10 +135,9 @@ typedef enum {
                              real call size the D2H) -> the host-link ceiling of that call */
     WC_OPT_INGEST_STATS = 5, /* 1 = the compress kernels also record each unit's min / max of the narrowed
                                 input values (src/preprocess.cpp:82-88), read with wc_plan_unit_stats */
-    WC_OPT_DECODE_PIPE = 6   /* decompress kernel of the cubes: 0 = phase-by-phase kernel, 1 (default) = warp-specialised
-                                pipeline for 32^3 (the decode of unit k+1 overlaps the stores of unit k; one hand-over
-                                group per unit, whole-row stores), 2 = pipeline with hand-over in groups of 4 x-blocks
-                                for 32^3 and 64^3 (finer overlap, 32-byte row pieces) */
+    WC_OPT_DECODE_PIPE = 6   /* decompress kernel of the 32^3 cubes: 0 = pairs are read straight from global memory,
+                                1 (default) = units that arrive without a segment table (files, wc_dplan) decode from a
+                                shared-memory staging area that TMA bulk copies fill one unit ahead, 2 = every unit */
 } wc_option;
 WC_API int wc_set_option(wc_ctx* ctx, int option, int64_t value);
 

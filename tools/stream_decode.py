@@ -41,7 +41,7 @@ have_phase = hasattr(ctx.lib, "wc_debug_phase_cycles")
 if have_phase:
     ctx.lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 out = (ctypes.c_ulonglong * 8)()
-for seg, pipe in ((0, 1), (0, 2), (0, 0), (1, 1)):
+for seg, pipe in ((0, 1), (0, 0)):
     ctx2 = pkg.Context(0, stream=stream.cuda_stream)
     ctx2.set_option(capi.WC_OPT_SEG_INDEX, seg)
     ctx2.set_option(capi.WC_OPT_DECODE_PIPE, pipe)
@@ -70,15 +70,10 @@ for seg, pipe in ((0, 1), (0, 2), (0, 0), (1, 1)):
         ctx2.set_profile(False)
     print(f"{which} seg_index={seg} pipe={pipe}: {ms:.4f} ms/step  {alg / ms / 1e6:.0f} GB/s algorithmic = {alg / ms / 1e6 / peak:.3f} of {peak}",
           {k: round(v[1] / 5, 4) for k, v in st.items()})
-    if have_phase and pipe:
-        v = np.array(list(out), dtype=np.float64)
-        items, passes = max(v[5], 1), max(v[7], 1)
-        print(f"    DG per item: P1 {v[0] / items:.0f}  P2 {v[1] / items:.0f}  P3/decode {v[2] / items:.0f}  (of which waiting for IG {v[3] / items:.0f})")
-        print(f"    IG per item: waiting for DG {v[4] / items:.0f}  working {v[6] / items:.0f}   ({passes / items:.1f} passes per item, items/step {items / 10:.0f})")
-    if have_phase and not pipe:
+    if have_phase:
         v = np.array(list(out), dtype=np.float64)
         units = max(v[5], 1)
-        for n, c in zip(["zero-fill+barrier", "-", "decode (scan+scatter)", "barrier+prefetch", "inverse+store"], v[:5]):
+        for n, c in zip(["top", "-", "decode (scan+scatter)", "barrier+stage/prefetch", "inverse+store"], v[:5]):
             print(f"    {n:22s} {c / units:9.0f} cycles/item  {100 * c / max(v[:5].sum(), 1):5.1f}%")
         print("    total cycles/item", v[:5].sum() / units, "items/step", units / 10)
     dp.close()

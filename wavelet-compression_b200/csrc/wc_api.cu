@@ -101,7 +101,7 @@ struct wc_ctx {
     int          opt_seg_index = 0;   // 0 = chunk-parallel k_seg_index2, 1 = one CTA per unit (k_seg_index)
     int          opt_copy_only = 0;   // probe: wc_plan_compress_to_host moves the bytes but skips the kernels
     int          opt_ingest_stats = 0; // compress also records per-unit min / max of the narrowed inputs
-    int          opt_decode_pipe = 1;  // 32^3 / 64^3 cubes decode with the warp-specialised pipeline kernel
+    int          opt_decode_pipe = 1;  // 32^3 cubes: table-less lists decode from the TMA-fed staging area
     int          sm_count = 0;
     wc_plan*     batch_plan = nullptr; // owner of the memory handed out by wc_compress_batch
     // workspace of the blocking decompress / rmse / primitive calls (grow-only)
@@ -1081,18 +1081,11 @@ static inline void dec_hash(uint64_t& h1, uint64_t& h2, uint64_t v) {
     h2 = (h2 + v) * 0xC2B2AE3D27D4EB4Full; h2 ^= h2 >> 31;
 }
 
-// the decompress kernel of one fused class list: the pipelined kernel for the literal cubes (unless switched off)
+// the decompress kernel of one fused class list (WC_OPT_DECODE_PIPE selects the staged variant of the 32^3 kernel)
 static cudaError_t launch_decode(wc_ctx* ctx, int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list,
                                  int n, int* err, int* counter, bool v1_tables) {
-    if (ctx->opt_decode_pipe && pipe_decode_class(fused_cls, ctx->opt_decode_pipe)) {
-        if (v1_tables) {   // tables by the one-CTA-per-unit index kernel first (WC_OPT_SEG_INDEX = 1)
-            cudaError_t e = launch_seg_index1(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls);
-            if (e != cudaSuccess) return e;
-        }
-        return launch_pipe_decompress(fused_cls, ctx->opt_decode_pipe, dec, inv, list, n, err, ctx->sm_count, ctx->stream,
-                                      &ctx->ls, counter);
-    }
-    return launch_fused_decompress(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls, counter, v1_tables);
+    return launch_fused_decompress(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls, counter, v1_tables,
+                                   ctx->opt_decode_pipe);
 }
 
 // A plan that decodes into the same boxes again (keep sweeps of the estimate mode) re-launches from the

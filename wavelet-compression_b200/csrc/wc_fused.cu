@@ -1465,6 +1465,177 @@ __device__ __forceinline__ void fd_decode_chunks(const int2* __restrict__ pairs,
     base = b;
 }
 
+// The same in two halves, so that a warp can have the first chunks of its NEXT segment in flight while it scans and
+// scatters the current one (the table-driven decode is a chain of dependent latencies per segment otherwise).
+template <int NCH>
+__device__ __forceinline__ void fd_load_chunks(const int2* __restrict__ pairs, int c0, int e1x, int lane, int2 (&pv)[NCH]) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int p = c0 + 32 * c + lane;
+        pv[c] = make_int2(-1, 0);
+        if (p < e1x) pv[c] = __ldg(pairs + p);
+    }
+}
+template <int NCH>
+__device__ __forceinline__ void fd_decode_loaded(const int2 (&pv)[NCH], int lane, uint32_t& base, uint32_t fseg,
+                                                 uint32_t seglen, uint32_t total, float* cseg) {
+    uint32_t inc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) inc[c] = pv[c].x >= 0 ? (uint32_t)pv[c].x + 1u : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc[c], o);
+            if (lane >= o) inc[c] += v;
+        }
+    }
+    uint32_t b = base;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const uint32_t f = b + inc[c];
+        if (pv[c].x >= 0 && f - fseg < seglen && f < total) cseg[f - fseg] = __int_as_float(pv[c].y);
+        b += __shfl_sync(0xffffffffu, inc[c], 31);
+    }
+    base = b;
+}
+
+// ---- staged decode (S = 1, table-less packed streams) ------------------------------------------------
+// The block-scan decode above is a chain of dependent latencies per tile (HBM load -> sum -> barrier -> scatter) that
+// nothing hides with one 128 KB coefficient array per SM.  Here the pair list of the NEXT item is copied into a
+// 96 KB staging area of shared memory by the TMA engine (one cp.async.bulk, completion on an mbarrier) while the
+// current item is inverted and stored, so the decode phase reads its pairs from shared memory: its HBM time is
+// hidden behind the store phase of the previous item and what is left is ~2 k cycles of scan + scatter.
+//   ST slot p + sh holds pair p for p < nst = min(K, ST_PAIRS); sh = 2 for 16-byte aligned lists, 1 otherwise (the
+//   bulk copy needs 16-byte aligned source, destination and size: a misaligned first pair and an odd last pair are
+//   moved by two ordinary loads).  Pairs past nst (lists longer than the staging area) come from global memory /
+//   L2 (prefetched), software-pipelined one tile ahead.
+//   A thread owns FS_PPT CONSECUTIVE pairs of a tile (one shuffle scan per tile instead of one per 32 pairs); with an
+//   odd FS_PPT the lanes' 8-byte shared-memory loads are conflict-free (stride FS_PPT * 8 bytes).
+constexpr int FS_PPT    = 7;
+constexpr int FS_SLOTS  = 12288;               // 96 KB
+constexpr int FS_PAIRS  = FS_SLOTS - 2;
+constexpr uint32_t FS_CL = 1u << 17;           // clamp of one pair's run + 1: > any ncoef of an S = 1 unit (32768), and
+                                               // 1024 threads * FS_PPT * FS_CL < 2^32, so plain u32 adds never wrap
+__device__ __forceinline__ bool mbar_try_wait_cta(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_cta(bar, parity)) { }
+}
+// Issued by ONE thread: stage the first pairs of a list; always completes exactly one phase of `bar`.
+__device__ __forceinline__ void fs_issue(const wc_pair* pairs, int K, int2* ST, uint32_t bar, u64 pol) {
+    const int nst = K < FS_PAIRS ? K : FS_PAIRS;
+    const int s0  = (int)((reinterpret_cast<uintptr_t>(pairs) >> 3) & 1u);
+    const int nb  = nst > s0 ? ((nst - s0) & ~1) : 0;           // pairs moved by the bulk copy
+    const uint32_t bytes = (uint32_t)nb * 8u;
+    if (bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(smem_u32(ST + 2)), "l"(pairs + s0), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+    } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+}
+// The (at most two) pairs of the staged range the bulk copy cannot move; any thread(s) but in program order before
+// the CTA barrier that precedes the decode.  which = 0: the misaligned first pair, 1: the odd last pair.
+__device__ __forceinline__ void fs_patch(const wc_pair* pairs, int K, int2* ST, int which) {
+    const int nst = K < FS_PAIRS ? K : FS_PAIRS;
+    const int s0  = (int)((reinterpret_cast<uintptr_t>(pairs) >> 3) & 1u);
+    const int nb  = nst > s0 ? ((nst - s0) & ~1) : 0;
+    const int sh  = 2 - s0;
+    const int2* gp = reinterpret_cast<const int2*>(pairs);
+    if (which == 0) { if (s0 && nst > 0) ST[sh] = __ldg(gp); }
+    else            { if (s0 + nb < nst) ST[s0 + nb + sh] = __ldg(gp + s0 + nb); }
+}
+
+template <int NT, class G>
+__device__ __forceinline__ void fd_decode_staged(const G& g, const int2* __restrict__ pairs, const int K, const uint32_t total,
+                                                 float* const C, const int2* const ST, uint32_t* const s_wt,
+                                                 const uint32_t bar, const uint32_t parity, int* __restrict__ err) {
+    constexpr int NW = NT / 32, TILE = NT * FS_PPT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nst = K < FS_PAIRS ? K : FS_PAIRS;
+    const int sh  = 2 - (int)((reinterpret_cast<uintptr_t>(pairs) >> 3) & 1u);
+    FastDiv dyz;
+    if (!G::is_static) dyz.init((uint32_t)(g.Y * g.Z), total);
+    int2 pr[FS_PPT], nx[FS_PPT];
+    auto from_global = [&](int p) { return p < K && p + FS_PPT > nst; };
+    auto load_global = [&](int p) {
+#pragma unroll
+        for (int j = 0; j < FS_PPT; ++j) nx[j] = (p + j < K) ? __ldg(pairs + p + j) : make_int2(0, 0);
+    };
+#pragma unroll
+    for (int j = 0; j < FS_PPT; ++j) nx[j] = make_int2(0, 0);
+    if (from_global(tid * FS_PPT)) load_global(tid * FS_PPT);
+    mbar_wait_cta(bar, parity);
+    bool bad = false;
+    uint32_t carry = 0;
+    int tile = 0;
+#pragma unroll 1
+    for (int p0 = 0; p0 < K; p0 += TILE, ++tile) {
+        const int p = p0 + tid * FS_PPT;
+        if (p + FS_PPT <= nst) {
+            const int2* sp = ST + p + sh;
+#pragma unroll
+            for (int j = 0; j < FS_PPT; ++j) pr[j] = sp[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < FS_PPT; ++j) pr[j] = nx[j];
+        }
+        if (p0 + TILE < K) {
+#pragma unroll
+            for (int j = 0; j < FS_PPT; ++j) nx[j] = make_int2(0, 0);
+            if (from_global(p + TILE)) load_global(p + TILE);
+        }
+        // run + 1 of the live pairs (negative runs: corrupt flag, skipped), clamped
+        uint32_t inc[FS_PPT], s = 0;
+#pragma unroll
+        for (int j = 0; j < FS_PPT; ++j) {
+            const bool in = p + j < K;
+            if (in && pr[j].x < 0) bad = true;
+            inc[j] = (in && pr[j].x >= 0) ? min((uint32_t)pr[j].x + 1u, FS_CL) : 0u;
+            s += inc[j];
+        }
+        uint32_t w = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        uint32_t* const wt = s_wt + (tile & 1) * 32;
+        if (lane == 31) wt[warp] = w;
+        __syncthreads();
+        uint32_t ws = lane < NW ? wt[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += v;
+        }
+        const uint32_t ttot = __shfl_sync(0xffffffffu, ws, 31);
+        uint32_t wpre = __shfl_sync(0xffffffffu, ws, (warp + 31) & 31);
+        if (warp == 0) wpre = 0;
+        uint32_t pre = carry + wpre + (w - s);                 // flat index this thread's first run starts at
+        carry = min(carry + ttot, 1u << 30);
+        if (pre < total) {
+#pragma unroll
+            for (int j = 0; j < FS_PPT; ++j) {
+                const uint32_t f  = pre + inc[j] - 1u;             // inc == 0 (dead pair): f = pre - 1, masked below
+                const uint32_t ip = G::is_static ? f / (uint32_t)(g.Y * g.Z) : dyz.div(f);
+                if (inc[j] && f < total) C[f + F_PAD * ip] = __int_as_float(pr[j].y);
+                pre += inc[j];
+            }
+        }
+    }
+    if (bad) atomicOr(err, 1);
+}
+
 // Unit descriptors are staged two items ahead through shared memory, like FLookahead of the compress
 // kernels; K (which may live on the device after a plan round trip) is resolved one item ahead, in time
 // for the L2 prefetch of the next unit's pair list (S = 1).
@@ -1529,10 +1700,17 @@ struct FDLookahead {
 };
 
 // One work item (unit, slab `rank`) of the fused decompress.  G: FGeom or SGeom<..., S>.
-template <int S, int NT, class G>
+struct FDStage {          // STG kernels only: staging area, its mbarrier, staged items so far (= phase parity)
+    int2*    ST;
+    uint32_t bar;
+    uint32_t n;
+    bool     ignore_tab;  // decode every S = 1 unit from the staged list, also when a segment table came with it
+    u64      pol;
+};
+template <int S, int NT, bool STG, class G>
 __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const InvUnitDev& iu, const int K,
                                         float* const C, uint32_t* const s_wt, FDLookahead<S>& la,
-                                        const uint32_t rank, int* __restrict__ err, const bool have_next) {
+                                        const uint32_t rank, int* __restrict__ err, const bool have_next, FDStage& stg) {
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b0 = rank * g.nb;
@@ -1546,9 +1724,9 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
     int2 te = make_int2(0, 0);
     // S = 1 units decode by segments too when a table came with them (plan round trip: the compress kernel
     // wrote it); without one they take the block-wide scan, which needs no second pass over the list
-    const bool use_tab = S > 1 || du.coef != nullptr;
+    const bool use_tab = S > 1 || (du.coef != nullptr && !(STG && stg.ignore_tab));
     if (!use_tab) {
-        fd_load_tile(pairs, vec16, tid * FD_PPT, K, pr);           // in flight during the zero-fill
+        if (!STG) fd_load_tile(pairs, vec16, tid * FD_PPT, K, pr);
     } else {
         // segment table entries of this warp's first 16 segments: lane 2q + e <- tab[m(q) + e]
         const int sg = fd_seg_of(lane >> 1, warp, NW);
@@ -1556,20 +1734,18 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
             te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sg >> 1) * (2 * S) + (sg & 1) * S + (int)rank + (lane & 1));
     }
 
-    // 1. zero-fill C (rle_decode starts from zeros, src/decompressor.cpp:17)
-    {
-        const int nwords = g.nlocal + F_PAD * g.X;
-        float4* c4 = reinterpret_cast<float4*>(C);
-#pragma unroll 4
-        for (int i = tid; i < (nwords + 3) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
+    // 1. C is all zeros here (rle_decode starts from zeros, src/decompressor.cpp:17): the kernel zeroes it once at the
+    //    start and step 3 of every item puts a zero back behind each coefficient it reads ("clean as you go"), which
+    //    removed a 128 KB zero-fill pass and a CTA-wide barrier per item.
     WC_PHASE_CLOCK(t1);
     if (tid == 0) la.stage2();
     WC_PHASE_CLOCK(t2);
 
     // 2. decode the pairs that land in this item's segments
-    if (!use_tab) {
+    if (STG && !use_tab) {
+        fd_decode_staged<NT>(g, pairs, K, total, C, stg.ST, s_wt, stg.bar, stg.n & 1u, err);
+        ++stg.n;
+    } else if (!use_tab) {
         // block-wide scan over the whole list; flat index -> (i', j', k') -> padded index in C
         FastDiv dyz;
         if (!G::is_static) dyz.init((uint32_t)(g.Y * g.Z), total);
@@ -1603,44 +1779,74 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         // Lanes 2q, 2q+1 hold the table entries of the warp's q-th segment (loaded before the zero-fill);
         // up to 8 chunks of 32 pairs are in flight per segment before the first one is decoded.
         const uint32_t seglen = (uint32_t)g.seglen;
+        // software pipeline over the warp's segments: the first 128 pairs of segment q + 1 are loaded before segment q
+        // is scanned and scattered
+        int2 cur[4], nxt[4];
+        auto seg_entries = [&](int q, int& e0x, int& e0y, int& e1x) {
+            const int ql = q & 15;
+            e0x = __shfl_sync(0xffffffffu, te.x, 2 * ql); e0y = __shfl_sync(0xffffffffu, te.y, 2 * ql);
+            e1x = __shfl_sync(0xffffffffu, te.x, 2 * ql + 1);
+        };
+        auto reload_entries = [&](int q) {
+            // a warp holds the entries of 16 segments at a time: next round (more than 16 segments per warp only
+            // happens with few warps and a long x axis, e.g. 48 x 4 x 8 boxes)
+            const int qq = q + (lane >> 1), sq = fd_seg_of(qq, warp, NW);
+            te = make_int2(0, 0);
+            if (qq * NW + warp < g.nseg)
+                te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sq >> 1) * (2 * S) + (sq & 1) * S + (int)rank + (lane & 1));
+        };
+        int e0x = 0, e0y = 0, e1x = 0;
+        if (warp < g.nseg) {
+            seg_entries(0, e0x, e0y, e1x);
+            fd_load_chunks<4>(pairs, e0x, e1x, lane, cur);
+        }
 #pragma unroll 1
         for (int q = 0; q * NW + warp < g.nseg; ++q) {
             const int sg = fd_seg_of(q, warp, NW);
             const int i = sg >> 1, half = sg & 1;
             const int m = i * (2 * S) + half * S + (int)rank;
-            if (q && (q & 15) == 0) {
-                // a warp holds the entries of 16 segments at a time: next round (more than 16 segments per
-                // warp only happens with few warps and a long x axis, e.g. 48 x 4 x 8 boxes)
-                const int qq = q + (lane >> 1), sq = fd_seg_of(qq, warp, NW);
-                te = make_int2(0, 0);
-                if (qq * NW + warp < g.nseg)
-                    te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sq >> 1) * (2 * S) + (sq & 1) * S + (int)rank + (lane & 1));
+            // entries + first chunks of the next segment
+            int n0x = 0, n0y = 0, n1x = 0;
+            const bool more = (q + 1) * NW + warp < g.nseg;
+            if (more) {
+                if (((q + 1) & 15) == 0) reload_entries(q + 1);
+                seg_entries(q + 1, n0x, n0y, n1x);
+                fd_load_chunks<4>(pairs, n0x, n1x, lane, nxt);
             }
-            const int ql = q & 15;
-            const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * ql), e0y = __shfl_sync(0xffffffffu, te.y, 2 * ql);
-            const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * ql + 1);
             float* const cseg = C + i * g.slab + half * g.seglen;    // C index of flat index m * seglen
             const uint32_t fseg = (uint32_t)m * seglen;
             uint32_t base = (uint32_t)e0y;                           // flat index of the pair before the first (or -1)
+            if (e0x < e1x) fd_decode_loaded<4>(cur, lane, base, fseg, seglen, total, cseg);
 #pragma unroll 1
-            for (int c0 = e0x; c0 < e1x; c0 += 256) {
+            for (int c0 = e0x + 128; c0 < e1x; c0 += 256) {
                 // 4 or 8 chunks of 32 pairs at once: the loads are all in flight together, and the chunks'
                 // shuffle scans are independent chains the scheduler interleaves (no branch between them)
                 if (e1x - c0 <= 128) fd_decode_chunks<4>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
                 else                 fd_decode_chunks<8>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
             }
+            e0x = n0x; e0y = n0y; e1x = n1x;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
         }
     }
     WC_PHASE_CLOCK(t3);
     if (tid == 0) la.resolve_k_store();
     __syncthreads();
 
-    // L2 prefetch of the NEXT unit's pair list (S = 1): lands while this unit is inverted
+    // the NEXT unit's pair list (S = 1) lands while this unit is inverted: in the staging area (TMA bulk copy; what
+    // does not fit is prefetched into L2), or in L2 only
     if (S == 1 && have_next) {
         const int Kn = la.next_slot->K;
         const char* base = reinterpret_cast<const char*>(la.next_slot->du.pairs);
+        int line0 = 0;
+        if (STG && (stg.ignore_tab || la.next_slot->du.coef == nullptr)) {
+            if (tid == 0)  fs_issue(la.next_slot->du.pairs, Kn, stg.ST, stg.bar, stg.pol);
+            if (tid == 32) fs_patch(la.next_slot->du.pairs, Kn, stg.ST, 0);
+            if (tid == 64) fs_patch(la.next_slot->du.pairs, Kn, stg.ST, 1);
+            line0 = (FS_PAIRS * 8) / 128;
+        }
         const int nlines = (Kn * 8 + 127) / 128;
-        for (int i = tid; i < nlines; i += NT)
+        for (int i = line0 + tid; i < nlines; i += NT)
             asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)i * 128));
     }
     WC_PHASE_CLOCK(t4);
@@ -1663,8 +1869,11 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
             const float* csrc = C + a * g.slab + bl * g.Z + 2 * cpi;
             float2 v[8];
 #pragma unroll
-            for (int o = 0; o < 8; ++o)
-                v[o] = *reinterpret_cast<const float2*>(csrc + (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3);
+            for (int o = 0; o < 8; ++o) {
+                float2* const pc = const_cast<float2*>(reinterpret_cast<const float2*>(csrc + (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3));
+                v[o] = *pc;
+                *pc  = make_float2(0.f, 0.f);        // clean as you go: the next item finds C zeroed
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) ihaar_pair2(v[2 * k], v[2 * k + 1]);                 // X
 #pragma unroll
@@ -1712,18 +1921,36 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
 }
 
 // STATIC: every unit of the list is the cube this variant is specialised for (32^3 for S = 1, 64^3 for S = 8).
-template <int S, int CAP, int NT, bool STATIC>
+template <int S, int CAP, int NT, bool STATIC, bool STG>
 __global__ void __launch_bounds__(NT, (CAP <= 512 ? 32 : CAP <= 4096 ? 4 : 1))
 k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
                    const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
-                   int* __restrict__ work_counter) {
+                   int* __restrict__ work_counter, int ignore_tab) {
+    static_assert(!STG || S == 1, "staged decode: whole-unit items only");
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int BASE = (CAP + F_CPAD) * 4;
     float* const    C    = reinterpret_cast<float*>(smem);
     uint32_t* const s_wt = reinterpret_cast<uint32_t*>(smem + BASE);               // [2][32]
     FDDesc* const s_desc = reinterpret_cast<FDDesc*>(smem + BASE + 256);          // [2] x 88 bytes
+    FDStage stg;
+    stg.ST  = reinterpret_cast<int2*>(smem + BASE + 1024);                        // STG: [FS_SLOTS] pairs
+    stg.bar = smem_u32(smem + BASE + 512);
+    stg.n   = 0;
+    stg.ignore_tab = ignore_tab != 0;
+    stg.pol = 0;
     const int tid = threadIdx.x;
+    if (STG) {
+        stg.pol = l2_policy_evict_first();
+        if (tid == 0) {
+            mbar_init(stg.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     const int n_items = n_list * S;
+    {   // the coefficient array starts out zeroed; every item leaves it zeroed (fd_unit step 3)
+        float4* c4 = reinterpret_cast<float4*>(C);
+        for (int i = tid; i < (CAP + F_CPAD) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     // dynamic hand-out of the items through a global counter (or a static stride without one)
     FDLookahead<S> la;
@@ -1746,6 +1973,15 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         }
     }
     __syncthreads();
+    if (STG) {      // the first item's list goes into the staging area here, every later one during its predecessor
+        const FDDesc& d = s_desc[0];
+        if (d.ui < n_items && (stg.ignore_tab || d.du.coef == nullptr)) {
+            if (tid == 0)  fs_issue(d.du.pairs, d.K, stg.ST, stg.bar, stg.pol);
+            if (tid == 32) fs_patch(d.du.pairs, d.K, stg.ST, 0);
+            if (tid == 64) fs_patch(d.du.pairs, d.K, stg.ST, 1);
+        }
+        __syncthreads();
+    }
     for (int k = 0;; ++k) {
         const FDDesc& d = s_desc[k & 1];
         if (d.ui >= n_items) break;
@@ -1757,7 +1993,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         la.next_slot = &s_desc[(k + 1) & 1];
         la.ui_prev   = la.next_slot->ui;
         const bool have_next = la.next_slot->ui < n_items;
-#define WC_FD_UNIT(GEOM) fd_unit<S, NT>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next)
+#define WC_FD_UNIT(GEOM) fd_unit<S, NT, STG>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next, stg)
         if constexpr (STATIC) {
             constexpr int CUBE = S == 1 ? (CAP <= 512 ? 8 : CAP <= 4096 ? 16 : 32) : 64;
             WC_FD_UNIT((SGeom<CUBE, CUBE, CUBE, 8, S>()));
@@ -1770,12 +2006,13 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
     }
 }
 
-template <int S, int CAP, int NT, bool STATIC>
+template <int S, int CAP, int NT, bool STATIC, bool STG = false>
 static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                              int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter,
-                             bool build_tables) {
-    auto kern = k_fused_decompress<S, CAP, NT, STATIC>;
-    constexpr int smem = (CAP + F_CPAD) * 4 + 1024;
+                             bool build_tables, bool ignore_tab = false) {
+    auto kern = k_fused_decompress<S, CAP, NT, STATIC, STG>;
+    constexpr int smem = (CAP + F_CPAD) * 4 + 1024 + (STG ? FS_SLOTS * 8 : 0);
+    static_assert(smem <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     if (S > 1 && build_tables) {
@@ -1796,7 +2033,7 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
     const long long items = (long long)n * S, slots = (long long)per_sm * sm_count;
     const int nc = (int)(slots < items ? slots : items);
     ls->begin(kid, st);
-    kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter);
+    kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter, ignore_tab ? 1 : 0);
     ls->end(st);
     return cudaGetLastError();
 }
@@ -1833,519 +2070,6 @@ cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dens
     return cudaGetLastError();
 }
 
-// =====================================================================================================
-// Pipelined decompress for the literal cubes (32^3: S = 1, one item per unit; 64^3: S = 8 slab items)
-// =====================================================================================================
-// k_fused_decompress runs its phases back to back behind CTA-wide barriers: zero-fill, decode (latency bound:
-// dependent loads + shuffle scans + scattered shared-memory stores), inverse + store (bandwidth bound).  With one
-// 128 KB coefficient array per SM nothing overlaps, and a unit costs the SUM of the phases (measured 15-19 k cycles
-// against an HBM floor of ~10 k).  Here the CTA is split into two warp-specialised groups that run concurrently:
-//   DG  warps 0-15   decode: pairs -> coefficient array C
-//   IG  warps 16-31  inverse transform of C -> global stores, and zeroing C behind itself ("clean as you go":
-//                    the separate zero-fill pass and its barrier disappear)
-// C is handed over in NG groups of 4 consecutive x-blocks a (= the 16 segments i' in {4g..4g+3, hx+4g..hx+4g+3}):
-// full[g] (DG -> IG, 16 arrivals: one per DG warp) and empty[g] (IG -> DG, one arrival per IG warp of the group) are
-// CTA-scope mbarriers that complete exactly one phase per item, in strict alternation, so a parity wait is never
-// ambiguous.  DG therefore runs up to one whole item ahead of IG: the decode of item k+1 overlaps the stores of
-// item k, and a unit costs max(decode, inverse) instead of their sum.
-//   A group of 4 x-blocks is the pipeline's grain because it is the store side's coalescing grain: 4 blocks = 8
-//   cells = one 32-byte sector of a float32 row (64 bytes of a float64 row).
-// S = 1 (32^3): no segment table is needed or used.  Every DG warp owns a contiguous run of the unit's 32-pair chunks
-//   and walks it twice, eight chunks per trip (eight 256-byte loads in flight per warp): P1 sums run+1 per chunk, P2
-//   (one warp-shuffle scan over <= 1024 sums) gives every chunk its starting flat index, P3 re-reads the chunks from
-//   L1 / L2, scans inside the chunk and scatters; before its first write into a group's rows a warp waits for IG to
-//   have handed that group back.  Perfectly balanced, every chunk independent.  HBM traffic 8K + 4N.
-// S = 8 (64^3 slabs): a slab's pairs are 2X separate sub-ranges of the unit's list, found through the segment table
-//   (written by the compress kernels or by k_seg_index2); a DG warp decodes one segment per group, rotated from group
-//   to group so that the heavy low-pass segments land on different warps.
-// Unit descriptors travel through a ring of 4 slots, published two items ahead by DG's first thread (dfull barriers).
-constexpr int PD_NT   = 1024;   // threads per CTA
-constexpr int PD_NDG  = 512;    // decode group: threads [0, 512); inverse group: [512, 1024)
-constexpr int PD_NDW  = 16;     // warps per group
-constexpr int PD_PAD  = 8;      // padding words per i' slab of C: IG's LDS.64 hit banks 8*al + 4*cq0 + 2*cp2 + {0,1}
-constexpr int PD_RING = 4;
-constexpr int PD_CL   = 1 << 20; // clamp of one pair's run+1 and of a chunk sum (> any ncoef here; keeps u32 sums exact)
-
-// GA = x-blocks per hand-over group: 4 (NG = hx / 4 groups, IG stores 32-byte row pieces) or hx (ONE group per item:
-// DG and IG only overlap across items, but IG writes whole rows — 128-byte lines — exactly like k_fused_decompress).
-template <int S, class G, int GA>
-struct PDSmem {
-    static constexpr int NG    = G::hx / GA;                      // groups per item
-    static constexpr int PAD   = NG == 1 ? F_PAD : PD_PAD;        // NG = 1: lanes are (cp2, a) as in k_fused_decompress
-    static constexpr int SLAB  = 2 * G::nb * G::Z + PAD;          // words of C per i'
-    static constexpr int CW    = G::X * SLAB;
-    static constexpr int PPG   = NG == 1 ? PD_NDG : G::npairs / NG;   // IG pair-slots (threads) per group and pass
-    static constexpr int GPP   = PD_NDG / PPG;                    // groups per IG pass
-    static constexpr int NPASS = NG == 1 ? G::npairs / PD_NDG : NG / GPP;
-    static constexpr int C     = 0;
-    static constexpr int CSUM  = C + CW * 4;                      // [2][1032] u32: chunk sums -> exclusive prefix (S = 1),
-                                                                  // double-buffered by item parity: P1 of item k + 1
-                                                                  // writes while slower warps still read item k's in P4
-    static constexpr int RANGE = CSUM + 2 * 1032 * 4;             // [NG][2] int2: chunk range of (group, x half)
-    static constexpr int WT    = RANGE + 16 * 8;                  // [32] u32 scan scratch
-    static constexpr int BARS  = WT + 32 * 4;                     // full[8] empty[8] dfull[4]
-    static constexpr int RINGO = BARS + 20 * 8;                   // [4] FDDesc (88 bytes, 8-byte aligned)
-    static constexpr int TOTAL = RINGO + PD_RING * 96;
-    static_assert(NG <= 8 && PPG * GPP == PD_NDG && NG % GPP == 0 && G::npairs % PD_NDG == 0, "group geometry");
-    static_assert((G::hz / 2) % 2 == 0 && G::ncq % 2 == 0, "every pair-slot of the cube is a full c-pair");
-};
-
-__device__ __forceinline__ bool mbar_try_wait_cta(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait_cta(bar, parity)) { }
-}
-__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void dg_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(PD_NDG) : "memory"); }
-
-// the ring's producer (DG thread 0 only): item k + 2 is fetched in five stages spread over item k
-template <int S>
-struct PDFetch {
-    const DecUnitDev* dec;
-    const InvUnitDev* inv;
-    const int*        unit_list;
-    int*              work_counter;
-    int               n_items, stride, ui_prev;
-    int               idx, uid, kreg;
-    FDDesc*           slot;
-    __device__ __forceinline__ void a_index() {
-        idx = work_counter ? atomicAdd(work_counter, 1) : ui_prev + stride;
-        ui_prev = idx;
-    }
-    __device__ __forceinline__ void b_unit() {
-        uid = -1;
-        if (idx < n_items) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(uid) : "l"(unit_list + idx / S));
-    }
-    __device__ __forceinline__ void c_copy() {
-        slot->ui  = idx;
-        slot->uid = uid;
-        if (uid >= 0) {
-            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&slot->du);
-            const char*    s0 = reinterpret_cast<const char*>(dec + uid);
-#pragma unroll
-            for (int b = 0; b < 40; b += 8)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + b), "l"(s0 + b) : "memory");
-            const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(&slot->iu);
-            const char*    s1 = reinterpret_cast<const char*>(inv + uid);
-#pragma unroll
-            for (int b = 0; b < 32; b += 8)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1 + b), "l"(s1 + b) : "memory");
-        }
-    }
-    __device__ __forceinline__ void d_count() {          // descriptor has landed: resolve K (may live on the device)
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        kreg = 0;
-        if (uid >= 0) {
-            kreg = slot->du.npairs;
-            const int32_t* kp = slot->du.npairs_dev;
-            if (kp) asm volatile("ld.global.s32 %0, [%1];" : "=r"(kreg) : "l"(kp));
-        }
-    }
-    __device__ __forceinline__ void e_publish(uint32_t bar) {
-        slot->K = kreg;
-        mbar_arrive_cta(bar);                              // release: the slot is visible to every waiter
-    }
-};
-
-template <int S, class G, int GA>
-__global__ void __launch_bounds__(PD_NT, 1)
-k_pipe_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
-                  const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
-                  int* __restrict__ work_counter) {
-    typedef PDSmem<S, G, GA> SM;
-    constexpr int NG = SM::NG, SLAB = SM::SLAB;
-    extern __shared__ __align__(128) unsigned char smem[];
-    float* const    C     = reinterpret_cast<float*>(smem + SM::C);
-    uint32_t* const csum2 = reinterpret_cast<uint32_t*>(smem + SM::CSUM);
-    int2* const     range = reinterpret_cast<int2*>(smem + SM::RANGE);
-    uint32_t* const wt    = reinterpret_cast<uint32_t*>(smem + SM::WT);
-    FDDesc* const   ring  = reinterpret_cast<FDDesc*>(smem + SM::RINGO);
-    const uint32_t  bars  = smem_u32(smem + SM::BARS);
-    auto full  = [&](int g) { return bars + 8u * (uint32_t)g; };
-    auto empty = [&](int g) { return bars + 64u + 8u * (uint32_t)g; };
-    auto dfull = [&](int r) { return bars + 128u + 8u * (uint32_t)r; };
-    const int tid = threadIdx.x, warp = (tid >> 5) & (PD_NDW - 1), lane = tid & 31;
-    const int n_items = n_list * S;
-
-    if (tid == 0) {
-        for (int g = 0; g < NG; ++g) {
-            mbar_init(full(g), PD_NDW);                 // one arrival per DG warp
-            mbar_init(empty(g), SM::PPG / 32);          // one arrival per IG warp of the group (and item)
-        }
-        for (int r = 0; r < PD_RING; ++r) mbar_init(dfull(r), 1);
-    }
-    {   // C starts out zeroed (rle_decode's zero fill, src/decompressor.cpp:17); IG keeps it that way
-        float4* c4 = reinterpret_cast<float4*>(C);
-        for (int i = tid; i < SM::CW / 4; i += PD_NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-
-    if (tid < PD_NDG) {
-        // ================================ decode group ================================
-        PDFetch<S> fe;
-        fe.dec = dec; fe.inv = inv; fe.unit_list = unit_list; fe.work_counter = work_counter;
-        fe.n_items = n_items; fe.stride = (int)gridDim.x; fe.ui_prev = (int)blockIdx.x - (int)gridDim.x;
-        fe.idx = 0; fe.uid = -1; fe.kreg = 0; fe.slot = ring;
-        if (tid == 0) {
-            for (int j = 0; j < 2; ++j) {               // items 0 and 1 of this CTA
-                fe.slot = &ring[j];
-                fe.a_index(); fe.b_unit(); fe.c_copy(); fe.d_count(); fe.e_publish(dfull(j));
-            }
-        }
-        bool bad = false;
-        for (int k = 0;; ++k) {
-            mbar_wait_cta(dfull(k & 3), (uint32_t)(k >> 2) & 1u);
-            const FDDesc& d = ring[k & 3];
-            if (d.ui >= n_items) break;
-            const DecUnitDev du = d.du;
-            const int K = d.K;
-            const uint32_t total = (uint32_t)du.total;
-            const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
-            const uint32_t epar = (uint32_t)(k - 1) & 1u;          // parity of empty[] completed by item k - 1
-            if (tid == 0) { fe.slot = &ring[(k + 2) & 3]; fe.a_index(); }
-            WC_PHASE_CLOCK(tp0);
-#ifdef WC_PHASE_PROFILE
-            long long dg_wait = 0;
-#endif
-
-            if constexpr (S == 1) {
-                constexpr uint32_t YZ = G::Y * G::Z;
-                uint32_t* const csum = csum2 + (k & 1) * 1032;
-                // Every warp owns a CONTIGUOUS run of the unit's chunks (32 pairs each) and walks it twice, 8 chunks per
-                // trip so that eight 256-byte loads are in flight per warp: P1 sums run+1 per chunk, P2 turns the sums
-                // into every chunk's starting flat index, P3 re-reads the chunks (L1 / L2) and scatters.
-                const int nch = (K + 31) >> 5;
-                const int cpw = (nch + PD_NDW - 1) / PD_NDW, cw0 = warp * cpw, cw1 = min(cw0 + cpw, nch);
-                // ---- P1: chunk sums ----
-#pragma unroll 1
-                for (int c0 = cw0; c0 < cw1; c0 += 8) {
-                    int2 pv[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int p = (c0 + j) * 32 + lane;
-                        pv[j] = (c0 + j < cw1 && p < K) ? __ldg(pairs + p) : make_int2(0, 0);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const bool in = c0 + j < cw1 && (c0 + j) * 32 + lane < K;
-                        if (in && pv[j].x < 0) bad = true;                 // negative run: flagged, counts as 0, skipped
-                        uint32_t inc = (in && pv[j].x >= 0) ? min((uint32_t)pv[j].x + 1u, (uint32_t)PD_CL) : 0u;
-                        inc = __reduce_add_sync(0xffffffffu, inc);
-                        if (lane == 0 && c0 + j < cw1) csum[c0 + j] = min(inc, (uint32_t)PD_CL);
-                    }
-                }
-                if (tid == 0) fe.b_unit();
-                {   // L2 prefetch of the NEXT item's list (its descriptor was published an item ago)
-                    const FDDesc& dn = ring[(k + 1) & 3];
-                    if (dn.ui < n_items) {
-                        const char* base = reinterpret_cast<const char*>(dn.du.pairs);
-                        const int nlines = (dn.K * 8 + 127) / 128;
-                        for (int i = tid; i < nlines; i += PD_NDG)
-                            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)i * 128));
-                    }
-                }
-                dg_barrier();
-                WC_PHASE_CLOCK(tp1);
-                // ---- P2: exclusive prefix E[0 .. nch] of the chunk sums, in place ----
-                {
-                    const int e0 = 2 * tid;
-                    const uint32_t a = e0 < nch ? csum[e0] : 0u, b = e0 + 1 < nch ? csum[e0 + 1] : 0u;
-                    uint32_t inc = a + b;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += v;
-                    }
-                    if (lane == 31) wt[warp] = inc;
-                    dg_barrier();
-                    uint32_t w = lane < PD_NDW ? wt[lane] : 0u;
-#pragma unroll
-                    for (int o = 1; o < PD_NDW; o <<= 1) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
-                        if (lane >= o) w += v;
-                    }
-                    const uint32_t wpre = warp ? __shfl_sync(0xffffffffu, w, warp - 1) : 0u;
-                    const uint32_t ex = wpre + inc - (a + b);
-                    if (e0 < nch) csum[e0] = ex;
-                    if (e0 + 1 < nch) csum[e0 + 1] = ex + a;
-                    if (e0 < nch && e0 + 2 >= nch) csum[nch] = ex + a + b;      // E[nch] = the whole list (nch <= 1024)
-                    if (nch == 0 && tid == 0) csum[0] = 0u;
-                }
-                if (tid == 0) fe.c_copy();
-                dg_barrier();
-                WC_PHASE_CLOCK(tp2);
-                // ---- P3: decode ----
-                uint32_t waited = k > 0 ? 0u : 0xffu;      // groups whose hand-back by IG (item k - 1) this warp has seen
-#pragma unroll 1
-                for (int c0 = cw0; c0 < cw1; c0 += 8) {
-                    int2     pv[8];
-                    uint32_t inc[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int p = (c0 + j) * 32 + lane;
-                        const bool in = c0 + j < cw1 && p < K;
-                        pv[j] = in ? __ldg(pairs + p) : make_int2(-1, 0);
-                        inc[j] = pv[j].x >= 0 ? min((uint32_t)pv[j].x + 1u, (uint32_t)PD_CL) : 0u;
-                    }
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint32_t v = __shfl_up_sync(0xffffffffu, inc[j], o);
-                            if (lane >= o) inc[j] += v;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (c0 + j < cw1) {                                  // warp-uniform
-                            const uint32_t e0 = csum[c0 + j], e1 = csum[c0 + j + 1];
-                            if (e0 < total && e1 > e0) {
-                                // the groups this chunk writes into: rows e0 / YZ .. (e1 - 1) / YZ (clipped to the box)
-                                const uint32_t r0 = e0 / YZ, r1 = min(e1 - 1u, total - 1u) / YZ;
-                                uint32_t need = 0;
-                                for (uint32_t r = r0; r <= r1 && r < r0 + 2u * G::hx; ++r) need |= 1u << ((r % G::hx) / GA);
-                                need &= ~waited;
-                                while (need) {
-                                    const int g = __ffs(need) - 1;
-                                    WC_PHASE_CLOCK(tw0);
-                                    mbar_wait_cta(empty(g), epar);
-#ifdef WC_PHASE_PROFILE
-                                    if (tid == 0) dg_wait += clock64() - tw0;
-#endif
-                                    waited |= 1u << g;
-                                    need &= need - 1u;
-                                }
-                            }
-                            const uint32_t f = e0 + inc[j] - 1u;
-                            if (pv[j].x >= 0 && f < total) C[(f / YZ) * SLAB + (f % YZ)] = __int_as_float(pv[j].y);
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0)
-                    for (int g = 0; g < NG; ++g) mbar_arrive_cta(full(g));
-                if (tid == 0) fe.d_count();
-#ifdef WC_PHASE_PROFILE
-                if (tid == 0 && blockIdx.x < 1024) {
-                    const long long t3 = clock64();
-                    unsigned long long* pc = g_phase_cycles[blockIdx.x];
-                    pc[0] += tp1 - tp0; pc[1] += tp2 - tp1; pc[2] += t3 - tp2; pc[3] += dg_wait; pc[5] += 1;
-                }
-#endif
-            } else {
-                // ---- slab item: one segment per warp and group, found through the unit's segment table ----
-                const uint32_t rank = (uint32_t)(d.ui % S);
-                const int2* tab = reinterpret_cast<const int2*>(du.coef);
-                constexpr uint32_t seglen = (uint32_t)G::seglen;
-                // round q of a warp: with x groups (NG > 1) the 16 segments of group q, rotated from group to group so that
-                // the heavy low-pass segments land on different warps; with one group per item (NG = 1) the segments
-                // warp, warp + 16, ... with the parity flipped every other round (fd_seg_of)
-                constexpr int NR = NG > 1 ? NG : G::nseg / PD_NDW;
-                static_assert(NR <= 16, "a warp holds the table entries of at most 16 segments");
-                auto seg_of = [&](int q, int& ip, int& sy) {
-                    if (NG > 1) {
-                        const int e = (warp + 5 * q) & 15;
-                        ip = (e >> 3) * G::hx + 4 * q + ((e >> 1) & 3);
-                        sy = e & 1;
-                    } else {
-                        const int sg = fd_seg_of(q, warp, PD_NDW);
-                        ip = sg >> 1;
-                        sy = sg & 1;
-                    }
-                    return ip * (2 * S) + sy * S + (int)rank;
-                };
-                int2 te = make_int2(0, 0);
-                if (lane < 2 * NR) {
-                    int ip, sy;
-                    const int m = seg_of(lane >> 1, ip, sy);
-                    te = __ldg(tab + m + (lane & 1));
-                }
-#pragma unroll 1
-                for (int q = 0; q < NR; ++q) {
-                    int ip, sy;
-                    const int m = seg_of(q, ip, sy);
-                    const int g = NG > 1 ? q : 0;
-                    const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * q), e0y = __shfl_sync(0xffffffffu, te.y, 2 * q);
-                    const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * q + 1);
-                    if (k > 0 && (NG > 1 || q == 0)) {
-                        WC_PHASE_CLOCK(tw0);
-                        mbar_wait_cta(empty(g), epar);
-#ifdef WC_PHASE_PROFILE
-                        if (tid == 0) dg_wait += clock64() - tw0;
-#endif
-                    }
-                    float* const cseg = C + ip * SLAB + sy * G::seglen;
-                    const uint32_t fseg = (uint32_t)m * seglen;
-                    uint32_t base = (uint32_t)e0y;
-#pragma unroll 1
-                    for (int c0 = e0x; c0 < e1x; c0 += 256) {
-                        if (e1x - c0 <= 128) fd_decode_chunks<4>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
-                        else                 fd_decode_chunks<8>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
-                    }
-                    if (NG > 1 || q == NR - 1) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cta(full(g));
-                    }
-                    if (tid == 0) {
-                        if (q == 1) fe.b_unit();
-                        if (q == 3) fe.c_copy();
-                        if (q == 5) fe.d_count();
-                    }
-                }
-#ifdef WC_PHASE_PROFILE
-                if (tid == 0 && blockIdx.x < 1024) {
-                    unsigned long long* pc = g_phase_cycles[blockIdx.x];
-                    pc[2] += clock64() - tp0; pc[3] += dg_wait; pc[5] += 1;
-                }
-#endif
-            }
-            if (tid == 0) fe.e_publish(dfull((k + 2) & 3));
-        }
-        if (bad) atomicOr(err, 1);
-    } else {
-        // ================================ inverse group ================================
-        const int q = tid - PD_NDG;
-        constexpr int o1 = G::hx * SLAB, o2 = G::nb * G::Z, o3 = G::hz;
-        for (int k = 0;; ++k) {
-            mbar_wait_cta(dfull(k & 3), (uint32_t)(k >> 2) & 1u);
-            const FDDesc& d = ring[k & 3];
-            if (d.ui >= n_items) break;
-            const InvUnitDev iu = d.iu;
-            const int b0 = (d.ui % S) * G::nb;
-            const bool f64 = iu.dtype == WC_F64;
-            const size_t es = f64 ? 8 : 4;
-            const size_t row_bytes = (size_t)G::X * es, plane_bytes = row_bytes * G::Y;
-            char* const out0 = static_cast<char*>(iu.out) + (size_t)(2 * b0) * row_bytes;
-#pragma unroll 1
-            for (int pass = 0; pass < SM::NPASS; ++pass) {
-                int g, a, bl, cpi;
-                if (NG > 1) {
-                    g = pass * SM::GPP + q / SM::PPG;
-                    const int idx = q % SM::PPG;
-                    // lanes: cp2 (1 bit), cq0 (1), al (2) -> conflict-free LDS.64 / STS.64; then the upper cq bits, then bl
-                    const int cp2 = idx & 1, cq0 = (idx >> 1) & 1, al = (idx >> 2) & 3, rest = idx >> 4;
-                    const int cqh = rest % (G::ncq / 2);
-                    bl = rest / (G::ncq / 2);
-                    a = 4 * g + al;
-                    cpi = 2 * (cq0 + 2 * cqh) + cp2;
-                } else {
-                    // one group: the pair-slot order of k_fused_decompress — a warp covers whole rows (2 c-pairs x 16 a)
-                    g = 0;
-                    const int qq = q + pass * PD_NDG;
-                    const int cp2 = qq & 1, t1 = qq >> 1;
-                    a = t1 % G::hx;
-                    const int t2 = t1 / G::hx;
-                    bl = t2 / G::ncq;
-                    cpi = 2 * (t2 % G::ncq) + cp2;
-                }
-                float* const csrc = C + a * SLAB + bl * G::Z + 2 * cpi;
-                WC_PHASE_CLOCK(ti0);
-                if (NG > 1 || pass == 0) mbar_wait_cta(full(g), (uint32_t)k & 1u);
-                WC_PHASE_CLOCK(ti1);
-                float2 v[8];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) {
-                    float2* const pc = reinterpret_cast<float2*>(csrc + (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3);
-                    v[o] = *pc;
-                    *pc  = make_float2(0.f, 0.f);                     // clean as you go
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ihaar_pair2(v[2 * j], v[2 * j + 1]);                 // X
-#pragma unroll
-                for (int zi = 0; zi < 2; ++zi)
-#pragma unroll
-                    for (int xi = 0; xi < 2; ++xi) ihaar_pair2(v[zi * 4 + xi], v[zi * 4 + 2 + xi]);   // Y
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ihaar_pair2(v[j], v[4 + j]);                         // Z
-                char* p0 = out0 + (size_t)(4 * cpi) * plane_bytes + (size_t)(2 * bl) * row_bytes + (size_t)a * 2 * es;
-#pragma unroll
-                for (int zi = 0; zi < 2; ++zi)
-#pragma unroll
-                    for (int yi = 0; yi < 2; ++yi) {
-                        const float2 lo = v[zi * 4 + yi * 2], hi = v[zi * 4 + yi * 2 + 1];   // xi = 0, 1
-                        char* pa = p0 + zi * plane_bytes + yi * row_bytes;        // block c:   planes 4cpi + zi
-                        char* pb = pa + 2 * plane_bytes;                          // block c+1: planes 4cpi + 2 + zi
-                        if (f64) {
-                            __stcs(reinterpret_cast<double2*>(pa), make_double2((double)lo.x, (double)hi.x));
-                            __stcs(reinterpret_cast<double2*>(pb), make_double2((double)lo.y, (double)hi.y));
-                        } else {
-                            __stcs(reinterpret_cast<float2*>(pa), make_float2(lo.x, hi.x));
-                            __stcs(reinterpret_cast<float2*>(pb), make_float2(lo.y, hi.y));
-                        }
-                    }
-                if (NG > 1 || pass == SM::NPASS - 1) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cta(empty(g));
-                }
-#ifdef WC_PHASE_PROFILE
-                if (q == 0 && blockIdx.x < 1024) {
-                    unsigned long long* pc = g_phase_cycles[blockIdx.x];
-                    pc[4] += ti1 - ti0; pc[6] += clock64() - ti1; pc[7] += 1;
-                }
-#endif
-            }
-        }
-    }
-}
-
-template <int S, class G, int GA>
-static cudaError_t launch_pd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n, int* err,
-                             int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter) {
-    auto kern = k_pipe_decompress<S, G, GA>;
-    constexpr int smem = PDSmem<S, G, GA>::TOTAL;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    const long long items = (long long)n * S;
-    const int nc = (int)(sm_count < items ? sm_count : items);
-    ls->begin(kid, st);
-    kern<<<nc, PD_NT, smem, st>>>(dec, inv, list, n, err, work_counter);
-    ls->end(st);
-    return cudaGetLastError();
-}
-
-// the one-CTA-per-unit index kernel on its own (WC_OPT_SEG_INDEX = 1 in front of the pipelined decode kernel)
-cudaError_t launch_seg_index1(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n, int* err,
-                              int sm_count, cudaStream_t st, LaunchStats* ls) {
-    if (n <= 0 || !fused_decode_needs_table(fused_cls)) return cudaSuccess;
-    const int nb = n < 2 * sm_count ? n : 2 * sm_count;
-    ls->begin(KID_SEG_INDEX, st);
-    k_seg_index<512><<<nb, 512, 0, st>>>(dec, inv, list, n, err, fused_decode_slabs(fused_cls));
-    ls->end(st);
-    return cudaGetLastError();
-}
-
-// variant 1: one hand-over group per item (whole-row stores); variant 2: groups of 4 x-blocks
-bool pipe_decode_class(int fused_cls, int variant) {
-    if (variant == 1) return fused_cls == FUSED_CLS_CUBE32;      // slab items gain nothing from one group (see DESIGN)
-    return variant == 2 && (fused_cls == FUSED_CLS_CUBE32 || fused_cls == FUSED_CLS_CUBE64);
-}
-
-cudaError_t launch_pipe_decompress(int fused_cls, int variant, const DecUnitDev* dec, const InvUnitDev* inv,
-                                   const int* unit_list, int n_list, int* err, int sm_count, cudaStream_t st,
-                                   LaunchStats* ls, int* work_counter) {
-    if (n_list <= 0) return cudaSuccess;
-    typedef SGeom<32, 32, 32, 8, 1> G32;
-    typedef SGeom<64, 64, 64, 8, 8> G64;
-    if (fused_cls == FUSED_CLS_CUBE32 && variant == 1)
-        return launch_pd<1, G32, G32::hx>(KID_PIPE_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
-    if (fused_cls == FUSED_CLS_CUBE32 && variant == 2)
-        return launch_pd<1, G32, 4>(KID_PIPE_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
-    if (fused_cls == FUSED_CLS_CUBE64 && variant == 1)
-        return launch_pd<8, G64, G64::hx>(KID_PIPE_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
-    if (fused_cls == FUSED_CLS_CUBE64 && variant == 2)
-        return launch_pd<8, G64, 4>(KID_PIPE_D8S, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
-    return cudaErrorInvalidValue;
-}
-
 // Which fused-decompress class a unit belongs to (FUSED_CLS_*, 0 = generic): same geometry rules as compress,
 // plus the output pointer alignment for the vector stores.
 int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_ptr) {
@@ -2378,8 +2102,11 @@ bool fused_decode_needs_table(int fused_cls) {
 
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
-                                    cudaStream_t st, LaunchStats* ls, int* work_counter, bool build_tables) {
+                                    cudaStream_t st, LaunchStats* ls, int* work_counter, bool build_tables, int stage) {
     if (n_list <= 0) return cudaSuccess;
+    if (stage && fused_cls == FUSED_CLS_CUBE32)
+        return launch_fd<1, 32768, 1024, true, true>(KID_STAGED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls,
+                                                     work_counter, false, stage == 2);
     switch (fused_cls) {
     case FUSED_CLS_R1:
         return launch_fd<1, 32768, 512, false>(KID_FUSED_D1, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter, false);

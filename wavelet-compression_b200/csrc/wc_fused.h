@@ -35,7 +35,9 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
                                     cudaStream_t st, LaunchStats* ls, int* work_counter = nullptr,
-                                    bool build_tables = true);
+                                    bool build_tables = true, int stage = 0);
+// stage (32^3 cubes): 0 = pairs straight from global memory, 1 = table-less units decode from a shared-memory staging
+// area filled by TMA bulk copies one item ahead (k_staged_decompress), 2 = units with a segment table as well
 
 // Chunk-parallel segment index for packed streams without tables (see k_seg_index2), and the device-side
 // preparation of a dense stream (k_dec_prepare).  SEG_CHUNK pairs per work item.
@@ -47,14 +49,6 @@ cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUni
 cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
                                const int* tab_list, const int* tab_n, int n_tab_lists, int2* items, int* rec_start,
                                const long long* item_off, int* err, cudaStream_t st, LaunchStats* ls);
-
-// Warp-specialised, pipelined decompress of the literal cubes (32^3, 64^3): decode and inverse + store overlap.
-bool pipe_decode_class(int fused_cls, int variant);
-cudaError_t launch_seg_index1(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n, int* err,
-                              int sm_count, cudaStream_t st, LaunchStats* ls);
-cudaError_t launch_pipe_decompress(int fused_cls, int variant, const DecUnitDev* dec, const InvUnitDev* inv,
-                                   const int* unit_list, int n_list, int* err, int sm_count, cudaStream_t st,
-                                   LaunchStats* ls, int* work_counter);
 
 #ifdef WC_PHASE_PROFILE
 cudaError_t debug_phase_cycles(unsigned long long out[8], bool reset);
