@@ -12,6 +12,7 @@ import torch
 
 pkg = g.package()
 which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+variants = [(0, int(c)) for c in sys.argv[2]] if len(sys.argv) > 2 else [(0, 1), (0, 0)]
 sys.argv = sys.argv[:1]
 import bench
 
@@ -41,7 +42,7 @@ have_phase = hasattr(ctx.lib, "wc_debug_phase_cycles")
 if have_phase:
     ctx.lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 out = (ctypes.c_ulonglong * 8)()
-for seg, pipe in ((0, 1), (0, 0)):
+for seg, pipe in variants:
     ctx2 = pkg.Context(0, stream=stream.cuda_stream)
     ctx2.set_option(capi.WC_OPT_SEG_INDEX, seg)
     ctx2.set_option(capi.WC_OPT_DECODE_PIPE, pipe)
@@ -75,6 +76,6 @@ for seg, pipe in ((0, 1), (0, 0)):
         units = max(v[5], 1)
         for n, c in zip(["top", "-", "decode (scan+scatter)", "barrier+stage/prefetch", "inverse+store"], v[:5]):
             print(f"    {n:22s} {c / units:9.0f} cycles/item  {100 * c / max(v[:5].sum(), 1):5.1f}%")
-        print("    total cycles/item", v[:5].sum() / units, "items/step", units / 10)
+        print(f"    total cycles/item {v[:5].sum() / units:.0f}  (staged decode: waiting for the bulk copy {v[6] / units:.0f})  items/step {units / 10:.0f}")
     dp.close()
     ctx2.close()

@@ -98,7 +98,7 @@ struct wc_ctx {
     uint64_t     h2d = 0, d2h = 0;
     int          opt_path = 0;
     int          opt_overlap = 1;
-    int          opt_seg_index = 0;   // 0 = chunk-parallel k_seg_index2, 1 = one CTA per unit (k_seg_index)
+    int          opt_seg_index = 0;   // 0 = streamed k_seg_index3 (TMA ring), 1 = k_seg_index (direct loads)
     int          opt_copy_only = 0;   // probe: wc_plan_compress_to_host moves the bytes but skips the kernels
     int          opt_ingest_stats = 0; // compress also records per-unit min / max of the narrowed inputs
     int          opt_decode_pipe = 1;  // 32^3 cubes: table-less lists decode from the TMA-fed staging area
@@ -107,7 +107,6 @@ struct wc_ctx {
     // workspace of the blocking decompress / rmse / primitive calls (grow-only)
     DevBuf ws_pairs, ws_coef, ws_boxes, ws_tbl0, ws_tbl1, ws_tbl2, ws_tiles0, ws_tiles1, ws_sum,
         ws_misc, ws_a, ws_b;
-    DevBuf ws_chunk, ws_status;   // chunk-parallel segment index: chunk_start and look-back status words
     PinBuf ws_pin;
     // second stream for running the single-CTA and cluster kernels of one step concurrently
     cudaStream_t s_aux = nullptr;
@@ -279,8 +278,6 @@ int wc_destroy(wc_ctx* ctx) {
                        &ctx->ws_tbl2, &ctx->ws_tiles0, &ctx->ws_tiles1, &ctx->ws_sum, &ctx->ws_misc,
                        &ctx->ws_a, &ctx->ws_b };
     for (DevBuf* b : bufs) b->release();
-    ctx->ws_chunk.release();
-    ctx->ws_status.release();
     ctx->ws_pin.release();
     ctx->ls.destroy();
     ctx->d_counter.release();
@@ -1107,33 +1104,13 @@ static int relaunch_decompress(wc_ctx* ctx, const DecCache* cache, DevBuf& d_dec
     return WC_OK;
 }
 
-// Segment tables of one slab-decoded class list with the chunk-parallel index kernel.  K is known on the
-// host here (blocking API): chunk_start is built on the host and uploaded.
-static int build_tables_chunked(wc_ctx* ctx, int fused_cls, const std::vector<DecUnitDev>& du, const std::vector<int>& list,
-                                const DecUnitDev* d_dec, const InvUnitDev* d_inv, int* d_err) {
-    const int n = (int)list.size();
-    std::vector<int>  cs(n + 1);
-    std::vector<int2> rec;
-    for (int j = 0; j < n; ++j) {
-        cs[j] = (int)rec.size();
-        const int k = du[list[j]].npairs;
-        const int nch = k > 0 ? (k + SEG_INDEX_CHUNK - 1) / SEG_INDEX_CHUNK : 1;
-        for (int c = 0; c < nch; ++c) rec.push_back(make_int2(list[j], c));
-    }
-    cs[n] = (int)rec.size();
-    const size_t items = rec.size();
-    CTX_CUDA(ctx, ctx->ws_chunk.reserve(sizeof(int) * (size_t)(n + 1) + 16 + sizeof(int2) * std::max<size_t>(items, 1)));
-    CTX_CUDA(ctx, ctx->ws_status.reserve(sizeof(u64) * std::max<size_t>(items, 1)));
+// Segment tables of one slab-decoded class list with the streamed index kernel (k_seg_index3).
+static int build_tables_streamed(wc_ctx* ctx, int fused_cls, const int* d_list, int n, const DecUnitDev* d_dec,
+                                 const InvUnitDev* d_inv, int* d_err) {
     CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
-    int*  d_cs  = ctx->ws_chunk.as<int>();
-    int2* d_rec = reinterpret_cast<int2*>(ctx->ws_chunk.as<char>() + align_up(sizeof(int) * (size_t)(n + 1), 16));
-    CTX_CUDA(ctx, cudaMemcpyAsync(d_cs, cs.data(), sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
-    if (items) CTX_CUDA(ctx, cudaMemcpyAsync(d_rec, rec.data(), sizeof(int2) * items, cudaMemcpyHostToDevice, ctx->stream));
-    CTX_CUDA(ctx, cudaMemsetAsync(ctx->ws_status.p, 0, sizeof(u64) * std::max<size_t>(items, 1), ctx->stream));
     int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
     CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-    CTX_CUDA(ctx, launch_seg_index2(fused_cls, d_dec, d_inv, d_rec, d_cs, 0, n, (long long)items, ctx->ws_status.as<u64>(),
-                                    counter, d_err, ctx->sm_count, ctx->stream, &ctx->ls));
+    CTX_CUDA(ctx, launch_seg_index3(fused_cls, d_dec, d_inv, d_list, n, counter, d_err, ctx->sm_count, ctx->stream, &ctx->ls));
     return WC_OK;
 }
 
@@ -1228,13 +1205,13 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
                                           cudaMemcpyHostToDevice, ctx->stream));
             bool v1_tables = build_tables[k];
             if (build_tables[k] && ctx->opt_seg_index == 0) {
-                // every unit of a slab-decoded class arrives either with or without its table; the chunk-parallel
+                // every unit of a slab-decoded class arrives either with or without its table; the streamed
                 // index only handles lists where all do without (mixed lists keep the one-CTA-per-unit kernel)
                 bool all_without = true;
                 for (int i : fl[k]) all_without = all_without && !slab_tab[i];
                 if (all_without) {
-                    int rc = build_tables_chunked(ctx, FL_CLASS[k], du, fl[k], d_dec_units.as<DecUnitDev>(),
-                                                  d_inv_units.as<InvUnitDev>(), d_err.as<int>());
+                    int rc = build_tables_streamed(ctx, FL_CLASS[k], dl + o, (int)fl[k].size(), d_dec_units.as<DecUnitDev>(),
+                                                   d_inv_units.as<InvUnitDev>(), d_err.as<int>());
                     if (rc != WC_OK) return rc;
                     v1_tables = false;
                 }
@@ -1397,14 +1374,8 @@ struct wc_dplan {
     std::vector<int> fl[FL_N];            // unit ids per fused class (ascending)
     bool      has_generic = false;        // some unit needs the generic kernels: decode falls back to run_decompress
     size_t    fl_off[FL_N] = {};          // offset of each class list inside d_lists
-    size_t    cs_off[FL_N] = {};          // offset of each slab-decoded class's chunk_start inside d_chunk
-    size_t    st_off[FL_N] = {};          // offset of its status words inside d_status
-    long long st_items[FL_N] = {};        // bound of its index items (K = ncoef)
-    std::vector<long long> st_prefix[FL_N];   // per listed unit: items bound in front of it (sub-list launches)
-    int       n_tab_lists = 0;
-    size_t    tab_floats = 0, status_items = 0, chunk_ints = 0;
-    DevBuf d_dec, d_inv, d_lists, d_tab, d_chunk, d_status, d_err, d_stage_out, d_pairs, d_npairs, d_tabn, d_counter,
-        d_items, d_itemoff;
+    size_t    tab_floats = 0;
+    DevBuf d_dec, d_inv, d_lists, d_tab, d_err, d_stage_out, d_pairs, d_npairs, d_counter;
     PinBuf h_err;
     unsigned counter_next = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -1482,31 +1453,11 @@ int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_sp
     DP_RESERVE(dp->d_counter, 64 * sizeof(int));
     if ((e = dp->h_err.reserve(64)) != cudaSuccess) return fail(e, "dplan pinned alloc");
     size_t n_fused = 0;
-    std::vector<int> lists, tabn;
+    std::vector<int> lists;
     for (int k = 0; k < FL_N; ++k) {
         dp->fl_off[k] = n_fused;
         n_fused += dp->fl[k].size();
         lists.insert(lists.end(), dp->fl[k].begin(), dp->fl[k].end());
-    }
-    // slab-decoded classes come first in FL_CLASS order, so their lists are a prefix of `lists`: exactly the
-    // layout k_dec_prepare walks (tab_list + tab_n)
-    for (int k = 0; k < FL_N; ++k) {
-        if (dp->fl[k].empty() || !fused_decode_needs_table(FL_CLASS[k])) continue;
-        tabn.push_back((int)dp->fl[k].size());
-        dp->cs_off[k] = dp->chunk_ints;
-        dp->chunk_ints += dp->fl[k].size() + 1;
-        dp->st_off[k] = dp->status_items;
-        dp->st_prefix[k].resize(dp->fl[k].size() + 1);
-        long long items = 0;
-        for (size_t j = 0; j < dp->fl[k].size(); ++j) {
-            dp->st_prefix[k][j] = items;
-            const long long n = du[dp->fl[k][j]].total;
-            items += std::max<long long>(1, (n + SEG_INDEX_CHUNK - 1) / SEG_INDEX_CHUNK);
-        }
-        dp->st_prefix[k][dp->fl[k].size()] = items;
-        dp->st_items[k] = items;
-        dp->status_items += (size_t)items;
-        ++dp->n_tab_lists;
     }
     for (int i = 0; i < n_units; ++i)
         if (cls_of[i] > 0 && fused_decode_needs_table(cls_of[i])) {
@@ -1514,20 +1465,6 @@ int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_sp
             iu[i].coef = du[i].coef;
         }
     DP_RESERVE(dp->d_lists, sizeof(int) * std::max<size_t>(n_fused, 1));
-    DP_RESERVE(dp->d_tabn, sizeof(int) * std::max<size_t>(tabn.size(), 1));
-    DP_RESERVE(dp->d_chunk, sizeof(int) * std::max<size_t>(dp->chunk_ints, 1));
-    DP_RESERVE(dp->d_status, sizeof(u64) * std::max<size_t>(dp->status_items, 1));
-    DP_RESERVE(dp->d_items, sizeof(int2) * std::max<size_t>(dp->status_items, 1));
-    DP_RESERVE(dp->d_itemoff, sizeof(long long) * FL_N);
-    {
-        std::vector<long long> ioff;
-        for (int k = 0; k < FL_N; ++k)
-            if (!dp->fl[k].empty() && fused_decode_needs_table(FL_CLASS[k])) ioff.push_back((long long)dp->st_off[k]);
-        if (!ioff.empty())
-            if ((e = cudaMemcpyAsync(dp->d_itemoff.p, ioff.data(), sizeof(long long) * ioff.size(), cudaMemcpyHostToDevice,
-                                     ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
-        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "dplan sync");   // ioff is a local
-    }
 #undef DP_RESERVE
     if (n_units) {
         if ((e = cudaMemcpyAsync(dp->d_dec.p, du.data(), sizeof(DecUnitDev) * n_units, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
@@ -1535,8 +1472,6 @@ int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_sp
     }
     if (n_fused)
         if ((e = cudaMemcpyAsync(dp->d_lists.p, lists.data(), sizeof(int) * n_fused, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
-    if (!tabn.empty())
-        if ((e = cudaMemcpyAsync(dp->d_tabn.p, tabn.data(), sizeof(int) * tabn.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e, "dplan upload");
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "dplan sync");
     *out = dp;
     return WC_OK;
@@ -1550,10 +1485,8 @@ int wc_dplan_destroy(wc_dplan* dp) {
     if (dp->s_h2d) { cudaStreamSynchronize(dp->s_h2d); cudaStreamDestroy(dp->s_h2d); }
     if (dp->s_d2h) { cudaStreamSynchronize(dp->s_d2h); cudaStreamDestroy(dp->s_d2h); }
     for (cudaEvent_t e : dp->ev) cudaEventDestroy(e);
-    dp->d_items.release();
-    dp->d_itemoff.release();
-    DevBuf* bufs[] = { &dp->d_dec, &dp->d_inv, &dp->d_lists, &dp->d_tab, &dp->d_chunk, &dp->d_status, &dp->d_err,
-                       &dp->d_stage_out, &dp->d_pairs, &dp->d_npairs, &dp->d_tabn, &dp->d_counter, &dp->g_coef,
+    DevBuf* bufs[] = { &dp->d_dec, &dp->d_inv, &dp->d_lists, &dp->d_tab, &dp->d_err,
+                       &dp->d_stage_out, &dp->d_pairs, &dp->d_npairs, &dp->d_counter, &dp->g_coef,
                        &dp->g_dec, &dp->g_inv, &dp->g_tiles, &dp->g_ptiles, &dp->g_psum, &dp->g_list };
     for (DevBuf* b : bufs) b->release();
     dp->h_err.release();
@@ -1580,10 +1513,7 @@ static int dplan_launch_range(wc_dplan* dp, int u0, int u1, size_t fi[FL_N]) {
                 if (ctx->opt_seg_index == 0) {
                     int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
                     CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-                    CTX_CUDA(ctx, launch_seg_index2(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(),
-                                                    dp->d_items.as<int2>() + dp->st_off[k], dp->d_chunk.as<int>() + dp->cs_off[k],
-                                                    (int)fi[k], (int)j, dp->st_prefix[k][j] - dp->st_prefix[k][fi[k]],
-                                                    dp->d_status.as<u64>() + dp->st_off[k],
+                    CTX_CUDA(ctx, launch_seg_index3(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
                                                     counter, dp->d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls));
                 } else {
                     v1 = true;
@@ -1677,11 +1607,7 @@ int wc_dplan_decode(wc_dplan* dp, const wc_pair* pairs, const int32_t* npairs, i
         if (rc != WC_OK) return rc;
     } else {
         if (dp->tab_floats) CTX_CUDA(ctx, cudaMemsetAsync(dp->d_tab.p, 0, sizeof(float) * dp->tab_floats, ctx->stream));
-        if (dp->status_items && ctx->opt_seg_index == 0)
-            CTX_CUDA(ctx, cudaMemsetAsync(dp->d_status.p, 0, sizeof(u64) * dp->status_items, ctx->stream));
-        CTX_CUDA(ctx, launch_dec_prepare(dp->d_dec.as<DecUnitDev>(), n, d_pairs, d_npairs, dp->d_lists.as<int>(),
-                                         dp->d_tabn.as<int>(), dp->n_tab_lists, dp->d_items.as<int2>(), dp->d_chunk.as<int>(),
-                                         dp->d_itemoff.as<long long>(), dp->d_err.as<int>(),
+        CTX_CUDA(ctx, launch_dec_prepare(dp->d_dec.as<DecUnitDev>(), n, d_pairs, d_npairs, dp->d_err.as<int>(),
                                          ctx->stream, &ctx->ls));
     }
     size_t fi[FL_N] = {};

@@ -30,6 +30,7 @@
 //   trip and it measured slower than direct loads + L2 prefetch.  The first decompress used 8-CTA clusters
 //   with a DSMEM scatter; the segment-table design replaced it.
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "wc_common.cuh"
@@ -141,6 +142,18 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait_cluster(bar, parity)) { }
+}
+__device__ __forceinline__ bool mbar_try_wait_cta(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_cta(bar, parity)) { }
 }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -1209,222 +1222,216 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
     }
 }
 
-// ---- chunk-parallel segment index (packed streams that arrive without tables: files, wc_dplan) -------
-// Same table as k_seg_index, but a work item is one CHUNK of SEG_CHUNK consecutive pairs of one unit
-// instead of a whole unit, so the index pass streams at HBM speed (a CTA per unit walked its ~100 k pairs
-// tile after tile, latency-bound).  A chunk needs the flat index its first pair starts from = the sum of
-// run+1 over all earlier pairs of the unit: chunks publish their sums in a status word and look back over
-// their predecessors (single-pass "decoupled look-back" scan; items are handed out in increasing order
-// from a global counter, so a predecessor is always running or done — no deadlock).
-//   chunk_start[j]  = first item of the j-th listed unit (exclusive prefix of max(1, ceil(K / SEG_CHUNK)));
-//                     built on the host (wc_decompress_batch) or by k_dec_prepare (wc_dplan).
-//   status[item]    = 0 | (1 << 62 | chunk sum) | (2 << 62 | inclusive prefix), zeroed before the launch.
-//   The unit's table memory is zeroed before the launch as well: entries nobody assigns (corrupt streams
-//   with negative runs) then describe empty pair ranges instead of garbage.
-constexpr int SEG_CHUNK = 4096;                      // 512 threads x FD_PPT pairs
-__device__ __forceinline__ u64 ld_acquire_u64(const u64* p) {
-    u64 v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u64(u64* p, u64 v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+// ---- streamed segment index (packed streams that arrive without tables: files, wc_dplan) -------------
+// Same table as k_seg_index, built at memory speed: a CTA walks one unit's list tile after tile, but the tiles
+// arrive through a three-stage ring of shared-memory buffers that the TMA engine fills (cp.async.bulk, one
+// mbarrier per stage) two to three tiles ahead, so the per-tile chain is shared-memory reads + one block scan and
+// never waits for HBM (k_seg_index: loads -> scan -> barrier in sequence per tile, 2 TB/s; the chunk-parallel
+// look-back version that came between them was bound by five dependent global round trips per 32 KB work item).
+// Two CTAs per SM, units handed out dynamically.
+//   A thread owns SI_PPT consecutive pairs of a tile (odd: conflict-free 8-byte shared-memory reads).
+//   Bulk copies need 16-byte aligned addresses and sizes: a list that starts on an odd pair is fetched from one
+//   pair earlier, an odd count is rounded up — both stay inside the 16-byte granule of a valid pair, so they never
+//   leave the allocation's pages; slot r + s0 of a stage holds the tile's r-th pair.
+constexpr int SI_NT = 512, SI_PPT = 7, SI_TILE = SI_NT * SI_PPT, SI_STAGES = 3, SI_SLOTS = SI_TILE + 2;
+constexpr uint32_t SI_CL = 1u << 19;   // clamp of one pair's run + 1: > any ncoef of a slab-decoded unit (262144);
+                                       // SI_TILE * SI_CL < 2^31 and the carry is clamped at 2^30: u32 sums never wrap
+constexpr int SI_SMEM = SI_STAGES * SI_SLOTS * 8 + 64 + 2 * 32 * 4 + 32;
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 3)
-k_seg_index2(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
-             const int2* __restrict__ items /* (unit id, chunk) per work item, unit-major, compact */,
-             const int* __restrict__ rec_start /* first item of every listed unit; [n] = total */, int j0, int j1,
-             u64* __restrict__ status, int* __restrict__ work_counter, int* __restrict__ err, int slabs) {
-    static_assert(NT * FD_PPT == SEG_CHUNK, "one tile per chunk");
-    __shared__ uint32_t s_wt[32];
-    __shared__ int s_item;
-    __shared__ uint32_t s_base;
-    const int tid = threadIdx.x;
-    const int first = rec_start[j0], n_items = rec_start[j1] - first;      // the listed units [j0, j1)
+__global__ void __launch_bounds__(SI_NT, 2)
+k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv, const int* __restrict__ unit_list,
+             int n_list, int* __restrict__ err, int slabs, int* __restrict__ work_counter) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    int2* const      stage  = reinterpret_cast<int2*>(smem);                                   // [SI_STAGES][SI_SLOTS]
+    const uint32_t   bars   = smem_u32(smem + SI_STAGES * SI_SLOTS * 8);                       // [SI_STAGES] mbarriers
+    uint32_t* const  s_wt   = reinterpret_cast<uint32_t*>(smem + SI_STAGES * SI_SLOTS * 8 + 64);   // [2][32]
+    int* const       s_unit = reinterpret_cast<int*>(smem + SI_STAGES * SI_SLOTS * 8 + 64 + 256);
+    u64* const       s_last = reinterpret_cast<u64*>(smem + SI_STAGES * SI_SLOTS * 8 + 64 + 256 + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u64 pol = l2_policy_evict_first();
+    if (tid == 0) {
+        for (int k = 0; k < SI_STAGES; ++k) mbar_init(bars + 8 * k, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t q0 = 0;                 // tiles this CTA has streamed so far: tile q uses stage q % 3, parity (q / 3) & 1
+    bool bad = false;
     for (;;) {
-        if (tid == 0) s_item = atomicAdd(work_counter, 1);
-        __syncthreads();
-        if (s_item >= n_items) break;
-        const int item = first + s_item;
-        const int2 it = __ldg(items + item);
-        const int uid = it.x, c = it.y, item0 = item - c;     // the unit's chunks are consecutive items
+        if (tid == 0) { *s_unit = atomicAdd(work_counter, 1); *s_last = 0ull; }
+        __syncthreads();             // also: every stage of the previous unit has been consumed
+        const int ui = *s_unit;
+        if (ui >= n_list) break;
+        const int uid = unit_list[ui];
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
         FGeom g;
         fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g);
         const uint32_t seglen = (uint32_t)g.seglen, total = (uint32_t)du.total;
-        const int nseg = g.nseg * slabs;
+        const int nseg = g.nseg * slabs;                   // == total / seglen
         int2* const tab = reinterpret_cast<int2*>(du.coef);
         const int K = du.npairs_dev ? *du.npairs_dev : du.npairs;
         const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
-        const bool vec16 = (reinterpret_cast<uintptr_t>(pairs) & 15u) == 0;
+        const int s0 = (int)((reinterpret_cast<uintptr_t>(pairs) >> 3) & 1u);
+        const int ntiles = (K + SI_TILE - 1) / SI_TILE;
         FastDiv dsl;
-        dsl.init(seglen, total);
-        const int p = c * SEG_CHUNK + tid * FD_PPT;
-        int2 pr[FD_PPT];
-        fd_load_tile(pairs, vec16, p, K, pr);
-        bool bad = false;
-        uint32_t ttot;
-        uint32_t pre = fd_tile_scan<NT>(pr, K - p, s_wt, bad, ttot);
-        // chunk base through the look-back: warp 0 inspects 32 predecessors per round (one L2 round trip for all
-        // of them instead of one per predecessor) and sums the aggregates in front of the nearest published prefix
-        if (tid < 32) {
-            uint32_t base = 0;
-            if (c > 0) {
-                if (tid == 0) st_release_u64(status + item, (1ull << 62) | ttot);
-                int hi = item - 1;                       // nearest predecessor not yet accounted for
-                for (;;) {
-                    const int k = hi - tid;              // lane 0 = nearest
-                    u64 v = 2ull << 62;                  // lanes in front of the unit's first chunk: prefix 0
-                    if (k >= item0) do { v = ld_acquire_u64(status + k); } while ((v >> 62) == 0);
-                    const uint32_t pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                    const int first = pm ? __ffs(pm) - 1 : 32;          // nearest lane holding an inclusive prefix
-                    uint32_t x = tid <= first ? (uint32_t)v : 0u;
+        dsl.init(seglen, total + seglen);
+        auto issue = [&](int t) {                          // thread 0: tile t of this unit into its stage
+            const uint32_t q = q0 + (uint32_t)t, st = q % SI_STAGES;
+            const int cnt = min(SI_TILE, K - t * SI_TILE) + s0;
+            const uint32_t bytes = (uint32_t)((cnt + 1) & ~1) * 8u;
+            const uint32_t bar = bars + 8 * st;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(smem_u32(stage + st * SI_SLOTS)), "l"(pairs + (size_t)t * SI_TILE - s0), "r"(bytes), "r"(bar), "l"(pol)
+                         : "memory");
+        };
+        if (tid == 0)
+            for (int t = 0; t < ntiles && t < SI_STAGES; ++t) issue(t);
+        uint32_t carry = 0;
+        int gk = 0, gl = -1;                               // this thread's last in-box pair: index + 1, flat index
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const uint32_t q = q0 + (uint32_t)t, st = q % SI_STAGES;
+            mbar_wait_cta(bars + 8 * st, (q / SI_STAGES) & 1u);
+            const int p = t * SI_TILE + tid * SI_PPT;      // first pair of this thread
+            int2 pr[SI_PPT];
+            {
+                const int2* sp = stage + st * SI_SLOTS + tid * SI_PPT + s0;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) x = sat_add(x, __shfl_xor_sync(0xffffffffu, x, o));
-                    base = sat_add(base, x);
-                    if (pm) break;
-                    hi -= 32;
-                }
+                for (int j = 0; j < SI_PPT; ++j) pr[j] = sp[j];
             }
-            if (tid == 0) {
-                st_release_u64(status + item, (2ull << 62) | sat_add(base, ttot));
-                s_base = base;
-            }
-        }
-        __syncthreads();
-        const uint32_t base = s_base;
-        pre = sat_add(pre, base);
-        // last in-box pair of this thread's group, and the boundaries its group crosses (as k_seg_index)
-        int gl = -1, gk = 0;
-        {
-            uint32_t rp = pre;
+            if (p + SI_PPT > K) {                          // pairs past the end of the list are dead: (-1, 0)
 #pragma unroll
-            for (int j = 0; j < FD_PPT; ++j) {
-                if (p + j < K && pr[j].x >= 0) {
-                    const uint32_t f = sat_add(rp, (uint32_t)pr[j].x);
-                    if (f < total) { gl = (int)f; gk = p + j + 1; }
-                    rp = sat_add(rp, (uint32_t)pr[j].x + 1u);
-                }
+                for (int j = 0; j < SI_PPT; ++j) if (p + j >= K) pr[j] = make_int2(-1, 0);
             }
-        }
-        if (gl >= 0) {
-            uint32_t m = pre == 0 ? 0u : dsl.div(pre - 1u) + 1u;
-            uint32_t fb = m * seglen;
-            if ((uint32_t)gl >= fb) {
-                uint32_t rp = pre;
+            uint32_t inc[SI_PPT];
+            int any = 0;
 #pragma unroll
-                for (int j = 0; j < FD_PPT; ++j) {
-                    if (p + j < K && pr[j].x >= 0) {
-                        const uint32_t f = sat_add(rp, (uint32_t)pr[j].x);
-                        if (f < total)
-                            for (; fb <= f; fb += seglen, ++m) tab[m] = make_int2(p + j, (int)rp - 1);
-                        rp = sat_add(rp, (uint32_t)pr[j].x + 1u);
+            for (int j = 0; j < SI_PPT; ++j) {
+                any |= pr[j].x;
+                inc[j] = min((uint32_t)pr[j].x + 1u, SI_CL);
+            }
+            if (any < 0) {
+#pragma unroll
+                for (int j = 0; j < SI_PPT; ++j)
+                    if (pr[j].x < 0) { inc[j] = 0; if (p + j < K) bad = true; }
+            }
+            const uint32_t s = ((inc[0] + inc[1]) + (inc[2] + inc[3])) + ((inc[4] + inc[5]) + inc[6]);
+            static_assert(SI_PPT == 7, "sum above");
+            uint32_t w = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            uint32_t* const wt = s_wt + (t & 1) * 32;
+            if (lane == 31) wt[warp] = w;
+            __syncthreads();                               // every thread has read its pairs: the stage is free
+            if (tid == 0 && t + SI_STAGES < ntiles) issue(t + SI_STAGES);
+            uint32_t ws = lane < SI_NT / 32 ? wt[lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += v;
+            }
+            const uint32_t ttot = __shfl_sync(0xffffffffu, ws, 31);
+            uint32_t wpre = __shfl_sync(0xffffffffu, ws, (warp + 31) & 31);
+            if (warp == 0) wpre = 0;
+            const uint32_t pre = carry + wpre + (w - s);   // flat index this thread's first run starts at
+            carry = min(carry + ttot, 1u << 30);
+            if (s != 0 && pre < total) {
+                const uint32_t end1 = pre + s - 1u;        // flat index of the thread's last live pair
+                if (any >= 0 && end1 < total) { gk = p + SI_PPT; gl = (int)end1; }
+                // segment boundaries m * seglen inside [pre, end1]: each belongs to the pair whose interval
+                // [start of its run, its flat index] holds it
+                const uint32_t mlo = dsl.div(pre + seglen - 1u), mhi = dsl.div(min(end1, total - 1u));
+                if (mlo <= mhi || any < 0 || end1 >= total) {
+                    uint32_t rp = pre, m = mlo, fb = mlo * seglen;
+#pragma unroll
+                    for (int j = 0; j < SI_PPT; ++j) {
+                        if (inc[j]) {
+                            const uint32_t f = rp + inc[j] - 1u;
+                            if (f < total) {
+                                gk = p + j + 1; gl = (int)f;
+                                for (; fb <= f; fb += seglen, ++m) tab[m] = make_int2(p + j, (int)rp - 1);
+                            }
+                            rp += inc[j];
+                        }
                     }
                 }
             }
         }
-        if (bad) atomicOr(err, 1);
-        // The tail entries (segments that start after the unit's last in-box pair) are written by the group
-        // that holds that pair: its successor pair does not exist or lies outside the box.
-        if (gl >= 0) {
-            const int pn = p + FD_PPT;               // first pair after this thread's group
-            bool last = gk < pn || pn >= K;          // the group itself ends the in-box pairs / the list
-            if (!last) {
-                // successor = first later pair with a non-negative run (negative runs are skipped)
-                uint32_t rp = pre;
-#pragma unroll
-                for (int j = 0; j < FD_PPT; ++j) if (pr[j].x >= 0) rp = sat_add(rp, (uint32_t)pr[j].x + 1u);
-                int q = pn;
-                int2 nx = __ldg(pairs + q);
-                while (nx.x < 0 && ++q < K) nx = __ldg(pairs + q);
-                last = nx.x < 0 || sat_add(rp, (uint32_t)nx.x) >= total;
-            }
-            if (last)
-                for (int m = (int)dsl.div((uint32_t)gl) + 1; m <= nseg; ++m) tab[m] = make_int2(gk, gl);
-        }
-        __syncthreads();     // s_item / s_wt / s_base are rewritten by the next item
+        q0 += (uint32_t)ntiles;
+        // entries of the segments that start after the unit's last in-box pair
+        if (gk > 0) atomicMax(s_last, ((u64)(uint32_t)gk << 32) | (uint32_t)gl);
+        __syncthreads();
+        const u64 last = *s_last;
+        const int ke = (int)(last >> 32), fl = ke > 0 ? (int)(uint32_t)last : -1;
+        for (int m = (fl < 0 ? 0 : (int)dsl.div((uint32_t)fl) + 1) + tid; m <= nseg; m += SI_NT)
+            tab[m] = make_int2(ke, fl);
+        __syncthreads();             // s_last is reset at the top of the next unit
     }
+    if (bad) atomicOr(err, 1);
 }
 
 // wc_dplan: the units' pairs arrive as ONE dense stream (unit after unit) plus the per-unit counts.  One CTA
-// turns the counts into per-unit pointers (exclusive scan) inside the DecUnitDev table, validates them
-// (0 <= K <= ncoef, else the corrupt flag) and, for the classes that decode by slabs, builds chunk_start
-// for k_seg_index2 — nothing of this touches the host.
+// turns the counts into per-unit pointers (exclusive scan) inside the DecUnitDev table and validates them
+// (0 <= K <= ncoef, else the corrupt flag) — nothing of this touches the host.
 __global__ void __launch_bounds__(1024)
 k_dec_prepare(DecUnitDev* __restrict__ dec, int n_units, const wc_pair* __restrict__ dense,
-              const int32_t* __restrict__ npairs, const int* __restrict__ tab_list, const int* __restrict__ tab_n,
-              int n_tab_lists, int2* __restrict__ items, int* __restrict__ rec_start,
-              const long long* __restrict__ item_off /* per list: offset of its records / status words (host-known bound) */,
-              int* __restrict__ err) {
+              const int32_t* __restrict__ npairs, int* __restrict__ err) {
     __shared__ long long s_w[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    auto block_scan = [&](long long v, long long& tot) -> long long {     // exclusive
-        long long inc = v;
+    // every thread owns a contiguous run of units; the loads of a run are independent (four in flight at a time)
+    const int per = (n_units + 1023) / 1024, i0 = min(tid * per, n_units), i1 = min(i0 + per, n_units);
+    long long mine = 0;
+    bool bad = false;
+    for (int i = i0; i < i1; i += 4) {
+        int k[4], tot[4];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            long long x = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += x;
+        for (int j = 0; j < 4; ++j) {
+            k[j] = 0; tot[j] = 0;
+            if (i + j < i1) { k[j] = __ldg(npairs + i + j); tot[j] = dec[i + j].total; }
         }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        long long w = s_w[lane];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            long long x = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += x;
-        }
-        tot = __shfl_sync(0xffffffffu, w, 31);
-        const long long wpre = warp ? __shfl_sync(0xffffffffu, w, warp - 1) : 0;
-        __syncthreads();
-        return wpre + inc - v;
-    };
-    // every thread owns a contiguous run of units: independent loads, ONE block scan
-    {
-        const int per = (n_units + 1023) / 1024, i0 = tid * per, i1 = min(i0 + per, n_units);
-        long long mine = 0;
-        for (int i = i0; i < i1; ++i) {
-            int k = npairs[i];
-            if (k < 0 || k > dec[i].total) { atomicOr(err, 1); k = 0; }
-            mine += k;
-        }
-        long long tot;
-        long long off = block_scan(mine, tot);
-        for (int i = i0; i < i1; ++i) {
-            int k = npairs[i];
-            if (k < 0 || k > dec[i].total) k = 0;
-            dec[i].pairs      = dense + off;
-            dec[i].npairs     = k;
-            dec[i].npairs_dev = nullptr;
-            off += k;
+        for (int j = 0; j < 4; ++j) {
+            if (k[j] < 0 || k[j] > tot[j]) { bad = true; k[j] = 0; }
+            mine += k[j];
         }
     }
+    if (bad) atomicOr(err, 1);
+    long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+    }
+    if (lane == 31) s_w[warp] = inc;
     __syncthreads();
-    // index work items (unit id, chunk) of every slab-decoded class list
-    int lo = 0;
-    for (int l = 0; l < n_tab_lists; ++l) {
-        const int n = tab_n[l];
-        const int per = (n + 1023) / 1024, j0 = tid * per, j1 = min(j0 + per, n);
-        long long mine = 0;
-        for (int j = j0; j < j1; ++j) {
-            const int k = dec[tab_list[lo + j]].npairs;      // written above by this CTA
-            mine += k > 0 ? (k + SEG_CHUNK - 1) / SEG_CHUNK : 1;
+    long long w = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long x = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += x;
+    }
+    const long long wpre = warp ? __shfl_sync(0xffffffffu, w, warp - 1) : 0;
+    long long off = wpre + inc - mine;
+    for (int i = i0; i < i1; i += 4) {
+        int k[4], tot[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            k[j] = 0; tot[j] = 0;
+            if (i + j < i1) { k[j] = __ldg(npairs + i + j); tot[j] = dec[i + j].total; }
         }
-        long long tot;
-        long long at = block_scan(mine, tot);
-        int2* const rec = items + item_off[l];
-        int* const  rs  = rec_start + lo + l;               // list l owns n + 1 entries
-        for (int j = j0; j < j1; ++j) {
-            const int uid = tab_list[lo + j], k = dec[uid].npairs;
-            const int nch = k > 0 ? (k + SEG_CHUNK - 1) / SEG_CHUNK : 1;
-            rs[j] = (int)at;
-            for (int c = 0; c < nch; ++c) rec[at + c] = make_int2(uid, c);
-            at += nch;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j < i1) {
+                if (k[j] < 0 || k[j] > tot[j]) k[j] = 0;
+                dec[i + j].pairs      = dense + off;
+                dec[i + j].npairs     = k[j];
+                dec[i + j].npairs_dev = nullptr;
+                off += k[j];
+            }
         }
-        if (tid == 0) rs[n] = (int)tot;
-        lo += n;
     }
 }
 
@@ -1517,18 +1524,6 @@ constexpr int FS_SLOTS  = 12288;               // 96 KB
 constexpr int FS_PAIRS  = FS_SLOTS - 2;
 constexpr uint32_t FS_CL = 1u << 17;           // clamp of one pair's run + 1: > any ncoef of an S = 1 unit (32768), and
                                                // 1024 threads * FS_PPT * FS_CL < 2^32, so plain u32 adds never wrap
-__device__ __forceinline__ bool mbar_try_wait_cta(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait_cta(bar, parity)) { }
-}
 // Issued by ONE thread: stage the first pairs of a list; always completes exactly one phase of `bar`.
 __device__ __forceinline__ void fs_issue(const wc_pair* pairs, int K, int2* ST, uint32_t bar, u64 pol) {
     const int nst = K < FS_PAIRS ? K : FS_PAIRS;
@@ -1565,44 +1560,53 @@ __device__ __forceinline__ void fd_decode_staged(const G& g, const int2* __restr
     const int sh  = 2 - (int)((reinterpret_cast<uintptr_t>(pairs) >> 3) & 1u);
     FastDiv dyz;
     if (!G::is_static) dyz.init((uint32_t)(g.Y * g.Z), total);
-    int2 pr[FS_PPT], nx[FS_PPT];
-    auto from_global = [&](int p) { return p < K && p + FS_PPT > nst; };
-    auto load_global = [&](int p) {
-#pragma unroll
-        for (int j = 0; j < FS_PPT; ++j) nx[j] = (p + j < K) ? __ldg(pairs + p + j) : make_int2(0, 0);
-    };
-#pragma unroll
-    for (int j = 0; j < FS_PPT; ++j) nx[j] = make_int2(0, 0);
-    if (from_global(tid * FS_PPT)) load_global(tid * FS_PPT);
+    int2 pr[FS_PPT];
+#ifdef WC_PHASE_PROFILE
+    const long long tw0 = clock64();
+#endif
     mbar_wait_cta(bar, parity);
+#ifdef WC_PHASE_PROFILE
+    if (tid == 0 && blockIdx.x < 1024) g_phase_cycles[blockIdx.x][6] += clock64() - tw0;
+#endif
     bool bad = false;
     uint32_t carry = 0;
     int tile = 0;
 #pragma unroll 1
     for (int p0 = 0; p0 < K; p0 += TILE, ++tile) {
         const int p = p0 + tid * FS_PPT;
+        if (p0 + warp * (32 * FS_PPT) >= K) {
+            // the whole warp lies past the end of the list (now and in every later tile): it only keeps the barrier
+            if (lane == 31) s_wt[(tile & 1) * 32 + warp] = 0u;
+            __syncthreads();
+            continue;
+        }
         if (p + FS_PPT <= nst) {
             const int2* sp = ST + p + sh;
 #pragma unroll
             for (int j = 0; j < FS_PPT; ++j) pr[j] = sp[j];
         } else {
+            // past the staged part (L2 holds it: prefetched with the bulk copy); pairs past the end of the list read as
+            // (-1, 0): run + 1 == 0 marks a dead pair
 #pragma unroll
-            for (int j = 0; j < FS_PPT; ++j) pr[j] = nx[j];
+            for (int j = 0; j < FS_PPT; ++j) pr[j] = (p + j < K) ? __ldg(pairs + p + j) : make_int2(-1, 0);
         }
-        if (p0 + TILE < K) {
-#pragma unroll
-            for (int j = 0; j < FS_PPT; ++j) nx[j] = make_int2(0, 0);
-            if (from_global(p + TILE)) load_global(p + TILE);
-        }
-        // run + 1 of the live pairs (negative runs: corrupt flag, skipped), clamped
-        uint32_t inc[FS_PPT], s = 0;
+        // run + 1 per pair, clamped (see FS_CL); dead pairs count 0.  Negative runs raise the corrupt flag and are
+        // skipped; the common case (a thread whose pairs are all inside the list, no negative run) takes no branch
+        // per pair
+        uint32_t inc[FS_PPT];
+        int any = 0;
 #pragma unroll
         for (int j = 0; j < FS_PPT; ++j) {
-            const bool in = p + j < K;
-            if (in && pr[j].x < 0) bad = true;
-            inc[j] = (in && pr[j].x >= 0) ? min((uint32_t)pr[j].x + 1u, FS_CL) : 0u;
-            s += inc[j];
+            any |= pr[j].x;
+            inc[j] = min((uint32_t)pr[j].x + 1u, FS_CL);
         }
+        if (any < 0) {
+#pragma unroll
+            for (int j = 0; j < FS_PPT; ++j)
+                if (pr[j].x < 0) { inc[j] = 0; if (p + j < K) bad = true; }
+        }
+        const uint32_t s = ((inc[0] + inc[1]) + (inc[2] + inc[3])) + ((inc[4] + inc[5]) + inc[6]);
+        static_assert(FS_PPT == 7, "sum above");
         uint32_t w = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1623,13 +1627,13 @@ __device__ __forceinline__ void fd_decode_staged(const G& g, const int2* __restr
         if (warp == 0) wpre = 0;
         uint32_t pre = carry + wpre + (w - s);                 // flat index this thread's first run starts at
         carry = min(carry + ttot, 1u << 30);
-        if (pre < total) {
+        if (pre < total && s != 0) {
 #pragma unroll
             for (int j = 0; j < FS_PPT; ++j) {
-                const uint32_t f  = pre + inc[j] - 1u;             // inc == 0 (dead pair): f = pre - 1, masked below
+                pre += inc[j];
+                const uint32_t f  = pre - 1u;                      // dead pair: the previous pair's index, masked below
                 const uint32_t ip = G::is_static ? f / (uint32_t)(g.Y * g.Z) : dyz.div(f);
                 if (inc[j] && f < total) C[f + F_PAD * ip] = __int_as_float(pr[j].y);
-                pre += inc[j];
             }
         }
     }
@@ -1647,6 +1651,19 @@ struct __align__(8) FDDesc {
     int        pad;
 };
 static_assert(sizeof(DecUnitDev) == 40 && sizeof(InvUnitDev) == 32 && sizeof(FDDesc) == 88, "FDDesc layout");
+// Thread 0 only; every piece of state lives in shared memory (FDLookState) and every global access lands there
+// through cp.async, so the hand-out costs the CTA no registers and no step waits for a value it has just requested:
+//   stage3 (after the post-decode barrier of item k)  item k's slot receives the descriptors of item k+2 (cp.async);
+//           the work-counter atomic for item k+4 is ISSUED — the one value that must travel in a register, across
+//           the straight-line inverse phase only
+//   stage4 (end of item k)  descriptors of k+2 have landed: its K is requested (plan round trips keep K on the
+//           device); the atomic's result becomes the index of item k+4 and its unit id is requested
+//   before the post-decode barrier of item k+1: cp.async.wait_all — K of k+2 and the unit id of k+4 are in place
+struct FDLookState {
+    int idx_a, uid_a;      // item k+2 (k+3 after stage3)
+    int idx_b, uid_b;      // item k+3 (k+4 after stage4)
+    int batch_next, batch_left;
+};
 template <int S>
 struct FDLookahead {
     const DecUnitDev* dec;
@@ -1654,34 +1671,19 @@ struct FDLookahead {
     const int*        unit_list;
     int*              work_counter;
     int               n_items, stride;    // items = S per listed unit: item i -> unit_list[i / S], slab i % S
+    FDLookState*      st;
     FDDesc*           slot;        // item k's slot: receives item k+2
-    FDDesc*           next_slot;   // item k+1: descriptor present, K still to be resolved
-    int               ui_prev;
-    int               idx, uid, kreg;   // thread 0 only
-    int               batch, batch_next, batch_left;
-    __device__ __forceinline__ void resolve_k_issue() {
-        kreg = 0;
-        if (next_slot->uid >= 0) {
-            kreg = next_slot->du.npairs;
-            const int32_t* kp = next_slot->du.npairs_dev;
-            if (kp) asm volatile("ld.global.s32 %0, [%1];" : "=r"(kreg) : "l"(kp));
-        }
+    FDDesc*           next_slot;   // item k+1
+    int               batch;
+    int               raw;         // in flight between stage3 and stage4
+    bool              refill;
+    __device__ __forceinline__ static void cp4(void* smem_dst, const void* gsrc) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
     }
-    __device__ __forceinline__ void stage1() {          // top of the item
-        if (!work_counter) { idx = ui_prev + stride; return; }
-        // dynamic hand-out, `batch` consecutive units per atomic: hundreds of CTAs hitting one address cost
-        // ~15-30 cycles per atomic chip-wide, which would bound the small-unit kernels
-        if (batch_left == 0) { batch_next = atomicAdd(work_counter, batch); batch_left = batch; }
-        idx = batch_next++;
-        --batch_left;
-    }
-    __device__ __forceinline__ void stage2() {          // after the first barrier: slot k&1 is free now
-        uid = -1;
-        if (idx < n_items) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(uid) : "l"(unit_list + idx / S));
-    }
-    __device__ __forceinline__ void resolve_k_store() { next_slot->K = kreg; }   // before the post-scatter barrier
+    __device__ __forceinline__ static void wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
     __device__ __forceinline__ void stage3() {
-        slot->ui  = idx;
+        slot->ui  = st->idx_a;
+        const int uid = st->uid_a;
         slot->uid = uid;
         if (uid >= 0) {
             const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&slot->du);
@@ -1695,11 +1697,59 @@ struct FDLookahead {
             for (int b = 0; b < 32; b += 8)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1 + b), "l"(s1 + b) : "memory");
         }
+        st->idx_a = st->idx_b; st->uid_a = st->uid_b;
+        // dynamic hand-out, `batch` consecutive units per atomic: hundreds of CTAs hitting one address cost
+        // ~15-30 cycles per atomic chip-wide, which would bound the small-unit kernels
+        refill = false;
+        if (work_counter && st->batch_left == 0) { raw = atomicAdd(work_counter, batch); refill = true; }
     }
-    __device__ __forceinline__ void stage4() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+    __device__ __forceinline__ void stage4() {
+        wait_all();                                     // descriptors of item k+2
+        if (slot->uid >= 0) {
+            slot->K = slot->du.npairs;
+            if (slot->du.npairs_dev) cp4(&slot->K, slot->du.npairs_dev);
+        }
+        int idx;
+        if (!work_counter) idx = st->idx_a + stride;
+        else {
+            if (refill) { st->batch_next = raw; st->batch_left = batch; }
+            idx = st->batch_next;
+            st->batch_next = idx + 1;
+            st->batch_left -= 1;
+        }
+        st->idx_b = idx;
+        st->uid_b = -1;
+        if (idx < n_items) cp4(&st->uid_b, unit_list + idx / S);
+    }
+    // the first four items of the CTA: 0 and 1 into the descriptor slots, 2 and 3 into the state
+    __device__ __forceinline__ void prologue(FDDesc* s_desc) {
+        st->batch_next = 0; st->batch_left = 0;
+        int prev = (int)blockIdx.x - stride;
+        for (int k = 0; k < 4; ++k) {
+            int idx;
+            if (!work_counter) idx = prev + stride;
+            else {
+                if (st->batch_left == 0) { st->batch_next = atomicAdd(work_counter, batch); st->batch_left = batch; }
+                idx = st->batch_next;
+                st->batch_next = idx + 1;
+                st->batch_left -= 1;
+            }
+            prev = idx;
+            const int uid = idx < n_items ? __ldg(unit_list + idx / S) : -1;
+            if (k < 2) {
+                FDDesc& d = s_desc[k];
+                d.ui = idx; d.uid = uid; d.K = 0;
+                if (uid >= 0) {
+                    d.du = dec[uid];
+                    d.iu = inv[uid];
+                    d.K  = d.du.npairs_dev ? *d.du.npairs_dev : d.du.npairs;
+                }
+            } else if (k == 2) { st->idx_a = idx; st->uid_a = uid; }
+            else               { st->idx_b = idx; st->uid_b = uid; }
+        }
+    }
 };
 
-// One work item (unit, slab `rank`) of the fused decompress.  G: FGeom or SGeom<..., S>.
 struct FDStage {          // STG kernels only: staging area, its mbarrier, staged items so far (= phase parity)
     int2*    ST;
     uint32_t bar;
@@ -1716,7 +1766,6 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
     const int b0 = rank * g.nb;
     const uint32_t total = (uint32_t)du.total;
     WC_PHASE_CLOCK(t0);
-    if (tid == 0) { la.stage1(); la.resolve_k_issue(); }
 
     const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
     const bool vec16 = (reinterpret_cast<uintptr_t>(pairs) & 15u) == 0;
@@ -1738,7 +1787,6 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
     //    start and step 3 of every item puts a zero back behind each coefficient it reads ("clean as you go"), which
     //    removed a 128 KB zero-fill pass and a CTA-wide barrier per item.
     WC_PHASE_CLOCK(t1);
-    if (tid == 0) la.stage2();
     WC_PHASE_CLOCK(t2);
 
     // 2. decode the pairs that land in this item's segments
@@ -1830,7 +1878,7 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         }
     }
     WC_PHASE_CLOCK(t3);
-    if (tid == 0) la.resolve_k_store();
+    if (tid == 0) la.wait_all();          // K of the next item, unit id of the item after the staged ones
     __syncthreads();
 
     // the NEXT unit's pair list (S = 1) lands while this unit is inverted: in the staging area (TMA bulk copy; what
@@ -1936,7 +1984,13 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
     stg.ST  = reinterpret_cast<int2*>(smem + BASE + 1024);                        // STG: [FS_SLOTS] pairs
     stg.bar = smem_u32(smem + BASE + 512);
     stg.n   = 0;
-    stg.ignore_tab = ignore_tab != 0;
+    stg.ignore_tab = (ignore_tab & 1) != 0;
+#ifdef WC_PHASE_PROFILE
+    if (const int sg = ignore_tab >> 8) {        // experiment: staggered CTA start
+        const long long t0 = clock64(), w = (long long)(blockIdx.x & 3) * sg * 256;
+        while (clock64() - t0 < w) { }
+    }
+#endif
     stg.pol = 0;
     const int tid = threadIdx.x;
     if (STG) {
@@ -1957,21 +2011,9 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
     la.dec = dec; la.inv = inv; la.unit_list = unit_list;
     la.work_counter = work_counter;
     la.n_items = n_items; la.stride = (int)gridDim.x;
-    la.idx = 0; la.uid = -1; la.kreg = 0;
-    la.batch = CAP <= 4096 ? 16 : 1; la.batch_next = 0; la.batch_left = 0;
-    if (tid == 0) {
-        la.ui_prev = (int)blockIdx.x - (int)gridDim.x;
-        for (int k = 0; k < 2; ++k) {
-            la.slot = &s_desc[k];
-            la.stage1(); la.stage2(); la.stage3();
-            la.ui_prev = la.idx;
-        }
-        la.stage4();
-        for (int k = 0; k < 2; ++k) {
-            la.next_slot = &s_desc[k];
-            la.resolve_k_issue(); la.resolve_k_store();
-        }
-    }
+    la.st = reinterpret_cast<FDLookState*>(smem + BASE + 448);
+    la.batch = CAP <= 4096 ? 16 : 1; la.raw = 0; la.refill = false;
+    if (tid == 0) la.prologue(s_desc);
     __syncthreads();
     if (STG) {      // the first item's list goes into the staging area here, every later one during its predecessor
         const FDDesc& d = s_desc[0];
@@ -1991,7 +2033,6 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         const uint32_t rank = (uint32_t)(d.ui % S);
         la.slot      = &s_desc[k & 1];
         la.next_slot = &s_desc[(k + 1) & 1];
-        la.ui_prev   = la.next_slot->ui;
         const bool have_next = la.next_slot->ui < n_items;
 #define WC_FD_UNIT(GEOM) fd_unit<S, NT, STG>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next, stg)
         if constexpr (STATIC) {
@@ -2033,7 +2074,11 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
     const long long items = (long long)n * S, slots = (long long)per_sm * sm_count;
     const int nc = (int)(slots < items ? slots : items);
     ls->begin(kid, st);
-    kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter, ignore_tab ? 1 : 0);
+    int karg = ignore_tab ? 1 : 0;
+#ifdef WC_PHASE_PROFILE
+    if (const char* sgv = getenv("WCGPU_STAGGER")) karg |= atoi(sgv) << 8;
+#endif
+    kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter, karg);
     ls->end(st);
     return cudaGetLastError();
 }
@@ -2047,25 +2092,23 @@ int fused_decode_slabs(int fused_cls) {
     return 1;
 }
 
-cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int2* items,
-                              const int* rec_start, int j0, int j1, long long items_bound, u64* status,
+cudaError_t launch_seg_index3(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                               int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls) {
-    if (items_bound <= 0) return cudaSuccess;
-    const long long slots = 3ll * sm_count;
-    const int nb = (int)(items_bound < slots ? items_bound : slots);
+    if (n <= 0 || !fused_decode_needs_table(fused_cls)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_seg_index3, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM);
+    if (e != cudaSuccess) return e;
+    const int nb = n < 2 * sm_count ? n : 2 * sm_count;
     ls->begin(KID_SEG_INDEX2, st);
-    k_seg_index2<512><<<nb, 512, 0, st>>>(dec, inv, items, rec_start, j0, j1, status, work_counter, err,
-                                          fused_decode_slabs(fused_cls));
+    k_seg_index3<<<nb, SI_NT, SI_SMEM, st>>>(dec, inv, list, n, err, fused_decode_slabs(fused_cls), work_counter);
     ls->end(st);
     return cudaGetLastError();
 }
 
-cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
-                               const int* tab_list, const int* tab_n, int n_tab_lists, int2* items, int* rec_start,
-                               const long long* item_off, int* err, cudaStream_t st, LaunchStats* ls) {
+cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs, int* err,
+                               cudaStream_t st, LaunchStats* ls) {
     if (n_units <= 0) return cudaSuccess;
     ls->begin(KID_DEC_PREPARE, st);
-    k_dec_prepare<<<1, 1024, 0, st>>>(dec, n_units, dense, npairs, tab_list, tab_n, n_tab_lists, items, rec_start, item_off, err);
+    k_dec_prepare<<<1, 1024, 0, st>>>(dec, n_units, dense, npairs, err);
     ls->end(st);
     return cudaGetLastError();
 }

@@ -39,16 +39,13 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
 // stage (32^3 cubes): 0 = pairs straight from global memory, 1 = table-less units decode from a shared-memory staging
 // area filled by TMA bulk copies one item ahead (k_staged_decompress), 2 = units with a segment table as well
 
-// Chunk-parallel segment index for packed streams without tables (see k_seg_index2), and the device-side
-// preparation of a dense stream (k_dec_prepare).  SEG_CHUNK pairs per work item.
-constexpr int SEG_INDEX_CHUNK = 4096;
+// Streamed segment index for packed streams without tables (see k_seg_index3), and the device-side preparation
+// of a dense stream (k_dec_prepare).
 int fused_decode_slabs(int fused_cls);
-cudaError_t launch_seg_index2(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int2* items,
-                              const int* rec_start, int j0, int j1, long long items_bound, u64* status,
+cudaError_t launch_seg_index3(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                               int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls);
-cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
-                               const int* tab_list, const int* tab_n, int n_tab_lists, int2* items, int* rec_start,
-                               const long long* item_off, int* err, cudaStream_t st, LaunchStats* ls);
+cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs, int* err,
+                               cudaStream_t st, LaunchStats* ls);
 
 #ifdef WC_PHASE_PROFILE
 cudaError_t debug_phase_cycles(unsigned long long out[8], bool reset);

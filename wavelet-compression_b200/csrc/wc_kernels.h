@@ -30,7 +30,7 @@ inline const char* kernel_name(int id) {
         "k_fused_decompress<8>", "k_fused_decompress<1,cube32>", "k_fused_decompress<8,cube64>", "k_seg_index", "k_fused_compress<1,small>", "k_fused_compress<1,cube16>",
         "k_fused_decompress<1,small>", "k_fused_decompress<1,cube16>", "k_fused_compress<1,cube8>",
         "k_fused_decompress<1,cube8>", "k_fused_compress<4>", "k_fused_compress<2>", "k_fused_decompress<4>",
-        "k_fused_decompress<2>", "k_minmax_tiles", "k_minmax_final", "k_seg_index2", "k_dec_prepare",
+        "k_fused_decompress<2>", "k_minmax_tiles", "k_minmax_final", "k_seg_index3", "k_dec_prepare",
         "k_patch_inputs", "k_staged_decompress<1,cube32>", "k_staged_decompress<1>" };
     return (id >= 0 && id < KID_N) ? n[id] : "?";
 }
