@@ -128,7 +128,7 @@ def test_dplan_overflow_drop_and_empty_streams(wc, ctx, oracle, seg_index, pipe)
         recon = ctx.decompress_batch(packed)           # the blocking call takes the same index kernel
     finally:
         ctx.set_option(wc.capi.WC_OPT_SEG_INDEX, 0)
-        ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, 1)
+        ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, 2)
     for i, (p, o, d) in enumerate(zip(packed, outs, dims)):
         ob = oracle.decompress_unit(p.runs, p.vals, d)
         assert same_bits(o, ob), (i, d)
@@ -311,7 +311,7 @@ def test_decode_kernels_many_units_all_densities(wc, ctx, oracle, pipe):
             dp.finish()
         dp.close()
     finally:
-        ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, 1)
+        ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, 2)
     for i in list(range(0, len(dims), 9)) + list(range(690, len(dims))):
         ob = oracle.decompress_unit(packed[i].runs, packed[i].vals, dims[i])
         assert same_bits(outs[i], ob), (i, dims[i], packed[i].npairs)

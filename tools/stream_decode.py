@@ -37,6 +37,9 @@ rec = torch.empty(int(ncoef.sum()), dtype=torch.float32, device='cuda')
 offs = np.concatenate([[0], np.cumsum(ncoef)])
 odescs = capi.box_descs([rec.data_ptr() + 4 * int(o) for o in offs[:-1]], [pkg.WC_F32] * len(sdims), sdims)
 alg = int((8 * k32.astype(np.int64) + 4 * ncoef).sum())
+for nn in sorted(set(ncoef.tolist())):
+    kk = k32[ncoef == nn]
+    print(f"units of {nn} cells: {kk.size}, K percentiles 1/10/50/90/99/max:", [int(x) for x in np.percentile(kk, [1, 10, 50, 90, 99, 100])])
 peak = 6549.4
 have_phase = hasattr(ctx.lib, "wc_debug_phase_cycles")
 if have_phase:

@@ -101,7 +101,7 @@ struct wc_ctx {
     int          opt_seg_index = 0;   // 0 = streamed k_seg_index3 (TMA ring), 1 = k_seg_index (direct loads)
     int          opt_copy_only = 0;   // probe: wc_plan_compress_to_host moves the bytes but skips the kernels
     int          opt_ingest_stats = 0; // compress also records per-unit min / max of the narrowed inputs
-    int          opt_decode_pipe = 1;  // 32^3 cubes: table-less lists decode from the TMA-fed staging area
+    int          opt_decode_pipe = 2;  // 32^3 cubes decode from the TMA-fed staging area (2: also when a table came along)
     int          sm_count = 0;
     wc_plan*     batch_plan = nullptr; // owner of the memory handed out by wc_compress_batch
     // workspace of the blocking decompress / rmse / primitive calls (grow-only)
@@ -1375,7 +1375,7 @@ struct wc_dplan {
     bool      has_generic = false;        // some unit needs the generic kernels: decode falls back to run_decompress
     size_t    fl_off[FL_N] = {};          // offset of each class list inside d_lists
     size_t    tab_floats = 0;
-    DevBuf d_dec, d_inv, d_lists, d_tab, d_err, d_stage_out, d_pairs, d_npairs, d_counter;
+    DevBuf d_dec, d_inv, d_lists, d_tab, d_err, d_stage_out, d_pairs, d_npairs, d_counter, d_chain;
     PinBuf h_err;
     unsigned counter_next = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -1451,6 +1451,7 @@ int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_sp
     DP_RESERVE(dp->d_err, 64);
     DP_RESERVE(dp->d_npairs, sizeof(int32_t) * std::max(n_units, 1));
     DP_RESERVE(dp->d_counter, 64 * sizeof(int));
+    DP_RESERVE(dp->d_chain, sizeof(unsigned long long) * ((size_t)(n_units + 1023) / 1024 + 2));
     if ((e = dp->h_err.reserve(64)) != cudaSuccess) return fail(e, "dplan pinned alloc");
     size_t n_fused = 0;
     std::vector<int> lists;
@@ -1486,7 +1487,7 @@ int wc_dplan_destroy(wc_dplan* dp) {
     if (dp->s_d2h) { cudaStreamSynchronize(dp->s_d2h); cudaStreamDestroy(dp->s_d2h); }
     for (cudaEvent_t e : dp->ev) cudaEventDestroy(e);
     DevBuf* bufs[] = { &dp->d_dec, &dp->d_inv, &dp->d_lists, &dp->d_tab, &dp->d_err,
-                       &dp->d_stage_out, &dp->d_pairs, &dp->d_npairs, &dp->d_counter, &dp->g_coef,
+                       &dp->d_stage_out, &dp->d_pairs, &dp->d_npairs, &dp->d_counter, &dp->d_chain, &dp->g_coef,
                        &dp->g_dec, &dp->g_inv, &dp->g_tiles, &dp->g_ptiles, &dp->g_psum, &dp->g_list };
     for (DevBuf* b : bufs) b->release();
     dp->h_err.release();
@@ -1607,8 +1608,8 @@ int wc_dplan_decode(wc_dplan* dp, const wc_pair* pairs, const int32_t* npairs, i
         if (rc != WC_OK) return rc;
     } else {
         if (dp->tab_floats) CTX_CUDA(ctx, cudaMemsetAsync(dp->d_tab.p, 0, sizeof(float) * dp->tab_floats, ctx->stream));
-        CTX_CUDA(ctx, launch_dec_prepare(dp->d_dec.as<DecUnitDev>(), n, d_pairs, d_npairs, dp->d_err.as<int>(),
-                                         ctx->stream, &ctx->ls));
+        CTX_CUDA(ctx, launch_dec_prepare(dp->d_dec.as<DecUnitDev>(), n, d_pairs, d_npairs, dp->d_chain.as<unsigned long long>(),
+                                         dp->d_err.as<int>(), ctx->stream, &ctx->ls));
     }
     size_t fi[FL_N] = {};
     if (!pipelined) {

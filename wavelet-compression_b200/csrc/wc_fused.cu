@@ -1373,33 +1373,29 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
     if (bad) atomicOr(err, 1);
 }
 
-// wc_dplan: the units' pairs arrive as ONE dense stream (unit after unit) plus the per-unit counts.  One CTA
+// wc_dplan: the units' pairs arrive as ONE dense stream (unit after unit) plus the per-unit counts.  This kernel
 // turns the counts into per-unit pointers (exclusive scan) inside the DecUnitDev table and validates them
 // (0 <= K <= ncoef, else the corrupt flag) — nothing of this touches the host.
+// One CTA per 1024 units, chained through `chain` (zeroed before the launch): [0] = tile ticket, [1 + t] = status of
+// tile t: 0 | 1 << 62 | tile total | 2 << 62 | inclusive prefix (totals stay below 2^62).  Tiles are taken in ticket
+// order, so a predecessor is always running or done.  (A single CTA took 40 us for 12800 units: the 40-byte stride of
+// the table makes every access its own sector, and one SM retires one sector per cycle.)
 __global__ void __launch_bounds__(1024)
 k_dec_prepare(DecUnitDev* __restrict__ dec, int n_units, const wc_pair* __restrict__ dense,
-              const int32_t* __restrict__ npairs, int* __restrict__ err) {
+              const int32_t* __restrict__ npairs, unsigned long long* __restrict__ chain, int* __restrict__ err) {
     __shared__ long long s_w[32];
+    __shared__ long long s_base;
+    __shared__ int s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // every thread owns a contiguous run of units; the loads of a run are independent (four in flight at a time)
-    const int per = (n_units + 1023) / 1024, i0 = min(tid * per, n_units), i1 = min(i0 + per, n_units);
-    long long mine = 0;
-    bool bad = false;
-    for (int i = i0; i < i1; i += 4) {
-        int k[4], tot[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            k[j] = 0; tot[j] = 0;
-            if (i + j < i1) { k[j] = __ldg(npairs + i + j); tot[j] = dec[i + j].total; }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (k[j] < 0 || k[j] > tot[j]) { bad = true; k[j] = 0; }
-            mine += k[j];
-        }
+    if (tid == 0) s_tile = (int)atomicAdd(chain, 1ull);
+    __syncthreads();
+    const int tile = s_tile, i = tile * 1024 + tid;
+    int k = 0;
+    if (i < n_units) {
+        k = __ldg(npairs + i);
+        if (k < 0 || k > dec[i].total) { atomicOr(err, 1); k = 0; }
     }
-    if (bad) atomicOr(err, 1);
-    long long inc = mine;
+    long long inc = k;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const long long x = __shfl_up_sync(0xffffffffu, inc, o);
@@ -1413,25 +1409,28 @@ k_dec_prepare(DecUnitDev* __restrict__ dec, int n_units, const wc_pair* __restri
         const long long x = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += x;
     }
+    const long long total = __shfl_sync(0xffffffffu, w, 31);
     const long long wpre = warp ? __shfl_sync(0xffffffffu, w, warp - 1) : 0;
-    long long off = wpre + inc - mine;
-    for (int i = i0; i < i1; i += 4) {
-        int k[4], tot[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            k[j] = 0; tot[j] = 0;
-            if (i + j < i1) { k[j] = __ldg(npairs + i + j); tot[j] = dec[i + j].total; }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i + j < i1) {
-                if (k[j] < 0 || k[j] > tot[j]) k[j] = 0;
-                dec[i + j].pairs      = dense + off;
-                dec[i + j].npairs     = k[j];
-                dec[i + j].npairs_dev = nullptr;
-                off += k[j];
+    if (tid == 0) {
+        unsigned long long* const st = chain + 1;
+        long long base = 0;
+        if (tile > 0) {
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(st + tile), "l"((1ull << 62) | (unsigned long long)total) : "memory");
+            for (int j = tile - 1; j >= 0; --j) {
+                unsigned long long v;
+                do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(st + j) : "memory"); } while ((v >> 62) == 0);
+                base += (long long)(v & ((1ull << 62) - 1));
+                if ((v >> 62) == 2) break;
             }
         }
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(st + tile), "l"((2ull << 62) | (unsigned long long)(base + total)) : "memory");
+        s_base = base;
+    }
+    __syncthreads();
+    if (i < n_units) {
+        dec[i].pairs      = dense + (s_base + wpre + inc - k);
+        dec[i].npairs     = k;
+        dec[i].npairs_dev = nullptr;
     }
 }
 
@@ -1468,41 +1467,6 @@ __device__ __forceinline__ void fd_decode_chunks(const int2* __restrict__ pairs,
         const uint32_t f = b + inc[c];
         if (pv[c].x >= 0 && f - fseg < seglen && f < total) cseg[f - fseg] = __int_as_float(pv[c].y);
         b += tot[c];
-    }
-    base = b;
-}
-
-// The same in two halves, so that a warp can have the first chunks of its NEXT segment in flight while it scans and
-// scatters the current one (the table-driven decode is a chain of dependent latencies per segment otherwise).
-template <int NCH>
-__device__ __forceinline__ void fd_load_chunks(const int2* __restrict__ pairs, int c0, int e1x, int lane, int2 (&pv)[NCH]) {
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int p = c0 + 32 * c + lane;
-        pv[c] = make_int2(-1, 0);
-        if (p < e1x) pv[c] = __ldg(pairs + p);
-    }
-}
-template <int NCH>
-__device__ __forceinline__ void fd_decode_loaded(const int2 (&pv)[NCH], int lane, uint32_t& base, uint32_t fseg,
-                                                 uint32_t seglen, uint32_t total, float* cseg) {
-    uint32_t inc[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) inc[c] = pv[c].x >= 0 ? (uint32_t)pv[c].x + 1u : 0u;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, inc[c], o);
-            if (lane >= o) inc[c] += v;
-        }
-    }
-    uint32_t b = base;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const uint32_t f = b + inc[c];
-        if (pv[c].x >= 0 && f - fseg < seglen && f < total) cseg[f - fseg] = __int_as_float(pv[c].y);
-        b += __shfl_sync(0xffffffffu, inc[c], 31);
     }
     base = b;
 }
@@ -1586,7 +1550,8 @@ __device__ __forceinline__ void fd_decode_staged(const G& g, const int2* __restr
             for (int j = 0; j < FS_PPT; ++j) pr[j] = sp[j];
         } else {
             // past the staged part (L2 holds it: prefetched with the bulk copy); pairs past the end of the list read as
-            // (-1, 0): run + 1 == 0 marks a dead pair
+            // (-1, 0): run + 1 == 0 marks a dead pair.  (Requesting these one tile ahead into registers measured
+            // slower: the 14 extra live registers spill in the 64-register kernel.)
 #pragma unroll
             for (int j = 0; j < FS_PPT; ++j) pr[j] = (p + j < K) ? __ldg(pairs + p + j) : make_int2(-1, 0);
         }
@@ -1783,9 +1748,17 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
             te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sg >> 1) * (2 * S) + (sg & 1) * S + (int)rank + (lane & 1));
     }
 
-    // 1. C is all zeros here (rle_decode starts from zeros, src/decompressor.cpp:17): the kernel zeroes it once at the
-    //    start and step 3 of every item puts a zero back behind each coefficient it reads ("clean as you go"), which
-    //    removed a 128 KB zero-fill pass and a CTA-wide barrier per item.
+    // 1. zero-fill C (rle_decode starts from zeros, src/decompressor.cpp:17).  The staged kernel instead zeroes C once at
+    //    its start and has step 3 put a zero back behind every coefficient it reads ("clean as you go": one pass over
+    //    C and one CTA barrier less per item, measured 0.603 -> 0.575 ms); for the table-driven items the separate pass
+    //    measured slightly faster (its 16-byte stores overlap the first pair loads).
+    if (!STG) {
+        const int nwords = g.nlocal + F_PAD * g.X;
+        float4* c4 = reinterpret_cast<float4*>(C);
+#pragma unroll 4
+        for (int i = tid; i < (nwords + 3) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+    }
     WC_PHASE_CLOCK(t1);
     WC_PHASE_CLOCK(t2);
 
@@ -1827,54 +1800,32 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         // Lanes 2q, 2q+1 hold the table entries of the warp's q-th segment (loaded before the zero-fill);
         // up to 8 chunks of 32 pairs are in flight per segment before the first one is decoded.
         const uint32_t seglen = (uint32_t)g.seglen;
-        // software pipeline over the warp's segments: the first 128 pairs of segment q + 1 are loaded before segment q
-        // is scanned and scattered
-        int2 cur[4], nxt[4];
-        auto seg_entries = [&](int q, int& e0x, int& e0y, int& e1x) {
-            const int ql = q & 15;
-            e0x = __shfl_sync(0xffffffffu, te.x, 2 * ql); e0y = __shfl_sync(0xffffffffu, te.y, 2 * ql);
-            e1x = __shfl_sync(0xffffffffu, te.x, 2 * ql + 1);
-        };
-        auto reload_entries = [&](int q) {
-            // a warp holds the entries of 16 segments at a time: next round (more than 16 segments per warp only
-            // happens with few warps and a long x axis, e.g. 48 x 4 x 8 boxes)
-            const int qq = q + (lane >> 1), sq = fd_seg_of(qq, warp, NW);
-            te = make_int2(0, 0);
-            if (qq * NW + warp < g.nseg)
-                te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sq >> 1) * (2 * S) + (sq & 1) * S + (int)rank + (lane & 1));
-        };
-        int e0x = 0, e0y = 0, e1x = 0;
-        if (warp < g.nseg) {
-            seg_entries(0, e0x, e0y, e1x);
-            fd_load_chunks<4>(pairs, e0x, e1x, lane, cur);
-        }
 #pragma unroll 1
         for (int q = 0; q * NW + warp < g.nseg; ++q) {
             const int sg = fd_seg_of(q, warp, NW);
             const int i = sg >> 1, half = sg & 1;
             const int m = i * (2 * S) + half * S + (int)rank;
-            // entries + first chunks of the next segment
-            int n0x = 0, n0y = 0, n1x = 0;
-            const bool more = (q + 1) * NW + warp < g.nseg;
-            if (more) {
-                if (((q + 1) & 15) == 0) reload_entries(q + 1);
-                seg_entries(q + 1, n0x, n0y, n1x);
-                fd_load_chunks<4>(pairs, n0x, n1x, lane, nxt);
+            if (q && (q & 15) == 0) {
+                // a warp holds the entries of 16 segments at a time: next round (more than 16 segments per
+                // warp only happens with few warps and a long x axis, e.g. 48 x 4 x 8 boxes)
+                const int qq = q + (lane >> 1), sq = fd_seg_of(qq, warp, NW);
+                te = make_int2(0, 0);
+                if (qq * NW + warp < g.nseg)
+                    te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sq >> 1) * (2 * S) + (sq & 1) * S + (int)rank + (lane & 1));
             }
+            const int ql = q & 15;
+            const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * ql), e0y = __shfl_sync(0xffffffffu, te.y, 2 * ql);
+            const int e1x = __shfl_sync(0xffffffffu, te.x, 2 * ql + 1);
             float* const cseg = C + i * g.slab + half * g.seglen;    // C index of flat index m * seglen
             const uint32_t fseg = (uint32_t)m * seglen;
             uint32_t base = (uint32_t)e0y;                           // flat index of the pair before the first (or -1)
-            if (e0x < e1x) fd_decode_loaded<4>(cur, lane, base, fseg, seglen, total, cseg);
 #pragma unroll 1
-            for (int c0 = e0x + 128; c0 < e1x; c0 += 256) {
+            for (int c0 = e0x; c0 < e1x; c0 += 256) {
                 // 4 or 8 chunks of 32 pairs at once: the loads are all in flight together, and the chunks'
                 // shuffle scans are independent chains the scheduler interleaves (no branch between them)
                 if (e1x - c0 <= 128) fd_decode_chunks<4>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
                 else                 fd_decode_chunks<8>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
             }
-            e0x = n0x; e0y = n0y; e1x = n1x;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
         }
     }
     WC_PHASE_CLOCK(t3);
@@ -1920,7 +1871,7 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
             for (int o = 0; o < 8; ++o) {
                 float2* const pc = const_cast<float2*>(reinterpret_cast<const float2*>(csrc + (o & 1) * o1 + ((o >> 1) & 1) * o2 + (o >> 2) * o3));
                 v[o] = *pc;
-                *pc  = make_float2(0.f, 0.f);        // clean as you go: the next item finds C zeroed
+                if (STG) *pc = make_float2(0.f, 0.f);        // clean as you go: the next item finds C zeroed
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) ihaar_pair2(v[2 * k], v[2 * k + 1]);                 // X
@@ -2001,7 +1952,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         }
     }
     const int n_items = n_list * S;
-    {   // the coefficient array starts out zeroed; every item leaves it zeroed (fd_unit step 3)
+    if (STG) {   // the coefficient array starts out zeroed; every item leaves it zeroed (fd_unit step 3)
         float4* c4 = reinterpret_cast<float4*>(C);
         for (int i = tid; i < (CAP + F_CPAD) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -2104,11 +2055,14 @@ cudaError_t launch_seg_index3(int fused_cls, const DecUnitDev* dec, const InvUni
     return cudaGetLastError();
 }
 
-cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs, int* err,
-                               cudaStream_t st, LaunchStats* ls) {
+cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
+                               unsigned long long* chain, int* err, cudaStream_t st, LaunchStats* ls) {
     if (n_units <= 0) return cudaSuccess;
+    const int tiles = (n_units + 1023) / 1024;
+    cudaError_t e = cudaMemsetAsync(chain, 0, sizeof(unsigned long long) * (size_t)(tiles + 1), st);
+    if (e != cudaSuccess) return e;
     ls->begin(KID_DEC_PREPARE, st);
-    k_dec_prepare<<<1, 1024, 0, st>>>(dec, n_units, dense, npairs, err);
+    k_dec_prepare<<<tiles, 1024, 0, st>>>(dec, n_units, dense, npairs, chain, err);
     ls->end(st);
     return cudaGetLastError();
 }

@@ -44,8 +44,9 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
 int fused_decode_slabs(int fused_cls);
 cudaError_t launch_seg_index3(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                               int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls);
-cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs, int* err,
-                               cudaStream_t st, LaunchStats* ls);
+cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
+                               unsigned long long* chain /* (n_units + 1023) / 1024 + 1 words */, int* err, cudaStream_t st,
+                               LaunchStats* ls);
 
 #ifdef WC_PHASE_PROFILE
 cudaError_t debug_phase_cycles(unsigned long long out[8], bool reset);
