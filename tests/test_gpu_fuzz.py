@@ -69,3 +69,53 @@ def test_fuzz_batch_and_plan_roundtrip(wc, ctx, oracle, seed):
             tol = 1e-12 if n <= (1 << 18) else max(1e-12, n * 2.0 ** -54)   # strict at every BASELINE size (test_gpu_parity.rmse_tol)
             assert abs(rm[i] - oe) <= tol * max(abs(oe), 1e-300), (seed, i, d, rm[i], oe)
     plan.close()
+
+
+BIG_SHAPES = [(128, 128, 128), (44, 44, 44), (52, 52, 52), (60, 60, 60), (96, 80, 64), (128, 64, 64), (64, 128, 96),
+              (130, 66, 34), (40, 40, 42), (31, 17, 9), (128, 2, 128), (72, 72, 72)]
+
+
+@pytest.mark.parametrize("seg_index", [0, 1])
+def test_big_and_irregular_boxes(wc, ctx, oracle, seg_index):
+    """Boxes outside the cluster classes: more than 262144 cells (128^3), half-heights no cluster of 2/4/8 divides (44^3,
+    52^3, 60^3) -> decoded by independent y-slab items with a run-time slab count (FUSED_CLS_RBIG: 64 slabs for 128^3,
+    11 for 44^3 ...) after the streamed segment index; odd dimensions and nz % 4 != 0 stay on the generic kernels.  Both
+    index kernels; one-shot batch API, dense-stream decode plan, plan round trip."""
+    rng = np.random.default_rng(4242 + seg_index)
+    shapes = BIG_SHAPES
+    boxes = []
+    for i, d in enumerate(shapes):
+        b = smooth_box(d, rng, dtype=np.float64 if i % 3 else np.float32, sym=bool(i % 2), noise=10.0 ** -(i % 4))
+        if i == 4:
+            b = -np.abs(b) - 0.5                     # negative max: everything kept (K = N)
+        boxes.append(b)
+    keep = float(np.float32(0.999))
+    ctx.set_option(wc.capi.WC_OPT_SEG_INDEX, seg_index)
+    try:
+        packed = ctx.compress_batch(boxes, keep, dims=shapes)
+        recon = ctx.decompress_batch(packed)
+        want = []
+        for b, d, p, r in zip(boxes, shapes, packed, recon):
+            runs, vals, _ = oracle.compress_unit(b, d, keep)
+            assert same_bits(p.runs, runs) and same_bits(p.vals, vals), (d, b.dtype)
+            ob = oracle.decompress_unit(runs, vals, d)
+            assert same_bits(r.reshape(ob.shape), ob), d
+            want.append(ob)
+        # the `-d` path: dense stream + counts through a decode plan (float64 boxes out)
+        kk = np.array([p.npairs for p in packed], np.int32)
+        pr = np.empty(max(int(kk.sum()), 1), wc.capi.PAIR)
+        o = 0
+        for p in packed:
+            pr["run"][o:o + p.npairs] = p.runs
+            pr["val"][o:o + p.npairs] = p.vals
+            o += p.npairs
+        outs = [np.full((d[2], d[1], d[0]), 7.0, np.float64) for d in shapes]
+        od = wc.capi.box_descs([o.ctypes.data for o in outs], [wc.WC_F64] * len(outs), shapes)
+        dp = ctx.decode_plan(od, wc.WC_HOST)
+        dp.decode(pr.ctypes.data, kk.ctypes.data, wc.WC_HOST)
+        dp.finish()
+        dp.close()
+        for o, ob, d in zip(outs, want, shapes):
+            assert same_bits(o.astype(np.float32), ob), d
+    finally:
+        ctx.set_option(wc.capi.WC_OPT_SEG_INDEX, 0)

@@ -123,9 +123,40 @@ struct DecCache {
 };
 // Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
 // stream), then the single-CTA kernels (second stream when both kinds are present).
-enum { FL_N = 9 };
+enum { FL_N = 10 };
 static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_R4, FUSED_CLS_R2, FUSED_CLS_CUBE32,
-                                    FUSED_CLS_R1, FUSED_CLS_CUBE16, FUSED_CLS_R1S, FUSED_CLS_CUBE8};
+                                    FUSED_CLS_R1, FUSED_CLS_CUBE16, FUSED_CLS_R1S, FUSED_CLS_CUBE8,
+                                    FUSED_CLS_RBIG /* decompress only; compress plans never fill it */};
+enum { FL_BIG = 9 };
+// One launch takes units of one slab count: the FUSED_CLS_RBIG list is kept sorted by it (then by unit id) and launched
+// run by run; every other class is a single run.  f(first, count, slabs)
+template <class Dims, class F>
+static int for_each_run(int cls, const std::vector<int>& list, Dims dims, F f) {
+    if (cls != FUSED_CLS_RBIG) return list.empty() ? WC_OK : f((size_t)0, list.size(), 0);
+    size_t a = 0;
+    while (a < list.size()) {
+        int nx, ny, nz;
+        dims(list[a], nx, ny, nz);
+        const int S = fused_decode_slabs_of(cls, nx, ny, nz);
+        size_t b = a + 1;
+        for (; b < list.size(); ++b) {
+            dims(list[b], nx, ny, nz);
+            if (fused_decode_slabs_of(cls, nx, ny, nz) != S) break;
+        }
+        int rc = f(a, b - a, S);
+        if (rc != WC_OK) return rc;
+        a = b;
+    }
+    return WC_OK;
+}
+template <class Dims>
+static void sort_big_list(std::vector<int>& list, Dims dims) {
+    std::stable_sort(list.begin(), list.end(), [&](int x, int y) {
+        int ax, ay, az, bx, by, bz;
+        dims(x, ax, ay, az); dims(y, bx, by, bz);
+        return fused_decode_slabs_of(FUSED_CLS_RBIG, ax, ay, az) < fused_decode_slabs_of(FUSED_CLS_RBIG, bx, by, bz);
+    });
+}
 static inline bool fl_is_cluster(int k) { return k < 4; }
 
 struct wc_plan {
@@ -499,7 +530,7 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
         if (fk >= 0) {
             p->fl[fk].push_back(i);
             // cluster classes: room for the decode-side segment table the compress kernel fills for free
-            const size_t te = fused_decode_table_entries(cls, b.nx);
+            const size_t te = fused_decode_table_entries(cls, b.nx, b.ny, b.nz);
             if (te) {
                 coef_off[i] = coef_floats;
                 coef_floats += align_up(2 * te, 4);
@@ -1080,9 +1111,9 @@ static inline void dec_hash(uint64_t& h1, uint64_t& h2, uint64_t v) {
 
 // the decompress kernel of one fused class list (WC_OPT_DECODE_PIPE selects the staged variant of the 32^3 kernel)
 static cudaError_t launch_decode(wc_ctx* ctx, int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list,
-                                 int n, int* err, int* counter, bool v1_tables) {
+                                 int n, int* err, int* counter, bool v1_tables, int s_rt = 0) {
     return launch_fused_decompress(fused_cls, dec, inv, list, n, err, ctx->sm_count, ctx->stream, &ctx->ls, counter, v1_tables,
-                                   ctx->opt_decode_pipe);
+                                   ctx->opt_decode_pipe, s_rt);
 }
 
 // A plan that decodes into the same boxes again (keep sweeps of the estimate mode) re-launches from the
@@ -1106,11 +1137,11 @@ static int relaunch_decompress(wc_ctx* ctx, const DecCache* cache, DevBuf& d_dec
 
 // Segment tables of one slab-decoded class list with the streamed index kernel (k_seg_index3).
 static int build_tables_streamed(wc_ctx* ctx, int fused_cls, const int* d_list, int n, const DecUnitDev* d_dec,
-                                 const InvUnitDev* d_inv, int* d_err) {
+                                 const InvUnitDev* d_inv, int* d_err, int s_rt = 0) {
     CTX_CUDA(ctx, ctx->d_counter.reserve(64 * sizeof(int)));
     int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
     CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-    CTX_CUDA(ctx, launch_seg_index3(fused_cls, d_dec, d_inv, d_list, n, counter, d_err, ctx->sm_count, ctx->stream, &ctx->ls));
+    CTX_CUDA(ctx, launch_seg_index3(fused_cls, d_dec, d_inv, d_list, n, counter, d_err, ctx->sm_count, ctx->stream, &ctx->ls, s_rt));
     return WC_OK;
 }
 
@@ -1137,7 +1168,7 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
         coef_off[i] = coef_floats;
         if (cls == 0) coef_floats += align_up((size_t)total, 4);
         else if (cls > 0 && !jobs[i].segtab && fused_decode_needs_table(cls))
-            coef_floats += align_up(2 * fused_decode_table_entries(cls, jobs[i].nx), 4);   // int2 segment table
+            coef_floats += align_up(2 * fused_decode_table_entries(cls, jobs[i].nx, jobs[i].ny, jobs[i].nz), 4);   // int2 segment table
         du[i].pairs      = jobs[i].pairs_dev;
         du[i].npairs_dev = jobs[i].npairs_dev;
         du[i].npairs     = jobs[i].npairs;
@@ -1162,6 +1193,8 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
                 }
         }
     }
+    auto job_dims = [&](int i, int& nx, int& ny, int& nz) { nx = jobs[i].nx; ny = jobs[i].ny; nz = jobs[i].nz; };
+    sort_big_list(fl[FL_BIG], job_dims);
     CTX_CUDA(ctx, d_coef.reserve(sizeof(float) * std::max<size_t>(coef_floats, 4)));
     for (int i = 0; i < n; ++i) {
         du[i].coef = d_coef.as<float>() + coef_off[i];
@@ -1203,28 +1236,30 @@ static int run_decompress(wc_ctx* ctx, const std::vector<DecJob>& jobs, DevBuf& 
             if (fl[k].empty()) continue;
             CTX_CUDA(ctx, cudaMemcpyAsync(dl + o, fl[k].data(), sizeof(int) * fl[k].size(),
                                           cudaMemcpyHostToDevice, ctx->stream));
-            bool v1_tables = build_tables[k];
-            if (build_tables[k] && ctx->opt_seg_index == 0) {
-                // every unit of a slab-decoded class arrives either with or without its table; the streamed
-                // index only handles lists where all do without (mixed lists keep the one-CTA-per-unit kernel)
-                bool all_without = true;
-                for (int i : fl[k]) all_without = all_without && !slab_tab[i];
-                if (all_without) {
-                    int rc = build_tables_streamed(ctx, FL_CLASS[k], dl + o, (int)fl[k].size(), d_dec_units.as<DecUnitDev>(),
-                                                   d_inv_units.as<InvUnitDev>(), d_err.as<int>());
-                    if (rc != WC_OK) return rc;
+            // every unit of a slab-decoded class arrives either with or without its table; the streamed
+            // index only handles lists where all do without (mixed lists keep the one-CTA-per-unit kernel)
+            bool all_without = true;
+            for (int i : fl[k]) all_without = all_without && !slab_tab[i];
+            int rc = for_each_run(FL_CLASS[k], fl[k], job_dims, [&](size_t a, size_t cnt, int s_rt) -> int {
+                bool v1_tables = build_tables[k];
+                if (build_tables[k] && ctx->opt_seg_index == 0 && all_without) {
+                    int rc2 = build_tables_streamed(ctx, FL_CLASS[k], dl + o + a, (int)cnt, d_dec_units.as<DecUnitDev>(),
+                                                    d_inv_units.as<InvUnitDev>(), d_err.as<int>(), s_rt);
+                    if (rc2 != WC_OK) return rc2;
                     v1_tables = false;
                 }
-            }
-            int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
-            CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-            CTX_CUDA(ctx, launch_decode(ctx, FL_CLASS[k], d_dec_units.as<DecUnitDev>(), d_inv_units.as<InvUnitDev>(), dl + o,
-                                        (int)fl[k].size(), d_err.as<int>(), counter, v1_tables));
+                int* counter = ctx->d_counter.as<int>() + (ctx->counter_next++ & 63);
+                CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+                CTX_CUDA(ctx, launch_decode(ctx, FL_CLASS[k], d_dec_units.as<DecUnitDev>(), d_inv_units.as<InvUnitDev>(), dl + o + a,
+                                            (int)cnt, d_err.as<int>(), counter, v1_tables, s_rt));
+                return WC_OK;
+            });
+            if (rc != WC_OK) return rc;
             o += fl[k].size();
         }
     }
     if (cache) {
-        bool ok = coef_floats == 0 && ptiles.empty() && xtiles.empty();
+        bool ok = coef_floats == 0 && ptiles.empty() && xtiles.empty() && fl[FL_BIG].empty();
         for (int k = 0; k < FL_N; ++k) {
             cache->fl_n[k] = fl[k].size();
             ok = ok && !build_tables[k];
@@ -1441,7 +1476,7 @@ int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_sp
                 dp->fl[k].push_back(i);
                 if (fused_decode_needs_table(cls)) {
                     tab_off[i] = dp->tab_floats;
-                    dp->tab_floats += align_up(2 * fused_decode_table_entries(cls, o.nx), 4);
+                    dp->tab_floats += align_up(2 * fused_decode_table_entries(cls, o.nx, o.ny, o.nz), 4);
                 }
             }
     }
@@ -1455,6 +1490,7 @@ int wc_dplan_create(wc_ctx* ctx, const wc_box_out* outs, int n_units, int out_sp
     if ((e = dp->h_err.reserve(64)) != cudaSuccess) return fail(e, "dplan pinned alloc");
     size_t n_fused = 0;
     std::vector<int> lists;
+    sort_big_list(dp->fl[FL_BIG], [&](int i, int& nx, int& ny, int& nz) { nx = outs[i].nx; ny = outs[i].ny; nz = outs[i].nz; });
     for (int k = 0; k < FL_N; ++k) {
         dp->fl_off[k] = n_fused;
         n_fused += dp->fl[k].size();
@@ -1507,23 +1543,29 @@ static int dplan_launch_range(wc_dplan* dp, int u0, int u1, size_t fi[FL_N]) {
         size_t j = fi[k];
         while (j < dp->fl[k].size() && dp->fl[k][j] < u1) ++j;
         if (j > fi[k]) {
-            const int* list = dp->d_lists.as<int>() + dp->fl_off[k] + fi[k];
-            const int  nl   = (int)(j - fi[k]);
-            bool v1 = false;
-            if (tab) {
-                if (ctx->opt_seg_index == 0) {
-                    int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
-                    CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-                    CTX_CUDA(ctx, launch_seg_index3(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
-                                                    counter, dp->d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls));
-                } else {
-                    v1 = true;
+            const std::vector<int> sub(dp->fl[k].begin() + fi[k], dp->fl[k].begin() + j);
+            auto dims = [&](int i, int& nx, int& ny, int& nz) { nx = dp->outs[i].nx; ny = dp->outs[i].ny; nz = dp->outs[i].nz; };
+            int rc = for_each_run(FL_CLASS[k], sub, dims, [&](size_t a, size_t cnt, int s_rt) -> int {
+                const int* list = dp->d_lists.as<int>() + dp->fl_off[k] + fi[k] + a;
+                const int  nl   = (int)cnt;
+                bool v1 = false;
+                if (tab) {
+                    if (ctx->opt_seg_index == 0) {
+                        int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
+                        CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+                        CTX_CUDA(ctx, launch_seg_index3(FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
+                                                        counter, dp->d_err.as<int>(), ctx->sm_count, ctx->stream, &ctx->ls, s_rt));
+                    } else {
+                        v1 = true;
+                    }
                 }
-            }
-            int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
-            CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-            CTX_CUDA(ctx, launch_decode(ctx, FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
-                                        dp->d_err.as<int>(), counter, v1));
+                int* counter = dp->d_counter.as<int>() + (dp->counter_next++ & 63);
+                CTX_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+                CTX_CUDA(ctx, launch_decode(ctx, FL_CLASS[k], dp->d_dec.as<DecUnitDev>(), dp->d_inv.as<InvUnitDev>(), list, nl,
+                                            dp->d_err.as<int>(), counter, v1, s_rt));
+                return WC_OK;
+            });
+            if (rc != WC_OK) return rc;
         }
         fi[k] = j;
         if (tab) ++tl;
@@ -1591,7 +1633,8 @@ int wc_dplan_decode(wc_dplan* dp, const wc_pair* pairs, const int32_t* npairs, i
     }
     const wc_pair*  d_pairs  = pairs;
     const int32_t*  d_npairs = npairs;
-    const bool pipelined = in_space == WC_HOST && !dp->has_generic;
+    // (the slab-count runs of the big-box class are not in unit order: no chunking by unit range when there are any)
+    const bool pipelined = in_space == WC_HOST && !dp->has_generic && dp->fl[FL_BIG].empty();
     if (in_space == WC_HOST) {
         CTX_CUDA(ctx, dp->d_pairs.reserve(sizeof(wc_pair) * std::max<size_t>(total_pairs, 1)));
         d_pairs  = dp->d_pairs.as<wc_pair>();

@@ -46,6 +46,8 @@ constexpr int F_PAD    = 4;      // padding words per i' slab of C (keeps float4
                                  // the a-lanes of a warp hit banks 4a + 2cp + {0,1})
 constexpr int F_CPAD   = 256;    // total padding words of C (F_PAD * X, X <= 64)
 constexpr int F_MAXSEG = 128;    // segments (2*X) per CTA
+constexpr int F_MAXSEG_BIG = 256;   // ... of the runtime-slab-count decompress class (nx <= 128)
+constexpr int F_CPAD_BIG   = 512;
 
 template <int R, int CAP>
 struct FSmem {
@@ -89,13 +91,13 @@ struct SGeom {
     static constexpr int slab   = 2 * nb * Z_ + F_PAD;
 };
 
-__host__ __device__ inline bool fused_geom(int X, int Y, int Z, int dtype, int R, int cap, FGeom& g) {
-    if (X < 2 || Y < 2 || Z < 4 || (X & 1) || (Y & 1) || (Z & 3)) return false;
+__host__ __device__ inline bool fused_geom(int X, int Y, int Z, int dtype, int R, int cap, FGeom& g, int maxseg = F_MAXSEG) {
+    if (X < 2 || Y < 2 || Z < 4 || (X & 1) || (Y & 1) || (Z & 3) || R < 1) return false;
     g.X = X; g.Y = Y; g.Z = Z;
     g.hx = X / 2; g.hy = Y / 2; g.hz = Z / 2;
     g.es = dtype == WC_F64 ? 8 : 4;
     if ((X * g.es) % 16) return false;       // 16-byte vector loads of (x, x+1) pairs, row-aligned
-    if (2 * X > F_MAXSEG) return false;
+    if (2 * X > maxseg) return false;
     long long n = (long long)X * Y * Z;
     if (g.hy % R) return false;
     if (n / R > cap) return false;
@@ -107,6 +109,22 @@ __host__ __device__ inline bool fused_geom(int X, int Y, int Z, int dtype, int R
     g.nlocal = g.nseg * g.seglen;
     g.slab   = 2 * g.nb * Z + F_PAD;
     return true;
+}
+
+// Slab count of a box the cluster classes do not take (more than 262144 cells, or a half-height no cluster of 2 / 4 / 8
+// divides): the fewest y-slabs of at most 32768 cells, 0 if the box has no such decomposition (odd dimension, nz not a
+// multiple of 4, nx > 128, a single block-row above 32768 cells).  Decompress only needs independent slab items
+// (FUSED_CLS_RBIG); compress has no cluster that large.
+__host__ __device__ inline int big_slabs(int nx, int ny, int nz) {
+    if (nx < 2 || ny < 2 || nz < 4 || (nx & 1) || (ny & 1) || (nz & 3) || 2 * nx > F_MAXSEG_BIG) return 0;
+    const long long row = 2ll * nx * nz;                // cells of one block-row
+    if (row > 32768) return 0;
+    const int hy = ny / 2;
+    int nb = (int)(32768 / row);
+    if (nb > hy) nb = hy;
+    while (hy % nb) --nb;
+    const int S = hy / nb;
+    return (S >= 2 && S <= 1024) ? S : 0;
 }
 
 int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
@@ -1155,7 +1173,7 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
         FGeom g;
-        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g);
+        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g, F_MAXSEG_BIG);
         const uint32_t seglen = (uint32_t)g.seglen, total = (uint32_t)du.total;
         const int nseg = g.nseg * slabs;                   // == total / seglen
         int2* const tab = reinterpret_cast<int2*>(du.coef);
@@ -1229,11 +1247,14 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
 // never waits for HBM (k_seg_index: loads -> scan -> barrier in sequence per tile, 2 TB/s; the chunk-parallel
 // look-back version that came between them was bound by five dependent global round trips per 32 KB work item).
 // Two CTAs per SM, units handed out dynamically.
-//   A thread owns SI_PPT consecutive pairs of a tile (odd: conflict-free 8-byte shared-memory reads).
+//   A thread owns SI_PPT consecutive pairs of a tile and reads only their runs (odd SI_PPT: the lanes' 4-byte reads at a
+//   stride of 2 * SI_PPT words are two-way conflicts at worst).  The kernel is bound by its instruction count, not by
+//   memory: ~4 instructions per pair for the sums, one block scan per 3840 pairs, and a branch-free search for the
+//   (usually single) segment boundary a thread's pairs cross.
 //   Bulk copies need 16-byte aligned addresses and sizes: a list that starts on an odd pair is fetched from one
 //   pair earlier, an odd count is rounded up — both stay inside the 16-byte granule of a valid pair, so they never
 //   leave the allocation's pages; slot r + s0 of a stage holds the tile's r-th pair.
-constexpr int SI_NT = 512, SI_PPT = 7, SI_TILE = SI_NT * SI_PPT, SI_STAGES = 3, SI_SLOTS = SI_TILE + 2;
+constexpr int SI_NT = 256, SI_PPT = 15, SI_TILE = SI_NT * SI_PPT, SI_STAGES = 3, SI_SLOTS = SI_TILE + 2;
 constexpr uint32_t SI_CL = 1u << 19;   // clamp of one pair's run + 1: > any ncoef of a slab-decoded unit (262144);
                                        // SI_TILE * SI_CL < 2^31 and the carry is clamped at 2^30: u32 sums never wrap
 constexpr int SI_SMEM = SI_STAGES * SI_SLOTS * 8 + 64 + 2 * 32 * 4 + 32;
@@ -1264,7 +1285,7 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
         FGeom g;
-        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g);
+        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g, F_MAXSEG_BIG);
         const uint32_t seglen = (uint32_t)g.seglen, total = (uint32_t)du.total;
         const int nseg = g.nseg * slabs;                   // == total / seglen
         int2* const tab = reinterpret_cast<int2*>(du.coef);
@@ -1293,30 +1314,31 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
             const uint32_t q = q0 + (uint32_t)t, st = q % SI_STAGES;
             mbar_wait_cta(bars + 8 * st, (q / SI_STAGES) & 1u);
             const int p = t * SI_TILE + tid * SI_PPT;      // first pair of this thread
-            int2 pr[SI_PPT];
+            int run[SI_PPT];
             {
-                const int2* sp = stage + st * SI_SLOTS + tid * SI_PPT + s0;
+                const int* sp = reinterpret_cast<const int*>(stage + st * SI_SLOTS + tid * SI_PPT + s0);
 #pragma unroll
-                for (int j = 0; j < SI_PPT; ++j) pr[j] = sp[j];
+                for (int j = 0; j < SI_PPT; ++j) run[j] = sp[2 * j];
             }
-            if (p + SI_PPT > K) {                          // pairs past the end of the list are dead: (-1, 0)
+            if (p + SI_PPT > K) {                          // pairs past the end of the list are dead: run = -1
 #pragma unroll
-                for (int j = 0; j < SI_PPT; ++j) if (p + j >= K) pr[j] = make_int2(-1, 0);
+                for (int j = 0; j < SI_PPT; ++j) if (p + j >= K) run[j] = -1;
             }
             uint32_t inc[SI_PPT];
             int any = 0;
+            uint32_t s = 0;
 #pragma unroll
             for (int j = 0; j < SI_PPT; ++j) {
-                any |= pr[j].x;
-                inc[j] = min((uint32_t)pr[j].x + 1u, SI_CL);
+                any |= run[j];
+                inc[j] = min((uint32_t)run[j] + 1u, SI_CL);
             }
             if (any < 0) {
 #pragma unroll
                 for (int j = 0; j < SI_PPT; ++j)
-                    if (pr[j].x < 0) { inc[j] = 0; if (p + j < K) bad = true; }
+                    if (run[j] < 0) { inc[j] = 0; if (p + j < K) bad = true; }
             }
-            const uint32_t s = ((inc[0] + inc[1]) + (inc[2] + inc[3])) + ((inc[4] + inc[5]) + inc[6]);
-            static_assert(SI_PPT == 7, "sum above");
+#pragma unroll
+            for (int j = 0; j < SI_PPT; ++j) s += inc[j];
             uint32_t w = s;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1329,22 +1351,36 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
             if (tid == 0 && t + SI_STAGES < ntiles) issue(t + SI_STAGES);
             uint32_t ws = lane < SI_NT / 32 ? wt[lane] : 0u;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
+            for (int o = 1; o < SI_NT / 32; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, ws, o);
                 if (lane >= o) ws += v;
             }
-            const uint32_t ttot = __shfl_sync(0xffffffffu, ws, 31);
+            const uint32_t ttot = __shfl_sync(0xffffffffu, ws, SI_NT / 32 - 1);
             uint32_t wpre = __shfl_sync(0xffffffffu, ws, (warp + 31) & 31);
             if (warp == 0) wpre = 0;
             const uint32_t pre = carry + wpre + (w - s);   // flat index this thread's first run starts at
             carry = min(carry + ttot, 1u << 30);
             if (s != 0 && pre < total) {
                 const uint32_t end1 = pre + s - 1u;        // flat index of the thread's last live pair
-                if (any >= 0 && end1 < total) { gk = p + SI_PPT; gl = (int)end1; }
+                const bool plain = any >= 0 && end1 < total;   // all pairs live and inside the box
+                if (plain) { gk = p + SI_PPT; gl = (int)end1; }
                 // segment boundaries m * seglen inside [pre, end1]: each belongs to the pair whose interval
                 // [start of its run, its flat index] holds it
                 const uint32_t mlo = dsl.div(pre + seglen - 1u), mhi = dsl.div(min(end1, total - 1u));
-                if (mlo <= mhi || any < 0 || end1 >= total) {
+                if (plain && mlo == mhi) {
+                    // one boundary (the usual case): count the pairs that end in front of it, without a branch
+                    const uint32_t fb = mlo * seglen;
+                    uint32_t rp = pre, start = pre;
+                    int nb = 0;
+#pragma unroll
+                    for (int j = 0; j < SI_PPT; ++j) {
+                        rp += inc[j];
+                        const bool before = rp <= fb;
+                        nb += before ? 1 : 0;
+                        start = before ? rp : start;
+                    }
+                    tab[mlo] = make_int2(p + nb, (int)start - 1);
+                } else if (!plain || mlo < mhi) {
                     uint32_t rp = pre, m = mlo, fb = mlo * seglen;
 #pragma unroll
                     for (int j = 0; j < SI_PPT; ++j) {
@@ -1636,6 +1672,8 @@ struct FDLookahead {
     const int*        unit_list;
     int*              work_counter;
     int               n_items, stride;    // items = S per listed unit: item i -> unit_list[i / S], slab i % S
+    int               s_rt;               // S == 0: the slab count is a launch argument (one value per launch)
+    __device__ __forceinline__ int unit_of(int idx) const { return S ? idx / S : idx / s_rt; }
     FDLookState*      st;
     FDDesc*           slot;        // item k's slot: receives item k+2
     FDDesc*           next_slot;   // item k+1
@@ -1684,7 +1722,7 @@ struct FDLookahead {
         }
         st->idx_b = idx;
         st->uid_b = -1;
-        if (idx < n_items) cp4(&st->uid_b, unit_list + idx / S);
+        if (idx < n_items) cp4(&st->uid_b, unit_list + unit_of(idx));
     }
     // the first four items of the CTA: 0 and 1 into the descriptor slots, 2 and 3 into the state
     __device__ __forceinline__ void prologue(FDDesc* s_desc) {
@@ -1700,7 +1738,7 @@ struct FDLookahead {
                 st->batch_left -= 1;
             }
             prev = idx;
-            const int uid = idx < n_items ? __ldg(unit_list + idx / S) : -1;
+            const int uid = idx < n_items ? __ldg(unit_list + unit_of(idx)) : -1;
             if (k < 2) {
                 FDDesc& d = s_desc[k];
                 d.ui = idx; d.uid = uid; d.K = 0;
@@ -1725,8 +1763,10 @@ struct FDStage {          // STG kernels only: staging area, its mbarrier, stage
 template <int S, int NT, bool STG, class G>
 __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const InvUnitDev& iu, const int K,
                                         float* const C, uint32_t* const s_wt, FDLookahead<S>& la,
-                                        const uint32_t rank, int* __restrict__ err, const bool have_next, FDStage& stg) {
+                                        const uint32_t rank, int* __restrict__ err, const bool have_next, FDStage& stg,
+                                        const int s_rt = 0) {
     constexpr int NW = NT / 32;
+    const int Sx = S ? S : s_rt;            // slabs per unit
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b0 = rank * g.nb;
     const uint32_t total = (uint32_t)du.total;
@@ -1738,14 +1778,14 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
     int2 te = make_int2(0, 0);
     // S = 1 units decode by segments too when a table came with them (plan round trip: the compress kernel
     // wrote it); without one they take the block-wide scan, which needs no second pass over the list
-    const bool use_tab = S > 1 || (du.coef != nullptr && !(STG && stg.ignore_tab));
+    const bool use_tab = S != 1 || (du.coef != nullptr && !(STG && stg.ignore_tab));
     if (!use_tab) {
         if (!STG) fd_load_tile(pairs, vec16, tid * FD_PPT, K, pr);
     } else {
         // segment table entries of this warp's first 16 segments: lane 2q + e <- tab[m(q) + e]
         const int sg = fd_seg_of(lane >> 1, warp, NW);
         if ((lane >> 1) * NW + warp < g.nseg)
-            te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sg >> 1) * (2 * S) + (sg & 1) * S + (int)rank + (lane & 1));
+            te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sg >> 1) * (2 * Sx) + (sg & 1) * Sx + (int)rank + (lane & 1));
     }
 
     // 1. zero-fill C (rle_decode starts from zeros, src/decompressor.cpp:17).  The staged kernel instead zeroes C once at
@@ -1804,14 +1844,14 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         for (int q = 0; q * NW + warp < g.nseg; ++q) {
             const int sg = fd_seg_of(q, warp, NW);
             const int i = sg >> 1, half = sg & 1;
-            const int m = i * (2 * S) + half * S + (int)rank;
+            const int m = i * (2 * Sx) + half * Sx + (int)rank;
             if (q && (q & 15) == 0) {
                 // a warp holds the entries of 16 segments at a time: next round (more than 16 segments per
                 // warp only happens with few warps and a long x axis, e.g. 48 x 4 x 8 boxes)
                 const int qq = q + (lane >> 1), sq = fd_seg_of(qq, warp, NW);
                 te = make_int2(0, 0);
                 if (qq * NW + warp < g.nseg)
-                    te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sq >> 1) * (2 * S) + (sq & 1) * S + (int)rank + (lane & 1));
+                    te = __ldg(reinterpret_cast<const int2*>(du.coef) + (sq >> 1) * (2 * Sx) + (sq & 1) * Sx + (int)rank + (lane & 1));
             }
             const int ql = q & 15;
             const int e0x = __shfl_sync(0xffffffffu, te.x, 2 * ql), e0y = __shfl_sync(0xffffffffu, te.y, 2 * ql);
@@ -1847,6 +1887,24 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         const int nlines = (Kn * 8 + 127) / 128;
         for (int i = line0 + tid; i < nlines; i += NT)
             asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)i * 128));
+    }
+    if (S != 1 && have_next) {
+        // slab items: the pair ranges of the NEXT item's segments (one per thread) go into L2 while this item is inverted.
+        // With ~600-byte ranges and one segment in flight per warp the decode was bound by memory latency (128^3 boxes:
+        // 12 GB/s per SM); the table entries are usually L2 hits (the index kernel has just written them).
+        const FDDesc* nd = la.next_slot;
+        const int2* ntab = reinterpret_cast<const int2*>(nd->du.coef);
+        const int nseg_n = 2 * nd->iu.nx;
+        if (ntab && tid < nseg_n) {
+            const int rank_n = nd->ui % Sx;
+            const int2* e = ntab + (tid >> 1) * (2 * Sx) + (tid & 1) * Sx + rank_n;
+            const int p0 = __ldg(&e[0].x), p1 = __ldg(&e[1].x);
+            const char* b0p = reinterpret_cast<const char*>(nd->du.pairs);
+            const uintptr_t a0 = (reinterpret_cast<uintptr_t>(b0p) + (size_t)p0 * 8) & ~(uintptr_t)127;
+            const uintptr_t a1 = reinterpret_cast<uintptr_t>(b0p) + (size_t)p1 * 8;
+            for (uintptr_t a = a0; a < a1; a += 128)
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a));
+        }
     }
     WC_PHASE_CLOCK(t4);
     if (tid == 0) la.stage3();
@@ -1924,10 +1982,11 @@ template <int S, int CAP, int NT, bool STATIC, bool STG>
 __global__ void __launch_bounds__(NT, (CAP <= 512 ? 32 : CAP <= 4096 ? 4 : 1))
 k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
                    const int* __restrict__ unit_list, int n_list, int* __restrict__ err,
-                   int* __restrict__ work_counter, int ignore_tab) {
+                   int* __restrict__ work_counter, int ignore_tab, int s_rt) {
     static_assert(!STG || S == 1, "staged decode: whole-unit items only");
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int BASE = (CAP + F_CPAD) * 4;
+    constexpr int BASE = (CAP + (S ? F_CPAD : F_CPAD_BIG)) * 4;
+    const int Sx = S ? S : s_rt;
     float* const    C    = reinterpret_cast<float*>(smem);
     uint32_t* const s_wt = reinterpret_cast<uint32_t*>(smem + BASE);               // [2][32]
     FDDesc* const s_desc = reinterpret_cast<FDDesc*>(smem + BASE + 256);          // [2] x 88 bytes
@@ -1951,7 +2010,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
-    const int n_items = n_list * S;
+    const int n_items = n_list * Sx;
     if (STG) {   // the coefficient array starts out zeroed; every item leaves it zeroed (fd_unit step 3)
         float4* c4 = reinterpret_cast<float4*>(C);
         for (int i = tid; i < (CAP + F_CPAD) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1961,7 +2020,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
     FDLookahead<S> la;
     la.dec = dec; la.inv = inv; la.unit_list = unit_list;
     la.work_counter = work_counter;
-    la.n_items = n_items; la.stride = (int)gridDim.x;
+    la.n_items = n_items; la.stride = (int)gridDim.x; la.s_rt = s_rt;
     la.st = reinterpret_cast<FDLookState*>(smem + BASE + 448);
     la.batch = CAP <= 4096 ? 16 : 1; la.raw = 0; la.refill = false;
     if (tid == 0) la.prologue(s_desc);
@@ -1981,17 +2040,17 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         const DecUnitDev du = d.du;
         const InvUnitDev iu = d.iu;
         const int K = d.K;
-        const uint32_t rank = (uint32_t)(d.ui % S);
+        const uint32_t rank = (uint32_t)(d.ui % Sx);
         la.slot      = &s_desc[k & 1];
         la.next_slot = &s_desc[(k + 1) & 1];
         const bool have_next = la.next_slot->ui < n_items;
-#define WC_FD_UNIT(GEOM) fd_unit<S, NT, STG>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next, stg)
+#define WC_FD_UNIT(GEOM) fd_unit<S, NT, STG>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next, stg, s_rt)
         if constexpr (STATIC) {
             constexpr int CUBE = S == 1 ? (CAP <= 512 ? 8 : CAP <= 4096 ? 16 : 32) : 64;
             WC_FD_UNIT((SGeom<CUBE, CUBE, CUBE, 8, S>()));
         } else {
             FGeom g;
-            fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, S, CAP, g);   // same rule as fused_decode_class
+            fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, Sx, CAP, g, S ? F_MAXSEG : F_MAXSEG_BIG);   // same rule as fused_decode_class
             WC_FD_UNIT(g);
         }
 #undef WC_FD_UNIT
@@ -2001,17 +2060,18 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
 template <int S, int CAP, int NT, bool STATIC, bool STG = false>
 static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                              int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter,
-                             bool build_tables, bool ignore_tab = false) {
+                             bool build_tables, bool ignore_tab = false, int s_rt = 0) {
     auto kern = k_fused_decompress<S, CAP, NT, STATIC, STG>;
-    constexpr int smem = (CAP + F_CPAD) * 4 + 1024 + (STG ? FS_SLOTS * 8 : 0);
+    constexpr int smem = (CAP + (S ? F_CPAD : F_CPAD_BIG)) * 4 + 1024 + (STG ? FS_SLOTS * 8 : 0);
+    const int Sx = S ? S : s_rt;
     static_assert(smem <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    if (S > 1 && build_tables) {
+    if (S != 1 && build_tables) {
         // segment tables first: one CTA per unit, a few units per SM
         const int nb = n < 2 * sm_count ? n : 2 * sm_count;
         ls->begin(KID_SEG_INDEX, st);
-        k_seg_index<512><<<nb, 512, 0, st>>>(dec, inv, list, n, err, S);
+        k_seg_index<512><<<nb, 512, 0, st>>>(dec, inv, list, n, err, Sx);
         ls->end(st);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -2022,14 +2082,14 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
-    const long long items = (long long)n * S, slots = (long long)per_sm * sm_count;
+    const long long items = (long long)n * Sx, slots = (long long)per_sm * sm_count;
     const int nc = (int)(slots < items ? slots : items);
     ls->begin(kid, st);
     int karg = ignore_tab ? 1 : 0;
 #ifdef WC_PHASE_PROFILE
     if (const char* sgv = getenv("WCGPU_STAGGER")) karg |= atoi(sgv) << 8;
 #endif
-    kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter, karg);
+    kern<<<nc, NT, smem, st>>>(dec, inv, list, n, err, work_counter, karg, s_rt);
     ls->end(st);
     return cudaGetLastError();
 }
@@ -2044,13 +2104,15 @@ int fused_decode_slabs(int fused_cls) {
 }
 
 cudaError_t launch_seg_index3(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
-                              int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls) {
+                              int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int s_rt) {
     if (n <= 0 || !fused_decode_needs_table(fused_cls)) return cudaSuccess;
+    const int slabs = fused_cls == FUSED_CLS_RBIG ? s_rt : fused_decode_slabs(fused_cls);
+    if (slabs < 2) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_seg_index3, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM);
     if (e != cudaSuccess) return e;
     const int nb = n < 2 * sm_count ? n : 2 * sm_count;
     ls->begin(KID_SEG_INDEX2, st);
-    k_seg_index3<<<nb, SI_NT, SI_SMEM, st>>>(dec, inv, list, n, err, fused_decode_slabs(fused_cls), work_counter);
+    k_seg_index3<<<nb, SI_NT, SI_SMEM, st>>>(dec, inv, list, n, err, slabs, work_counter);
     ls->end(st);
     return cudaGetLastError();
 }
@@ -2081,10 +2143,15 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
     if (fused_geom(nx, ny, nz, WC_F64, 2, 32768, g)) return FUSED_CLS_R2;
     if (fused_geom(nx, ny, nz, WC_F64, 4, 32768, g)) return FUSED_CLS_R4;
     if (fused_geom(nx, ny, nz, WC_F64, 8, 32768, g)) return FUSED_CLS_R8;
+    if (big_slabs(nx, ny, nz)) return FUSED_CLS_RBIG;
     return FUSED_CLS_NONE;
 }
+int fused_decode_slabs_of(int fused_cls, int nx, int ny, int nz) {
+    return fused_cls == FUSED_CLS_RBIG ? big_slabs(nx, ny, nz) : fused_decode_slabs(fused_cls);
+}
 // int2 entries of the segment table a slab-decoded unit needs (0 for the other classes)
-size_t fused_decode_table_entries(int fused_cls, int nx) {
+size_t fused_decode_table_entries(int fused_cls, int nx, int ny, int nz) {
+    if (fused_cls == FUSED_CLS_RBIG) return (size_t)(2 * nx * big_slabs(nx, ny, nz) + 1);
     if (fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64) return (size_t)(2 * nx * 8 + 1);
     if (fused_cls == FUSED_CLS_R4) return (size_t)(2 * nx * 4 + 1);
     if (fused_cls == FUSED_CLS_R2) return (size_t)(2 * nx * 2 + 1);
@@ -2094,13 +2161,19 @@ size_t fused_decode_table_entries(int fused_cls, int nx) {
     return 0;
 }
 bool fused_decode_needs_table(int fused_cls) {
-    return fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64 || fused_cls == FUSED_CLS_R4 || fused_cls == FUSED_CLS_R2;
+    return fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64 || fused_cls == FUSED_CLS_R4 || fused_cls == FUSED_CLS_R2 ||
+           fused_cls == FUSED_CLS_RBIG;
 }
 
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
-                                    cudaStream_t st, LaunchStats* ls, int* work_counter, bool build_tables, int stage) {
+                                    cudaStream_t st, LaunchStats* ls, int* work_counter, bool build_tables, int stage,
+                                    int s_rt) {
     if (n_list <= 0) return cudaSuccess;
+    if (fused_cls == FUSED_CLS_RBIG)
+        return s_rt >= 2 ? launch_fd<0, 32768, 512, false>(KID_FUSED_DBIG, dec, inv, unit_list, n_list, err, sm_count, st, ls,
+                                                          work_counter, build_tables, false, s_rt)
+                         : cudaErrorInvalidValue;
     if (stage && fused_cls == FUSED_CLS_CUBE32)
         return launch_fd<1, 32768, 1024, true, true>(KID_STAGED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls,
                                                      work_counter, false, stage == 2);

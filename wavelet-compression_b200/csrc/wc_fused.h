@@ -22,10 +22,12 @@ enum { FUSED_FULL = 0, FUSED_KEYS_ONLY = 1, FUSED_GIVEN_THRESH = 2,
 enum { FUSED_CLS_NONE = 0, FUSED_CLS_R1 = 1, FUSED_CLS_R1S = 2, FUSED_CLS_R8 = 8, FUSED_CLS_R4 = 24,
        FUSED_CLS_R2 = 22,      // clusters of 4 / 2: boxes whose half-height is not a multiple of 8 (40^3 ...)
        FUSED_CLS_CUBE32 = 101,
-       FUSED_CLS_CUBE64 = 108, FUSED_CLS_CUBE16 = 116, FUSED_CLS_CUBE8 = 117 };
+       FUSED_CLS_CUBE64 = 108, FUSED_CLS_CUBE16 = 116, FUSED_CLS_CUBE8 = 117,
+       FUSED_CLS_RBIG = 200 };  // decompress only: any number of y-slabs of <= 32768 cells (128^3 ...), one launch per slab count
 int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
-size_t fused_decode_table_entries(int fused_cls, int nx);   // int2 entries of a unit's segment table
+size_t fused_decode_table_entries(int fused_cls, int nx, int ny, int nz);   // int2 entries of a unit's segment table
+int fused_decode_slabs_of(int fused_cls, int nx, int ny, int nz);         // y-slabs (work items) per unit
 bool fused_decode_needs_table(int fused_cls);               // slab-decoded classes cannot decode without one
 
 cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states,
@@ -35,7 +37,7 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
                                     const int* unit_list, int n_list, int* err, int sm_count,
                                     cudaStream_t st, LaunchStats* ls, int* work_counter = nullptr,
-                                    bool build_tables = true, int stage = 0);
+                                    bool build_tables = true, int stage = 0, int s_rt = 0);
 // stage (32^3 cubes): 0 = pairs straight from global memory, 1 = table-less units decode from a shared-memory staging
 // area filled by TMA bulk copies one item ahead (k_staged_decompress), 2 = units with a segment table as well
 
@@ -43,7 +45,8 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
 // of a dense stream (k_dec_prepare).
 int fused_decode_slabs(int fused_cls);
 cudaError_t launch_seg_index3(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
-                              int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls);
+                              int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int s_rt = 0);
+// s_rt: slab count of the FUSED_CLS_RBIG units of this launch (every listed unit has the same)
 cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dense, const int32_t* npairs,
                                unsigned long long* chain /* (n_units + 1023) / 1024 + 1 words */, int* err, cudaStream_t st,
                                LaunchStats* ls);
