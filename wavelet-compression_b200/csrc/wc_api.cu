@@ -167,6 +167,8 @@ struct wc_plan {
     std::vector<UnitDev>     h_units;
     // unit ids per path: fl[k] = the fused class FL_CLASS[k] (ascending ids), generic = the rest
     std::vector<int>         fl[FL_N], generic;
+    std::vector<int>         bigfwd;     // generic units whose forward transform runs by y-slabs (k_big_forward), sorted by slab count
+    DevBuf                   d_bigfwd;
     std::vector<char>        has_segtab;                     // per unit: UnitDev::coef is a segment table
     long long total_n = 0;     // sum of ncoef
     size_t    in_bytes = 0;    // sum of input bytes
@@ -541,8 +543,12 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
             is_generic[i] = 1;
             coef_off[i] = coef_floats;
             coef_floats += align_up((size_t)n, 4);
-            int nt = xtile_count(b.nx, b.ny, b.nz);
-            for (int t = 0; t < nt; ++t) xtiles.push_back(make_int2(i, t));
+            if (ctx->opt_path != 1 && big_forward_slabs(b.nx, b.ny, b.nz, b.dtype, cls_ptr)) {
+                p->bigfwd.push_back(i);
+            } else {
+                int nt = xtile_count(b.nx, b.ny, b.nz);
+                for (int t = 0; t < nt; ++t) xtiles.push_back(make_int2(i, t));
+            }
             u.ctile0  = (int32_t)ctiles.size();
             u.nctiles = ctile_count(n);
             for (int t = 0; t < u.nctiles; ++t) ctiles.push_back(make_int2(i, t));
@@ -600,6 +606,13 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
                                  cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
             return fail(e, "fused list upload");
     }
+    if (!p->bigfwd.empty()) {
+        sort_big_list(p->bigfwd, [&](int i, int& nx, int& ny, int& nz) { nx = p->h_units[i].nx; ny = p->h_units[i].ny; nz = p->h_units[i].nz; });
+        PLAN_RESERVE(p->d_bigfwd, sizeof(int) * p->bigfwd.size());
+        if ((e = cudaMemcpyAsync(p->d_bigfwd.p, p->bigfwd.data(), sizeof(int) * p->bigfwd.size(), cudaMemcpyHostToDevice,
+                                 ctx->stream)) != cudaSuccess)
+            return fail(e, "big-box list upload");
+    }
 #undef PLAN_RESERVE
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "plan sync");
     *out = p;
@@ -617,6 +630,7 @@ int wc_plan_destroy(wc_plan* p) {
                        &p->d_stage_out };
     for (DevBuf* b : bufs) b->release();
     for (int k = 0; k < FL_N; ++k) p->d_fl[k].release();
+    p->d_bigfwd.release();
     p->d_running.release();
     p->d_counter.release();
     p->d_rmse_tiles.release();
@@ -720,6 +734,18 @@ static int plan_forward(wc_plan* p, bool global_mode) {
     CTX_CUDA(ctx, launch_forward_generic(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
                                          p->d_xtiles.as<int2>(), p->n_xtiles, ctx->stream,
                                          &ctx->ls));
+    if (!p->bigfwd.empty()) {
+        auto dims = [&](int i, int& nx, int& ny, int& nz) { nx = p->h_units[i].nx; ny = p->h_units[i].ny; nz = p->h_units[i].nz; };
+        int rc = for_each_run(FUSED_CLS_RBIG, p->bigfwd, dims, [&](size_t a, size_t cnt, int s_rt) -> int {
+            int* counter = nullptr;
+            int rc2 = plan_counter(p, ctx->stream, &counter);
+            if (rc2 != WC_OK) return rc2;
+            CTX_CUDA(ctx, launch_big_forward(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(), p->d_bigfwd.as<int>() + a,
+                                             (int)cnt, s_rt, counter, ctx->sm_count, ctx->stream, &ctx->ls));
+            return WC_OK;
+        });
+        if (rc != WC_OK) return rc;
+    }
     if (global_mode) {
         for (int k = 0; k < FL_N; ++k)
             if (!p->fl[k].empty()) {

@@ -1059,6 +1059,98 @@ cudaError_t debug_phase_cycles(unsigned long long out[8], bool reset) {
 }
 #endif
 
+// ---- big boxes: forward transform of one y-slab per CTA, coefficients to the unit's scratch -----------------------
+// Boxes no cluster holds (more than 262144 cells: 128^3 ..., or a half-height no cluster size divides) take two passes:
+// this kernel (transform + arg-max key), then threshold and ordered packing from the coefficient scratch.  An item is a
+// (unit, y-slab) of at most 32768 cells, exactly the slab of the cluster kernels: phase A of k_fused_compress fills the
+// shared-memory array C from coalesced 16-byte row loads, and C leaves in whole segments (nb * Z consecutive
+// coefficients of the flat order) with 16-byte stores — 8N in, 4N out, where the tiled transform of the generic path
+// (shared-memory transposes, 4-byte scattered stores) ran at 2.3 TB/s.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+k_big_forward(const UnitDev* __restrict__ units, UnitState* __restrict__ states, const int* __restrict__ unit_list,
+              int n_list, int s_rt, int* __restrict__ work_counter) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* const C     = reinterpret_cast<float*>(smem);
+    u64* const   s_red = reinterpret_cast<u64*>(smem + (32768 + F_CPAD_BIG) * 4);          // [32]
+    int* const   s_it  = reinterpret_cast<int*>(smem + (32768 + F_CPAD_BIG) * 4 + 256);    // [2]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u64 pol = l2_policy_evict_first();
+    const int n_items = n_list * s_rt;
+    if (tid == 0) s_it[0] = atomicAdd(work_counter, 1);
+    __syncthreads();
+    for (int k = 0;; ++k) {
+        const int item = s_it[k & 1];
+        if (item >= n_items) break;
+        int next = 0;
+        if (tid == 0) next = atomicAdd(work_counter, 1);       // consumed at the end of this item
+        const int uid = __ldg(unit_list + item / s_rt);
+        const uint32_t rank = (uint32_t)(item % s_rt);
+        const UnitDev u = units[uid];
+        FGeom g;
+        fused_geom(u.nx, u.ny, u.nz, u.dtype, s_rt, 32768, g, F_MAXSEG_BIG);
+        const int b0 = rank * g.nb;
+        float bp = 0.f, bn = 0.f, vmn = 0.f, vmx = 0.f;
+        bool nan0 = false;
+        {
+            const char* in0 = static_cast<const char*>(u.in) + (size_t)(2 * b0) * ((size_t)g.X * g.es);
+            if (g.es == 8) phase_a<NT, 8, false>(g, in0, C, rank, pol, bp, bn, nan0, vmn, vmx);
+            else           phase_a<NT, 4, false>(g, in0, C, rank, pol, bp, bn, nan0, vmn, vmx);
+        }
+        __syncthreads();
+        // C -> scratch, segment by segment (a warp per segment at a time), and the arg-max key of the slab: largest
+        // |c|, lowest flat index among equals, NaNs skipped (make_key) — the rule of std::max_element on the flat array
+        u64 key = 0ull;
+        const int q4 = g.seglen >> 2;                              // float4 per segment (Z % 4 == 0)
+#pragma unroll 1
+        for (int sg = warp; sg < g.nseg; sg += NT / 32) {
+            const float4* src = reinterpret_cast<const float4*>(C + sg * g.seglen + F_PAD * (sg >> 1));
+            const uint32_t f0 = (uint32_t)(((sg >> 1) * g.Y + (sg & 1) * g.hy + b0) * g.Z);
+            float4* dst = reinterpret_cast<float4*>(u.coef + f0);
+#pragma unroll 2
+            for (int i = lane; i < q4; i += 32) {
+                const float4 v = src[i];
+                __stcs(dst + i, v);
+                const uint32_t f = f0 + 4u * (uint32_t)i;
+                key = max_u64(key, max_u64(max_u64(make_key(v.x, f), make_key(v.y, f + 1)),
+                                           max_u64(make_key(v.z, f + 2), make_key(v.w, f + 3))));
+            }
+        }
+        if (rank == 0 && tid == 0 && isnan(C[0])) atomicOr(&states[uid].flags, UNIT_FLAG_NAN0);
+        key = warp_max_u64(key);
+        if (lane == 0) s_red[warp] = key;
+        if (tid == 0) s_it[(k + 1) & 1] = next;
+        __syncthreads();                                           // C and s_red are rewritten by the next item
+        if (warp == 0) {
+            u64 x = lane < NT / 32 ? s_red[lane] : 0ull;
+            x = warp_max_u64(x);
+            if (lane == 0 && x != 0ull) atomicMax(&states[uid].key, x);
+        }
+    }
+}
+
+cudaError_t launch_big_forward(const UnitDev* units, UnitState* states, const int* unit_list, int n_list, int s_rt,
+                               int* work_counter, int sm_count, cudaStream_t st, LaunchStats* ls) {
+    if (n_list <= 0) return cudaSuccess;
+    if (s_rt < 2) return cudaErrorInvalidValue;
+    constexpr int NT = 512, smem = (32768 + F_CPAD_BIG) * 4 + 512;
+    cudaError_t e = cudaFuncSetAttribute(k_big_forward<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (long long)n_list * s_rt;
+    const int nc = (int)(items < sm_count ? items : sm_count);
+    ls->begin(KID_BIG_FORWARD, st);
+    k_big_forward<NT><<<nc, NT, smem, st>>>(units, states, unit_list, n_list, s_rt, work_counter);
+    ls->end(st);
+    return cudaGetLastError();
+}
+// slab count of a big box for the compress side (0: the tiled generic transform takes it)
+int big_forward_slabs(int nx, int ny, int nz, int dtype, const void* ptr) {
+    if (reinterpret_cast<uintptr_t>(ptr) & 15u) return 0;
+    FGeom g;
+    const int S = big_slabs(nx, ny, nz);
+    return (S && fused_geom(nx, ny, nz, dtype, S, 32768, g, F_MAXSEG_BIG)) ? S : 0;
+}
+
 // =====================================================================================================
 // Fused decompress: rle_decode (src/decompressor.cpp:14-30) + inverse_wavelet_decompose (:79-159)
 // =====================================================================================================

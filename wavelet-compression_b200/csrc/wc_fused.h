@@ -41,6 +41,12 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
 // stage (32^3 cubes): 0 = pairs straight from global memory, 1 = table-less units decode from a shared-memory staging
 // area filled by TMA bulk copies one item ahead (k_staged_decompress), 2 = units with a segment table as well
 
+// Big boxes (no cluster holds them): y-slab forward transform into the unit's coefficient scratch + arg-max key;
+// threshold and packing then run on the scratch like for every generic unit.  One launch per slab count.
+int big_forward_slabs(int nx, int ny, int nz, int dtype, const void* in_device_ptr);
+cudaError_t launch_big_forward(const UnitDev* units, UnitState* states, const int* unit_list, int n_list, int s_rt,
+                               int* work_counter, int sm_count, cudaStream_t st, LaunchStats* ls);
+
 // Streamed segment index for packed streams without tables (see k_seg_index3), and the device-side preparation
 // of a dense stream (k_dec_prepare).
 int fused_decode_slabs(int fused_cls);
