@@ -169,6 +169,8 @@ struct wc_plan {
     std::vector<int>         fl[FL_N], generic;
     std::vector<int>         bigfwd;     // generic units whose forward transform runs by y-slabs (k_big_forward), sorted by slab count
     DevBuf                   d_bigfwd;
+    int                      n_pk_items = 0;   // (unit, chunk) items of the one-pass packing kernel, every generic unit
+    DevBuf                   d_pk_items, d_pk_status;
     std::vector<char>        has_segtab;                     // per unit: UnitDev::coef is a segment table
     long long total_n = 0;     // sum of ncoef
     size_t    in_bytes = 0;    // sum of input bytes
@@ -503,7 +505,7 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
     // classify + lay out
     size_t slot_pairs = 0, coef_floats = 0, in_off = 0;
     std::vector<size_t> slot_off(n_units), coef_off(n_units);
-    std::vector<int2> xtiles, ctiles;
+    std::vector<int2> xtiles, ctiles, pk_items;
     for (int i = 0; i < n_units; ++i) {
         const wc_box_desc& b = units[i];
         long long n = (long long)b.nx * b.ny * b.nz;
@@ -552,8 +554,10 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
             u.ctile0  = (int32_t)ctiles.size();
             u.nctiles = ctile_count(n);
             for (int t = 0; t < u.nctiles; ++t) ctiles.push_back(make_int2(i, t));
+            for (int c = 0, nc = big_pack_chunks(n); c < nc; ++c) pk_items.push_back(make_int2(i, c));
         }
     }
+    p->n_pk_items = (int)pk_items.size();
     p->n_xtiles = (int)xtiles.size();
     p->n_ctiles = (int)ctiles.size();
 
@@ -606,6 +610,13 @@ int wc_plan_create(wc_ctx* ctx, const wc_box_desc* units, int n_units, int in_sp
                                  cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
             return fail(e, "fused list upload");
     }
+    if (p->n_pk_items) {
+        PLAN_RESERVE(p->d_pk_items, sizeof(int2) * (size_t)p->n_pk_items);
+        PLAN_RESERVE(p->d_pk_status, sizeof(u64) * (size_t)p->n_pk_items);
+        if ((e = cudaMemcpyAsync(p->d_pk_items.p, pk_items.data(), sizeof(int2) * (size_t)p->n_pk_items, cudaMemcpyHostToDevice,
+                                 ctx->stream)) != cudaSuccess)
+            return fail(e, "pack item upload");
+    }
     if (!p->bigfwd.empty()) {
         sort_big_list(p->bigfwd, [&](int i, int& nx, int& ny, int& nz) { nx = p->h_units[i].nx; ny = p->h_units[i].ny; nz = p->h_units[i].nz; });
         PLAN_RESERVE(p->d_bigfwd, sizeof(int) * p->bigfwd.size());
@@ -631,6 +642,8 @@ int wc_plan_destroy(wc_plan* p) {
     for (DevBuf* b : bufs) b->release();
     for (int k = 0; k < FL_N; ++k) p->d_fl[k].release();
     p->d_bigfwd.release();
+    p->d_pk_items.release();
+    p->d_pk_status.release();
     p->d_running.release();
     p->d_counter.release();
     p->d_rmse_tiles.release();
@@ -774,12 +787,21 @@ static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
                                              global_key_dev, ctx->stream, &ctx->ls));
     }
     if (!p->generic.empty()) {
-        int* ti = p->d_tile_i.as<int>();
-        size_t nt = (size_t)p->n_ctiles;
-        CTX_CUDA(ctx, launch_pack_generic(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
-                                          p->n_units, p->d_ctiles.as<int2>(), p->n_ctiles, ti,
-                                          ti + nt, ti + 2 * nt, ti + 3 * nt, ctx->stream,
-                                          &ctx->ls));
+        if (ctx->opt_path == 1 && ctx->opt_seg_index == 1) {
+            // the three-kernel packing (count, scan, emit), kept selectable for comparison
+            int* ti = p->d_tile_i.as<int>();
+            size_t nt = (size_t)p->n_ctiles;
+            CTX_CUDA(ctx, launch_pack_generic(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(),
+                                              p->n_units, p->d_ctiles.as<int2>(), p->n_ctiles, ti,
+                                              ti + nt, ti + 2 * nt, ti + 3 * nt, ctx->stream,
+                                              &ctx->ls));
+        } else {
+            int* counter = nullptr;
+            int rc = plan_counter(p, ctx->stream, &counter);
+            if (rc != WC_OK) return rc;
+            CTX_CUDA(ctx, launch_big_pack(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(), p->d_pk_items.as<int2>(),
+                                          p->n_pk_items, p->d_pk_status.as<u64>(), counter, ctx->sm_count, ctx->stream, &ctx->ls));
+        }
     }
     int mode = global_key_dev ? FUSED_GIVEN_THRESH : (FUSED_FULL | (ctx->opt_ingest_stats ? FUSED_MINMAX : 0));
     // The cluster kernel cannot use every SM (clusters of 8 must fit inside a GPC: 15 clusters = 120 of 148

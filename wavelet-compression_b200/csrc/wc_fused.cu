@@ -1143,6 +1143,309 @@ cudaError_t launch_big_forward(const UnitDev* units, UnitState* states, const in
     ls->end(st);
     return cudaGetLastError();
 }
+// ---- ordered packing from a flat coefficient array (second pass of the big-box / generic units) ------------------
+// One pass over the unit's coefficient scratch instead of count + scan + emit (which read it twice and, at 0.8 SM
+// cycles per coefficient, ran at a quarter of the fused kernels' packing rate).  An item is a chunk of PK_ELEMS
+// consecutive coefficients of one unit: a single TMA bulk copy brings it into shared memory, phases C1 / C2 of the
+// fused kernels count and emit it segment by segment (512 coefficients, a warp at a time), and the chunk's position in
+// the unit's pair list — pairs kept before it, flat index of the last one — comes from its predecessors through a
+// status word per item (single-pass "decoupled look-back": items are handed out in order, so a predecessor is always
+// running or done).  status = flag << 62 | count << 31 | (last kept flat index + 1); flag 1: this chunk alone,
+// 2: inclusive prefix of the unit up to and including this chunk; zeroed before the launch.  Flag and payload share the
+// word, so relaxed 8-byte accesses are enough: with release / acquire the fence in front of every status store waited
+// for the warp's own pair stores of the previous item to drain (33 k cycles per item, measured).
+constexpr int PK_NT = 256, PK_ELEMS = 8192, PK_SEG = 512;
+constexpr int PK_SMEM = 2 * PK_ELEMS * 4 + 1024;
+__device__ __forceinline__ u64 pk_pack(u64 flag, uint32_t cnt, int last) {
+    return (flag << 62) | ((u64)cnt << 31) | (u64)(uint32_t)(last + 1);
+}
+struct PkDesc {          // one item, fetched by thread 0 while the previous item is emitted
+    const float* coef;   // the chunk's first coefficient
+    int2*        out;
+    int          item, uid, chunk, f0, ne, n;
+    float        tf;
+    int          c_f0, c_ne;   // the chunk counted ahead by this ticket
+    float        c_tf;
+    const float* c_coef;
+};
+// Two chunk buffers: while an item is emitted, thread 0 takes the next ticket, reads its descriptors and starts its
+// bulk copy into the other buffer.  The ticket is taken as late as that (not an item ahead): a chunk that is taken but
+// not yet counted holds up every later chunk of its unit in the look-back.
+__global__ void __launch_bounds__(PK_NT, 3)
+k_big_pack(const UnitDev* __restrict__ units, UnitState* __restrict__ states, const int2* __restrict__ items, int n_items,
+           u64* __restrict__ status, int* __restrict__ work_counter, int ahead) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char*  tail    = smem + 2 * PK_ELEMS * 4;
+    uint32_t* const s_pk    = reinterpret_cast<uint32_t*>(tail);             // [32] cnt << 16 | last (0xffff: none)
+    int* const      s_base  = reinterpret_cast<int*>(tail + 128);            // [32] pairs of the chunk before the segment
+    int* const      s_prev  = reinterpret_cast<int*>(tail + 256);            // [32] last kept local index before it, -1
+    int* const      s_lb    = reinterpret_cast<int*>(tail + 384);            // base count, base last
+    int* const      s_next  = reinterpret_cast<int*>(tail + 392);
+    int* const      s_ca    = reinterpret_cast<int*>(tail + 640);            // [2][8] count-ahead partials
+    PkDesc* const   s_desc  = reinterpret_cast<PkDesc*>(tail + 448);         // [2] x 64 bytes
+    const uint32_t  bars    = smem_u32(tail + 576);                          // [2]
+    static_assert(sizeof(PkDesc) == 64, "PkDesc layout");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const u64 pol = l2_policy_evict_first();
+    u64 pol_last;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    auto fetch = [&](int slot) {                                             // thread 0
+        PkDesc& d = s_desc[slot];
+        const int item = atomicAdd(work_counter, 1);
+        d.item = item;
+        if (item >= n_items) return;
+        const int2 it = __ldg(items + item);
+        const UnitDev u = units[it.x];
+        d.uid = it.x; d.chunk = it.y; d.n = u.n;
+        d.f0 = it.y * PK_ELEMS;
+        d.ne = min(PK_ELEMS, u.n - d.f0);                                    // coefficients of this chunk (> 0)
+        d.coef = u.coef + d.f0;
+        d.out = reinterpret_cast<int2*>(u.out);
+        d.tf = states[it.x].thresh_f;
+        // the chunk this CTA counts ahead of time (see "count ahead" below)
+        d.c_ne = 0;
+        if (item + ahead < n_items) {
+            const int2 ic = __ldg(items + item + ahead);
+            const UnitDev uc = units[ic.x];
+            d.c_f0 = ic.y * PK_ELEMS;
+            d.c_ne = min(PK_ELEMS, uc.n - d.c_f0);
+            d.c_coef = uc.coef + d.c_f0;
+            d.c_tf = states[ic.x].thresh_f;
+        }
+        // the scratch of a unit is padded to a multiple of 4 floats, and f0 * 4 is a multiple of 16
+        const uint32_t bytes = (uint32_t)((d.ne + 3) & ~3) * 4u, bar = bars + 8 * slot;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(smem_u32(smem + slot * PK_ELEMS * 4)), "l"(d.coef), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+    };
+    if (tid == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fetch(0);
+    }
+    __syncthreads();
+    for (int k = 0;; ++k) {
+        const int slot = k & 1;
+        const PkDesc d = s_desc[slot];
+        if (d.item >= n_items) break;
+        WC_PHASE_CLOCK(t0);
+        float* const C = reinterpret_cast<float*>(smem + slot * PK_ELEMS * 4);
+        const float tf = d.tf;
+        const int f0 = d.f0, ne = d.ne, item = d.item, chunk = d.chunk;
+        const int nseg = (ne + PK_SEG - 1) / PK_SEG;
+        if (tid == 0) *s_next = 0;
+        // ---- count ahead: the aggregate (kept count, last kept index) of the chunk `ahead` tickets further on, straight
+        // from global memory (its lines stay in L2 for the bulk copy that emits it).  `ahead` exceeds the number of
+        // chunks in flight, so by the time a chunk is emitted the aggregates of all its predecessors have long been
+        // published and the look-back below never waits — without this every chunk waited for the slowest of its ~30
+        // nearest predecessors to load and count (10 k cycles per item, a convoy).  The loads are issued here and
+        // consumed after C1, which covers their latency.
+        constexpr int CA = PK_ELEMS / 4 / PK_NT;
+        float4 ca[CA];
+        const int c_n4 = (d.c_ne + 3) >> 2;
+        if (d.c_ne > 0) {
+            const float4* src = reinterpret_cast<const float4*>(d.c_coef);
+#pragma unroll
+            for (int r = 0; r < CA; ++r) {
+                const int i4 = tid + r * PK_NT;
+                ca[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i4 < c_n4)
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                                 : "=f"(ca[r].x), "=f"(ca[r].y), "=f"(ca[r].z), "=f"(ca[r].w) : "l"(src + i4), "l"(pol_last));
+            }
+        }
+        mbar_wait_cta(bars + 8 * slot, (uint32_t)(k >> 1) & 1u);
+        WC_PHASE_CLOCK(t1);
+        // a ragged last segment: NaN is never kept (|NaN| > tf is false for every tf)
+        for (int i = tid; i < nseg * PK_SEG - ne; i += PK_NT) C[ne + i] = __int_as_float(0x7fc00000);
+        __syncthreads();
+
+        // ---- C1: kept count and last kept index of every segment (fused kernels, phase C1)
+        for (int sg = warp; sg < nseg; sg += PK_NT / 32) {
+            const float4* cs = reinterpret_cast<const float4*>(C + sg * PK_SEG);
+            uint32_t m = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 c = cs[lane + 32 * r];
+                m |= ((keep_coef(c.x, tf) ? 1u : 0u) | (keep_coef(c.y, tf) ? 2u : 0u) |
+                      (keep_coef(c.z, tf) ? 4u : 0u) | (keep_coef(c.w, tf) ? 8u : 0u)) << (4 * r);
+            }
+            int cnt = __popc(m), last = -1;
+            if (m) {
+                const int hb = (int)bfind_u32(m);               // bit 4 * r + j -> w = 128 * r + 4 * lane + j
+                last = 128 * (hb >> 2) + 4 * lane + (hb & 3);
+            }
+            cnt  = __reduce_add_sync(0xffffffffu, cnt);
+            last = __reduce_max_sync(0xffffffffu, last);
+            if (lane == 0) s_pk[sg] = ((uint32_t)cnt << 16) | ((uint32_t)last & 0xffffu);
+        }
+        if (d.c_ne > 0) {                                        // count ahead, second half
+            const float ctf = d.c_tf;
+            int cnt = 0, last = -1;
+#pragma unroll
+            for (int r = 0; r < CA; ++r) {
+                const int e = 4 * (tid + r * PK_NT);
+                const float4 c = ca[r];
+                const uint32_t m = ((e     < d.c_ne && keep_coef(c.x, ctf)) ? 1u : 0u) | ((e + 1 < d.c_ne && keep_coef(c.y, ctf)) ? 2u : 0u) |
+                                   ((e + 2 < d.c_ne && keep_coef(c.z, ctf)) ? 4u : 0u) | ((e + 3 < d.c_ne && keep_coef(c.w, ctf)) ? 8u : 0u);
+                cnt += __popc(m);
+                if (m) last = e + (int)bfind_u32(m);
+            }
+            cnt  = __reduce_add_sync(0xffffffffu, cnt);
+            last = __reduce_max_sync(0xffffffffu, last);
+            if (lane == 0) { s_ca[warp] = cnt; s_ca[8 + warp] = last; }
+        }
+        __syncthreads();
+        WC_PHASE_CLOCK(t2);
+        if (tid == 0 && d.c_ne > 0) {
+            int tc = 0, tl = -1;
+#pragma unroll
+            for (int w = 0; w < PK_NT / 32; ++w) { tc += s_ca[w]; tl = max(tl, s_ca[8 + w]); }
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(status + item + ahead),
+                         "l"(pk_pack(1, (uint32_t)tc, tl >= 0 ? d.c_f0 + tl : -1)) : "memory");
+        }
+
+        // ---- scan of the (at most 16) segments + look-back over the unit's earlier chunks, all in warp 0
+        if (warp == 0) {
+            const uint32_t pk = lane < nseg ? s_pk[lane] : 0xffffu;
+            const int cnt = (int)(pk >> 16);
+            const int lastl = (pk & 0xffffu) != 0xffffu ? lane * PK_SEG + (int)(pk & 0xffffu) : -1;
+            int isum = cnt, imax = lastl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ps = __shfl_up_sync(0xffffffffu, isum, o), pm = __shfl_up_sync(0xffffffffu, imax, o);
+                if (lane >= o) { isum += ps; imax = max(imax, pm); }
+            }
+            const int total = __shfl_sync(0xffffffffu, isum, 31), lastc = __shfl_sync(0xffffffffu, imax, 31);
+            int em = __shfl_up_sync(0xffffffffu, imax, 1);
+            if (lane == 0) em = -1;
+            s_base[lane] = isum - cnt;
+            s_prev[lane] = em;
+            const int lastg = lastc >= 0 ? f0 + lastc : -1;       // flat index of the chunk's last kept coefficient
+            uint32_t bcnt = 0;
+            int blast = -1;
+            if (chunk > 0) {
+                if (lane == 0 && item < ahead)       // later chunks were counted ahead of time
+                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(status + item), "l"(pk_pack(1, (uint32_t)total, lastg)) : "memory");
+                int hi = item - 1;
+                for (;;) {
+                    const int j = hi - lane;                    // lane 0 = nearest predecessor
+                    u64 v = 2ull << 62;                         // in front of the unit's first chunk: nothing kept
+                    if (j >= item - chunk)
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(status + j) : "memory");
+                    // only the words between this chunk and the nearest inclusive prefix have to be there
+                    const uint32_t incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                    const uint32_t none = __ballot_sync(0xffffffffu, (v >> 62) == 0);
+                    const int first = incl ? __ffs(incl) - 1 : 31;
+                    if (none & (0xffffffffu >> (31 - first))) continue;      // poll again
+                    const bool use = lane <= first;
+                    const uint32_t c31 = use ? (uint32_t)((v >> 31) & 0x7fffffffu) : 0u;
+                    bcnt += __reduce_add_sync(0xffffffffu, c31);
+                    const uint32_t l31 = use ? (uint32_t)(v & 0x7fffffffu) : 0u;
+                    const uint32_t has = __ballot_sync(0xffffffffu, l31 != 0u);
+                    if (blast < 0 && has) blast = (int)__shfl_sync(0xffffffffu, l31, __ffs(has) - 1) - 1;
+                    if (incl) break;
+                    hi -= 32;
+                }
+            }
+            if (lane == 0) {
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(status + item),
+                             "l"(pk_pack(2, bcnt + (uint32_t)total, lastg >= 0 ? lastg : blast)) : "memory");
+                s_lb[0] = (int)bcnt;
+                s_lb[1] = blast;
+                if (f0 + ne >= d.n) {                           // the unit's last chunk: K and need32 (as k_scan_tiles)
+                    const int K = (int)bcnt + total;
+                    states[d.uid].npairs = K;
+                    const UnitState st = states[d.uid];
+                    if (K > 0 && unit_need32(fabsf(key_value(st.key)), st.thresh_f)) states[d.uid].flags = st.flags | UNIT_FLAG_NEED32;
+                }
+            }
+        }
+        __syncthreads();
+        WC_PHASE_CLOCK(t3);
+        if (tid == 0) fetch(slot ^ 1);     // the other buffer was emitted before the barrier at the end of the last item
+
+        // ---- C2: emit (run, value) pairs, segments handed out dynamically (fused kernels, phase C2)
+        const uint32_t bcnt = (uint32_t)s_lb[0];
+        const int blast = s_lb[1];
+        int2* const out = d.out;
+        for (;;) {
+            int sg = 0;
+            if (lane == 0) sg = atomicAdd(s_next, 1);
+            sg = __shfl_sync(0xffffffffu, sg, 0);
+            if (sg >= nseg) break;
+            const int scnt = (int)(s_pk[sg] >> 16);
+            if (scnt == 0) continue;
+            const float* cs = C + sg * PK_SEG;
+            const int fstart = f0 + sg * PK_SEG;
+            uint32_t pos = bcnt + (uint32_t)s_base[sg];
+            int prev = s_prev[sg] >= 0 ? f0 + s_prev[sg] : blast;
+            if (scnt == PK_SEG) {
+                for (int w = lane; w < PK_SEG; w += 32)
+                    st_pair_pred(true, out + (pos + (uint32_t)w), w == 0 ? fstart - prev - 1 : 0, cs[w], pol);
+                continue;
+            }
+#pragma unroll 1
+            for (int w0 = 0; w0 < PK_SEG; w0 += 128) {
+                float    c[4];
+                uint32_t bal[4];
+                bool     kf[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    c[j]   = cs[w0 + 32 * j + lane];
+                    kf[j]  = keep_coef(c[j], tf);
+                    bal[j] = __ballot_sync(0xffffffffu, kf[j]);
+                }
+                int prel = prev - (fstart + w0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (bal[j] != 0u) {
+                        const uint32_t lower = bal[j] & lt;
+                        const int pl = lower ? bfind_alu(lower) : prel;
+                        st_pair_pred(kf[j], out + (pos + __popc(lower)), lane - pl - 1, c[j], pol);
+                        pos += __popc(bal[j]);
+                        prel = bfind_alu(bal[j]);
+                    }
+                    prel -= 32;
+                }
+                prev = prel + fstart + w0 + 128;
+            }
+        }
+        __syncthreads();       // this buffer, the segment arrays, s_next and the next descriptor change hands
+#ifdef WC_PHASE_PROFILE
+        if (tid == 0 && blockIdx.x < 1024) {   // 0 load, 1 C1, 2 scan + look-back, 3 C2
+            long long t4 = clock64();
+            unsigned long long* pc = g_phase_cycles[blockIdx.x];
+            pc[0] += t1 - t0; pc[1] += t2 - t1; pc[2] += t3 - t2; pc[3] += t4 - t3; pc[5] += 1;
+        }
+#endif
+    }
+}
+
+cudaError_t launch_big_pack(const UnitDev* units, UnitState* states, const int2* items, int n_items, u64* status,
+                            int* work_counter, int sm_count, cudaStream_t st, LaunchStats* ls) {
+    if (n_items <= 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_big_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM);
+    if (e != cudaSuccess) return e;
+    int& per_sm = ls->occ[KID_BIG_PACK];
+    if (per_sm == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_big_pack, PK_NT, PK_SMEM);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    }
+    e = cudaMemsetAsync(status, 0, sizeof(u64) * (size_t)n_items, st);
+    if (e != cudaSuccess) return e;
+    const long long slots = (long long)per_sm * sm_count;
+    const int nc = (int)(n_items < slots ? n_items : slots);
+    ls->begin(KID_BIG_PACK, st);
+    k_big_pack<<<nc, PK_NT, PK_SMEM, st>>>(units, states, items, n_items, status, work_counter, 2 * nc);
+    ls->end(st);
+    return cudaGetLastError();
+}
+int big_pack_chunks(long long n) { return (int)((n + PK_ELEMS - 1) / PK_ELEMS); }
+
 // slab count of a big box for the compress side (0: the tiled generic transform takes it)
 int big_forward_slabs(int nx, int ny, int nz, int dtype, const void* ptr) {
     if (reinterpret_cast<uintptr_t>(ptr) & 15u) return 0;

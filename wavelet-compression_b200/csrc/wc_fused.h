@@ -47,6 +47,13 @@ int big_forward_slabs(int nx, int ny, int nz, int dtype, const void* in_device_p
 cudaError_t launch_big_forward(const UnitDev* units, UnitState* states, const int* unit_list, int n_list, int s_rt,
                                int* work_counter, int sm_count, cudaStream_t st, LaunchStats* ls);
 
+// Ordered packing of generic / big-box units from their coefficient scratch in ONE pass (k_big_pack: TMA bulk loads,
+// chunk position by decoupled look-back).  items[i] = (unit, chunk) for every chunk of big_pack_chunks(n) per unit, unit
+// after unit; status: one word per item (zeroed by the launcher).
+int big_pack_chunks(long long ncoef);
+cudaError_t launch_big_pack(const UnitDev* units, UnitState* states, const int2* items, int n_items, u64* status,
+                            int* work_counter, int sm_count, cudaStream_t st, LaunchStats* ls);
+
 // Streamed segment index for packed streams without tables (see k_seg_index3), and the device-side preparation
 // of a dense stream (k_dec_prepare).
 int fused_decode_slabs(int fused_cls);
