@@ -1087,6 +1087,16 @@ k_big_forward(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
         const int uid = __ldg(unit_list + item / s_rt);
         const uint32_t rank = (uint32_t)(item % s_rt);
         const UnitDev u = units[uid];
+        // Items are handed out in order, so the item gridDim.x further on starts when this one ends, on this CTA or on a
+        // neighbour: its input slab goes into L2 while this item's coefficients are written out (L2 is shared, so it does
+        // not matter who gets it).  The descriptor loads are issued here and consumed after phase A.
+        const int ahead = item + (int)gridDim.x;
+        const void* pf_in = nullptr;
+        int pf_nx = 0, pf_ny = 0, pf_nz = 0, pf_dt = 0;
+        if (ahead < n_items) {
+            const UnitDev* u2 = units + __ldg(unit_list + ahead / s_rt);
+            pf_in = u2->in; pf_nx = u2->nx; pf_ny = u2->ny; pf_nz = u2->nz; pf_dt = u2->dtype;
+        }
         FGeom g;
         fused_geom(u.nx, u.ny, u.nz, u.dtype, s_rt, 32768, g, F_MAXSEG_BIG);
         const int b0 = rank * g.nb;
@@ -1096,6 +1106,17 @@ k_big_forward(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
             const char* in0 = static_cast<const char*>(u.in) + (size_t)(2 * b0) * ((size_t)g.X * g.es);
             if (g.es == 8) phase_a<NT, 8, false>(g, in0, C, rank, pol, bp, bn, nan0, vmn, vmx);
             else           phase_a<NT, 4, false>(g, in0, C, rank, pol, bp, bn, nan0, vmn, vmx);
+        }
+        if (pf_in) {
+            const size_t row = (size_t)pf_nx * (pf_dt == WC_F64 ? 8 : 4);
+            const int nb2 = (pf_ny / 2) / s_rt;
+            const size_t piece = 2 * (size_t)nb2 * row;                       // one z-plane's share of the slab
+            const int lpp = (int)((piece + 127) >> 7);
+            const char* base = static_cast<const char*>(pf_in) + (size_t)(2 * (ahead % s_rt) * nb2) * row;
+            for (int i = tid; i < lpp * pf_nz; i += NT) {
+                const int z = i / lpp, l = i - z * lpp;
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)z * row * pf_ny + (size_t)l * 128));
+            }
         }
         __syncthreads();
         // C -> scratch, segment by segment (a warp per segment at a time), and the arg-max key of the slab: largest
