@@ -315,3 +315,40 @@ def test_decode_kernels_many_units_all_densities(wc, ctx, oracle, pipe):
     for i in list(range(0, len(dims), 9)) + list(range(690, len(dims))):
         ob = oracle.decompress_unit(packed[i].runs, packed[i].vals, dims[i])
         assert same_bits(outs[i], ob), (i, dims[i], packed[i].npairs)
+
+
+@pytest.mark.parametrize("pipe", [2, 0])
+def test_all_kept_lists_with_and_without_a_stray_run(wc, ctx, oracle, pipe):
+    """K == ncoef: the staged kernel copies such lists without a scan when every run is 0 (negative max, SURVEY D3');
+    a single non-zero (or negative) run must send the unit through the general decode — pairs shifted, the tail dropped
+    (src/decompressor.cpp:24-27) — and a negative run is WC_ERR_CORRUPT."""
+    rng = np.random.default_rng(77)
+    d = (32, 32, 32)
+    n = 32768
+    packed = []
+    for i in range(6):
+        runs = np.zeros(n, np.int32)
+        if i == 1: runs[20000] = 3
+        if i == 2: runs[0] = 1
+        if i == 3: runs[n - 1] = 5
+        if i == 4: runs[12286] = 7           # first pair past the staging area
+        packed.append(wc.PackedUnit(d, n, runs, rng.standard_normal(n).astype(np.float32)))
+    pr, k = dense_stream(wc, packed)
+    outs = [np.full((32, 32, 32), 7.0, np.float32) for _ in packed]
+    od = wc.capi.box_descs([o.ctypes.data for o in outs], [wc.WC_F32] * len(outs), [d] * len(outs))
+    ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, pipe)
+    try:
+        dp = ctx.decode_plan(od, wc.WC_HOST)
+        for _ in range(2):
+            dp.decode(pr.ctypes.data, k.ctypes.data, wc.WC_HOST)
+            dp.finish()
+        for p, o in zip(packed, outs):
+            assert same_bits(o, oracle.decompress_unit(p.runs, p.vals, d))
+        pr["run"][5 * n + 100] = -2
+        dp.decode(pr.ctypes.data, k.ctypes.data, wc.WC_HOST)
+        with pytest.raises(wc.WcError) as e:
+            dp.finish()
+        assert e.value.status == 7
+        dp.close()
+    finally:
+        ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, 2)

@@ -198,8 +198,9 @@ struct wc_plan {
     // wc_plan_set_inputs: ring of pinned pointer tables (host) + one device table, patched by k_patch_inputs
     enum { IN_RING = 4 };
     PinBuf      h_inptr[IN_RING];
-    cudaEvent_t ev_inptr[IN_RING] = {};
-    DevBuf      d_inptr;
+    cudaEvent_t ev_inptr[IN_RING] = {}, ev_patch[IN_RING] = {};
+    DevBuf      d_inptr[IN_RING];
+    cudaStream_t s_inptr = nullptr;      // side stream of the pointer-table copies
     unsigned    inptr_next = 0;
 };
 
@@ -648,9 +649,11 @@ int wc_plan_destroy(wc_plan* p) {
     p->d_counter.release();
     p->d_rmse_tiles.release();
     p->d_dec_list.release();
-    p->d_inptr.release();
+    if (p->s_inptr) { cudaStreamSynchronize(p->s_inptr); cudaStreamDestroy(p->s_inptr); }
     for (int i = 0; i < wc_plan::IN_RING; ++i) {
         p->h_inptr[i].release();
+        p->d_inptr[i].release();
+        if (p->ev_patch[i]) cudaEventDestroy(p->ev_patch[i]);
         if (p->ev_inptr[i]) cudaEventDestroy(p->ev_inptr[i]);
     }
     delete p->dec_cache;
@@ -691,22 +694,32 @@ int wc_plan_set_inputs(wc_plan* p, const wc_box_desc* units) {
     }
     if (p->in_space == WC_DEVICE && p->n_units > 0) {
         // Stream-ordered and without a host synchronisation: the new addresses go through a ring of pinned
-        // tables (one H2D of 8 bytes per unit) and a kernel patches UnitDev::in, so a timestep series can call
-        // this between two wc_plan_compress without draining the GPU.  A ring slot is reused only after the
-        // copy that read it has completed (event).
+        // tables and device tables (one H2D of 8 bytes per unit, on a side stream so that it overlaps whatever the
+        // ctx stream is still doing — in-stream it cost ~30 us per step, ~80 us with eight ranks sharing the host) and
+        // a kernel on the ctx stream patches UnitDev::in, so a timestep series can call this between two
+        // wc_plan_compress without draining the GPU.  A pinned slot is reused only after the copy that read it has
+        // completed, a device slot only after the patch kernel that read it (events).
         const int slot = (int)(p->inptr_next++ % wc_plan::IN_RING);
         const size_t bytes = sizeof(void*) * (size_t)p->n_units;
         CTX_CUDA(ctx, p->h_inptr[slot].reserve(bytes));
-        CTX_CUDA(ctx, p->d_inptr.reserve(bytes));
-        if (!p->ev_inptr[slot]) CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_inptr[slot], cudaEventDisableTiming));
-        else CTX_CUDA(ctx, cudaEventSynchronize(p->ev_inptr[slot]));
+        CTX_CUDA(ctx, p->d_inptr[slot].reserve(bytes));
+        if (!p->s_inptr) CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p->s_inptr, cudaStreamNonBlocking));
+        if (!p->ev_inptr[slot]) {
+            CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_inptr[slot], cudaEventDisableTiming));
+            CTX_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_patch[slot], cudaEventDisableTiming));
+        } else {
+            CTX_CUDA(ctx, cudaEventSynchronize(p->ev_inptr[slot]));
+            CTX_CUDA(ctx, cudaStreamWaitEvent(p->s_inptr, p->ev_patch[slot], 0));
+        }
         const void** hp = p->h_inptr[slot].as<const void*>();
         for (int i = 0; i < p->n_units; ++i) hp[i] = units[i].data;
-        CTX_CUDA(ctx, cudaMemcpyAsync(p->d_inptr.p, hp, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        CTX_CUDA(ctx, cudaEventRecord(p->ev_inptr[slot], ctx->stream));
+        CTX_CUDA(ctx, cudaMemcpyAsync(p->d_inptr[slot].p, hp, bytes, cudaMemcpyHostToDevice, p->s_inptr));
+        CTX_CUDA(ctx, cudaEventRecord(p->ev_inptr[slot], p->s_inptr));
         ctx->h2d += bytes;
-        CTX_CUDA(ctx, launch_patch_inputs(p->d_units.as<UnitDev>(), p->d_inptr.as<const void*>(), p->n_units,
+        CTX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->ev_inptr[slot], 0));
+        CTX_CUDA(ctx, launch_patch_inputs(p->d_units.as<UnitDev>(), p->d_inptr[slot].as<const void*>(), p->n_units,
                                           ctx->stream, &ctx->ls));
+        CTX_CUDA(ctx, cudaEventRecord(p->ev_patch[slot], ctx->stream));
     }
     return WC_OK;
 }
