@@ -485,9 +485,12 @@ def main():
                   "stream_decompress_bit_exact": bool(ok_stream), "rmse_max_rel_err": worst,
                   "rmse_tolerance": 1e-12, "mean_rmse_per_component": [float(np.mean(rm[c::N_COMP])) for c in range(N_COMP)]}
     if world > 1:
-        gt_ok = global_threshold_parity(pkg, ctx, stream, device, rank, world)
+        gt_ok, gq_ok = global_threshold_parity(pkg, ctx, stream, device, rank, world)
         if rank == 0:
             parity["global_threshold_ok"] = gt_ok
+            parity["global_quantile_ok"] = gq_ok
+            parity["global_quantile_note"] = ("quantile extension: radix-select histograms of the sharded batch summed over "
+                                              "NCCL, every rank's pairs == oracle threshold_pack at the numpy quantile")
             parity["global_threshold_note"] = ("config-5 extension: one threshold for a seeded batch sharded over the ranks, "
                                                "NCCL MAX all-reduce of the arg-max key, every rank's pairs == oracle "
                                                "threshold_pack with the oracle's concatenation-rule threshold")
@@ -713,14 +716,27 @@ def global_threshold_parity(pkg, ctx, stream, device, rank, world):
         pkg.distributed.compress_global_threshold(plan, keep, lo, device)
         got = plan.fetch_host()
         plan.close()
+        # the quantile extension: radix-select histograms summed over NCCL (plan with a scratch for every unit)
+        ctx.set_path(1)
+        plan = ctx.plan(descs, pkg.WC_DEVICE)
+        pkg.distributed.compress_global_quantile(plan, keep, sum(b.size for b in boxes[lo:hi]), device)
+        got_q = plan.fetch_host()
+        plan.close()
+        ctx.set_path(0)
     flats = [orc.haar_forward(orc.narrow(b), d) for b, d in zip(boxes, dims)]
     tg = orc.select_threshold_global(flats, keep)
     for i, p in enumerate(got):
         rg, vg = orc.threshold_pack(flats[lo + i], tg)
         ok &= p.runs.tobytes() == rg.tobytes() and p.vals.tobytes() == vg.tobytes()
-    flag = torch.tensor([1 if ok else 0], device=device)
+    from oracle.pyoracle import quantile_threshold
+    tq = quantile_threshold(flats, keep)
+    okq = True
+    for i, p in enumerate(got_q):
+        rq, vq = orc.threshold_pack(flats[lo + i], tq)
+        okq &= p.runs.tobytes() == rq.tobytes() and p.vals.tobytes() == vq.tobytes()
+    flag = torch.tensor([1 if ok else 0, 1 if okq else 0], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    return bool(flag.item())
+    return bool(flag[0].item()), bool(flag[1].item())
 
 
 def _run():

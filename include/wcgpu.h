@@ -62,8 +62,14 @@ typedef enum { WC_HOST = 0, WC_DEVICE = 1 } wc_space;
 /* How the threshold of src/compressor.cpp:212-216 is scoped. */
 typedef enum {
     WC_THRESH_PER_UNIT = 0, /* the reference: one threshold per (box, component)                    */
-    WC_THRESH_GLOBAL   = 1  /* EXTENSION: one threshold for the whole batch, same max-rule applied to
+    WC_THRESH_GLOBAL   = 1, /* EXTENSION: one threshold for the whole batch, same max-rule applied to
                                the concatenation of the units in batch order (BASELINE config 5)   */
+    WC_THRESH_QUANTILE = 2, /* EXTENSION (no counterpart in the reference, whose threshold is max * (1 - keep)): keep the
+                               Kt = n - floor(keep * n) coefficients of largest magnitude of every unit — threshold = the
+                               magnitude of rank Kt (descending, NaNs last), mask |c| > threshold, ties at the threshold
+                               dropped.  Radix select over the unit's coefficients; needs a plan created under
+                               WC_OPT_PATH = 1 (WC_ERR_STATE otherwise).                                              */
+    WC_THRESH_QUANTILE_GLOBAL = 3 /* the same over the concatenation of all units of the batch */
 } wc_thresh_mode;
 
 typedef struct wc_ctx  wc_ctx;
@@ -258,6 +264,18 @@ WC_API int wc_plan_rmse(wc_plan* plan, const wc_box_desc* recon, double* rmse);
  *   wc_plan_pack_with_key   : threshold from *key_dev (device) + mask + pack                     */
 WC_API int wc_plan_transform(wc_plan* plan, uint64_t** key_dev);
 WC_API int wc_plan_pack_with_key(wc_plan* plan, double keep, const uint64_t* key_dev);
+/* EXTENSION for multi-GPU WC_THRESH_QUANTILE_GLOBAL: the radix select split at its histograms, so that the caller can
+ * all-reduce them (NCCL ncclSum over 2048 uint64) and every rank picks the same bucket — the kept set is then the same
+ * as on one GPU.
+ *   wc_plan_quantile_begin : forward transform into the scratch; n_total = coefficients of ALL ranks (0: this plan's)
+ *   per pass 0, 1, 2       : wc_plan_quantile_hist (-> *hist_dev, device uint64[2048], add the other ranks' in place)
+ *                            then wc_plan_quantile_pick
+ *   wc_plan_quantile_pack  : thresholds -> mask + ordered packing
+ * (global = 0 runs the per-unit mode through the same calls; its histograms are one row per unit.) */
+WC_API int wc_plan_quantile_begin(wc_plan* plan, double keep, int global, uint64_t n_total);
+WC_API int wc_plan_quantile_hist(wc_plan* plan, int pass, uint64_t** hist_dev);
+WC_API int wc_plan_quantile_pick(wc_plan* plan, int pass);
+WC_API int wc_plan_quantile_pack(wc_plan* plan);
 
 /* ---- decode plans: decompress() (src/decompressor.cpp:238-255) for a batch, stream-in ------------------ *
  * A decode plan fixes the output boxes (dims, dtype, addresses) of a batch and owns the device tables; each

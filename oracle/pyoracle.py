@@ -193,6 +193,20 @@ class Oracle:
         return self.lib.wco_select_threshold_global(ptrs, ns, len(flats), float(keep))
 
 
+def quantile_threshold(flats, keep):
+    """EXTENSION oracle (no counterpart in the reference: parity UNPINNED, defined here): the threshold of
+    WC_THRESH_QUANTILE over the concatenation of `flats` (one array: per-unit mode).  n counts every coefficient, NaNs
+    included; Kt = n - floor(keep * n); threshold = the magnitude of rank Kt in descending order (NaNs last), or -1
+    (keep every non-NaN coefficient) when fewer than Kt + 1 coefficients are comparable.  Mask: |c| > threshold."""
+    a = np.abs(np.concatenate([np.asarray(f, np.float32).reshape(-1) for f in flats])) if len(flats) else np.zeros(0, np.float32)
+    n = a.size
+    kt = n - min(int(np.floor(float(keep) * n)), n)
+    valid = a[~np.isnan(a)]
+    if kt >= valid.size:
+        return -1.0
+    return float(np.partition(valid, valid.size - 1 - kt)[valid.size - 1 - kt])
+
+
 class Ref:
     """The reference's own code (oracle/_ref/libwcref.so).  Same conventions as Oracle."""
 

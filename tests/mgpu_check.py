@@ -1,5 +1,6 @@
-"""Launched by torchrun (one rank per GPU): sharded per-unit compression + the NCCL global-threshold
-extension, checked on rank 0 against the oracle over the WHOLE batch.  Exit code 0 = parity."""
+"""Launched by torchrun (one rank per GPU): sharded per-unit compression + the NCCL global-threshold extension (MAX of the
+arg-max key) + the NCCL global-quantile extension (SUM of the radix-select histograms), checked against the oracle over
+the WHOLE batch.  Exit code 0 = parity."""
 import os
 import sys
 
@@ -41,9 +42,22 @@ def main():
         # 2. extension: one threshold for the whole batch (NCCL MAX all-reduce of the arg-max key)
         wc.distributed.compress_global_threshold(plan, keep, lo, dev)
         packed_g = plan.fetch_host()
+        # 3. extension: one QUANTILE threshold for the whole batch (NCCL SUM all-reduce of the radix-select histograms);
+        #    needs a coefficient scratch for every unit, i.e. a plan created under WC_OPT_PATH = 1
+        ctx.set_path(1)
+        plan_q = ctx.plan(descs, wc.WC_DEVICE)
+        wc.distributed.compress_global_quantile(plan_q, keep, sum(sizes[lo:hi]), dev)
+        packed_q = plan_q.fetch_host()
+        plan_q.close()
+        ctx.set_path(0)
     orc = Oracle()
     flats = [orc.haar_forward(orc.narrow(b), d) for b, d in zip(boxes, dims)]
     tg = orc.select_threshold_global(flats, keep)
+    from oracle.pyoracle import quantile_threshold
+    tq = quantile_threshold(flats, keep)
+    for i, pq in enumerate(packed_q):
+        rq, vq = orc.threshold_pack(flats[lo + i], tq)
+        ok &= same_bits(pq.runs, rq) and same_bits(pq.vals, vq)
     for i, (p, pg) in enumerate(zip(packed, packed_g)):
         u = lo + i
         runs, vals, _ = orc.compress_unit(boxes[u], dims[u], keep)

@@ -112,3 +112,59 @@ def test_shard_units_balances_by_size():
         assert all(slices[i][1] == slices[i + 1][0] for i in range(world - 1))
         loads = [sum(sizes[a:b]) for a, b in slices]
         assert max(loads) - min(loads) <= 64 ** 3
+
+
+def _quantile_worker(rank, world, port, q):
+    """Radix select across two ranks with all-reduced histograms (gloo): the host model of k_q_hist / k_q_pick."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        import __graft_entry__ as g
+        pkg = g.package()
+        d = pkg.distributed
+        rng = np.random.default_rng(5)
+        allv = np.concatenate([rng.standard_normal(5000).astype(np.float32) * 10.0 ** rng.integers(-3, 4, 5000),
+                               np.zeros(700, np.float32), np.full(300, 2.5, np.float32), np.full(5, np.nan, np.float32)]).astype(np.float32)
+        rng.shuffle(allv)
+        mine = np.ascontiguousarray(allv[rank::world])
+        keys = mine.view(np.uint32) & np.uint32(0x7fffffff)
+        keys = keys[keys <= np.uint32(0x7f800000)]
+        out = []
+        for keep in (0.0, 0.5, 0.9, 0.999, 1.0):
+            n = torch.tensor([mine.size], dtype=torch.int64)
+            dist.all_reduce(n)
+            ntot = int(n.item())
+            rank_ = ntot - min(int(np.floor(keep * ntot)), ntot)
+            prefix, thresh = 0, None
+            for p, (shift, bits) in enumerate(d.radix_select_passes()):
+                h = torch.from_numpy(d.radix_histogram_host(keys, prefix, p))
+                d.allreduce_histogram(h)
+                b, rank_ = d.radix_pick_host(h.numpy(), rank_)
+                if b is None:
+                    thresh = -1.0
+                    break
+                prefix = (prefix << bits) | b
+            if thresh is None:
+                thresh = float(np.array([prefix], np.uint32).view(np.float32)[0])
+            out.append(thresh)
+        if rank == 0:
+            from oracle.pyoracle import quantile_threshold
+            q.put((out, [quantile_threshold([allv], k) for k in (0.0, 0.5, 0.9, 0.999, 1.0)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_quantile_select_across_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_quantile_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    got, want = q.get(timeout=60)
+    for p in procs: p.join(60)
+    assert got == want, (got, want)

@@ -352,3 +352,56 @@ def test_all_kept_lists_with_and_without_a_stray_run(wc, ctx, oracle, pipe):
         dp.close()
     finally:
         ctx.set_option(wc.capi.WC_OPT_DECODE_PIPE, 2)
+
+
+def test_quantile_thresholds_extension(wc, oracle):
+    """EXTENSION (the north star's radix select; the reference thresholds at max * (1 - keep), so parity is defined by
+    oracle.pyoracle.quantile_threshold): WC_THRESH_QUANTILE keeps the n - floor(keep * n) largest magnitudes of every
+    unit (ties at the threshold dropped), WC_THRESH_QUANTILE_GLOBAL the same over the whole batch; pairs = the oracle's
+    threshold_pack with that threshold.  Needs a plan created under WC_OPT_PATH = 1."""
+    from oracle.pyoracle import quantile_threshold
+    rng = np.random.default_rng(2025)
+    dims = [(32, 32, 32), (64, 64, 64), (16, 16, 16), (5, 7, 3), (40, 40, 42), (8, 8, 8), (4, 2, 2)]
+    boxes = [smooth_box(d, rng, dtype=np.float64 if i % 2 else np.float32, sym=bool(i % 3 == 0), noise=10.0 ** -(i % 3))
+             for i, d in enumerate(dims)]
+    boxes[5][:] = 3.0                                   # constant box: one non-zero coefficient, the rest ties at 0
+    boxes[2].reshape(-1)[7] = np.nan
+    ctx = wc.Context(0)
+    try:
+        plan = ctx.plan_host(boxes, dims)
+        with pytest.raises(wc.WcError) as e:             # fused classes keep no coefficient scratch
+            plan.compress(0.99, wc.WC_THRESH_QUANTILE)
+        assert e.value.status == 8
+        plan.close()
+        ctx.set_path(1)
+        plan = ctx.plan_host(boxes, dims)
+        flats = [oracle.haar_forward(oracle.narrow(b) if b.dtype == np.float64 else b, d) for b, d in zip(boxes, dims)]
+        for keep in (0.999, 0.9, 0.5, 0.0, 1.0):
+            plan.compress(keep, wc.WC_THRESH_QUANTILE)
+            got = plan.fetch_host()
+            for i, (p, f) in enumerate(zip(got, flats)):
+                t = quantile_threshold([f], keep)
+                runs, vals = oracle.threshold_pack(f, t)
+                assert same_bits(p.runs, runs) and same_bits(p.vals, vals), (keep, i, dims[i], t, p.npairs, runs.size)
+                n = f.size
+                assert p.npairs <= n - min(int(np.floor(keep * n)), n)
+            plan.compress(keep, wc.WC_THRESH_QUANTILE_GLOBAL)
+            got = plan.fetch_host()
+            t = quantile_threshold(flats, keep)
+            for i, (p, f) in enumerate(zip(got, flats)):
+                runs, vals = oracle.threshold_pack(f, t)
+                assert same_bits(p.runs, runs) and same_bits(p.vals, vals), ("global", keep, i, dims[i], t)
+        # the split API a multi-GPU caller uses (histograms exposed between hist and pick) gives the same result
+        plan.quantile_begin(0.9, True, 0)
+        for ps in range(3):
+            assert plan.quantile_hist(ps)
+            plan.quantile_pick(ps)
+        plan.quantile_pack()
+        got = plan.fetch_host()
+        t = quantile_threshold(flats, 0.9)
+        for p, f in zip(got, flats):
+            runs, vals = oracle.threshold_pack(f, t)
+            assert same_bits(p.runs, runs) and same_bits(p.vals, vals)
+        plan.close()
+    finally:
+        ctx.close()

@@ -20,6 +20,6 @@ try:  # torch is only needed for the multi-process helpers
 except ImportError:  # pragma: no cover
     distributed = None
 from .capi import (WC_DEVICE, WC_F32, WC_F64, WC_HOST, WC_THRESH_GLOBAL,  # noqa: F401
-                   WC_THRESH_PER_UNIT, WcError)
+                   WC_THRESH_PER_UNIT, WC_THRESH_QUANTILE, WC_THRESH_QUANTILE_GLOBAL, WcError)
 from .core import Context, DecodePlan, PackedUnit, Plan  # noqa: F401
 from .refapi import calc_adj_loss, calc_rmse_per_box, compress, decompress  # noqa: F401

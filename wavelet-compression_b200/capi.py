@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("WCGPU_LIB") or os.path.join(PKG_DIR, "libwcgpu.so")
 WC_OK = 0
 WC_F32, WC_F64 = 0, 1
 WC_HOST, WC_DEVICE = 0, 1
-WC_THRESH_PER_UNIT, WC_THRESH_GLOBAL = 0, 1
+WC_THRESH_PER_UNIT, WC_THRESH_GLOBAL, WC_THRESH_QUANTILE, WC_THRESH_QUANTILE_GLOBAL = 0, 1, 2, 3
 WC_OPT_PATH, WC_OPT_PROFILE, WC_OPT_OVERLAP, WC_OPT_SEG_INDEX, WC_OPT_COPY_ONLY, WC_OPT_INGEST_STATS = 0, 1, 2, 3, 4, 5
 WC_OPT_DECODE_PIPE = 6
 WC_PACKED_NEED32 = 1
@@ -78,6 +78,10 @@ SIGNATURES = {
     "wc_plan_rmse": (_i, [_vp, _vp, _vp]),
     "wc_plan_transform": (_i, [_vp, C.POINTER(_vp)]),
     "wc_plan_pack_with_key": (_i, [_vp, _d, _vp]),
+    "wc_plan_quantile_begin": (_i, [_vp, _d, _i, C.c_uint64]),
+    "wc_plan_quantile_hist": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "wc_plan_quantile_pick": (_i, [_vp, _i]),
+    "wc_plan_quantile_pack": (_i, [_vp]),
 }
 
 

@@ -297,6 +297,23 @@ class Plan:
         check(self.lib.wc_plan_pack_with_key(self.h, float(keep), C.c_void_p(key_dev)),
               "wc_plan_pack_with_key", self.ctx.h)
 
+    # EXTENSION: quantile thresholds (radix select), split at the histograms for multi-GPU runs
+    def quantile_begin(self, keep: float, global_mode: bool, n_total: int = 0):
+        check(self.lib.wc_plan_quantile_begin(self.h, float(keep), int(global_mode), int(n_total)),
+              "wc_plan_quantile_begin", self.ctx.h)
+
+    def quantile_hist(self, pass_: int) -> int:
+        """Histogram of radix-select pass 0, 1 or 2; returns the device address of the uint64[2048] row(s)."""
+        h = C.c_void_p()
+        check(self.lib.wc_plan_quantile_hist(self.h, int(pass_), C.byref(h)), "wc_plan_quantile_hist", self.ctx.h)
+        return h.value
+
+    def quantile_pick(self, pass_: int):
+        check(self.lib.wc_plan_quantile_pick(self.h, int(pass_)), "wc_plan_quantile_pick", self.ctx.h)
+
+    def quantile_pack(self):
+        check(self.lib.wc_plan_quantile_pack(self.h), "wc_plan_quantile_pack", self.ctx.h)
+
     def total_pairs(self) -> int:
         t = C.c_int64(0)
         check(self.lib.wc_plan_total_pairs(self.h, C.byref(t)), "wc_plan_total_pairs", self.ctx.h)

@@ -171,6 +171,10 @@ struct wc_plan {
     DevBuf                   d_bigfwd;
     int                      n_pk_items = 0;   // (unit, chunk) items of the one-pass packing kernel, every generic unit
     DevBuf                   d_pk_items, d_pk_status;
+    // quantile thresholds (extension): radix-select state and histograms, one row per unit or one for the batch
+    DevBuf                   d_q, d_qhist, d_qrank;
+    int                      q_global = -1;    // -1: no quantile run in progress; 0 / 1: mode of the run begun
+    double                   q_keep = 0.0;
     std::vector<char>        has_segtab;                     // per unit: UnitDev::coef is a segment table
     long long total_n = 0;     // sum of ncoef
     size_t    in_bytes = 0;    // sum of input bytes
@@ -645,6 +649,9 @@ int wc_plan_destroy(wc_plan* p) {
     p->d_bigfwd.release();
     p->d_pk_items.release();
     p->d_pk_status.release();
+    p->d_q.release();
+    p->d_qhist.release();
+    p->d_qrank.release();
     p->d_running.release();
     p->d_counter.release();
     p->d_rmse_tiles.release();
@@ -855,7 +862,95 @@ static int plan_pack(wc_plan* p, double keep, const u64* global_key_dev) {
     return WC_OK;
 }
 
+// ---- EXTENSION: quantile thresholds (radix select over the coefficient scratch, see k_q_hist) -----------------
+int wc_plan_quantile_begin(wc_plan* p, double keep, int global, uint64_t n_total) {
+    if (!p || !(keep >= 0.0 && keep <= 1.0)) return WC_ERR_INVALID_ARG;
+    wc_ctx* ctx = p->ctx;
+    // every unit needs its coefficients in HBM: plans whose units all take the scratch path (WC_OPT_PATH = 1 at creation)
+    for (int k = 0; k < FL_N; ++k)
+        if (!p->fl[k].empty()) {
+            ctx->last_error = "quantile thresholds need a plan created under WC_OPT_PATH = 1 (a coefficient scratch for every unit)";
+            return WC_ERR_STATE;
+        }
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = plan_stage_inputs(p);
+    if (rc != WC_OK) return rc;
+    p->has_stats = false;
+    rc = plan_forward(p, false);
+    if (rc != WC_OK) return rc;
+    const int nq = global ? 1 : p->n_units;
+    std::vector<unsigned long long> rank((size_t)std::max(nq, 1));
+    auto kept_target = [&](unsigned long long n) {            // Kt = n - floor(keep * n): rank of the threshold element
+        const unsigned long long drop = (unsigned long long)std::floor(keep * (double)n);
+        return n - std::min(drop, n);
+    };
+    if (global) {
+        unsigned long long n = n_total;
+        if (n == 0) n = (unsigned long long)p->total_n;
+        rank[0] = kept_target(n);
+    } else {
+        for (int i = 0; i < p->n_units; ++i) rank[i] = kept_target((unsigned long long)p->h_units[i].n);
+    }
+    CTX_CUDA(ctx, p->d_q.reserve(sizeof(QState) * (size_t)std::max(nq, 1)));
+    CTX_CUDA(ctx, p->d_qhist.reserve(sizeof(unsigned long long) * Q_BINS * (size_t)std::max(nq, 1)));
+    CTX_CUDA(ctx, p->d_qrank.reserve(sizeof(unsigned long long) * (size_t)std::max(nq, 1)));
+    CTX_CUDA(ctx, cudaMemcpyAsync(p->d_qrank.p, rank.data(), sizeof(unsigned long long) * nq, cudaMemcpyHostToDevice, ctx->stream));
+    CTX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // `rank` is a local
+    CTX_CUDA(ctx, cudaMemsetAsync(p->d_qhist.p, 0, sizeof(unsigned long long) * Q_BINS * (size_t)nq, ctx->stream));
+    CTX_CUDA(ctx, launch_q_init(p->d_q.as<QState>(), p->d_qrank.as<unsigned long long>(), nq, ctx->stream));
+    p->q_global = global ? 1 : 0;
+    p->q_keep = keep;
+    return WC_OK;
+}
+
+int wc_plan_quantile_hist(wc_plan* p, int pass, uint64_t** hist_dev) {
+    if (!p || pass < 0 || pass > 2) return WC_ERR_INVALID_ARG;
+    if (p->q_global < 0) return WC_ERR_STATE;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    CTX_CUDA(ctx, launch_q_hist(p->d_units.as<UnitDev>(), p->d_ctiles.as<int2>(), p->n_ctiles, p->d_q.as<QState>(),
+                                p->d_qhist.as<unsigned long long>(), pass, p->q_global == 1, ctx->stream, &ctx->ls));
+    if (hist_dev) *hist_dev = reinterpret_cast<uint64_t*>(p->d_qhist.p);
+    return WC_OK;
+}
+
+int wc_plan_quantile_pick(wc_plan* p, int pass) {
+    if (!p || pass < 0 || pass > 2) return WC_ERR_INVALID_ARG;
+    if (p->q_global < 0) return WC_ERR_STATE;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    CTX_CUDA(ctx, launch_q_pick(p->d_q.as<QState>(), p->d_qhist.as<unsigned long long>(), p->q_global ? 1 : p->n_units, pass,
+                                ctx->stream, &ctx->ls));
+    return WC_OK;
+}
+
+int wc_plan_quantile_pack(wc_plan* p) {
+    if (!p) return WC_ERR_INVALID_ARG;
+    if (p->q_global < 0) return WC_ERR_STATE;
+    wc_ctx* ctx = p->ctx;
+    CTX_CUDA(ctx, cudaSetDevice(ctx->device));
+    CTX_CUDA(ctx, launch_q_apply(p->d_states.as<UnitState>(), p->d_q.as<QState>(), p->n_units, p->q_global == 1, ctx->stream));
+    if (!p->generic.empty()) {
+        int* counter = nullptr;
+        int rc = plan_counter(p, ctx->stream, &counter);
+        if (rc != WC_OK) return rc;
+        CTX_CUDA(ctx, launch_big_pack(p->d_units.as<UnitDev>(), p->d_states.as<UnitState>(), p->d_pk_items.as<int2>(),
+                                      p->n_pk_items, p->d_pk_status.as<u64>(), counter, ctx->sm_count, ctx->stream, &ctx->ls));
+    }
+    p->q_global = -1;
+    p->compressed = true;
+    return WC_OK;
+}
+
 int wc_plan_compress(wc_plan* p, double keep, int thresh_mode) {
+    if (p && (thresh_mode == WC_THRESH_QUANTILE || thresh_mode == WC_THRESH_QUANTILE_GLOBAL)) {
+        int rc = wc_plan_quantile_begin(p, keep, thresh_mode == WC_THRESH_QUANTILE_GLOBAL, 0);
+        for (int pass = 0; pass < 3 && rc == WC_OK; ++pass) {
+            rc = wc_plan_quantile_hist(p, pass, nullptr);
+            if (rc == WC_OK) rc = wc_plan_quantile_pick(p, pass);
+        }
+        return rc == WC_OK ? wc_plan_quantile_pack(p) : rc;
+    }
     if (!p || (thresh_mode != WC_THRESH_PER_UNIT && thresh_mode != WC_THRESH_GLOBAL))
         return WC_ERR_INVALID_ARG;
     wc_ctx* ctx = p->ctx;

@@ -258,6 +258,134 @@ __global__ void k_global_key(const UnitDev* __restrict__ units, const UnitState*
 }
 
 // ============================================================================================
+// EXTENSION: quantile thresholds by radix select (WC_THRESH_QUANTILE / WC_THRESH_QUANTILE_GLOBAL)
+// ============================================================================================
+// The reference's threshold is max * (1 - keep) (src/compressor.cpp:212-216), not a quantile; this mode exists because
+// the north star names it: keep the Kt = n - floor(keep * n) coefficients of largest magnitude, i.e. thresh = the
+// magnitude of rank Kt (0-based, descending; NaNs rank last and are never kept), mask |c| > thresh as everywhere else —
+// ties at the threshold are all dropped, so the kept set does not depend on any order.  Three passes over the
+// coefficient scratch, each a histogram of 11 / 11 / 9 key bits (key = the float's bit pattern without the sign: for
+// non-NaN magnitudes integer order = float order) among the coefficients that match the prefix chosen so far; a pick
+// kernel walks the histogram from the top.  One histogram row per unit, or ONE row for the whole batch (global mode:
+// the row is what ranks all-reduce with NCCL between hist and pick, so every rank picks the same bucket).
+__global__ void k_q_init(QState* __restrict__ q, const unsigned long long* __restrict__ rank, int nq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    QState s;
+    s.rank = rank[i]; s.nvalid = 0; s.prefix = 0; s.done = 0; s.thresh = __int_as_float(0x7f800000); s.pad = 0;
+    q[i] = s;
+}
+
+__global__ void __launch_bounds__(CT_THREADS)
+k_q_hist(const UnitDev* __restrict__ units, const int2* __restrict__ tiles, const QState* __restrict__ q,
+         unsigned long long* __restrict__ hist, int pass, int global) {
+    __shared__ uint32_t s_h[Q_BINS];
+    const int2    tl = tiles[blockIdx.x];
+    const UnitDev u  = units[tl.x];
+    const int row = global ? 0 : tl.x;
+    const QState st = q[row];
+    if (st.done) return;
+    for (int i = threadIdx.x; i < Q_BINS; i += CT_THREADS) s_h[i] = 0;
+    __syncthreads();
+    const int shift = pass == 0 ? 20 : pass == 1 ? 9 : 0;
+    const uint32_t mask = pass == 2 ? 511u : 2047u;
+    const int pshift = pass == 1 ? 20 : 9;                 // bits below the prefix of the previous passes
+    for (int j = threadIdx.x; j < CT_ELEMS; j += CT_THREADS) {
+        const int f = tl.y * CT_ELEMS + j;
+        if (f < u.n) {
+            const uint32_t key = __float_as_uint(u.coef[f]) & 0x7fffffffu;
+            if (key <= 0x7f800000u && (pass == 0 || (key >> pshift) == st.prefix))
+                atomicAdd(&s_h[(key >> shift) & mask], 1u);
+        }
+    }
+    __syncthreads();
+    unsigned long long* h = hist + (size_t)row * Q_BINS;
+    for (int i = threadIdx.x; i < Q_BINS; i += CT_THREADS)
+        if (s_h[i]) atomicAdd(&h[i], (unsigned long long)s_h[i]);
+}
+
+// one warp per row: the bucket that holds rank `rank` counted from the top, then the row is cleared for the next pass
+__global__ void k_q_pick(QState* __restrict__ q, unsigned long long* __restrict__ hist, int nq, int pass) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= nq) return;
+    QState st = q[row];
+    unsigned long long* h = hist + (size_t)row * Q_BINS;
+    constexpr int PER = Q_BINS / 32;
+    if (!st.done) {
+        unsigned long long mine = 0;
+        for (int i = 0; i < PER; ++i) mine += h[lane * PER + i];
+        // inclusive suffix sums over the lanes (lane 31 holds the top buckets)
+        unsigned long long suf = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long x = __shfl_down_sync(0xffffffffu, suf, o);
+            if (lane + o < 32) suf += x;
+        }
+        const unsigned long long total = __shfl_sync(0xffffffffu, suf, 0);
+        if (pass == 0) st.nvalid = total;
+        if (st.rank >= total) {
+            // fewer (matching) coefficients than the rank asks for: in pass 0 this means "keep every non-NaN
+            // coefficient"; in later passes it cannot happen (the bucket of the previous pass held the rank)
+            st.done = 1;
+            st.thresh = -1.0f;
+        } else {
+            const unsigned long long above = suf - mine;                       // coefficients in higher lanes' buckets
+            const bool here = above <= st.rank && st.rank < suf;               // exactly one lane
+            const int src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+            unsigned long long r = st.rank - above;
+            int b = 0;
+            if (here) {
+                unsigned long long c = 0;
+                for (b = lane * PER + PER - 1;; --b) {                         // from this lane's top bucket down
+                    c += h[b];
+                    if (c > r) { r -= c - h[b]; break; }
+                }
+            }
+            b = __shfl_sync(0xffffffffu, b, src);
+            r = __shfl_sync(0xffffffffu, r, src);
+            const int bits = pass == 2 ? 9 : 11;
+            st.prefix = (st.prefix << bits) | (uint32_t)b;
+            st.rank = r;
+            if (pass == 2) { st.done = 1; st.thresh = __uint_as_float(st.prefix); }
+        }
+        if (lane == 0) q[row] = st;
+    }
+    __syncwarp();
+    for (int i = 0; i < PER; ++i) h[lane * PER + i] = 0ull;
+}
+
+__global__ void k_q_apply(UnitState* __restrict__ states, const QState* __restrict__ q, int n_units, int global) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_units) states[i].thresh_f = q[global ? 0 : i].thresh;
+}
+
+cudaError_t launch_q_init(QState* q, const unsigned long long* rank, int nq, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    k_q_init<<<(nq + 255) / 256, 256, 0, st>>>(q, rank, nq);
+    return cudaGetLastError();
+}
+cudaError_t launch_q_hist(const UnitDev* units, const int2* ctiles, int n_ctiles, const QState* q, unsigned long long* hist,
+                          int pass, bool global, cudaStream_t st, LaunchStats* ls) {
+    if (n_ctiles <= 0) return cudaSuccess;
+    ls->begin(KID_Q_HIST, st);
+    k_q_hist<<<n_ctiles, CT_THREADS, 0, st>>>(units, ctiles, q, hist, pass, global ? 1 : 0);
+    ls->end(st);
+    return cudaGetLastError();
+}
+cudaError_t launch_q_pick(QState* q, unsigned long long* hist, int nq, int pass, cudaStream_t st, LaunchStats* ls) {
+    if (nq <= 0) return cudaSuccess;
+    ls->begin(KID_Q_PICK, st);
+    k_q_pick<<<(nq + 7) / 8, 256, 0, st>>>(q, hist, nq, pass);
+    ls->end(st);
+    return cudaGetLastError();
+}
+cudaError_t launch_q_apply(UnitState* states, const QState* q, int n_units, bool global, cudaStream_t st) {
+    if (n_units <= 0) return cudaSuccess;
+    k_q_apply<<<(n_units + 255) / 256, 256, 0, st>>>(states, q, n_units, global ? 1 : 0);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
 // flat tiles: mask + ordered (run, value) packing
 // ============================================================================================
 // A flat tile is CT_ELEMS consecutive coefficients of one unit.  Warp w of the CTA owns elements

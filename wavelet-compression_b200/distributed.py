@@ -69,6 +69,66 @@ def compress_global_threshold(plan, keep: float, unit_offset: int, device, group
     return g
 
 
+Q_BINS = 2048
+
+
+def allreduce_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of the ranks' radix-select histograms (int64[2048], exact: counts stay far below 2^63)."""
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def radix_select_passes():
+    """(shift, bits) of the three radix-select passes over the 31 magnitude bits (as k_q_hist)."""
+    return ((20, 11), (9, 11), (0, 9))
+
+
+def radix_histogram_host(keys, prefix: int, pass_: int):
+    """Host model of k_q_hist for one shard: histogram (int64[2048]) of pass `pass_` over the uint32 magnitude keys
+    (NaNs removed) that match `prefix`.  Used by the CPU tests of the multi-rank select; the product path is the kernel."""
+    import numpy as np
+    shift, bits = radix_select_passes()[pass_]
+    k = np.asarray(keys, np.uint32)
+    if pass_ > 0:
+        k = k[(k >> np.uint32(shift + bits)) == np.uint32(prefix)]
+    return np.bincount(((k >> np.uint32(shift)) & np.uint32((1 << bits) - 1)).astype(np.int64), minlength=Q_BINS).astype(np.int64)
+
+
+def radix_pick_host(hist, rank: int):
+    """Host model of k_q_pick: bucket holding `rank` counted from the top, and the rank inside it (None: rank >= total)."""
+    total = int(hist.sum())
+    if rank >= total:
+        return None, rank
+    c = 0
+    for b in range(len(hist) - 1, -1, -1):
+        if c + int(hist[b]) > rank:
+            return b, rank - c
+        c += int(hist[b])
+    raise AssertionError("unreachable")
+
+
+def compress_global_quantile(plan, keep: float, n_local: int, device, group=None):
+    """WC_THRESH_QUANTILE_GLOBAL across ranks (EXTENSION): every rank histograms its own coefficients, the histograms
+    are summed with NCCL, every rank picks the same bucket — three passes — and packs with the common threshold, so
+    the kept set is the one a single GPU holding all units would keep."""
+    ctx = plan.ctx
+    from .capi import check
+    n = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+    plan.quantile_begin(keep, True, int(n.item()))
+    h = torch.empty(Q_BINS, dtype=torch.int64, device=device)
+    for p in range(3):
+        hist_dev = plan.quantile_hist(p)
+        check(ctx.lib.wc_memcpy(ctx.h, h.data_ptr(), hist_dev, 8 * Q_BINS, 2), "wc_memcpy", ctx.h)
+        ctx.sync()
+        allreduce_histogram(h, group)
+        if h.is_cuda:
+            torch.cuda.current_stream(device).synchronize()
+        check(ctx.lib.wc_memcpy(ctx.h, hist_dev, h.data_ptr(), 8 * Q_BINS, 2), "wc_memcpy", ctx.h)
+        plan.quantile_pick(p)
+    plan.quantile_pack()
+
+
 def gather_unit_stats(local: torch.Tensor, group=None):
     """Per-unit statistics (pair counts, RMSE) of every rank on rank 0, in unit order.  Ranks may
     hold different numbers of units."""
