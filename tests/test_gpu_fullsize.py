@@ -4,7 +4,9 @@ size-independent properties plus oracle spot checks on sampled units:
   * the all-kept units (negative max, SURVEY.md D3') reconstruct the narrowed input up to the rounding of
     one forward + inverse Haar pass,
   * per-unit pairs, reconstruction and RMSE equal the oracle's on every sampled unit,
-  * forced-generic and fused kernels produce identical packed bytes (checksum of checksums)."""
+  * forced-generic and fused kernels produce identical packed bytes (checksum of checksums),
+  * the plan round trip and the stream (`-d`) decode paths (staged / direct kernels, both index kernels) reconstruct
+    the same bits for every unit of the level."""
 import zlib
 
 import numpy as np
@@ -82,6 +84,31 @@ def test_amr_level_properties(wc, ctx, oracle, level):
         box32 = flat_in[i * n:(i + 1) * n].to(torch.float32)
         got = rec[i * n:(i + 1) * n]
         assert float((box32 - got).abs().max()) <= 2e-6 * float(box32.abs().max())
+
+    # the `-d` path on the same level: a second context decodes the dense device-resident pair stream through a decode
+    # plan (staged TMA-fed kernel for 32^3, streamed segment index + slab items for 64^3) and then with the direct
+    # kernels; all three reconstructions — plan round trip, stream, stream without staging — are the same bits
+    hrec = plan.fetch_records(wc.WC_HOST).copy()
+    k32 = hrec["npairs"].astype(np.int32)
+    total = int(k32.sum())
+    d_stream = torch.empty(max(total, 1), dtype=torch.int64, device="cuda")
+    wc.capi.check(ctx.lib.wc_memcpy(ctx.h, d_stream.data_ptr(), int(hrec[0]["pairs"]), 8 * total, 0), "wc_memcpy", ctx.h)
+    d_k = torch.from_numpy(k32).cuda()
+    ctx2 = wc.Context(0)
+    try:
+        for pipe, seg in ((2, 0), (0, 1)):
+            ctx2.set_option(wc.capi.WC_OPT_DECODE_PIPE, pipe)
+            ctx2.set_option(wc.capi.WC_OPT_SEG_INDEX, seg)
+            rec2 = torch.full((len(dims) * n,), 5.0, dtype=torch.float32, device="cuda")
+            od2 = wc.capi.box_descs([rec2.data_ptr() + 4 * n * i for i in range(len(dims))], [wc.WC_F32] * len(dims), dims)
+            dp = ctx2.decode_plan(od2, wc.WC_DEVICE)
+            dp.decode(d_stream.data_ptr(), d_k.data_ptr(), wc.WC_DEVICE)
+            dp.finish()
+            dp.close()
+            assert torch.equal(rec2.view(torch.int32), rec.view(torch.int32)), (pipe, seg)
+            del rec2
+    finally:
+        ctx2.close()
 
     # oracle spot checks
     for i in list(range(0, len(dims), max(1, len(dims) // 12)))[:12]:
