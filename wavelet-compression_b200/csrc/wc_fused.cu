@@ -1302,7 +1302,10 @@ k_big_pack(const UnitDev* __restrict__ units, UnitState* __restrict__ states, co
             last = __reduce_max_sync(0xffffffffu, last);
             if (lane == 0) s_pk[sg] = ((uint32_t)cnt << 16) | ((uint32_t)last & 0xffffu);
         }
-        if (d.c_ne > 0) {                                        // count ahead, second half
+        __syncthreads();
+        WC_PHASE_CLOCK(t2);
+        auto count_ahead = [&]() {                               // count ahead, second half (per warp)
+            if (d.c_ne <= 0) return;
             const float ctf = d.c_tf;
             int cnt = 0, last = -1;
 #pragma unroll
@@ -1317,16 +1320,9 @@ k_big_pack(const UnitDev* __restrict__ units, UnitState* __restrict__ states, co
             cnt  = __reduce_add_sync(0xffffffffu, cnt);
             last = __reduce_max_sync(0xffffffffu, last);
             if (lane == 0) { s_ca[warp] = cnt; s_ca[8 + warp] = last; }
-        }
-        __syncthreads();
-        WC_PHASE_CLOCK(t2);
-        if (tid == 0 && d.c_ne > 0) {
-            int tc = 0, tl = -1;
-#pragma unroll
-            for (int w = 0; w < PK_NT / 32; ++w) { tc += s_ca[w]; tl = max(tl, s_ca[8 + w]); }
-            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(status + item + ahead),
-                         "l"(pk_pack(1, (uint32_t)tc, tl >= 0 ? d.c_f0 + tl : -1)) : "memory");
-        }
+        };
+        // warps 1.. count ahead while warp 0 scans the segments and looks back (it counts its own share afterwards)
+        if (warp != 0) count_ahead();
 
         // ---- scan of the (at most 16) segments + look-back over the unit's earlier chunks, all in warp 0
         if (warp == 0) {
@@ -1384,8 +1380,16 @@ k_big_pack(const UnitDev* __restrict__ units, UnitState* __restrict__ states, co
                 }
             }
         }
+        if (warp == 0) count_ahead();
         __syncthreads();
         WC_PHASE_CLOCK(t3);
+        if (tid == 0 && d.c_ne > 0) {
+            int tc = 0, tl = -1;
+#pragma unroll
+            for (int w = 0; w < PK_NT / 32; ++w) { tc += s_ca[w]; tl = max(tl, s_ca[8 + w]); }
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(status + item + ahead),
+                         "l"(pk_pack(1, (uint32_t)tc, tl >= 0 ? d.c_f0 + tl : -1)) : "memory");
+        }
         if (tid == 0) fetch(slot ^ 1);     // the other buffer was emitted before the barrier at the end of the last item
 
         // ---- C2: emit (run, value) pairs, segments handed out dynamically (fused kernels, phase C2)
