@@ -1939,7 +1939,10 @@ __device__ __forceinline__ void fd_decode_chunks(const int2* __restrict__ pairs,
 //   L2 (prefetched), software-pipelined one tile ahead.
 //   A thread owns FS_PPT CONSECUTIVE pairs of a tile (one shuffle scan per tile instead of one per 32 pairs); with an
 //   odd FS_PPT the lanes' 8-byte shared-memory loads are conflict-free (stride FS_PPT * 8 bytes).
-constexpr int FS_PPT    = 7;
+#ifndef WC_FS_PPT
+#define WC_FS_PPT 11
+#endif
+constexpr int FS_PPT    = WC_FS_PPT;     // odd
 constexpr int FS_SLOTS  = 12288;               // 96 KB
 constexpr int FS_PAIRS  = FS_SLOTS - 2;
 constexpr uint32_t FS_CL = 1u << 17;           // clamp of one pair's run + 1: > any ncoef of an S = 1 unit (32768), and
@@ -2045,8 +2048,9 @@ __device__ __forceinline__ void fd_decode_staged(const G& g, const int2* __restr
             for (int j = 0; j < FS_PPT; ++j)
                 if (pr[j].x < 0) { inc[j] = 0; if (p + j < K) bad = true; }
         }
-        const uint32_t s = ((inc[0] + inc[1]) + (inc[2] + inc[3])) + ((inc[4] + inc[5]) + inc[6]);
-        static_assert(FS_PPT == 7, "sum above");
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < FS_PPT; ++j) s += inc[j];
         uint32_t w = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
