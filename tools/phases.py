@@ -16,18 +16,22 @@ else: sel = list(range(len(dims)))
 if len(sys.argv) > 2 and sys.argv[2].isdigit(): sel = sel[:int(sys.argv[2])]   # few units: the input stays in L2 (hot-input diagnostic)
 plan = ctx.plan(descs[sel], pkg.WC_DEVICE)
 lib = ctx.lib
-lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+have_prof = hasattr(lib, 'wc_debug_phase_cycles')   # only in `make prof` builds; the product library just gets timed
+if have_prof: lib.wc_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 out = (ctypes.c_ulonglong * 8)()
 with torch.cuda.stream(stream):
     for _ in range(3): plan.compress(bench.KEEP)
     torch.cuda.synchronize()
-    lib.wc_debug_phase_cycles(ctx.h, out, 1)
+    if have_prof: lib.wc_debug_phase_cycles(ctx.h, out, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(10): plan.compress(bench.KEEP)
     e1.record(stream)
     torch.cuda.synchronize()
-    lib.wc_debug_phase_cycles(ctx.h, out, 1)
+    if have_prof: lib.wc_debug_phase_cycles(ctx.h, out, 1)
+if not have_prof:
+    print(which, 'ms/step', e0.elapsed_time(e1) / 10)
+    sys.exit(0)
 v = np.array(list(out), dtype=np.float64)
 units = v[5]
 print(which, "ms/step", e0.elapsed_time(e1)/10, "units", units/10)
@@ -35,3 +39,4 @@ names = ["A(transform+wait)", "B(threshold)", "C1(count)", "scan/exchange", "C2(
 for n, c in zip(names, v[:5]):
     print(f"  {n:20s} {c/units:9.0f} cycles/unit  {100*c/v[:5].sum():5.1f}%")
 print("  total cycles/unit", v[:5].sum()/units)
+print(f"  cluster waits (inside B / scan): {v[6]/units:.0f} / {v[7]/units:.0f} cycles/unit")

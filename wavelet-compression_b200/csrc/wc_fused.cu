@@ -259,6 +259,16 @@ __device__ __forceinline__ void st_pair_pred(bool p, int2* addr, int run, float 
 // exchange), 4 = C2 (emit), 5 = units processed.
 // Only in builds with -DWC_PHASE_PROFILE (make PHASE_PROFILE=1): the read-modify-writes cost thread 0 some
 // 600 cycles per unit.
+#ifdef WC_HANG_DEBUG
+// Developer aid (never in the product build): per-warp progress markers in mapped host memory, readable while a kernel hangs.
+__device__ int* g_dbg_ptr;
+#define WC_MARK(s) do { if (g_dbg_ptr && (threadIdx.x & 31) == 0) { ((volatile int*)g_dbg_ptr)[blockIdx.x * 32 + (threadIdx.x >> 5)] = (s); __threadfence_system(); } } while (0)
+extern "C" __attribute__((visibility("default"))) int wc_debug_set_marker(void* p) {
+    return (int)cudaMemcpyToSymbol(g_dbg_ptr, &p, sizeof(p));
+}
+#else
+#define WC_MARK(s) do { } while (0)
+#endif
 #ifdef WC_PHASE_PROFILE
 __device__ unsigned long long g_phase_cycles[1024][8];
 #define WC_PHASE_CLOCK(t) long long t = clock64()
@@ -494,7 +504,11 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     float vmn = __int_as_float(0x7f800000), vmx = __int_as_float(0xff800000);   // MM: min / max of the inputs
     bool  nan0 = false;
     WC_PHASE_CLOCK(t0);
+#ifdef WC_PHASE_PROFILE
+    long long wait_b = 0, wait_s = 0;      // cycles in the two cluster-scope mbarrier waits
+#endif
     if (tid == 0) la.stage1();
+    __syncwarp();      // see the note at the C2 loop: thread 0 must be back before the next warp collective
 
     // ---------------- phase A: load, narrow, transform two blocks per thread, store into C -------
     {
@@ -520,6 +534,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
 
     // ---------------- phase B: the threshold ----------------
     WC_PHASE_CLOCK(t1);
+    WC_MARK(1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         bp = fmaxf(bp, __shfl_xor_sync(0xffffffffu, bp, o));
@@ -540,7 +555,9 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
                         (u64)((__float_as_uint(bn) & 0x7fffffffu) | (any_nan0 ? 0x80000000u : 0u));
     }
     __syncthreads();
+    WC_MARK(2);
     if (tid == 0) la.stage2();
+    __syncwarp();
     if (MM && warp == 0) {
         // one atomic pair per CTA and unit: vmax holds the order code of the max, vmin the INVERTED code of
         // the min (both reduce with atomicMax over a zeroed word; wc_plan_unit_stats decodes them)
@@ -581,8 +598,14 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
             st_cluster_u64(mapa(smem_u32(&S.xs1[par * 8 + rank]), tid), pay);
             mbar_arrive_remote(mapa(S.xb1, tid));
         }
+        WC_PHASE_CLOCK(tw0);
         mbar_wait_cluster(S.xb1, par);
+        WC_PHASE_CLOCK(tw1);
+#ifdef WC_PHASE_PROFILE
+        wait_b = tw1 - tw0;
+#endif
         ++xph1;
+    WC_MARK(3);
         float p = 0.f, n = 0.f;
         bool fn = false;
 #pragma unroll
@@ -663,6 +686,7 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
 
     // ---------------- phase C1: per-segment count and last kept ----------------
     WC_PHASE_CLOCK(t2);
+    WC_MARK(4);
     const int gpar = R > 1 ? (int)(xph2 & 1) : 0;
     uint32_t* const my_pk = S.g_pk + gpar * SM::MAXG;
 #pragma unroll 1
@@ -702,40 +726,64 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
         }
     }
     WC_PHASE_CLOCK(t3);
+    WC_MARK(5);
     if (R > 1) {
+#ifndef WC_C1_FENCE
+#define WC_C1_FENCE 1
+#endif
+#if WC_C1_FENCE
         fence_cluster();
+#endif
         __syncthreads();
         if (tid < R) mbar_arrive_remote(mapa(S.xb2, tid));
+        WC_PHASE_CLOCK(tw2);
         mbar_wait_cluster(S.xb2, gpar);
+        WC_PHASE_CLOCK(tw3);
+#ifdef WC_PHASE_PROFILE
+        wait_s = tw3 - tw2;
+#endif
         ++xph2;
+    WC_MARK(6);
     } else {
         __syncthreads();
     }
 
     // ---------------- scan over the segments in global order ----------------
     {
-        constexpr int EPT = (SM::MAXG + NT - 1) / NT;   // entries per thread
+        // entries per thread: a thread of a cluster kernel owns ONE segment with the entries of all R CTAs (they are
+        // adjacent in the global order), so at most four warps scan and every thread reads 2 * NWA warp totals
+        // instead of 2 * NW (one entry per thread kept all 32 warps of the 64^3 kernel busy with 64 shared-memory
+        // reads each: ~2 k cycles per slab)
+        // entries per thread: a thread of a cluster kernel owns ONE segment with the entries of all R CTAs (they are
+        // adjacent in the global order), so at most four warps scan and every thread reads 2 * NWA warp totals
+        // instead of 2 * NW (one entry per thread kept all 32 warps of the 64^3 kernel busy with 64 shared-memory
+        // reads each).  Nothing but (isum, imax) lives across the barrier: the entries are read again behind it —
+        // the kernel sits at its 64-register cap, and a version that kept them spilled to local memory.
+        constexpr int EPT = R > 1 ? R : (SM::MAXG + NT - 1) / NT;
+        constexpr int NWA = (SM::MAXG / EPT + 31) / 32 < NW ? (SM::MAXG / EPT + 31) / 32 : NW;   // warps that own entries
         const int NG = g.nseg * R;                      // <= MAXG, entry e = sg * R + r
         int* sr = reinterpret_cast<int*>(S.s_red);
-        // only the warps that own entries work; the others (all but the first for R = 1) just publish
-        // neutral elements and meet the barriers
+        // only the warps that own entries work; the others (all but the first for R = 1) just meet the barriers
         const bool active = warp * 32 * EPT < NG;
-        int cv[EPT], lv[EPT];
+        // entry e -> (kept count, flat index of its last kept coefficient or -1)
+        auto entry = [&](int e, int& cnt, int& last) {
+            cnt = 0; last = -1;
+            if (e < NG) {
+                const uint32_t pk = my_pk[e];
+                const int sg = e / R, r = e % R;
+                cnt = (int)(pk >> 16);
+                if ((pk & 0xffffu) != 0xffffu)
+                    last = ((sg >> 1) * g.Y + (sg & 1) * g.hy + r * g.nb) * g.Z + (int)(pk & 0xffffu);
+            }
+        };
         int isum = 0, imax = -1;
         if (active) {
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {
-                const int e = tid * EPT + j;
-                cv[j] = 0; lv[j] = -1;
-                if (e < NG) {
-                    const uint32_t pk = my_pk[e];
-                    const int sg = e / R, r = e % R;
-                    cv[j] = (int)(pk >> 16);
-                    if ((pk & 0xffffu) != 0xffffu)
-                        lv[j] = ((sg >> 1) * g.Y + (sg & 1) * g.hy + r * g.nb) * g.Z + (int)(pk & 0xffffu);
-                }
-                isum += cv[j];
-                imax = max(imax, lv[j]);
+                int c, l;
+                entry(tid * EPT + j, c, l);
+                isum += c;
+                imax = max(imax, l);
             }
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -744,12 +792,13 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
                 if (lane >= o) { isum += ps; imax = max(imax, pm); }
             }
         }
-        if (lane == 31) { sr[warp] = isum; sr[32 + warp] = imax; }
+        if (lane == 31 && warp < NWA) { sr[warp] = isum; sr[32 + warp] = imax; }
         __syncthreads();
+    WC_MARK(7);
         if (active) {
             int wsum = 0, wmax = -1, total = 0;
 #pragma unroll
-            for (int i = 0; i < NW; ++i) {
+            for (int i = 0; i < NWA; ++i) {
                 int xs = sr[i], xm = sr[32 + i];
                 if (i < warp) { wsum += xs; wmax = max(wmax, xm); }
                 total += xs;
@@ -767,8 +816,12 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
                     // decode-side segment table (k_seg_index): first pair of the segment, last kept before it
                     if (u.coef) reinterpret_cast<int2*>(u.coef)[e] = make_int2(es, em);
                 }
-                es += cv[j];
-                em = max(em, lv[j]);
+                if (j + 1 < EPT) {
+                    int c, l;
+                    entry(e, c, l);
+                    es += c;
+                    em = max(em, l);
+                }
             }
             if (tid == 0 && rank == 0) {
                 states[uid].npairs = total;
@@ -786,7 +839,14 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
     // (detail bands below the threshold) to a full copy, and a static round-robin left half of the
     // warps idle at the closing barrier.
     WC_PHASE_CLOCK(t4);
+    WC_MARK(8);
     if (tid == 0) la.stage3();
+    // Thread 0 has to be back in its warp before the loop's first __shfl_sync.  ptxas 12.9 does not always put a
+    // reconvergence point behind this one-thread region (it sits inside a larger region that spans CTA barriers), and
+    // it issues the loop's SHFL without a WARPSYNC: lanes 1..31 of warp 0 then read the segment number from an absent
+    // lane 0, never see it reach nseg and spin forever — the hang of DESIGN.md §4.5.  Which builds are hit depends on
+    // register allocation and block layout around the scan, not on the scan's arithmetic.
+    __syncwarp();
     int2* const out = reinterpret_cast<int2*>(u.out);
     for (;;) {
         int sg = 0;
@@ -835,13 +895,16 @@ __device__ __forceinline__ void fc_unit(const G& g, const UnitDev& u, const int 
             prev = prel + fstart + w0 + 128;
         }
     }
+    WC_MARK(9);
     if (tid == 0) la.stage4();
     __syncthreads();   // C and the segment arrays are rewritten by the next unit
+    WC_MARK(10);
 #ifdef WC_PHASE_PROFILE
     if (tid == 0 && blockIdx.x < 1024) {
         long long t5 = clock64();
         unsigned long long* pc = g_phase_cycles[blockIdx.x];
         pc[0] += t1 - t0; pc[1] += t2 - t1; pc[2] += t3 - t2; pc[3] += t4 - t3; pc[4] += t5 - t4; pc[5] += 1;
+        pc[6] += wait_b; pc[7] += wait_s;
     }
 #endif
 }
@@ -882,6 +945,7 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
         cluster_sync_all();
     }
 
+    WC_MARK(20);
     const uint32_t lt = lanemask_lt();
     const u64 pol = l2_policy_evict_first();
     uint32_t xph1 = 0, xph2 = 0, xph3 = 0;
@@ -942,7 +1006,9 @@ k_fused_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ stat
         }
 #undef WC_FC_UNIT
     }
+    WC_MARK(21);
     if (R > 1) cluster_sync_all();   // no CTA may exit while peers can still write into its smem
+    WC_MARK(22);
 }
 
 // ---- launchers --------------------------------------------------------------------------------------
