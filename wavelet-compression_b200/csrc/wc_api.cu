@@ -128,7 +128,8 @@ static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_R4,
                                     FUSED_CLS_R1, FUSED_CLS_CUBE16, FUSED_CLS_R1S, FUSED_CLS_CUBE8,
                                     FUSED_CLS_RBIG /* decompress only; compress plans never fill it */};
 enum { FL_BIG = 9 };
-// One launch takes units of one slab count: the FUSED_CLS_RBIG list is kept sorted by it (then by unit id) and launched
+// One launch takes units of one launch key (slab count, 128^3 cube or not: big_run_key): the FUSED_CLS_RBIG list is kept
+// sorted by it (then by unit id) and launched
 // run by run; every other class is a single run.  f(first, count, slabs)
 template <class Dims, class F>
 static int for_each_run(int cls, const std::vector<int>& list, Dims dims, F f) {
@@ -137,11 +138,11 @@ static int for_each_run(int cls, const std::vector<int>& list, Dims dims, F f) {
     while (a < list.size()) {
         int nx, ny, nz;
         dims(list[a], nx, ny, nz);
-        const int S = fused_decode_slabs_of(cls, nx, ny, nz);
+        const int S = big_run_key(nx, ny, nz);
         size_t b = a + 1;
         for (; b < list.size(); ++b) {
             dims(list[b], nx, ny, nz);
-            if (fused_decode_slabs_of(cls, nx, ny, nz) != S) break;
+            if (big_run_key(nx, ny, nz) != S) break;
         }
         int rc = f(a, b - a, S);
         if (rc != WC_OK) return rc;
@@ -154,7 +155,7 @@ static void sort_big_list(std::vector<int>& list, Dims dims) {
     std::stable_sort(list.begin(), list.end(), [&](int x, int y) {
         int ax, ay, az, bx, by, bz;
         dims(x, ax, ay, az); dims(y, bx, by, bz);
-        return fused_decode_slabs_of(FUSED_CLS_RBIG, ax, ay, az) < fused_decode_slabs_of(FUSED_CLS_RBIG, bx, by, bz);
+        return big_run_key(ax, ay, az) < big_run_key(bx, by, bz);
     });
 }
 static inline bool fl_is_cluster(int k) { return k < 4; }

@@ -127,6 +127,11 @@ __host__ __device__ inline int big_slabs(int nx, int ny, int nz) {
     return (S >= 2 && S <= 1024) ? S : 0;
 }
 
+int big_run_key(int nx, int ny, int nz) {
+    const int S = big_slabs(nx, ny, nz);
+    return S | ((nx == 128 && ny == 128 && nz == 128) ? (int)BIG_CUBE128 : 0);
+}
+
 int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
     if (reinterpret_cast<uintptr_t>(ptr) & 15u) return 0;
     FGeom g;
@@ -1219,6 +1224,7 @@ k_big_forward(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
 cudaError_t launch_big_forward(const UnitDev* units, UnitState* states, const int* unit_list, int n_list, int s_rt,
                                int* work_counter, int sm_count, cudaStream_t st, LaunchStats* ls) {
     if (n_list <= 0) return cudaSuccess;
+    s_rt &= BIG_SLAB_MASK;      // launch key -> slab count
     if (s_rt < 2) return cudaErrorInvalidValue;
     constexpr int NT = 512, smem = (32768 + F_CPAD_BIG) * 4 + 512;
     cudaError_t e = cudaFuncSetAttribute(k_big_forward<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1993,6 +1999,51 @@ __device__ __forceinline__ void fd_decode_chunks(const int2* __restrict__ pairs,
     base = b;
 }
 
+// Two segments at once, NCH chunks of 32 pairs each (both have at most 32 * NCH pairs): all 2 * NCH loads are in flight
+// together and the scans are independent chains, so a warp pays ONE memory round trip for the two segments.  Short
+// segments are the rule for slab items (64^3: 96 of a slab's 128 segments are detail bands with a few dozen pairs;
+// 128^3: 256 segments of ~77 pairs, 16 per warp) and the decode was a chain of one L2 latency per segment.
+struct FdSeg {
+    int      c0, e1x;       // pair range
+    uint32_t base, fseg;    // flat index of the pair before the first; flat index of the segment's first coefficient
+    float*   cseg;
+};
+template <int NCH>
+__device__ __forceinline__ void fd_decode_two(const int2* __restrict__ pairs, const FdSeg& a, const FdSeg& b, int lane,
+                                              uint32_t seglen, uint32_t total) {
+    int2     pv[2 * NCH];
+    uint32_t inc[2 * NCH];
+#pragma unroll
+    for (int c = 0; c < 2 * NCH; ++c) {
+        const FdSeg& sgm = c < NCH ? a : b;
+        const int p = sgm.c0 + 32 * (c < NCH ? c : c - NCH) + lane;
+        pv[c] = make_int2(-1, 0);
+        if (p < sgm.e1x) pv[c] = __ldg(pairs + p);
+    }
+#pragma unroll
+    for (int c = 0; c < 2 * NCH; ++c) inc[c] = pv[c].x >= 0 ? (uint32_t)pv[c].x + 1u : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < 2 * NCH; ++c) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc[c], o);
+            if (lane >= o) inc[c] += v;
+        }
+    }
+    uint32_t tot[2 * NCH];
+#pragma unroll
+    for (int c = 0; c < 2 * NCH; ++c) tot[c] = __shfl_sync(0xffffffffu, inc[c], 31);
+    uint32_t ba = a.base, bb = b.base;
+#pragma unroll
+    for (int c = 0; c < 2 * NCH; ++c) {
+        const FdSeg& sgm = c < NCH ? a : b;
+        uint32_t& bs = c < NCH ? ba : bb;
+        const uint32_t f = bs + inc[c];
+        if (pv[c].x >= 0 && f - sgm.fseg < seglen && f < total) sgm.cseg[f - sgm.fseg] = __int_as_float(pv[c].y);
+        bs += tot[c];
+    }
+}
+
 // ---- staged decode (S = 1, table-less packed streams) ------------------------------------------------
 // The block-scan decode above is a chain of dependent latencies per tile (HBM load -> sum -> barrier -> scatter) that
 // nothing hides with one 128 KB coefficient array per SM.  Here the pair list of the NEXT item is copied into a
@@ -2349,6 +2400,8 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
         // Lanes 2q, 2q+1 hold the table entries of the warp's q-th segment (loaded before the zero-fill);
         // up to 8 chunks of 32 pairs are in flight per segment before the first one is decoded.
         const uint32_t seglen = (uint32_t)g.seglen;
+        bool have_held = false;      // a short segment waiting for a partner (fd_decode_two)
+        FdSeg held = {0, 0, 0u, 0u, nullptr};
 #pragma unroll 1
         for (int q = 0; q * NW + warp < g.nseg; ++q) {
             const int sg = fd_seg_of(q, warp, NW);
@@ -2368,6 +2421,14 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
             float* const cseg = C + i * g.slab + half * g.seglen;    // C index of flat index m * seglen
             const uint32_t fseg = (uint32_t)m * seglen;
             uint32_t base = (uint32_t)e0y;                           // flat index of the pair before the first (or -1)
+            if (e1x <= e0x) continue;                                // nothing kept in this segment
+            if (S != 1 && e1x - e0x <= 128) {
+                // short segment: decoded together with the warp's next short one (one memory round trip for both)
+                const FdSeg cur = {e0x, e1x, base, fseg, cseg};
+                if (have_held) { fd_decode_two<4>(pairs, held, cur, lane, seglen, total); have_held = false; }
+                else           { held = cur; have_held = true; }
+                continue;
+            }
 #pragma unroll 1
             for (int c0 = e0x; c0 < e1x; c0 += 256) {
                 // 4 or 8 chunks of 32 pairs at once: the loads are all in flight together, and the chunks'
@@ -2376,6 +2437,7 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
                 else                 fd_decode_chunks<8>(pairs, c0, e1x, lane, base, fseg, seglen, total, cseg);
             }
         }
+        if (have_held) fd_decode_chunks<4>(pairs, held.c0, held.e1x, lane, held.base, held.fseg, seglen, total, held.cseg);
     }
     WC_PHASE_CLOCK(t3);
     if (tid == 0) la.wait_all();          // K of the next item, unit id of the item after the staged ones
@@ -2486,7 +2548,10 @@ __device__ __forceinline__ void fd_unit(const G& g, const DecUnitDev& du, const 
 #endif
 }
 
-// STATIC: every unit of the list is the cube this variant is specialised for (32^3 for S = 1, 64^3 for S = 8).
+// padding words of C: F_PAD per i' slab, X <= 64 for the cluster-sized classes, <= 128 for the run-time / 64-slab ones
+__host__ __device__ constexpr int fd_cpad(int S) { return (S >= 1 && S <= 8) ? F_CPAD : F_CPAD_BIG; }
+// STATIC: every unit of the list is the cube this variant is specialised for (32^3 for S = 1, 64^3 for S = 8, 128^3 for
+// S = 64).
 template <int S, int CAP, int NT, bool STATIC, bool STG>
 __global__ void __launch_bounds__(NT, (CAP <= 512 ? 32 : CAP <= 4096 ? 4 : 1))
 k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv,
@@ -2494,7 +2559,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
                    int* __restrict__ work_counter, int ignore_tab, int s_rt) {
     static_assert(!STG || S == 1, "staged decode: whole-unit items only");
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int BASE = (CAP + (S ? F_CPAD : F_CPAD_BIG)) * 4;
+    constexpr int BASE = (CAP + fd_cpad(S)) * 4;
     const int Sx = S ? S : s_rt;
     float* const    C    = reinterpret_cast<float*>(smem);
     uint32_t* const s_wt = reinterpret_cast<uint32_t*>(smem + BASE);               // [2][32]
@@ -2555,7 +2620,7 @@ k_fused_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restr
         const bool have_next = la.next_slot->ui < n_items;
 #define WC_FD_UNIT(GEOM) fd_unit<S, NT, STG>(GEOM, du, iu, K, C, s_wt, la, rank, err, have_next, stg, s_rt)
         if constexpr (STATIC) {
-            constexpr int CUBE = S == 1 ? (CAP <= 512 ? 8 : CAP <= 4096 ? 16 : 32) : 64;
+            constexpr int CUBE = S == 1 ? (CAP <= 512 ? 8 : CAP <= 4096 ? 16 : 32) : S == 64 ? 128 : 64;
             WC_FD_UNIT((SGeom<CUBE, CUBE, CUBE, 8, S>()));
         } else {
             FGeom g;
@@ -2571,7 +2636,7 @@ static cudaError_t launch_fd(int kid, const DecUnitDev* dec, const InvUnitDev* i
                              int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter,
                              bool build_tables, bool ignore_tab = false, int s_rt = 0) {
     auto kern = k_fused_decompress<S, CAP, NT, STATIC, STG>;
-    constexpr int smem = (CAP + (S ? F_CPAD : F_CPAD_BIG)) * 4 + 1024 + (STG ? FS_SLOTS * 8 : 0);
+    constexpr int smem = (CAP + fd_cpad(S)) * 4 + 1024 + (STG ? FS_SLOTS * 8 : 0);
     const int Sx = S ? S : s_rt;
     static_assert(smem <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -2615,7 +2680,7 @@ int fused_decode_slabs(int fused_cls) {
 cudaError_t launch_seg_index3(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                               int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int s_rt) {
     if (n <= 0 || !fused_decode_needs_table(fused_cls)) return cudaSuccess;
-    const int slabs = fused_cls == FUSED_CLS_RBIG ? s_rt : fused_decode_slabs(fused_cls);
+    const int slabs = fused_cls == FUSED_CLS_RBIG ? (s_rt & BIG_SLAB_MASK) : fused_decode_slabs(fused_cls);
     if (slabs < 2) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_seg_index3, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM);
     if (e != cudaSuccess) return e;
@@ -2679,10 +2744,15 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
                                     cudaStream_t st, LaunchStats* ls, int* work_counter, bool build_tables, int stage,
                                     int s_rt) {
     if (n_list <= 0) return cudaSuccess;
-    if (fused_cls == FUSED_CLS_RBIG)
-        return s_rt >= 2 ? launch_fd<0, 32768, 512, false>(KID_FUSED_DBIG, dec, inv, unit_list, n_list, err, sm_count, st, ls,
-                                                          work_counter, build_tables, false, s_rt)
-                         : cudaErrorInvalidValue;
+    if (fused_cls == FUSED_CLS_RBIG) {
+        const int slabs = s_rt & BIG_SLAB_MASK;
+        if (slabs < 2) return cudaErrorInvalidValue;
+        if ((s_rt & BIG_CUBE128) && slabs == 64)      // the 128^3 cube: literal geometry, 1024 threads
+            return launch_fd<64, 32768, 1024, true>(KID_FUSED_D128, dec, inv, unit_list, n_list, err, sm_count, st, ls,
+                                                    work_counter, build_tables);
+        return launch_fd<0, 32768, 512, false>(KID_FUSED_DBIG, dec, inv, unit_list, n_list, err, sm_count, st, ls,
+                                               work_counter, build_tables, false, slabs);
+    }
     if (stage && fused_cls == FUSED_CLS_CUBE32)
         return launch_fd<1, 32768, 1024, true, true>(KID_STAGED_D1S, dec, inv, unit_list, n_list, err, sm_count, st, ls,
                                                      work_counter, false, stage == 2);

@@ -28,6 +28,10 @@ int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
 size_t fused_decode_table_entries(int fused_cls, int nx, int ny, int nz);   // int2 entries of a unit's segment table
 int fused_decode_slabs_of(int fused_cls, int nx, int ny, int nz);         // y-slabs (work items) per unit
+// Launch key of a FUSED_CLS_RBIG unit: its slab count, plus BIG_CUBE128 for the 128^3 cube (which has a literal-geometry
+// decode kernel of its own).  One launch takes units of one key; the launchers take the key as their s_rt argument.
+enum { BIG_SLAB_MASK = 0xfffff, BIG_CUBE128 = 1 << 20 };
+int big_run_key(int nx, int ny, int nz);
 bool fused_decode_needs_table(int fused_cls);               // slab-decoded classes cannot decode without one
 
 cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states,
