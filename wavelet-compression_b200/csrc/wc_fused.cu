@@ -1463,6 +1463,7 @@ k_big_pack(const UnitDev* __restrict__ units, UnitState* __restrict__ states, co
                          "l"(pk_pack(1, (uint32_t)tc, tl >= 0 ? d.c_f0 + tl : -1)) : "memory");
         }
         if (tid == 0) fetch(slot ^ 1);     // the other buffer was emitted before the barrier at the end of the last item
+        __syncwarp();      // thread 0 back in its warp before the loop's __shfl_sync (see k_fused_compress, phase C2)
 
         // ---- C2: emit (run, value) pairs, segments handed out dynamically (fused kernels, phase C2)
         const uint32_t bcnt = (uint32_t)s_lb[0];
@@ -1799,6 +1800,7 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
         };
         if (tid == 0)
             for (int t = 0; t < ntiles && t < SI_STAGES; ++t) issue(t);
+        __syncwarp();      // one-thread region in front of warp collectives: explicit reconvergence (k_fused_compress, phase C2)
         uint32_t carry = 0;
         int gk = 0, gl = -1;                               // this thread's last in-box pair: index + 1, flat index
 #pragma unroll 1
@@ -1841,6 +1843,7 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
             if (lane == 31) wt[warp] = w;
             __syncthreads();                               // every thread has read its pairs: the stage is free
             if (tid == 0 && t + SI_STAGES < ntiles) issue(t + SI_STAGES);
+            __syncwarp();
             uint32_t ws = lane < SI_NT / 32 ? wt[lane] : 0u;
 #pragma unroll
             for (int o = 1; o < SI_NT / 32; o <<= 1) {
