@@ -119,3 +119,25 @@ def test_big_and_irregular_boxes(wc, ctx, oracle, seg_index):
             assert same_bits(o.astype(np.float32), ob), d
     finally:
         ctx.set_option(wc.capi.WC_OPT_SEG_INDEX, 0)
+
+
+@pytest.mark.parametrize("seg_index", [0, 1])
+def test_big_box_runs_longer_than_half_a_million(wc, ctx, oracle, seg_index):
+    """A 128^3 unit (2^21 coefficients) whose pair list holds zero runs above 2^19: the streamed index kernel clamps run + 1
+    per pair so that its 32-bit sums cannot wrap, and that clamp has to sit above the unit's size (it sat at 2^19, the
+    bound of the cluster classes).  Also a run that jumps past the end in the middle of the list."""
+    d = (128, 128, 128)
+    n = d[0] * d[1] * d[2]
+    rng = np.random.default_rng(5 + seg_index)
+    units = []
+    for gaps in ([0, 600000, 5, 1400000 - 8, 3], [524287, 524288, 524289, 17], [7, 2 ** 20, 2 ** 21, 4, 4], [n - 1], [n], []):
+        head = rng.integers(0, 4, 3000).astype(np.int32)                 # an ordinary stretch first, then the long runs
+        runs = np.concatenate([head, np.array(gaps, np.int32), rng.integers(0, 3, 500).astype(np.int32)])
+        units.append(wc.PackedUnit(d, n, runs, rng.standard_normal(runs.size).astype(np.float32)))
+    ctx.set_option(wc.capi.WC_OPT_SEG_INDEX, seg_index)
+    try:
+        recon = ctx.decompress_batch(units)
+        for i, (p, r) in enumerate(zip(units, recon)):
+            assert same_bits(r.reshape(-1), oracle.decompress_unit(p.runs, p.vals, d).reshape(-1)), i
+    finally:
+        ctx.set_option(wc.capi.WC_OPT_SEG_INDEX, 0)

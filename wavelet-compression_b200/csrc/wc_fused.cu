@@ -133,7 +133,9 @@ int big_run_key(int nx, int ny, int nz) {
 }
 
 int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
-    if (reinterpret_cast<uintptr_t>(ptr) & 15u) return 0;
+    // the x-slab classes (wc_xslab.cu) only need element alignment: they take what the y-slab classes refuse
+    const bool elem_aligned = (reinterpret_cast<uintptr_t>(ptr) & (dtype == WC_F64 ? 7u : 3u)) == 0;
+    if (reinterpret_cast<uintptr_t>(ptr) & 15u) return elem_aligned ? xs_class_of(nx, ny, nz) : FUSED_CLS_NONE;
     FGeom g;
     if (nx == 32 && ny == 32 && nz == 32) return FUSED_CLS_CUBE32;
     if (nx == 64 && ny == 64 && nz == 64) return FUSED_CLS_CUBE64;
@@ -144,7 +146,8 @@ int fused_class(int nx, int ny, int nz, int dtype, const void* ptr) {
     if (fused_geom(nx, ny, nz, dtype, 2, 32768, g)) return FUSED_CLS_R2;
     if (fused_geom(nx, ny, nz, dtype, 4, 32768, g)) return FUSED_CLS_R4;
     if (fused_geom(nx, ny, nz, dtype, 8, 32768, g)) return FUSED_CLS_R8;
-    return FUSED_CLS_NONE;
+    if (big_forward_slabs(nx, ny, nz, dtype, ptr)) return FUSED_CLS_NONE;     // two passes over a scratch (k_big_forward)
+    return xs_class_of(nx, ny, nz);
 }
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -1081,6 +1084,9 @@ cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units,
                                   const u64* global_key, int sm_count, cudaStream_t st,
                                   LaunchStats* ls, int* work_counter) {
     if (n_list <= 0) return cudaSuccess;
+    if (xs_class_slabs(fused_cls))
+        return launch_xs_compress(fused_cls, mode, units, states, unit_list, n_list, one_minus_keep, global_key, sm_count,
+                                  st, ls);
     switch (fused_cls) {
     case FUSED_CLS_R1:
         return launch_fc<1, 32768, 512, false>(KID_FUSED_C1, mode, units, states, unit_list, n_list,
@@ -1648,6 +1654,20 @@ __device__ __forceinline__ uint32_t fd_tile_scan(const int2 (&pr)[FD_PPT], int n
     return sat_add(wpre, exl);
 }
 
+// Geometry of a unit's table for the index kernels: `slabs` y-slabs (segments of nb * Z coefficients, 2 * X per slab), or,
+// for the x-slab classes of wc_xslab.cu (slabs < 0), one entry per plane i' of the flat order (Y * Z coefficients, X planes).
+__device__ __forceinline__ void index_geom(const InvUnitDev& iu, int slabs, uint32_t& seglen, int& nseg) {
+    if (slabs < 0) {
+        seglen = (uint32_t)(iu.ny * iu.nz);
+        nseg   = iu.nx;
+    } else {
+        FGeom g;
+        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g, F_MAXSEG_BIG);
+        seglen = (uint32_t)g.seglen;
+        nseg   = g.nseg * slabs;                   // == total / seglen
+    }
+}
+
 // ---- segment index of the slab-decoded units --------------------------------------------------------
 // tab[m] = (first pair p whose flat index F_p >= m * seglen, flat index of the pair before it or -1),
 // m = 0 .. nseg; pairs at or past `total` (and everything after them) are dropped as rle_decode does:
@@ -1665,10 +1685,10 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
         const int uid = unit_list[ui];
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
-        FGeom g;
-        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g, F_MAXSEG_BIG);
-        const uint32_t seglen = (uint32_t)g.seglen, total = (uint32_t)du.total;
-        const int nseg = g.nseg * slabs;                   // == total / seglen
+        uint32_t seglen;
+        int nseg;
+        index_geom(iu, slabs, seglen, nseg);
+        const uint32_t total = (uint32_t)du.total;
         int2* const tab = reinterpret_cast<int2*>(du.coef);
         const int K = du.npairs_dev ? *du.npairs_dev : du.npairs;
         const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
@@ -1748,8 +1768,12 @@ k_seg_index(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ i
 //   pair earlier, an odd count is rounded up — both stay inside the 16-byte granule of a valid pair, so they never
 //   leave the allocation's pages; slot r + s0 of a stage holds the tile's r-th pair.
 constexpr int SI_NT = 256, SI_PPT = 15, SI_TILE = SI_NT * SI_PPT, SI_STAGES = 3, SI_SLOTS = SI_TILE + 2;
-constexpr uint32_t SI_CL = 1u << 19;   // clamp of one pair's run + 1: > any ncoef of a slab-decoded unit (262144);
-                                       // SI_TILE * SI_CL < 2^31 and the carry is clamped at 2^30: u32 sums never wrap
+constexpr uint32_t SI_CL = 1u << 19;   // clamp of one pair's run + 1 for units below 2^19 coefficients (the cluster and x-slab
+                                       // classes): SI_TILE * SI_CL < 2^31 and the carry is clamped at 2^30: u32 sums never wrap.
+constexpr uint32_t SI_CL_BIG = 1u << 26;   // units of 2^19 coefficients and more (FUSED_CLS_RBIG: up to 2^25): a run can exceed
+                                       // 2^19 there, so the clamp has to sit above the unit's size; thread sums are then clamped
+                                       // at 2^26 and warp totals at 2^28 as well — every clamped value stays above `total`
+                                       // ("past the end"), every exact one is untouched, and no u32 sum below can wrap.
 constexpr int SI_SMEM = SI_STAGES * SI_SLOTS * 8 + 64 + 2 * 32 * 4 + 32;
 
 __global__ void __launch_bounds__(SI_NT, 2)
@@ -1777,10 +1801,10 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
         const int uid = unit_list[ui];
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
-        FGeom g;
-        fused_geom(iu.nx, iu.ny, iu.nz, WC_F64, slabs, 32768, g, F_MAXSEG_BIG);
-        const uint32_t seglen = (uint32_t)g.seglen, total = (uint32_t)du.total;
-        const int nseg = g.nseg * slabs;                   // == total / seglen
+        uint32_t seglen;
+        int nseg;
+        index_geom(iu, slabs, seglen, nseg);
+        const uint32_t total = (uint32_t)du.total;
         int2* const tab = reinterpret_cast<int2*>(du.coef);
         const int K = du.npairs_dev ? *du.npairs_dev : du.npairs;
         const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
@@ -1788,6 +1812,7 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
         const int ntiles = (K + SI_TILE - 1) / SI_TILE;
         FastDiv dsl;
         dsl.init(seglen, total + seglen);
+        const uint32_t cl = total < SI_CL ? SI_CL : SI_CL_BIG;
         auto issue = [&](int t) {                          // thread 0: tile t of this unit into its stage
             const uint32_t q = q0 + (uint32_t)t, st = q % SI_STAGES;
             const int cnt = min(SI_TILE, K - t * SI_TILE) + s0;
@@ -1824,7 +1849,7 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
 #pragma unroll
             for (int j = 0; j < SI_PPT; ++j) {
                 any |= run[j];
-                inc[j] = min((uint32_t)run[j] + 1u, SI_CL);
+                inc[j] = min((uint32_t)run[j] + 1u, cl);
             }
             if (any < 0) {
 #pragma unroll
@@ -1833,12 +1858,14 @@ k_seg_index3(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ 
             }
 #pragma unroll
             for (int j = 0; j < SI_PPT; ++j) s += inc[j];
+            s = min(s, SI_CL_BIG);                         // no-op below 2^19 coefficients (s < 2^23)
             uint32_t w = s;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
                 if (lane >= o) w += v;
             }
+            w = min(w, 1u << 28);                          // likewise (w <= 2^28 there)
             uint32_t* const wt = s_wt + (t & 1) * 32;
             if (lane == 31) wt[warp] = w;
             __syncthreads();                               // every thread has read its pairs: the stage is free
@@ -2677,14 +2704,16 @@ int fused_decode_slabs(int fused_cls) {
     case FUSED_CLS_R4: return 4;
     case FUSED_CLS_R2: return 2;
     }
+    if (const int xs = xs_class_slabs(fused_cls)) return xs;
     return 1;
 }
 
 cudaError_t launch_seg_index3(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* list, int n,
                               int* work_counter, int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int s_rt) {
     if (n <= 0 || !fused_decode_needs_table(fused_cls)) return cudaSuccess;
-    const int slabs = fused_cls == FUSED_CLS_RBIG ? (s_rt & BIG_SLAB_MASK) : fused_decode_slabs(fused_cls);
-    if (slabs < 2) return cudaErrorInvalidValue;
+    const int slabs = fused_cls == FUSED_CLS_RBIG ? (s_rt & BIG_SLAB_MASK)
+                    : xs_class_slabs(fused_cls) ? -1 /* plane table */ : fused_decode_slabs(fused_cls);
+    if (slabs >= 0 && slabs < 2) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_seg_index3, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM);
     if (e != cudaSuccess) return e;
     const int nb = n < 2 * sm_count ? n : 2 * sm_count;
@@ -2709,7 +2738,11 @@ cudaError_t launch_dec_prepare(DecUnitDev* dec, int n_units, const wc_pair* dens
 // Which fused-decompress class a unit belongs to (FUSED_CLS_*, 0 = generic): same geometry rules as compress,
 // plus the output pointer alignment for the vector stores.
 int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_ptr) {
-    if (reinterpret_cast<uintptr_t>(out_ptr) & (out_dtype == WC_F64 ? 15u : 7u)) return FUSED_CLS_NONE;
+    if (reinterpret_cast<uintptr_t>(out_ptr) & (out_dtype == WC_F64 ? 15u : 7u)) {
+        // element-aligned is enough for the x-slab classes (scalar stores)
+        const bool elem_aligned = (reinterpret_cast<uintptr_t>(out_ptr) & (out_dtype == WC_F64 ? 7u : 3u)) == 0;
+        return elem_aligned ? xs_class_of(nx, ny, nz) : FUSED_CLS_NONE;
+    }
     if (nx == 32 && ny == 32 && nz == 32) return FUSED_CLS_CUBE32;
     if (nx == 64 && ny == 64 && nz == 64) return FUSED_CLS_CUBE64;
     if (nx == 16 && ny == 16 && nz == 16) return FUSED_CLS_CUBE16;
@@ -2721,7 +2754,7 @@ int fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_pt
     if (fused_geom(nx, ny, nz, WC_F64, 4, 32768, g)) return FUSED_CLS_R4;
     if (fused_geom(nx, ny, nz, WC_F64, 8, 32768, g)) return FUSED_CLS_R8;
     if (big_slabs(nx, ny, nz)) return FUSED_CLS_RBIG;
-    return FUSED_CLS_NONE;
+    return xs_class_of(nx, ny, nz);
 }
 int fused_decode_slabs_of(int fused_cls, int nx, int ny, int nz) {
     return fused_cls == FUSED_CLS_RBIG ? big_slabs(nx, ny, nz) : fused_decode_slabs(fused_cls);
@@ -2735,11 +2768,12 @@ size_t fused_decode_table_entries(int fused_cls, int nx, int ny, int nz) {
     if (fused_cls == FUSED_CLS_R1 || fused_cls == FUSED_CLS_CUBE32 || fused_cls == FUSED_CLS_R1S ||
         fused_cls == FUSED_CLS_CUBE16 || fused_cls == FUSED_CLS_CUBE8)
         return (size_t)(2 * nx + 1);
+    if (xs_class_slabs(fused_cls) > 1) return (size_t)(nx + 2);      // one entry per plane i' + the end of the list
     return 0;
 }
 bool fused_decode_needs_table(int fused_cls) {
     return fused_cls == FUSED_CLS_R8 || fused_cls == FUSED_CLS_CUBE64 || fused_cls == FUSED_CLS_R4 || fused_cls == FUSED_CLS_R2 ||
-           fused_cls == FUSED_CLS_RBIG;
+           fused_cls == FUSED_CLS_RBIG || xs_class_slabs(fused_cls) > 1;
 }
 
 cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv,
@@ -2747,6 +2781,17 @@ cudaError_t launch_fused_decompress(int fused_cls, const DecUnitDev* dec, const 
                                     cudaStream_t st, LaunchStats* ls, int* work_counter, bool build_tables, int stage,
                                     int s_rt) {
     if (n_list <= 0) return cudaSuccess;
+    if (const int xs = xs_class_slabs(fused_cls)) {
+        if (xs > 1 && build_tables) {      // plane tables by the direct-load index kernel (WC_OPT_SEG_INDEX = 1, mixed lists)
+            const int nb = n_list < 2 * sm_count ? n_list : 2 * sm_count;
+            ls->begin(KID_SEG_INDEX, st);
+            k_seg_index<512><<<nb, 512, 0, st>>>(dec, inv, unit_list, n_list, err, -1);
+            ls->end(st);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+        return launch_xs_decompress(fused_cls, dec, inv, unit_list, n_list, err, sm_count, st, ls, work_counter);
+    }
     if (fused_cls == FUSED_CLS_RBIG) {
         const int slabs = s_rt & BIG_SLAB_MASK;
         if (slabs < 2) return cudaErrorInvalidValue;

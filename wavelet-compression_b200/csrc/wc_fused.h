@@ -23,7 +23,10 @@ enum { FUSED_CLS_NONE = 0, FUSED_CLS_R1 = 1, FUSED_CLS_R1S = 2, FUSED_CLS_R8 = 8
        FUSED_CLS_R2 = 22,      // clusters of 4 / 2: boxes whose half-height is not a multiple of 8 (40^3 ...)
        FUSED_CLS_CUBE32 = 101,
        FUSED_CLS_CUBE64 = 108, FUSED_CLS_CUBE16 = 116, FUSED_CLS_CUBE8 = 117,
-       FUSED_CLS_RBIG = 200 };  // decompress only: any number of y-slabs of <= 32768 cells (128^3 ...), one launch per slab count
+       FUSED_CLS_RBIG = 200,    // decompress only: any number of y-slabs of <= 32768 cells (128^3 ...), one launch per slab count
+       // x-slab classes (wc_xslab.cu): ANY shape the y-slab classes refuse (odd dimensions, nz % 4 != 0, rows that are not
+       // 16-byte multiples, unaligned pointers) whose x-slab of 1 / 2 / 4 / 8 fits a CTA; compress = one cluster per unit
+       FUSED_CLS_XS1 = 301, FUSED_CLS_XS2 = 302, FUSED_CLS_XS4 = 304, FUSED_CLS_XS8 = 308 };
 int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
 size_t fused_decode_table_entries(int fused_cls, int nx, int ny, int nz);   // int2 entries of a unit's segment table
@@ -33,6 +36,16 @@ int fused_decode_slabs_of(int fused_cls, int nx, int ny, int nz);         // y-s
 enum { BIG_SLAB_MASK = 0xfffff, BIG_CUBE128 = 1 << 20 };
 int big_run_key(int nx, int ny, int nz);
 bool fused_decode_needs_table(int fused_cls);               // slab-decoded classes cannot decode without one
+
+// x-slab classes (wc_xslab.cu)
+int xs_slabs(int nx, int ny, int nz);                       // 1 / 2 / 4 / 8 x-slabs, 0 = the box does not fit
+int xs_class_of(int nx, int ny, int nz);                    // FUSED_CLS_XS* or FUSED_CLS_NONE
+int xs_class_slabs(int fused_cls);                          // slabs of an x-slab class, 0 for every other class
+cudaError_t launch_xs_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states, const int* unit_list,
+                               int n_list, double one_minus_keep, const u64* global_key, int sm_count, cudaStream_t st,
+                               LaunchStats* ls);
+cudaError_t launch_xs_decompress(int fused_cls, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
+                                 int n_list, int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter);
 
 cudaError_t launch_fused_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states,
                                   const int* unit_list, int n_list, double one_minus_keep,
