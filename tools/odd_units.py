@@ -1,4 +1,6 @@
-"""Per-kernel breakdown on boxes that stay on the generic kernels (40x40x42: nz % 4 != 0)."""
+"""Per-kernel breakdown on boxes the y-slab classes refuse (40x40x42: nz % 4 != 0; odd dimensions): the x-slab classes of
+wc_xslab.cu (path 0) against the generic multi-kernel path (path 1).
+usage: python tools/odd_units.py [X Y Z [n_units [path]]]"""
 import sys
 sys.path.insert(0, '.')
 import __graft_entry__ as g
@@ -7,8 +9,13 @@ pkg = g.package()
 stream = torch.cuda.Stream()
 ctx = pkg.Context(0, stream=stream.cuda_stream)
 KEEP = 0.9990000128746033
-dims, n_units = (40, 40, 42), 16384
+a = [int(v) for v in sys.argv[1:]]
+dims = tuple(a[:3]) if len(a) >= 3 else (40, 40, 42)
 n = dims[0] * dims[1] * dims[2]
+n_units = a[3] if len(a) >= 4 and a[3] > 0 else max(1, (1 << 30) // (8 * n))      # ~1 GB of float64 input
+path = a[4] if len(a) >= 5 else 0
+ctx.set_path(path)
+print("dims", dims, "units", n_units, "path", path, "(0 = auto: x-slab classes, 1 = generic kernels)")
 gen = torch.Generator(device='cuda'); gen.manual_seed(1)
 x = torch.linspace(0, 50, n_units * n, device='cuda', dtype=torch.float64).sin_() * 100 + \
     torch.randn(n_units * n, device='cuda', dtype=torch.float64, generator=gen) * 0.05

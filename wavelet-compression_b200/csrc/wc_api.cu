@@ -123,11 +123,11 @@ struct DecCache {
 };
 // Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
 // stream), then the single-CTA kernels (second stream when both kinds are present).
-enum { FL_N = 14 };
+enum { FL_N = 15 };
 static const int FL_CLASS[FL_N] = {FUSED_CLS_CUBE64, FUSED_CLS_R8, FUSED_CLS_R4, FUSED_CLS_R2, FUSED_CLS_CUBE32,
                                     FUSED_CLS_R1, FUSED_CLS_CUBE16, FUSED_CLS_R1S, FUSED_CLS_CUBE8,
                                     FUSED_CLS_RBIG /* decompress only; compress plans never fill it */,
-                                    FUSED_CLS_XS1, FUSED_CLS_XS2, FUSED_CLS_XS4, FUSED_CLS_XS8 /* any shape: wc_xslab.cu */};
+                                    FUSED_CLS_XS1, FUSED_CLS_XS2, FUSED_CLS_XS4, FUSED_CLS_XS8, FUSED_CLS_XS1S /* any shape: wc_xslab.cu */};
 static_assert(sizeof(DecCache::fl_n) / sizeof(size_t) >= FL_N, "DecCache::fl_n");
 enum { FL_BIG = 9 };
 // One launch takes units of one launch key (slab count, 128^3 cube or not: big_run_key): the FUSED_CLS_RBIG list is kept

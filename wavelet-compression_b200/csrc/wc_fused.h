@@ -26,7 +26,8 @@ enum { FUSED_CLS_NONE = 0, FUSED_CLS_R1 = 1, FUSED_CLS_R1S = 2, FUSED_CLS_R8 = 8
        FUSED_CLS_RBIG = 200,    // decompress only: any number of y-slabs of <= 32768 cells (128^3 ...), one launch per slab count
        // x-slab classes (wc_xslab.cu): ANY shape the y-slab classes refuse (odd dimensions, nz % 4 != 0, rows that are not
        // 16-byte multiples, unaligned pointers) whose x-slab of 1 / 2 / 4 / 8 fits a CTA; compress = one cluster per unit
-       FUSED_CLS_XS1 = 301, FUSED_CLS_XS2 = 302, FUSED_CLS_XS4 = 304, FUSED_CLS_XS8 = 308 };
+       FUSED_CLS_XS1 = 301, FUSED_CLS_XS2 = 302, FUSED_CLS_XS4 = 304, FUSED_CLS_XS8 = 308,
+       FUSED_CLS_XS1S = 300 };  // one CTA, at most 8448 words of C: 128 threads, five CTAs per SM
 int  fused_class(int nx, int ny, int nz, int dtype, const void* device_ptr);
 int  fused_decode_class(int nx, int ny, int nz, int out_dtype, const void* out_device_ptr);
 size_t fused_decode_table_entries(int fused_cls, int nx, int ny, int nz);   // int2 entries of a unit's segment table

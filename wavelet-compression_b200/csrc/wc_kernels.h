@@ -18,7 +18,7 @@ struct UnitState;
 enum KernelId {
     KID_FORWARD_GENERIC, KID_ARGMAX_FLAT, KID_FINALIZE, KID_GLOBAL_KEY, KID_COUNT, KID_SCAN, KID_EMIT,
     KID_RLE_SUMS, KID_RLE_SCAN, KID_RLE_SCATTER, KID_INVERSE_GENERIC, KID_RMSE_TILES, KID_RMSE_FINAL,
-    KID_OFFSETS, KID_GATHER, KID_FUSED_C1, KID_FUSED_C8, KID_FUSED_C1S, KID_FUSED_C8S, KID_FUSED_D1, KID_FUSED_D8, KID_FUSED_D1S, KID_FUSED_D8S, KID_SEG_INDEX, KID_FUSED_C1T, KID_FUSED_C16, KID_FUSED_D1T, KID_FUSED_D16, KID_FUSED_C8C, KID_FUSED_D8C, KID_FUSED_C4, KID_FUSED_C2, KID_FUSED_D4, KID_FUSED_D2, KID_MINMAX_TILES, KID_MINMAX_FINAL, KID_SEG_INDEX2, KID_DEC_PREPARE, KID_PATCH_INPUTS, KID_STAGED_D1S, KID_FUSED_DBIG, KID_BIG_FORWARD, KID_BIG_PACK, KID_Q_HIST, KID_Q_PICK, KID_FUSED_D128, KID_XS_C1, KID_XS_C2, KID_XS_C4, KID_XS_C8, KID_XS_D, KID_N
+    KID_OFFSETS, KID_GATHER, KID_FUSED_C1, KID_FUSED_C8, KID_FUSED_C1S, KID_FUSED_C8S, KID_FUSED_D1, KID_FUSED_D8, KID_FUSED_D1S, KID_FUSED_D8S, KID_SEG_INDEX, KID_FUSED_C1T, KID_FUSED_C16, KID_FUSED_D1T, KID_FUSED_D16, KID_FUSED_C8C, KID_FUSED_D8C, KID_FUSED_C4, KID_FUSED_C2, KID_FUSED_D4, KID_FUSED_D2, KID_MINMAX_TILES, KID_MINMAX_FINAL, KID_SEG_INDEX2, KID_DEC_PREPARE, KID_PATCH_INPUTS, KID_STAGED_D1S, KID_FUSED_DBIG, KID_BIG_FORWARD, KID_BIG_PACK, KID_Q_HIST, KID_Q_PICK, KID_FUSED_D128, KID_XS_C1, KID_XS_C2, KID_XS_C4, KID_XS_C8, KID_XS_D, KID_XS_C1S, KID_XS_DS, KID_N
 };
 inline const char* kernel_name(int id) {
     static const char* n[KID_N] = {
@@ -32,7 +32,8 @@ inline const char* kernel_name(int id) {
         "k_fused_decompress<1,cube8>", "k_fused_compress<4>", "k_fused_compress<2>", "k_fused_decompress<4>",
         "k_fused_decompress<2>", "k_minmax_tiles", "k_minmax_final", "k_seg_index3", "k_dec_prepare",
         "k_patch_inputs", "k_staged_decompress<1,cube32>", "k_fused_decompress<slabs>", "k_big_forward", "k_big_pack", "k_q_hist", "k_q_pick", "k_fused_decompress<64,cube128>",
-        "k_xs_compress<1>", "k_xs_compress<2>", "k_xs_compress<4>", "k_xs_compress<8>", "k_xs_decompress" };
+        "k_xs_compress<1>", "k_xs_compress<2>", "k_xs_compress<4>", "k_xs_compress<8>", "k_xs_decompress",
+        "k_xs_compress<1,small>", "k_xs_decompress<small>" };
     return (id >= 0 && id < KID_N) ? n[id] : "?";
 }
 struct LaunchStats {

@@ -34,22 +34,29 @@ namespace cg = cooperative_groups;
 
 namespace wc {
 
-constexpr int XS_NT     = 512;
-constexpr int XS_NW     = XS_NT / 32;
-constexpr int XS_CWORDS = 56320;               // words of C per CTA (220 KB: one CTA per SM either way)
-constexpr int XS_MAXPL  = 272;                 // local planes per CTA: at most 2 * 128 + 1 (nx <= 256)
-constexpr int XS_PPT    = 8;                   // pairs per thread per tile of the decoder's block scan
-// shared memory layout (bytes)
-constexpr int XS_OFF_CNT  = XS_CWORDS * 4;                 // int[XS_MAXPL]   kept coefficients per local plane
-constexpr int XS_OFF_LAST = XS_OFF_CNT + XS_MAXPL * 4;     // int[XS_MAXPL]   flat index of the last kept one, or -1
-constexpr int XS_OFF_BASE = XS_OFF_LAST + XS_MAXPL * 4;    // int[XS_MAXPL]   pairs of the same range in front of the plane
-constexpr int XS_OFF_PREV = XS_OFF_BASE + XS_MAXPL * 4;    // int[XS_MAXPL]   last kept flat index of the range before it
-constexpr int XS_OFF_RED  = XS_OFF_PREV + XS_MAXPL * 4;    // u64[64]         block reductions
-constexpr int XS_OFF_X1   = XS_OFF_RED + 64 * 8;           // u64[2][2]       exchange 1: arg-max key, NaN-at-f=0
-constexpr int XS_OFF_X2   = XS_OFF_X1 + 32;                // int[2][4]       exchange 2: count / last of either range
-constexpr int XS_OFF_MISC = XS_OFF_X2 + 32;                // int[8]
-constexpr int XS_SMEM     = XS_OFF_MISC + 32;
-static_assert(XS_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
+// Two configurations: 512 threads and a coefficient array of 220 KB (one CTA per SM), and — for the units that fit 33 KB
+// (FUSED_CLS_XS1S: 16^3-sized boxes and smaller) — 128 threads with five CTAs per SM, which overlap each other's barriers
+// and load latencies the way the small-unit variants of the y-slab kernels do.
+constexpr int XS_CWORDS   = 56320;             // words of C per CTA, large configuration
+constexpr int XS_CWORDS_S = 8448;              // ... small configuration
+constexpr int XS_SEG      = 512;               // coefficients per segment: the unit of work of the packing phases
+constexpr int XS_MAXSEG   = 384;               // local segments: npl * ceil(YZ / 512) <= CWORDS / 512 + 257 (nx <= 256)
+constexpr int XS_PPT      = 8;                 // pairs per thread per tile of the decoder's block scan
+// shared memory layout (bytes) behind the CW words of C
+template <int CW>
+struct XSmem {
+    static constexpr int CNT   = CW * 4;                      // int[XS_MAXSEG]  kept coefficients per local segment
+    static constexpr int LAST  = CNT + XS_MAXSEG * 4;         // int[XS_MAXSEG]  flat index of the last kept one, or -1
+    static constexpr int BASE  = LAST + XS_MAXSEG * 4;        // int[XS_MAXSEG]  pairs of the same range in front of it
+    static constexpr int PREV  = BASE + XS_MAXSEG * 4;        // int[XS_MAXSEG]  last kept flat index of the range before it
+    static constexpr int RED   = PREV + XS_MAXSEG * 4;        // u64[64]         block reductions / scan scratch
+    static constexpr int X1    = RED + 64 * 8;                // u64[2][2]       exchange 1: arg-max key, NaN-at-f=0
+    static constexpr int X2    = X1 + 32;                     // int[2][4]       exchange 2: count / last of either range
+    static constexpr int X3    = X2 + 32;                     // u64[2]          exchange 3 (+M / -M ties): lowest flat index
+    static constexpr int MISC  = X3 + 16;                     // int[8]
+    static constexpr int TOTAL = MISC + 32;
+};
+static_assert(XSmem<XS_CWORDS>::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 __host__ __device__ inline int xs_plane_stride(int yz) { return (yz | 31) + 2; }
 
@@ -65,12 +72,18 @@ int xs_slabs(int nx, int ny, int nz) {
     }
     return 0;
 }
+static bool xs_fits_small(int nx, int ny, int nz) {
+    if (nx < 1 || ny < 1 || nz < 1 || nx > 256) return false;
+    const long long yz = (long long)ny * nz;
+    return yz <= XS_CWORDS_S && (long long)nx * xs_plane_stride((int)yz) <= XS_CWORDS_S;
+}
 
 struct XGeom {
     int X, Y, Z, hx, hy, hz, ox, oy, oz;
     int YZ, PS;
     int a0, nl, own1;      // this slab: first block column, block columns, owns the trailing plane x = X-1
     int npl;               // local planes: 2 * nl + own1
+    int spp;               // segments per plane: ceil(YZ / XS_SEG)
     __device__ __forceinline__ void init(int nx, int ny, int nz, int S, int rank) {
         X = nx; Y = ny; Z = nz;
         hx = nx >> 1; hy = ny >> 1; hz = nz >> 1;
@@ -82,55 +95,80 @@ struct XGeom {
         nl = min(hx, a0 + na) - a0;
         own1 = (ox && rank == S - 1) ? 1 : 0;
         npl = 2 * nl + own1;
+        spp = (YZ + XS_SEG - 1) / XS_SEG;
     }
     // global plane i' of local plane p (low planes, high planes, then the trailing plane)
     __device__ __forceinline__ int gplane(int p) const { return p < nl ? a0 + p : (p < 2 * nl ? hx + a0 + (p - nl) : X - 1); }
 };
 
-template <class T> __device__ __forceinline__ float xs_load(const void* base, size_t idx);
-template <> __device__ __forceinline__ float xs_load<double>(const void* base, size_t idx) {
-    return __double2float_rn(__ldg(static_cast<const double*>(base) + idx));      // src/preprocess.cpp:78
-}
-template <> __device__ __forceinline__ float xs_load<float>(const void* base, size_t idx) {
-    return __ldg(static_cast<const float*>(base) + idx);
-}
+// q / d by a magic multiply: exact while q * d < 2^32 (block and cell counts here stay below 2^17)
+__device__ __forceinline__ uint32_t xs_magic(uint32_t d) { return d <= 1 ? 0u : (0xffffffffu / d) + 1u; }
+__device__ __forceinline__ uint32_t xs_div(uint32_t q, uint32_t m) { return m ? __umulhi(q, m) : q; }
 
 // Phase A of one slab: every thread takes generalized blocks (al fastest, then b, then c): up to 2 x 2 x 2 cells, a single
-// cell wide along an axis whose trailing element it holds.  Coefficients go to C, the running arg-max key (make_key:
-// largest |c|, lowest flat index, NaNs skipped — std::max_element of src/compressor.cpp:212-215) stays in a register.
-template <class T, bool MM>
-__device__ __forceinline__ void xs_phase_a(const XGeom& g, const void* in, float* C, u64& key, float& vmn, float& vmx) {
+// cell wide along an axis whose trailing element it holds.  Coefficients go to C; the arg-max is tracked as two running float
+// maxima (max c, max -c; fmaxf skips NaNs as std::max_element's comparison does, src/compressor.cpp:212-215) — only an exact
+// +M == -M tie needs the flat index, and that is searched for in C afterwards (k_xs_compress, phase B).
+// Full blocks (all but the trailing planes) take a path without predicates: one 64-bit address per block, 32-bit offsets.
+template <class T> __device__ __forceinline__ float xs_ld(const T* p);
+template <> __device__ __forceinline__ float xs_ld<double>(const double* p) { return __double2float_rn(__ldg(p)); }   // src/preprocess.cpp:78
+template <> __device__ __forceinline__ float xs_ld<float>(const float* p) { return __ldg(p); }
+
+template <class T, bool MM, int NT>
+__device__ __forceinline__ void xs_phase_a(const XGeom& g, const void* in, float* C, float& bp, float& bn, float& vmn,
+                                           float& vmx) {
     const int nbx = g.nl + g.own1, nby = g.hy + g.oy, nbz = g.hz + g.oz;
     const int nblk = nbx * nby * nbz;
+    const uint32_t m_bx = xs_magic(nbx), m_by = xs_magic(nby);
+    const T* const src = static_cast<const T*>(in);
+    const int sy = g.X, sz = g.X * g.Y;                                  // element strides of the box
+    const int o_hx = g.nl * g.PS, o_hy = g.hy * g.Z, o_hz = g.hz;        // offsets of the high bands in C
 #pragma unroll 1
-    for (int q = threadIdx.x; q < nblk; q += XS_NT) {
-        const int al = q % nbx, t = q / nbx, b = t % nby, c = t / nby;
+    for (int q = threadIdx.x; q < nblk; q += NT) {
+        const int t = (int)xs_div(q, m_bx), al = q - t * nbx, c = (int)xs_div(t, m_by), b = t - c * nby;
         const bool wx = al < g.nl, wy = b < g.hy, wz = c < g.hz;
-        const int x0 = wx ? 2 * (g.a0 + al) : g.X - 1, y0 = wy ? 2 * b : g.Y - 1, z0 = wz ? 2 * c : g.Z - 1;
         float v[8];
+        if (wx && wy && wz) {
+            const T* p = src + ((size_t)(2 * c) * sz + (size_t)(2 * b) * sy + (size_t)(2 * (g.a0 + al)));
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const int xi = o & 1, yi = (o >> 1) & 1, zi = o >> 2;
-            const bool valid = (xi == 0 || wx) && (yi == 0 || wy) && (zi == 0 || wz);
-            v[o] = 0.f;
-            if (valid) {
-                v[o] = xs_load<T>(in, ((size_t)(z0 + zi) * g.Y + (size_t)(y0 + yi)) * g.X + (size_t)(x0 + xi));
-                if (MM) { vmn = fminf(vmn, v[o]); vmx = fmaxf(vmx, v[o]); }
+            for (int o = 0; o < 8; ++o) v[o] = xs_ld<T>(p + ((o >> 2) * sz + ((o >> 1) & 1) * sy + (o & 1)));
+            if (MM) {
+#pragma unroll
+                for (int o = 0; o < 8; ++o) { vmn = fminf(vmn, v[o]); vmx = fmaxf(vmx, v[o]); }
             }
-        }
-        haar_block_forward(v, wx, wy, wz);
-        const int pl0 = wx ? al : 2 * g.nl, pl1 = g.nl + al;           // local planes of the low / high x band
-        const int gi0 = wx ? g.a0 + al : g.X - 1, gi1 = g.hx + g.a0 + al;
-        const int j0 = wy ? b : g.Y - 1, j1 = g.hy + b, k0 = wz ? c : g.Z - 1, k1 = g.hz + c;
+            haar_block_forward_full(v);
+            float* cd = C + al * g.PS + b * g.Z + c;
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const int sx = o & 1, sy = (o >> 1) & 1, sz = o >> 2;
-            const bool valid = (sx == 0 || wx) && (sy == 0 || wy) && (sz == 0 || wz);
-            if (valid) {
-                const int j = sy ? j1 : j0, k = sz ? k1 : k0;
-                C[(sx ? pl1 : pl0) * g.PS + j * g.Z + k] = v[o];
-                const uint32_t f = (uint32_t)(((sx ? gi1 : gi0) * g.Y + j) * g.Z + k);
-                key = max_u64(key, make_key(v[o], f));
+            for (int o = 0; o < 8; o += 2) {
+                cd[((o >> 1) & 1) * o_hy + (o >> 2) * o_hz]        = v[o];
+                cd[o_hx + ((o >> 1) & 1) * o_hy + (o >> 2) * o_hz] = v[o + 1];
+                bp = fmaxf(fmaxf(bp, v[o]), v[o + 1]);
+                bn = fmaxf(fmaxf(bn, -v[o]), -v[o + 1]);
+            }
+        } else {
+            const int x0 = wx ? 2 * (g.a0 + al) : g.X - 1, y0 = wy ? 2 * b : g.Y - 1, z0 = wz ? 2 * c : g.Z - 1;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const int xi = o & 1, yi = (o >> 1) & 1, zi = o >> 2;
+                const bool valid = (xi == 0 || wx) && (yi == 0 || wy) && (zi == 0 || wz);
+                v[o] = 0.f;
+                if (valid) {
+                    v[o] = xs_ld<T>(src + ((size_t)(z0 + zi) * sz + (size_t)(y0 + yi) * sy + (size_t)(x0 + xi)));
+                    if (MM) { vmn = fminf(vmn, v[o]); vmx = fmaxf(vmx, v[o]); }
+                }
+            }
+            haar_block_forward(v, wx, wy, wz);
+            const int pl0 = wx ? al : 2 * g.nl, pl1 = g.nl + al;           // local planes of the low / high x band
+            const int j0 = wy ? b : g.Y - 1, j1 = g.hy + b, k0 = wz ? c : g.Z - 1, k1 = g.hz + c;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const int sx = o & 1, sy2 = (o >> 1) & 1, sz2 = o >> 2;
+                const bool valid = (sx == 0 || wx) && (sy2 == 0 || wy) && (sz2 == 0 || wz);
+                if (valid) {
+                    C[(sx ? pl1 : pl0) * g.PS + (sy2 ? j1 : j0) * g.Z + (sz2 ? k1 : k0)] = v[o];
+                    bp = fmaxf(bp, v[o]);
+                    bn = fmaxf(bn, -v[o]);
+                }
             }
         }
     }
@@ -144,18 +182,24 @@ __device__ __forceinline__ uint32_t xs_order_code(float f) {      // monotone fl
 // ---- compress ------------------------------------------------------------------------------------------------------
 // One cluster of S CTAs per unit, units taken round-robin by the clusters.  mode: FUSED_FULL / FUSED_KEYS_ONLY /
 // FUSED_GIVEN_THRESH, FUSED_MINMAX or-ed in (wc_fused.h), with the meaning they have for k_fused_compress.
-__global__ void __launch_bounds__(XS_NT, 1)
+// The packing phases work on SEGMENTS of at most XS_SEG consecutive coefficients of one plane (a warp per segment at a
+// time): with whole planes as the unit of work a 63^3 slab had 9 work items of 3969 coefficients for 16 warps.
+template <int NT, int CW, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states, const int* __restrict__ unit_list,
               int n_list, double one_minus_keep, const u64* __restrict__ global_key, int mode_flags) {
+    typedef XSmem<CW> SM;
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     float* const C      = reinterpret_cast<float*>(smem);
-    int* const   s_cnt  = reinterpret_cast<int*>(smem + XS_OFF_CNT);
-    int* const   s_last = reinterpret_cast<int*>(smem + XS_OFF_LAST);
-    int* const   s_base = reinterpret_cast<int*>(smem + XS_OFF_BASE);
-    int* const   s_prev = reinterpret_cast<int*>(smem + XS_OFF_PREV);
-    u64* const   s_red  = reinterpret_cast<u64*>(smem + XS_OFF_RED);
-    u64* const   s_x1   = reinterpret_cast<u64*>(smem + XS_OFF_X1);
-    int* const   s_x2   = reinterpret_cast<int*>(smem + XS_OFF_X2);
+    int* const   s_cnt  = reinterpret_cast<int*>(smem + SM::CNT);
+    int* const   s_last = reinterpret_cast<int*>(smem + SM::LAST);
+    int* const   s_base = reinterpret_cast<int*>(smem + SM::BASE);
+    int* const   s_prev = reinterpret_cast<int*>(smem + SM::PREV);
+    u64* const   s_red  = reinterpret_cast<u64*>(smem + SM::RED);
+    u64* const   s_x1   = reinterpret_cast<u64*>(smem + SM::X1);
+    int* const   s_x2   = reinterpret_cast<int*>(smem + SM::X2);
+    u64* const   s_x3   = reinterpret_cast<u64*>(smem + SM::X3);      // [2]  exchange 3 (ties only)
 
     cg::cluster_group cluster = cg::this_cluster();
     const int S    = (int)cluster.num_blocks();
@@ -175,16 +219,23 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
         g.init(u.nx, u.ny, u.nz, S, rank);
 
         // ---------------- phase A ----------------
-        u64   key = 0ull;
+        float bp = 0.f, bn = 0.f;              // running max of +c and of -c
         float vmn = __int_as_float(0x7f800000), vmx = __int_as_float(0xff800000);
         if (u.dtype == WC_F64) {
-            if (mm) xs_phase_a<double, true>(g, u.in, C, key, vmn, vmx);
-            else    xs_phase_a<double, false>(g, u.in, C, key, vmn, vmx);
+            if (mm) xs_phase_a<double, true, NT>(g, u.in, C, bp, bn, vmn, vmx);
+            else    xs_phase_a<double, false, NT>(g, u.in, C, bp, bn, vmn, vmx);
         } else {
-            if (mm) xs_phase_a<float, true>(g, u.in, C, key, vmn, vmx);
-            else    xs_phase_a<float, false>(g, u.in, C, key, vmn, vmx);
+            if (mm) xs_phase_a<float, true, NT>(g, u.in, C, bp, bn, vmn, vmx);
+            else    xs_phase_a<float, false, NT>(g, u.in, C, bp, bn, vmn, vmx);
         }
-        key = warp_max_u64(key);
+        // both maxima are >= 0 (a -0 cannot win against the initial +0; masked all the same): the halves reduce separately
+        u64 key = ((u64)(__float_as_uint(bp) & 0x7fffffffu) << 32) | (u64)(__float_as_uint(bn) & 0x7fffffffu);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const u64 x = __shfl_xor_sync(0xffffffffu, key, o);
+            const uint32_t hi = max((uint32_t)(key >> 32), (uint32_t)(x >> 32)), lo = max((uint32_t)key, (uint32_t)x);
+            key = ((u64)hi << 32) | lo;        // non-negative floats order like their bit patterns
+        }
         if (mm) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -200,8 +251,13 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
 
         // ---------------- phase B: the unit's arg-max key over the cluster, the threshold ----------------
         if (warp == 0) {
-            u64 k = lane < XS_NW ? s_red[lane] : 0ull;
-            k = warp_max_u64(k);
+            u64 k = lane < NW ? s_red[lane] : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const u64 x = __shfl_xor_sync(0xffffffffu, k, o);
+                const uint32_t hi = max((uint32_t)(k >> 32), (uint32_t)(x >> 32)), lo = max((uint32_t)k, (uint32_t)x);
+                k = ((u64)hi << 32) | lo;
+            }
             if (lane == 0) {
                 s_x1[par * 2]     = k;
                 // the coefficient at f = 0 sits in rank 0's first local plane (the trailing plane when X == 1)
@@ -209,7 +265,7 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
             }
             __syncwarp();      // explicit reconvergence behind one-lane regions that precede warp collectives
             if (mm) {
-                const u64 x = lane < XS_NW ? s_red[32 + lane] : (((u64)0x7f800000u << 32) | 0xff800000u);
+                const u64 x = lane < NW ? s_red[32 + lane] : (((u64)0x7f800000u << 32) | 0xff800000u);
                 float a = __uint_as_float((uint32_t)(x >> 32)), b = __uint_as_float((uint32_t)x);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -226,10 +282,58 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
         cluster.sync();                        // exchange 1 (for S == 1 a CTA barrier)
         u64  ukey = 0ull;
         bool first_nan = false;
-        for (int r = 0; r < S; ++r) {
-            const u64* px = cluster.map_shared_rank(s_x1 + par * 2, r);
-            ukey = max_u64(ukey, px[0]);
-            first_nan = first_nan || px[1] != 0ull;
+        {
+            uint32_t mp = 0u, mn = 0u;
+            for (int r = 0; r < S; ++r) {
+                const u64* px = cluster.map_shared_rank(s_x1 + par * 2, r);
+                const u64 x = px[0];
+                mp = max(mp, (uint32_t)(x >> 32)); mn = max(mn, (uint32_t)x);
+                first_nan = first_nan || px[1] != 0ull;
+            }
+            const uint32_t mb = max(mp, mn);
+            uint32_t sign = mn > mp ? 1u : 0u;
+            if (mp == mn && mb != 0u && !first_nan && mode != FUSED_GIVEN_THRESH) {
+                // +M and -M tie: the FIRST one in f order decides (std::max_element) -> lowest flat index with |c| == M
+                // over the cluster; every CTA takes this branch together (mp, mn are cluster-wide values)
+                const float M = __uint_as_float(mb);
+                u64 best = ~0ull;
+                for (int p = warp; p < g.npl; p += NW) {
+                    const float* cs = C + p * g.PS;
+                    const uint32_t f0 = (uint32_t)(g.gplane(p) * g.YZ);
+                    for (int w = lane; w < g.YZ; w += 32) {
+                        const float c = cs[w];
+                        if (fabsf(c) == M) {
+                            const u64 cand = ((u64)(f0 + (uint32_t)w) << 1) | (u64)(__float_as_uint(c) >> 31);
+                            best = cand < best ? cand : best;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const u64 x = __shfl_xor_sync(0xffffffffu, best, o);
+                    best = x < best ? x : best;
+                }
+                __syncthreads();               // s_red reuse
+                if (lane == 0) s_red[warp] = best;
+                __syncthreads();
+                if (warp == 0) {
+                    best = lane < NW ? s_red[lane] : ~0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const u64 x = __shfl_xor_sync(0xffffffffu, best, o);
+                        best = x < best ? x : best;
+                    }
+                    if (lane == 0) s_x3[par] = best;
+                }
+                cluster.sync();
+                best = ~0ull;
+                for (int r = 0; r < S; ++r) {
+                    const u64 x = *cluster.map_shared_rank(s_x3 + par, r);
+                    best = x < best ? x : best;
+                }
+                sign = (uint32_t)(best & 1ull);
+            }
+            ukey = ((u64)mb << 32) | 2ull | (u64)sign;      // the canonical key of k_fused_compress
         }
         float tf;
         if (mode == FUSED_GIVEN_THRESH) {
@@ -248,35 +352,47 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
             continue;
         }
 
-        // ---------------- phase C1: kept count and last kept coefficient of every local plane ----------------
+        // ---------------- phase C1: kept count and last kept coefficient of every local segment ----------------
+        const int nsl = g.npl * g.spp;         // local segments, in flat order: e = p * spp + q
 #pragma unroll 1
-        for (int p = warp; p < g.npl; p += XS_NW) {
+        for (int e = warp; e < nsl; e += NW) {
+            const int p = e / g.spp, w_lo = (e - p * g.spp) * XS_SEG, w_hi = min(g.YZ, w_lo + XS_SEG);
             const float* cs = C + p * g.PS;
-            int cnt = 0, last = -1;
-            for (int w0 = 0; w0 < g.YZ; w0 += 32) {
-                const int  w  = w0 + lane;
-                const bool kf = w < g.YZ && keep_coef(cs[w], tf);
-                const uint32_t bal = __ballot_sync(0xffffffffu, kf);
-                if (bal) { cnt += __popc(bal); last = w0 + 31 - __clz(bal); }
+            int cnt = 0, lw = 0;
+            uint32_t lb = 0u;
+            // 128 coefficients per trip: four independent loads and ballots (reads past w_hi stay inside the CTA's
+            // shared memory and are masked out)
+#pragma unroll 1
+            for (int w0 = w_lo; w0 < w_hi; w0 += 128) {
+                uint32_t bal[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int w = w0 + 32 * j + lane;
+                    bal[j] = __ballot_sync(0xffffffffu, w < w_hi && keep_coef(cs[w], tf));
+                }
+                cnt += __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]) + __popc(bal[3]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (bal[j]) { lb = bal[j]; lw = w0 + 32 * j; }
             }
             if (lane == 0) {
-                s_cnt[p]  = cnt;
-                s_last[p] = last >= 0 ? g.gplane(p) * g.YZ + last : -1;
+                s_cnt[e]  = cnt;
+                s_last[e] = lb ? g.gplane(p) * g.YZ + lw + 31 - __clz(lb) : -1;
             }
             __syncwarp();
         }
         __syncthreads();
-        // scan inside either range (low planes, high planes + trailing plane): pairs in front of every plane, last kept
-        // flat index in front of it; the totals go to the cluster
+        // scan inside either range (low planes; high planes + trailing plane): pairs in front of every segment, last
+        // kept flat index in front of it; the totals go to the cluster
         if (warp == 0) {
             int tot[2], lastf[2];
 #pragma unroll
             for (int grp = 0; grp < 2; ++grp) {
-                const int lo = grp ? g.nl : 0, hi = grp ? g.npl : g.nl;
+                const int lo = grp ? g.nl * g.spp : 0, hi = grp ? nsl : g.nl * g.spp;
                 int carry = 0, cmax = -1;
                 for (int base = lo; base < hi; base += 32) {
-                    const int p = base + lane;
-                    const int c = p < hi ? s_cnt[p] : 0, l = p < hi ? s_last[p] : -1;
+                    const int e = base + lane;
+                    const int c = e < hi ? s_cnt[e] : 0, l = e < hi ? s_last[e] : -1;
                     int isum = c, imax = l;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -285,7 +401,7 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                     }
                     int emax = __shfl_up_sync(0xffffffffu, imax, 1);
                     if (lane == 0) emax = -1;
-                    if (p < hi) { s_base[p] = carry + isum - c; s_prev[p] = max(cmax, emax); }
+                    if (e < hi) { s_base[e] = carry + isum - c; s_prev[e] = max(cmax, emax); }
                     __syncwarp();
                     carry += __shfl_sync(0xffffffffu, isum, 31);
                     cmax = max(cmax, __shfl_sync(0xffffffffu, imax, 31));
@@ -317,45 +433,65 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
             if (tab) tab[g.X] = make_int2(K, last_all);
         }
 
-        // ---------------- phase C2: emit (run, value) pairs, a warp per plane ----------------
+        // ---------------- phase C2: emit (run, value) pairs, a warp per segment ----------------
         int2* const out = reinterpret_cast<int2*>(u.out);
 #pragma unroll 1
-        for (int p = warp; p < g.npl; p += XS_NW) {
+        for (int e = warp; e < nsl; e += NW) {
+            const int p = e / g.spp, q = e - p * g.spp, w_lo = q * XS_SEG, w_hi = min(g.YZ, w_lo + XS_SEG);
             const bool hi_grp = p >= g.nl;
-            int pos  = (hi_grp ? base_hi : base_lo) + s_base[p];
-            int prev = max(hi_grp ? prev_hi : prev_lo, s_prev[p]);
+            int pos  = (hi_grp ? base_hi : base_lo) + s_base[e];
+            int prev = max(hi_grp ? prev_hi : prev_lo, s_prev[e]);
             const int fstart = g.gplane(p) * g.YZ;
-            if (tab && lane == 0) tab[g.gplane(p)] = make_int2(pos, prev);
+            if (tab && q == 0 && lane == 0) tab[g.gplane(p)] = make_int2(pos, prev);
             __syncwarp();
-            if (s_cnt[p] == 0) continue;
+            const int scnt = s_cnt[e];
+            if (scnt == 0) continue;
             const float* cs = C + p * g.PS;
-            for (int w0 = 0; w0 < g.YZ; w0 += 32) {
-                const int   w  = w0 + lane;
-                const float c  = w < g.YZ ? cs[w] : 0.f;
-                const bool  kf = w < g.YZ && keep_coef(c, tf);
-                const uint32_t bal = __ballot_sync(0xffffffffu, kf);
-                if (bal) {
-                    const uint32_t lower = bal & lt;
-                    // flat index of the previous kept coefficient: a lower lane of this group, or the carried one
-                    const int pf = lower ? fstart + w0 + 31 - __clz(lower) : prev;
-                    if (kf) out[pos + __popc(lower)] = make_int2(fstart + w - pf - 1, __float_as_int(c));
-                    pos += __popc(bal);
-                    prev = fstart + w0 + 31 - __clz(bal);
+            if (scnt == w_hi - w_lo) {
+                // every coefficient kept (e.g. a negative max, SURVEY.md D3'): runs are 0, ranks are w - w_lo
+                for (int w = w_lo + lane; w < w_hi; w += 32)
+                    out[pos + (w - w_lo)] = make_int2(w == w_lo ? fstart + w_lo - prev - 1 : 0, __float_as_int(cs[w]));
+                continue;
+            }
+#pragma unroll 1
+            for (int w0 = w_lo; w0 < w_hi; w0 += 128) {
+                float    c[4];
+                bool     kf[4];
+                uint32_t bal[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int w = w0 + 32 * j + lane;
+                    c[j]   = cs[w];
+                    kf[j]  = w < w_hi && keep_coef(c[j], tf);
+                    bal[j] = __ballot_sync(0xffffffffu, kf[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (bal[j]) {                                      // warp-uniform
+                        const uint32_t lower = bal[j] & lt;
+                        const int f0 = fstart + w0 + 32 * j;           // flat index of lane 0's coefficient
+                        // previous kept coefficient: a lower lane of this group, or the carried one
+                        const int pf = lower ? f0 + 31 - __clz(lower) : prev;
+                        if (kf[j]) out[pos + __popc(lower)] = make_int2(f0 + lane - pf - 1, __float_as_int(c[j]));
+                        pos += __popc(bal[j]);
+                        prev = f0 + 31 - __clz(bal[j]);
+                    }
                 }
             }
         }
-        __syncthreads();                       // C and the plane arrays are rewritten by the next unit
+        __syncthreads();                       // C and the segment arrays are rewritten by the next unit
     }
     cluster.sync();                            // no CTA may exit while a peer can still read its shared memory
 }
 
 // ---- decompress ----------------------------------------------------------------------------------------------------
-// Block-wide exclusive prefix of run + 1 over one tile of XS_NT * XS_PPT pairs (saturating at 2^30, so corrupt streams
+// Block-wide exclusive prefix of run + 1 over one tile of NT * XS_PPT pairs (saturating at 2^30, so corrupt streams
 // cannot wrap; negative runs are flagged, count as 0 and are skipped by the caller).  wt: 32 words per tile parity.
 __device__ __forceinline__ uint32_t xs_sat_add(uint32_t a, uint32_t b) {
     const uint32_t s = a + b;
     return s > 0x40000000u ? 0x40000000u : s;
 }
+template <int NT>
 __device__ __forceinline__ uint32_t xs_tile_scan(const int2 (&pr)[XS_PPT], int nvalid, uint32_t* wt, bool& bad,
                                                  uint32_t& ttot) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -374,7 +510,7 @@ __device__ __forceinline__ uint32_t xs_tile_scan(const int2 (&pr)[XS_PPT], int n
     }
     if (lane == 31) wt[warp] = inc;
     __syncthreads();
-    uint32_t winc = lane < XS_NW ? wt[lane] : 0u;
+    uint32_t winc = lane < NT / 32 ? wt[lane] : 0u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
@@ -391,17 +527,18 @@ __device__ __forceinline__ uint32_t xs_tile_scan(const int2 (&pr)[XS_PPT], int n
 // rle_decode (src/decompressor.cpp:14-30) of the pairs [pb, pe) whose first run starts at flat index `cur`: every pair
 // that lands in [f0, f1) goes to C (plane (f - f0) / YZ + pbase); pairs past f1 — and with them every later one, flat
 // indices only grow — are dropped, which for f1 <= total is the reference's `if (idx < total)`.
+template <int NT>
 __device__ __forceinline__ void xs_decode_range(const int2* __restrict__ pairs, int pb, int pe, uint32_t cur, uint32_t f0,
                                                 uint32_t f1, int pbase, const XGeom& g, float* C, uint32_t* s_wt, int& tile,
                                                 bool& bad) {
 #pragma unroll 1
-    for (int p0 = pb; p0 < pe; p0 += XS_NT * XS_PPT, ++tile) {
+    for (int p0 = pb; p0 < pe; p0 += NT * XS_PPT, ++tile) {
         const int p = p0 + (int)threadIdx.x * XS_PPT;
         int2 pr[XS_PPT];
 #pragma unroll
         for (int j = 0; j < XS_PPT; ++j) pr[j] = (p + j < pe) ? __ldg(pairs + p + j) : make_int2(0, 0);
         uint32_t ttot;
-        uint32_t rp = xs_sat_add(cur, xs_tile_scan(pr, pe - p, s_wt + (tile & 1) * 32, bad, ttot));
+        uint32_t rp = xs_sat_add(cur, xs_tile_scan<NT>(pr, pe - p, s_wt + (tile & 1) * 32, bad, ttot));
 #pragma unroll
         for (int j = 0; j < XS_PPT; ++j) {
             if (p + j < pe && pr[j].x >= 0) {
@@ -418,47 +555,45 @@ __device__ __forceinline__ void xs_decode_range(const int2* __restrict__ pairs, 
     }
 }
 
-template <class T>
+template <class T, int NT>
 __device__ __forceinline__ void xs_inverse_store(const XGeom& g, const float* C, T* __restrict__ out) {
     const int tid = threadIdx.x;
     // full 2 x 2 x 2 blocks: X, then Y, then Z (src/decompressor.cpp:90-156)
     const int nblk = g.nl * g.hy * g.hz;
+    const uint32_t m_nl = xs_magic(g.nl), m_hy = xs_magic(g.hy);
+    const int sy = g.X, sz = g.X * g.Y;                                  // element strides of the box
+    const int o_hx = g.nl * g.PS, o_hy = g.hy * g.Z, o_hz = g.hz;        // offsets of the high bands in C
 #pragma unroll 1
-    for (int q = tid; q < nblk; q += XS_NT) {
-        const int al = q % g.nl, t = q / g.nl, b = t % g.hy, c = t / g.hy;
+    for (int q = tid; q < nblk; q += NT) {
+        const int t = (int)xs_div(q, m_nl), al = q - t * g.nl, c = (int)xs_div(t, m_hy), b = t - c * g.hy;
         float v[8];
+        const float* cd = C + al * g.PS + b * g.Z + c;
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const int sx = o & 1, sy = (o >> 1) & 1, sz = o >> 2;
-            v[o] = C[(sx ? g.nl + al : al) * g.PS + (sy ? g.hy + b : b) * g.Z + (sz ? g.hz + c : c)];
-        }
+        for (int o = 0; o < 8; ++o) v[o] = cd[(o & 1) * o_hx + ((o >> 1) & 1) * o_hy + (o >> 2) * o_hz];
         haar_block_inverse_full(v);
-        const int x0 = 2 * (g.a0 + al);
+        T* po = out + ((size_t)(2 * c) * sz + (size_t)(2 * b) * sy + (size_t)(2 * (g.a0 + al)));
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const int xi = o & 1, yi = (o >> 1) & 1, zi = o >> 2;
-            out[((size_t)(2 * c + zi) * g.Y + (size_t)(2 * b + yi)) * g.X + (size_t)(x0 + xi)] = (T)v[o];
-        }
+        for (int o = 0; o < 8; ++o) po[(o >> 2) * sz + ((o >> 1) & 1) * sy + (o & 1)] = (T)v[o];
     }
     // trailing cells of odd axes: the inverse leaves them at +0
     const int nxs = 2 * g.nl + g.own1;                    // x positions of this slab (incl. the trailing plane)
     auto xpos = [&](int i) { return i < 2 * g.nl ? 2 * g.a0 + i : g.X - 1; };
     if (g.oz) {
-        for (int q = tid; q < nxs * g.Y; q += XS_NT) {
+        for (int q = tid; q < nxs * g.Y; q += NT) {
             const int i = q % nxs, y = q / nxs;
             out[((size_t)(g.Z - 1) * g.Y + (size_t)y) * g.X + (size_t)xpos(i)] = (T)0;
         }
     }
     if (g.oy) {
         const int nz2 = g.Z - g.oz;
-        for (int q = tid; q < nxs * nz2; q += XS_NT) {
+        for (int q = tid; q < nxs * nz2; q += NT) {
             const int i = q % nxs, z = q / nxs;
             out[((size_t)z * g.Y + (size_t)(g.Y - 1)) * g.X + (size_t)xpos(i)] = (T)0;
         }
     }
     if (g.own1) {
         const int ny2 = g.Y - g.oy, nz2 = g.Z - g.oz;
-        for (int q = tid; q < ny2 * nz2; q += XS_NT) {
+        for (int q = tid; q < ny2 * nz2; q += NT) {
             const int y = q % ny2, z = q / ny2;
             out[((size_t)z * g.Y + (size_t)y) * g.X + (size_t)(g.X - 1)] = (T)0;
         }
@@ -466,13 +601,14 @@ __device__ __forceinline__ void xs_inverse_store(const XGeom& g, const float* C,
 }
 
 // Work item = (unit, x-slab r of S); one CTA per item, items handed out through a global counter.
-__global__ void __launch_bounds__(XS_NT, 1)
+template <int NT, int CW, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_xs_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict__ inv, const int* __restrict__ unit_list,
                 int n_list, int S, int* __restrict__ err, int* __restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* const    C      = reinterpret_cast<float*>(smem);
-    uint32_t* const s_wt   = reinterpret_cast<uint32_t*>(smem + XS_OFF_RED);      // [2][32]
-    int* const      s_item = reinterpret_cast<int*>(smem + XS_OFF_MISC);
+    uint32_t* const s_wt   = reinterpret_cast<uint32_t*>(smem + CW * 4);          // [2][32]
+    int* const      s_item = reinterpret_cast<int*>(smem + CW * 4 + 256);
     const int tid = threadIdx.x;
     const int n_items = n_list * S;
     bool bad = false;
@@ -488,7 +624,7 @@ k_xs_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict
         g.init(iu.nx, iu.ny, iu.nz, S, rank);
         if (g.npl > 0) {
             // the slab's low and high planes start out zero (src/decompressor.cpp:16)
-            for (int i = tid; i < 2 * g.nl * g.PS; i += XS_NT) C[i] = 0.f;
+            for (int i = tid; i < 2 * g.nl * g.PS; i += NT) C[i] = 0.f;
             __syncthreads();
             const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
             int K = du.npairs_dev ? *du.npairs_dev : du.npairs;
@@ -496,20 +632,20 @@ k_xs_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict
             int tile = 0;
             if (g.nl > 0) {
                 if (S == 1) {
-                    xs_decode_range(pairs, 0, K, 0u, 0u, (uint32_t)(2 * g.hx * g.YZ), 0, g, C, s_wt, tile, bad);
+                    xs_decode_range<NT>(pairs, 0, K, 0u, 0u, (uint32_t)(2 * g.hx * g.YZ), 0, g, C, s_wt, tile, bad);
                 } else {
                     const int2* tab = reinterpret_cast<const int2*>(du.coef);
                     const int2 l0 = tab[g.a0], l1 = tab[g.a0 + g.nl];
                     const int2 h0 = tab[g.hx + g.a0], h1 = tab[g.hx + g.a0 + g.nl];
-                    xs_decode_range(pairs, max(0, l0.x), min(K, l1.x), (uint32_t)(l0.y + 1), (uint32_t)(g.a0 * g.YZ),
+                    xs_decode_range<NT>(pairs, max(0, l0.x), min(K, l1.x), (uint32_t)(l0.y + 1), (uint32_t)(g.a0 * g.YZ),
                                     (uint32_t)((g.a0 + g.nl) * g.YZ), 0, g, C, s_wt, tile, bad);
-                    xs_decode_range(pairs, max(0, h0.x), min(K, h1.x), (uint32_t)(h0.y + 1), (uint32_t)((g.hx + g.a0) * g.YZ),
+                    xs_decode_range<NT>(pairs, max(0, h0.x), min(K, h1.x), (uint32_t)(h0.y + 1), (uint32_t)((g.hx + g.a0) * g.YZ),
                                     (uint32_t)((g.hx + g.a0 + g.nl) * g.YZ), g.nl, g, C, s_wt, tile, bad);
                 }
             }
             __syncthreads();
-            if (iu.dtype == WC_F64) xs_inverse_store<double>(g, C, static_cast<double*>(iu.out));
-            else                    xs_inverse_store<float>(g, C, static_cast<float*>(iu.out));
+            if (iu.dtype == WC_F64) xs_inverse_store<double, NT>(g, C, static_cast<double*>(iu.out));
+            else                    xs_inverse_store<float, NT>(g, C, static_cast<float*>(iu.out));
         }
         __syncthreads();                       // C and s_item are rewritten by the next item
     }
@@ -519,6 +655,7 @@ k_xs_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict
 // ---- launchers -----------------------------------------------------------------------------------------------------
 int xs_class_slabs(int fused_cls) {
     switch (fused_cls) {
+    case FUSED_CLS_XS1S:
     case FUSED_CLS_XS1: return 1;
     case FUSED_CLS_XS2: return 2;
     case FUSED_CLS_XS4: return 4;
@@ -528,7 +665,7 @@ int xs_class_slabs(int fused_cls) {
 }
 int xs_class_of(int nx, int ny, int nz) {
     switch (xs_slabs(nx, ny, nz)) {
-    case 1: return FUSED_CLS_XS1;
+    case 1: return xs_fits_small(nx, ny, nz) ? FUSED_CLS_XS1S : FUSED_CLS_XS1;
     case 2: return FUSED_CLS_XS2;
     case 4: return FUSED_CLS_XS4;
     case 8: return FUSED_CLS_XS8;
@@ -536,18 +673,21 @@ int xs_class_of(int nx, int ny, int nz) {
     return FUSED_CLS_NONE;
 }
 
-cudaError_t launch_xs_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states, const int* unit_list,
+constexpr int XS_NT = 512, XS_NT_S = 128, XS_MINB_S = 5;
+constexpr int XS_DSMEM   = XS_CWORDS * 4 + 512;        // decompress: C + scan scratch
+constexpr int XS_DSMEM_S = XS_CWORDS_S * 4 + 512;
+
+template <int NT, int CW, int MINB>
+static cudaError_t launch_xs_c(int kid, int S, int mode, const UnitDev* units, UnitState* states, const int* unit_list,
                                int n_list, double one_minus_keep, const u64* global_key, int sm_count, cudaStream_t st,
                                LaunchStats* ls) {
-    const int S = xs_class_slabs(fused_cls);
-    if (S == 0) return cudaErrorInvalidValue;
-    if (n_list <= 0) return cudaSuccess;
-    const int kid = S == 1 ? KID_XS_C1 : S == 2 ? KID_XS_C2 : S == 4 ? KID_XS_C4 : KID_XS_C8;
-    cudaError_t e = cudaFuncSetAttribute(k_xs_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, XS_SMEM);
+    auto kern = k_xs_compress<NT, CW, MINB>;
+    constexpr int smem = XSmem<CW>::TOTAL;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim         = dim3(XS_NT);
-    cfg.dynamicSmemBytes = XS_SMEM;
+    cfg.blockDim         = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream           = st;
     cudaLaunchAttribute attr[1];
     attr[0].id               = cudaLaunchAttributeClusterDimension;
@@ -560,7 +700,7 @@ cudaError_t launch_xs_compress(int fused_cls, int mode, const UnitDev* units, Un
     if (max_clusters == 0) {
         cfg.gridDim = dim3(S * sm_count);
         int nc = 0;
-        e = cudaOccupancyMaxActiveClusters(&nc, k_xs_compress, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
         if (e != cudaSuccess) return e;
         if (nc < 1) return cudaErrorLaunchOutOfResources;
         max_clusters = nc;
@@ -568,9 +708,43 @@ cudaError_t launch_xs_compress(int fused_cls, int mode, const UnitDev* units, Un
     const int nc = max_clusters < n_list ? max_clusters : n_list;
     cfg.gridDim = dim3(nc * S);
     ls->begin(kid, st);
-    e = cudaLaunchKernelEx(&cfg, k_xs_compress, units, states, unit_list, n_list, one_minus_keep, global_key, mode);
+    e = cudaLaunchKernelEx(&cfg, kern, units, states, unit_list, n_list, one_minus_keep, global_key, mode);
     ls->end(st);
     if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xs_compress(int fused_cls, int mode, const UnitDev* units, UnitState* states, const int* unit_list,
+                               int n_list, double one_minus_keep, const u64* global_key, int sm_count, cudaStream_t st,
+                               LaunchStats* ls) {
+    const int S = xs_class_slabs(fused_cls);
+    if (S == 0) return cudaErrorInvalidValue;
+    if (n_list <= 0) return cudaSuccess;
+    if (fused_cls == FUSED_CLS_XS1S)
+        return launch_xs_c<XS_NT_S, XS_CWORDS_S, XS_MINB_S>(KID_XS_C1S, 1, mode, units, states, unit_list, n_list,
+                                                            one_minus_keep, global_key, sm_count, st, ls);
+    const int kid = S == 1 ? KID_XS_C1 : S == 2 ? KID_XS_C2 : S == 4 ? KID_XS_C4 : KID_XS_C8;
+    return launch_xs_c<XS_NT, XS_CWORDS, 1>(kid, S, mode, units, states, unit_list, n_list, one_minus_keep, global_key,
+                                            sm_count, st, ls);
+}
+
+template <int NT, int CW, int MINB>
+static cudaError_t launch_xs_d(int kid, int S, int smem, const DecUnitDev* dec, const InvUnitDev* inv, const int* unit_list,
+                               int n_list, int* err, int sm_count, cudaStream_t st, LaunchStats* ls, int* work_counter) {
+    auto kern = k_xs_decompress<NT, CW, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int& per_sm = ls->occ[kid];                // resident CTAs per SM, cached per ctx
+    if (per_sm == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    }
+    const long long items = (long long)n_list * S, slots = (long long)per_sm * sm_count;
+    const int nc = (int)(items < slots ? items : slots);
+    ls->begin(kid, st);
+    kern<<<nc, NT, smem, st>>>(dec, inv, unit_list, n_list, S, err, work_counter);
+    ls->end(st);
     return cudaGetLastError();
 }
 
@@ -579,14 +753,11 @@ cudaError_t launch_xs_decompress(int fused_cls, const DecUnitDev* dec, const Inv
     const int S = xs_class_slabs(fused_cls);
     if (S == 0) return cudaErrorInvalidValue;
     if (n_list <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_xs_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, XS_SMEM);
-    if (e != cudaSuccess) return e;
-    const long long items = (long long)n_list * S;
-    const int nc = (int)(items < sm_count ? items : sm_count);
-    ls->begin(KID_XS_D, st);
-    k_xs_decompress<<<nc, XS_NT, XS_SMEM, st>>>(dec, inv, unit_list, n_list, S, err, work_counter);
-    ls->end(st);
-    return cudaGetLastError();
+    if (fused_cls == FUSED_CLS_XS1S)
+        return launch_xs_d<XS_NT_S, XS_CWORDS_S, XS_MINB_S>(KID_XS_DS, 1, XS_DSMEM_S, dec, inv, unit_list, n_list, err,
+                                                            sm_count, st, ls, work_counter);
+    return launch_xs_d<XS_NT, XS_CWORDS, 1>(KID_XS_D, S, XS_DSMEM, dec, inv, unit_list, n_list, err, sm_count, st, ls,
+                                            work_counter);
 }
 
 } // namespace wc
