@@ -200,6 +200,7 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
     u64* const   s_x1   = reinterpret_cast<u64*>(smem + SM::X1);
     int* const   s_x2   = reinterpret_cast<int*>(smem + SM::X2);
     u64* const   s_x3   = reinterpret_cast<u64*>(smem + SM::X3);      // [2]  exchange 3 (ties only)
+    int* const   s_seed = reinterpret_cast<int*>(smem + SM::MISC);    // [8]  reduced exchange values of this CTA
 
     cg::cluster_group cluster = cg::this_cluster();
     const int S    = (int)cluster.num_blocks();
@@ -283,13 +284,22 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
         u64  ukey = 0ull;
         bool first_nan = false;
         {
-            uint32_t mp = 0u, mn = 0u;
-            for (int r = 0; r < S; ++r) {
-                const u64* px = cluster.map_shared_rank(s_x1 + par * 2, r);
-                const u64 x = px[0];
-                mp = max(mp, (uint32_t)(x >> 32)); mn = max(mn, (uint32_t)x);
-                first_nan = first_nan || px[1] != 0ull;
+            // one warp reads the peers (lane r <- rank r) and leaves the reduced values in this CTA's shared memory: with
+            // every thread reading every peer a 63^3 slab spent more time in remote loads than in its cluster barriers
+            if (warp == 0) {
+                u64 x = 0ull, f = 0ull;
+                if (lane < S) {
+                    const u64* px = cluster.map_shared_rank(s_x1 + par * 2, lane);
+                    x = px[0]; f = px[1];
+                }
+                const uint32_t rp = __reduce_max_sync(0xffffffffu, (uint32_t)(x >> 32));
+                const uint32_t rn = __reduce_max_sync(0xffffffffu, (uint32_t)x);
+                const bool     fn = __any_sync(0xffffffffu, f != 0ull);
+                if (lane == 0) { s_seed[0] = (int)rp; s_seed[1] = (int)rn; s_seed[2] = fn ? 1 : 0; }
             }
+            __syncthreads();
+            const uint32_t mp = (uint32_t)s_seed[0], mn = (uint32_t)s_seed[1];
+            first_nan = s_seed[2] != 0;
             const uint32_t mb = max(mp, mn);
             uint32_t sign = mn > mp ? 1u : 0u;
             if (mp == mn && mb != 0u && !first_nan && mode != FUSED_GIVEN_THRESH) {
@@ -415,16 +425,25 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
         }
         cluster.sync();                        // exchange 2
         // position of this CTA's two ranges in the unit's pair list: low ranges of ranks 0 .. S-1, then the high ranges
-        int base_lo = 0, prev_lo = -1, base_hi = 0, prev_hi = -1, lo_all = 0, lastlo_all = -1, K = 0, last_all = -1;
-        for (int r = 0; r < S; ++r) {
-            const int* x = cluster.map_shared_rank(s_x2 + par * 4, r);
-            const int c0 = x[0], l0 = x[1], c1 = x[2], l1 = x[3];
-            if (r < rank) { base_lo += c0; prev_lo = max(prev_lo, l0); base_hi += c1; prev_hi = max(prev_hi, l1); }
-            lo_all += c0; lastlo_all = max(lastlo_all, l0);
-            K += c0 + c1; last_all = max(last_all, max(l0, l1));
+        if (warp == 0) {
+            int c0 = 0, l0 = -1, c1 = 0, l1 = -1;
+            if (lane < S) {
+                const int* x = cluster.map_shared_rank(s_x2 + par * 4, lane);
+                c0 = x[0]; l0 = x[1]; c1 = x[2]; l1 = x[3];
+            }
+            const bool before = lane < rank;
+            const int blo = __reduce_add_sync(0xffffffffu, before ? c0 : 0), plo = __reduce_max_sync(0xffffffffu, before ? l0 : -1);
+            const int bhi = __reduce_add_sync(0xffffffffu, before ? c1 : 0), phi = __reduce_max_sync(0xffffffffu, before ? l1 : -1);
+            const int loa = __reduce_add_sync(0xffffffffu, c0), lla = __reduce_max_sync(0xffffffffu, l0);
+            const int kk  = __reduce_add_sync(0xffffffffu, c0 + c1), la = __reduce_max_sync(0xffffffffu, max(l0, l1));
+            if (lane == 0) {
+                s_seed[0] = blo; s_seed[1] = plo; s_seed[2] = bhi + loa; s_seed[3] = max(phi, lla);
+                s_seed[4] = kk;  s_seed[5] = la;
+            }
         }
-        base_hi += lo_all;
-        prev_hi = max(prev_hi, lastlo_all);
+        __syncthreads();
+        const int base_lo = s_seed[0], prev_lo = s_seed[1], base_hi = s_seed[2], prev_hi = s_seed[3], K = s_seed[4],
+                  last_all = s_seed[5];
         int2* const tab = reinterpret_cast<int2*>(u.coef);     // decode-side plane table (cluster classes), or null
         if (tid == 0 && rank == 0) {
             const float M = fabsf(key_value(ukey));
@@ -531,12 +550,19 @@ template <int NT>
 __device__ __forceinline__ void xs_decode_range(const int2* __restrict__ pairs, int pb, int pe, uint32_t cur, uint32_t f0,
                                                 uint32_t f1, int pbase, const XGeom& g, float* C, uint32_t* s_wt, int& tile,
                                                 bool& bad) {
+    const uint32_t m_yz = xs_magic((uint32_t)g.YZ);            // d / YZ: d * YZ < 2^32 (d < 2^17 per range, YZ < 2^16)
+    int2 pr[XS_PPT], nxt[XS_PPT];
+    auto load = [&](int p, int2 (&dst)[XS_PPT]) {
+#pragma unroll
+        for (int j = 0; j < XS_PPT; ++j) dst[j] = (p + j < pe) ? __ldg(pairs + p + j) : make_int2(0, 0);
+    };
+    if (pb < pe) load(pb + (int)threadIdx.x * XS_PPT, nxt);
 #pragma unroll 1
     for (int p0 = pb; p0 < pe; p0 += NT * XS_PPT, ++tile) {
         const int p = p0 + (int)threadIdx.x * XS_PPT;
-        int2 pr[XS_PPT];
 #pragma unroll
-        for (int j = 0; j < XS_PPT; ++j) pr[j] = (p + j < pe) ? __ldg(pairs + p + j) : make_int2(0, 0);
+        for (int j = 0; j < XS_PPT; ++j) pr[j] = nxt[j];
+        if (p0 + NT * XS_PPT < pe) load(p + NT * XS_PPT, nxt);     // the next tile is in flight during this one's scan
         uint32_t ttot;
         uint32_t rp = xs_sat_add(cur, xs_tile_scan<NT>(pr, pe - p, s_wt + (tile & 1) * 32, bad, ttot));
 #pragma unroll
@@ -544,7 +570,7 @@ __device__ __forceinline__ void xs_decode_range(const int2* __restrict__ pairs, 
             if (p + j < pe && pr[j].x >= 0) {
                 const uint32_t f = xs_sat_add(rp, (uint32_t)pr[j].x);
                 if (f >= f0 && f < f1) {
-                    const uint32_t d = f - f0, pl = d / (uint32_t)g.YZ;
+                    const uint32_t d = f - f0, pl = xs_div(d, m_yz);
                     C[(pbase + (int)pl) * g.PS + (int)(d - pl * (uint32_t)g.YZ)] = __int_as_float(pr[j].y);
                 }
                 rp = xs_sat_add(rp, (uint32_t)pr[j].x + 1u);
@@ -624,7 +650,10 @@ k_xs_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict
         g.init(iu.nx, iu.ny, iu.nz, S, rank);
         if (g.npl > 0) {
             // the slab's low and high planes start out zero (src/decompressor.cpp:16)
-            for (int i = tid; i < 2 * g.nl * g.PS; i += NT) C[i] = 0.f;
+            {
+                float4* c4 = reinterpret_cast<float4*>(C);
+                for (int i = tid; i < (2 * g.nl * g.PS + 3) / 4; i += NT) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             __syncthreads();
             const int2* pairs = reinterpret_cast<const int2*>(du.pairs);
             int K = du.npairs_dev ? *du.npairs_dev : du.npairs;
