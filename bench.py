@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lzma", action="store_true")
+    ap.add_argument("--no-irregular", action="store_true", help="skip the irregular-box leg (x-slab kernels)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seg-index", type=int, default=0, help="WC_OPT_SEG_INDEX for the stream decompress leg")
     args = ap.parse_args()
@@ -599,6 +600,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_lzma and not args.no_e2e:
         e2e_lzma = lzma_leg(pkg, ctx)
 
+    # ---- boxes the 16-byte vector kernels refuse (nz % 4 != 0, odd dimensions): the x-slab kernels ---------
+    irregular = None
+    if rank == 0 and world == 1 and not args.no_irregular:
+        irregular = irregular_leg(pkg, local, stream, device, peak, args.path)
+
     # ---- CPU baseline: the reference's own code on this box's host cores ---------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -623,7 +629,7 @@ def main():
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "decompress_stream": decompress_stream, "decompress_roundtrip": decompress_roundtrip,
-                "rmse": rmse_info, "e2e_with_lzma": e2e_lzma, "parity": parity}
+                "rmse": rmse_info, "e2e_with_lzma": e2e_lzma, "irregular_boxes": irregular, "parity": parity}
         print(json.dumps(line))
     dplan.close()
     ctx2.close()
@@ -632,6 +638,77 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def irregular_leg(pkg, local, stream, device, peak, path):
+    """Off-BASELINE shapes, reported beside the headline: boxes with nz % 4 != 0 or odd dimensions (the trailing element
+    passes through, src/compressor.cpp:98-175, and comes back as 0, src/decompressor.cpp:99-108) on the x-slab kernels of
+    csrc/wc_xslab.cu — device-resident compress and plan round-trip decompress per shape, algorithmic bytes 8N + 8K and
+    8K + 4N, and a bit-for-bit check of a few units against the oracle (not timed)."""
+    import torch
+    capi = pkg.capi
+    from oracle.pyoracle import Oracle
+    orc = Oracle()
+    ctx = pkg.Context(local, stream=stream.cuda_stream)
+    ctx.set_path(path)
+    out = {}
+
+    def timed(fn, warm=2, steps=5):
+        with torch.cuda.stream(stream):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(steps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / steps
+
+    for dims in ((40, 40, 42), (31, 17, 9), (65, 61, 57)):
+        n = dims[0] * dims[1] * dims[2]
+        n_units = max(1, (1 << 29) // (8 * n))                      # ~0.5 GB of float64 input per shape (> L2)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(17)
+        x = torch.linspace(0, 50, n_units * n, device=device, dtype=torch.float64).sin_() * 100 + \
+            torch.randn(n_units * n, device=device, dtype=torch.float64, generator=gen) * 0.05
+        rec = torch.empty(n_units * n, dtype=torch.float32, device=device)
+        descs = capi.box_descs([x.data_ptr() + 8 * n * i for i in range(n_units)], [pkg.WC_F64] * n_units, [dims] * n_units)
+        odescs = capi.box_descs([rec.data_ptr() + 4 * n * i for i in range(n_units)], [pkg.WC_F32] * n_units, [dims] * n_units)
+        torch.cuda.synchronize()
+        plan = ctx.plan(descs, pkg.WC_DEVICE)
+        c_ms = timed(lambda: plan.compress(KEEP))
+        k = plan.total_pairs()
+        d_ms = timed(lambda: plan.decompress(odescs, pkg.WC_DEVICE))
+        ctx.sync()
+        plan.close()
+        # parity of the first units (a small plan of its own: fetching every unit's pairs would dominate the leg)
+        m = min(3, n_units)
+        small = ctx.plan(descs[:m], pkg.WC_DEVICE)
+        small.compress(KEEP)
+        small.decompress(odescs[:m], pkg.WC_DEVICE)
+        ctx.sync()
+        got = small.fetch_host()
+        ok = True
+        for i in range(m):
+            b = x[i * n:(i + 1) * n].cpu().numpy().reshape(dims[2], dims[1], dims[0])
+            runs, vals, _ = orc.compress_unit(b, dims, KEEP)
+            ok = ok and got[i].runs.tobytes() == runs.tobytes() and got[i].vals.tobytes() == vals.tobytes()
+            ob = orc.decompress_unit(runs, vals, dims)
+            ok = ok and rec[i * n:(i + 1) * n].cpu().numpy().tobytes() == ob.tobytes()
+        small.close()
+        c_alg, d_alg = 8 * n * n_units + 8 * k, 8 * k + 4 * n * n_units
+        out["x".join(map(str, dims))] = {
+            "units": n_units, "kept_fraction": k / (n * n_units),
+            "compress_ms": c_ms, "compress_alg_gbs": c_alg / (c_ms * 1e-3) / 1e9, "compress_frac": c_alg / (c_ms * 1e-3) / 1e9 / peak,
+            "decompress_ms": d_ms, "decompress_alg_gbs": d_alg / (d_ms * 1e-3) / 1e9,
+            "decompress_frac": d_alg / (d_ms * 1e-3) / 1e9 / peak, "bit_exact_vs_oracle": bool(ok)}
+        del x, rec
+    ctx.close()
+    out["note"] = ("plan compress / plan round-trip decompress of ~0.5 GB of float64 boxes per shape, CUDA events; fractions of "
+                   "the measured HBM peak on algorithmic bytes (8N + 8K, 8K + 4N)")
+    return out
 
 
 def pin_to_gpu_numa_node(index):

@@ -1,6 +1,6 @@
 """Small end-to-end workload for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): a few units of every
-kernel class (fused cubes, clusters of 2 / 4 / 8, small units, big boxes by y-slabs, odd dimensions on the generic
-kernels) through compress -> plan round trip -> stream decode (staged and direct kernels, both segment index kernels)
+kernel class (fused cubes, clusters of 2 / 4 / 8, small units, big boxes by y-slabs, odd dimensions on the x-slab
+kernels, one box on the generic kernels) through compress -> plan round trip -> stream decode (staged and direct kernels, both segment index kernels)
 -> RMSE -> unit stats, checked against the oracle.  Kept tiny: kernels run 10-100x slower under the tool.
 
     compute-sanitizer --tool memcheck  python tools/sanitize_target.py
@@ -21,7 +21,9 @@ capi = pkg.capi
 orc = Oracle()
 rng = np.random.default_rng(3)
 dims = ([(32, 32, 32)] * 3 + [(64, 64, 64)] * 2 + [(16, 16, 16)] * 3 + [(8, 8, 8)] * 3 + [(40, 40, 40)] + [(36, 36, 36)] +
-        [(16, 32, 64)] * 2 + [(8, 4, 4)] + [(5, 7, 3)] + [(8, 4, 2)] + [(44, 44, 44)] + [(64, 72, 64)] + [(34, 18, 10)])
+        [(16, 32, 64)] * 2 + [(8, 4, 4)] + [(5, 7, 3)] + [(8, 4, 2)] + [(44, 44, 44)] + [(64, 72, 64)] + [(34, 18, 10)] +
+        [(31, 17, 9), (33, 33, 33), (40, 40, 42), (63, 47, 41), (65, 61, 57)] +     # x-slab classes: one CTA, clusters of 2 / 4 / 8
+        [(96, 96, 50)])                                                             # generic kernels (no fused class holds it)
 boxes = [smooth_box(d, rng, dtype=np.float64 if i % 2 else np.float32, sym=(i % 3 == 0)) for i, d in enumerate(dims)]
 keep = float(np.float32(0.999))
 ctx = pkg.Context(0)
