@@ -210,6 +210,8 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
     const uint32_t lt = lanemask_lt();
     const int  mode = mode_flags & 15;
     const bool mm   = (mode_flags & FUSED_MINMAX) != 0;
+    // cluster-wide barrier with release / acquire of shared memory; a plain CTA barrier when the cluster is one CTA
+    auto xsync = [&]() { if (S == 1) __syncthreads(); else cluster.sync(); };
 
     int it = 0;
     for (int ui = cid; ui < n_list; ui += ncl, ++it) {
@@ -228,6 +230,17 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
         } else {
             if (mm) xs_phase_a<float, true, NT>(g, u.in, C, bp, bn, vmn, vmx);
             else    xs_phase_a<float, false, NT>(g, u.in, C, bp, bn, vmn, vmx);
+        }
+        // L2 prefetch of this cluster's NEXT unit (every CTA takes 1/S of its 128-byte lines), issued behind this unit's own
+        // loads: the packing phases below read nothing from HBM, so the next phase A finds its input in L2
+        if (ui + ncl < n_list) {
+            const UnitDev* un = units + unit_list[ui + ncl];
+            const char*  nb  = static_cast<const char*>(un->in);
+            const size_t nby = (size_t)un->n * (un->dtype == WC_F64 ? 8 : 4);
+            const int lines = (int)((nby + 127) >> 7), per = (lines + S - 1) / S;
+            const int l0 = rank * per, l1 = min(lines, l0 + per);
+            for (int i = l0 + tid; i < l1; i += NT)
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nb + (size_t)i * 128));
         }
         // both maxima are >= 0 (a -0 cannot win against the initial +0; masked all the same): the halves reduce separately
         u64 key = ((u64)(__float_as_uint(bp) & 0x7fffffffu) << 32) | (u64)(__float_as_uint(bn) & 0x7fffffffu);
@@ -280,7 +293,7 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                 }
             }
         }
-        cluster.sync();                        // exchange 1 (for S == 1 a CTA barrier)
+        xsync();                               // exchange 1
         u64  ukey = 0ull;
         bool first_nan = false;
         {
@@ -335,7 +348,7 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                     }
                     if (lane == 0) s_x3[par] = best;
                 }
-                cluster.sync();
+                xsync();
                 best = ~0ull;
                 for (int r = 0; r < S; ++r) {
                     const u64 x = *cluster.map_shared_rank(s_x3 + par, r);
@@ -423,7 +436,7 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
                 x2[0] = tot[0]; x2[1] = lastf[0]; x2[2] = tot[1]; x2[3] = lastf[1];
             }
         }
-        cluster.sync();                        // exchange 2
+        xsync();                               // exchange 2
         // position of this CTA's two ranges in the unit's pair list: low ranges of ranks 0 .. S-1, then the high ranges
         if (warp == 0) {
             int c0 = 0, l0 = -1, c1 = 0, l1 = -1;
@@ -500,7 +513,7 @@ k_xs_compress(const UnitDev* __restrict__ units, UnitState* __restrict__ states,
         }
         __syncthreads();                       // C and the segment arrays are rewritten by the next unit
     }
-    cluster.sync();                            // no CTA may exit while a peer can still read its shared memory
+    xsync();                                   // no CTA may exit while a peer can still read its shared memory
 }
 
 // ---- decompress ----------------------------------------------------------------------------------------------------
@@ -635,6 +648,8 @@ k_xs_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict
     float* const    C      = reinterpret_cast<float*>(smem);
     uint32_t* const s_wt   = reinterpret_cast<uint32_t*>(smem + CW * 4);          // [2][32]
     int* const      s_item = reinterpret_cast<int*>(smem + CW * 4 + 256);
+    const char** const s_pfp = reinterpret_cast<const char**>(smem + CW * 4 + 264);   // pair list of the item gridDim.x ahead
+    int* const      s_pfk  = reinterpret_cast<int*>(smem + CW * 4 + 272);             // [2]: its K, its slab
     const int tid = threadIdx.x;
     const int n_items = n_list * S;
     bool bad = false;
@@ -644,6 +659,21 @@ k_xs_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict
         const int item = *s_item;
         if (item >= n_items) break;
         const int uid = unit_list[item / S], rank = item % S;
+        if (tid == 32 % NT) {
+            // Items are handed out in order, so the item gridDim.x further on starts when this one ends, on this CTA or a
+            // neighbour: its share of its unit's pair list (1/S of the lines: the S items of a unit run at about the same
+            // time) goes into L2 while this item is inverted and stored.  Read here, consumed behind the decode's barrier.
+            const int ahead = item + (int)gridDim.x;
+            int k2 = 0;
+            if (ahead < n_items) {
+                const DecUnitDev* d2 = dec + unit_list[ahead / S];
+                k2 = d2->npairs_dev ? *d2->npairs_dev : d2->npairs;
+                k2 = max(0, min(k2, d2->total));
+                *s_pfp = reinterpret_cast<const char*>(d2->pairs);
+                s_pfk[1] = ahead % S;
+            }
+            s_pfk[0] = k2;
+        }
         const DecUnitDev du = dec[uid];
         const InvUnitDev iu = inv[uid];
         XGeom g;
@@ -673,6 +703,13 @@ k_xs_decompress(const DecUnitDev* __restrict__ dec, const InvUnitDev* __restrict
                 }
             }
             __syncthreads();
+            if (const int k2 = s_pfk[0]) {
+                const int lines = (int)(((size_t)k2 * 8 + 127) >> 7), per = (lines + S - 1) / S;
+                const int l0 = s_pfk[1] * per, l1 = min(lines, l0 + per);
+                const char* pb2 = *s_pfp;
+                for (int i = l0 + tid; i < l1; i += NT)
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pb2 + (size_t)i * 128));
+            }
             if (iu.dtype == WC_F64) xs_inverse_store<double, NT>(g, C, static_cast<double*>(iu.out));
             else                    xs_inverse_store<float, NT>(g, C, static_cast<float*>(iu.out));
         }
