@@ -120,6 +120,9 @@ struct DecCache {
     uint64_t h1 = 0, h2 = 0;      // 128-bit hash of (output space, pointers, dtypes) of the cached call
     bool     valid = false;
     size_t   fl_n[16] = {};
+    // copy of the cached call's output descriptors (device outputs only): an identical array re-launches without the
+    // per-unit validation and hashing, which cost ~5 ns per unit and made the round trip of a million 8^3 boxes host-bound
+    std::vector<wc_box_out> last_out;
 };
 // Fused compress classes (wc_fused.h: fused_class) in launch order: cluster kernels first (they go on the ctx
 // stream), then the single-CTA kernels (second stream when both kinds are present).
@@ -1435,6 +1438,10 @@ int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
     wc_ctx* ctx = p->ctx;
     CTX_CUDA(ctx, cudaSetDevice(ctx->device));
     int n = p->n_units;
+    if (!p->dec_cache) p->dec_cache = new DecCache();
+    if (out_space == WC_DEVICE && n > 0 && p->dec_cache->valid && p->dec_cache->last_out.size() == (size_t)n &&
+        std::memcmp(p->dec_cache->last_out.data(), out, sizeof(wc_box_out) * (size_t)n) == 0)
+        return relaunch_decompress(ctx, p->dec_cache, p->d_dec_units, p->d_inv_units, p->d_err, p->d_dec_list);
     size_t stage = 0;
     std::vector<size_t> stage_off(n);
     uint64_t h1 = 0x243F6A8885A308D3ull ^ (uint64_t)out_space, h2 = 0x13198A2E03707344ull + (uint64_t)n;
@@ -1450,7 +1457,6 @@ int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
     }
     if (out_space == WC_HOST) CTX_CUDA(ctx, p->d_stage_out.reserve(std::max<size_t>(stage, 256)));
     dec_hash(h1, h2, (uint64_t)(uintptr_t)p->d_stage_out.p);
-    if (!p->dec_cache) p->dec_cache = new DecCache();
     const bool hit = p->dec_cache->valid && p->dec_cache->h1 == h1 && p->dec_cache->h2 == h2;
     std::vector<DecJob> jobs(hit ? 0 : n);
     if (!hit)
@@ -1469,6 +1475,8 @@ int wc_plan_decompress(wc_plan* p, const wc_box_out* out, int out_space) {
                                   p->d_ptiles, p->d_psum, p->d_err, p->d_dec_list, p->dec_cache);
     if (rc != WC_OK) return rc;
     p->dec_cache->h1 = h1; p->dec_cache->h2 = h2;
+    if (out_space == WC_DEVICE) p->dec_cache->last_out.assign(out, out + n);
+    else                        p->dec_cache->last_out.clear();
     if (out_space == WC_HOST) {
         CopyList cl;
         for (int i = 0; i < n; ++i)
