@@ -1,5 +1,5 @@
 // Fused on-chip kernels for boxes of ANY shape (odd dimensions, nz % 4 != 0, rows that are not 16-byte multiples,
-// unaligned pointers): the x-slab classes FUSED_CLS_XS1 / XS2 / XS4 / XS8.
+// unaligned pointers): the x-slab classes FUSED_CLS_XS1S / XS1 / XS2 / XS4 / XS8.
 //
 // The y-slab kernels of wc_fused.cu owe their speed to 16-byte vector accesses, and with them to even dimensions and
 // nz % 4 == 0.  Everything else used to take the generic multi-kernel path (coefficient scratch in HBM: 20N + 8K bytes of
@@ -9,9 +9,10 @@
 // plane x = X-1 of an odd X (which passes through the x stage, src/compressor.cpp:153-175) goes to the last CTA.  The
 // coefficients of a slab are whole PLANES i' of the flat order f = (i'*Y + j')*Z + k' (src/compressor.cpp:178-181): the
 // low planes [a0, a1) and the high planes [hx+a0, hx+a1) (+ the plane X-1) — two contiguous flat ranges.  So
-//   compress:   a cluster of S CTAs exchanges, through distributed shared memory, one arg-max key and four words (kept
-//               count and last kept flat index of either range) per CTA — nothing else is needed to place a CTA's pairs
-//               in the unit's ordered pair list and to know the zero run in front of its first pair;
+//   compress:   a cluster of S CTAs exchanges, through distributed shared memory, the arg-max (max c, max -c, NaN at f = 0)
+//               and four words (kept count and last kept flat index of either range) per CTA — nothing else is needed to
+//               place a CTA's pairs in the unit's ordered pair list and to know the zero run in front of its first pair;
+//               behind its own loads a CTA prefetches its share of the cluster's NEXT unit into L2;
 //   decompress: the S slab items of a unit are independent once the position of every plane in the pair list is known:
 //               tab[i'] = (first pair at/after flat index i'*Y*Z, flat index of the pair before it).  The compress kernel
 //               writes that table for free; for streams the index kernels of wc_fused.cu build it (seglen = Y*Z).
@@ -24,7 +25,8 @@
 // the lanes of a warp work on consecutive block columns a, i.e. on consecutive planes, and hit 32 different banks.
 // All global accesses are element-wise (4 or 8 bytes per lane, consecutive lanes on consecutive block columns): coalesced
 // without any alignment requirement.  Simplicity over the last 20 %: these shapes are rare in AMR plotfiles (boxes are
-// multiples of the blocking factor); the point is that they no longer fall off the fused path.
+// multiples of the blocking factor); the point is that they no longer fall off the fused path.  Measurements, the ncu
+// tables and what was tried: profiles/r02_xslab.md; design: DESIGN.md §4.6.
 #include <cooperative_groups.h>
 
 #include "wc_common.cuh"
