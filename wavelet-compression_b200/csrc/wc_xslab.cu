@@ -115,6 +115,17 @@ __device__ __forceinline__ uint32_t xs_div(uint32_t q, uint32_t m) { return m ? 
 template <class T> __device__ __forceinline__ float xs_ld(const T* p);
 template <> __device__ __forceinline__ float xs_ld<double>(const double* p) { return __double2float_rn(__ldg(p)); }   // src/preprocess.cpp:78
 template <> __device__ __forceinline__ float xs_ld<float>(const float* p) { return __ldg(p); }
+// the (x, x+1) outputs of a full block: one vector store where the pair happens to be aligned (even X and an aligned box:
+// every row; odd X: every other row), two element stores otherwise: decode +3..6 %.  (The same for the loads of phase A
+// measured 1..7 % SLOWER — the alignment test sits in front of the loads it guards — and was dropped.)
+__device__ __forceinline__ void xs_st2(double* p, float a, float b) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) *reinterpret_cast<double2*>(p) = make_double2((double)a, (double)b);
+    else { p[0] = (double)a; p[1] = (double)b; }
+}
+__device__ __forceinline__ void xs_st2(float* p, float a, float b) {
+    if ((reinterpret_cast<uintptr_t>(p) & 7u) == 0) *reinterpret_cast<float2*>(p) = make_float2(a, b);
+    else { p[0] = a; p[1] = b; }
+}
 
 template <class T, bool MM, int NT>
 __device__ __forceinline__ void xs_phase_a(const XGeom& g, const void* in, float* C, float& bp, float& bn, float& vmn,
@@ -614,7 +625,7 @@ __device__ __forceinline__ void xs_inverse_store(const XGeom& g, const float* C,
         haar_block_inverse_full(v);
         T* po = out + ((size_t)(2 * c) * sz + (size_t)(2 * b) * sy + (size_t)(2 * (g.a0 + al)));
 #pragma unroll
-        for (int o = 0; o < 8; ++o) po[(o >> 2) * sz + ((o >> 1) & 1) * sy + (o & 1)] = (T)v[o];
+        for (int o = 0; o < 8; o += 2) xs_st2(po + ((o >> 2) * sz + ((o >> 1) & 1) * sy), v[o], v[o + 1]);
     }
     // trailing cells of odd axes: the inverse leaves them at +0
     const int nxs = 2 * g.nl + g.own1;                    // x positions of this slab (incl. the trailing plane)
