@@ -603,7 +603,10 @@ def main():
     # ---- boxes the 16-byte vector kernels refuse (nz % 4 != 0, odd dimensions): the x-slab kernels ---------
     irregular = None
     if rank == 0 and world == 1 and not args.no_irregular:
-        irregular = irregular_leg(pkg, local, stream, device, peak, args.path)
+        try:
+            irregular = irregular_leg(pkg, local, stream, device, peak, args.path)
+        except Exception as e:      # a side leg must not take the headline line down with it
+            irregular = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline: the reference's own code on this box's host cores ---------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
