@@ -115,6 +115,13 @@ typedef struct {
 WC_API int         wc_version(void);
 WC_API const char* wc_strerror(int status);
 WC_API int         wc_device_count(int* count);
+/* Informational (no GPU needed, no reference counterpart): the name of the kernel class a box of this shape gets when its
+ * pointers are 16-byte aligned — `decompress` = 0: the compress side, 1: the decompress side.  "cube8" / "cube16" /
+ * "cube32" / "cube64" and "r1s" / "r1" / "r2" / "r4" / "r8" are the fused y-slab kernels (one CTA, or a cluster of 2 / 4 / 8),
+ * "yslab" the two-pass y-slab kernels of boxes no cluster holds (128^3 ...), "xs1s" / "xs1" / "xs2" / "xs4" / "xs8" the x-slab
+ * kernels that take any shape (odd dimensions, nz % 4 != 0 ...), "generic" the multi-kernel path, "empty" a box without
+ * cells, "invalid" a negative dimension or an unknown dtype.  Results never depend on the class. */
+WC_API const char* wc_box_kernel_class(int nx, int ny, int nz, int dtype, int decompress);
 
 /* Creates a context on CUDA device `device_id` with its own non-blocking stream. */
 WC_API int wc_create(wc_ctx** ctx, int device_id);

@@ -78,3 +78,34 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "wc_oracle" not in txt and "libwcref" not in txt, f
+
+
+def test_box_kernel_classes_cover_every_shape(wc):
+    """Host-side classification (no GPU): which kernels a box gets.  Pins the rules of
+    fused_class / fused_decode_class / big_slabs / xs_slabs: the y-slab classes need even dimensions, nz % 4 == 0 and 16-byte
+    rows; everything else of ordinary size goes to the x-slab classes; only what no CTA or cluster of 8 holds stays generic."""
+    lib = wc.capi.load()
+    F32, F64 = wc.capi.WC_F32, wc.capi.WC_F64
+    cls = lambda d, dt=F64, dec=0: lib.wc_box_kernel_class(d[0], d[1], d[2], dt, dec).decode()
+    both = {(8, 8, 8): "cube8", (16, 16, 16): "cube16", (32, 32, 32): "cube32", (64, 64, 64): "cube64", (8, 4, 4): "r1s",
+            (16, 32, 64): "r1", (40, 40, 40): "r2", (56, 56, 40): "r4", (48, 48, 48): "r4", (48, 64, 64): "r8",
+            # the x-slab classes: odd dimensions, nz % 4 != 0, any mix
+            (3, 5, 7): "xs1s", (31, 17, 9): "xs1s", (15, 15, 15): "xs1s", (1, 1, 1): "xs1s",
+            (33, 33, 33): "xs1", (6, 100, 90): "xs1", (40, 40, 42): "xs2", (41, 39, 37): "xs2", (63, 47, 41): "xs4",
+            (63, 63, 63): "xs8", (130, 66, 34): "xs8",
+            # nothing holds these
+            (96, 96, 50): "generic", (2, 256, 250): "generic", (300, 5, 3): "generic"}
+    for d, want in both.items():
+        assert cls(d) == want and cls(d, dec=1) == want, (d, cls(d), cls(d, dec=1), want)
+    # boxes no cluster holds: two passes by y-slabs on the compress side, slab items on the decompress side
+    for d in [(128, 128, 128), (44, 44, 44), (60, 60, 60), (96, 80, 64)]:
+        assert cls(d) == "yslab" and cls(d, dec=1) == "yslab", d
+    # float32 rows must be 16-byte multiples for the y-slab classes (nx % 4 == 0); otherwise the x-slab classes take the box
+    assert cls((2, 4, 8), F64) == "r1s" and cls((2, 4, 8), F32) == "xs1s"
+    assert cls((0, 4, 4)) == "empty" and cls((-1, 4, 4)) == "invalid" and cls((4, 4, 4), 7) == "invalid"
+    # every shape of ordinary size has a fused class: a sweep over small dimensions finds no generic box
+    for nx in range(1, 20):
+        for ny in (1, 2, 5, 8, 13):
+            for nz in (1, 3, 4, 6, 16):
+                for dec in (0, 1):
+                    assert cls((nx, ny, nz), dec=dec) != "generic", (nx, ny, nz, dec)

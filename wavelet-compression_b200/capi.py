@@ -37,6 +37,7 @@ _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
 SIGNATURES = {
     "wc_version": (_i, []),
     "wc_strerror": (C.c_char_p, [_i]),
+    "wc_box_kernel_class": (C.c_char_p, [_i, _i, _i, _i, _i]),
     "wc_device_count": (_i, [C.POINTER(_i)]),
     "wc_create": (_i, [C.POINTER(_vp), _i]),
     "wc_create_on_stream": (_i, [C.POINTER(_vp), _i, _vp]),

@@ -253,6 +253,33 @@ const char* wc_strerror(int status) {
     }
 }
 
+const char* wc_box_kernel_class(int nx, int ny, int nz, int dtype, int decompress) {
+    if (nx < 0 || ny < 0 || nz < 0 || (dtype != WC_F32 && dtype != WC_F64)) return "invalid";
+    if ((long long)nx * ny * nz == 0) return "empty";
+    const void* aligned = reinterpret_cast<const void*>(static_cast<uintptr_t>(256));
+    const int cls = decompress ? fused_decode_class(nx, ny, nz, dtype, aligned) : fused_class(nx, ny, nz, dtype, aligned);
+    switch (cls) {
+    case FUSED_CLS_CUBE8: return "cube8";
+    case FUSED_CLS_CUBE16: return "cube16";
+    case FUSED_CLS_CUBE32: return "cube32";
+    case FUSED_CLS_CUBE64: return "cube64";
+    case FUSED_CLS_R1S: return "r1s";
+    case FUSED_CLS_R1: return "r1";
+    case FUSED_CLS_R2: return "r2";
+    case FUSED_CLS_R4: return "r4";
+    case FUSED_CLS_R8: return "r8";
+    case FUSED_CLS_RBIG: return "yslab";
+    case FUSED_CLS_XS1S: return "xs1s";
+    case FUSED_CLS_XS1: return "xs1";
+    case FUSED_CLS_XS2: return "xs2";
+    case FUSED_CLS_XS4: return "xs4";
+    case FUSED_CLS_XS8: return "xs8";
+    }
+    // compress: boxes no cluster holds run their forward transform by y-slabs into the coefficient scratch
+    if (!decompress && big_forward_slabs(nx, ny, nz, dtype, aligned)) return "yslab";
+    return "generic";
+}
+
 int wc_device_count(int* count) {
     if (!count) return WC_ERR_INVALID_ARG;
     int n = 0;
