@@ -169,6 +169,31 @@ int main() {
         for (int c = 0; c < 2; ++c) REQUIRE(std::fabs(f.mean_rmse[c] - acc[c] / 5.0) <= 1e-12 * (acc[c] / 5.0));
         std::filesystem::remove_all(d);
     }
+    {   // odd dimensions through compress() / decompress() (the x-slab kernels): the trailing element of an odd axis passes
+        // through the forward stage (src/compressor.cpp:98-175) and the inverse leaves it at 0 (src/decompressor.cpp:99-108),
+        // everything else comes back as for even boxes; keep = 1 keeps every non-zero coefficient
+        const int shapes[3][3] = { { 5, 7, 3 }, { 41, 39, 37 }, { 40, 40, 42 } };
+        for (auto& sh : shapes) {
+            const int X = sh[0], Y = sh[1], Z = sh[2];
+            Box3D bx(X, Y, Z), want(X, Y, Z);
+            for (int k = 0; k < Z; ++k)
+                for (int j = 0; j < Y; ++j)
+                    for (int i = 0; i < X; ++i) {
+                        bx(i, j, k) = 3.f + 0.5f * std::sin(0.1f * i) * std::cos(0.07f * j) * std::sin(0.05f * k + 1.f);
+                        const bool trailing = ((X & 1) && i == X - 1) || ((Y & 1) && j == Y - 1) || ((Z & 1) && k == Z - 1);
+                        want(i, j, k) = trailing ? 0.f : bx(i, j, k);
+                    }
+            multiBox3D mb;
+            mb.push_back(bx.clone());
+            std::vector<int> comps = { 0 };
+            std::string d = scratch_dir();
+            auto cw = compress(mb, comps, 1.0, 0, 0, 0, d);
+            REQUIRE(cw.size() == 1 && cw[0].rle_encoded.size() <= (size_t)X * Y * Z);
+            Box3D back = decompress(d + "/compressed-wavelet-0-0-0-0.xz", 0, 0, 0, 0);
+            REQUIRE(want.equals(back, 1e-5f));
+            std::filesystem::remove_all(d);
+        }
+    }
     {   // one host thread per GPU: contexts are per (thread, device) — two threads on device 0 must not share one
         std::atomic<int> ok { 0 };
         auto work = [&] {
